@@ -1,0 +1,142 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference/scripts/augmentations.py (numpy 2.3.5 + opencv 4.13.0, the
+versions the reference pins) and records its outputs for seeded synthetic inputs:
+
+  * golden_small.npz   -- full input/output arrays for small and odd shapes
+  * golden_hashes.json -- sha256 of the outputs at BASELINE.json sizes, the
+                          random-apply decision sequences, and library versions
+
+Inputs are regenerated from their seeds by the tests, so only outputs are stored for
+the large cases.  /root/reference does not exist on the GPU box; the tests read only
+these two files.
+"""
+import hashlib
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = "/root/reference"
+
+SMALL_SHAPES = [(1, 1), (1, 7), (7, 1), (2, 2), (2, 3), (3, 5), (4, 2), (5, 4), (8, 8), (9, 13),
+                (17, 9), (16, 48), (33, 47), (64, 64), (31, 100), (48, 129)]
+BIG_CASES = [  # (name, seed, h, w)
+    ("visdrone_765x1360", 12345, 765, 1360),
+    ("cfg2_img0", 2000, 765, 1360),
+    ("odd_1079x1917", 3001, 1079, 1917),
+    ("even_1080x1920", 3002, 1080, 1920),
+    ("mixed_1050x1400", 3003, 1050, 1400),
+    ("max_1500x2000", 3004, 1500, 2000),
+    ("max_1499x1999", 3005, 1499, 1999),
+    ("mosaic_1024", 3006, 1024, 1024),
+    ("patch_256", 3007, 256, 256),
+    ("wide_9x1361", 3008, 9, 1361),
+]
+
+
+def synth(seed, h, w, kind="uniform"):
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":
+        return rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    if kind == "binary":
+        return (rng.integers(0, 2, (h, w, 3)) * 255).astype(np.uint8)
+    raise ValueError(kind)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    sys.path.insert(0, REF_ROOT)
+    import cv2
+    from scripts import augmentations as ref
+
+    small = {}
+    for i, (h, w) in enumerate(SMALL_SHAPES):
+        for kind in ("uniform", "binary"):
+            img = synth(100 + i, h, w, kind)
+            tag = f"{kind}_{h}x{w}"
+            small[f"in_{tag}"] = img
+            small[f"blur9_{tag}"] = ref.apply_motion_blur(img, 9, 0)
+            small[f"blur5_{tag}"] = ref.apply_motion_blur(img, 5, 0)
+            small[f"lowres_{tag}"] = ref.apply_lowres(img, 0.5)
+            np.random.seed(7 + i)
+            small[f"noise_{tag}"] = ref.apply_noise(img, 15)
+    # strided (non-contiguous crop) input, as train_restoration.py:84 passes
+    base = synth(999, 80, 120)
+    crop = base[5:53, 7:91]
+    small["in_crop_base"] = base
+    small["blur9_crop"] = ref.apply_motion_blur(crop, 9, 0)
+    small["lowres_crop"] = ref.apply_lowres(crop, 0.5)
+    # other factors on a small image
+    img = synth(555, 45, 70)
+    small["in_factor"] = img
+    for f in (0.25, 0.3, 0.75):
+        small[f"lowres_f{f}"] = ref.apply_lowres(img, f)
+    # truncation / clipping cases of SURVEY 8d config 1
+    const = np.full((32, 40, 3), 128, np.uint8)
+    np.random.seed(11)
+    small["noise_const128"] = ref.apply_noise(const, 15)
+    rails = synth(556, 32, 40, "binary")
+    small["in_rails"] = rails
+    np.random.seed(12)
+    small["noise_rails"] = ref.apply_noise(rails, 15)
+    # the motion-blur kernel itself
+    small["kernel_9_0"] = ref._motion_blur_kernel(9, 0)
+    np.savez_compressed(os.path.join(HERE, "golden_small.npz"), **small)
+
+    hashes = {"versions": {"numpy": np.__version__, "cv2": cv2.__version__},
+              "big": {}, "decisions": {}, "noise_sequence": {}}
+    for name, seed, h, w in BIG_CASES:
+        img = synth(seed, h, w)
+        np.random.seed(42)
+        hashes["big"][name] = {
+            "seed": seed, "h": h, "w": w, "in": sha(img),
+            "blur9": sha(ref.apply_motion_blur(img, 9, 0)),
+            "lowres": sha(ref.apply_lowres(img, 0.5)),
+            "noise_seed42": sha(ref.apply_noise(img, 15)),
+        }
+    # config 1: 4 sequential apply_noise calls after one np.random.seed(42)
+    np.random.seed(42)
+    seq = []
+    for i in range(4):
+        seq.append(sha(ref.apply_noise(synth(1000 + i, 765, 1360), 15)))
+    hashes["noise_sequence"] = {"seed": 42, "first_image_seed": 1000, "sha": seq}
+    # random-apply decisions (a6-a8): which op each of 64 consecutive calls picks
+    names = {"noise": 1, "blur": 2, "lowres": 3}
+    for gate in ("ultralytics", "pil"):
+        random.seed(42)
+        ops = []
+        for _ in range(64):
+            r = random.random()
+            applied = (r < 0.5) if gate == "ultralytics" else not (r > 0.5)
+            ops.append(names[random.choice(["noise", "blur", "lowres"])] if applied else 0)
+        hashes["decisions"][gate] = ops
+    # _apply_random_corruption end to end on a small image (python + numpy streams)
+    random.seed(3)
+    np.random.seed(3)
+    img = synth(777, 40, 56)
+    outs = [sha(ref._apply_random_corruption(img)) for _ in range(12)]
+    hashes["random_corruption"] = {"py_seed": 3, "np_seed": 3, "img_seed": 777, "h": 40, "w": 56, "sha": outs}
+    # RandomCorruption (PIL, RGB) end to end
+    from PIL import Image
+    random.seed(4)
+    np.random.seed(4)
+    pil = Image.fromarray(synth(778, 40, 56))
+    t = ref.RandomCorruption(p=0.5)
+    hashes["pil_transform"] = {"py_seed": 4, "np_seed": 4, "img_seed": 778, "h": 40, "w": 56,
+                               "sha": [sha(np.array(t(pil))) for _ in range(12)]}
+    with open(os.path.join(HERE, "golden_hashes.json"), "w") as f:
+        json.dump(hashes, f, indent=1)
+    print("wrote", len(small), "arrays and", len(hashes["big"]), "big-case hashes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,80 @@
+"""CPU: the oracle restatement vs golden vectors recorded from the unmodified reference
+(tests/golden/make_golden.py).  Bit-exact (integer/byte work)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import corruption_oracle as orc
+from tests.helpers import SMALL_SHAPES, sha, synth
+
+
+@pytest.mark.parametrize("kind", ["uniform", "binary"])
+def test_small_shapes_all_ops(golden_small, kind):
+    for i, (h, w) in enumerate(SMALL_SHAPES):
+        tag = f"{kind}_{h}x{w}"
+        img = golden_small[f"in_{tag}"]
+        assert np.array_equal(img, synth(100 + i, h, w, kind))
+        assert np.array_equal(orc.apply_motion_blur(img, 9, 0), golden_small[f"blur9_{tag}"]), tag
+        assert np.array_equal(orc.apply_motion_blur(img, 5, 0), golden_small[f"blur5_{tag}"]), tag
+        assert np.array_equal(orc.apply_lowres(img, 0.5), golden_small[f"lowres_{tag}"]), tag
+        np.random.seed(7 + i)
+        assert np.array_equal(orc.apply_noise(img, 15), golden_small[f"noise_{tag}"]), tag
+
+
+def test_strided_crop_and_factors(golden_small):
+    crop = golden_small["in_crop_base"][5:53, 7:91]
+    assert not crop.flags["C_CONTIGUOUS"]
+    assert np.array_equal(orc.apply_motion_blur(crop, 9, 0), golden_small["blur9_crop"])
+    assert np.array_equal(orc.apply_lowres(crop, 0.5), golden_small["lowres_crop"])
+    img = golden_small["in_factor"]
+    for f in (0.25, 0.3, 0.75):
+        assert np.array_equal(orc.apply_lowres(img, f), golden_small[f"lowres_f{f}"])
+
+
+def test_noise_truncation_and_rails(golden_small):
+    np.random.seed(11)
+    out = orc.apply_noise(np.full((32, 40, 3), 128, np.uint8), 15)
+    assert np.array_equal(out, golden_small["noise_const128"])
+    # truncation bias: mean(out - in) ~ -0.5 on mid-range input
+    assert abs(float(out.astype(np.float64).mean()) - 127.5) < 0.6
+    np.random.seed(12)
+    assert np.array_equal(orc.apply_noise(golden_small["in_rails"], 15), golden_small["noise_rails"])
+
+
+def test_blur_kernel_is_nine_equal_taps(golden_small):
+    k = golden_small["kernel_9_0"]
+    assert k.dtype == np.float32 and k.shape == (9, 9)
+    assert np.count_nonzero(k) == 9 and np.all(k[4] == np.float32(1.0) / np.float32(9.0))
+    assert orc.motion_blur_taps(9, 0) == 9
+    with pytest.raises(NotImplementedError):
+        orc.motion_blur_taps(9, 45)
+
+
+def test_big_cases_sha(golden_hashes):
+    for name, g in golden_hashes["big"].items():
+        img = synth(g["seed"], g["h"], g["w"])
+        assert sha(img) == g["in"], name
+        assert sha(orc.apply_motion_blur(img, 9, 0)) == g["blur9"], name
+        assert sha(orc.apply_lowres(img, 0.5)) == g["lowres"], name
+        if g["h"] * g["w"] <= 1100000:
+            np.random.seed(42)
+            assert sha(orc.apply_noise(img, 15)) == g["noise_seed42"], name
+
+
+def test_noise_sequence_config1(golden_hashes):
+    g = golden_hashes["noise_sequence"]
+    np.random.seed(g["seed"])
+    for i, want in enumerate(g["sha"][:2]):
+        assert sha(orc.apply_noise(synth(g["first_image_seed"] + i, 765, 1360), 15)) == want
+
+
+def test_decisions_and_random_corruption(golden_hashes):
+    for gate in ("ultralytics", "pil"):
+        random.seed(42)
+        assert orc.draw_decisions(64, gate) == golden_hashes["decisions"][gate]
+    g = golden_hashes["random_corruption"]
+    random.seed(g["py_seed"])
+    np.random.seed(g["np_seed"])
+    img = synth(g["img_seed"], g["h"], g["w"])
+    assert [sha(orc.apply_random_corruption(img)) for _ in g["sha"]] == g["sha"]
