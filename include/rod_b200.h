@@ -1,0 +1,129 @@
+/* rod_b200.h -- C ABI of the B200-native corruption pipeline (librod_b200.so).
+ *
+ * Drop-in boundary for the hot path of ysbbin/Robust-Object-Detection:
+ * scripts/augmentations.py (apply_noise :30-33, apply_motion_blur :36-38,
+ * apply_lowres :41-45, _apply_random_corruption :48-56) and its batch twin
+ * scripts/build_corrupted_testsets.py:41-59,108-124.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Every function returns a
+ * rod_status (0 = ok) and never throws.  "Device" pointers are CUDA device
+ * addresses on the current device; `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream).  All device work is stream-ordered and the
+ * library never synchronises unless the function name ends in _host.
+ *
+ * Images are HWC uint8 with 3 interleaved channels (BGR for the reference's
+ * callers; every operation is per channel).  A batch is described by a table of
+ * rod_image_desc: byte offsets into one source and one destination buffer, so
+ * ragged (mixed-resolution) batches are one flat buffer + a descriptor table.
+ */
+#ifndef ROD_B200_H
+#define ROD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ROD_API __attribute__((visibility("default")))
+#else
+#define ROD_API
+#endif
+
+typedef enum rod_status {
+    ROD_OK = 0,
+    ROD_ERR_INVALID_ARG = 1,  /* bad shape / pitch / NULL pointer                     */
+    ROD_ERR_UNSUPPORTED = 2,  /* parameter outside the exact-parity domain            */
+    ROD_ERR_CUDA = 3,         /* a CUDA call failed; see rod_last_cuda_error()        */
+    ROD_ERR_NO_DEVICE = 4,    /* no CUDA device: there is NO CPU fallback             */
+    ROD_ERR_OOM = 5
+} rod_status;
+
+/* Op-codes of the random one-of-three apply (augmentations.py:50-56); 0 = not applied. */
+enum { ROD_OP_NONE = 0, ROD_OP_NOISE = 1, ROD_OP_BLUR = 2, ROD_OP_LOWRES = 3 };
+
+typedef struct rod_image_desc {
+    uint64_t src_offset; /* byte offset of pixel (0,0) channel 0 from the src base pointer */
+    uint64_t dst_offset; /* same for the dst base pointer                                   */
+    int32_t  height;     /* rows    (>= 1)                                                  */
+    int32_t  width;      /* pixels  (>= 1); a row holds 3*width bytes                       */
+    int64_t  src_pitch;  /* bytes between consecutive source rows, >= 3*width              */
+    int64_t  dst_pitch;  /* bytes between consecutive destination rows, >= 3*width         */
+} rod_image_desc;
+
+typedef struct rod_plan rod_plan; /* opaque: device descriptor table + tile lists + resize tables */
+
+/* Library / device probing ------------------------------------------------------------ */
+ROD_API const char* rod_version(void);
+ROD_API int         rod_device_count(void);           /* 0 when no GPU is visible */
+ROD_API int         rod_last_cuda_error(void);        /* cudaError_t of the last failing CUDA call (thread local) */
+ROD_API const char* rod_status_string(int status);
+
+/* Plans ------------------------------------------------------------------------------- */
+/* Uploads the descriptor table (host array) to the current device and precomputes the
+ * per-op tile lists.  The plan can be reused for any number of launches on any stream. */
+ROD_API int  rod_plan_create(const rod_image_desc* images, int n_images, rod_plan** out_plan);
+ROD_API void rod_plan_destroy(rod_plan* plan);
+ROD_API int  rod_plan_num_images(const rod_plan* plan);
+/* Sum over images of 3*H*W: bytes one full-resolution pass reads (and writes). */
+ROD_API uint64_t rod_plan_payload_bytes(const rod_plan* plan);
+/* Number of kernels one call of the given op launches (for launch accounting). */
+ROD_API int  rod_plan_launches(const rod_plan* plan, int op);
+
+/* a1: apply_noise (augmentations.py:30-33).
+ * compat mode (noise != NULL): `noise` is a device float32 array holding, image after
+ *   image in plan order, the H*W*3 field the reference would have drawn; result is
+ *   uint8(trunc(clamp(float(src) + noise, 0, 255))) -- bit-exact with the reference.
+ * philox mode (noise == NULL): the field is generated in registers from
+ *   Philox4x32-10(key = seed, counter = (element/4, first_image_index + i, offset)) +
+ *   Box-Muller, scaled by sigma; reproducible for any batch split / GPU count.
+ * opcodes (device uint8[n_images], may be NULL): when given, only images whose
+ *   op-code equals ROD_OP_NOISE are processed; the others are left untouched. */
+ROD_API int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const float* noise,
+                 float sigma, uint64_t seed, uint64_t first_image_index, uint32_t offset,
+                 const uint8_t* opcodes, void* stream);
+/* The float32 field philox mode adds (same layout as `noise` above); for tests/resume. */
+ROD_API int rod_noise_field_f32(const rod_plan* plan, float* out_field, float sigma, uint64_t seed,
+                        uint64_t first_image_index, uint32_t offset, void* stream);
+
+/* a2+a3: apply_motion_blur(img, k, angle_deg) (augmentations.py:21-38) for angle_deg == 0:
+ * horizontal k-tap box, BORDER_REFLECT_101, out = (2S + k) / (2k).  k odd, 1 <= k <= 31;
+ * anything else returns ROD_ERR_UNSUPPORTED (never an approximation). */
+ROD_API int rod_blur_h_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, double angle_deg,
+                  const uint8_t* opcodes, void* stream);
+
+/* a4+a5: apply_lowres(img, factor) (augmentations.py:41-45): INTER_AREA down to
+ * (max(1,int(W*factor)), max(1,int(H*factor))) then 8-bit INTER_LINEAR back, fused: the
+ * low-resolution intermediate lives in shared memory only.  0 < factor <= 1. */
+ROD_API int rod_lowres_u8(rod_plan* plan, const uint8_t* src, uint8_t* dst, double factor,
+                  const uint8_t* opcodes, void* stream);
+
+/* a6-a9: one launch group that applies opcodes[i] to image i (ROD_OP_NONE = byte copy),
+ * with the reference's constants unless overridden: sigma, k, factor.  Noise is philox
+ * mode unless `noise` is given. */
+ROD_API int rod_corrupt_batch_u8(rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
+                         const float* noise, float sigma, int k, double factor, uint64_t seed,
+                         uint64_t first_image_index, uint32_t offset, void* stream);
+
+/* Training path (BASELINE config 5): corruption fused with the detector-input formatting
+ * of Ultralytics' LetterBox + Format + preprocess_batch: INTER_LINEAR resize-to-fit of the
+ * CORRUPTED pixels, constant pad, BGR->RGB, HWC->CHW, half(float(u8)/255).  `out` is a
+ * device fp16 array [n_images, 3, out_h, out_w]. */
+ROD_API int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, const uint8_t* opcodes,
+                              void* out_f16, int out_h, int out_w, int pad_value,
+                              const float* noise, float sigma, int k, double factor, uint64_t seed,
+                              uint64_t first_image_index, uint32_t offset, void* stream);
+
+/* Host-buffer entry points (what a per-image Python/cgo/JNI caller binds): src/dst are HOST
+ * pointers laid out by the plan's descriptors; the call stages through pinned memory,
+ * overlaps H2D / kernel / D2H in chunks of images, and returns after dst is complete. */
+ROD_API int rod_apply_host(rod_plan* plan, int op, const uint8_t* src_host, uint8_t* dst_host,
+                   const float* noise_host, float sigma, int k, double factor, uint64_t seed,
+                   uint64_t first_image_index, uint32_t offset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROD_B200_H */

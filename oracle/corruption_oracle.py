@@ -99,33 +99,33 @@ def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
 
 def philox_noise_field(n_elems: int, sigma: float, seed: int, image_index: int,
                        offset: int = 0) -> np.ndarray:
-    """float64 restatement of the kernel's Philox noise stream for one image.
+    """float64 restatement of the kernel's Philox noise stream for one image
+    (robust-object-detection_b200/csrc/rod_core.h: philox4x32_10 + boxmuller4).
 
     Element e (flat HWC index) belongs to group g = e // 4, lane j = e % 4.
-    counter = (g_lo32, g_hi32, image_index_lo32 , offset_lo32 ^ (image_index_hi32 << 0...)) --
-    exactly: ctr = [g & 0xffffffff, g >> 32, image_index & 0xffffffff, offset & 0xffffffff],
-    key = [seed & 0xffffffff, seed >> 32].
-    r[0..3] -> u_a = (r0 + 0.5) * 2^-32, u_b = (r1 + 0.5) * 2^-32, u_c, u_d likewise;
-    (z0, z1) = sqrt(-2 ln u_a) * (cos, sin)(2 pi u_b); (z2, z3) from (u_c, u_d).
-    noise[e] = sigma * z_j.
+      ctr = [g, image_index & 0xffffffff, image_index >> 32, offset]
+      key = [seed & 0xffffffff, seed >> 32]
+      r = Philox4x32-10(ctr, key)
+      ua = (r0 + 0.5) * 2^-32                      radius uniform of pair 0 (r2 for pair 1)
+      th = pi * (((r1 >> 9) + 0.5) * 2^-22 - 1)    angle of pair 0 (r3 for pair 1)
+      z0 = sqrt(-2 ln ua) cos th, z1 = sqrt(-2 ln ua) sin th;  noise[e] = sigma * z_j.
     """
     n_groups = (n_elems + 3) // 4
     g = np.arange(n_groups, dtype=np.uint64)
     ctr = np.empty((n_groups, 4), dtype=np.uint32)
     ctr[:, 0] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)
-    ctr[:, 1] = (g >> np.uint64(32)).astype(np.uint32)
-    ctr[:, 2] = np.uint32(image_index & 0xFFFFFFFF)
+    ctr[:, 1] = np.uint32(image_index & 0xFFFFFFFF)
+    ctr[:, 2] = np.uint32((image_index >> 32) & 0xFFFFFFFF)
     ctr[:, 3] = np.uint32(offset & 0xFFFFFFFF)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
-    r = philox4x32_10(ctr, key).astype(np.float64)
-    u = (r + 0.5) * (2.0 ** -32)
-    rad0 = np.sqrt(-2.0 * np.log(u[:, 0]))
-    rad1 = np.sqrt(-2.0 * np.log(u[:, 2]))
+    r = philox4x32_10(ctr, key)
     z = np.empty((n_groups, 4), dtype=np.float64)
-    z[:, 0] = rad0 * np.cos(2.0 * np.pi * u[:, 1])
-    z[:, 1] = rad0 * np.sin(2.0 * np.pi * u[:, 1])
-    z[:, 2] = rad1 * np.cos(2.0 * np.pi * u[:, 3])
-    z[:, 3] = rad1 * np.sin(2.0 * np.pi * u[:, 3])
+    for p in range(2):
+        ua = (r[:, 2 * p].astype(np.float64) + 0.5) * (2.0 ** -32)
+        sb = ((r[:, 2 * p + 1] >> np.uint32(9)).astype(np.float64) + 0.5) * (2.0 ** -22) - 1.0
+        rad = np.sqrt(-2.0 * np.log(ua))
+        z[:, 2 * p] = rad * np.cos(np.pi * sb)
+        z[:, 2 * p + 1] = rad * np.sin(np.pi * sb)
     return (sigma * z).reshape(-1)[:n_elems]
 
 

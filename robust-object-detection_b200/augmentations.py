@@ -1,0 +1,172 @@
+"""Drop-in for scripts/augmentations.py of ysbbin/Robust-Object-Detection.
+
+Same module surface, same signatures, same observable RNG behaviour -- but every pixel is
+computed on a B200 by librod_b200.so (hand-written sm_100a CUDA, include/rod_b200.h).
+There is no CPU fallback: without the built library or without a GPU the calls raise.
+
+    reference (scripts/augmentations.py)            here
+    ---------------------------------------------   --------------------------------------------
+    NOISE_SIGMA .. DOWNSCALE_FACTOR      :14-17     same names and values
+    _motion_blur_kernel(k, angle_deg)    :21-27     same (host-side, float32 k x k; angle 0 only)
+    apply_noise(img_bgr, sigma)          :30-33     rod_apply_host(ROD_OP_NOISE)
+    apply_motion_blur(img_bgr, k, angle) :36-38     rod_apply_host(ROD_OP_BLUR)
+    apply_lowres(img_bgr, factor)        :41-45     rod_apply_host(ROD_OP_LOWRES)
+    _apply_random_corruption(img_bgr)    :48-56     same dispatch, same `random.choice`
+    RandomCorruption(p)                  :60-74     same gate (skip iff random() > p)
+    patch_ultralytics_augmentations()    :78-98     same gate (apply iff random() < 0.5)
+
+Noise modes.  'compat' (default) draws the field on the host with
+np.random.normal(0, sigma, shape).astype(float32) -- consuming NumPy's global legacy stream
+exactly like the reference -- and the GPU does the add/clip/truncate, so outputs are
+bit-identical to the reference under the same np.random.seed.  'philox' generates the field
+inside the kernel (Philox4x32-10 + Box-Muller keyed by seed and a running image counter):
+no host RNG work, statistically equivalent, not bit-identical.
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+
+from . import _native as N
+from .batch import CorruptionPlan
+
+# ---- Parameters (same as build_corrupted_testsets.py:13-23) ----
+NOISE_SIGMA = 15
+BLUR_KERNEL = 9
+BLUR_ANGLE_DEG = 0
+DOWNSCALE_FACTOR = 0.5
+
+_noise_mode = "compat"
+_philox_seed = 0
+_philox_counter = 0
+_plans: dict = {}
+_PLAN_CACHE_MAX = 64
+
+
+def set_noise_mode(mode: str, seed: int = 0) -> None:
+    """'compat' (bit-exact, host RNG) or 'philox' (in-kernel RNG; `seed` keys the stream)."""
+    global _noise_mode, _philox_seed, _philox_counter
+    if mode not in ("compat", "philox"):
+        raise ValueError("mode must be 'compat' or 'philox'")
+    _noise_mode, _philox_seed, _philox_counter = mode, int(seed), 0
+
+
+def _as_rows(img: np.ndarray):
+    """Validate an HWC uint8 image; return (array whose rows are contiguous, row pitch in bytes)."""
+    if not isinstance(img, np.ndarray) or img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+        raise ValueError("expected a uint8 HxWx3 numpy image")
+    h, w, _ = img.shape
+    if h < 1 or w < 1:
+        raise ValueError("empty image")  # cv2 raises cv2.error on empty input as well
+    if img.strides[2] != 1 or img.strides[1] != 3 or img.strides[0] < 3 * w:
+        img = np.ascontiguousarray(img)  # exotic views (flipped, channel-sliced): compact first
+    return img, img.strides[0]
+
+
+def _plan_for(h: int, w: int, pitch: int) -> CorruptionPlan:
+    key = (h, w, pitch)
+    plan = _plans.get(key)
+    if plan is None:
+        if len(_plans) >= _PLAN_CACHE_MAX:
+            _plans.pop(next(iter(_plans)))
+        plan = CorruptionPlan([(h, w)], [0], [0], src_pitches=[pitch], dst_pitches=[3 * w])
+        _plans[key] = plan
+    return plan
+
+
+def _run(op: int, img_bgr: np.ndarray, *, noise=None, sigma=0.0, k=BLUR_KERNEL, factor=DOWNSCALE_FACTOR,
+         seed=0, index=0) -> np.ndarray:
+    img, pitch = _as_rows(img_bgr)
+    h, w, _ = img.shape
+    out = np.empty((h, w, 3), dtype=np.uint8)  # fresh, C-contiguous, caller-owned
+    _plan_for(h, w, pitch).apply_host(op, img, out, noise_host=noise, sigma=sigma, k=k, factor=factor, seed=seed,
+                                      first_image_index=index)
+    return out
+
+
+# ---- Low-level corruption functions ----
+def _motion_blur_kernel(k: int, angle_deg: float):
+    """The k x k float32 kernel of augmentations.py:21-27.  At angle 0 the warpAffine there is
+    the identity, so the kernel is row k//2 filled with float32(1)/float32(k)."""
+    if float(angle_deg) != 0.0:
+        raise NotImplementedError("only angle_deg == 0 is implemented (the reference never passes another value)")
+    kernel = np.zeros((k, k), dtype=np.float32)
+    kernel[k // 2, :] = 1.0
+    return kernel / (kernel.sum() + 1e-8)
+
+
+def apply_noise(img_bgr: np.ndarray, sigma: float) -> np.ndarray:
+    global _philox_counter
+    if _noise_mode == "compat":
+        # the exact draw of augmentations.py:31 (global legacy NumPy RNG, float64 -> float32)
+        noise = np.random.normal(0, sigma, img_bgr.shape).astype(np.float32)
+        return _run(N.OP_NOISE, img_bgr, noise=np.ascontiguousarray(noise), sigma=float(sigma))
+    idx = _philox_counter
+    _philox_counter += 1
+    return _run(N.OP_NOISE, img_bgr, sigma=float(sigma), seed=_philox_seed, index=idx)
+
+
+def apply_motion_blur(img_bgr: np.ndarray, k: int, angle_deg: float) -> np.ndarray:
+    if float(angle_deg) != 0.0:
+        raise NotImplementedError("apply_motion_blur: only angle_deg == 0 is implemented on the B200 path")
+    if int(k) != k or k < 1 or k % 2 == 0 or k > 31:
+        raise NotImplementedError("apply_motion_blur: k must be odd and in [1, 31] on the B200 path")
+    return _run(N.OP_BLUR, img_bgr, k=int(k))
+
+
+def apply_lowres(img_bgr: np.ndarray, factor: float) -> np.ndarray:
+    return _run(N.OP_LOWRES, img_bgr, factor=float(factor))
+
+
+# name -> call with the module constants looked up at call time (augmentations.py:51-56)
+_DISPATCH = {
+    "noise": lambda im: apply_noise(im, NOISE_SIGMA),
+    "blur": lambda im: apply_motion_blur(im, BLUR_KERNEL, BLUR_ANGLE_DEG),
+    "lowres": lambda im: apply_lowres(im, DOWNSCALE_FACTOR),
+}
+
+
+def _apply_random_corruption(img_bgr: np.ndarray) -> np.ndarray:
+    """One of the three corruptions, picked with the same `random.choice` draw as the reference."""
+    return _DISPATCH[random.choice(["noise", "blur", "lowres"])](img_bgr)
+
+
+# ---- FRCNN: PIL Image transform ----
+class RandomCorruption:
+    """PIL Image transform that randomly applies one corruption (torchvision pipelines).
+
+    All three corruptions act per channel, so the RGB<->BGR swaps of the reference
+    (augmentations.py:72,74) only decide which noise plane meets which channel: the image is
+    reversed along the channel axis before and after, as the reference does."""
+
+    def __init__(self, p: float = 0.5):
+        self.p = p
+
+    def __call__(self, img):
+        from PIL import Image
+        if random.random() > self.p:
+            return img
+        arr = np.array(img)[:, :, ::-1]          # RGB -> BGR (a strided view; compacted on upload)
+        arr = _apply_random_corruption(np.ascontiguousarray(arr))
+        return Image.fromarray(np.ascontiguousarray(arr[:, :, ::-1]))
+
+
+# ---- Ultralytics: monkey-patch Albumentations ----
+def patch_ultralytics_augmentations():
+    """Inject the corruption into Ultralytics' Albumentations transform (call ONCE before
+    model.train()).  With DataLoader workers > 0 the hook runs inside worker processes; CUDA
+    cannot be initialised in a fork()ed child of a process that already uses it, so use
+    workers=0 / the 'spawn' start method, or the batched main-process driver
+    (robust_object_detection_b200.batch.CorruptionPlan.corrupt_letterbox) instead."""
+    from ultralytics.data import augment as _augment
+
+    _OrigCall = _augment.Albumentations.__call__
+
+    def _patched_call(self, labels):
+        if random.random() < 0.5:
+            labels["img"] = _apply_random_corruption(labels["img"])
+        return _OrigCall(self, labels)
+
+    _augment.Albumentations.__call__ = _patched_call
+    print("[augmentations] Ultralytics Albumentations patched with corruption augmentations (B200 path)")

@@ -1,0 +1,176 @@
+"""Device-resident batches for the corruption path (the batch driver of
+scripts/build_corrupted_testsets.py:108-124 and the training-time hook of
+scripts/augmentations.py:91-95, moved onto the GPU).
+
+A `CorruptionPlan` wraps one `rod_plan` (include/rod_b200.h): a descriptor table for a
+uniform [N,H,W,3] tensor or for a ragged flat buffer of mixed-resolution images.  PyTorch is
+used only for device memory and the current stream; all pixel work happens in librod_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+import random
+from typing import Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+NOISE_SIGMA = 15
+BLUR_KERNEL = 9
+BLUR_ANGLE_DEG = 0
+DOWNSCALE_FACTOR = 0.5
+IMAGE_ALIGN = 256  # byte alignment of each image inside a ragged flat buffer
+
+
+def _ptr(t) -> Optional[int]:
+    """Device (or host) address of a torch tensor / numpy array / int / None."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def _stream_handle(stream=None) -> Optional[int]:
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream or None
+
+
+def draw_decisions(n: int, gate: str = "ultralytics", p: float = 0.5) -> np.ndarray:
+    """Op-codes for n consecutive images, consuming Python's global `random` exactly as n
+    consecutive reference hook calls would: gate 'ultralytics' = apply iff random() < 0.5
+    (augmentations.py:93), gate 'pil' = skip iff random() > p (augmentations.py:70); then
+    random.choice(["noise","blur","lowres"]) (augmentations.py:50)."""
+    ops = np.zeros(n, dtype=np.uint8)
+    for i in range(n):
+        r = random.random()
+        applied = (r < 0.5) if gate == "ultralytics" else not (r > p)
+        if applied:
+            ops[i] = 1 + ("noise", "blur", "lowres").index(random.choice(["noise", "blur", "lowres"]))
+    return ops
+
+
+class CorruptionPlan:
+    """Descriptor table + tile lists + resize tables for one batch layout."""
+
+    def __init__(self, shapes: Sequence[Tuple[int, int]], src_offsets: Sequence[int], dst_offsets: Sequence[int],
+                 src_pitches: Optional[Sequence[int]] = None, dst_pitches: Optional[Sequence[int]] = None):
+        N.require_device()
+        n = len(shapes)
+        if n < 1:
+            raise ValueError("a plan needs at least one image")
+        descs = (N.ImageDesc * n)()
+        for i, (h, w) in enumerate(shapes):
+            descs[i].src_offset = int(src_offsets[i])
+            descs[i].dst_offset = int(dst_offsets[i])
+            descs[i].height, descs[i].width = int(h), int(w)
+            descs[i].src_pitch = int(src_pitches[i]) if src_pitches is not None else 3 * int(w)
+            descs[i].dst_pitch = int(dst_pitches[i]) if dst_pitches is not None else 3 * int(w)
+        handle = ctypes.c_void_p()
+        N.check(N.lib().rod_plan_create(descs, n, ctypes.byref(handle)), "rod_plan_create")
+        self._h = handle
+        self.shapes = [(int(h), int(w)) for h, w in shapes]
+        self.n_images = n
+        self.src_offsets = [int(o) for o in src_offsets]
+        self.dst_offsets = [int(o) for o in dst_offsets]
+        self.payload_bytes = int(N.lib().rod_plan_payload_bytes(handle))
+        last = n - 1
+        self.src_bytes = max(o + (h - 1) * (src_pitches[i] if src_pitches is not None else 3 * w) + 3 * w
+                             for i, (o, (h, w)) in enumerate(zip(self.src_offsets, self.shapes)))
+        self.dst_bytes = max(o + (h - 1) * (dst_pitches[i] if dst_pitches is not None else 3 * w) + 3 * w
+                             for i, (o, (h, w)) in enumerate(zip(self.dst_offsets, self.shapes)))
+        del last
+
+    # -- constructors ------------------------------------------------------------------
+    @classmethod
+    def uniform(cls, n: int, h: int, w: int) -> "CorruptionPlan":
+        """Contiguous [n, h, w, 3] uint8 tensors for both src and dst."""
+        size = 3 * h * w
+        offs = [i * size for i in range(n)]
+        return cls([(h, w)] * n, offs, offs)
+
+    @classmethod
+    def ragged(cls, shapes: Iterable[Tuple[int, int]], align: int = IMAGE_ALIGN) -> "CorruptionPlan":
+        """Mixed-resolution images packed into one flat buffer, each image contiguous and
+        starting at a multiple of `align` bytes (same layout for src and dst)."""
+        shapes = list(shapes)
+        offs, cur = [], 0
+        for h, w in shapes:
+            offs.append(cur)
+            cur += (3 * h * w + align - 1) // align * align
+        return cls(shapes, offs, offs)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                N.lib().rod_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- helpers -----------------------------------------------------------------------
+    def launches(self, op: int) -> int:
+        return int(N.lib().rod_plan_launches(self._h, int(op)))
+
+    def pack(self, images: Sequence[np.ndarray]) -> np.ndarray:
+        """Host flat uint8 buffer holding `images` at this plan's source offsets."""
+        buf = np.zeros(self.src_bytes, dtype=np.uint8)
+        for img, off, (h, w) in zip(images, self.src_offsets, self.shapes):
+            assert img.shape == (h, w, 3) and img.dtype == np.uint8
+            buf[off:off + 3 * h * w] = np.ascontiguousarray(img).reshape(-1)
+        return buf
+
+    def unpack(self, flat: np.ndarray):
+        """Views of the images inside a host flat buffer laid out by the dst offsets."""
+        return [flat[off:off + 3 * h * w].reshape(h, w, 3) for off, (h, w) in zip(self.dst_offsets, self.shapes)]
+
+    # -- device ops (torch CUDA uint8 tensors or raw device addresses) -------------------
+    def noise(self, src, dst, noise=None, sigma: float = NOISE_SIGMA, seed: int = 0, first_image_index: int = 0,
+              offset: int = 0, opcodes=None, stream=None) -> None:
+        N.check(N.lib().rod_noise_u8(self._h, _ptr(src), _ptr(dst), _ptr(noise), float(sigma), int(seed),
+                                     int(first_image_index), int(offset), _ptr(opcodes), _stream_handle(stream)),
+                "rod_noise_u8")
+
+    def noise_field(self, out, sigma: float = NOISE_SIGMA, seed: int = 0, first_image_index: int = 0, offset: int = 0,
+                    stream=None) -> None:
+        N.check(N.lib().rod_noise_field_f32(self._h, _ptr(out), float(sigma), int(seed), int(first_image_index),
+                                            int(offset), _stream_handle(stream)), "rod_noise_field_f32")
+
+    def blur(self, src, dst, k: int = BLUR_KERNEL, angle_deg: float = BLUR_ANGLE_DEG, opcodes=None, stream=None) -> None:
+        N.check(N.lib().rod_blur_h_u8(self._h, _ptr(src), _ptr(dst), int(k), float(angle_deg), _ptr(opcodes),
+                                      _stream_handle(stream)), "rod_blur_h_u8")
+
+    def lowres(self, src, dst, factor: float = DOWNSCALE_FACTOR, opcodes=None, stream=None) -> None:
+        N.check(N.lib().rod_lowres_u8(self._h, _ptr(src), _ptr(dst), float(factor), _ptr(opcodes),
+                                      _stream_handle(stream)), "rod_lowres_u8")
+
+    def corrupt(self, src, dst, opcodes, noise=None, sigma: float = NOISE_SIGMA, k: int = BLUR_KERNEL,
+                factor: float = DOWNSCALE_FACTOR, seed: int = 0, first_image_index: int = 0, offset: int = 0,
+                stream=None) -> None:
+        """opcodes: device uint8[n_images] (0 none / 1 noise / 2 blur / 3 lowres)."""
+        N.check(N.lib().rod_corrupt_batch_u8(self._h, _ptr(src), _ptr(dst), _ptr(opcodes), _ptr(noise), float(sigma),
+                                             int(k), float(factor), int(seed), int(first_image_index), int(offset),
+                                             _stream_handle(stream)), "rod_corrupt_batch_u8")
+
+    def corrupt_letterbox(self, src, opcodes, out_f16, out_h: int = 640, out_w: int = 640, pad_value: int = 114,
+                          noise=None, sigma: float = NOISE_SIGMA, k: int = BLUR_KERNEL,
+                          factor: float = DOWNSCALE_FACTOR, seed: int = 0, first_image_index: int = 0,
+                          offset: int = 0, stream=None) -> None:
+        """Training path: corruption + letterbox + BGR->RGB + CHW + /255 -> fp16 [n,3,out_h,out_w]."""
+        N.check(N.lib().rod_corrupt_letterbox_f16(self._h, _ptr(src), _ptr(opcodes), _ptr(out_f16), int(out_h),
+                                                  int(out_w), int(pad_value), _ptr(noise), float(sigma), int(k),
+                                                  float(factor), int(seed), int(first_image_index), int(offset),
+                                                  _stream_handle(stream)), "rod_corrupt_letterbox_f16")
+
+    # -- host-buffer path (H2D + kernel + D2H inside the call) ---------------------------
+    def apply_host(self, op: int, src_host, dst_host, noise_host=None, sigma: float = NOISE_SIGMA,
+                   k: int = BLUR_KERNEL, factor: float = DOWNSCALE_FACTOR, seed: int = 0, first_image_index: int = 0,
+                   offset: int = 0) -> None:
+        N.check(N.lib().rod_apply_host(self._h, int(op), _ptr(src_host), _ptr(dst_host), _ptr(noise_host),
+                                       float(sigma), int(k), float(factor), int(seed), int(first_image_index),
+                                       int(offset)), "rod_apply_host")

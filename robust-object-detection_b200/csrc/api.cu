@@ -1,0 +1,213 @@
+// api.cu -- extern "C" entry points of librod_b200.so (declared in include/rod_b200.h).
+#include <algorithm>
+
+#include "rod_internal.h"
+
+using namespace rod;
+
+namespace {
+
+bool blur_supported(int k, double angle) { return angle == 0.0 && k >= 1 && k <= 31 && (k & 1) == 1; }
+
+int run_op(rod_plan* plan, int op, const uint8_t* src, uint8_t* dst, const float* noise, float sigma, int k,
+           double factor, uint64_t seed, uint64_t first_image, uint32_t offset, const uint8_t* opcodes,
+           cudaStream_t stream, int img_lo, int img_hi) {
+    switch (op) {
+        case ROD_OP_NONE:
+            return launch_noise(plan, NOISE_COPY, src, dst, nullptr, nullptr, 0.f, 0, 0, 0, opcodes, ROD_OP_NONE,
+                                stream, img_lo, img_hi);
+        case ROD_OP_NOISE:
+            return launch_noise(plan, noise ? NOISE_COMPAT : NOISE_PHILOX, src, dst, noise, nullptr, sigma, seed,
+                                first_image, offset, opcodes, ROD_OP_NOISE, stream, img_lo, img_hi);
+        case ROD_OP_BLUR:
+            if (!blur_supported(k, 0.0)) return ROD_ERR_UNSUPPORTED;
+            if (k == 1)
+                return launch_noise(plan, NOISE_COPY, src, dst, nullptr, nullptr, 0.f, 0, 0, 0, opcodes, ROD_OP_BLUR,
+                                    stream, img_lo, img_hi);
+            return launch_blur(plan, src, dst, k, opcodes, stream, img_lo, img_hi);
+        case ROD_OP_LOWRES: {
+            int rc = ensure_lowres_tables(plan, factor);
+            if (rc != ROD_OK) return rc;
+            if (plan->lowres_all_identity)
+                return launch_noise(plan, NOISE_COPY, src, dst, nullptr, nullptr, 0.f, 0, 0, 0, opcodes,
+                                    ROD_OP_LOWRES, stream, img_lo, img_hi);
+            return launch_lowres(plan, src, dst, opcodes, stream, img_lo, img_hi);
+        }
+        default:
+            return ROD_ERR_INVALID_ARG;
+    }
+}
+
+}  // namespace
+
+extern "C" const char* rod_version(void) { return "rod_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int rod_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int rod_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" const char* rod_status_string(int status) {
+    switch (status) {
+        case ROD_OK: return "ok";
+        case ROD_ERR_INVALID_ARG: return "invalid argument";
+        case ROD_ERR_UNSUPPORTED: return "parameter outside the exact-parity domain (no approximation, no CPU fallback)";
+        case ROD_ERR_CUDA: return "CUDA error";
+        case ROD_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case ROD_ERR_OOM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int rod_plan_launches(const rod_plan* plan, int op) {
+    if (plan == nullptr) return 0;
+    switch (op) {
+        case ROD_OP_NONE: case ROD_OP_NOISE: case ROD_OP_BLUR: case ROD_OP_LOWRES: return 1;
+        case 100: return 4;  // rod_corrupt_batch_u8: copy + noise + blur + lowres
+        case 101: return 5;  // rod_corrupt_letterbox_f16: the four above + letterbox
+        default: return 0;
+    }
+}
+
+extern "C" int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const float* noise, float sigma,
+                            uint64_t seed, uint64_t first_image_index, uint32_t offset, const uint8_t* opcodes,
+                            void* stream) {
+    if (plan == nullptr || src == nullptr || dst == nullptr) return ROD_ERR_INVALID_ARG;
+    if (!(sigma >= 0.0f)) return ROD_ERR_INVALID_ARG;
+    return launch_noise(plan, noise ? NOISE_COMPAT : NOISE_PHILOX, src, dst, noise, nullptr, sigma, seed,
+                        first_image_index, offset, opcodes, ROD_OP_NOISE, (cudaStream_t)stream, 0, plan->n_images);
+}
+
+extern "C" int rod_noise_field_f32(const rod_plan* plan, float* out_field, float sigma, uint64_t seed,
+                                   uint64_t first_image_index, uint32_t offset, void* stream) {
+    if (plan == nullptr || out_field == nullptr) return ROD_ERR_INVALID_ARG;
+    return launch_noise(plan, NOISE_FIELD, nullptr, nullptr, nullptr, out_field, sigma, seed, first_image_index,
+                        offset, nullptr, ROD_OP_NOISE, (cudaStream_t)stream, 0, plan->n_images);
+}
+
+extern "C" int rod_blur_h_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, double angle_deg,
+                             const uint8_t* opcodes, void* stream) {
+    if (plan == nullptr || src == nullptr || dst == nullptr) return ROD_ERR_INVALID_ARG;
+    if (!blur_supported(k, angle_deg)) return ROD_ERR_UNSUPPORTED;
+    return run_op(const_cast<rod_plan*>(plan), ROD_OP_BLUR, src, dst, nullptr, 0.f, k, 0.0, 0, 0, 0, opcodes,
+                  (cudaStream_t)stream, 0, plan->n_images);
+}
+
+extern "C" int rod_lowres_u8(rod_plan* plan, const uint8_t* src, uint8_t* dst, double factor, const uint8_t* opcodes,
+                             void* stream) {
+    if (plan == nullptr || src == nullptr || dst == nullptr) return ROD_ERR_INVALID_ARG;
+    return run_op(plan, ROD_OP_LOWRES, src, dst, nullptr, 0.f, 0, factor, 0, 0, 0, opcodes, (cudaStream_t)stream, 0,
+                  plan->n_images);
+}
+
+extern "C" int rod_corrupt_batch_u8(rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
+                                    const float* noise, float sigma, int k, double factor, uint64_t seed,
+                                    uint64_t first_image_index, uint32_t offset, void* stream) {
+    if (plan == nullptr || src == nullptr || dst == nullptr || opcodes == nullptr) return ROD_ERR_INVALID_ARG;
+    for (int op = ROD_OP_NONE; op <= ROD_OP_LOWRES; ++op) {
+        int rc = run_op(plan, op, src, dst, noise, sigma, k, factor, seed, first_image_index, offset, opcodes,
+                        (cudaStream_t)stream, 0, plan->n_images);
+        if (rc != ROD_OK) return rc;
+    }
+    return ROD_OK;
+}
+
+extern "C" int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, const uint8_t* opcodes, void* out_f16,
+                                         int out_h, int out_w, int pad_value, const float* noise, float sigma, int k,
+                                         double factor, uint64_t seed, uint64_t first_image_index, uint32_t offset,
+                                         void* stream) {
+    if (plan == nullptr || src == nullptr || out_f16 == nullptr || opcodes == nullptr) return ROD_ERR_INVALID_ARG;
+    if (pad_value < 0 || pad_value > 255) return ROD_ERR_INVALID_ARG;
+    int rc = ensure_letterbox_tables(plan, out_h, out_w);
+    if (rc != ROD_OK) return rc;
+    if (plan->d_scratch == nullptr || plan->scratch_bytes < plan->dst_extent) {
+        if (plan->d_scratch) cudaFree(plan->d_scratch);
+        plan->d_scratch = nullptr;
+        ROD_CUDA(cudaMalloc((void**)&plan->d_scratch, plan->dst_extent + 64));
+        plan->scratch_bytes = plan->dst_extent;
+    }
+    rc = rod_corrupt_batch_u8(plan, src, plan->d_scratch, opcodes, noise, sigma, k, factor, seed, first_image_index,
+                              offset, stream);
+    if (rc != ROD_OK) return rc;
+    return launch_letterbox(plan, plan->d_scratch, out_f16, pad_value, (cudaStream_t)stream);
+}
+
+// Host-buffer path: chunks of images are pipelined over three streams so the H2D copy of chunk
+// c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap.
+extern "C" int rod_apply_host(rod_plan* plan, int op, const uint8_t* src_host, uint8_t* dst_host,
+                              const float* noise_host, float sigma, int k, double factor, uint64_t seed,
+                              uint64_t first_image_index, uint32_t offset) {
+    if (plan == nullptr || src_host == nullptr || dst_host == nullptr) return ROD_ERR_INVALID_ARG;
+    if (op < ROD_OP_NONE || op > ROD_OP_LOWRES) return ROD_ERR_INVALID_ARG;
+    if (op == ROD_OP_BLUR && !blur_supported(k, 0.0)) return ROD_ERR_UNSUPPORTED;
+    if (op == ROD_OP_LOWRES) {
+        int rc = ensure_lowres_tables(plan, factor);
+        if (rc != ROD_OK) return rc;
+    }
+    if (plan->d_stage_src == nullptr) {
+        ROD_CUDA(cudaMalloc((void**)&plan->d_stage_src, plan->src_extent + 64));
+        ROD_CUDA(cudaMalloc((void**)&plan->d_stage_dst, plan->dst_extent + 64));
+        for (auto& s : plan->streams) ROD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    }
+    const bool compat = (op == ROD_OP_NOISE && noise_host != nullptr);
+    if (compat && plan->d_stage_noise == nullptr)
+        ROD_CUDA(cudaMalloc((void**)&plan->d_stage_noise, plan->payload_bytes * sizeof(float) + 64));
+
+    // chunking: ~32 MiB of payload per chunk when the layout allows per-chunk byte ranges
+    const int n = plan->n_images;
+    std::vector<int> cuts{0};
+    if (plan->monotonic && n > 1) {
+        uint64_t acc = 0;
+        for (int i = 0; i < n; ++i) {
+            acc += 3ull * plan->descs[i].height * plan->descs[i].width;
+            if (acc >= (32ull << 20) && i + 1 < n) { cuts.push_back(i + 1); acc = 0; }
+        }
+    }
+    cuts.push_back(n);
+    bool dst_packed = plan->monotonic;
+    for (int i = 0; i < n && dst_packed; ++i) {
+        const rod_image_desc& d = plan->descs[i];
+        if (d.dst_pitch != 3ll * d.width) dst_packed = false;
+        if (i + 1 < n && plan->descs[i + 1].dst_offset != d.dst_offset + 3ull * d.width * d.height) dst_packed = false;
+    }
+    int rc = ROD_OK;
+    for (size_t c = 0; c + 1 < cuts.size() && rc == ROD_OK; ++c) {
+        const int lo = cuts[c], hi = cuts[c + 1];
+        cudaStream_t st = plan->streams[c % 3];
+        const rod_image_desc& a = plan->descs[lo];
+        const rod_image_desc& b = plan->descs[hi - 1];
+        const uint64_t s_lo = a.src_offset, s_hi = b.src_offset + (uint64_t)(b.height - 1) * b.src_pitch + 3ull * b.width;
+        const uint64_t d_lo = a.dst_offset, d_hi = b.dst_offset + (uint64_t)(b.height - 1) * b.dst_pitch + 3ull * b.width;
+        ROD_CUDA(cudaMemcpyAsync(plan->d_stage_src + s_lo, src_host + s_lo, s_hi - s_lo, cudaMemcpyHostToDevice, st));
+        if (compat) {
+            const uint64_t e_lo = plan->h_images[lo].elem_base;
+            const uint64_t e_hi = plan->h_images[hi - 1].elem_base + 3ull * b.height * b.width;
+            ROD_CUDA(cudaMemcpyAsync(plan->d_stage_noise + e_lo, noise_host + e_lo, (e_hi - e_lo) * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+        }
+        rc = run_op(plan, op, plan->d_stage_src, plan->d_stage_dst, compat ? plan->d_stage_noise : nullptr, sigma, k,
+                    factor, seed, first_image_index, offset, nullptr, st, lo, hi);
+        if (rc != ROD_OK) break;
+        if (dst_packed) {
+            ROD_CUDA(cudaMemcpyAsync(dst_host + d_lo, plan->d_stage_dst + d_lo, d_hi - d_lo, cudaMemcpyDeviceToHost, st));
+        } else {  // never write the caller's pitch padding / gaps: one 2-D copy per image
+            for (int i = lo; i < hi; ++i) {
+                const rod_image_desc& d = plan->descs[i];
+                ROD_CUDA(cudaMemcpy2DAsync(dst_host + d.dst_offset, (size_t)d.dst_pitch, plan->d_stage_dst + d.dst_offset,
+                                           (size_t)d.dst_pitch, 3ull * d.width, (size_t)d.height,
+                                           cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    for (auto& s : plan->streams) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess && rc == ROD_OK) rc = cuda_fail(e);
+    }
+    return rc;
+}

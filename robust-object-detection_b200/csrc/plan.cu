@@ -1,0 +1,204 @@
+// plan.cu -- batch plans: descriptor upload, tile lists, resize tables (host side of librod_b200.so).
+#include <map>
+#include <new>
+
+#include "rod_internal.h"
+#include "rod_tables.h"
+
+namespace rod {
+
+thread_local int g_last_cuda_error = 0;
+
+int grid_for(const rod_plan* plan, int n_tiles, int ctas_per_sm) {
+    long long cap = (long long)plan->sm_count * ctas_per_sm;
+    return (int)(n_tiles < cap ? n_tiles : cap);
+}
+
+template <typename T>
+static int upload(const std::vector<T>& v, T** dptr) {
+    *dptr = nullptr;
+    if (v.empty()) return ROD_OK;
+    ROD_CUDA(cudaMalloc((void**)dptr, v.size() * sizeof(T)));
+    ROD_CUDA(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return ROD_OK;
+}
+
+int ensure_lowres_tables(rod_plan* plan, double factor) {
+    if (plan->d_shapes != nullptr && plan->lowres_factor == factor) return ROD_OK;
+    if (!(factor > 0.0) || factor > 1.0) return ROD_ERR_UNSUPPORTED;
+    std::vector<uint32_t> blob;
+    std::vector<DevShape> shapes(plan->shapes.size());
+    bool all_identity = true;
+    int max_rows = 1, max_cols = 1;
+    for (size_t s = 0; s < plan->shapes.size(); ++s) {
+        const int h = plan->shapes[s].h, w = plan->shapes[s].w;
+        if (!build_lowres_shape(h, w, factor, kMaxAreaTaps, blob, &shapes[s])) return ROD_ERR_UNSUPPORTED;
+        const DevShape& sh = shapes[s];
+        if (sh.lin_identity) continue;
+        all_identity = false;
+        // worst-case low-res footprint of one output tile
+        const int32_t* lx = (const int32_t*)(blob.data() + sh.lx_s0);
+        const uint32_t* ly = blob.data() + sh.ly_s;
+        for (int y0 = 0; y0 < h; y0 += kLowresTH) {
+            const int y1 = std::min(h, y0 + kLowresTH) - 1;
+            max_rows = std::max(max_rows, (int)(ly[y1] >> 16) - (int)(ly[y0] & 0xFFFF) + 1);
+        }
+        for (int x0 = 0; x0 < w; x0 += kLowresTW) {
+            const int x1 = std::min(w, x0 + kLowresTW) - 1;
+            max_cols = std::max(max_cols, std::min(lx[x1] + 1, sh.nw - 1) - lx[x0] + 1);
+        }
+    }
+    if (blob.empty()) blob.push_back(0);
+    if (plan->d_shapes) { cudaFree(plan->d_shapes); plan->d_shapes = nullptr; }
+    if (plan->d_tab) { cudaFree(plan->d_tab); plan->d_tab = nullptr; }
+    int rc = upload(shapes, &plan->d_shapes);
+    if (rc != ROD_OK) return rc;
+    rc = upload(blob, &plan->d_tab);
+    if (rc != ROD_OK) return rc;
+    plan->lowres_factor = factor;
+    plan->lowres_all_identity = all_identity;
+    plan->lowres_half_rows = max_rows;
+    plan->lowres_half_cols = max_cols;
+    return ROD_OK;
+}
+
+int ensure_letterbox_tables(rod_plan* plan, int out_h, int out_w) {
+    if (plan->d_lb != nullptr && plan->lb_out_h == out_h && plan->lb_out_w == out_w) return ROD_OK;
+    if (out_h < 1 || out_w < 1) return ROD_ERR_INVALID_ARG;
+    std::vector<uint32_t> blob;
+    std::vector<DevLetterbox> lbs(plan->shapes.size());
+    for (size_t s = 0; s < plan->shapes.size(); ++s) {
+        DevLetterbox g;
+        memset(&g, 0, sizeof(g));
+        g.h = plan->shapes[s].h; g.w = plan->shapes[s].w;
+        letterbox_geometry(g.h, g.w, out_h, out_w, &g.new_h, &g.new_w, &g.top, &g.left);
+        if (g.new_h < 1 || g.new_w < 1 || g.h > 65535 || g.w > 65535) return ROD_ERR_UNSUPPORTED;
+        g.identity = (g.new_h == g.h && g.new_w == g.w);
+        g.area2 = (!g.identity && g.h == 2 * g.new_h && g.w == 2 * g.new_w);
+        if (!g.identity && !g.area2) {
+            LinearAxis lx = build_linear_axis(g.w, g.new_w, true);
+            LinearAxis ly = build_linear_axis(g.h, g.new_h, false);
+            std::vector<uint32_t> ys(g.new_h);
+            for (int y = 0; y < g.new_h; ++y) ys[y] = (uint32_t)ly.s0[y] | ((uint32_t)ly.s1[y] << 16);
+            g.lx_s0 = blob_push(blob, lx.s0);
+            g.lx_a = blob_push(blob, lx.coef);
+            g.ly_s = blob_push(blob, ys);
+            g.ly_b = blob_push(blob, ly.coef);
+        }
+        lbs[s] = g;
+    }
+    if (blob.empty()) blob.push_back(0);
+    std::vector<Tile> tiles;
+    for (int i = 0; i < plan->n_images; ++i)
+        for (int y = 0; y < out_h; y += kLbTH)
+            for (int x = 0; x < out_w; x += kLbTW) tiles.push_back(Tile{i, y, x, 0});
+    if (plan->d_lb) { cudaFree(plan->d_lb); plan->d_lb = nullptr; }
+    if (plan->d_lb_tab) { cudaFree(plan->d_lb_tab); plan->d_lb_tab = nullptr; }
+    if (plan->d_lb_tiles) { cudaFree(plan->d_lb_tiles); plan->d_lb_tiles = nullptr; }
+    int rc = upload(lbs, &plan->d_lb);
+    if (rc != ROD_OK) return rc;
+    rc = upload(blob, &plan->d_lb_tab);
+    if (rc != ROD_OK) return rc;
+    rc = upload(tiles, &plan->d_lb_tiles);
+    if (rc != ROD_OK) return rc;
+    plan->n_lb_tiles = (int)tiles.size();
+    plan->lb_out_h = out_h;
+    plan->lb_out_w = out_w;
+    return ROD_OK;
+}
+
+}  // namespace rod
+
+using namespace rod;
+
+extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_plan** out_plan) {
+    if (out_plan == nullptr) return ROD_ERR_INVALID_ARG;
+    *out_plan = nullptr;
+    if (images == nullptr || n_images < 1) return ROD_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return ROD_ERR_NO_DEVICE;
+    }
+    rod_plan* plan = new (std::nothrow) rod_plan();
+    if (plan == nullptr) return ROD_ERR_OOM;
+    cudaError_t e = cudaGetDevice(&plan->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device);
+    if (e != cudaSuccess) { delete plan; return cuda_fail(e); }
+    plan->n_images = n_images;
+    plan->descs.assign(images, images + n_images);
+    plan->h_images.resize(n_images);
+    std::map<std::pair<int, int>, int> shape_ids;
+    uint64_t elem = 0;
+    for (int i = 0; i < n_images; ++i) {
+        const rod_image_desc& d = images[i];
+        if (d.height < 1 || d.width < 1 || d.width > 65535 || d.height > 65535 || d.src_pitch < 3LL * d.width ||
+            d.dst_pitch < 3LL * d.width || (uint64_t)d.height * d.width * 3 > 0x7FFFFFFFull) {
+            delete plan;
+            return ROD_ERR_INVALID_ARG;
+        }
+        DevImage& im = plan->h_images[i];
+        im.src_off = d.src_offset; im.dst_off = d.dst_offset;
+        im.src_pitch = d.src_pitch; im.dst_pitch = d.dst_pitch;
+        im.h = d.height; im.w = d.width;
+        im.elem_base = elem;
+        im.contiguous = (d.src_pitch == 3LL * d.width && d.dst_pitch == 3LL * d.width) ? 1 : 0;
+        elem += (uint64_t)d.height * d.width * 3;
+        auto key = std::make_pair(d.height, d.width);
+        auto it = shape_ids.find(key);
+        if (it == shape_ids.end()) {
+            it = shape_ids.emplace(key, (int)plan->shapes.size()).first;
+            plan->shapes.push_back(HostShape{d.height, d.width});
+        }
+        im.shape_id = it->second;
+        plan->max_w = std::max(plan->max_w, d.width);
+        plan->all_contiguous = plan->all_contiguous && im.contiguous;
+        plan->src_extent = std::max<uint64_t>(plan->src_extent, d.src_offset + (uint64_t)(d.height - 1) * d.src_pitch + 3ull * d.width);
+        plan->dst_extent = std::max<uint64_t>(plan->dst_extent, d.dst_offset + (uint64_t)(d.height - 1) * d.dst_pitch + 3ull * d.width);
+    }
+    plan->payload_bytes = elem;
+    std::vector<Tile> nt, bt, lt;
+    build_noise_tiles(plan->h_images, kNoiseSpan, nt);
+    build_blur_tiles(plan->h_images, kBlurRowsPerTile, bt);
+    build_grid_tiles(plan->h_images, kLowresTH, kLowresTW, lt);
+    auto starts = [&](const std::vector<Tile>& tl, std::vector<int>& st) {
+        st.assign(n_images + 1, (int)tl.size());
+        for (int t = (int)tl.size() - 1; t >= 0; --t) st[tl[t].img] = t;
+        for (int i = n_images - 1; i >= 0; --i) st[i] = std::min(st[i], st[i + 1]);
+    };
+    starts(nt, plan->noise_tile_start);
+    starts(bt, plan->blur_tile_start);
+    starts(lt, plan->lowres_tile_start);
+    for (int i = 1; i < n_images; ++i) {
+        const rod_image_desc& a = images[i - 1];
+        const rod_image_desc& b = images[i];
+        if (b.src_offset < a.src_offset + (uint64_t)a.height * a.src_pitch - (a.src_pitch - 3ull * a.width) ||
+            b.dst_offset < a.dst_offset + (uint64_t)a.height * a.dst_pitch - (a.dst_pitch - 3ull * a.width))
+            plan->monotonic = false;
+    }
+    plan->n_noise_tiles = (int)nt.size();
+    plan->n_blur_tiles = (int)bt.size();
+    plan->n_lowres_tiles = (int)lt.size();
+    int rc = upload(plan->h_images, &plan->d_images);
+    if (rc == ROD_OK) rc = upload(nt, &plan->d_noise_tiles);
+    if (rc == ROD_OK) rc = upload(bt, &plan->d_blur_tiles);
+    if (rc == ROD_OK) rc = upload(lt, &plan->d_lowres_tiles);
+    if (rc != ROD_OK) { rod_plan_destroy(plan); return rc; }
+    *out_plan = plan;
+    return ROD_OK;
+}
+
+extern "C" void rod_plan_destroy(rod_plan* plan) {
+    if (plan == nullptr) return;
+    void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_shapes,
+                    plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
+                    plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (cudaStream_t s : plan->streams)
+        if (s) cudaStreamDestroy(s);
+    delete plan;
+}
+
+extern "C" int rod_plan_num_images(const rod_plan* plan) { return plan ? plan->n_images : 0; }
+extern "C" uint64_t rod_plan_payload_bytes(const rod_plan* plan) { return plan ? plan->payload_bytes : 0; }

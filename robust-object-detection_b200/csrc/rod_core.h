@@ -1,0 +1,271 @@
+// rod_core.h -- arithmetic of the corruption path, written once for device and host.
+//
+// Every function here is a pure per-element / per-chunk routine with no thread
+// cooperation, so the very same code is (a) inlined into the sm_100a kernels and
+// (b) compiled by g++ into tests/emu (a sequential harness that replays the kernels'
+// tile loops on the CPU against the oracle, because the build container has no GPU).
+// The harness is test infrastructure; the product never runs these on the host.
+//
+// Arithmetic specs: SURVEY.md section 8a (a1, a3, a4, a5), i.e. NumPy 2.3.5
+// `astype/clip` semantics and OpenCV 4.13.0 filter2D / resize(INTER_AREA) /
+// resize(INTER_LINEAR, 8U) as called from scripts/augmentations.py:30-45.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define ROD_HD __host__ __device__ __forceinline__
+#else
+#define ROD_HD inline
+#endif
+
+namespace rod {
+
+// ---------------------------------------------------------------------------------
+// Device-resident descriptors (built by plan.cu)
+// ---------------------------------------------------------------------------------
+struct DevImage {
+    uint64_t src_off, dst_off;  // bytes from the src / dst base pointers
+    int64_t src_pitch, dst_pitch;
+    uint64_t elem_base;         // packed element index of this image's first byte (noise field offset)
+    int32_t h, w;
+    int32_t shape_id;           // index into the DevShape table (lowres / letterbox)
+    int32_t contiguous;         // 1 when both pitches equal 3*w
+};
+
+// One work item of a kernel.  Meaning of a/b/c depends on the op:
+//   noise : a = first element (flat index inside the image or row), b = element count, c = row (or -1: flat)
+//   blur  : a = first row, b = row count
+//   lowres: a = first output row, b = first output column (pixels)
+struct Tile {
+    int32_t img, a, b, c;
+};
+
+enum AreaMode { AREA_GENERAL = 0, AREA_FAST2 = 1, AREA_FASTN = 2, AREA_IDENTITY = 3 };
+
+// Resize tables of one (src h, src w) -> (nh, nw) -> (h, w) lowres round trip, or of
+// one letterbox geometry.  Offsets are in 32-bit words into the plan's table blob.
+struct DevShape {
+    int32_t h, w, nh, nw;       // full size, low-res size
+    int32_t area_mode;
+    int32_t ix, iy;             // integer scales (AREA_FASTN)
+    int32_t xt, yt;             // taps per destination (AREA_GENERAL), row stride of the alpha tables
+    uint32_t ax_first, ax_alpha;  // int32 first[nw]; float alpha[nw*xt] (unused taps are 0 with index clamped)
+    uint32_t ay_first, ay_alpha;  // int32 first[nh]; float alpha[nh*yt]
+    uint32_t ax_count, ay_count;  // int32 count[nw], count[nh]
+    uint32_t lx_s0, lx_a;       // int32 s0[w]; uint32 (a0 | a1 << 16)[w]   (low-res -> full, x axis)
+    uint32_t ly_s, ly_b;        // uint32 (s0 | s1 << 16)[h]; uint32 (b0 | b1 << 16)[h]
+    float inv_area;             // float(1 / (ix*iy))
+    int32_t lin_identity;       // 1 when (nh, nw) == (h, w): the INTER_LINEAR step is a copy
+};
+
+// ---------------------------------------------------------------------------------
+// float helpers: never contracted into FMA (OpenCV's resizeArea_ uses separate mul/add)
+// ---------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+ROD_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+ROD_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+ROD_HD float frint(float a) { return rintf(a); }
+ROD_HD float fadd_rz(float a, float b) { return __fadd_rz(a, b); }
+ROD_HD uint32_t fbits(float a) { return __float_as_uint(a); }
+ROD_HD float bitsf(uint32_t a) { return __uint_as_float(a); }
+#else
+ROD_HD float fmul(float a, float b) { volatile float r = a * b; return r; }
+ROD_HD float fadd(float a, float b) { volatile float r = a + b; return r; }
+ROD_HD float frint(float a) { return nearbyintf(a); }
+// host stand-in for add.rz.f32, exact for the only use (0 <= a <= 255, b = 2^23)
+ROD_HD float fadd_rz(float a, float b) { return (float)floor((double)a + (double)b); }
+ROD_HD uint32_t fbits(float a) { uint32_t u; memcpy(&u, &a, 4); return u; }
+ROD_HD float bitsf(uint32_t a) { float f; memcpy(&f, &a, 4); return f; }
+#endif
+
+// cv::borderInterpolate(BORDER_REFLECT_101), periodic form (valid for any reach, n >= 1).
+ROD_HD int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    int period = 2 * (n - 1);
+    int m = i % period;
+    if (m < 0) m += period;
+    return m < n ? m : period - m;
+}
+
+// ---------------------------------------------------------------------------------
+// a1: noise.  out = uint8(trunc(clamp(float(v) + noise, 0, 255)))  (augmentations.py:32-33)
+// ---------------------------------------------------------------------------------
+// vf is the pixel already converted to float (exact).
+ROD_HD uint32_t noise_px(float vf, float nz) {
+    float s = fadd(vf, nz);  // one RN add
+    s = fmaxf(s, 0.0f);
+    s = fminf(s, 255.0f);
+    // truncation == numpy astype(uint8) on [0,255]: 2^23 + s rounded toward zero keeps floor(s) in the low byte
+    return fbits(fadd_rz(s, 8388608.0f)) & 0xFFu;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter c[4], key k[2].
+ROD_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+ROD_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t r[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+
+// Four N(0,1) samples from one Philox block: (r0,r1) and (r2,r3) are Box-Muller pairs.
+//   radius uniform  ua = (r_a + 0.5) * 2^-32            in (0,1)   (full 32 bits: tail to 6.7 sigma)
+//   angle           th = pi * (((r_b >> 9) + 0.5) * 2^-22 - 1)      in (-pi, pi), 23 bits
+//   z0 = sqrt(-2 ln ua) * cos(th),  z1 = sqrt(-2 ln ua) * sin(th)
+// Integer->float conversions use the 2^23 mantissa trick (FADD) instead of I2F.
+ROD_HD void boxmuller4(const uint32_t r[4], float z[4]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        uint32_t ra = r[2 * p], rb = r[2 * p + 1];
+        float na = bitsf(0x4B000000u | (ra >> 9)) - 8388608.0f;   // exact (ra >> 9)
+        float la = bitsf(0x4B000000u | (ra & 511u)) - 8388608.0f; // exact (ra & 511)
+        float ua = fmaf(la, 2.3283064365386963e-10f, fmaf(na, 1.1920928955078125e-07f, 1.1641532182693481e-10f));
+        ua = fminf(ua, 0.99999994f);
+        float nb = bitsf(0x4B000000u | (rb >> 9)) - 8388608.0f;
+        float sb = fmaf(nb, 2.384185791015625e-07f, 1.1920928955078125e-07f - 1.0f);
+        float l2 = __log2f(ua);
+        float rad;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * l2));
+        float th = 3.14159265358979f * sb;
+        z[2 * p] = rad * __cosf(th);
+        z[2 * p + 1] = rad * __sinf(th);
+    }
+#else
+    for (int p = 0; p < 2; ++p) {
+        double ua = ((double)r[2 * p] + 0.5) * 2.3283064365386963e-10;
+        double sb = ((double)(r[2 * p + 1] >> 9) + 0.5) * 2.384185791015625e-07 - 1.0;
+        double rad = sqrt(-2.0 * log(ua));
+        z[2 * p] = (float)(rad * cos(3.141592653589793 * sb));
+        z[2 * p + 1] = (float)(rad * sin(3.141592653589793 * sb));
+    }
+#endif
+}
+
+// ---------------------------------------------------------------------------------
+// a3: horizontal k-tap box blur on an interleaved 3-channel row that has been staged
+// (with its reflected halo) in a byte buffer.  `row` points at the byte of pixel 0.
+// ---------------------------------------------------------------------------------
+// Generic odd k (slow path): one output byte.
+ROD_HD uint32_t blur_byte_generic(const uint8_t* row, int i, int k) {
+    int r = k >> 1;
+    int s = 0;
+    for (int j = -r; j <= r; ++j) s += row[i + 3 * j];
+    return (uint32_t)((2 * s + k) / (2 * k));
+}
+
+// Byte `p` (0..47) of a 12-word window.
+ROD_HD uint32_t win_byte(const uint32_t* w, int p) { return (w[p >> 2] >> (8 * (p & 3))) & 0xFFu; }
+
+// k = 9 fast path: 16 consecutive outputs from a 48-byte window w[0..11] that holds
+// input bytes [-16, 32) relative to the first output byte.  Uses 3 interleaved running
+// prefix sums (one per channel phase): C[p] = C[p-3] + B[p];  S[n] = C[n+12] - C[n-15].
+// out = (S + 4) / 9 == ((S + 4) * 7282) >> 16 for S <= 2295.
+ROD_HD void blur9_chunk16(const uint32_t* w, uint32_t out[4]) {
+    // window byte index q = p + 16, p in [-15, 27]
+    uint32_t C[43];  // C[t] for p = t - 15
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int t = 0; t < 43; ++t) {
+        int q = t + 1;  // p + 16
+        uint32_t prev = (t >= 3) ? C[t - 3] : 0u;
+        // the three chain heads p = -15,-14,-13 carry B[p] = 0 contribution: start sums at p >= -12
+        if (t < 3) { C[t] = 0u; continue; }
+        C[t] = __dp4a(w[q >> 2], 1u << (8 * (q & 3)), prev);
+    }
+#else
+    for (int t = 0; t < 43; ++t) {
+        int q = t + 1;
+        if (t < 3) { C[t] = 0u; continue; }
+        C[t] = C[t - 3] + win_byte(w, q);
+    }
+#endif
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int n = 4 * g + b;
+            uint32_t s = C[n + 27] - C[n];  // C[p=n+12] - C[p=n-15]
+            uint32_t qv = (s * 7282u + 29128u) >> 16;
+            o |= qv << (8 * b);
+        }
+        out[g] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// a4: INTER_AREA, one low-res value (channel c of low-res pixel (dy, dx)).
+// src points at pixel (0,0) of the full-res image, pitch in bytes.
+// ---------------------------------------------------------------------------------
+ROD_HD uint32_t area_value(const uint8_t* src, int64_t pitch, const DevShape& sh, const uint32_t* tab, int dy,
+                           int dx, int c) {
+    if (sh.area_mode == AREA_FAST2) {
+        const uint8_t* p = src + (int64_t)(2 * dy) * pitch + (2 * dx) * 3 + c;
+        return ((uint32_t)p[0] + p[3] + p[pitch] + p[pitch + 3] + 2u) >> 2;
+    }
+    if (sh.area_mode == AREA_IDENTITY) {
+        return src[(int64_t)dy * pitch + dx * 3 + c];
+    }
+    if (sh.area_mode == AREA_FASTN) {
+        uint32_t s = 0;
+        for (int yy = 0; yy < sh.iy; ++yy) {
+            const uint8_t* p = src + (int64_t)(dy * sh.iy + yy) * pitch + (dx * sh.ix) * 3 + c;
+            for (int xx = 0; xx < sh.ix; ++xx) s += p[3 * xx];
+        }
+        float r = frint(fmul((float)s, sh.inv_area));
+        r = r < 0.f ? 0.f : (r > 255.f ? 255.f : r);
+        return (uint32_t)(int)r;
+    }
+    const int32_t* xfirst = (const int32_t*)(tab + sh.ax_first);
+    const int32_t* xcount = (const int32_t*)(tab + sh.ax_count);
+    const float* xalpha = (const float*)(tab + sh.ax_alpha) + dx * sh.xt;
+    const int32_t* yfirst = (const int32_t*)(tab + sh.ay_first);
+    const int32_t* ycount = (const int32_t*)(tab + sh.ay_count);
+    const float* yalpha = (const float*)(tab + sh.ay_alpha) + dy * sh.yt;
+    int sx0 = xfirst[dx], nx = xcount[dx];
+    int sy0 = yfirst[dy], ny = ycount[dy];
+    float sum = 0.f;
+    for (int ty = 0; ty < ny; ++ty) {
+        const uint8_t* p = src + (int64_t)(sy0 + ty) * pitch + sx0 * 3 + c;
+        float buf = 0.f;
+        for (int tx = 0; tx < nx; ++tx) buf = fadd(buf, fmul((float)p[3 * tx], xalpha[tx]));
+        float prod = fmul(yalpha[ty], buf);
+        sum = (ty == 0) ? prod : fadd(sum, prod);
+    }
+    float r = frint(sum);
+    r = r < 0.f ? 0.f : (r > 255.f ? 255.f : r);
+    return (uint32_t)(int)r;
+}
+
+// ---------------------------------------------------------------------------------
+// a5: INTER_LINEAR 8U.  Horizontal stage: (S[s0]*a0 + S[s1]*a1) >> 4 (fits 16 bits).
+// ---------------------------------------------------------------------------------
+ROD_HD uint32_t linear_h4(uint32_t s0v, uint32_t s1v, uint32_t a_packed) {
+    return (s0v * (a_packed & 0xFFFFu) + s1v * (a_packed >> 16)) >> 4;
+}
+// Vertical stage + pack: (((b0*h0) >> 16) + ((b1*h1) >> 16) + 2) >> 2.
+ROD_HD uint32_t linear_v(uint32_t h0, uint32_t h1, uint32_t b_packed) {
+    return ((((b_packed & 0xFFFFu) * h0) >> 16) + (((b_packed >> 16) * h1) >> 16) + 2u) >> 2;
+}
+
+// Detector-input normalisation: half(float(u8) / 255.f) is done with __float2half_rn on
+// device; the host harness does not cover it (tests compare against numpy float16).
+
+}  // namespace rod

@@ -1,0 +1,109 @@
+// rod_internal.h -- host-side plan object shared by the translation units of librod_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/rod_b200.h"
+#include "rod_core.h"
+
+namespace rod {
+
+// Tile geometry shared by the host tile builders and the kernels.
+constexpr int kNoiseSpan = 16384;  // elements (bytes) per noise work item
+constexpr int kBlurRowsPerTile = 8;  // one row per warp, 8 warps per CTA
+constexpr int kLowresTH = 32;      // output rows per lowres tile
+constexpr int kLowresTW = 128;     // output pixels per lowres tile
+constexpr int kLbTH = 16;          // letterbox output tile
+constexpr int kLbTW = 64;
+constexpr int kMaxAreaTaps = 8;
+
+struct HostShape {
+    int h, w;
+};
+
+// Letterbox geometry + tables of one source shape.
+struct DevLetterbox {
+    int32_t h, w, new_h, new_w, top, left;
+    int32_t area2;             // 1: exact 2x2 decimation (cv::resize rewrites INTER_LINEAR to INTER_AREA)
+    int32_t identity;          // 1: new size == source size
+    uint32_t lx_s0, lx_a;      // int32 s0[new_w], uint32 (a0 | a1<<16)[new_w]
+    uint32_t ly_s, ly_b;       // uint32 (s0 | s1<<16)[new_h], uint32 (b0 | b1<<16)[new_h]
+};
+
+}  // namespace rod
+
+struct rod_plan {
+    int device = 0;
+    int n_images = 0;
+    int sm_count = 148;
+    std::vector<rod_image_desc> descs;
+    std::vector<rod::DevImage> h_images;
+    std::vector<rod::HostShape> shapes;  // distinct (h, w)
+    uint64_t payload_bytes = 0;
+    int max_w = 0;
+    bool all_contiguous = true;
+    uint64_t src_extent = 0, dst_extent = 0;  // bytes spanned by the descriptors in src / dst
+
+    rod::DevImage* d_images = nullptr;
+    rod::Tile* d_noise_tiles = nullptr;
+    rod::Tile* d_blur_tiles = nullptr;
+    rod::Tile* d_lowres_tiles = nullptr;
+    int n_noise_tiles = 0, n_blur_tiles = 0, n_lowres_tiles = 0;
+    // tiles of image i are [start[i], start[i+1]) in each list (lists are in image order)
+    std::vector<int> noise_tile_start, blur_tile_start, lowres_tile_start;
+    bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
+
+    // lowres tables, rebuilt when the factor changes
+    double lowres_factor = -1.0;
+    rod::DevShape* d_shapes = nullptr;
+    uint32_t* d_tab = nullptr;
+    bool lowres_all_identity = false;
+    int lowres_half_rows = 0, lowres_half_cols = 0;  // worst-case low-res rows / cols one tile touches
+
+    // letterbox tables, rebuilt when (out_h, out_w) changes
+    int lb_out_h = 0, lb_out_w = 0;
+    rod::DevLetterbox* d_lb = nullptr;
+    uint32_t* d_lb_tab = nullptr;
+    rod::Tile* d_lb_tiles = nullptr;
+    int n_lb_tiles = 0;
+    uint8_t* d_scratch = nullptr;  // corrupted full-res images for the letterbox path
+    uint64_t scratch_bytes = 0;
+
+    // host-buffer (e2e) staging
+    uint8_t* d_stage_src = nullptr;
+    uint8_t* d_stage_dst = nullptr;
+    float* d_stage_noise = nullptr;
+    uint8_t* d_stage_ops = nullptr;
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+};
+
+namespace rod {
+extern thread_local int g_last_cuda_error;
+inline int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return e == cudaErrorMemoryAllocation ? ROD_ERR_OOM : ROD_ERR_CUDA;
+}
+#define ROD_CUDA(call)                                  \
+    do {                                                \
+        cudaError_t _e = (call);                        \
+        if (_e != cudaSuccess) return rod::cuda_fail(_e); \
+    } while (0)
+
+int grid_for(const rod_plan* plan, int n_tiles, int ctas_per_sm);
+
+// kernel launchers (one per .cu)
+int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* dst, const float* noise,
+                 float* field_out, float sigma, uint64_t seed, uint64_t first_image, uint32_t offset,
+                 const uint8_t* opcodes, int my_op, cudaStream_t stream, int img_lo, int img_hi);
+int launch_blur(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, const uint8_t* opcodes,
+                cudaStream_t stream, int img_lo, int img_hi);
+int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
+                  cudaStream_t stream, int img_lo, int img_hi);
+int launch_letterbox(const rod_plan* plan, const uint8_t* img, void* out_f16, int pad_value, cudaStream_t stream);
+
+int ensure_lowres_tables(rod_plan* plan, double factor);
+int ensure_letterbox_tables(rod_plan* plan, int out_h, int out_w);
+
+enum NoiseMode { NOISE_COMPAT = 0, NOISE_PHILOX = 1, NOISE_COPY = 2, NOISE_FIELD = 3 };
+}  // namespace rod

@@ -1,0 +1,194 @@
+// rod_tables.h -- host-side (plain C++) construction of the resize tables and tile lists.
+//
+// Restates, in double/float arithmetic identical to OpenCV 4.13.0's resize.cpp, the
+// coefficient tables of cv::resize(INTER_AREA) (computeResizeAreaTab) and of the 8-bit
+// INTER_LINEAR path (fixed point, INTER_RESIZE_COEF_BITS = 11) that
+// scripts/augmentations.py:44-45 invokes.  Used by plan.cu (uploaded to the GPU) and by
+// the CPU emulation harness in tests/emu (no CUDA needed).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "rod_core.h"
+
+namespace rod {
+
+struct AreaAxis {
+    std::vector<int32_t> first, count;
+    std::vector<float> alpha;  // [dsize * taps]
+    int taps = 1;
+};
+
+// computeResizeAreaTab: taps of destination d are consecutive source indices.
+inline AreaAxis build_area_axis(int ssize, int dsize) {
+    AreaAxis ax;
+    ax.first.assign(dsize, 0);
+    ax.count.assign(dsize, 0);
+    std::vector<std::vector<float>> rows(dsize);
+    double scale = (double)ssize / (double)dsize;
+    for (int d = 0; d < dsize; ++d) {
+        double f1 = d * scale;
+        double f2 = f1 + scale;
+        double cell = std::min(scale, ssize - f1);
+        int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+        s2 = std::min(s2, ssize - 1);
+        s1 = std::min(s1, s2);
+        bool have = false;
+        auto emit = [&](int s, float a) {
+            if (!have) { ax.first[d] = s; have = true; }
+            rows[d].push_back(a);
+        };
+        if (s1 - f1 > 1e-3) emit(s1 - 1, (float)((s1 - f1) / cell));
+        for (int s = s1; s < s2; ++s) emit(s, (float)(1.0 / cell));
+        if (f2 - s2 > 1e-3) emit(s2, (float)(std::min(std::min(f2 - s2, 1.0), cell) / cell));
+        ax.count[d] = (int)rows[d].size();
+        ax.taps = std::max(ax.taps, ax.count[d]);
+    }
+    ax.alpha.assign((size_t)dsize * ax.taps, 0.0f);
+    for (int d = 0; d < dsize; ++d)
+        for (int t = 0; t < ax.count[d]; ++t) ax.alpha[(size_t)d * ax.taps + t] = rows[d][t];
+    return ax;
+}
+
+struct LinearAxis {
+    std::vector<int32_t> s0, s1;     // clipped source indices
+    std::vector<uint32_t> coef;      // a0 | a1 << 16   (11-bit fixed point)
+};
+
+// 8-bit INTER_LINEAR tables.  clamp_x = true: the x axis (index and fraction clamped at both
+// ends); false: the y axis (fraction kept, only the two row indices are clipped).
+inline LinearAxis build_linear_axis(int ssize, int dsize, bool clamp_x) {
+    LinearAxis ax;
+    ax.s0.resize(dsize);
+    ax.s1.resize(dsize);
+    ax.coef.resize(dsize);
+    double scale = 1.0 / ((double)dsize / (double)ssize);
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (clamp_x) {
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        }
+        volatile float c0 = 1.f - f;
+        volatile float m0 = c0 * 2048.f, m1 = f * 2048.f;
+        int a0 = (int)lrintf(m0), a1 = (int)lrintf(m1);
+        ax.s0[d] = std::min(std::max(s, 0), ssize - 1);
+        ax.s1[d] = std::min(std::max(s + 1, 0), ssize - 1);
+        ax.coef[d] = (uint32_t)(a0 & 0xFFFF) | ((uint32_t)(a1 & 0xFFFF) << 16);
+    }
+    return ax;
+}
+
+inline void lowres_small_size(int h, int w, double factor, int* nh, int* nw) {
+    // augmentations.py:43: max(1, int(w * factor)) -- Python float multiply then truncation
+    *nw = std::max(1, (int)((double)w * factor));
+    *nh = std::max(1, (int)((double)h * factor));
+}
+
+// Append a 32-bit-word array to the blob and return its word offset.
+template <typename T>
+inline uint32_t blob_push(std::vector<uint32_t>& blob, const std::vector<T>& v) {
+    static_assert(sizeof(T) == 4, "table entries are 32-bit");
+    uint32_t off = (uint32_t)blob.size();
+    blob.resize(blob.size() + v.size());
+    if (!v.empty()) memcpy(blob.data() + off, v.data(), v.size() * 4);
+    while (blob.size() % 4) blob.push_back(0);  // keep every table 16-byte aligned
+    return off;
+}
+
+// Tables of the lowres round trip for one (h, w).  Returns false if unsupported (too many taps).
+inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::vector<uint32_t>& blob,
+                               DevShape* out) {
+    DevShape sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.h = h; sh.w = w;
+    lowres_small_size(h, w, factor, &sh.nh, &sh.nw);
+    if (sh.nh > h || sh.nw > w) return false;
+    sh.lin_identity = (sh.nh == h && sh.nw == w) ? 1 : 0;
+    sh.xt = sh.yt = 1;
+    sh.ix = sh.iy = 1;
+    sh.inv_area = 1.0f;
+    if (sh.lin_identity) {
+        sh.area_mode = AREA_IDENTITY;
+    } else if (w == 2 * sh.nw && h == 2 * sh.nh) {
+        sh.area_mode = AREA_FAST2;
+        sh.ix = sh.iy = 2;
+    } else if (w % sh.nw == 0 && h % sh.nh == 0) {
+        sh.area_mode = AREA_FASTN;
+        sh.ix = w / sh.nw;
+        sh.iy = h / sh.nh;
+        sh.inv_area = (float)(1.0 / (sh.ix * sh.iy));
+    } else {
+        sh.area_mode = AREA_GENERAL;
+        AreaAxis ax = build_area_axis(w, sh.nw);
+        AreaAxis ay = build_area_axis(h, sh.nh);
+        if (ax.taps > max_taps || ay.taps > max_taps) return false;
+        sh.xt = ax.taps; sh.yt = ay.taps;
+        sh.ax_first = blob_push(blob, ax.first);
+        sh.ax_count = blob_push(blob, ax.count);
+        sh.ax_alpha = blob_push(blob, ax.alpha);
+        sh.ay_first = blob_push(blob, ay.first);
+        sh.ay_count = blob_push(blob, ay.count);
+        sh.ay_alpha = blob_push(blob, ay.alpha);
+    }
+    if (!sh.lin_identity) {
+        LinearAxis lx = build_linear_axis(sh.nw, w, true);
+        LinearAxis ly = build_linear_axis(sh.nh, h, false);
+        std::vector<uint32_t> ys(h);
+        for (int y = 0; y < h; ++y) ys[y] = (uint32_t)ly.s0[y] | ((uint32_t)ly.s1[y] << 16);
+        sh.lx_s0 = blob_push(blob, lx.s0);
+        sh.lx_a = blob_push(blob, lx.coef);
+        sh.ly_s = blob_push(blob, ys);
+        sh.ly_b = blob_push(blob, ly.coef);
+    }
+    *out = sh;
+    return true;
+}
+
+// Ultralytics 8.3.x LetterBox geometry (auto=False, scaleup=True, center=True).
+inline void letterbox_geometry(int h, int w, int out_h, int out_w, int* new_h, int* new_w, int* top, int* left) {
+    double r = std::min((double)out_h / h, (double)out_w / w);
+    // Python round(): half to even on the double
+    *new_w = (int)nearbyint(w * r);
+    *new_h = (int)nearbyint(h * r);
+    double dw = (out_w - *new_w) / 2.0, dh = (out_h - *new_h) / 2.0;
+    *top = (int)nearbyint(dh - 0.1);
+    *left = (int)nearbyint(dw - 0.1);
+}
+
+// Tile lists ---------------------------------------------------------------------------
+inline void build_noise_tiles(const std::vector<DevImage>& imgs, int span, std::vector<Tile>& tiles) {
+    for (int i = 0; i < (int)imgs.size(); ++i) {
+        const DevImage& im = imgs[i];
+        int64_t row = 3LL * im.w;
+        if (im.contiguous) {
+            int64_t n = row * im.h;
+            for (int64_t e = 0; e < n; e += span)
+                tiles.push_back(Tile{i, (int32_t)e, (int32_t)std::min<int64_t>(span, n - e), -1});
+        } else {
+            for (int y = 0; y < im.h; ++y)
+                for (int64_t e = 0; e < row; e += span)
+                    tiles.push_back(Tile{i, (int32_t)e, (int32_t)std::min<int64_t>(span, row - e), y});
+        }
+    }
+}
+
+inline void build_blur_tiles(const std::vector<DevImage>& imgs, int rows_per_tile, std::vector<Tile>& tiles) {
+    for (int i = 0; i < (int)imgs.size(); ++i)
+        for (int y = 0; y < imgs[i].h; y += rows_per_tile)
+            tiles.push_back(Tile{i, y, std::min(rows_per_tile, imgs[i].h - y), 0});
+}
+
+inline void build_grid_tiles(const std::vector<DevImage>& imgs, int th, int tw, std::vector<Tile>& tiles) {
+    for (int i = 0; i < (int)imgs.size(); ++i)
+        for (int y = 0; y < imgs[i].h; y += th)
+            for (int x = 0; x < imgs[i].w; x += tw) tiles.push_back(Tile{i, y, x, 0});
+}
+
+}  // namespace rod

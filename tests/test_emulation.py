@@ -1,0 +1,102 @@
+"""CPU: sequential replay of the CUDA kernels' tile loops (tests/emu/emu_harness.cpp, built from
+the same rod_core.h / rod_tables.h the kernels compile) against the oracle.  Validates the
+host-built resize tables, the index math and the per-chunk arithmetic without a GPU.
+Bit-exact for blur / lowres / compat noise; Philox field within 2e-3 (float vs float64 math)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import corruption_oracle as orc
+from tests.helpers import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emu", "emu_harness.cpp")
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "libemu.so")
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, SRC])
+    lib = ctypes.CDLL(out)
+    u8p, f32p = ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_float)
+    lib.emu_blur.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int]
+    lib.emu_lowres.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_int]
+    lib.emu_noise.argtypes = [u8p, u8p, f32p, f32p, ctypes.c_long, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
+    lib.emu_letterbox_u8.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return lib
+
+
+def _p(a, t=ctypes.c_uint8):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+SHAPES = [(1, 1), (1, 2), (2, 1), (3, 3), (2, 5), (7, 4), (5, 9), (9, 13), (17, 21), (33, 47), (40, 128), (64, 129),
+          (65, 255), (70, 257), (31, 1361), (100, 700), (77, 350), (50, 16), (36, 48)]
+
+
+@pytest.mark.parametrize("k", [9, 3, 5, 15, 31])
+def test_emu_blur(emu, k):
+    for n, (h, w) in enumerate(SHAPES):
+        img = synth(400 + n, h, w)
+        want = orc.apply_motion_blur(img, k, 0)
+        for phase in (0, 5, 15):
+            got = np.zeros_like(img)
+            assert emu.emu_blur(_p(img), _p(got), h, w, 3 * w, 3 * w, k, phase) == 0
+            assert np.array_equal(got, want), (h, w, k, phase)
+
+
+@pytest.mark.parametrize("factor", [0.5, 0.25, 0.3, 0.75, 1.0])
+def test_emu_lowres(emu, factor):
+    for n, (h, w) in enumerate(SHAPES):
+        img = synth(500 + n, h, w)
+        want = orc.apply_lowres(img, factor)
+        for phase in (0, 7):
+            got = np.zeros_like(img)
+            rc = emu.emu_lowres(_p(img), _p(got), h, w, 3 * w, 3 * w, factor, phase)
+            assert rc == 0, (h, w, factor, rc)
+            assert np.array_equal(got, want), (h, w, factor, phase)
+
+
+def test_emu_lowres_visdrone_shape(emu):
+    img = synth(12345, 765, 1360)
+    got = np.zeros_like(img)
+    assert emu.emu_lowres(_p(img), _p(got), 765, 1360, 4080, 4080, 0.5, 0) == 0
+    assert np.array_equal(got, orc.apply_lowres(img, 0.5))
+
+
+def test_emu_noise_compat_and_philox(emu):
+    img = synth(600, 37, 53)
+    n = img.size
+    np.random.seed(9)
+    field = orc.draw_noise_field(img.shape, 15)
+    got = np.zeros_like(img)
+    emu.emu_noise(_p(img), _p(got), _p(field, ctypes.c_float), None, n, 15.0, 0, 0, 0)
+    assert np.array_equal(got, orc.add_noise_field(img, field))
+    # philox stream: host replay (double math) vs numpy restatement
+    out = np.zeros(n, np.float32)
+    emu.emu_noise(_p(img), _p(got), None, _p(out, ctypes.c_float), n, 15.0, 0x1234567890ABCDEF, 5, 3)
+    want = orc.philox_noise_field(n, 15.0, 0x1234567890ABCDEF, 5, 3)
+    assert np.max(np.abs(out - want)) < 2e-3
+    assert np.array_equal(got, orc.add_noise_field(img, out.reshape(img.shape)))
+
+
+def test_philox_known_answer():
+    # Random123 KAT for philox4x32_10: ctr = key = 0 and the all-ones vector
+    r = orc.philox4x32_10(np.zeros((1, 4), np.uint32), np.zeros((1, 2), np.uint32))[0]
+    assert [hex(int(x)) for x in r] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    r = orc.philox4x32_10(np.full((1, 4), 0xFFFFFFFF, np.uint32), np.full((1, 2), 0xFFFFFFFF, np.uint32))[0]
+    assert [hex(int(x)) for x in r] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+@pytest.mark.parametrize("shape", [(765, 1360), (720, 1280), (360, 480), (640, 640), (333, 517)])
+def test_emu_letterbox(emu, shape):
+    h, w = shape
+    img = synth(700 + h, h, w)
+    canvas = np.zeros((640, 640, 3), np.uint8)
+    assert emu.emu_letterbox_u8(_p(img), h, w, 3 * w, _p(canvas), 640, 640, 114) == 0
+    want = orc.letterbox_norm_f16(img, 640, 640, 114)
+    got = (canvas[:, :, ::-1].transpose(2, 0, 1).astype(np.float32) / np.float32(255)).astype(np.float16)
+    assert np.array_equal(got, want)

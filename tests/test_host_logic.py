@@ -1,0 +1,122 @@
+"""CPU: the C-ABI library loads and exports every declared symbol; host-side logic
+(random-apply protocol, layouts, sharding incl. a world_size-2 gloo run).  No compute calls."""
+import os
+import re
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "robust-object-detection_b200", "librod_b200.so")
+
+
+@pytest.fixture(scope="module")
+def built():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+        g.build()
+    return LIB
+
+
+def test_abi_exports_every_declared_symbol(built):
+    from robust_object_detection_b200 import _native
+    header = open(os.path.join(ROOT, "include", "rod_b200.h")).read()
+    declared = set(re.findall(r"ROD_API[^;(]*?\b(rod_\w+)\s*\(", header))
+    assert len(declared) >= 16
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    lib = _native.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    exported = subprocess.check_output(["nm", "-D", "--defined-only", built], text=True)
+    exported = set(re.findall(r" T (rod_\w+)", exported))
+    assert declared <= exported
+    assert b"sm_100a" in lib.rod_version()
+
+
+def test_no_cpu_fallback_without_device(built):
+    from robust_object_detection_b200 import _native
+    if _native.lib().rod_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    from robust_object_detection_b200 import augmentations as aug
+    with pytest.raises(_native.RodError):
+        aug.apply_motion_blur(np.zeros((4, 4, 3), np.uint8), 9, 0)
+
+
+def test_argument_validation_precedes_device_work(built):
+    from robust_object_detection_b200 import augmentations as aug
+    with pytest.raises(NotImplementedError):
+        aug.apply_motion_blur(np.zeros((4, 4, 3), np.uint8), 9, 45)
+    with pytest.raises(NotImplementedError):
+        aug.apply_motion_blur(np.zeros((4, 4, 3), np.uint8), 8, 0)
+    with pytest.raises(ValueError):
+        aug.apply_lowres(np.zeros((4, 4), np.uint8), 0.5)
+    with pytest.raises(ValueError):
+        aug.apply_noise(np.zeros((4, 4, 3), np.float32), 15)
+
+
+def test_constants_and_kernel(golden_small):
+    from robust_object_detection_b200 import augmentations as aug
+    assert (aug.NOISE_SIGMA, aug.BLUR_KERNEL, aug.BLUR_ANGLE_DEG, aug.DOWNSCALE_FACTOR) == (15, 9, 0, 0.5)
+    k = aug._motion_blur_kernel(9, 0)
+    assert k.dtype == np.float32 and np.array_equal(k, golden_small["kernel_9_0"])
+
+
+def test_draw_decisions_matches_reference_streams(golden_hashes):
+    from robust_object_detection_b200.batch import draw_decisions
+    for gate in ("ultralytics", "pil"):
+        random.seed(42)
+        assert draw_decisions(64, gate).tolist() == golden_hashes["decisions"][gate]
+
+
+def test_shard_ranges_cover_everything_once():
+    from robust_object_detection_b200.sharding import shard_by_bytes, shard_range
+    for n in (1, 7, 256, 1610):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = shard_range(n, r, world)
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))
+    sizes = [3 * h * w for h, w in [(765, 1360), (1080, 1920), (360, 480), (1500, 2000)] * 50]
+    for world in (1, 2, 4, 8):
+        blocks = shard_by_bytes(sizes, world)
+        assert blocks[0][0] == 0 and blocks[-1][1] == len(sizes)
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        loads = [sum(sizes[lo:hi]) for lo, hi in blocks]
+        assert max(loads) <= 1.1 * sum(sizes) / world + max(sizes)
+
+
+_GLOO_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from robust_object_detection_b200.sharding import shard_range, gather_records
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+lo, hi = shard_range(1610, dist.get_rank(), 2)
+recs = gather_records({"rank": dist.get_rank(), "lo": lo, "hi": hi, "ms": 1.0 + dist.get_rank()})
+if dist.get_rank() == 0:
+    print(json.dumps(recs))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    import json
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs)
+    recs = json.loads(outs[0].strip().splitlines()[-1])
+    assert [r["rank"] for r in recs] == [0, 1]
+    assert recs[0]["lo"] == 0 and recs[0]["hi"] == recs[1]["lo"] and recs[1]["hi"] == 1610
+    assert max(r["ms"] for r in recs) == 2.0
