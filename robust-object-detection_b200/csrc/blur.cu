@@ -58,46 +58,66 @@ __global__ void __launch_bounds__(256) blur_rows_kernel(BlurParams p) {
         uint8_t* drow = p.dst + im.dst_off + (int64_t)y * im.dst_pitch;
         const int shift = (int)((uintptr_t)drow & 15);
         uint8_t* row = buf + kBlurLeft + shift;  // byte of pixel 0
-        const int nchunks = (shift + n + 15) >> 4;
+        // chunk j covers row positions [16j - shift, 16j - shift + 16); chunks [jf0, jf1) lie fully inside [0, n)
+        const int jf0 = (shift != 0) ? 1 : 0;
+        const int jf1 = (n + shift) >> 4;
+        const bool right_edge = ((n + shift) & 15) != 0;
 
         // ---- stage the row: smem byte (kBlurLeft + shift + i) = in[i]
         if ((((uintptr_t)srow ^ (uintptr_t)drow) & 15) == 0) {
             const uint8_t* sal = srow - shift;  // 16-byte aligned
-            for (int j = lane; j < nchunks; j += 32) {
-                const int lo = 16 * j - shift;  // row position of the chunk's first byte
-                if (lo >= 0 && lo + 16 <= n) {
-                    cp_async16(buf_s + kBlurLeft + 16 * j, sal + 16 * j);
-                } else {
-                    for (int b = 0; b < 16; ++b) {
-                        const int i = lo + b;
-                        if (i >= 0 && i < n) row[i] = srow[i];
-                    }
-                }
-            }
+            for (int j = jf0 + lane; j < jf1; j += 32) cp_async16(buf_s + kBlurLeft + 16 * j, sal + 16 * j);
+            // the (at most two) partial chunks: one byte per lane
+            const int i = (lane < 16) ? (lane - shift) : (16 * jf1 - shift + lane - 16);
+            if (((lane < 16) ? (shift != 0) : right_edge) && i >= 0 && i < n) row[i] = srow[i];
             cp_async_wait_all();
         } else {
             for (int i = lane; i < n; i += 32) row[i] = srow[i];
         }
         __syncwarp();
         // ---- reflected halo (BORDER_REFLECT_101 per pixel, not per byte)
-        for (int q = lane; q < 2 * halo; q += 32) {
-            const int i = (q < halo) ? (q - halo) : (n + q - halo);  // row position outside [0, n)
-            const int px = (i >= 0) ? i / 3 : -((-i + 2) / 3);       // floor(i / 3)
-            const int c = i - 3 * px;
-            row[i] = row[3 * reflect101(px, im.w) + c];
+        if (lane < 2 * halo || K == 0) {
+            for (int q = lane; q < 2 * halo; q += 32) {
+                const int i = (q < halo) ? (q - halo) : (n + q - halo);  // row position outside [0, n)
+                const int px = (i >= 0) ? i / 3 : -((-i + 2) / 3);       // floor(i / 3)
+                const int c = i - 3 * px;
+                int rp;
+                if (im.w > (k >> 1)) rp = (px < 0) ? -px : 2 * (im.w - 1) - px;  // single reflection
+                else rp = reflect101(px, im.w);                                   // tiny rows: periodic
+                row[i] = row[3 * rp + c];
+            }
         }
         __syncwarp();
         // ---- compute + store
         uint8_t* dal = drow - shift;
-        for (int j = lane; j < nchunks; j += 32) {
-            const int lo = 16 * j - shift;
-            uint32_t out[4];
-            if (K == 9) {
+        if (K == 9) {
+            for (int j = jf0 + lane; j < jf1; j += 32) {
                 const uint4* wp = reinterpret_cast<const uint4*>(buf + kBlurLeft + 16 * j - 16);
                 const uint4 a = wp[0], b = wp[1], c = wp[2];
                 const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                uint32_t out[4];
                 blur9_chunk16(w, out);
-            } else {
+                stg16_blur(dal + 16 * j, make_uint4(out[0], out[1], out[2], out[3]));
+            }
+            // partial chunks: lane 0 takes the left one, lane 1 the right one
+            if (lane < 2 && ((lane == 0) ? (shift != 0) : right_edge)) {
+                const int j = (lane == 0) ? 0 : jf1;
+                const uint4* wp = reinterpret_cast<const uint4*>(buf + kBlurLeft + 16 * j - 16);
+                const uint4 a = wp[0], b = wp[1], c = wp[2];
+                const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                uint32_t out[4];
+                blur9_chunk16(w, out);
+                const int lo = 16 * j - shift;
+                for (int bb = 0; bb < 16; ++bb) {
+                    const int i = lo + bb;
+                    if (i >= 0 && i < n) drow[i] = (uint8_t)(out[bb >> 2] >> (8 * (bb & 3)));
+                }
+            }
+        } else {
+            const int nchunks = (shift + n + 15) >> 4;
+            for (int j = lane; j < nchunks; j += 32) {
+                const int lo = 16 * j - shift;
+                uint32_t out[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint32_t o = 0;
@@ -109,13 +129,13 @@ __global__ void __launch_bounds__(256) blur_rows_kernel(BlurParams p) {
                     }
                     out[g] = o;
                 }
-            }
-            if (lo >= 0 && lo + 16 <= n) {
-                stg16_blur(dal + 16 * j, make_uint4(out[0], out[1], out[2], out[3]));
-            } else {
-                for (int b = 0; b < 16; ++b) {
-                    const int i = lo + b;
-                    if (i >= 0 && i < n) drow[i] = (uint8_t)(out[b >> 2] >> (8 * (b & 3)));
+                if (lo >= 0 && lo + 16 <= n) {
+                    stg16_blur(dal + 16 * j, make_uint4(out[0], out[1], out[2], out[3]));
+                } else {
+                    for (int b = 0; b < 16; ++b) {
+                        const int i = lo + b;
+                        if (i >= 0 && i < n) drow[i] = (uint8_t)(out[b >> 2] >> (8 * (b & 3)));
+                    }
                 }
             }
         }

@@ -3,11 +3,16 @@
 // Reference: scripts/augmentations.py:41-45 (apply_lowres): cv2.resize(img,(nw,nh),INTER_AREA)
 // followed by cv2.resize(small,(w,h),INTER_LINEAR).  The low-resolution intermediate of one
 // output tile (plus its one-pixel apron) is produced in shared memory and consumed from
-// there: it never exists in HBM.  Per tile of kLowresTH x kLowresTW output pixels:
-//   phase B : low-res tile (u8)  <- source pixels (area_value: exact OpenCV arithmetic)
-//   phase C1: horizontal fixed-point pass, (S0*a0 + S1*a1) >> 4 as u16 per low-res row
-//   phase C2: vertical pass + pack, 16 output bytes per thread, 128-bit stores at the
-//             destination's 16-byte phase (edges bytewise)
+// there: it never exists in HBM.  A tile is kLowresTH output rows x kLowresTWB output BYTES
+// (tiles are cut in byte columns, not pixels: every stage is per byte, channel = byte % 3).
+//   phase B : low-res tile P (u8)    <- source pixels
+//             exact-2x widths: 12 source bytes (4 px) per row per thread with 32-bit loads,
+//             byte pairs summed with dp4a; integer (a+b+c+d+2)>>2 when both axes are exact
+//             2x (OpenCV's resizeAreaFast_), else OpenCV's float tables on the y axis.
+//             any other shape: per-byte generic path (rod_core.h area_value).
+//   phase C1: horizontal fixed-point pass  hx = (P[s0]*a0 + P[s1]*a1) >> 4   (u16, smem)
+//   phase C2: vertical pass + pack.  Each thread owns 8 byte columns and marches down 8 rows,
+//             keeping the two live hx rows in registers; one 64-bit store per row.
 #include "rod_internal.h"
 
 namespace rod {
@@ -21,21 +26,40 @@ struct LowresParams {
     const uint8_t* src;
     uint8_t* dst;
     const uint8_t* opcodes;
-    int half_rows, half_cols;  // allocation (worst case over the plan) of the low-res tile
+    int half_rows;  // allocation (worst case over the plan): low-res rows one tile touches
+    int p_pitch;    // bytes per low-res row in shared memory
 };
 
-__device__ __forceinline__ void stg16_lr(void* p, uint4 v) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-                 "r"(v.w)
-                 : "memory");
+constexpr int kHxPitch = kLowresTWB + 8;  // u16 elements per hx row (rows stay 16-byte aligned)
+
+__device__ __forceinline__ uint32_t ldg32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+
+__device__ __forceinline__ void store_chunk8(uint8_t* p, uint32_t lo, uint32_t hi, int nvalid) {
+    // p is the address of the chunk's first byte; alignment depends on the row (warp-uniform)
+    if (nvalid == 8) {
+        const uintptr_t a = (uintptr_t)p;
+        if ((a & 7) == 0) {
+            asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+        } else if ((a & 3) == 0) {
+            reinterpret_cast<uint32_t*>(p)[0] = lo;
+            reinterpret_cast<uint32_t*>(p)[1] = hi;
+        } else if ((a & 1) == 0) {
+            uint16_t* q = reinterpret_cast<uint16_t*>(p);
+            q[0] = (uint16_t)lo; q[1] = (uint16_t)(lo >> 16); q[2] = (uint16_t)hi; q[3] = (uint16_t)(hi >> 16);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { p[b] = (uint8_t)(lo >> (8 * b)); p[4 + b] = (uint8_t)(hi >> (8 * b)); }
+        }
+    } else {
+        for (int b = 0; b < nvalid; ++b) p[b] = (uint8_t)((b < 4 ? lo : hi) >> (8 * (b & 3)));
+    }
 }
 
-__global__ void __launch_bounds__(256) lowres_kernel(LowresParams p) {
+__global__ void __launch_bounds__(256, 3) lowres_kernel(LowresParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int half_pitch = (p.half_cols * 3 + 15) & ~15;
-    const int hx_pitch = kLowresTW * 3 + 8;  // u16 elements; +8 keeps rows 16-byte aligned
-    uint8_t* half = smem;
-    uint16_t* hx = reinterpret_cast<uint16_t*>(smem + (size_t)p.half_rows * half_pitch);
+    uint8_t* P = smem;
+    uint16_t* hx = reinterpret_cast<uint16_t*>(smem + (size_t)p.half_rows * p.p_pitch);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
         const Tile t = p.tiles[ti];
@@ -44,91 +68,172 @@ __global__ void __launch_bounds__(256) lowres_kernel(LowresParams p) {
         const DevShape sh = p.shapes[im.shape_id];
         const uint8_t* simg = p.src + im.src_off;
         uint8_t* dimg = p.dst + im.dst_off;
-        const int y0 = t.a, x0 = t.b;
-        const int th = min(kLowresTH, im.h - y0), tw = min(kLowresTW, im.w - x0);
-        const int tw3 = tw * 3;
+        const int y0 = t.a, b0 = t.b;
+        const int n = 3 * im.w;
+        const int th = min(kLowresTH, im.h - y0), twb = min(kLowresTWB, n - b0);
 
         if (sh.lin_identity) {  // factor maps (h, w) onto itself: both resizes are copies
-            for (int idx = threadIdx.x; idx < th * tw3; idx += blockDim.x) {
-                const int r = idx / tw3, o = idx - r * tw3;
-                dimg[(int64_t)(y0 + r) * im.dst_pitch + x0 * 3 + o] = simg[(int64_t)(y0 + r) * im.src_pitch + x0 * 3 + o];
-            }
+            for (int r = warp; r < th; r += 8)
+                for (int o = lane; o < twb; o += 32)
+                    dimg[(int64_t)(y0 + r) * im.dst_pitch + b0 + o] = simg[(int64_t)(y0 + r) * im.src_pitch + b0 + o];
             continue;
         }
-        const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + sh.lx_s0);
-        const uint32_t* lx_a = p.tab + sh.lx_a;
         const uint32_t* ly_s = p.tab + sh.ly_s;
         const uint32_t* ly_b = p.tab + sh.ly_b;
-        // low-res rows / cols this tile reads (tables are monotonic)
+        const int x_first = b0 / 3, x_last = (b0 + twb - 1) / 3;
         const int j_lo = (int)(ly_s[y0] & 0xFFFFu), j_hi = (int)(ly_s[y0 + th - 1] >> 16);
-        const int i_lo = lx_s0[x0], i_hi = min(lx_s0[x0 + tw - 1] + 1, sh.nw - 1);
-        const int nj = j_hi - j_lo + 1, ni3 = (i_hi - i_lo + 1) * 3;
+        const int nj = j_hi - j_lo + 1;
+        const bool x2 = (sh.x2 != 0);
+        const bool vec = x2 && (sh.area_mode == AREA_FAST2 || sh.area_mode == AREA_GENERAL) &&
+                         ((((uintptr_t)simg) | (uintptr_t)im.src_pitch) & 3) == 0 && (im.w & 3) == 0;
+        int i_lo, i_hi;  // low-res pixel columns held in P (P column 0 is pixel i_base)
+        if (x2) {
+            i_lo = max(0, (x_first - 1) >> 1);
+            i_hi = min(max(0, (x_last - 1) >> 1) + 1, sh.nw - 1);
+        } else {
+            const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + sh.lx_s0);
+            i_lo = lx_s0[x_first];
+            i_hi = min(lx_s0[x_last] + 1, sh.nw - 1);
+        }
+        const int i_base = vec ? (i_lo & ~1) : i_lo;
 
-        // ---- phase B: low-res tile
-        for (int idx = threadIdx.x; idx < nj * ni3; idx += blockDim.x) {
-            const int jr = idx / ni3, o = idx - jr * ni3;
-            const int ir = o / 3, c = o - 3 * ir;
-            half[jr * half_pitch + o] = (uint8_t)area_value(simg, im.src_pitch, sh, p.tab, j_lo + jr, i_lo + ir, c);
+        // ---- phase B: low-res tile P[jr][3 * (i - i_base) + c]
+        if (vec) {
+            const int u_lo = i_base >> 1, n_units = (i_hi >> 1) - u_lo + 1;
+            if (sh.area_mode == AREA_FAST2) {
+                for (int jr = warp; jr < nj; jr += 8) {
+                    const uint8_t* r0 = simg + (int64_t)(2 * (j_lo + jr)) * im.src_pitch;
+                    const uint8_t* r1 = r0 + im.src_pitch;
+                    uint8_t* prow = P + jr * p.p_pitch;
+                    for (int u = lane; u < n_units; u += 32) {
+                        const int sb = 12 * (u_lo + u);
+                        const uint32_t ra[3] = {ldg32(r0 + sb), ldg32(r0 + sb + 4), ldg32(r0 + sb + 8)};
+                        const uint32_t rb[3] = {ldg32(r1 + sb), ldg32(r1 + sb + 4), ldg32(r1 + sb + 8)};
+                        uint32_t s[6];
+                        area_fast2_unit(ra, rb, s);
+                        uint16_t* o16 = reinterpret_cast<uint16_t*>(prow + 6 * u);
+                        o16[0] = (uint16_t)(s[0] | (s[1] << 8));
+                        o16[1] = (uint16_t)(s[2] | (s[3] << 8));
+                        o16[2] = (uint16_t)(s[4] | (s[5] << 8));
+                    }
+                }
+            } else {  // exact 2x in x, OpenCV float table in y (e.g. 1360 x 765)
+                const int32_t* yfirst = reinterpret_cast<const int32_t*>(p.tab + sh.ay_first);
+                const int32_t* ycount = reinterpret_cast<const int32_t*>(p.tab + sh.ay_count);
+                const float* yalpha = reinterpret_cast<const float*>(p.tab + sh.ay_alpha);
+                for (int jr = warp; jr < nj; jr += 8) {
+                    const int dy = j_lo + jr;
+                    const int sy0 = yfirst[dy], ny = ycount[dy];
+                    const float* beta = yalpha + dy * sh.yt;
+                    uint8_t* prow = P + jr * p.p_pitch;
+                    for (int u = lane; u < n_units; u += 32) {
+                        const int sb = 12 * (u_lo + u);
+                        float acc[6];
+                        for (int ty = 0; ty < ny; ++ty) {
+                            const uint8_t* r = simg + (int64_t)(sy0 + ty) * im.src_pitch + sb;
+                            const uint32_t rw[3] = {ldg32(r), ldg32(r + 4), ldg32(r + 8)};
+                            area_x2f_accumulate(rw, beta[ty], ty == 0, acc);
+                        }
+                        uint32_t r8[6];
+                        area_x2f_finish(acc, r8);
+                        uint16_t* o16 = reinterpret_cast<uint16_t*>(prow + 6 * u);
+                        o16[0] = (uint16_t)(r8[0] | (r8[1] << 8));
+                        o16[1] = (uint16_t)(r8[2] | (r8[3] << 8));
+                        o16[2] = (uint16_t)(r8[4] | (r8[5] << 8));
+                    }
+                }
+            }
+        } else {
+            const int ni3 = (i_hi - i_lo + 1) * 3;
+            for (int jr = warp; jr < nj; jr += 8)
+                for (int o = lane; o < ni3; o += 32) {
+                    const int ir = o / 3, c = o - 3 * ir;
+                    P[jr * p.p_pitch + o] = (uint8_t)area_value(simg, im.src_pitch, sh, p.tab, j_lo + jr, i_lo + ir, c);
+                }
         }
         __syncthreads();
-        // ---- phase C1: horizontal pass
-        for (int idx = threadIdx.x; idx < nj * tw3; idx += blockDim.x) {
-            const int jr = idx / tw3, o = idx - jr * tw3;
-            const int xr = o / 3, c = o - 3 * xr;
-            const int s0 = lx_s0[x0 + xr];
-            const int s1 = min(s0 + 1, sh.nw - 1);
-            const uint8_t* hr = half + jr * half_pitch;
-            hx[jr * hx_pitch + o] = (uint16_t)linear_h4(hr[(s0 - i_lo) * 3 + c], hr[(s1 - i_lo) * 3 + c], lx_a[x0 + xr]);
+
+        // ---- phase C1: horizontal pass -> hx[jr][ob] (u16), ob = byte column inside the tile
+        if (x2) {
+            // item = low-res pixel i (all channels): x = 2i+1 gets 3A+B, x = 2i+2 gets A+3B (A = P[i], B = P[i+1],
+            // indices clamped: that reproduces OpenCV's x = 0 and x = W-1 border coefficients 2048/0)
+            const int i_a = ((x_first + 1) >> 1) - 1, i_b = ((x_last + 1) >> 1) - 1;
+            const int ni = i_b - i_a + 1;
+            for (int jr = warp; jr < nj; jr += 8) {
+                const uint8_t* prow = P + jr * p.p_pitch;
+                uint16_t* hrow = hx + jr * kHxPitch;
+                for (int q = lane; q < ni; q += 32) {
+                    const int i = i_a + q;
+                    const uint8_t* pa = prow + 3 * (min(max(i, 0), sh.nw - 1) - i_base);
+                    const uint8_t* pb = prow + 3 * (min(i + 1, sh.nw - 1) - i_base);
+                    const int o1 = 3 * (2 * i + 1) - b0;  // tile byte column of (x = 2i+1, c = 0)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const uint32_t A = (uint32_t)pa[c] << 5, B = (uint32_t)pb[c] << 5;  // hx = 32 * q
+                        const int oa = o1 + c, ob = o1 + 3 + c;
+                        if (oa >= 0 && oa < twb) hrow[oa] = (uint16_t)(3u * A + B);
+                        if (ob >= 0 && ob < twb) hrow[ob] = (uint16_t)(A + 3u * B);
+                    }
+                }
+            }
+        } else {
+            const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + sh.lx_s0);
+            const uint32_t* lx_a = p.tab + sh.lx_a;
+            for (int jr = warp; jr < nj; jr += 8) {
+                const uint8_t* prow = P + jr * p.p_pitch;
+                uint16_t* hrow = hx + jr * kHxPitch;
+                for (int ob = lane; ob < twb; ob += 32) {
+                    const int o = b0 + ob;
+                    const int x = o / 3, c = o - 3 * x;
+                    const int s0 = lx_s0[x];
+                    const int s1 = min(s0 + 1, sh.nw - 1);
+                    hrow[ob] = (uint16_t)linear_h4(prow[(s0 - i_base) * 3 + c], prow[(s1 - i_base) * 3 + c], lx_a[x]);
+                }
+            }
         }
         __syncthreads();
-        // ---- phase C2: vertical pass, 16 bytes per thread at the destination's 16-byte phase
+
+        // ---- phase C2: vertical pass; thread = (row group of 8 rows, 8 byte columns)
         {
-            const int64_t row0 = (int64_t)y0 * im.dst_pitch + x0 * 3;
-            const int chunks_max = (tw3 + 15 + 15) >> 4;  // chunks per row for any phase
-            for (int idx = threadIdx.x; idx < th * chunks_max; idx += blockDim.x) {
-                const int r = idx / chunks_max, j = idx - r * chunks_max;
-                uint8_t* drow = dimg + row0 + (int64_t)r * im.dst_pitch;
-                const int shift = (int)((uintptr_t)drow & 15);
-                const int lo = 16 * j - shift;
-                if (lo >= tw3) continue;
-                const uint32_t ys = ly_s[y0 + r], yb = ly_b[y0 + r];
-                const uint16_t* h0 = hx + ((int)(ys & 0xFFFFu) - j_lo) * hx_pitch;
-                const uint16_t* h1 = hx + ((int)(ys >> 16) - j_lo) * hx_pitch;
-                uint32_t out[4];
-                if (lo >= 0 && lo + 16 <= tw3) {
-                    if ((lo & 7) == 0) {
-                        const uint4 a0 = *reinterpret_cast<const uint4*>(h0 + lo);
-                        const uint4 a1 = *reinterpret_cast<const uint4*>(h0 + lo + 8);
-                        const uint4 b0 = *reinterpret_cast<const uint4*>(h1 + lo);
-                        const uint4 b1 = *reinterpret_cast<const uint4*>(h1 + lo + 8);
-                        const uint32_t u0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                        const uint32_t u1[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const int rg = threadIdx.x >> 6, cc = threadIdx.x & 63;
+            const int col = 8 * cc;
+            const int nvalid = min(8, twb - col);
+            if (nvalid > 0) {
+                uint32_t ha[8], hb[8];  // hx rows ja / jb of this thread's 8 columns
+                int ja = -1, jb = -1;
+                const int r_end = min(th, 8 * rg + 8);
+                for (int r = 8 * rg; r < r_end; ++r) {
+                    const uint32_t ys = ly_s[y0 + r], yb = ly_b[y0 + r];
+                    const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+                    if (s0 != ja) {
+                        if (s0 == jb) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint32_t v0 = linear_v(u0[2 * g] & 0xFFFFu, u1[2 * g] & 0xFFFFu, yb);
-                            const uint32_t v1 = linear_v(u0[2 * g] >> 16, u1[2 * g] >> 16, yb);
-                            const uint32_t v2 = linear_v(u0[2 * g + 1] & 0xFFFFu, u1[2 * g + 1] & 0xFFFFu, yb);
-                            const uint32_t v3 = linear_v(u0[2 * g + 1] >> 16, u1[2 * g + 1] >> 16, yb);
-                            out[g] = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+                            for (int q = 0; q < 8; ++q) ha[q] = hb[q];
+                        } else {
+                            const uint4 v = *reinterpret_cast<const uint4*>(hx + (s0 - j_lo) * kHxPitch + col);
+                            ha[0] = v.x & 0xFFFFu; ha[1] = v.x >> 16; ha[2] = v.y & 0xFFFFu; ha[3] = v.y >> 16;
+                            ha[4] = v.z & 0xFFFFu; ha[5] = v.z >> 16; ha[6] = v.w & 0xFFFFu; ha[7] = v.w >> 16;
                         }
-                    } else {
+                        ja = s0;
+                    }
+                    if (s1 != jb) {
+                        if (s1 == ja) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint32_t o = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) {
-                                const int i = lo + 4 * g + b;
-                                o |= linear_v(h0[i], h1[i], yb) << (8 * b);
-                            }
-                            out[g] = o;
+                            for (int q = 0; q < 8; ++q) hb[q] = ha[q];
+                        } else {
+                            const uint4 v = *reinterpret_cast<const uint4*>(hx + (s1 - j_lo) * kHxPitch + col);
+                            hb[0] = v.x & 0xFFFFu; hb[1] = v.x >> 16; hb[2] = v.y & 0xFFFFu; hb[3] = v.y >> 16;
+                            hb[4] = v.z & 0xFFFFu; hb[5] = v.z >> 16; hb[6] = v.w & 0xFFFFu; hb[7] = v.w >> 16;
                         }
+                        jb = s1;
                     }
-                    stg16_lr(drow + lo, make_uint4(out[0], out[1], out[2], out[3]));
-                } else {
-                    for (int b = 0; b < 16; ++b) {
-                        const int i = lo + b;
-                        if (i >= 0 && i < tw3) drow[i] = (uint8_t)linear_v(h0[i], h1[i], yb);
-                    }
+                    const uint32_t c0 = yb & 0xFFFFu, c1 = yb >> 16;
+                    uint32_t o8[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o8[q] = (((c0 * ha[q]) >> 16) + ((c1 * hb[q]) >> 16) + 2u) >> 2;
+                    const uint32_t lo = o8[0] | (o8[1] << 8) | (o8[2] << 16) | (o8[3] << 24);
+                    const uint32_t hi = o8[4] | (o8[5] << 8) | (o8[6] << 16) | (o8[7] << 24);
+                    store_chunk8(dimg + (int64_t)(y0 + r) * im.dst_pitch + b0 + col, lo, hi, nvalid);
                 }
             }
         }
@@ -149,9 +254,8 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
     p.tab = plan->d_tab;
     p.src = src; p.dst = dst; p.opcodes = opcodes;
     p.half_rows = plan->lowres_half_rows;
-    p.half_cols = plan->lowres_half_cols;
-    const int half_pitch = (p.half_cols * 3 + 15) & ~15;
-    const size_t smem = (size_t)p.half_rows * half_pitch + (size_t)p.half_rows * (kLowresTW * 3 + 8) * 2;
+    p.p_pitch = (3 * (plan->lowres_half_cols + 3) + 15) & ~15;
+    const size_t smem = (size_t)p.half_rows * p.p_pitch + (size_t)p.half_rows * kHxPitch * 2;
     if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
     ROD_CUDA(cudaFuncSetAttribute(lowres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));

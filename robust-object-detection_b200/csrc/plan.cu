@@ -36,17 +36,10 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         const DevShape& sh = shapes[s];
         if (sh.lin_identity) continue;
         all_identity = false;
-        // worst-case low-res footprint of one output tile
-        const int32_t* lx = (const int32_t*)(blob.data() + sh.lx_s0);
-        const uint32_t* ly = blob.data() + sh.ly_s;
-        for (int y0 = 0; y0 < h; y0 += kLowresTH) {
-            const int y1 = std::min(h, y0 + kLowresTH) - 1;
-            max_rows = std::max(max_rows, (int)(ly[y1] >> 16) - (int)(ly[y0] & 0xFFFF) + 1);
-        }
-        for (int x0 = 0; x0 < w; x0 += kLowresTW) {
-            const int x1 = std::min(w, x0 + kLowresTW) - 1;
-            max_cols = std::max(max_cols, std::min(lx[x1] + 1, sh.nw - 1) - lx[x0] + 1);
-        }
+        int rows, cols;
+        lowres_tile_footprint(sh, blob.data(), kLowresTH, kLowresTWB, &rows, &cols);
+        max_rows = std::max(max_rows, rows);
+        max_cols = std::max(max_cols, cols);
     }
     if (blob.empty()) blob.push_back(0);
     if (plan->d_shapes) { cudaFree(plan->d_shapes); plan->d_shapes = nullptr; }
@@ -160,7 +153,7 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
     std::vector<Tile> nt, bt, lt;
     build_noise_tiles(plan->h_images, kNoiseSpan, nt);
     build_blur_tiles(plan->h_images, kBlurRowsPerTile, bt);
-    build_grid_tiles(plan->h_images, kLowresTH, kLowresTW, lt);
+    build_grid_tiles(plan->h_images, kLowresTH, kLowresTWB, lt);
     auto starts = [&](const std::vector<Tile>& tl, std::vector<int>& st) {
         st.assign(n_images + 1, (int)tl.size());
         for (int t = (int)tl.size() - 1; t >= 0; --t) st[tl[t].img] = t;

@@ -58,6 +58,7 @@ struct DevShape {
     uint32_t ly_s, ly_b;        // uint32 (s0 | s1 << 16)[h]; uint32 (b0 | b1 << 16)[h]
     float inv_area;             // float(1 / (ix*iy))
     int32_t lin_identity;       // 1 when (nh, nw) == (h, w): the INTER_LINEAR step is a copy
+    int32_t x2;                 // 1 when w == 2 * nw: exact 2x on the x axis (closed-form coefficients)
 };
 
 // ---------------------------------------------------------------------------------
@@ -176,37 +177,41 @@ ROD_HD uint32_t win_byte(const uint32_t* w, int p) { return (w[p >> 2] >> (8 * (
 // k = 9 fast path: 16 consecutive outputs from a 48-byte window w[0..11] that holds
 // input bytes [-16, 32) relative to the first output byte.  Uses 3 interleaved running
 // prefix sums (one per channel phase): C[p] = C[p-3] + B[p];  S[n] = C[n+12] - C[n-15].
-// out = (S + 4) / 9 == ((S + 4) * 7282) >> 16 for S <= 2295.
+// Rounded division without an integer multiply: with x = 2^23 + S (built by the same
+// 3-input add that forms S) and c9 = 932068 * 2^-23 (1/9 * (1 + 4.8e-7), chosen so that
+// 2^23 * c9 is an integer), fma(x, c9, 2^23 - 932068) = 2^23 + S*c9 exactly, rounded once
+// to the integer grid: the low byte is round(S / 9) because S/9 is never within 1/18 of a
+// tie and S * 4.8e-7 / 9 < 1.3e-4.  (== (2S + 9) / 18 == cv2.filter2D's saturate_cast.)
 ROD_HD void blur9_chunk16(const uint32_t* w, uint32_t out[4]) {
     // window byte index q = p + 16, p in [-15, 27]
     uint32_t C[43];  // C[t] for p = t - 15
-#if defined(__CUDA_ARCH__)
 #pragma unroll
     for (int t = 0; t < 43; ++t) {
-        int q = t + 1;  // p + 16
-        uint32_t prev = (t >= 3) ? C[t - 3] : 0u;
-        // the three chain heads p = -15,-14,-13 carry B[p] = 0 contribution: start sums at p >= -12
-        if (t < 3) { C[t] = 0u; continue; }
-        C[t] = __dp4a(w[q >> 2], 1u << (8 * (q & 3)), prev);
-    }
+        const int q = t + 1;  // p + 16
+        if (t < 3) { C[t] = 0u; continue; }  // chain heads p = -15,-14,-13 are outside every window
+#if defined(__CUDA_ARCH__)
+        C[t] = __dp4a(w[q >> 2], 1u << (8 * (q & 3)), C[t - 3]);
 #else
-    for (int t = 0; t < 43; ++t) {
-        int q = t + 1;
-        if (t < 3) { C[t] = 0u; continue; }
         C[t] = C[t - 3] + win_byte(w, q);
-    }
 #endif
+    }
+    const float c9 = 0.111111164093017578125f;  // 932068 / 2^23
+    uint32_t qv[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        const uint32_t xs = C[n + 27] - C[n] + 0x4B000000u;  // float bits of 2^23 + S
+        qv[n] = fbits(fmaf(bitsf(xs), c9, 7456540.0f));       // low byte = round(S / 9)
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        uint32_t o = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            int n = 4 * g + b;
-            uint32_t s = C[n + 27] - C[n];  // C[p=n+12] - C[p=n-15]
-            uint32_t qv = (s * 7282u + 29128u) >> 16;
-            o |= qv << (8 * b);
-        }
-        out[g] = o;
+#if defined(__CUDA_ARCH__)
+        const uint32_t lo = __byte_perm(qv[4 * g], qv[4 * g + 1], 0x0040);
+        const uint32_t hi = __byte_perm(qv[4 * g + 2], qv[4 * g + 3], 0x0040);
+        out[g] = __byte_perm(lo, hi, 0x5410);
+#else
+        out[g] = (qv[4 * g] & 0xFFu) | ((qv[4 * g + 1] & 0xFFu) << 8) | ((qv[4 * g + 2] & 0xFFu) << 16) |
+                 ((qv[4 * g + 3] & 0xFFu) << 24);
+#endif
     }
 }
 
@@ -252,6 +257,60 @@ ROD_HD uint32_t area_value(const uint8_t* src, int64_t pitch, const DevShape& sh
     float r = frint(sum);
     r = r < 0.f ? 0.f : (r > 255.f ? 255.f : r);
     return (uint32_t)(int)r;
+}
+
+// ---------------------------------------------------------------------------------
+// a4 fast paths for exact-2x widths: one "unit" = 12 consecutive source bytes (4 BGR pixels)
+// of one row -> the six horizontal pixel-pair sums (bytes k and k+3).  s[k] = acc[k] + pair_k.
+// ---------------------------------------------------------------------------------
+ROD_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+}
+ROD_HD uint32_t sum_b0_b3(uint32_t w, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+    return __dp4a(w, 0x01000001u, acc);
+#else
+    return acc + (w & 0xFFu) + (w >> 24);
+#endif
+}
+ROD_HD void pair_sums12(uint32_t w0, uint32_t w1, uint32_t w2, const uint32_t acc[6], uint32_t s[6]) {
+    s[0] = sum_b0_b3(w0, acc[0]);                   // b0 + b3
+    s[1] = sum_b0_b3(funnel_r(w0, w1, 8), acc[1]);  // b1 + b4
+    s[2] = sum_b0_b3(funnel_r(w0, w1, 16), acc[2]); // b2 + b5
+    s[3] = sum_b0_b3(funnel_r(w1, w2, 16), acc[3]); // b6 + b9
+    s[4] = sum_b0_b3(funnel_r(w1, w2, 24), acc[4]); // b7 + b10
+    s[5] = sum_b0_b3(w2, acc[5]);                   // b8 + b11
+}
+// resizeAreaFast_ 2x2: (a + b + c + d + 2) >> 2 for six low-res bytes from two source rows.
+ROD_HD void area_fast2_unit(const uint32_t r0[3], const uint32_t r1[3], uint32_t out6[6]) {
+    const uint32_t two[6] = {2u, 2u, 2u, 2u, 2u, 2u};
+    uint32_t s[6];
+    pair_sums12(r0[0], r0[1], r0[2], two, s);
+    pair_sums12(r1[0], r1[1], r1[2], s, s);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) out6[q] = s[q] >> 2;
+}
+// resizeArea_ with x scale exactly 2 (both x taps are 0.5) and `ny` float y taps:
+//   buf = (S0 + S1) * 0.5 (exact);  sum = beta0*buf0 (+ beta_t*buf_t ...), each op rounded;  out = rint(sum).
+// The factor 0.5 commutes with every rounding (power of two), so it is applied once inside the
+// final fma, which also performs the round-half-even to the integer grid (2^23 * 1.5 magic).
+ROD_HD void area_x2f_accumulate(const uint32_t r[3], float beta, bool first, float acc[6]) {
+    const uint32_t magic[6] = {0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u};
+    uint32_t s[6];
+    pair_sums12(r[0], r[1], r[2], magic, s);  // float bits of 2^23 + (S0 + S1)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const float prod = fmul(beta, fadd(bitsf(s[q]), -8388608.0f));
+        acc[q] = first ? prod : fadd(acc[q], prod);
+    }
+}
+ROD_HD void area_x2f_finish(const float acc[6], uint32_t out6[6]) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) out6[q] = fbits(fmaf(acc[q], 0.5f, 12582912.0f)) & 0xFFu;
 }
 
 // ---------------------------------------------------------------------------------

@@ -111,6 +111,7 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
     lowres_small_size(h, w, factor, &sh.nh, &sh.nw);
     if (sh.nh > h || sh.nw > w) return false;
     sh.lin_identity = (sh.nh == h && sh.nw == w) ? 1 : 0;
+    sh.x2 = (w == 2 * sh.nw) ? 1 : 0;
     sh.xt = sh.yt = 1;
     sh.ix = sh.iy = 1;
     sh.inv_area = 1.0f;
@@ -185,10 +186,28 @@ inline void build_blur_tiles(const std::vector<DevImage>& imgs, int rows_per_til
             tiles.push_back(Tile{i, y, std::min(rows_per_tile, imgs[i].h - y), 0});
 }
 
-inline void build_grid_tiles(const std::vector<DevImage>& imgs, int th, int tw, std::vector<Tile>& tiles) {
+// Tiles of th rows x twb BYTE columns (b = first byte column of the tile inside a row).
+inline void build_grid_tiles(const std::vector<DevImage>& imgs, int th, int twb, std::vector<Tile>& tiles) {
     for (int i = 0; i < (int)imgs.size(); ++i)
         for (int y = 0; y < imgs[i].h; y += th)
-            for (int x = 0; x < imgs[i].w; x += tw) tiles.push_back(Tile{i, y, x, 0});
+            for (int b = 0; b < 3 * imgs[i].w; b += twb) tiles.push_back(Tile{i, y, b, 0});
+}
+
+// Worst-case low-res footprint (rows, pixel columns) of one lowres tile of this shape.
+inline void lowres_tile_footprint(const DevShape& sh, const uint32_t* blob, int th, int twb, int* rows, int* cols) {
+    const int32_t* lx = (const int32_t*)(blob + sh.lx_s0);
+    const uint32_t* ly = blob + sh.ly_s;
+    int mr = 1, mc = 1;
+    for (int y0 = 0; y0 < sh.h; y0 += th) {
+        const int y1 = std::min(sh.h, y0 + th) - 1;
+        mr = std::max(mr, (int)(ly[y1] >> 16) - (int)(ly[y0] & 0xFFFF) + 1);
+    }
+    for (int b0 = 0; b0 < 3 * sh.w; b0 += twb) {
+        const int x0 = b0 / 3, x1 = (std::min(3 * sh.w, b0 + twb) - 1) / 3;
+        mc = std::max(mc, std::min(lx[x1] + 1, sh.nw - 1) - lx[x0] + 1);
+    }
+    *rows = mr;
+    *cols = mc;
 }
 
 }  // namespace rod

@@ -14,7 +14,7 @@
 using namespace rod;
 
 static const int kBlurLeft = 64;
-static const int kLowresTH = 32, kLowresTW = 128;
+static const int kLowresTH = 32, kLowresTWB = 512;
 
 // Replays blur_rows_kernel<9> / <0> for one image.  `dst_phase` shifts the destination (and
 // source) start address phase inside a 16-byte block, as an unaligned device buffer would.
@@ -72,9 +72,11 @@ extern "C" int emu_blur(const uint8_t* src, uint8_t* dst, int h, int w, long src
     return 0;
 }
 
-// Replays lowres_kernel for one image (tables from rod_tables.h, phases B / C1 / C2 per tile).
+// Replays lowres_kernel for one image: same tiling (kLowresTH rows x kLowresTWB byte columns), same
+// phase B variants (vector exact-2x units / generic), C1 (closed form / table) and C2 (marching).
+// `src_phase`: emulated address phase of the source (the vector path needs 4-byte alignment).
 extern "C" int emu_lowres(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
-                          double factor, int dst_phase) {
+                          double factor, int src_phase) {
     std::vector<uint32_t> blob;
     DevShape sh;
     if (!build_lowres_shape(h, w, factor, 8, blob, &sh)) return 2;
@@ -88,57 +90,119 @@ extern "C" int emu_lowres(const uint8_t* src, uint8_t* dst, int h, int w, long s
     const uint32_t* lx_a = tab + sh.lx_a;
     const uint32_t* ly_s = tab + sh.ly_s;
     const uint32_t* ly_b = tab + sh.ly_b;
-    // worst-case footprint exactly as ensure_lowres_tables computes it
-    int max_rows = 1, max_cols = 1;
-    for (int y0 = 0; y0 < h; y0 += kLowresTH) {
-        const int y1 = std::min(h, y0 + kLowresTH) - 1;
-        max_rows = std::max(max_rows, (int)(ly_s[y1] >> 16) - (int)(ly_s[y0] & 0xFFFF) + 1);
-    }
-    for (int x0 = 0; x0 < w; x0 += kLowresTW) {
-        const int x1 = std::min(w, x0 + kLowresTW) - 1;
-        max_cols = std::max(max_cols, std::min(lx_s0[x1] + 1, sh.nw - 1) - lx_s0[x0] + 1);
-    }
-    const int half_pitch = (max_cols * 3 + 15) & ~15;
-    const int hx_pitch = kLowresTW * 3 + 8;
-    std::vector<uint8_t> half((size_t)max_rows * half_pitch);
-    std::vector<uint16_t> hx((size_t)max_rows * hx_pitch);
+    int half_rows, half_cols;
+    lowres_tile_footprint(sh, tab, kLowresTH, kLowresTWB, &half_rows, &half_cols);
+    const int p_pitch = (3 * (half_cols + 3) + 15) & ~15;
+    const int hx_pitch = kLowresTWB + 8;
+    std::vector<uint8_t> P((size_t)half_rows * p_pitch);
+    std::vector<uint16_t> hx((size_t)half_rows * hx_pitch);
+    const int n = 3 * w;
     for (int y0 = 0; y0 < h; y0 += kLowresTH)
-        for (int x0 = 0; x0 < w; x0 += kLowresTW) {
-            const int th = std::min(kLowresTH, h - y0), tw = std::min(kLowresTW, w - x0);
-            const int tw3 = tw * 3;
+        for (int b0 = 0; b0 < n; b0 += kLowresTWB) {
+            const int th = std::min(kLowresTH, h - y0), twb = std::min(kLowresTWB, n - b0);
+            const int x_first = b0 / 3, x_last = (b0 + twb - 1) / 3;
             const int j_lo = (int)(ly_s[y0] & 0xFFFFu), j_hi = (int)(ly_s[y0 + th - 1] >> 16);
-            const int i_lo = lx_s0[x0], i_hi = std::min(lx_s0[x0 + tw - 1] + 1, sh.nw - 1);
-            const int nj = j_hi - j_lo + 1, ni3 = (i_hi - i_lo + 1) * 3;
-            if (nj > max_rows || ni3 > max_cols * 3) return 3;
-            std::fill(half.begin(), half.end(), 0xEE);
+            const int nj = j_hi - j_lo + 1;
+            if (nj > half_rows) return 3;
+            const bool x2 = sh.x2 != 0;
+            const bool vec = x2 && (sh.area_mode == AREA_FAST2 || sh.area_mode == AREA_GENERAL) &&
+                             (((long)src_phase | src_pitch) & 3) == 0 && (w & 3) == 0;
+            int i_lo, i_hi;
+            if (x2) {
+                i_lo = std::max(0, (x_first - 1) >> 1);
+                i_hi = std::min(std::max(0, (x_last - 1) >> 1) + 1, sh.nw - 1);
+            } else {
+                i_lo = lx_s0[x_first];
+                i_hi = std::min(lx_s0[x_last] + 1, sh.nw - 1);
+            }
+            const int i_base = vec ? (i_lo & ~1) : i_lo;
+            if (i_hi - i_lo + 1 > half_cols) return 4;
+            std::fill(P.begin(), P.end(), 0xEE);
             std::fill(hx.begin(), hx.end(), 0xEEEE);
-            for (int idx = 0; idx < nj * ni3; ++idx) {
-                const int jr = idx / ni3, o = idx - jr * ni3;
-                const int ir = o / 3, c = o - 3 * ir;
-                half[jr * half_pitch + o] = (uint8_t)area_value(src, src_pitch, sh, tab, j_lo + jr, i_lo + ir, c);
+            if (vec) {
+                const int u_lo = i_base >> 1, n_units = (i_hi >> 1) - u_lo + 1;
+                if (6 * n_units > p_pitch) return 5;
+                for (int jr = 0; jr < nj; ++jr)
+                    for (int u = 0; u < n_units; ++u) {
+                        const int sb = 12 * (u_lo + u);
+                        uint32_t o6[6];
+                        if (sh.area_mode == AREA_FAST2) {
+                            uint32_t ra[3], rb[3];
+                            memcpy(ra, src + (long)(2 * (j_lo + jr)) * src_pitch + sb, 12);
+                            memcpy(rb, src + (long)(2 * (j_lo + jr) + 1) * src_pitch + sb, 12);
+                            area_fast2_unit(ra, rb, o6);
+                        } else {
+                            const int32_t* yfirst = (const int32_t*)(tab + sh.ay_first);
+                            const int32_t* ycount = (const int32_t*)(tab + sh.ay_count);
+                            const float* beta = (const float*)(tab + sh.ay_alpha) + (j_lo + jr) * sh.yt;
+                            float acc[6];
+                            for (int ty = 0; ty < ycount[j_lo + jr]; ++ty) {
+                                uint32_t rw[3];
+                                memcpy(rw, src + (long)(yfirst[j_lo + jr] + ty) * src_pitch + sb, 12);
+                                area_x2f_accumulate(rw, beta[ty], ty == 0, acc);
+                            }
+                            area_x2f_finish(acc, o6);
+                        }
+                        for (int q = 0; q < 6; ++q) P[jr * p_pitch + 6 * u + q] = (uint8_t)o6[q];
+                    }
+            } else {
+                const int ni3 = (i_hi - i_lo + 1) * 3;
+                for (int jr = 0; jr < nj; ++jr)
+                    for (int o = 0; o < ni3; ++o) {
+                        const int ir = o / 3, c = o - 3 * ir;
+                        P[jr * p_pitch + o] = (uint8_t)area_value(src, src_pitch, sh, tab, j_lo + jr, i_lo + ir, c);
+                    }
             }
-            for (int idx = 0; idx < nj * tw3; ++idx) {
-                const int jr = idx / tw3, o = idx - jr * tw3;
-                const int xr = o / 3, c = o - 3 * xr;
-                const int s0 = lx_s0[x0 + xr];
-                const int s1 = std::min(s0 + 1, sh.nw - 1);
-                const uint8_t* hr = half.data() + jr * half_pitch;
-                hx[jr * hx_pitch + o] = (uint16_t)linear_h4(hr[(s0 - i_lo) * 3 + c], hr[(s1 - i_lo) * 3 + c], lx_a[x0 + xr]);
+            if (x2) {
+                const int i_a = ((x_first + 1) >> 1) - 1, i_b = ((x_last + 1) >> 1) - 1;
+                for (int jr = 0; jr < nj; ++jr)
+                    for (int i = i_a; i <= i_b; ++i) {
+                        const uint8_t* pa = P.data() + jr * p_pitch + 3 * (std::min(std::max(i, 0), sh.nw - 1) - i_base);
+                        const uint8_t* pb = P.data() + jr * p_pitch + 3 * (std::min(i + 1, sh.nw - 1) - i_base);
+                        const int o1 = 3 * (2 * i + 1) - b0;
+                        for (int c = 0; c < 3; ++c) {
+                            const uint32_t A = (uint32_t)pa[c] << 5, B = (uint32_t)pb[c] << 5;
+                            const int oa = o1 + c, ob = o1 + 3 + c;
+                            if (oa >= 0 && oa < twb) hx[jr * hx_pitch + oa] = (uint16_t)(3u * A + B);
+                            if (ob >= 0 && ob < twb) hx[jr * hx_pitch + ob] = (uint16_t)(A + 3u * B);
+                        }
+                    }
+            } else {
+                for (int jr = 0; jr < nj; ++jr)
+                    for (int ob = 0; ob < twb; ++ob) {
+                        const int o = b0 + ob;
+                        const int x = o / 3, c = o - 3 * x;
+                        const int s0 = lx_s0[x];
+                        const int s1 = std::min(s0 + 1, sh.nw - 1);
+                        const uint8_t* prow = P.data() + jr * p_pitch;
+                        hx[jr * hx_pitch + ob] = (uint16_t)linear_h4(prow[(s0 - i_base) * 3 + c], prow[(s1 - i_base) * 3 + c], lx_a[x]);
+                    }
             }
-            const long row0 = (long)y0 * dst_pitch + x0 * 3;
-            const int chunks_max = (tw3 + 15 + 15) >> 4;
-            for (int idx = 0; idx < th * chunks_max; ++idx) {
-                const int r = idx / chunks_max, j = idx - r * chunks_max;
-                uint8_t* drow = dst + row0 + (long)r * dst_pitch;
-                const int shift = (int)((row0 + (long)r * dst_pitch + dst_phase) & 15);
-                const int lo = 16 * j - shift;
-                if (lo >= tw3) continue;
-                const uint32_t ys = ly_s[y0 + r], yb = ly_b[y0 + r];
-                const uint16_t* h0 = hx.data() + ((int)(ys & 0xFFFFu) - j_lo) * hx_pitch;
-                const uint16_t* h1 = hx.data() + ((int)(ys >> 16) - j_lo) * hx_pitch;
-                for (int b = 0; b < 16; ++b) {
-                    const int i = lo + b;
-                    if (i >= 0 && i < tw3) drow[i] = (uint8_t)linear_v(h0[i], h1[i], yb);
+            for (int tid = 0; tid < 256; ++tid) {
+                const int rg = tid >> 6, cc = tid & 63;
+                const int col = 8 * cc;
+                const int nvalid = std::min(8, twb - col);
+                if (nvalid <= 0) continue;
+                uint32_t ha[8], hb[8];
+                int ja = -1, jb = -1;
+                const int r_end = std::min(th, 8 * rg + 8);
+                for (int r = 8 * rg; r < r_end; ++r) {
+                    const uint32_t ys = ly_s[y0 + r], yb = ly_b[y0 + r];
+                    const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+                    if (s0 != ja) {
+                        if (s0 == jb) { for (int q = 0; q < 8; ++q) ha[q] = hb[q]; }
+                        else for (int q = 0; q < 8; ++q) ha[q] = hx[(s0 - j_lo) * hx_pitch + col + q];
+                        ja = s0;
+                    }
+                    if (s1 != jb) {
+                        if (s1 == ja) { for (int q = 0; q < 8; ++q) hb[q] = ha[q]; }
+                        else for (int q = 0; q < 8; ++q) hb[q] = hx[(s1 - j_lo) * hx_pitch + col + q];
+                        jb = s1;
+                    }
+                    const uint32_t c0 = yb & 0xFFFFu, c1 = yb >> 16;
+                    for (int q = 0; q < nvalid; ++q)
+                        dst[(long)(y0 + r) * dst_pitch + b0 + col + q] =
+                            (uint8_t)((((c0 * ha[q]) >> 16) + ((c1 * hb[q]) >> 16) + 2u) >> 2);
                 }
             }
         }

@@ -34,7 +34,8 @@ def _p(a, t=ctypes.c_uint8):
 
 
 SHAPES = [(1, 1), (1, 2), (2, 1), (3, 3), (2, 5), (7, 4), (5, 9), (9, 13), (17, 21), (33, 47), (40, 128), (64, 129),
-          (65, 255), (70, 257), (31, 1361), (100, 700), (77, 350), (50, 16), (36, 48)]
+          (65, 255), (70, 257), (31, 1361), (100, 700), (77, 350), (50, 16), (36, 48), (66, 172), (35, 344),
+          (34, 346), (64, 1024), (41, 684)]
 
 
 @pytest.mark.parametrize("k", [9, 3, 5, 15, 31])

@@ -200,7 +200,8 @@ def test_philox_statistics_and_reproducibility(torch_):
     out = dst.cpu().numpy().astype(np.int32)
     d0 = out[0] - img[0]
     mid = (img[0] >= 70) & (img[0] <= 185)
-    assert abs(d0[mid].mean() + 0.5) < 0.02
+    # 1.4 M mid-range samples: standard error of the mean is 15/sqrt(n) = 0.013 -> 4 sigma
+    assert abs(d0[mid].mean() + 0.5) < 0.05
     assert abs(d0[mid].std() - 15.0) < 0.05
     # clipping fractions against the reference's own numpy draw on the same image (binomial noise ~1e-4)
     np.random.seed(1)
@@ -209,7 +210,7 @@ def test_philox_statistics_and_reproducibility(torch_):
     assert abs((out[0] == 255).mean() - (ref == 255).mean()) < 6e-4
     assert 0.020 < ((out[0] == 0) & (img[0] > 0)).mean() + (img[0] == 0).mean() * 0.5 < 0.029
     d1 = out[1] - 128
-    assert abs(d1.mean() + 0.5) < 0.02 and abs(d1.std() - 15.0) < 0.03
+    assert abs(d1.mean() + 0.5) < 0.035 and abs(d1.std() - 15.0) < 0.03
     # chi-square of the residual histogram on the constant image against N(0, 15^2) bins
     from scipy import stats
     edges = np.arange(-60, 62)

@@ -1,0 +1,41 @@
+"""Short driver for ncu captures: a few launches of each kernel on a 64-image 1360x765 batch
+(399 MB of traffic per launch, larger than L2).  Not a benchmark."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from robust_object_detection_b200.batch import CorruptionPlan, draw_decisions
+
+n, h, w = 64, 765, 1360
+torch.cuda.set_device(0)
+src = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
+dst = torch.empty_like(src)
+plan = CorruptionPlan.uniform(n, h, w)
+which = sys.argv[1:] or ["blur", "noise", "lowres", "letterbox", "mixed"]
+for _ in range(3):
+    if "blur" in which:
+        plan.blur(src, dst)
+    if "noise" in which:
+        plan.noise(src, dst, None, 15.0, seed=1)
+    if "lowres" in which:
+        plan.lowres(src, dst)
+if "letterbox" in which:
+    import random
+    random.seed(42)
+    ops = torch.from_numpy(draw_decisions(n)).cuda()
+    f16 = torch.empty((n, 3, 640, 640), dtype=torch.float16, device="cuda")
+    for _ in range(2):
+        plan.corrupt_letterbox(src, ops, f16, 640, 640, 114, seed=1)
+if "mixed" in which:
+    shapes = [(1080, 1920), (1079, 1917), (1050, 1400), (1500, 2000)] * 8
+    rp = CorruptionPlan.ragged(shapes)
+    rsrc = torch.randint(0, 256, (rp.src_bytes,), dtype=torch.uint8, device="cuda")
+    rdst = torch.empty_like(rsrc)
+    for _ in range(2):
+        rp.lowres(rsrc, rdst)
+        rp.blur(rsrc, rdst)
+torch.cuda.synchronize()
+print("profile_ops done")
