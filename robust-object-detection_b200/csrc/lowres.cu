@@ -241,28 +241,221 @@ __global__ void __launch_bounds__(256, 3) lowres_kernel(LowresParams p) {
     }
 }
 
+// =====================================================================================
+// Fast kernel for exact-2x widths (w == 2 * nw: every even-width image, e.g. 1360 x 765).
+// Work item of a CTA = one full-width strip of `strip_rows` output rows of one image.
+//   phase B: low-res rows of the strip -> shared memory P (u8), one thread per 12 source bytes x taps
+//            P row layout: [0] unused, [1..3] = pixel 0 replicated, [4 + 3i + c] = pixel i, then pixel nw-1 replicated
+//   phase C: item = (8 output rows, 8 output pixels = 24 bytes).  The horizontal stage runs in registers
+//            (dp2a on gathered byte pairs -> 24 floats per low-res row, kept in two parity slots while the
+//            thread walks down its 8 rows); the vertical stage is four fp32 ops per byte (x2_vertical).
+// =====================================================================================
+struct LowresX2Params {
+    const DevImage* images;
+    const Tile* tiles;   // a = first output row of the strip
+    int n_tiles;
+    const DevShape* shapes;
+    const uint32_t* tab;
+    const uint8_t* src;
+    uint8_t* dst;
+    const uint8_t* opcodes;
+};
+
+__device__ __forceinline__ void x2_load_row(const uint8_t* prow, int chunk, float x[24]) {
+    // window bytes [12*chunk + 1, +20) of the P row: six aligned words, funnel-shifted by one byte
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(prow) + 3 * chunk;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5];
+    const uint32_t win[5] = {funnel_r(w0, w1, 8), funnel_r(w1, w2, 8), funnel_r(w2, w3, 8), funnel_r(w3, w4, 8),
+                             funnel_r(w4, w5, 8)};
+    x2_expand24(win, x);
+}
+
+__device__ __forceinline__ void x2_emit_row(const float* xlo, const float* xhi, const X2Row& rc, uint8_t* dptr,
+                                            int nvalid) {
+    uint32_t o[24];
+#pragma unroll
+    for (int t = 0; t < 24; ++t) o[t] = x2_vertical(xlo[t], xhi[t], rc);
+    uint32_t wds[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g) {
+        const uint32_t lo = __byte_perm(o[4 * g], o[4 * g + 1], 0x0040);
+        const uint32_t hi = __byte_perm(o[4 * g + 2], o[4 * g + 3], 0x0040);
+        wds[g] = __byte_perm(lo, hi, 0x5410);
+    }
+    if (nvalid == 24) {
+        store_chunk8(dptr, wds[0], wds[1], 8);
+        store_chunk8(dptr + 8, wds[2], wds[3], 8);
+        store_chunk8(dptr + 16, wds[4], wds[5], 8);
+    } else {
+        for (int b = 0; b < nvalid; ++b) dptr[b] = (uint8_t)(wds[b >> 2] >> (8 * (b & 3)));
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) lowres_x2_kernel(LowresX2Params p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
+        const Tile t = p.tiles[ti];
+        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
+        const DevImage im = p.images[t.img];
+        const DevShape sh = p.shapes[im.shape_id];
+        const uint8_t* simg = p.src + im.src_off;
+        uint8_t* dimg = p.dst + im.dst_off;
+        const int y0 = t.a;
+        const int th = min(sh.strip_rows, im.h - y0);
+        const int n = 3 * im.w, nw = sh.nw;
+        const int p_pitch = (3 * nw + 24 + 15) & ~15;
+        const uint32_t* ly_s = p.tab + sh.ly_s;
+        const uint32_t* ly_b = p.tab + sh.ly_b;
+        const int j_lo = (int)(ly_s[y0] & 0xFFFFu), j_hi = (int)(ly_s[y0 + th - 1] >> 16);
+        const int nj = j_hi - j_lo + 1;
+
+        // ---- phase B
+        const bool vec = (sh.area_mode == AREA_FAST2 || sh.area_mode == AREA_GENERAL) && (im.w & 3) == 0 &&
+                         ((((uintptr_t)simg) | (uintptr_t)im.src_pitch) & 3) == 0;
+        if (vec) {
+            const int n_units = nw >> 1;
+            const uint32_t magic_div = 0xFFFFFFFFu / (uint32_t)n_units + 1u;  // floor(idx / n_units) = umulhi(idx, magic)
+            const int total = nj * n_units;
+            const int32_t* yfirst = reinterpret_cast<const int32_t*>(p.tab + sh.ay_first);
+            const int32_t* ycount = reinterpret_cast<const int32_t*>(p.tab + sh.ay_count);
+            const float* yalpha = reinterpret_cast<const float*>(p.tab + sh.ay_alpha);
+            const bool fast2 = (sh.area_mode == AREA_FAST2);
+            for (int idx = threadIdx.x; idx < total; idx += 256) {
+                const int jr = (n_units == 1) ? idx : (int)__umulhi((uint32_t)idx, magic_div);
+                const int u = idx - jr * n_units;
+                const int dy = j_lo + jr;
+                const int sb = 12 * u;
+                uint32_t o6[6];
+                if (fast2) {
+                    const uint8_t* r0 = simg + (int64_t)(2 * dy) * im.src_pitch + sb;
+                    const uint8_t* r1 = r0 + im.src_pitch;
+                    const uint32_t ra[3] = {ldg32(r0), ldg32(r0 + 4), ldg32(r0 + 8)};
+                    const uint32_t rb[3] = {ldg32(r1), ldg32(r1 + 4), ldg32(r1 + 8)};
+                    area_fast2_unit(ra, rb, o6);
+                } else {
+                    const int sy0 = yfirst[dy], ny = ycount[dy];
+                    const float* beta = yalpha + dy * sh.yt;
+                    const uint8_t* r = simg + (int64_t)sy0 * im.src_pitch + sb;
+                    float acc[6];
+                    {
+                        const uint32_t rw[3] = {ldg32(r), ldg32(r + 4), ldg32(r + 8)};
+                        area_x2f_accumulate(rw, beta[0], true, acc);
+                    }
+                    for (int ty = 1; ty < ny; ++ty) {
+                        r += im.src_pitch;
+                        const uint32_t rw[3] = {ldg32(r), ldg32(r + 4), ldg32(r + 8)};
+                        area_x2f_accumulate(rw, beta[ty], false, acc);
+                    }
+                    area_x2f_finish(acc, o6);
+                }
+                uint8_t* prow = smem + jr * p_pitch;
+                uint16_t* o16 = reinterpret_cast<uint16_t*>(prow + 4 + 6 * u);
+                o16[0] = (uint16_t)(o6[0] | (o6[1] << 8));
+                o16[1] = (uint16_t)(o6[2] | (o6[3] << 8));
+                o16[2] = (uint16_t)(o6[4] | (o6[5] << 8));
+                if (u == 0) { prow[1] = (uint8_t)o6[0]; prow[2] = (uint8_t)o6[1]; prow[3] = (uint8_t)o6[2]; }
+                if (u == n_units - 1) {
+                    prow[4 + 3 * nw] = (uint8_t)o6[3]; prow[5 + 3 * nw] = (uint8_t)o6[4]; prow[6 + 3 * nw] = (uint8_t)o6[5];
+                }
+            }
+        } else {
+            const int total = nj * 3 * nw;
+            for (int idx = threadIdx.x; idx < total; idx += 256) {
+                const int jr = idx / (3 * nw), o = idx - jr * 3 * nw;
+                const int i = o / 3, c = o - 3 * i;
+                const uint8_t v = (uint8_t)area_value(simg, im.src_pitch, sh, p.tab, j_lo + jr, i, c);
+                uint8_t* prow = smem + jr * p_pitch;
+                prow[4 + o] = v;
+                if (i == 0) prow[1 + c] = v;
+                if (i == nw - 1) prow[4 + 3 * nw + c] = v;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase C
+        {
+            const int nchunks = (im.w + 7) >> 3;
+            const int ngroups = (th + 7) >> 3;
+            const uint32_t magic_div = 0xFFFFFFFFu / (uint32_t)nchunks + 1u;
+            const int total = ngroups * nchunks;
+            for (int idx = threadIdx.x; idx < total; idx += 256) {
+                const int rg = (nchunks == 1) ? idx : (int)__umulhi((uint32_t)idx, magic_div);
+                const int ch = idx - rg * nchunks;
+                const int nvalid = min(24, n - 24 * ch);
+                float xe[24], xo[24];  // horizontal stage of the even / odd low-res row currently held
+                int je = -1, jo = -1;
+                const int r_end = min(th, 8 * rg + 8);
+                for (int r = 8 * rg; r < r_end; ++r) {
+                    const uint32_t ys = ly_s[y0 + r];
+                    const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+                    const X2Row rc = x2_row_consts(ly_b[y0 + r]);
+                    // make sure both rows sit in their parity slot
+                    if ((s0 & 1) ? (jo != s0) : (je != s0)) {
+                        if (s0 & 1) { x2_load_row(smem + (s0 - j_lo) * p_pitch, ch, xo); jo = s0; }
+                        else { x2_load_row(smem + (s0 - j_lo) * p_pitch, ch, xe); je = s0; }
+                    }
+                    if ((s1 & 1) ? (jo != s1) : (je != s1)) {
+                        if (s1 & 1) { x2_load_row(smem + (s1 - j_lo) * p_pitch, ch, xo); jo = s1; }
+                        else { x2_load_row(smem + (s1 - j_lo) * p_pitch, ch, xe); je = s1; }
+                    }
+                    uint8_t* dptr = dimg + (int64_t)(y0 + r) * im.dst_pitch + 24 * ch;
+                    if (s0 & 1) {
+                        if (s1 & 1) x2_emit_row(xo, xo, rc, dptr, nvalid);
+                        else x2_emit_row(xo, xe, rc, dptr, nvalid);
+                    } else {
+                        if (s1 & 1) x2_emit_row(xe, xo, rc, dptr, nvalid);
+                        else x2_emit_row(xe, xe, rc, dptr, nvalid);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // P is rewritten by the next strip
+    }
+}
+
 int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
                   cudaStream_t stream, int img_lo, int img_hi) {
-    if (plan->n_lowres_tiles == 0) return ROD_OK;
-    LowresParams p;
-    p.images = plan->d_images;
-    const int t_lo = plan->lowres_tile_start[img_lo], t_hi = plan->lowres_tile_start[img_hi];
-    if (t_hi <= t_lo) return ROD_OK;
-    p.tiles = plan->d_lowres_tiles + t_lo;
-    p.n_tiles = t_hi - t_lo;
-    p.shapes = plan->d_shapes;
-    p.tab = plan->d_tab;
-    p.src = src; p.dst = dst; p.opcodes = opcodes;
-    p.half_rows = plan->lowres_half_rows;
-    p.p_pitch = (3 * (plan->lowres_half_cols + 3) + 15) & ~15;
-    const size_t smem = (size_t)p.half_rows * p.p_pitch + (size_t)p.half_rows * kHxPitch * 2;
-    if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
-    ROD_CUDA(cudaFuncSetAttribute(lowres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
-    ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
-    const int grid = grid_for(plan, p.n_tiles, ctas_per_sm);
-    lowres_kernel<<<grid, 256, smem, stream>>>(p);
-    ROD_CUDA(cudaGetLastError());
+    // generic tiles (shapes that are not exact-2x in x)
+    {
+        const int t_lo = plan->lowres_tile_start[img_lo], t_hi = plan->lowres_tile_start[img_hi];
+        if (t_hi > t_lo) {
+            LowresParams p;
+            p.images = plan->d_images;
+            p.tiles = plan->d_lowres_tiles + t_lo;
+            p.n_tiles = t_hi - t_lo;
+            p.shapes = plan->d_shapes;
+            p.tab = plan->d_tab;
+            p.src = src; p.dst = dst; p.opcodes = opcodes;
+            p.half_rows = plan->lowres_half_rows;
+            p.p_pitch = (3 * (plan->lowres_half_cols + 3) + 15) & ~15;
+            const size_t smem = (size_t)p.half_rows * p.p_pitch + (size_t)p.half_rows * kHxPitch * 2;
+            if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
+            ROD_CUDA(cudaFuncSetAttribute(lowres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+            ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 3 ? 3 : ctas_per_sm);
+            lowres_kernel<<<grid_for(plan, p.n_tiles, ctas_per_sm), 256, smem, stream>>>(p);
+            ROD_CUDA(cudaGetLastError());
+        }
+    }
+    // full-width strips of exact-2x shapes
+    {
+        const int t_lo = plan->lowres_x2_tile_start[img_lo], t_hi = plan->lowres_x2_tile_start[img_hi];
+        if (t_hi > t_lo) {
+            LowresX2Params p;
+            p.images = plan->d_images;
+            p.tiles = plan->d_lowres_x2_tiles + t_lo;
+            p.n_tiles = t_hi - t_lo;
+            p.shapes = plan->d_shapes;
+            p.tab = plan->d_tab;
+            p.src = src; p.dst = dst; p.opcodes = opcodes;
+            const size_t smem = plan->lowres_x2_smem;
+            ROD_CUDA(cudaFuncSetAttribute(lowres_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+            ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 2 ? 2 : ctas_per_sm);
+            lowres_x2_kernel<<<grid_for(plan, p.n_tiles, ctas_per_sm), 256, smem, stream>>>(p);
+            ROD_CUDA(cudaGetLastError());
+        }
+    }
     return ROD_OK;
 }
 

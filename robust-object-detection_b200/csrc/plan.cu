@@ -23,6 +23,12 @@ static int upload(const std::vector<T>& v, T** dptr) {
     return ROD_OK;
 }
 
+static void tile_starts(const std::vector<Tile>& tl, int n_images, std::vector<int>& st) {
+    st.assign(n_images + 1, (int)tl.size());
+    for (int t = (int)tl.size() - 1; t >= 0; --t) st[tl[t].img] = t;
+    for (int i = n_images - 1; i >= 0; --i) st[i] = std::min(st[i], st[i + 1]);
+}
+
 int ensure_lowres_tables(rod_plan* plan, double factor) {
     if (plan->d_shapes != nullptr && plan->lowres_factor == factor) return ROD_OK;
     if (!(factor > 0.0) || factor > 1.0) return ROD_ERR_UNSUPPORTED;
@@ -30,24 +36,38 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     std::vector<DevShape> shapes(plan->shapes.size());
     bool all_identity = true;
     int max_rows = 1, max_cols = 1;
+    size_t x2_smem = 0;
     for (size_t s = 0; s < plan->shapes.size(); ++s) {
         const int h = plan->shapes[s].h, w = plan->shapes[s].w;
         if (!build_lowres_shape(h, w, factor, kMaxAreaTaps, blob, &shapes[s])) return ROD_ERR_UNSUPPORTED;
-        const DevShape& sh = shapes[s];
+        DevShape& sh = shapes[s];
         if (sh.lin_identity) continue;
         all_identity = false;
+        x2_smem = std::max(x2_smem, choose_strip_rows(&sh, blob.data()));
+        if (sh.strip_rows > 0) continue;
         int rows, cols;
         lowres_tile_footprint(sh, blob.data(), kLowresTH, kLowresTWB, &rows, &cols);
         max_rows = std::max(max_rows, rows);
         max_cols = std::max(max_cols, cols);
     }
     if (blob.empty()) blob.push_back(0);
-    if (plan->d_shapes) { cudaFree(plan->d_shapes); plan->d_shapes = nullptr; }
-    if (plan->d_tab) { cudaFree(plan->d_tab); plan->d_tab = nullptr; }
+    std::vector<Tile> gen_tiles, x2_tiles;
+    build_strip_tiles(plan->h_images, shapes, false, kLowresTH, kLowresTWB, gen_tiles);
+    build_strip_tiles(plan->h_images, shapes, true, kLowresTH, kLowresTWB, x2_tiles);
+    void* old[] = {plan->d_shapes, plan->d_tab, plan->d_lowres_tiles, plan->d_lowres_x2_tiles};
+    for (void* q : old)
+        if (q) cudaFree(q);
+    plan->d_shapes = nullptr; plan->d_tab = nullptr; plan->d_lowres_tiles = nullptr; plan->d_lowres_x2_tiles = nullptr;
     int rc = upload(shapes, &plan->d_shapes);
+    if (rc == ROD_OK) rc = upload(blob, &plan->d_tab);
+    if (rc == ROD_OK) rc = upload(gen_tiles, &plan->d_lowres_tiles);
+    if (rc == ROD_OK) rc = upload(x2_tiles, &plan->d_lowres_x2_tiles);
     if (rc != ROD_OK) return rc;
-    rc = upload(blob, &plan->d_tab);
-    if (rc != ROD_OK) return rc;
+    plan->n_lowres_tiles = (int)gen_tiles.size();
+    plan->n_lowres_x2_tiles = (int)x2_tiles.size();
+    tile_starts(gen_tiles, plan->n_images, plan->lowres_tile_start);
+    tile_starts(x2_tiles, plan->n_images, plan->lowres_x2_tile_start);
+    plan->lowres_x2_smem = x2_smem;
     plan->lowres_factor = factor;
     plan->lowres_all_identity = all_identity;
     plan->lowres_half_rows = max_rows;
@@ -150,10 +170,9 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
         plan->dst_extent = std::max<uint64_t>(plan->dst_extent, d.dst_offset + (uint64_t)(d.height - 1) * d.dst_pitch + 3ull * d.width);
     }
     plan->payload_bytes = elem;
-    std::vector<Tile> nt, bt, lt;
+    std::vector<Tile> nt, bt;
     build_noise_tiles(plan->h_images, kNoiseSpan, nt);
     build_blur_tiles(plan->h_images, kBlurRowsPerTile, bt);
-    build_grid_tiles(plan->h_images, kLowresTH, kLowresTWB, lt);
     auto starts = [&](const std::vector<Tile>& tl, std::vector<int>& st) {
         st.assign(n_images + 1, (int)tl.size());
         for (int t = (int)tl.size() - 1; t >= 0; --t) st[tl[t].img] = t;
@@ -161,7 +180,6 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
     };
     starts(nt, plan->noise_tile_start);
     starts(bt, plan->blur_tile_start);
-    starts(lt, plan->lowres_tile_start);
     for (int i = 1; i < n_images; ++i) {
         const rod_image_desc& a = images[i - 1];
         const rod_image_desc& b = images[i];
@@ -171,11 +189,9 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
     }
     plan->n_noise_tiles = (int)nt.size();
     plan->n_blur_tiles = (int)bt.size();
-    plan->n_lowres_tiles = (int)lt.size();
     int rc = upload(plan->h_images, &plan->d_images);
     if (rc == ROD_OK) rc = upload(nt, &plan->d_noise_tiles);
     if (rc == ROD_OK) rc = upload(bt, &plan->d_blur_tiles);
-    if (rc == ROD_OK) rc = upload(lt, &plan->d_lowres_tiles);
     if (rc != ROD_OK) { rod_plan_destroy(plan); return rc; }
     *out_plan = plan;
     return ROD_OK;
@@ -183,7 +199,7 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
 
 extern "C" void rod_plan_destroy(rod_plan* plan) {
     if (plan == nullptr) return;
-    void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_shapes,
+    void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles, plan->d_shapes,
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};
     for (void* p : ptrs)

@@ -59,6 +59,8 @@ struct DevShape {
     float inv_area;             // float(1 / (ix*iy))
     int32_t lin_identity;       // 1 when (nh, nw) == (h, w): the INTER_LINEAR step is a copy
     int32_t x2;                 // 1 when w == 2 * nw: exact 2x on the x axis (closed-form coefficients)
+    int32_t strip_rows;         // x2 kernel: output rows per strip (multiple of 8)
+    int32_t strip_half_rows;    // x2 kernel: worst-case low-res rows one strip touches
 };
 
 // ---------------------------------------------------------------------------------
@@ -322,6 +324,96 @@ ROD_HD uint32_t linear_h4(uint32_t s0v, uint32_t s1v, uint32_t a_packed) {
 // Vertical stage + pack: (((b0*h0) >> 16) + ((b1*h1) >> 16) + 2) >> 2.
 ROD_HD uint32_t linear_v(uint32_t h0, uint32_t h1, uint32_t b_packed) {
     return ((((b_packed & 0xFFFFu) * h0) >> 16) + (((b_packed >> 16) * h1) >> 16) + 2u) >> 2;
+}
+
+// ---------------------------------------------------------------------------------
+// a5 fast path for exact-2x widths (w == 2 * nw).  OpenCV's x coefficients are then
+// (2048,0) at x = 0 and x = w-1 and otherwise (1536,512) for odd x = 2i+1 (taps i, i+1) and
+// (512,1536) for even x = 2i+2 (taps i, i+1), so the horizontal stage is hx = 32 * q with
+// q = 3A + B or A + 3B, and ((b * hx) >> 16) == floor(b * q / 2048).
+//
+// One "chunk" = 8 output pixels x = 8m .. 8m+7 (24 bytes) needs the six low-res pixels
+// p0..p5 = P[4m-1 .. 4m+4] (18 bytes; P[-1] := P[0], P[nw] := P[nw-1] are replicated by the
+// producer).  win[] holds those 18 bytes starting at byte 0 of win[0].
+// x[t] = float(2^23 + q[t]) for the 24 output bytes t = 3 * pixel + channel.
+// ---------------------------------------------------------------------------------
+ROD_HD uint32_t dot2_lo(uint32_t w16x2, uint32_t bytes, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+    return __dp2a_lo(w16x2, bytes, acc);
+#else
+    return acc + (w16x2 & 0xFFFFu) * (bytes & 0xFFu) + (w16x2 >> 16) * ((bytes >> 8) & 0xFFu);
+#endif
+}
+ROD_HD uint32_t dot2_hi(uint32_t w16x2, uint32_t bytes, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+    return __dp2a_hi(w16x2, bytes, acc);
+#else
+    return acc + (w16x2 & 0xFFFFu) * ((bytes >> 16) & 0xFFu) + (w16x2 >> 16) * (bytes >> 24);
+#endif
+}
+// bytes (a, a+3, a+1, a+4) of the window, a = 3 * pair + c: [A_c, B_c, A_c+1, B_c+1]
+ROD_HD uint32_t x2_gather(const uint32_t* win, int a) {
+#if defined(__CUDA_ARCH__)
+    const int k = a >> 2, o = a & 3;  // all four bytes lie in win[k], win[k+1]
+    return __byte_perm(win[k], win[k + 1], (o) | ((o + 3) << 4) | ((o + 1) << 8) | ((o + 4) << 12));
+#else
+    const uint8_t* b = (const uint8_t*)win;
+    return (uint32_t)b[a] | ((uint32_t)b[a + 3] << 8) | ((uint32_t)b[a + 1] << 16) | ((uint32_t)b[a + 4] << 24);
+#endif
+}
+ROD_HD void x2_expand24(const uint32_t win[5], float x[24]) {
+    const uint32_t W31 = 3u | (1u << 16), W13 = 1u | (3u << 16), M = 0x4B000000u;
+    // pair m = (p_m, p_m+1); channels handled two at a time: (0,1) from one gather, (2, next pair's 0) from another
+    // outputs: pair0 -> px0 (1,3); pair1 -> px1 (3,1), px2 (1,3); pair2 -> px3, px4; pair3 -> px5, px6; pair4 -> px7 (3,1)
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        const uint32_t g01 = x2_gather(win, 3 * m);      // channels 0,1 of pair m
+        const uint32_t g2x = x2_gather(win, 3 * m + 2);  // channel 2 of pair m (and channel 0 of pair m+1, unused)
+        const int podd = 2 * m - 1, peven = 2 * m;       // output pixels fed by pair m
+        if (podd >= 0) {
+            x[3 * podd + 0] = bitsf(dot2_lo(W31, g01, M));
+            x[3 * podd + 1] = bitsf(dot2_hi(W31, g01, M));
+            x[3 * podd + 2] = bitsf(dot2_lo(W31, g2x, M));
+        }
+        if (peven < 8) {
+            x[3 * peven + 0] = bitsf(dot2_lo(W13, g01, M));
+            x[3 * peven + 1] = bitsf(dot2_hi(W13, g01, M));
+            x[3 * peven + 2] = bitsf(dot2_lo(W13, g2x, M));
+        }
+    }
+}
+
+// Per-output-row constants of the float vertical stage (b0, b1 = 11-bit y coefficients).
+struct X2Row {
+    float c0s, c1s;   // b0 * 2^-11, b1 * 2^-11
+    float k0;         // 2^23 - b0 * 4096
+    float negc1;      // -b1 * 4096
+};
+ROD_HD X2Row x2_row_consts(uint32_t b_packed) {
+    X2Row r;
+    const float b0 = (float)(b_packed & 0xFFFFu), b1 = (float)(b_packed >> 16);
+    r.c0s = b0 * 4.8828125e-4f;
+    r.c1s = b1 * 4.8828125e-4f;
+    r.k0 = 8388608.0f - b0 * 4096.0f;
+    r.negc1 = -b1 * 4096.0f;
+    return r;
+}
+// out = (floor(b0*q0/2048) + floor(b1*q1/2048) + 2) >> 2 with x = 2^23 + q, all in fp32 with
+// round-toward-zero fused multiply-adds (every intermediate is an exact integer + 2^23).
+ROD_HD uint32_t x2_vertical(float x0, float x1, const X2Row& r) {
+#if defined(__CUDA_ARCH__)
+    const float y1 = __fmaf_rz(x0, r.c0s, r.k0);         // 2^23 + F0
+    const float z = __fadd_rn(y1, r.negc1);              // exact
+    const float y2 = __fmaf_rz(x1, r.c1s, z);            // 2^23 + F0 + F1
+    const float o = __fmaf_rz(y2, 0.25f, 6291456.5f);    // 2^23 + ((F0 + F1 + 2) >> 2)
+    return __float_as_uint(o);                           // low byte is the result
+#else
+    const double y1 = floor((double)x0 * r.c0s + r.k0);
+    const double z = y1 + r.negc1;
+    const double y2 = floor((double)x1 * r.c1s + z);
+    const double o = floor(y2 * 0.25 + 6291456.5);
+    return fbits((float)o);
+#endif
 }
 
 // Detector-input normalisation: half(float(u8) / 255.f) is done with __float2half_rn on

@@ -51,7 +51,10 @@ struct rod_plan {
     rod::Tile* d_lowres_tiles = nullptr;
     int n_noise_tiles = 0, n_blur_tiles = 0, n_lowres_tiles = 0;
     // tiles of image i are [start[i], start[i+1]) in each list (lists are in image order)
-    std::vector<int> noise_tile_start, blur_tile_start, lowres_tile_start;
+    std::vector<int> noise_tile_start, blur_tile_start, lowres_tile_start, lowres_x2_tile_start;
+    rod::Tile* d_lowres_x2_tiles = nullptr;
+    int n_lowres_x2_tiles = 0;
+    size_t lowres_x2_smem = 0;
     bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
 
     // lowres tables, rebuilt when the factor changes

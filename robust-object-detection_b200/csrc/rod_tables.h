@@ -152,6 +152,51 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
     return true;
 }
 
+// Exact-2x shapes are processed in full-width strips (lowres_x2_kernel).  Pick the strip height that
+// fills the 256-thread CTA best: items = (strip_rows / 8) * ceil(w / 8); fewer apron rows is better too.
+// Sets sh->strip_rows / strip_half_rows (0 = use the generic tiled kernel) and returns the shared bytes.
+inline size_t choose_strip_rows(DevShape* sh, const uint32_t* blob, size_t max_smem = 100 * 1024) {
+    sh->strip_rows = 0;
+    sh->strip_half_rows = 0;
+    if (!sh->x2 || sh->lin_identity) return 0;
+    const size_t pitch = (size_t)((3 * sh->nw + 24 + 15) & ~15);
+    const uint32_t* ly = blob + sh->ly_s;
+    const int nchunks = (sh->w + 7) / 8;
+    double best = -1.0;
+    size_t best_smem = 0;
+    for (int R = 16; R <= 64; R += 8) {
+        int nj = 1;
+        for (int y0 = 0; y0 < sh->h; y0 += R) {
+            const int y1 = std::min(sh->h, y0 + R) - 1;
+            nj = std::max(nj, (int)(ly[y1] >> 16) - (int)(ly[y0] & 0xFFFF) + 1);
+        }
+        const size_t smem = (size_t)nj * pitch;
+        if (smem > max_smem) continue;
+        const int rows = std::min(R, sh->h);
+        const int items = ((rows + 7) / 8) * nchunks;
+        const double fill = (double)items / (double)(((items + 255) / 256) * 256);
+        const double apron = (double)rows / (2.0 * nj);  // useful low-res rows / computed low-res rows (for 0.5x)
+        const double score = fill * std::min(1.0, apron);
+        if (score > best + 1e-9) { best = score; sh->strip_rows = R; sh->strip_half_rows = nj; best_smem = smem; }
+    }
+    return best_smem;
+}
+
+inline void build_strip_tiles(const std::vector<DevImage>& imgs, const std::vector<DevShape>& shapes, bool want_x2,
+                              int th, int twb, std::vector<Tile>& tiles) {
+    for (int i = 0; i < (int)imgs.size(); ++i) {
+        const DevShape& sh = shapes[imgs[i].shape_id];
+        const bool is_x2 = sh.strip_rows > 0;
+        if (is_x2 != want_x2) continue;
+        if (is_x2) {
+            for (int y = 0; y < imgs[i].h; y += sh.strip_rows) tiles.push_back(Tile{i, y, 0, 0});
+        } else {
+            for (int y = 0; y < imgs[i].h; y += th)
+                for (int b = 0; b < 3 * imgs[i].w; b += twb) tiles.push_back(Tile{i, y, b, 0});
+        }
+    }
+}
+
 // Ultralytics 8.3.x LetterBox geometry (auto=False, scaleup=True, center=True).
 inline void letterbox_geometry(int h, int w, int out_h, int out_w, int* new_h, int* new_w, int* top, int* left) {
     double r = std::min((double)out_h / h, (double)out_w / w);

@@ -75,8 +75,8 @@ extern "C" int emu_blur(const uint8_t* src, uint8_t* dst, int h, int w, long src
 // Replays lowres_kernel for one image: same tiling (kLowresTH rows x kLowresTWB byte columns), same
 // phase B variants (vector exact-2x units / generic), C1 (closed form / table) and C2 (marching).
 // `src_phase`: emulated address phase of the source (the vector path needs 4-byte alignment).
-extern "C" int emu_lowres(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
-                          double factor, int src_phase) {
+static int emu_lowres_generic(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
+                              double factor, int src_phase) {
     std::vector<uint32_t> blob;
     DevShape sh;
     if (!build_lowres_shape(h, w, factor, 8, blob, &sh)) return 2;
@@ -207,6 +207,118 @@ extern "C" int emu_lowres(const uint8_t* src, uint8_t* dst, int h, int w, long s
             }
         }
     return 0;
+}
+
+// Replays lowres_x2_kernel (full-width strips of exact-2x shapes).
+static int emu_lowres_x2(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
+                         const DevShape& sh, const uint32_t* tab, int src_phase) {
+    const int n = 3 * w, nw = sh.nw;
+    const int p_pitch = (3 * nw + 24 + 15) & ~15;
+    const uint32_t* ly_s = tab + sh.ly_s;
+    const uint32_t* ly_b = tab + sh.ly_b;
+    std::vector<uint32_t> smem_words((size_t)sh.strip_half_rows * p_pitch / 4 + 8);
+    uint8_t* smem = (uint8_t*)smem_words.data();
+    for (int y0 = 0; y0 < h; y0 += sh.strip_rows) {
+        const int th = std::min(sh.strip_rows, h - y0);
+        const int j_lo = (int)(ly_s[y0] & 0xFFFFu), j_hi = (int)(ly_s[y0 + th - 1] >> 16);
+        const int nj = j_hi - j_lo + 1;
+        if (nj > sh.strip_half_rows) return 6;
+        memset(smem, 0xEE, (size_t)sh.strip_half_rows * p_pitch);
+        const bool vec = (sh.area_mode == AREA_FAST2 || sh.area_mode == AREA_GENERAL) && (w & 3) == 0 &&
+                         (((long)src_phase | src_pitch) & 3) == 0;
+        if (vec) {
+            const int n_units = nw >> 1;
+            const uint32_t magic_div = 0xFFFFFFFFu / (uint32_t)n_units + 1u;
+            const int total = nj * n_units;
+            for (int idx = 0; idx < total; ++idx) {
+                const int jr = (n_units == 1) ? idx : (int)mulhi32((uint32_t)idx, magic_div);
+                const int u = idx - jr * n_units;
+                if (jr != idx / n_units) return 7;
+                const int dy = j_lo + jr, sb = 12 * u;
+                uint32_t o6[6];
+                if (sh.area_mode == AREA_FAST2) {
+                    uint32_t ra[3], rb[3];
+                    memcpy(ra, src + (long)(2 * dy) * src_pitch + sb, 12);
+                    memcpy(rb, src + (long)(2 * dy + 1) * src_pitch + sb, 12);
+                    area_fast2_unit(ra, rb, o6);
+                } else {
+                    const int32_t* yfirst = (const int32_t*)(tab + sh.ay_first);
+                    const int32_t* ycount = (const int32_t*)(tab + sh.ay_count);
+                    const float* beta = (const float*)(tab + sh.ay_alpha) + dy * sh.yt;
+                    float acc[6];
+                    for (int ty = 0; ty < ycount[dy]; ++ty) {
+                        uint32_t rw[3];
+                        memcpy(rw, src + (long)(yfirst[dy] + ty) * src_pitch + sb, 12);
+                        area_x2f_accumulate(rw, beta[ty], ty == 0, acc);
+                    }
+                    area_x2f_finish(acc, o6);
+                }
+                uint8_t* prow = smem + jr * p_pitch;
+                for (int q = 0; q < 6; ++q) prow[4 + 6 * u + q] = (uint8_t)o6[q];
+                if (u == 0) { prow[1] = (uint8_t)o6[0]; prow[2] = (uint8_t)o6[1]; prow[3] = (uint8_t)o6[2]; }
+                if (u == n_units - 1) {
+                    prow[4 + 3 * nw] = (uint8_t)o6[3]; prow[5 + 3 * nw] = (uint8_t)o6[4]; prow[6 + 3 * nw] = (uint8_t)o6[5];
+                }
+            }
+        } else {
+            const int total = nj * 3 * nw;
+            for (int idx = 0; idx < total; ++idx) {
+                const int jr = idx / (3 * nw), o = idx - jr * 3 * nw;
+                const int i = o / 3, c = o - 3 * i;
+                const uint8_t v = (uint8_t)area_value(src, src_pitch, sh, tab, j_lo + jr, i, c);
+                uint8_t* prow = smem + jr * p_pitch;
+                prow[4 + o] = v;
+                if (i == 0) prow[1 + c] = v;
+                if (i == nw - 1) prow[4 + 3 * nw + c] = v;
+            }
+        }
+        const int nchunks = (w + 7) >> 3, ngroups = (th + 7) >> 3;
+        const uint32_t magic_div = 0xFFFFFFFFu / (uint32_t)nchunks + 1u;
+        for (int idx = 0; idx < ngroups * nchunks; ++idx) {
+            const int rg = (nchunks == 1) ? idx : (int)mulhi32((uint32_t)idx, magic_div);
+            const int ch = idx - rg * nchunks;
+            if (rg != idx / nchunks) return 8;
+            const int nvalid = std::min(24, n - 24 * ch);
+            float xe[24], xo[24];
+            int je = -1, jo = -1;
+            auto load_row = [&](int j, float* x) {
+                const uint32_t* wq = (const uint32_t*)(smem + (j - j_lo) * p_pitch) + 3 * ch;
+                uint32_t win[5];
+                for (int k = 0; k < 5; ++k) win[k] = funnel_r(wq[k], wq[k + 1], 8);
+                x2_expand24(win, x);
+            };
+            const int r_end = std::min(th, 8 * rg + 8);
+            for (int r = 8 * rg; r < r_end; ++r) {
+                const uint32_t ys = ly_s[y0 + r];
+                const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+                const X2Row rc = x2_row_consts(ly_b[y0 + r]);
+                if ((s0 & 1) ? (jo != s0) : (je != s0)) { if (s0 & 1) { load_row(s0, xo); jo = s0; } else { load_row(s0, xe); je = s0; } }
+                if ((s1 & 1) ? (jo != s1) : (je != s1)) { if (s1 & 1) { load_row(s1, xo); jo = s1; } else { load_row(s1, xe); je = s1; } }
+                const float* xlo = (s0 & 1) ? xo : xe;
+                const float* xhi = (s1 & 1) ? xo : xe;
+                for (int t = 0; t < nvalid; ++t)
+                    dst[(long)(y0 + r) * dst_pitch + 24 * ch + t] = (uint8_t)(x2_vertical(xlo[t], xhi[t], rc) & 0xFFu);
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int emu_lowres(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
+                          double factor, int src_phase) {
+    std::vector<uint32_t> blob;
+    DevShape sh;
+    if (!build_lowres_shape(h, w, factor, 8, blob, &sh)) return 2;
+    if (blob.empty()) blob.push_back(0);
+    choose_strip_rows(&sh, blob.data());
+    if (sh.strip_rows > 0) return emu_lowres_x2(src, dst, h, w, src_pitch, dst_pitch, sh, blob.data(), src_phase);
+    return emu_lowres_generic(src, dst, h, w, src_pitch, dst_pitch, factor, src_phase);
+}
+
+// The generic tiled kernel on any shape (exact-2x shapes included), for coverage of both kernels.
+extern "C" int emu_lowres_tiled(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
+                                double factor, int src_phase) {
+    return emu_lowres_generic(src, dst, h, w, src_pitch, dst_pitch, factor, src_phase);
 }
 
 // Replays noise_kernel (compat / philox / field) over one image's flat element range.

@@ -24,6 +24,7 @@ def emu(tmp_path_factory):
     u8p, f32p = ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_float)
     lib.emu_blur.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int]
     lib.emu_lowres.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_int]
+    lib.emu_lowres_tiled.argtypes = lib.emu_lowres.argtypes
     lib.emu_noise.argtypes = [u8p, u8p, f32p, f32p, ctypes.c_long, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
     lib.emu_letterbox_u8.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return lib
@@ -56,9 +57,11 @@ def test_emu_lowres(emu, factor):
         want = orc.apply_lowres(img, factor)
         for phase in (0, 7):
             got = np.zeros_like(img)
-            rc = emu.emu_lowres(_p(img), _p(got), h, w, 3 * w, 3 * w, factor, phase)
-            assert rc == 0, (h, w, factor, rc)
-            assert np.array_equal(got, want), (h, w, factor, phase)
+            for fn in (emu.emu_lowres, emu.emu_lowres_tiled):
+                got[:] = 0
+                rc = fn(_p(img), _p(got), h, w, 3 * w, 3 * w, factor, phase)
+                assert rc == 0, (h, w, factor, rc)
+                assert np.array_equal(got, want), (h, w, factor, phase)
 
 
 def test_emu_lowres_visdrone_shape(emu):
@@ -66,6 +69,11 @@ def test_emu_lowres_visdrone_shape(emu):
     got = np.zeros_like(img)
     assert emu.emu_lowres(_p(img), _p(got), 765, 1360, 4080, 4080, 0.5, 0) == 0
     assert np.array_equal(got, orc.apply_lowres(img, 0.5))
+    for h, w in [(1080, 1920), (540, 962), (333, 1916)]:
+        img = synth(h + w, h, w)
+        got = np.zeros_like(img)
+        assert emu.emu_lowres(_p(img), _p(got), h, w, 3 * w, 3 * w, 0.5, 0) == 0
+        assert np.array_equal(got, orc.apply_lowres(img, 0.5)), (h, w)
 
 
 def test_emu_noise_compat_and_philox(emu):
