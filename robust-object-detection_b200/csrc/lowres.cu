@@ -137,9 +137,9 @@ __global__ void __launch_bounds__(256, 3) lowres_kernel(LowresParams p) {
                         uint32_t r8[6];
                         area_x2f_finish(acc, r8);
                         uint16_t* o16 = reinterpret_cast<uint16_t*>(prow + 6 * u);
-                        o16[0] = (uint16_t)(r8[0] | (r8[1] << 8));
-                        o16[1] = (uint16_t)(r8[2] | (r8[3] << 8));
-                        o16[2] = (uint16_t)(r8[4] | (r8[5] << 8));
+                        o16[0] = (uint16_t)__byte_perm(r8[0], r8[1], 0x0040);
+                        o16[1] = (uint16_t)__byte_perm(r8[2], r8[3], 0x0040);
+                        o16[2] = (uint16_t)__byte_perm(r8[4], r8[5], 0x0040);
                     }
                 }
             }
@@ -309,53 +309,59 @@ __global__ void __launch_bounds__(256, 2) lowres_x2_kernel(LowresX2Params p) {
         const int j_lo = (int)(ly_s[y0] & 0xFFFFu), j_hi = (int)(ly_s[y0 + th - 1] >> 16);
         const int nj = j_hi - j_lo + 1;
 
-        // ---- phase B
-        const bool vec = (sh.area_mode == AREA_FAST2 || sh.area_mode == AREA_GENERAL) && (im.w & 3) == 0 &&
-                         ((((uintptr_t)simg) | (uintptr_t)im.src_pitch) & 3) == 0;
+        // ---- phase B: two (low-res row, 12-byte unit) items per thread per step, all loads issued first
+        const bool vec = (im.w & 3) == 0 && ((((uintptr_t)simg) | (uintptr_t)im.src_pitch) & 3) == 0 &&
+                         (sh.area_mode == AREA_FAST2 || (sh.area_mode == AREA_GENERAL && sh.ay_packed));
         if (vec) {
             const int n_units = nw >> 1;
             const uint32_t magic_div = 0xFFFFFFFFu / (uint32_t)n_units + 1u;  // floor(idx / n_units) = umulhi(idx, magic)
             const int total = nj * n_units;
-            const int32_t* yfirst = reinterpret_cast<const int32_t*>(p.tab + sh.ay_first);
-            const int32_t* ycount = reinterpret_cast<const int32_t*>(p.tab + sh.ay_count);
-            const float* yalpha = reinterpret_cast<const float*>(p.tab + sh.ay_alpha);
             const bool fast2 = (sh.area_mode == AREA_FAST2);
-            for (int idx = threadIdx.x; idx < total; idx += 256) {
-                const int jr = (n_units == 1) ? idx : (int)__umulhi((uint32_t)idx, magic_div);
-                const int u = idx - jr * n_units;
-                const int dy = j_lo + jr;
-                const int sb = 12 * u;
-                uint32_t o6[6];
-                if (fast2) {
-                    const uint8_t* r0 = simg + (int64_t)(2 * dy) * im.src_pitch + sb;
+            const uint4* ypack = reinterpret_cast<const uint4*>(p.tab + sh.ay_pack);
+            for (int base = threadIdx.x; base < total; base += 512) {
+                uint32_t rw[2][3][3];
+                float beta[2][3];
+                int jrs[2], us[2];
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int idx = (base + 256 * it < total) ? base + 256 * it : base;  // tail: redo item 0, dropped below
+                    const int jr = (n_units == 1) ? idx : (int)__umulhi((uint32_t)idx, magic_div);
+                    const int u = idx - jr * n_units;
+                    const int dy = j_lo + jr;
+                    jrs[it] = jr; us[it] = u;
+                    int sy0 = 2 * dy;
+                    beta[it][0] = beta[it][1] = beta[it][2] = 0.f;
+                    if (!fast2) {
+                        const uint4 pk = __ldg(ypack + dy);
+                        sy0 = (int)pk.x;
+                        beta[it][0] = __uint_as_float(pk.y); beta[it][1] = __uint_as_float(pk.z); beta[it][2] = __uint_as_float(pk.w);
+                    }
+                    const uint8_t* r0 = simg + (int64_t)sy0 * im.src_pitch + 12 * u;
                     const uint8_t* r1 = r0 + im.src_pitch;
-                    const uint32_t ra[3] = {ldg32(r0), ldg32(r0 + 4), ldg32(r0 + 8)};
-                    const uint32_t rb[3] = {ldg32(r1), ldg32(r1 + 4), ldg32(r1 + 8)};
-                    area_fast2_unit(ra, rb, o6);
-                } else {
-                    const int sy0 = yfirst[dy], ny = ycount[dy];
-                    const float* beta = yalpha + dy * sh.yt;
-                    const uint8_t* r = simg + (int64_t)sy0 * im.src_pitch + sb;
-                    float acc[6];
-                    {
-                        const uint32_t rw[3] = {ldg32(r), ldg32(r + 4), ldg32(r + 8)};
-                        area_x2f_accumulate(rw, beta[0], true, acc);
+                    rw[it][0][0] = ldg32(r0); rw[it][0][1] = ldg32(r0 + 4); rw[it][0][2] = ldg32(r0 + 8);
+                    rw[it][1][0] = ldg32(r1); rw[it][1][1] = ldg32(r1 + 4); rw[it][1][2] = ldg32(r1 + 8);
+                    if (!fast2) {  // third tap: weight 0 (and a clamped row) when this low-res row has two taps only
+                        const uint8_t* r2 = simg + (int64_t)min(sy0 + 2, im.h - 1) * im.src_pitch + 12 * u;
+                        rw[it][2][0] = ldg32(r2); rw[it][2][1] = ldg32(r2 + 4); rw[it][2][2] = ldg32(r2 + 8);
                     }
-                    for (int ty = 1; ty < ny; ++ty) {
-                        r += im.src_pitch;
-                        const uint32_t rw[3] = {ldg32(r), ldg32(r + 4), ldg32(r + 8)};
-                        area_x2f_accumulate(rw, beta[ty], false, acc);
-                    }
-                    area_x2f_finish(acc, o6);
                 }
-                uint8_t* prow = smem + jr * p_pitch;
-                uint16_t* o16 = reinterpret_cast<uint16_t*>(prow + 4 + 6 * u);
-                o16[0] = (uint16_t)(o6[0] | (o6[1] << 8));
-                o16[1] = (uint16_t)(o6[2] | (o6[3] << 8));
-                o16[2] = (uint16_t)(o6[4] | (o6[5] << 8));
-                if (u == 0) { prow[1] = (uint8_t)o6[0]; prow[2] = (uint8_t)o6[1]; prow[3] = (uint8_t)o6[2]; }
-                if (u == n_units - 1) {
-                    prow[4 + 3 * nw] = (uint8_t)o6[3]; prow[5 + 3 * nw] = (uint8_t)o6[4]; prow[6 + 3 * nw] = (uint8_t)o6[5];
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    if (it == 1 && base + 256 >= total) break;
+                    uint32_t o6[6];
+                    if (fast2) {
+                        area_fast2_unit(rw[it][0], rw[it][1], o6);
+                    } else {
+                        float acc[6];
+                        area_x2f_accumulate(rw[it][0], beta[it][0], true, acc);
+                        area_x2f_accumulate(rw[it][1], beta[it][1], false, acc);
+                        area_x2f_accumulate(rw[it][2], beta[it][2], false, acc);
+                        area_x2f_finish(acc, o6);
+                    }
+                    uint16_t* o16 = reinterpret_cast<uint16_t*>(smem + jrs[it] * p_pitch + 4 + 6 * us[it]);
+                    o16[0] = (uint16_t)__byte_perm(o6[0], o6[1], 0x0040);
+                    o16[1] = (uint16_t)__byte_perm(o6[2], o6[3], 0x0040);
+                    o16[2] = (uint16_t)__byte_perm(o6[4], o6[5], 0x0040);
                 }
             }
         } else {
@@ -363,12 +369,16 @@ __global__ void __launch_bounds__(256, 2) lowres_x2_kernel(LowresX2Params p) {
             for (int idx = threadIdx.x; idx < total; idx += 256) {
                 const int jr = idx / (3 * nw), o = idx - jr * 3 * nw;
                 const int i = o / 3, c = o - 3 * i;
-                const uint8_t v = (uint8_t)area_value(simg, im.src_pitch, sh, p.tab, j_lo + jr, i, c);
-                uint8_t* prow = smem + jr * p_pitch;
-                prow[4 + o] = v;
-                if (i == 0) prow[1 + c] = v;
-                if (i == nw - 1) prow[4 + 3 * nw + c] = v;
+                smem[jr * p_pitch + 4 + o] = (uint8_t)area_value(simg, im.src_pitch, sh, p.tab, j_lo + jr, i, c);
             }
+        }
+        __syncthreads();
+        // replicate the border pixels: P[-1] := P[0], P[nw] := P[nw-1] (OpenCV's clamped x taps)
+        for (int q = threadIdx.x; q < nj * 6; q += 256) {
+            const int jr = q / 6, kk = q - 6 * jr;
+            uint8_t* prow = smem + jr * p_pitch;
+            if (kk < 3) prow[1 + kk] = prow[4 + kk];
+            else prow[4 + 3 * nw + (kk - 3)] = prow[4 + 3 * (nw - 1) + (kk - 3)];
         }
         __syncthreads();
 

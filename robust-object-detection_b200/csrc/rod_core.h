@@ -61,6 +61,8 @@ struct DevShape {
     int32_t x2;                 // 1 when w == 2 * nw: exact 2x on the x axis (closed-form coefficients)
     int32_t strip_rows;         // x2 kernel: output rows per strip (multiple of 8)
     int32_t strip_half_rows;    // x2 kernel: worst-case low-res rows one strip touches
+    uint32_t ay_pack;           // x2 kernel, yt <= 3: uint4 per low-res row {first source row, beta0, beta1, beta2 bits}
+    int32_t ay_packed;          // 1 when ay_pack is valid
 };
 
 // ---------------------------------------------------------------------------------
@@ -304,15 +306,18 @@ ROD_HD void area_x2f_accumulate(const uint32_t r[3], float beta, bool first, flo
     const uint32_t magic[6] = {0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u};
     uint32_t s[6];
     pair_sums12(r[0], r[1], r[2], magic, s);  // float bits of 2^23 + (S0 + S1)
+    // beta * (x - 2^23) == fma(x, beta, -beta * 2^23): the fma is exact before its single rounding and
+    // beta * 2^23 is exact, so this is fl(beta * S) -- the same value as the separate convert + multiply.
+    const float nb = fmul(beta, -8388608.0f);
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
-        const float prod = fmul(beta, fadd(bitsf(s[q]), -8388608.0f));
+        const float prod = fmaf(bitsf(s[q]), beta, nb);
         acc[q] = first ? prod : fadd(acc[q], prod);
     }
 }
 ROD_HD void area_x2f_finish(const float acc[6], uint32_t out6[6]) {
 #pragma unroll
-    for (int q = 0; q < 6; ++q) out6[q] = fbits(fmaf(acc[q], 0.5f, 12582912.0f)) & 0xFFu;
+    for (int q = 0; q < 6; ++q) out6[q] = fbits(fmaf(acc[q], 0.5f, 12582912.0f));  // result in the low byte
 }
 
 // ---------------------------------------------------------------------------------
@@ -335,7 +340,8 @@ ROD_HD uint32_t linear_v(uint32_t h0, uint32_t h1, uint32_t b_packed) {
 // One "chunk" = 8 output pixels x = 8m .. 8m+7 (24 bytes) needs the six low-res pixels
 // p0..p5 = P[4m-1 .. 4m+4] (18 bytes; P[-1] := P[0], P[nw] := P[nw-1] are replicated by the
 // producer).  win[] holds those 18 bytes starting at byte 0 of win[0].
-// x[t] = float(2^23 + q[t]) for the 24 output bytes t = 3 * pixel + channel.
+// x[t] = float(2^22 + q[t]) for the 24 output bytes t = 3 * pixel + channel (the float's mantissa step is
+// 0.5 there, so the dot products use doubled weights and the bit pattern 0x4A800000 + 2q).
 // ---------------------------------------------------------------------------------
 ROD_HD uint32_t dot2_lo(uint32_t w16x2, uint32_t bytes, uint32_t acc) {
 #if defined(__CUDA_ARCH__)
@@ -362,7 +368,7 @@ ROD_HD uint32_t x2_gather(const uint32_t* win, int a) {
 #endif
 }
 ROD_HD void x2_expand24(const uint32_t win[5], float x[24]) {
-    const uint32_t W31 = 3u | (1u << 16), W13 = 1u | (3u << 16), M = 0x4B000000u;
+    const uint32_t W31 = 6u | (2u << 16), W13 = 2u | (6u << 16), M = 0x4A800000u;
     // pair m = (p_m, p_m+1); channels handled two at a time: (0,1) from one gather, (2, next pair's 0) from another
     // outputs: pair0 -> px0 (1,3); pair1 -> px1 (3,1), px2 (1,3); pair2 -> px3, px4; pair3 -> px5, px6; pair4 -> px7 (3,1)
 #pragma unroll
@@ -383,36 +389,35 @@ ROD_HD void x2_expand24(const uint32_t win[5], float x[24]) {
     }
 }
 
-// Per-output-row constants of the float vertical stage (b0, b1 = 11-bit y coefficients).
+// Per-output-row constants of the float vertical stage (b0, b1 = 11-bit y coefficients, <= 2048).
 struct X2Row {
     float c0s, c1s;   // b0 * 2^-11, b1 * 2^-11
-    float k0;         // 2^23 - b0 * 4096
-    float negc1;      // -b1 * 4096
+    float k0;         // 2^23 - b0 * 2048
+    float k2;         // 6291456.5 - b1 * 512
 };
 ROD_HD X2Row x2_row_consts(uint32_t b_packed) {
     X2Row r;
     const float b0 = (float)(b_packed & 0xFFFFu), b1 = (float)(b_packed >> 16);
     r.c0s = b0 * 4.8828125e-4f;
     r.c1s = b1 * 4.8828125e-4f;
-    r.k0 = 8388608.0f - b0 * 4096.0f;
-    r.negc1 = -b1 * 4096.0f;
+    r.k0 = 8388608.0f - b0 * 2048.0f;
+    r.k2 = 6291456.5f - b1 * 512.0f;
     return r;
 }
-// out = (floor(b0*q0/2048) + floor(b1*q1/2048) + 2) >> 2 with x = 2^23 + q, all in fp32 with
-// round-toward-zero fused multiply-adds (every intermediate is an exact integer + 2^23).
+// out = (floor(b0*q0/2048) + floor(b1*q1/2048) + 2) >> 2 with x = 2^22 + q, in three fp32 fused
+// multiply-adds rounded toward zero; every intermediate is an exact integer in [2^23, 2^24):
+//   y1 = x0*c0s + k0 = 2^23 + F0                      (x0*c0s = b0*2048 + q0*b0/2048)
+//   y2 = x1*c1s + y1 = 2^23 + b1*2048 + F0 + F1       (< 2^24 because b1 <= 2048)
+//   o  = y2/4 + k2   = 2^23 + ((F0 + F1 + 2) >> 2)    (k2 removes b1*512 and adds 0.5)
 ROD_HD uint32_t x2_vertical(float x0, float x1, const X2Row& r) {
 #if defined(__CUDA_ARCH__)
-    const float y1 = __fmaf_rz(x0, r.c0s, r.k0);         // 2^23 + F0
-    const float z = __fadd_rn(y1, r.negc1);              // exact
-    const float y2 = __fmaf_rz(x1, r.c1s, z);            // 2^23 + F0 + F1
-    const float o = __fmaf_rz(y2, 0.25f, 6291456.5f);    // 2^23 + ((F0 + F1 + 2) >> 2)
-    return __float_as_uint(o);                           // low byte is the result
+    const float y1 = __fmaf_rz(x0, r.c0s, r.k0);
+    const float y2 = __fmaf_rz(x1, r.c1s, y1);
+    return __float_as_uint(__fmaf_rz(y2, 0.25f, r.k2));  // low byte is the result
 #else
     const double y1 = floor((double)x0 * r.c0s + r.k0);
-    const double z = y1 + r.negc1;
-    const double y2 = floor((double)x1 * r.c1s + z);
-    const double o = floor(y2 * 0.25 + 6291456.5);
-    return fbits((float)o);
+    const double y2 = floor((double)x1 * r.c1s + y1);
+    return fbits((float)floor(y2 * 0.25 + r.k2));
 #endif
 }
 

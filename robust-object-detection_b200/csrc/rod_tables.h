@@ -137,6 +137,15 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
         sh.ay_first = blob_push(blob, ay.first);
         sh.ay_count = blob_push(blob, ay.count);
         sh.ay_alpha = blob_push(blob, ay.alpha);
+        if (ay.taps <= 3) {  // packed {first, beta0, beta1, beta2} per low-res row (unused taps are 0)
+            std::vector<uint32_t> pk((size_t)sh.nh * 4, 0u);
+            for (int d = 0; d < sh.nh; ++d) {
+                pk[4 * d] = (uint32_t)ay.first[d];
+                for (int q = 0; q < ay.count[d]; ++q) memcpy(&pk[4 * d + 1 + q], &ay.alpha[(size_t)d * ay.taps + q], 4);
+            }
+            sh.ay_pack = blob_push(blob, pk);
+            sh.ay_packed = 1;
+        }
     }
     if (!sh.lin_identity) {
         LinearAxis lx = build_linear_axis(sh.nw, w, true);

@@ -224,8 +224,8 @@ static int emu_lowres_x2(const uint8_t* src, uint8_t* dst, int h, int w, long sr
         const int nj = j_hi - j_lo + 1;
         if (nj > sh.strip_half_rows) return 6;
         memset(smem, 0xEE, (size_t)sh.strip_half_rows * p_pitch);
-        const bool vec = (sh.area_mode == AREA_FAST2 || sh.area_mode == AREA_GENERAL) && (w & 3) == 0 &&
-                         (((long)src_phase | src_pitch) & 3) == 0;
+        const bool vec = (w & 3) == 0 && (((long)src_phase | src_pitch) & 3) == 0 &&
+                         (sh.area_mode == AREA_FAST2 || (sh.area_mode == AREA_GENERAL && sh.ay_packed));
         if (vec) {
             const int n_units = nw >> 1;
             const uint32_t magic_div = 0xFFFFFFFFu / (uint32_t)n_units + 1u;
@@ -242,35 +242,33 @@ static int emu_lowres_x2(const uint8_t* src, uint8_t* dst, int h, int w, long sr
                     memcpy(rb, src + (long)(2 * dy + 1) * src_pitch + sb, 12);
                     area_fast2_unit(ra, rb, o6);
                 } else {
-                    const int32_t* yfirst = (const int32_t*)(tab + sh.ay_first);
-                    const int32_t* ycount = (const int32_t*)(tab + sh.ay_count);
-                    const float* beta = (const float*)(tab + sh.ay_alpha) + dy * sh.yt;
+                    const uint32_t* pk = tab + sh.ay_pack + 4 * dy;
+                    const int sy0 = (int)pk[0];
                     float acc[6];
-                    for (int ty = 0; ty < ycount[dy]; ++ty) {
+                    for (int ty = 0; ty < 3; ++ty) {
                         uint32_t rw[3];
-                        memcpy(rw, src + (long)(yfirst[dy] + ty) * src_pitch + sb, 12);
-                        area_x2f_accumulate(rw, beta[ty], ty == 0, acc);
+                        const int row = (ty < 2) ? sy0 + ty : std::min(sy0 + 2, h - 1);
+                        memcpy(rw, src + (long)row * src_pitch + sb, 12);
+                        area_x2f_accumulate(rw, bitsf(pk[1 + ty]), ty == 0, acc);
                     }
                     area_x2f_finish(acc, o6);
                 }
                 uint8_t* prow = smem + jr * p_pitch;
                 for (int q = 0; q < 6; ++q) prow[4 + 6 * u + q] = (uint8_t)o6[q];
-                if (u == 0) { prow[1] = (uint8_t)o6[0]; prow[2] = (uint8_t)o6[1]; prow[3] = (uint8_t)o6[2]; }
-                if (u == n_units - 1) {
-                    prow[4 + 3 * nw] = (uint8_t)o6[3]; prow[5 + 3 * nw] = (uint8_t)o6[4]; prow[6 + 3 * nw] = (uint8_t)o6[5];
-                }
             }
         } else {
             const int total = nj * 3 * nw;
             for (int idx = 0; idx < total; ++idx) {
                 const int jr = idx / (3 * nw), o = idx - jr * 3 * nw;
                 const int i = o / 3, c = o - 3 * i;
-                const uint8_t v = (uint8_t)area_value(src, src_pitch, sh, tab, j_lo + jr, i, c);
-                uint8_t* prow = smem + jr * p_pitch;
-                prow[4 + o] = v;
-                if (i == 0) prow[1 + c] = v;
-                if (i == nw - 1) prow[4 + 3 * nw + c] = v;
+                smem[jr * p_pitch + 4 + o] = (uint8_t)area_value(src, src_pitch, sh, tab, j_lo + jr, i, c);
             }
+        }
+        for (int q = 0; q < nj * 6; ++q) {
+            const int jr = q / 6, kk = q - 6 * jr;
+            uint8_t* prow = smem + jr * p_pitch;
+            if (kk < 3) prow[1 + kk] = prow[4 + kk];
+            else prow[4 + 3 * nw + (kk - 3)] = prow[4 + 3 * (nw - 1) + (kk - 3)];
         }
         const int nchunks = (w + 7) >> 3, ngroups = (th + 7) >> 3;
         const uint32_t magic_div = 0xFFFFFFFFu / (uint32_t)nchunks + 1u;
