@@ -291,7 +291,8 @@ __device__ __forceinline__ void x2_emit_row(const float* xlo, const float* xhi, 
     }
 }
 
-__global__ void __launch_bounds__(256, 2) lowres_x2_kernel(LowresX2Params p) {
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) lowres_x2_kernel(LowresX2Params p) {
     extern __shared__ __align__(16) uint8_t smem[];
     for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
         const Tile t = p.tiles[ti];
@@ -318,13 +319,13 @@ __global__ void __launch_bounds__(256, 2) lowres_x2_kernel(LowresX2Params p) {
             const int total = nj * n_units;
             const bool fast2 = (sh.area_mode == AREA_FAST2);
             const uint4* ypack = reinterpret_cast<const uint4*>(p.tab + sh.ay_pack);
-            for (int base = threadIdx.x; base < total; base += 512) {
+            for (int base = threadIdx.x; base < total; base += 2 * NT) {
                 uint32_t rw[2][3][3];
                 float beta[2][3];
                 int jrs[2], us[2];
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
-                    const int idx = (base + 256 * it < total) ? base + 256 * it : base;  // tail: redo item 0, dropped below
+                    const int idx = (base + NT * it < total) ? base + NT * it : base;  // tail: redo item 0, dropped below
                     const int jr = (n_units == 1) ? idx : (int)__umulhi((uint32_t)idx, magic_div);
                     const int u = idx - jr * n_units;
                     const int dy = j_lo + jr;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(256, 2) lowres_x2_kernel(LowresX2Params p) {
                 }
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
-                    if (it == 1 && base + 256 >= total) break;
+                    if (it == 1 && base + NT >= total) break;
                     uint32_t o6[6];
                     if (fast2) {
                         area_fast2_unit(rw[it][0], rw[it][1], o6);
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(256, 2) lowres_x2_kernel(LowresX2Params p) {
             }
         } else {
             const int total = nj * 3 * nw;
-            for (int idx = threadIdx.x; idx < total; idx += 256) {
+            for (int idx = threadIdx.x; idx < total; idx += NT) {
                 const int jr = idx / (3 * nw), o = idx - jr * 3 * nw;
                 const int i = o / 3, c = o - 3 * i;
                 smem[jr * p_pitch + 4 + o] = (uint8_t)area_value(simg, im.src_pitch, sh, p.tab, j_lo + jr, i, c);
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(256, 2) lowres_x2_kernel(LowresX2Params p) {
         }
         __syncthreads();
         // replicate the border pixels: P[-1] := P[0], P[nw] := P[nw-1] (OpenCV's clamped x taps)
-        for (int q = threadIdx.x; q < nj * 6; q += 256) {
+        for (int q = threadIdx.x; q < nj * 6; q += NT) {
             const int jr = q / 6, kk = q - 6 * jr;
             uint8_t* prow = smem + jr * p_pitch;
             if (kk < 3) prow[1 + kk] = prow[4 + kk];
@@ -388,34 +389,25 @@ __global__ void __launch_bounds__(256, 2) lowres_x2_kernel(LowresX2Params p) {
             const int ngroups = (th + 7) >> 3;
             const uint32_t magic_div = 0xFFFFFFFFu / (uint32_t)nchunks + 1u;
             const int total = ngroups * nchunks;
-            for (int idx = threadIdx.x; idx < total; idx += 256) {
+            for (int idx = threadIdx.x; idx < total; idx += NT) {
                 const int rg = (nchunks == 1) ? idx : (int)__umulhi((uint32_t)idx, magic_div);
                 const int ch = idx - rg * nchunks;
                 const int nvalid = min(24, n - 24 * ch);
                 float xe[24], xo[24];  // horizontal stage of the even / odd low-res row currently held
                 int je = -1, jo = -1;
                 const int r_end = min(th, 8 * rg + 8);
+                uint32_t ys = ly_s[y0 + 8 * rg], yb = ly_b[y0 + 8 * rg];
                 for (int r = 8 * rg; r < r_end; ++r) {
-                    const uint32_t ys = ly_s[y0 + r];
                     const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
-                    const X2Row rc = x2_row_consts(ly_b[y0 + r]);
-                    // make sure both rows sit in their parity slot
-                    if ((s0 & 1) ? (jo != s0) : (je != s0)) {
-                        if (s0 & 1) { x2_load_row(smem + (s0 - j_lo) * p_pitch, ch, xo); jo = s0; }
-                        else { x2_load_row(smem + (s0 - j_lo) * p_pitch, ch, xe); je = s0; }
-                    }
-                    if ((s1 & 1) ? (jo != s1) : (je != s1)) {
-                        if (s1 & 1) { x2_load_row(smem + (s1 - j_lo) * p_pitch, ch, xo); jo = s1; }
-                        else { x2_load_row(smem + (s1 - j_lo) * p_pitch, ch, xe); je = s1; }
-                    }
+                    const X2Row rc = x2_row_consts(yb);
+                    if (r + 1 < r_end) { ys = ly_s[y0 + r + 1]; yb = ly_b[y0 + r + 1]; }  // prefetch the next row's table entries
+                    // slot (s0 & 1) must hold row s0 and the other slot row s1 (s1 == s0 only on the first / last image rows)
+                    const int want_e = (s0 & 1) ? s1 : s0, want_o = (s0 & 1) ? s0 : s1;
+                    if (je != want_e) { x2_load_row(smem + (want_e - j_lo) * p_pitch, ch, xe); je = want_e; }
+                    if (jo != want_o) { x2_load_row(smem + (want_o - j_lo) * p_pitch, ch, xo); jo = want_o; }
                     uint8_t* dptr = dimg + (int64_t)(y0 + r) * im.dst_pitch + 24 * ch;
-                    if (s0 & 1) {
-                        if (s1 & 1) x2_emit_row(xo, xo, rc, dptr, nvalid);
-                        else x2_emit_row(xo, xe, rc, dptr, nvalid);
-                    } else {
-                        if (s1 & 1) x2_emit_row(xe, xo, rc, dptr, nvalid);
-                        else x2_emit_row(xe, xe, rc, dptr, nvalid);
-                    }
+                    if (s0 & 1) x2_emit_row(xo, xe, rc, dptr, nvalid);
+                    else x2_emit_row(xe, xo, rc, dptr, nvalid);
                 }
             }
         }
@@ -459,10 +451,15 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             const size_t smem = plan->lowres_x2_smem;
-            ROD_CUDA(cudaFuncSetAttribute(lowres_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
-            ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 2 ? 2 : ctas_per_sm);
-            lowres_x2_kernel<<<grid_for(plan, p.n_tiles, ctas_per_sm), 256, smem, stream>>>(p);
+            ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm;
+            if (plan->lowres_x2_threads == 128) {
+                ROD_CUDA(cudaFuncSetAttribute(lowres_x2_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                lowres_x2_kernel<128, 4><<<grid_for(plan, p.n_tiles, ctas_per_sm > 4 ? 4 : ctas_per_sm), 128, smem, stream>>>(p);
+            } else {
+                ROD_CUDA(cudaFuncSetAttribute(lowres_x2_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                lowres_x2_kernel<256, 2><<<grid_for(plan, p.n_tiles, ctas_per_sm > 2 ? 2 : ctas_per_sm), 256, smem, stream>>>(p);
+            }
             ROD_CUDA(cudaGetLastError());
         }
     }

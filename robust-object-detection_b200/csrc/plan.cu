@@ -1,4 +1,6 @@
 // plan.cu -- batch plans: descriptor upload, tile lists, resize tables (host side of librod_b200.so).
+#include <stdlib.h>
+
 #include <map>
 #include <new>
 
@@ -37,13 +39,20 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     bool all_identity = true;
     int max_rows = 1, max_cols = 1;
     size_t x2_smem = 0;
+    // tuning knobs (benchmarks only): CTA size, forced strip height, shared-memory budget per CTA
+    const char* e_thr = getenv("ROD_X2_THREADS");
+    const char* e_rows = getenv("ROD_X2_STRIP");
+    const int x2_threads = (e_thr && atoi(e_thr) == 256) ? 256 : 128;
+    const int x2_force_rows = e_rows ? atoi(e_rows) : 0;
+    const size_t x2_max_smem = (x2_threads == 128) ? 54 * 1024 : 100 * 1024;
+    plan->lowres_x2_threads = x2_threads;
     for (size_t s = 0; s < plan->shapes.size(); ++s) {
         const int h = plan->shapes[s].h, w = plan->shapes[s].w;
         if (!build_lowres_shape(h, w, factor, kMaxAreaTaps, blob, &shapes[s])) return ROD_ERR_UNSUPPORTED;
         DevShape& sh = shapes[s];
         if (sh.lin_identity) continue;
         all_identity = false;
-        x2_smem = std::max(x2_smem, choose_strip_rows(&sh, blob.data()));
+        x2_smem = std::max(x2_smem, choose_strip_rows(&sh, blob.data(), x2_max_smem, x2_threads, x2_force_rows));
         if (sh.strip_rows > 0) continue;
         int rows, cols;
         lowres_tile_footprint(sh, blob.data(), kLowresTH, kLowresTWB, &rows, &cols);

@@ -55,6 +55,7 @@ struct rod_plan {
     rod::Tile* d_lowres_x2_tiles = nullptr;
     int n_lowres_x2_tiles = 0;
     size_t lowres_x2_smem = 0;
+    int lowres_x2_threads = 128;  // CTA size of lowres_x2_kernel (ROD_X2_THREADS=128|256)
     bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
 
     // lowres tables, rebuilt when the factor changes
