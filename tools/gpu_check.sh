@@ -1,0 +1,18 @@
+#!/bin/bash
+# One gpurun call: parity tests, bench (both arms), launch list, full ncu capture of each kernel.
+# Usage (from the repo root on the GPU box): bash tools/gpu_check.sh <tag>
+tag=${1:-r1}
+out=gpurun_out
+mkdir -p $out
+nvidia-smi --query-gpu=name,memory.total --format=csv > $out/gpu_$tag.txt; nproc >> $out/gpu_$tag.txt
+python -m pytest tests -m gpu -x -q > $out/pytest_$tag.log 2>&1; echo "pytest exit $?" | tee -a $out/pytest_$tag.log
+python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; echo "smoke exit $?" | tee -a $out/smoke_$tag.log
+python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench exit $?"
+python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; echo "ref exit $?"
+python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/plain_bench_$tag.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches_$tag.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/ncu_launch_$tag.log 2>&1
+python tools/profile_ops.py > $out/plain_profile_$tag.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'blur|noise|lowres|letterbox' -s 3 -c 22 -f \
+    -o $out/prof_$tag python tools/profile_ops.py > $out/ncu_full_$tag.log 2>&1
+echo "done"
