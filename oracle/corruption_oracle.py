@@ -97,20 +97,29 @@ def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
     return c.astype(np.uint32)
 
 
+_PHILOX_TAIL_FLIP = 0x80000000
+_NOISE_K_PER_SIGMA = np.float32(1.17741002251547466)       # sqrt(2 ln 2), as the fp32 constant the kernel uses
+_ANGLE_SCALE = float(np.float32(9.58737992428525768e-05))  # float32(2 pi / 65536)
+_ANGLE_BIAS = float(np.float32(-804.2476806640625))        # float32((0.5 - 2^23) * 2 pi / 65536)
+
+
 def philox_noise_field(n_elems: int, sigma: float, seed: int, image_index: int,
                        offset: int = 0) -> np.ndarray:
-    """float64 restatement of the kernel's Philox noise stream for one image
-    (robust-object-detection_b200/csrc/rod_core.h: philox4x32_10 + boxmuller4).
+    """float64 restatement of the kernel's Philox-mode noise stream for one image
+    (robust-object-detection_b200/csrc/rod_core.h: philox4x32_10 + gauss8).
 
-    Element e (flat HWC index) belongs to group g = e // 4, lane j = e % 4.
-      ctr = [g, image_index & 0xffffffff, image_index >> 32, offset]
-      key = [seed & 0xffffffff, seed >> 32]
+    Element e (flat HWC index) belongs to group g = e // 8; word p = (e % 8) // 2 of the
+    group's Philox block makes the Box-Muller pair (8g + 2p, 8g + 2p + 1):
+      ctr = [g, image_index & 0xffffffff, image_index >> 32, offset], key = [seed lo, seed hi]
       r = Philox4x32-10(ctr, key)
-      ua = (r0 + 0.5) * 2^-32                      radius uniform of pair 0 (r2 for pair 1)
-      th = pi * (((r1 >> 9) + 0.5) * 2^-22 - 1)    angle of pair 0 (r3 for pair 1)
-      z0 = sqrt(-2 ln ua) cos th, z1 = sqrt(-2 ln ua) sin th;  noise[e] = sigma * z_j.
+      u  = ((r_p >> 16) + 0.5) * 2^-16                         radius uniform (stratified, 16 bits)
+           if r_p >> 16 == 0: u = (t_p + 0.5) * 2^-48 with t = Philox block at ctr[2] ^ 0x80000000
+      th = (2^23 + (r_p & 0xffff)) * float32(2 pi / 65536) + float32((0.5 - 2^23) 2 pi / 65536)
+      s0 = sqrt(-log2 u) cos th, s1 = sqrt(-log2 u) sin th
+      noise[e] = K * s with K = float32(sigma) * float32(sqrt(2 ln 2)).
+    The kernel's output is add_philox_noise(img, noise): clamp(v + floor(noise), 0, 255).
     """
-    n_groups = (n_elems + 3) // 4
+    n_groups = (n_elems + 7) // 8
     g = np.arange(n_groups, dtype=np.uint64)
     ctr = np.empty((n_groups, 4), dtype=np.uint32)
     ctr[:, 0] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)
@@ -119,14 +128,30 @@ def philox_noise_field(n_elems: int, sigma: float, seed: int, image_index: int,
     ctr[:, 3] = np.uint32(offset & 0xFFFFFFFF)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
     r = philox4x32_10(ctr, key)
-    z = np.empty((n_groups, 4), dtype=np.float64)
-    for p in range(2):
-        ua = (r[:, 2 * p].astype(np.float64) + 0.5) * (2.0 ** -32)
-        sb = ((r[:, 2 * p + 1] >> np.uint32(9)).astype(np.float64) + 0.5) * (2.0 ** -22) - 1.0
-        rad = np.sqrt(-2.0 * np.log(ua))
-        z[:, 2 * p] = rad * np.cos(np.pi * sb)
-        z[:, 2 * p + 1] = rad * np.sin(np.pi * sb)
-    return (sigma * z).reshape(-1)[:n_elems]
+    ctr_t = ctr.copy()
+    ctr_t[:, 2] ^= np.uint32(_PHILOX_TAIL_FLIP)
+    t = philox4x32_10(ctr_t, key)
+    K = float(np.float32(sigma) * _NOISE_K_PER_SIGMA)
+    s = np.empty((n_groups, 8), dtype=np.float64)
+    for p in range(4):
+        hi = (r[:, p] >> np.uint32(16)).astype(np.float64)
+        lo = (r[:, p] & np.uint32(0xFFFF)).astype(np.float64)
+        u = (hi + 0.5) * 2.0 ** -16
+        u = np.where(hi == 0, (t[:, p].astype(np.float64) + 0.5) * 2.0 ** -48, u)
+        rad = np.sqrt(-np.log2(u))
+        th = (8388608.0 + lo) * _ANGLE_SCALE + _ANGLE_BIAS
+        s[:, 2 * p] = rad * np.cos(th)
+        s[:, 2 * p + 1] = rad * np.sin(th)
+    return (K * s).reshape(-1)[:n_elems]
+
+
+def add_philox_noise(img: np.ndarray, noise: np.ndarray) -> np.ndarray:
+    """Philox-mode output: clamp(v + floor(noise), 0, 255).  Equals the reference's
+    trunc(clip(v + noise, 0, 255)) in real arithmetic (v is an integer); the reference's float32
+    rounding of v + noise moves about 4e-6 of the elements across an integer, which Philox mode
+    (validated statistically, not bit-exactly) does not reproduce."""
+    x = img.astype(np.int64) + np.floor(np.asarray(noise, dtype=np.float64)).astype(np.int64).reshape(img.shape)
+    return np.clip(x, 0, 255).astype(np.uint8)
 
 
 # ----------------------------------------------------------------------------

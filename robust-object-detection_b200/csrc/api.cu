@@ -7,6 +7,8 @@ using namespace rod;
 
 namespace {
 
+constexpr float kPhiloxMaxSigma = 2048.0f;  // floor(K s) must fit int16 (rod_core.h noise_floor16)
+
 bool blur_supported(int k, double angle) { return angle == 0.0 && k >= 1 && k <= 31 && (k & 1) == 1; }
 
 int run_op(rod_plan* plan, int op, const uint8_t* src, uint8_t* dst, const float* noise, float sigma, int k,
@@ -17,6 +19,7 @@ int run_op(rod_plan* plan, int op, const uint8_t* src, uint8_t* dst, const float
             return launch_noise(plan, NOISE_COPY, src, dst, nullptr, nullptr, 0.f, 0, 0, 0, opcodes, ROD_OP_NONE,
                                 stream, img_lo, img_hi);
         case ROD_OP_NOISE:
+            if (noise == nullptr && sigma > kPhiloxMaxSigma) return ROD_ERR_UNSUPPORTED;
             return launch_noise(plan, noise ? NOISE_COMPAT : NOISE_PHILOX, src, dst, noise, nullptr, sigma, seed,
                                 first_image, offset, opcodes, ROD_OP_NOISE, stream, img_lo, img_hi);
         case ROD_OP_BLUR:
@@ -80,6 +83,7 @@ extern "C" int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* d
                             void* stream) {
     if (plan == nullptr || src == nullptr || dst == nullptr) return ROD_ERR_INVALID_ARG;
     if (!(sigma >= 0.0f)) return ROD_ERR_INVALID_ARG;
+    if (noise == nullptr && sigma > kPhiloxMaxSigma) return ROD_ERR_UNSUPPORTED;
     return launch_noise(plan, noise ? NOISE_COMPAT : NOISE_PHILOX, src, dst, noise, nullptr, sigma, seed,
                         first_image_index, offset, opcodes, ROD_OP_NOISE, (cudaStream_t)stream, 0, plan->n_images);
 }
@@ -87,6 +91,7 @@ extern "C" int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* d
 extern "C" int rod_noise_field_f32(const rod_plan* plan, float* out_field, float sigma, uint64_t seed,
                                    uint64_t first_image_index, uint32_t offset, void* stream) {
     if (plan == nullptr || out_field == nullptr) return ROD_ERR_INVALID_ARG;
+    if (!(sigma >= 0.0f) || sigma > kPhiloxMaxSigma) return ROD_ERR_UNSUPPORTED;
     return launch_noise(plan, NOISE_FIELD, nullptr, nullptr, nullptr, out_field, sigma, seed, first_image_index,
                         offset, nullptr, ROD_OP_NOISE, (cudaStream_t)stream, 0, plan->n_images);
 }

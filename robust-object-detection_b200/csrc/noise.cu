@@ -43,6 +43,14 @@ __device__ __forceinline__ float4 ldg_stream16f(const void* p) {
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg4(void* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void stg16(void* p, uint4 v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                  "r"(v.w)
@@ -62,20 +70,33 @@ __device__ __forceinline__ uint32_t noise_word(uint32_t word, float n0, float n1
     return o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
 }
 
-template <int MODE>
-__device__ __forceinline__ void group_noise(const NoiseParams& p, uint64_t elem_base, uint32_t img_global_lo,
-                                            uint32_t img_global_hi, uint32_t group, float nz[4]) {
-    // Philox counter: (group, image index lo, image index hi, offset); key = seed
+// One Philox group: the eight factors s[0..7] of elements 8g .. 8g+7 (rod_core.h gauss8).
+__device__ __forceinline__ void group_gauss8(const NoiseParams& p, uint32_t ig_lo, uint32_t ig_hi, uint32_t g,
+                                             float s[8]) {
     uint32_t r[4];
-    philox4x32_10(group, img_global_lo, img_global_hi, p.offset, p.key0, p.key1, r);
-    float z[4];
-    boxmuller4(r, z);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) nz[j] = p.sigma * z[j];
+    philox4x32_10(g, ig_lo, ig_hi, p.offset, p.key0, p.key1, r);
+    if (philox_needs_tail(r)) {  // 2^-14 of the groups: refine the radius of the words whose high half is 0
+        uint32_t t[4];
+        philox4x32_10(g, ig_lo, ig_hi ^ ROD_PHILOX_TAIL_FLIP, p.offset, p.key0, p.key1, t);
+        gauss8(r, t, s);
+    } else {
+        gauss8(r, nullptr, s);
+    }
+}
+
+// four pixels (one word) + four factors -> four output bytes: clamp(v + floor(K s), 0, 255)
+__device__ __forceinline__ uint32_t philox_word(uint32_t word, const float* s, float K) {
+    const uint32_t f01 = __byte_perm(noise_floor16(s[0], K), noise_floor16(s[1], K), 0x5410);
+    const uint32_t f23 = __byte_perm(noise_floor16(s[2], K), noise_floor16(s[3], K), 0x5410);
+    const uint32_t v01 = __byte_perm(word, 0u, 0x4140), v23 = __byte_perm(word, 0u, 0x4342);
+    const uint32_t q01 = __viaddmin_s16x2_relu(f01, v01, 0x00FF00FFu);
+    const uint32_t q23 = __viaddmin_s16x2_relu(f23, v23, 0x00FF00FFu);
+    return __byte_perm(q01, q23, 0x6420);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(256) noise_kernel(NoiseParams p) {
+    const float K = p.sigma * ROD_NOISE_K_PER_SIGMA;
     for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
         const Tile t = p.tiles[ti];
         if (p.opcodes != nullptr && p.opcodes[t.img] != p.my_op) continue;
@@ -99,58 +120,82 @@ __global__ void __launch_bounds__(256) noise_kernel(NoiseParams p) {
         const float* nzp = (MODE == NOISE_COMPAT) ? p.noise + im.elem_base + e0 : nullptr;
         float* fout = (MODE == NOISE_FIELD) ? p.field_out + im.elem_base + e0 : nullptr;
 
-        bool vec = (e0 & 3u) == 0;
-        if (MODE != NOISE_FIELD) vec = vec && ((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0;
-        if (MODE == NOISE_COMPAT) vec = vec && (((uintptr_t)nzp) & 15) == 0;
-        if (MODE == NOISE_FIELD) vec = vec && (((uintptr_t)fout) & 15) == 0;
-        const uint32_t nvec = vec ? (n >> 4) : 0;
-
-        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-            const uint32_t e = 16u * i;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (MODE != NOISE_FIELD) v = ldg_stream16(s + e);
-            if (MODE == NOISE_COPY) {
-                stg16(d + e, v);
-                continue;
-            }
-            uint32_t in[4] = {v.x, v.y, v.z, v.w};
-            uint32_t out[4];
+        uint32_t done = 0;  // elements of the span finished by the vector paths
+        if (MODE == NOISE_COMPAT) {
+            // 4 pixels (one word) + one float4 of the field per thread step; every warp instruction is fully
+            // coalesced (128 B of pixels, 512 B of field); four independent steps in flight per thread
+            const bool vec4 = (e0 & 3u) == 0 && ((((uintptr_t)s) | ((uintptr_t)d)) & 3) == 0 && (((uintptr_t)nzp) & 15) == 0;
+            const uint32_t nw = vec4 ? (n >> 2) : 0;
+            for (uint32_t base = threadIdx.x; base < nw; base += 4 * blockDim.x) {
+                uint32_t px[4];
+                float4 f[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float nz[4];
-                if (MODE == NOISE_COMPAT) {
-                    float4 f = ldg_stream16f(nzp + e + 4 * g);
-                    nz[0] = f.x; nz[1] = f.y; nz[2] = f.z; nz[3] = f.w;
-                } else {
-                    group_noise<MODE>(p, im.elem_base, ig_lo, ig_hi, ((e0 + e) >> 2) + g, nz);
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t idx = base + u * blockDim.x;
+                    if (idx < nw) {
+                        px[u] = ldg_stream4(s + 4 * idx);
+                        f[u] = ldg_stream16f(nzp + 4 * idx);
+                    }
                 }
-                if (MODE == NOISE_FIELD) {
-                    *reinterpret_cast<float4*>(fout + e + 4 * g) = make_float4(nz[0], nz[1], nz[2], nz[3]);
-                } else {
-                    out[g] = noise_word(in[g], nz[0], nz[1], nz[2], nz[3]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t idx = base + u * blockDim.x;
+                    if (idx < nw) stg4(d + 4 * idx, noise_word(px[u], f[u].x, f[u].y, f[u].z, f[u].w));
                 }
             }
-            if (MODE != NOISE_FIELD) stg16(d + e, make_uint4(out[0], out[1], out[2], out[3]));
+            done = nw << 2;
+        } else {
+            // 16 bytes per thread step = two Philox groups: needs the span to start on a group boundary
+            bool vec = (e0 & 7u) == 0;
+            if (MODE != NOISE_FIELD) vec = vec && ((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0;
+            if (MODE == NOISE_FIELD) vec = vec && (((uintptr_t)fout) & 15) == 0;
+            const uint32_t nvec = vec ? (n >> 4) : 0;
+            for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+                const uint32_t e = 16u * i;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (MODE != NOISE_FIELD) v = ldg_stream16(s + e);
+                if (MODE == NOISE_COPY) {
+                    stg16(d + e, v);
+                    continue;
+                }
+                const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+                uint32_t out[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float sf[8];
+                    group_gauss8(p, ig_lo, ig_hi, ((e0 + e) >> 3) + h, sf);
+                    if (MODE == NOISE_FIELD) {
+                        float4* fo = reinterpret_cast<float4*>(fout + e + 8 * h);
+                        fo[0] = make_float4(K * sf[0], K * sf[1], K * sf[2], K * sf[3]);
+                        fo[1] = make_float4(K * sf[4], K * sf[5], K * sf[6], K * sf[7]);
+                    } else {
+                        out[2 * h] = philox_word(in[2 * h], sf, K);
+                        out[2 * h + 1] = philox_word(in[2 * h + 1], sf + 4, K);
+                    }
+                }
+                if (MODE != NOISE_FIELD) stg16(d + e, make_uint4(out[0], out[1], out[2], out[3]));
+            }
+            done = nvec << 4;
         }
 
-        // remainder (and the whole span when unaligned): one Philox group (<= 4 elements) per thread step
-        const uint32_t r0 = nvec << 4;           // first element not yet done, relative to the span
+        // remainder (and the whole span when unaligned): one Philox group (<= 8 elements) per thread step
+        const uint32_t r0 = done;                // first element not yet done, relative to the span
         if (r0 < n) {
             const uint32_t ea = e0 + r0, eb = e0 + n;      // absolute element range [ea, eb)
-            const uint32_t g_first = ea >> 2, g_last = (eb - 1) >> 2;
+            const uint32_t g_first = ea >> 3, g_last = (eb - 1) >> 3;
             for (uint32_t g = g_first + threadIdx.x; g <= g_last; g += blockDim.x) {
-                float nz[4] = {0.f, 0.f, 0.f, 0.f};
-                if (MODE == NOISE_PHILOX || MODE == NOISE_FIELD) group_noise<MODE>(p, im.elem_base, ig_lo, ig_hi, g, nz);
+                float sf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (MODE == NOISE_PHILOX || MODE == NOISE_FIELD) group_gauss8(p, ig_lo, ig_hi, g, sf);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t e = 4u * g + j;
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t e = 8u * g + j;
                     if (e < ea || e >= eb) continue;
                     const uint32_t rel = e - e0;
-                    if (MODE == NOISE_FIELD) { fout[rel] = nz[j]; continue; }
+                    if (MODE == NOISE_FIELD) { fout[rel] = K * sf[j]; continue; }
                     const uint32_t v = s[rel];
                     if (MODE == NOISE_COPY) { d[rel] = (uint8_t)v; continue; }
-                    const float nzv = (MODE == NOISE_COMPAT) ? nzp[rel] : nz[j];
-                    d[rel] = (uint8_t)noise_px(__uint_as_float(0x4B000000u | v) - 8388608.0f, nzv);
+                    if (MODE == NOISE_COMPAT) d[rel] = (uint8_t)noise_px(__uint_as_float(0x4B000000u | v) - 8388608.0f, nzp[rel]);
+                    else d[rel] = (uint8_t)noise_philox_px(v, sf[j], K);
                 }
             }
         }

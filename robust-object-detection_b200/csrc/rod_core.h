@@ -129,38 +129,67 @@ ROD_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
 }
 
-// Four N(0,1) samples from one Philox block: (r0,r1) and (r2,r3) are Box-Muller pairs.
-//   radius uniform  ua = (r_a + 0.5) * 2^-32            in (0,1)   (full 32 bits: tail to 6.7 sigma)
-//   angle           th = pi * (((r_b >> 9) + 0.5) * 2^-22 - 1)      in (-pi, pi), 23 bits
-//   z0 = sqrt(-2 ln ua) * cos(th),  z1 = sqrt(-2 ln ua) * sin(th)
-// Integer->float conversions use the 2^23 mantissa trick (FADD) instead of I2F.
-ROD_HD void boxmuller4(const uint32_t r[4], float z[4]) {
+// Philox-mode noise (rod_noise_u8 with noise == NULL).  One Philox block r[4] serves the GROUP of 8
+// consecutive elements e = 8g .. 8g+7 of an image (counter = (g, image lo, image hi, offset), key = seed);
+// word r[p] makes the Box-Muller pair (8g + 2p, 8g + 2p + 1):
+//   radius uniform  u  = (hi16 + 0.5) * 2^-16, hi16 = r[p] >> 16      (stratified; reaches 4.86 sigma)
+//     tail          if hi16 == 0 (probability 2^-16): u = (t[p] + 0.5) * 2^-48 with t = the Philox block
+//                   at counter (g, image lo, image hi ^ 0x80000000, offset) -> the tail reaches 8.2 sigma
+//   angle           th = 2 pi (lo16 + 0.5) / 65536, lo16 = r[p] & 0xffff
+//   s[2p] = sqrt(-log2 u) cos th,  s[2p+1] = sqrt(-log2 u) sin th      (unit-free factors)
+//   noise n = K s with K = sigma * sqrt(2 ln 2);   out = clamp(v + floor(n), 0, 255)
+// (v is an integer, so v + floor(n) == floor(v + n): the reference's truncation of the clipped sum.)
+// The fp32 constants below are part of the definition (oracle/corruption_oracle.py restates them).
+#define ROD_PHILOX_TAIL_FLIP 0x80000000u
+#define ROD_NOISE_K_PER_SIGMA 1.17741002251547466f  // sqrt(2 ln 2)
+#define ROD_ANGLE_SCALE 9.58737992428525768e-05f    // float(2 pi / 65536)
+#define ROD_ANGLE_BIAS (-804.247680664062500f)      // float((0.5 - 2^23) * 2 pi / 65536)
+ROD_HD bool philox_needs_tail(const uint32_t r[4]) {
+    uint32_t m = r[0] < r[1] ? r[0] : r[1];
+    const uint32_t m2 = r[2] < r[3] ? r[2] : r[3];
+    m = m < m2 ? m : m2;
+    return m < 0x10000u;
+}
+// t may be NULL when !philox_needs_tail(r).
+ROD_HD void gauss8(const uint32_t r[4], const uint32_t* t, float s[8]) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        uint32_t ra = r[2 * p], rb = r[2 * p + 1];
-        float na = bitsf(0x4B000000u | (ra >> 9)) - 8388608.0f;   // exact (ra >> 9)
-        float la = bitsf(0x4B000000u | (ra & 511u)) - 8388608.0f; // exact (ra & 511)
-        float ua = fmaf(la, 2.3283064365386963e-10f, fmaf(na, 1.1920928955078125e-07f, 1.1641532182693481e-10f));
-        ua = fminf(ua, 0.99999994f);
-        float nb = bitsf(0x4B000000u | (rb >> 9)) - 8388608.0f;
-        float sb = fmaf(nb, 2.384185791015625e-07f, 1.1920928955078125e-07f - 1.0f);
-        float l2 = __log2f(ua);
-        float rad;
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * l2));
-        float th = 3.14159265358979f * sb;
-        z[2 * p] = rad * __cosf(th);
-        z[2 * p + 1] = rad * __sinf(th);
+    for (int p = 0; p < 4; ++p) {
+        // 2^23 + hi16 and 2^23 + lo16 assembled by byte permutes (no I2F)
+        const float xh = bitsf(__byte_perm(r[p], 0x4B000000u, 0x7432));
+        const float xl = bitsf(__byte_perm(r[p], 0x4B000000u, 0x7410));
+        float u = fmaf(xh, 1.52587890625e-05f, -127.99999237060546875f);  // (hi16 + 0.5) * 2^-16, exact
+        if (t != nullptr && r[p] < 0x10000u) u = fmaf((float)t[p], 3.5527136788005009e-15f, 1.7763568394002505e-15f);
+        float l2, rad;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-l2));
+        const float th = fmaf(xl, ROD_ANGLE_SCALE, ROD_ANGLE_BIAS);
+        s[2 * p] = rad * __cosf(th);
+        s[2 * p + 1] = rad * __sinf(th);
     }
 #else
-    for (int p = 0; p < 2; ++p) {
-        double ua = ((double)r[2 * p] + 0.5) * 2.3283064365386963e-10;
-        double sb = ((double)(r[2 * p + 1] >> 9) + 0.5) * 2.384185791015625e-07 - 1.0;
-        double rad = sqrt(-2.0 * log(ua));
-        z[2 * p] = (float)(rad * cos(3.141592653589793 * sb));
-        z[2 * p + 1] = (float)(rad * sin(3.141592653589793 * sb));
+    for (int p = 0; p < 4; ++p) {
+        double u = ((double)(r[p] >> 16) + 0.5) * 1.52587890625e-05;
+        if (t != nullptr && r[p] < 0x10000u) u = ((double)t[p] + 0.5) * 3.5527136788005009e-15;
+        const double rad = sqrt(-log2(u));
+        const double th = (8388608.0 + (double)(r[p] & 0xFFFFu)) * (double)ROD_ANGLE_SCALE + (double)ROD_ANGLE_BIAS;
+        s[2 * p] = (float)(rad * cos(th));
+        s[2 * p + 1] = (float)(rad * sin(th));
     }
 #endif
+}
+// int16 floor(K * s) in the low half of the result (two's complement), valid for |K s| < 32768:
+// fma rounded toward -inf onto the integer grid of [2^23, 2^24) (1.5 * 2^23 keeps negatives in the binade).
+ROD_HD uint32_t noise_floor16(float s, float K) {
+#if defined(__CUDA_ARCH__)
+    return fbits(__fmaf_rd(s, K, 12582912.0f));
+#else
+    return (uint32_t)(int32_t)floor((double)s * (double)K) & 0xFFFFu;
+#endif
+}
+ROD_HD uint32_t noise_philox_px(uint32_t v, float s, float K) {
+    int x = (int)v + (int)(int16_t)(noise_floor16(s, K) & 0xFFFFu);
+    return (uint32_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
 }
 
 // ---------------------------------------------------------------------------------

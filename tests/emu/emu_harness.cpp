@@ -322,22 +322,31 @@ extern "C" int emu_lowres_tiled(const uint8_t* src, uint8_t* dst, int h, int w, 
 // Replays noise_kernel (compat / philox / field) over one image's flat element range.
 extern "C" int emu_noise(const uint8_t* src, uint8_t* dst, const float* noise, float* field_out, long n_elems,
                          float sigma, uint64_t seed, uint64_t image_index, uint32_t offset) {
-    for (long g = 0; g < (n_elems + 3) / 4; ++g) {
-        float nz[4] = {0, 0, 0, 0};
+    const float K = sigma * ROD_NOISE_K_PER_SIGMA;
+    for (long g = 0; g < (n_elems + 7) / 8; ++g) {
+        float sf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (noise == nullptr) {
-            uint32_t r[4];
-            float z[4];
-            philox4x32_10((uint32_t)g, (uint32_t)image_index, (uint32_t)(image_index >> 32), offset, (uint32_t)seed,
-                          (uint32_t)(seed >> 32), r);
-            boxmuller4(r, z);
-            for (int j = 0; j < 4; ++j) nz[j] = sigma * z[j];
+            uint32_t r[4], t[4];
+            const uint32_t ig_lo = (uint32_t)image_index, ig_hi = (uint32_t)(image_index >> 32);
+            philox4x32_10((uint32_t)g, ig_lo, ig_hi, offset, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+            if (philox_needs_tail(r)) {
+                philox4x32_10((uint32_t)g, ig_lo, ig_hi ^ ROD_PHILOX_TAIL_FLIP, offset, (uint32_t)seed,
+                              (uint32_t)(seed >> 32), t);
+                gauss8(r, t, sf);
+            } else {
+                gauss8(r, nullptr, sf);
+            }
         }
-        for (int j = 0; j < 4; ++j) {
-            long e = 4 * g + j;
+        for (int j = 0; j < 8; ++j) {
+            long e = 8 * g + j;
             if (e >= n_elems) break;
-            float nv = noise ? noise[e] : nz[j];
-            if (field_out) field_out[e] = nv;
-            if (dst) dst[e] = (uint8_t)noise_px((float)src[e], nv);
+            if (noise) {
+                if (field_out) field_out[e] = noise[e];
+                if (dst) dst[e] = (uint8_t)noise_px((float)src[e], noise[e]);
+            } else {
+                if (field_out) field_out[e] = K * sf[j];
+                if (dst) dst[e] = (uint8_t)noise_philox_px(src[e], sf[j], K);
+            }
         }
     }
     return 0;

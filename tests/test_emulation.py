@@ -89,7 +89,7 @@ def test_emu_noise_compat_and_philox(emu):
     emu.emu_noise(_p(img), _p(got), None, _p(out, ctypes.c_float), n, 15.0, 0x1234567890ABCDEF, 5, 3)
     want = orc.philox_noise_field(n, 15.0, 0x1234567890ABCDEF, 5, 3)
     assert np.max(np.abs(out - want)) < 2e-3
-    assert np.array_equal(got, orc.add_noise_field(img, out.reshape(img.shape)))
+    assert np.mean(got != orc.add_philox_noise(img, want)) < 1e-3
 
 
 def test_philox_known_answer():
@@ -109,3 +109,27 @@ def test_emu_letterbox(emu, shape):
     want = orc.letterbox_norm_f16(img, 640, 640, 114)
     got = (canvas[:, :, ::-1].transpose(2, 0, 1).astype(np.float32) / np.float32(255)).astype(np.float16)
     assert np.array_equal(got, want)
+
+
+def test_philox_stream_statistics_cpu():
+    """The restated Philox-mode stream on the CPU: moments, tails, the truncation bias and
+    clip fractions of add_philox_noise, and the 2^-16 tail-refinement branch."""
+    from scipy import stats
+    n = 1 << 21
+    f = orc.philox_noise_field(n, 15.0, 42, 0)
+    z = f / 15.0
+    assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.std() - 1.0) < 3e-3
+    assert abs(stats.kurtosis(z)) < 0.02 and abs(stats.skew(z)) < 0.01
+    assert stats.kstest(z[::7], "norm").pvalue > 1e-3
+    # pairs are uncorrelated, neighbouring groups too
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 5e-3 and abs(np.corrcoef(z[:-8], z[8:])[0, 1]) < 5e-3
+    # the stratified 16-bit radius alone stops at sqrt(2 ln 2^17) = 4.855 sigma: the refinement reaches beyond
+    big = orc.philox_noise_field(1 << 24, 1.0, 7, 3)
+    assert np.abs(big).max() > 4.9 and abs((np.abs(big) > 4.0).mean() - 2 * stats.norm.sf(4.0)) < 2e-5
+    # truncation bias and clipping of the fused output
+    img = synth(1000, 256, 1024)
+    out = orc.add_philox_noise(img, f[:img.size]).astype(np.int32)
+    mid = (img >= 70) & (img <= 185)
+    d = (out - img)[mid]
+    assert abs(d.mean() + 0.5) < 0.05 and abs(d.std() - 15.0) < 0.05
+    assert 0.020 < (out == 0).mean() < 0.029 and 0.020 < (out == 255).mean() < 0.029

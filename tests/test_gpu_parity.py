@@ -180,13 +180,19 @@ def test_philox_field_and_fused_output(torch_):
         n = 3 * h * w
         want = orc.philox_noise_field(n, 15.0, seed, first + i, off)
         assert np.max(np.abs(f[e:e + n] - want)) < 2e-3, i
-        # the fused kernel adds exactly the field it reports
-        assert np.array_equal(outs[i], orc.add_noise_field(img, f[e:e + n].reshape(h, w, 3))), i
+        # the fused kernel adds the field it reports: clamp(v + floor(noise), 0, 255); the dumped field is the
+        # fp32-rounded product, the kernel floors the unrounded one, so a byte may differ only where noise is
+        # within an ulp of an integer
+        mism = outs[i] != orc.add_philox_noise(img, f[e:e + n])
+        assert mism.mean() < 1e-4, i
+        assert np.abs(outs[i].astype(int) - orc.add_philox_noise(img, want)).max() <= 1 and \
+            (outs[i] != orc.add_philox_noise(img, want)).mean() < 1e-3, i
         e += n
-    # compat path on the dumped field gives the same bytes (device-resident supplied-noise mode)
+    # compat path on the dumped field (device-resident supplied-noise mode) agrees up to the reference's
+    # float32 rounding of v + noise
     dst2 = torch_.zeros_like(src)
     plan.noise(src, dst2, field, 15.0)
-    assert torch_.equal(dst, dst2)
+    assert (dst != dst2).float().mean().item() < 1e-4
 
 
 def test_philox_statistics_and_reproducibility(torch_):
@@ -260,8 +266,8 @@ def test_uniform_batch_all_ops(torch_):
     assert np.array_equal(out[1], imgs[1]) and np.array_equal(out[5], imgs[5])
     assert np.array_equal(out[2], orc.apply_motion_blur(imgs[2], 9, 0))
     assert np.array_equal(out[3], orc.apply_lowres(imgs[3], 0.5))
-    fld = orc.philox_noise_field(imgs[4].size, 15.0, 9, 4).astype(np.float32).reshape(imgs[4].shape)
-    assert np.mean(out[4] != orc.add_noise_field(imgs[4], fld)) < 1e-3  # float-vs-double field at .0 boundaries
+    fld = orc.philox_noise_field(imgs[4].size, 15.0, 9, 4)
+    assert np.mean(out[4] != orc.add_philox_noise(imgs[4], fld)) < 1e-3  # float-vs-double field at .0 boundaries
 
 
 CONFIG3_SHAPES = [(765, 1360), (1050, 1400), (788, 1400), (1078, 1916), (1080, 1920), (1500, 2000), (540, 960),
