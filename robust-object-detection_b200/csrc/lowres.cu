@@ -30,7 +30,8 @@ struct LowresParams {
     int p_pitch;    // bytes per low-res row in shared memory
 };
 
-constexpr int kHxPitch = kLowresTWB + 8;  // u16 elements per hx row (rows stay 16-byte aligned)
+constexpr int kHxPitch = kLowresTWB + 8;
+
 
 __device__ __forceinline__ uint32_t ldg32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 
@@ -270,8 +271,13 @@ __device__ __forceinline__ void x2_load_row(const uint8_t* prow, int chunk, floa
     x2_expand24(win, x);
 }
 
+__device__ __forceinline__ void stg8(void* p, uint32_t lo, uint32_t hi) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+}
+// HINT: the caller knows (uniformly) whether every row start is 8-byte aligned (`al8`)
+template <bool HINT = false>
 __device__ __forceinline__ void x2_emit_row(const float* xlo, const float* xhi, const X2Row& rc, uint8_t* dptr,
-                                            int nvalid) {
+                                            int nvalid, bool al8 = false) {
     uint32_t o[24];
 #pragma unroll
     for (int t = 0; t < 24; ++t) o[t] = x2_vertical(xlo[t], xhi[t], rc);
@@ -282,7 +288,11 @@ __device__ __forceinline__ void x2_emit_row(const float* xlo, const float* xhi, 
         const uint32_t hi = __byte_perm(o[4 * g + 2], o[4 * g + 3], 0x0040);
         wds[g] = __byte_perm(lo, hi, 0x5410);
     }
-    if (nvalid == 24) {
+    if (HINT && al8 && nvalid == 24) {
+        stg8(dptr, wds[0], wds[1]);
+        stg8(dptr + 8, wds[2], wds[3]);
+        stg8(dptr + 16, wds[4], wds[5]);
+    } else if (nvalid == 24) {
         store_chunk8(dptr, wds[0], wds[1], 8);
         store_chunk8(dptr + 8, wds[2], wds[3], 8);
         store_chunk8(dptr + 16, wds[4], wds[5], 8);
@@ -415,6 +425,169 @@ __global__ void __launch_bounds__(NT, MINB) lowres_x2_kernel(LowresX2Params p) {
     }
 }
 
+// =====================================================================================
+// Warp-marching kernel for exact-2x widths (w % 4 == 0, 4-byte aligned rows): no shared memory, no block barrier.
+// A work item is a column strip of 30 output chunks (8 pixels = 24 bytes each) x a band of output rows of one
+// image; one warp owns it and walks down the rows.  Lane l holds chunk 30*strip - 1 + l, so lanes 0 and 31 are
+// halo lanes: they compute low-res pixels like everybody else but store nothing.
+//   * a low-res row is produced ONCE per lane, in registers: the lane loads its own 24 source bytes of each tap
+//     row (coalesced 768 B per warp and row), forms its four low-res pixels (same arithmetic as the strip kernel),
+//     and gets the neighbouring low-res pixel on either side by warp shuffle;
+//   * the source words of the NEXT low-res row are already in flight while the current one is processed
+//     (register prefetch), so global-load latency is off the critical path;
+//   * the horizontal 2x stage of each low-res row is expanded once into 24 floats (parity slots xe / xo) and
+//     reused by the two or three output rows that blend it; the vertical stage is x2_vertical (3 FFMA.RZ / byte).
+// The low-resolution intermediate never leaves the register file.
+// =====================================================================================
+struct LowresX2wParams {
+    const DevImage* images;
+    const Tile* tiles;   // a = first output row of the band, b = end row (exclusive), c = column strip
+    int n_tiles;
+    const DevShape* shapes;
+    const uint32_t* tab;
+    const uint8_t* src;
+    uint8_t* dst;
+    const uint8_t* opcodes;
+};
+
+constexpr int kX2wChunksPerStrip = 30;
+
+struct X2wCtx {
+    const uint8_t* scol;     // this lane's source column: simg + 24 * chunk
+    int64_t pitch;
+    const uint4* ypack;
+    int h;
+    bool fast2, al8, second_unit;  // second_unit: the chunk has four low-res pixels (else two: last chunk, w % 8 == 4)
+    bool first_chunk, last_chunk;
+};
+
+// issue the loads of the source words low-res row j needs (3 tap rows x 24 bytes; tap 2 unused for fast2)
+__device__ __forceinline__ void x2w_prefetch(const X2wCtx& c, int j, uint32_t rw[3][6]) {
+    int sy0 = 2 * j;
+    if (!c.fast2) sy0 = (int)__ldg(&c.ypack[j].x);
+    const uint8_t* r0 = c.scol + (int64_t)sy0 * c.pitch;
+    const uint8_t* r1 = r0 + c.pitch;
+    const uint8_t* r2 = c.scol + (int64_t)min(sy0 + 2, c.h - 1) * c.pitch;
+    const int o2 = c.second_unit ? 12 : 0;  // a two-pixel chunk re-reads its first unit (the result is discarded)
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        if (t == 2 && c.fast2) break;
+        const uint8_t* r = (t == 0) ? r0 : (t == 1) ? r1 : r2;
+        if (c.al8 && c.second_unit) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2*>(r));
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(r + 8));
+            const uint2 d = __ldg(reinterpret_cast<const uint2*>(r + 16));
+            rw[t][0] = a.x; rw[t][1] = a.y; rw[t][2] = b.x; rw[t][3] = b.y; rw[t][4] = d.x; rw[t][5] = d.y;
+        } else {
+            rw[t][0] = ldg32(r); rw[t][1] = ldg32(r + 4); rw[t][2] = ldg32(r + 8);
+            rw[t][3] = ldg32(r + o2); rw[t][4] = ldg32(r + o2 + 4); rw[t][5] = ldg32(r + o2 + 8);
+        }
+    }
+}
+
+// the lane's four low-res pixels of row j (12 bytes in own[3]) from the prefetched words
+__device__ __forceinline__ void x2w_reduce(const X2wCtx& c, int j, const uint32_t rw[3][6], uint32_t own[3]) {
+    uint32_t o6[2][6];
+    if (c.fast2) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) area_fast2_unit(&rw[0][3 * hf], &rw[1][3 * hf], o6[hf]);
+    } else {
+        const uint4 pk = __ldg(c.ypack + j);
+        const float b0 = __uint_as_float(pk.y), b1 = __uint_as_float(pk.z), b2 = __uint_as_float(pk.w);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            float acc[6];
+            area_x2f_accumulate(&rw[0][3 * hf], b0, true, acc);
+            area_x2f_accumulate(&rw[1][3 * hf], b1, false, acc);
+            area_x2f_accumulate(&rw[2][3 * hf], b2, false, acc);
+            area_x2f_finish(acc, o6[hf]);
+        }
+    }
+    const uint32_t a01 = __byte_perm(o6[0][0], o6[0][1], 0x0040), a23 = __byte_perm(o6[0][2], o6[0][3], 0x0040);
+    const uint32_t a45 = __byte_perm(o6[0][4], o6[0][5], 0x0040);
+    const uint32_t c01 = __byte_perm(o6[1][0], o6[1][1], 0x0040), c23 = __byte_perm(o6[1][2], o6[1][3], 0x0040);
+    const uint32_t c45 = __byte_perm(o6[1][4], o6[1][5], 0x0040);
+    own[0] = __byte_perm(a01, a23, 0x5410);
+    own[1] = __byte_perm(a45, c01, 0x5410);
+    own[2] = __byte_perm(c23, c45, 0x5410);
+    if (!c.second_unit) {  // two-pixel last chunk: pixel 2 := pixel 1 (OpenCV's clamped right tap P[nw] = P[nw-1])
+        own[2] = __byte_perm(own[1], 0u, 0x4441);             // byte 8 = byte 5
+        own[1] = __byte_perm(own[0], own[1], 0x4354);         // bytes 4,5 kept; bytes 6,7 = bytes 3,4
+    }
+}
+
+// own 12 bytes + the neighbouring pixels (by shuffle, or replicated at the image border) -> 24 horizontal-stage floats
+__device__ __forceinline__ void x2w_expand(const X2wCtx& c, const uint32_t own[3], float x[24]) {
+    const uint32_t from_left = __shfl_up_sync(0xFFFFFFFFu, own[2], 1);     // left lane's last pixel = its bytes 9..11
+    const uint32_t from_right = __shfl_down_sync(0xFFFFFFFFu, own[0], 1);  // right lane's first pixel = its bytes 0..2
+    const uint32_t w0 = c.first_chunk ? (own[0] << 8) : (from_left & 0xFFFFFF00u);
+    const uint32_t w4 = c.last_chunk ? (own[2] >> 8) : (from_right & 0x00FFFFFFu);
+    const uint32_t win[5] = {funnel_r(w0, own[0], 8), funnel_r(own[0], own[1], 8), funnel_r(own[1], own[2], 8),
+                             funnel_r(own[2], w4, 8), w4 >> 8};
+    x2_expand24(win, x);
+}
+
+__global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int ti = blockIdx.x * wpb + warp; ti < p.n_tiles; ti += gridDim.x * wpb) {
+        const Tile t = p.tiles[ti];
+        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
+        const DevImage im = p.images[t.img];
+        const DevShape sh = p.shapes[im.shape_id];
+        const uint8_t* simg = p.src + im.src_off;
+        uint8_t* dimg = p.dst + im.dst_off;
+        const int n = 3 * im.w, nw = sh.nw;
+        const int nchunks = (im.w + 7) >> 3;
+        const int ch = kX2wChunksPerStrip * t.c - 1 + lane;
+        const bool cvalid = ch >= 0 && ch < nchunks;
+        const int cc = min(max(ch, 0), nchunks - 1);
+        X2wCtx c;
+        c.scol = simg + 24 * cc;
+        c.pitch = im.src_pitch;
+        c.ypack = reinterpret_cast<const uint4*>(p.tab + sh.ay_pack);
+        c.h = im.h;
+        c.fast2 = (sh.area_mode == AREA_FAST2);
+        c.al8 = ((((uintptr_t)simg) | (uintptr_t)im.src_pitch) & 7) == 0;
+        c.second_unit = (nw - 4 * cc) >= 4;
+        c.first_chunk = (cc == 0);
+        c.last_chunk = (cc == nchunks - 1);
+        const int nvalid = (cvalid && lane >= 1 && lane <= kX2wChunksPerStrip) ? min(24, n - 24 * cc) : 0;
+        const bool dst_al8 = ((((uintptr_t)dimg) | (uintptr_t)im.dst_pitch) & 7) == 0;
+        const uint32_t* ly_s = p.tab + sh.ly_s;
+        const float4* ly_rc = reinterpret_cast<const float4*>(p.tab + sh.ly_rc);
+        const int Y0 = t.a, Y1 = t.b;
+        const int j_first = (int)(ly_s[Y0] & 0xFFFFu), j_last = (int)(ly_s[Y1 - 1] >> 16);
+
+        uint32_t rw[3][6];
+        float xe[24], xo[24];  // horizontal stage of the even / odd low-res row currently held
+        int have = j_first - 1;  // highest low-res row produced so far
+        x2w_prefetch(c, j_first, rw);
+        uint8_t* dptr = dimg + (int64_t)Y0 * im.dst_pitch + 24 * cc;
+        for (int r = Y0; r < Y1; ++r, dptr += im.dst_pitch) {
+            const uint32_t ys = ly_s[r];
+            const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+            while (have < s1) {
+                ++have;
+                uint32_t own[3];
+                x2w_reduce(c, have, rw, own);
+                if (have < j_last) x2w_prefetch(c, have + 1, rw);
+                if (have & 1) x2w_expand(c, own, xo);
+                else x2w_expand(c, own, xe);
+            }
+            const float4 rf = ly_rc[r];
+            X2Row rc;
+            rc.c0s = rf.x; rc.c1s = rf.y; rc.k0 = rf.z; rc.k2 = rf.w;
+            if (s0 & 1) {
+                if (s1 & 1) x2_emit_row<true>(xo, xo, rc, dptr, nvalid, dst_al8);
+                else x2_emit_row<true>(xo, xe, rc, dptr, nvalid, dst_al8);
+            } else {
+                if (s1 & 1) x2_emit_row<true>(xe, xo, rc, dptr, nvalid, dst_al8);
+                else x2_emit_row<true>(xe, xe, rc, dptr, nvalid, dst_al8);
+            }
+        }
+    }
+}
+
 int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
                   cudaStream_t stream, int img_lo, int img_hi) {
     // generic tiles (shapes that are not exact-2x in x)
@@ -439,13 +612,31 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             ROD_CUDA(cudaGetLastError());
         }
     }
-    // full-width strips of exact-2x shapes
+    // exact-2x shapes: warp-marching kernel when the rows are 4-byte aligned, full-width strips otherwise
+    const bool use_bands = plan->n_lowres_x2w_tiles > 0 && (((uintptr_t)src) & 3) == 0;
+    if (use_bands) {
+        const int t_lo = plan->lowres_x2w_tile_start[img_lo], t_hi = plan->lowres_x2w_tile_start[img_hi];
+        if (t_hi > t_lo) {
+            LowresX2wParams p;
+            p.images = plan->d_images;
+            p.tiles = plan->d_lowres_x2w_tiles + t_lo;
+            p.n_tiles = t_hi - t_lo;
+            p.shapes = plan->d_shapes;
+            p.tab = plan->d_tab;
+            p.src = src; p.dst = dst; p.opcodes = opcodes;
+            const int ctas = (p.n_tiles + 3) / 4;
+            lowres_x2w_kernel<<<grid_for(plan, ctas, 4), 128, 0, stream>>>(p);
+            ROD_CUDA(cudaGetLastError());
+        }
+    }
     {
-        const int t_lo = plan->lowres_x2_tile_start[img_lo], t_hi = plan->lowres_x2_tile_start[img_hi];
+        const std::vector<int>& starts = use_bands ? plan->lowres_x2_rest_tile_start : plan->lowres_x2_tile_start;
+        const Tile* tiles = use_bands ? plan->d_lowres_x2_rest_tiles : plan->d_lowres_x2_tiles;
+        const int t_lo = starts[img_lo], t_hi = starts[img_hi];
         if (t_hi > t_lo) {
             LowresX2Params p;
             p.images = plan->d_images;
-            p.tiles = plan->d_lowres_x2_tiles + t_lo;
+            p.tiles = tiles + t_lo;
             p.n_tiles = t_hi - t_lo;
             p.shapes = plan->d_shapes;
             p.tab = plan->d_tab;

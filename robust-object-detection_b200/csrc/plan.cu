@@ -60,22 +60,60 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         max_cols = std::max(max_cols, cols);
     }
     if (blob.empty()) blob.push_back(0);
-    std::vector<Tile> gen_tiles, x2_tiles;
+    // warp-marching kernel: one tile = (band of rows, strip of 30 chunks); band height from the amount of work
+    // (aim at >= 4 tiles per resident warp; 16 warps per SM)
+    const char* e_march = getenv("ROD_X2_MARCH");
+    const bool march = !(e_march && atoi(e_march) == 0);
+    auto march_image = [&](int i) {
+        const DevImage& im = plan->h_images[i];
+        return shapes[im.shape_id].x2w != 0 && (im.src_pitch & 3) == 0 && (im.src_off & 3) == 0;
+    };
+    auto n_strips = [&](int w) { return ((w + 7) / 8 + 29) / 30; };
+    int band_rows = 0;
+    if (march) {
+        long long strip_rows = 0;
+        for (int i = 0; i < plan->n_images; ++i)
+            if (march_image(i)) strip_rows += (long long)plan->h_images[i].h * n_strips(plan->h_images[i].w);
+        const char* e_band = getenv("ROD_X2_BAND");
+        band_rows = e_band ? atoi(e_band) : (int)(strip_rows / (64LL * plan->sm_count));
+        band_rows = std::max(24, std::min(512, band_rows & ~7));
+    }
+    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2_rest_tiles;
     build_strip_tiles(plan->h_images, shapes, false, kLowresTH, kLowresTWB, gen_tiles);
     build_strip_tiles(plan->h_images, shapes, true, kLowresTH, kLowresTWB, x2_tiles);
-    void* old[] = {plan->d_shapes, plan->d_tab, plan->d_lowres_tiles, plan->d_lowres_x2_tiles};
+    for (int i = 0; i < plan->n_images; ++i) {
+        const DevShape& sh = shapes[plan->h_images[i].shape_id];
+        if (sh.strip_rows <= 0) continue;
+        if (march && march_image(i)) {
+            for (int y = 0; y < plan->h_images[i].h; y += band_rows)
+                for (int st = 0; st < n_strips(plan->h_images[i].w); ++st)
+                    x2w_tiles.push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows), st});
+        } else {
+            for (int y = 0; y < plan->h_images[i].h; y += sh.strip_rows) x2_rest_tiles.push_back(Tile{i, y, 0, 0});
+        }
+    }
+    void* old[] = {plan->d_shapes, plan->d_tab, plan->d_lowres_tiles, plan->d_lowres_x2_tiles, plan->d_lowres_x2w_tiles,
+                   plan->d_lowres_x2_rest_tiles};
     for (void* q : old)
         if (q) cudaFree(q);
     plan->d_shapes = nullptr; plan->d_tab = nullptr; plan->d_lowres_tiles = nullptr; plan->d_lowres_x2_tiles = nullptr;
+    plan->d_lowres_x2w_tiles = nullptr; plan->d_lowres_x2_rest_tiles = nullptr;
     int rc = upload(shapes, &plan->d_shapes);
     if (rc == ROD_OK) rc = upload(blob, &plan->d_tab);
     if (rc == ROD_OK) rc = upload(gen_tiles, &plan->d_lowres_tiles);
     if (rc == ROD_OK) rc = upload(x2_tiles, &plan->d_lowres_x2_tiles);
+    if (rc == ROD_OK) rc = upload(x2w_tiles, &plan->d_lowres_x2w_tiles);
+    if (rc == ROD_OK) rc = upload(x2_rest_tiles, &plan->d_lowres_x2_rest_tiles);
     if (rc != ROD_OK) return rc;
     plan->n_lowres_tiles = (int)gen_tiles.size();
     plan->n_lowres_x2_tiles = (int)x2_tiles.size();
+    plan->n_lowres_x2w_tiles = (int)x2w_tiles.size();
+    plan->n_lowres_x2_rest_tiles = (int)x2_rest_tiles.size();
     tile_starts(gen_tiles, plan->n_images, plan->lowres_tile_start);
     tile_starts(x2_tiles, plan->n_images, plan->lowres_x2_tile_start);
+    tile_starts(x2w_tiles, plan->n_images, plan->lowres_x2w_tile_start);
+    tile_starts(x2_rest_tiles, plan->n_images, plan->lowres_x2_rest_tile_start);
+    plan->lowres_x2w_band_rows = band_rows;
     plan->lowres_x2_smem = x2_smem;
     plan->lowres_factor = factor;
     plan->lowres_all_identity = all_identity;
@@ -208,7 +246,8 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
 
 extern "C" void rod_plan_destroy(rod_plan* plan) {
     if (plan == nullptr) return;
-    void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles, plan->d_shapes,
+    void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles,
+                    plan->d_lowres_x2w_tiles, plan->d_lowres_x2_rest_tiles, plan->d_shapes,
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};
     for (void* p : ptrs)

@@ -63,6 +63,8 @@ struct DevShape {
     int32_t strip_half_rows;    // x2 kernel: worst-case low-res rows one strip touches
     uint32_t ay_pack;           // x2 kernel, yt <= 3: uint4 per low-res row {first source row, beta0, beta1, beta2 bits}
     int32_t ay_packed;          // 1 when ay_pack is valid
+    uint32_t ly_rc;             // float4 per output row: the vertical-stage constants (X2Row) of the exact-2x kernels
+    int32_t x2w;                // 1: eligible for the warp-marching exact-2x kernel (lowres_x2w_kernel)
 };
 
 // ---------------------------------------------------------------------------------

@@ -56,6 +56,13 @@ struct rod_plan {
     int n_lowres_x2_tiles = 0;
     size_t lowres_x2_smem = 0;
     int lowres_x2_threads = 128;  // CTA size of lowres_x2_kernel (ROD_X2_THREADS=128|256)
+    // warp-marching x2 kernel (4-byte aligned rows of eligible exact-2x shapes): band x strip tiles; the strip-kernel
+    // list restricted to the remaining exact-2x images
+    rod::Tile* d_lowres_x2w_tiles = nullptr;
+    rod::Tile* d_lowres_x2_rest_tiles = nullptr;
+    int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
+    std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
+    int lowres_x2w_band_rows = 0;
     bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
 
     // lowres tables, rebuilt when the factor changes

@@ -156,6 +156,15 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
         sh.lx_a = blob_push(blob, lx.coef);
         sh.ly_s = blob_push(blob, ys);
         sh.ly_b = blob_push(blob, ly.coef);
+        if (sh.x2) {  // vertical-stage constants of the exact-2x kernels, one float4 per output row
+            std::vector<float> rc((size_t)h * 4);
+            for (int y = 0; y < h; ++y) {
+                const X2Row r = x2_row_consts(ly.coef[y]);
+                rc[4 * y] = r.c0s; rc[4 * y + 1] = r.c1s; rc[4 * y + 2] = r.k0; rc[4 * y + 3] = r.k2;
+            }
+            sh.ly_rc = blob_push(blob, rc);
+            sh.x2w = ((w & 3) == 0 && h >= 2 && (sh.area_mode == AREA_FAST2 || (sh.area_mode == AREA_GENERAL && sh.ay_packed))) ? 1 : 0;
+        }
     }
     *out = sh;
     return true;

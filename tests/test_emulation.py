@@ -25,6 +25,7 @@ def emu(tmp_path_factory):
     lib.emu_blur.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int]
     lib.emu_lowres.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_int]
     lib.emu_lowres_tiled.argtypes = lib.emu_lowres.argtypes
+    lib.emu_lowres_x2w.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_int]
     lib.emu_noise.argtypes = [u8p, u8p, f32p, f32p, ctypes.c_long, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
     lib.emu_letterbox_u8.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return lib
@@ -133,3 +134,23 @@ def test_philox_stream_statistics_cpu():
     d = (out - img)[mid]
     assert abs(d.mean() + 0.5) < 0.05 and abs(d.std() - 15.0) < 0.05
     assert 0.020 < (out == 0).mean() < 0.029 and 0.020 < (out == 255).mean() < 0.029
+
+
+X2W_SHAPES = [(765, 1360), (360, 480), (100, 8), (9, 4), (2, 4), (5, 12), (64, 64), (65, 128), (131, 36), (201, 1400),
+              (97, 1916), (540, 960), (33, 2000), (40, 20), (77, 1364), (50, 240), (51, 244), (52, 248)]
+
+
+@pytest.mark.parametrize("band_rows", [24, 56, 512])
+def test_emu_lowres_warp_marching(emu, band_rows):
+    """lowres_x2w_kernel replayed lane by lane on the CPU: strips of 30 chunks with halo lanes, neighbour pixels by
+    shuffle, border replication, two-pixel last chunks (w % 8 == 4), exact-2x and odd heights, pitched rows."""
+    for i, (h, w) in enumerate(X2W_SHAPES):
+        img = synth(700 + i, h, w)
+        want = orc.apply_lowres(img, 0.5)
+        pitch = 3 * w + (0 if i % 3 else 20)
+        buf = np.full((h, pitch), 0xAB, np.uint8)
+        buf[:, :3 * w] = img.reshape(h, 3 * w)
+        got = np.zeros_like(img)
+        rc = emu.emu_lowres_x2w(_p(buf), _p(got), h, w, pitch, 3 * w, 0.5, band_rows)
+        assert rc == 0, (h, w, rc)
+        assert np.array_equal(got, want), (h, w, band_rows)

@@ -298,6 +298,54 @@ def test_ragged_mixed_resolution_batch(torch_):
         assert np.array_equal(out, orc.add_noise_field(img, fields[i])), (i, shapes[i])
 
 
+def test_lowres_marching_kernel_alignments(torch_):
+    """lowres_x2w_kernel (warp-marching bands x strips): images packed at 4-byte granularity (rows that are not
+    8-byte aligned take the 32-bit load path), widths with a two-pixel last chunk, pitched rows, and a source base
+    that is not 4-byte aligned (falls back to the strip kernel)."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    shapes = [(765, 1360), (360, 480), (100, 8), (9, 4), (2, 4), (5, 12), (64, 64), (65, 128), (131, 36), (201, 1400),
+              (97, 1916), (540, 960), (33, 2000), (40, 20), (77, 1364), (1080, 1920), (1050, 1400), (41, 44)]
+    imgs = [synth(4200 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    want = [orc.apply_lowres(im, 0.5) for im in imgs]
+    for align in (4, 256):
+        plan = CorruptionPlan.ragged(shapes, align=align)
+        packed = plan.pack(imgs)
+        for lead in (0, 1):
+            buf = torch_.zeros(lead + plan.src_bytes, dtype=torch_.uint8, device="cuda")
+            src = buf[lead:]
+            src.copy_(torch_.from_numpy(packed))
+            dst = torch_.zeros(plan.dst_bytes, dtype=torch_.uint8, device="cuda")
+            plan.lowres(src, dst)
+            for i, out in enumerate(plan.unpack(dst.cpu().numpy())):
+                assert np.array_equal(out, want[i]), (align, lead, i, shapes[i])
+    # pitched source and destination rows (crop-like views)
+    sp = [3 * w + 20 for h, w in shapes]
+    dp = [3 * w + 8 for h, w in shapes]
+    so = np.concatenate([[0], np.cumsum([(h * q + 255) // 256 * 256 for (h, w), q in zip(shapes, sp)])])
+    do = np.concatenate([[0], np.cumsum([(h * q + 255) // 256 * 256 for (h, w), q in zip(shapes, dp)])])
+    plan = CorruptionPlan(shapes, so[:-1], do[:-1], src_pitches=sp, dst_pitches=dp)
+    hsrc = np.full(int(so[-1]), 0xAB, np.uint8)
+    for img, o, q in zip(imgs, so, sp):
+        h, w, _ = img.shape
+        hsrc[o:o + h * q].reshape(h, q)[:, :3 * w] = img.reshape(h, 3 * w)
+    src = torch_.from_numpy(hsrc).cuda()
+    dst = torch_.full((int(do[-1]),), 7, dtype=torch_.uint8, device="cuda")
+    plan.lowres(src, dst)
+    hdst = dst.cpu().numpy()
+    for i, (img, o, q) in enumerate(zip(imgs, do, dp)):
+        h, w, _ = img.shape
+        rows = hdst[o:o + h * q].reshape(h, q)
+        assert np.array_equal(rows[:, :3 * w].reshape(h, w, 3), want[i]), (i, shapes[i])
+        assert (rows[:, 3 * w:] == 7).all(), i  # pitch padding untouched
+    # many bands per image and op-code masking
+    plan = CorruptionPlan.uniform(3, 765, 1360)
+    src = torch_.from_numpy(np.stack([imgs[0]] * 3)).cuda()
+    dst = torch_.full_like(src, 9)
+    plan.lowres(src, dst, opcodes=torch_.tensor([3, 0, 3], dtype=torch_.uint8, device="cuda"))
+    out = dst.cpu().numpy()
+    assert np.array_equal(out[0], want[0]) and np.array_equal(out[2], want[0]) and (out[1] == 9).all()
+
+
 def test_full_size_config2_batch_by_replication(torch_):
     """BASELINE config 2 at full size (256 x 765x1360): 8 distinct images repeated 32 times; every
     replica must equal the oracle's output for its source image (bit-exact)."""
