@@ -461,10 +461,15 @@ struct X2wCtx {
     bool first_chunk, last_chunk;
 };
 
-// issue the loads of the source words low-res row j needs (3 tap rows x 24 bytes; tap 2 unused for fast2)
-__device__ __forceinline__ void x2w_prefetch(const X2wCtx& c, int j, uint32_t rw[3][6]) {
+// issue the loads of the source words low-res row j needs (3 tap rows x 24 bytes; tap 2 unused for fast2) and of
+// its packed y table entry {first source row, beta0, beta1, beta2}
+template <bool AL8>
+__device__ __forceinline__ void x2w_prefetch(const X2wCtx& c, int j, uint32_t rw[3][6], uint4& pk) {
     int sy0 = 2 * j;
-    if (!c.fast2) sy0 = (int)__ldg(&c.ypack[j].x);
+    if (!c.fast2) {
+        pk = __ldg(c.ypack + j);
+        sy0 = (int)pk.x;
+    }
     const uint8_t* r0 = c.scol + (int64_t)sy0 * c.pitch;
     const uint8_t* r1 = r0 + c.pitch;
     const uint8_t* r2 = c.scol + (int64_t)min(sy0 + 2, c.h - 1) * c.pitch;
@@ -473,7 +478,7 @@ __device__ __forceinline__ void x2w_prefetch(const X2wCtx& c, int j, uint32_t rw
     for (int t = 0; t < 3; ++t) {
         if (t == 2 && c.fast2) break;
         const uint8_t* r = (t == 0) ? r0 : (t == 1) ? r1 : r2;
-        if (c.al8 && c.second_unit) {
+        if (AL8) {  // rows are 8-byte aligned (and then every chunk has both units: w % 8 == 0)
             const uint2 a = __ldg(reinterpret_cast<const uint2*>(r));
             const uint2 b = __ldg(reinterpret_cast<const uint2*>(r + 8));
             const uint2 d = __ldg(reinterpret_cast<const uint2*>(r + 16));
@@ -485,14 +490,13 @@ __device__ __forceinline__ void x2w_prefetch(const X2wCtx& c, int j, uint32_t rw
     }
 }
 
-// the lane's four low-res pixels of row j (12 bytes in own[3]) from the prefetched words
-__device__ __forceinline__ void x2w_reduce(const X2wCtx& c, int j, const uint32_t rw[3][6], uint32_t own[3]) {
+// the lane's four low-res pixels of a row (12 bytes in own[3]) from the prefetched words and table entry
+__device__ __forceinline__ void x2w_reduce(const X2wCtx& c, const uint4 pk, const uint32_t rw[3][6], uint32_t own[3]) {
     uint32_t o6[2][6];
     if (c.fast2) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) area_fast2_unit(&rw[0][3 * hf], &rw[1][3 * hf], o6[hf]);
     } else {
-        const uint4 pk = __ldg(c.ypack + j);
         const float b0 = __uint_as_float(pk.y), b1 = __uint_as_float(pk.z), b2 = __uint_as_float(pk.w);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -527,6 +531,7 @@ __device__ __forceinline__ void x2w_expand(const X2wCtx& c, const uint32_t own[3
     x2_expand24(win, x);
 }
 
+template <bool AL8>
 __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (int ti = blockIdx.x * wpb + warp; ti < p.n_tiles; ti += gridDim.x * wpb) {
@@ -547,7 +552,7 @@ __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
         c.ypack = reinterpret_cast<const uint4*>(p.tab + sh.ay_pack);
         c.h = im.h;
         c.fast2 = (sh.area_mode == AREA_FAST2);
-        c.al8 = ((((uintptr_t)simg) | (uintptr_t)im.src_pitch) & 7) == 0;
+        c.al8 = AL8;
         c.second_unit = (nw - 4 * cc) >= 4;
         c.first_chunk = (cc == 0);
         c.last_chunk = (cc == nchunks - 1);
@@ -559,24 +564,29 @@ __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
         const int j_first = (int)(ly_s[Y0] & 0xFFFFu), j_last = (int)(ly_s[Y1 - 1] >> 16);
 
         uint32_t rw[3][6];
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
         float xe[24], xo[24];  // horizontal stage of the even / odd low-res row currently held
         int have = j_first - 1;  // highest low-res row produced so far
-        x2w_prefetch(c, j_first, rw);
+        x2w_prefetch<AL8>(c, j_first, rw, pk);
         uint8_t* dptr = dimg + (int64_t)Y0 * im.dst_pitch + 24 * cc;
+        uint32_t ys = ly_s[Y0];
+        float4 rf = ly_rc[Y0];
         for (int r = Y0; r < Y1; ++r, dptr += im.dst_pitch) {
-            const uint32_t ys = ly_s[r];
             const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+            X2Row rc;
+            rc.c0s = rf.x; rc.c1s = rf.y; rc.k0 = rf.z; rc.k2 = rf.w;
+            if (r + 1 < Y1) {  // next row's table entries, one iteration ahead
+                ys = ly_s[r + 1];
+                rf = ly_rc[r + 1];
+            }
             while (have < s1) {
                 ++have;
                 uint32_t own[3];
-                x2w_reduce(c, have, rw, own);
-                if (have < j_last) x2w_prefetch(c, have + 1, rw);
+                x2w_reduce(c, pk, rw, own);
+                if (have < j_last) x2w_prefetch<AL8>(c, have + 1, rw, pk);
                 if (have & 1) x2w_expand(c, own, xo);
                 else x2w_expand(c, own, xe);
             }
-            const float4 rf = ly_rc[r];
-            X2Row rc;
-            rc.c0s = rf.x; rc.c1s = rf.y; rc.k0 = rf.z; rc.k2 = rf.w;
             if (s0 & 1) {
                 if (s1 & 1) x2_emit_row<true>(xo, xo, rc, dptr, nvalid, dst_al8);
                 else x2_emit_row<true>(xo, xe, rc, dptr, nvalid, dst_al8);
@@ -625,7 +635,9 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             const int ctas = (p.n_tiles + 3) / 4;
-            lowres_x2w_kernel<<<grid_for(plan, ctas, 4), 128, 0, stream>>>(p);
+            // 64-bit source loads when every row of every image is 8-byte aligned
+            if (plan->x2w_all_al8 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, 4), 128, 0, stream>>>(p);
+            else lowres_x2w_kernel<false><<<grid_for(plan, ctas, 4), 128, 0, stream>>>(p);
             ROD_CUDA(cudaGetLastError());
         }
     }

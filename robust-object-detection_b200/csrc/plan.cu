@@ -114,6 +114,12 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     tile_starts(x2w_tiles, plan->n_images, plan->lowres_x2w_tile_start);
     tile_starts(x2_rest_tiles, plan->n_images, plan->lowres_x2_rest_tile_start);
     plan->lowres_x2w_band_rows = band_rows;
+    plan->x2w_all_al8 = true;
+    for (int i = 0; i < plan->n_images; ++i)
+        if (march && march_image(i)) {
+            const DevImage& im = plan->h_images[i];
+            if ((im.src_pitch & 7) != 0 || (im.src_off & 7) != 0 || (im.w & 7) != 0) plan->x2w_all_al8 = false;
+        }
     plan->lowres_x2_smem = x2_smem;
     plan->lowres_factor = factor;
     plan->lowres_all_identity = all_identity;

@@ -63,6 +63,7 @@ struct rod_plan {
     int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
     std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
     int lowres_x2w_band_rows = 0;
+    bool x2w_all_al8 = false;  // every x2w image has 8-byte aligned rows and w % 8 == 0
     bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
 
     // lowres tables, rebuilt when the factor changes
