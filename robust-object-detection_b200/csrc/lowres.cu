@@ -452,10 +452,30 @@ struct LowresX2wParams {
 
 constexpr int kX2wChunksPerStrip = 30;
 
+__device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_pinned4(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_pinned16f(const void* p) {
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void ldg_stream8(const void* p, uint32_t& a, uint32_t& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+}
+
 struct X2wCtx {
     const uint8_t* scol;     // this lane's source column: simg + 24 * chunk
     int64_t pitch;
-    const uint4* ypack;
+    const uint4* ypack;      // this warp's shared copy of the packed y table, entry 0 = low-res row j_first
+    int j_first;
     int h;
     bool fast2, al8, second_unit;  // second_unit: the chunk has four low-res pixels (else two: last chunk, w % 8 == 4)
     bool first_chunk, last_chunk;
@@ -467,7 +487,7 @@ template <bool AL8>
 __device__ __forceinline__ void x2w_prefetch(const X2wCtx& c, int j, uint32_t rw[3][6], uint4& pk) {
     int sy0 = 2 * j;
     if (!c.fast2) {
-        pk = __ldg(c.ypack + j);
+        pk = c.ypack[j - c.j_first];
         sy0 = (int)pk.x;
     }
     const uint8_t* r0 = c.scol + (int64_t)sy0 * c.pitch;
@@ -478,14 +498,14 @@ __device__ __forceinline__ void x2w_prefetch(const X2wCtx& c, int j, uint32_t rw
     for (int t = 0; t < 3; ++t) {
         if (t == 2 && c.fast2) break;
         const uint8_t* r = (t == 0) ? r0 : (t == 1) ? r1 : r2;
+        // streaming loads that do not allocate in L1: the small per-row tables stay resident there
         if (AL8) {  // rows are 8-byte aligned (and then every chunk has both units: w % 8 == 0)
-            const uint2 a = __ldg(reinterpret_cast<const uint2*>(r));
-            const uint2 b = __ldg(reinterpret_cast<const uint2*>(r + 8));
-            const uint2 d = __ldg(reinterpret_cast<const uint2*>(r + 16));
-            rw[t][0] = a.x; rw[t][1] = a.y; rw[t][2] = b.x; rw[t][3] = b.y; rw[t][4] = d.x; rw[t][5] = d.y;
+            ldg_stream8(r, rw[t][0], rw[t][1]);
+            ldg_stream8(r + 8, rw[t][2], rw[t][3]);
+            ldg_stream8(r + 16, rw[t][4], rw[t][5]);
         } else {
-            rw[t][0] = ldg32(r); rw[t][1] = ldg32(r + 4); rw[t][2] = ldg32(r + 8);
-            rw[t][3] = ldg32(r + o2); rw[t][4] = ldg32(r + o2 + 4); rw[t][5] = ldg32(r + o2 + 8);
+            rw[t][0] = ldg_stream4(r); rw[t][1] = ldg_stream4(r + 4); rw[t][2] = ldg_stream4(r + 8);
+            rw[t][3] = ldg_stream4(r + o2); rw[t][4] = ldg_stream4(r + o2 + 4); rw[t][5] = ldg_stream4(r + o2 + 8);
         }
     }
 }
@@ -531,9 +551,21 @@ __device__ __forceinline__ void x2w_expand(const X2wCtx& c, const uint32_t own[3
     x2_expand24(win, x);
 }
 
+// per-warp shared tables of one band (loads from shared memory use the short scoreboard, so waiting for a table
+// entry never waits for the source prefetch that is in flight on the long scoreboard)
+constexpr int kX2wMaxBandRows = 256;
+constexpr int kX2wMaxLowRows = kX2wMaxBandRows / 2 + 8;
+struct X2wWarpTables {
+    float4 rc[kX2wMaxBandRows];   // vertical-stage constants per output row
+    uint4 pk[kX2wMaxLowRows];     // {first source row, beta0, beta1, beta2} per low-res row
+    uint32_t ys[kX2wMaxBandRows]; // s0 | s1 << 16 per output row
+};
+
 template <bool AL8>
 __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    X2wWarpTables& tb = reinterpret_cast<X2wWarpTables*>(smem)[warp];
     for (int ti = blockIdx.x * wpb + warp; ti < p.n_tiles; ti += gridDim.x * wpb) {
         const Tile t = p.tiles[ti];
         if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
@@ -546,10 +578,15 @@ __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
         const int ch = kX2wChunksPerStrip * t.c - 1 + lane;
         const bool cvalid = ch >= 0 && ch < nchunks;
         const int cc = min(max(ch, 0), nchunks - 1);
+        const uint32_t* ly_s = p.tab + sh.ly_s;
+        const float4* ly_rc = reinterpret_cast<const float4*>(p.tab + sh.ly_rc);
+        const int Y0 = t.a, Y1 = t.b;
+        const int j_first = (int)(ly_s[Y0] & 0xFFFFu), j_last = (int)(ly_s[Y1 - 1] >> 16);
         X2wCtx c;
         c.scol = simg + 24 * cc;
         c.pitch = im.src_pitch;
-        c.ypack = reinterpret_cast<const uint4*>(p.tab + sh.ay_pack);
+        c.ypack = tb.pk;
+        c.j_first = j_first;
         c.h = im.h;
         c.fast2 = (sh.area_mode == AREA_FAST2);
         c.al8 = AL8;
@@ -558,10 +595,17 @@ __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
         c.last_chunk = (cc == nchunks - 1);
         const int nvalid = (cvalid && lane >= 1 && lane <= kX2wChunksPerStrip) ? min(24, n - 24 * cc) : 0;
         const bool dst_al8 = ((((uintptr_t)dimg) | (uintptr_t)im.dst_pitch) & 7) == 0;
-        const uint32_t* ly_s = p.tab + sh.ly_s;
-        const float4* ly_rc = reinterpret_cast<const float4*>(p.tab + sh.ly_rc);
-        const int Y0 = t.a, Y1 = t.b;
-        const int j_first = (int)(ly_s[Y0] & 0xFFFFu), j_last = (int)(ly_s[Y1 - 1] >> 16);
+
+        __syncwarp();  // the previous band's tables are dead
+        for (int i = lane; i < Y1 - Y0; i += 32) {
+            tb.ys[i] = ly_s[Y0 + i];
+            tb.rc[i] = ly_rc[Y0 + i];
+        }
+        if (!c.fast2) {
+            const uint4* ypack = reinterpret_cast<const uint4*>(p.tab + sh.ay_pack);
+            for (int i = lane; i <= j_last - j_first; i += 32) tb.pk[i] = ypack[j_first + i];
+        }
+        __syncwarp();
 
         uint32_t rw[3][6];
         uint4 pk = make_uint4(0u, 0u, 0u, 0u);
@@ -569,16 +613,12 @@ __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
         int have = j_first - 1;  // highest low-res row produced so far
         x2w_prefetch<AL8>(c, j_first, rw, pk);
         uint8_t* dptr = dimg + (int64_t)Y0 * im.dst_pitch + 24 * cc;
-        uint32_t ys = ly_s[Y0];
-        float4 rf = ly_rc[Y0];
         for (int r = Y0; r < Y1; ++r, dptr += im.dst_pitch) {
+            const uint32_t ys = tb.ys[r - Y0];
+            const float4 rf = tb.rc[r - Y0];
             const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
             X2Row rc;
             rc.c0s = rf.x; rc.c1s = rf.y; rc.k0 = rf.z; rc.k2 = rf.w;
-            if (r + 1 < Y1) {  // next row's table entries, one iteration ahead
-                ys = ly_s[r + 1];
-                rf = ly_rc[r + 1];
-            }
             while (have < s1) {
                 ++have;
                 uint32_t own[3];
@@ -636,8 +676,9 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             const int ctas = (p.n_tiles + 3) / 4;
             // 64-bit source loads when every row of every image is 8-byte aligned
-            if (plan->x2w_all_al8 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, 4), 128, 0, stream>>>(p);
-            else lowres_x2w_kernel<false><<<grid_for(plan, ctas, 4), 128, 0, stream>>>(p);
+            const size_t smem = 4 * sizeof(X2wWarpTables);
+            if (plan->x2w_all_al8 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, 4), 128, smem, stream>>>(p);
+            else lowres_x2w_kernel<false><<<grid_for(plan, ctas, 4), 128, smem, stream>>>(p);
             ROD_CUDA(cudaGetLastError());
         }
     }
