@@ -13,6 +13,8 @@
 //   phase C1: horizontal fixed-point pass  hx = (P[s0]*a0 + P[s1]*a1) >> 4   (u16, smem)
 //   phase C2: vertical pass + pack.  Each thread owns 8 byte columns and marches down 8 rows,
 //             keeping the two live hx rows in registers; one 64-bit store per row.
+#include <algorithm>
+
 #include "rod_internal.h"
 
 namespace rod {
@@ -28,6 +30,7 @@ struct LowresParams {
     const uint8_t* opcodes;
     int half_rows;  // allocation (worst case over the plan): low-res rows one tile touches
     int p_pitch;    // bytes per low-res row in shared memory
+    int hb_pitch;   // floats per source row of the horizontal INTER_AREA buffer
 };
 
 constexpr int kHxPitch = kLowresTWB + 8;
@@ -59,8 +62,9 @@ __device__ __forceinline__ void store_chunk8(uint8_t* p, uint32_t lo, uint32_t h
 __global__ void __launch_bounds__(256, 3) lowres_kernel(LowresParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* P = smem;
-    uint16_t* hx = reinterpret_cast<uint16_t*>(smem + (size_t)p.half_rows * p.p_pitch);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* un = smem + (((size_t)p.half_rows * p.p_pitch + 15) & ~(size_t)15);
+    float* hbuf = reinterpret_cast<float*>(un);       // phase B: horizontal INTER_AREA pass, [source row][low-res byte col]
+    uint16_t* hx = reinterpret_cast<uint16_t*>(un);   // phase C: horizontal INTER_LINEAR pass (same bytes, later)
 
     for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
         const Tile t = p.tiles[ti];
@@ -74,123 +78,113 @@ __global__ void __launch_bounds__(256, 3) lowres_kernel(LowresParams p) {
         const int th = min(kLowresTH, im.h - y0), twb = min(kLowresTWB, n - b0);
 
         if (sh.lin_identity) {  // factor maps (h, w) onto itself: both resizes are copies
-            for (int r = warp; r < th; r += 8)
-                for (int o = lane; o < twb; o += 32)
-                    dimg[(int64_t)(y0 + r) * im.dst_pitch + b0 + o] = simg[(int64_t)(y0 + r) * im.src_pitch + b0 + o];
+            for (int idx = threadIdx.x; idx < th * twb; idx += 256) {
+                const int r = idx / twb, o = idx - r * twb;
+                dimg[(int64_t)(y0 + r) * im.dst_pitch + b0 + o] = simg[(int64_t)(y0 + r) * im.src_pitch + b0 + o];
+            }
             continue;
         }
         const uint32_t* ly_s = p.tab + sh.ly_s;
         const uint32_t* ly_b = p.tab + sh.ly_b;
+        const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + sh.lx_s0);
+        const uint32_t* lx_a = p.tab + sh.lx_a;
         const int x_first = b0 / 3, x_last = (b0 + twb - 1) / 3;
         const int j_lo = (int)(ly_s[y0] & 0xFFFFu), j_hi = (int)(ly_s[y0 + th - 1] >> 16);
         const int nj = j_hi - j_lo + 1;
-        const bool x2 = (sh.x2 != 0);
-        const bool vec = x2 && (sh.area_mode == AREA_FAST2 || sh.area_mode == AREA_GENERAL) &&
-                         ((((uintptr_t)simg) | (uintptr_t)im.src_pitch) & 3) == 0 && (im.w & 3) == 0;
-        int i_lo, i_hi;  // low-res pixel columns held in P (P column 0 is pixel i_base)
-        if (x2) {
-            i_lo = max(0, (x_first - 1) >> 1);
-            i_hi = min(max(0, (x_last - 1) >> 1) + 1, sh.nw - 1);
-        } else {
-            const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + sh.lx_s0);
-            i_lo = lx_s0[x_first];
-            i_hi = min(lx_s0[x_last] + 1, sh.nw - 1);
-        }
-        const int i_base = vec ? (i_lo & ~1) : i_lo;
+        const int i_lo = lx_s0[x_first], i_hi = min(lx_s0[x_last] + 1, sh.nw - 1);  // low-res pixel columns held in P
+        const int ncol = 3 * (i_hi - i_lo + 1);
+        const bool general = (sh.area_mode == AREA_GENERAL);
+        const int32_t* xfirst = reinterpret_cast<const int32_t*>(p.tab + sh.ax_first);
+        const int32_t* xcount = reinterpret_cast<const int32_t*>(p.tab + sh.ax_count);
+        const float* xalpha = reinterpret_cast<const float*>(p.tab + sh.ax_alpha);
+        const int32_t* yfirst = reinterpret_cast<const int32_t*>(p.tab + sh.ay_first);
+        const int32_t* ycount = reinterpret_cast<const int32_t*>(p.tab + sh.ay_count);
+        const float* yalpha = reinterpret_cast<const float*>(p.tab + sh.ay_alpha);
+        // source rows the tile's low-res rows read
+        const int sy_lo = general ? yfirst[j_lo] : j_lo * sh.iy;
+        const int sy_hi = general ? yfirst[j_hi] + ycount[j_hi] - 1 : j_hi * sh.iy + sh.iy - 1;
+        const int nsr = sy_hi - sy_lo + 1;
 
-        // ---- phase B: low-res tile P[jr][3 * (i - i_base) + c]
-        if (vec) {
-            const int u_lo = i_base >> 1, n_units = (i_hi >> 1) - u_lo + 1;
-            if (sh.area_mode == AREA_FAST2) {
-                for (int jr = warp; jr < nj; jr += 8) {
-                    const uint8_t* r0 = simg + (int64_t)(2 * (j_lo + jr)) * im.src_pitch;
-                    const uint8_t* r1 = r0 + im.src_pitch;
-                    uint8_t* prow = P + jr * p.p_pitch;
-                    for (int u = lane; u < n_units; u += 32) {
-                        const int sb = 12 * (u_lo + u);
-                        const uint32_t ra[3] = {ldg32(r0 + sb), ldg32(r0 + sb + 4), ldg32(r0 + sb + 8)};
-                        const uint32_t rb[3] = {ldg32(r1 + sb), ldg32(r1 + sb + 4), ldg32(r1 + sb + 8)};
-                        uint32_t s[6];
-                        area_fast2_unit(ra, rb, s);
-                        uint16_t* o16 = reinterpret_cast<uint16_t*>(prow + 6 * u);
-                        o16[0] = (uint16_t)(s[0] | (s[1] << 8));
-                        o16[1] = (uint16_t)(s[2] | (s[3] << 8));
-                        o16[2] = (uint16_t)(s[4] | (s[5] << 8));
-                    }
+        // ---- phase B1: horizontal INTER_AREA pass (OpenCV's resizeArea_ / resizeAreaFast_ row buffer), one thread
+        //      per low-res byte column walking down the source rows: hbuf[sr][o]
+        for (int o = threadIdx.x; o < ncol; o += 256) {
+            const int ir = o / 3, cch = o - 3 * ir, dx = i_lo + ir;
+            const int sx0 = general ? xfirst[dx] : dx * sh.ix;
+            const int nx = general ? xcount[dx] : sh.ix;
+            const uint8_t* sp = simg + (int64_t)sy_lo * im.src_pitch + 3 * sx0 + cch;
+            float* hb = hbuf + o;
+            if (general && nx <= 4) {
+                // taps beyond nx carry weight 0 (adding +0 is exact) and re-read the last valid tap
+                float al[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) al[q] = (q < nx) ? xalpha[dx * sh.xt + q] : 0.f;
+                const int o1 = 3 * min(1, nx - 1), o2 = 3 * min(2, nx - 1), o3 = 3 * min(3, nx - 1);
+                for (int sr = 0; sr < nsr; ++sr, sp += im.src_pitch, hb += p.hb_pitch) {
+                    float buf = fmul((float)sp[0], al[0]);
+                    buf = fadd(buf, fmul((float)sp[o1], al[1]));
+                    buf = fadd(buf, fmul((float)sp[o2], al[2]));
+                    buf = fadd(buf, fmul((float)sp[o3], al[3]));
+                    *hb = buf;
                 }
-            } else {  // exact 2x in x, OpenCV float table in y (e.g. 1360 x 765)
-                const int32_t* yfirst = reinterpret_cast<const int32_t*>(p.tab + sh.ay_first);
-                const int32_t* ycount = reinterpret_cast<const int32_t*>(p.tab + sh.ay_count);
-                const float* yalpha = reinterpret_cast<const float*>(p.tab + sh.ay_alpha);
-                for (int jr = warp; jr < nj; jr += 8) {
-                    const int dy = j_lo + jr;
-                    const int sy0 = yfirst[dy], ny = ycount[dy];
-                    const float* beta = yalpha + dy * sh.yt;
-                    uint8_t* prow = P + jr * p.p_pitch;
-                    for (int u = lane; u < n_units; u += 32) {
-                        const int sb = 12 * (u_lo + u);
-                        float acc[6];
-                        for (int ty = 0; ty < ny; ++ty) {
-                            const uint8_t* r = simg + (int64_t)(sy0 + ty) * im.src_pitch + sb;
-                            const uint32_t rw[3] = {ldg32(r), ldg32(r + 4), ldg32(r + 8)};
-                            area_x2f_accumulate(rw, beta[ty], ty == 0, acc);
-                        }
-                        uint32_t r8[6];
-                        area_x2f_finish(acc, r8);
-                        uint16_t* o16 = reinterpret_cast<uint16_t*>(prow + 6 * u);
-                        o16[0] = (uint16_t)__byte_perm(r8[0], r8[1], 0x0040);
-                        o16[1] = (uint16_t)__byte_perm(r8[2], r8[3], 0x0040);
-                        o16[2] = (uint16_t)__byte_perm(r8[4], r8[5], 0x0040);
-                    }
+            } else if (general) {
+                const float* al = xalpha + dx * sh.xt;
+                for (int sr = 0; sr < nsr; ++sr, sp += im.src_pitch, hb += p.hb_pitch) {
+                    float buf = 0.f;
+                    for (int q = 0; q < nx; ++q) buf = fadd(buf, fmul((float)sp[3 * q], al[q]));
+                    *hb = buf;
+                }
+            } else {  // integer scale: exact sums
+                for (int sr = 0; sr < nsr; ++sr, sp += im.src_pitch, hb += p.hb_pitch) {
+                    uint32_t sum = 0;
+                    for (int q = 0; q < nx; ++q) sum += sp[3 * q];
+                    *hb = (float)sum;
                 }
             }
-        } else {
-            const int ni3 = (i_hi - i_lo + 1) * 3;
-            for (int jr = warp; jr < nj; jr += 8)
-                for (int o = lane; o < ni3; o += 32) {
-                    const int ir = o / 3, c = o - 3 * ir;
-                    P[jr * p.p_pitch + o] = (uint8_t)area_value(simg, im.src_pitch, sh, p.tab, j_lo + jr, i_lo + ir, c);
+        }
+        __syncthreads();
+        // ---- phase B2: vertical INTER_AREA pass -> low-res tile P[jr][o] (u8)
+        for (int o = threadIdx.x; o < ncol; o += 256) {
+            for (int jr = 0; jr < nj; ++jr) {
+                const int j = j_lo + jr;
+                uint32_t v;
+                if (general) {
+                    const int ny = ycount[j];
+                    const float* be = yalpha + j * sh.yt;
+                    const float* hp = hbuf + (yfirst[j] - sy_lo) * p.hb_pitch + o;
+                    float sum = fmul(be[0], hp[0]);
+                    for (int q = 1; q < ny; ++q) sum = fadd(sum, fmul(be[q], hp[q * p.hb_pitch]));
+                    float r = frint(sum);
+                    r = r < 0.f ? 0.f : (r > 255.f ? 255.f : r);
+                    v = (uint32_t)(int)r;
+                } else {
+                    const float* hp = hbuf + (j * sh.iy - sy_lo) * p.hb_pitch + o;
+                    float sum = 0.f;
+                    for (int q = 0; q < sh.iy; ++q) sum += hp[q * p.hb_pitch];  // exact (integers < 2^24)
+                    if (sh.area_mode == AREA_FAST2) {
+                        v = ((uint32_t)sum + 2u) >> 2;
+                    } else {
+                        float r = frint(fmul(sum, sh.inv_area));
+                        r = r < 0.f ? 0.f : (r > 255.f ? 255.f : r);
+                        v = (uint32_t)(int)r;
+                    }
                 }
+                P[jr * p.p_pitch + o] = (uint8_t)v;
+            }
         }
         __syncthreads();
 
-        // ---- phase C1: horizontal pass -> hx[jr][ob] (u16), ob = byte column inside the tile
-        if (x2) {
-            // item = low-res pixel i (all channels): x = 2i+1 gets 3A+B, x = 2i+2 gets A+3B (A = P[i], B = P[i+1],
-            // indices clamped: that reproduces OpenCV's x = 0 and x = W-1 border coefficients 2048/0)
-            const int i_a = ((x_first + 1) >> 1) - 1, i_b = ((x_last + 1) >> 1) - 1;
-            const int ni = i_b - i_a + 1;
-            for (int jr = warp; jr < nj; jr += 8) {
-                const uint8_t* prow = P + jr * p.p_pitch;
-                uint16_t* hrow = hx + jr * kHxPitch;
-                for (int q = lane; q < ni; q += 32) {
-                    const int i = i_a + q;
-                    const uint8_t* pa = prow + 3 * (min(max(i, 0), sh.nw - 1) - i_base);
-                    const uint8_t* pb = prow + 3 * (min(i + 1, sh.nw - 1) - i_base);
-                    const int o1 = 3 * (2 * i + 1) - b0;  // tile byte column of (x = 2i+1, c = 0)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const uint32_t A = (uint32_t)pa[c] << 5, B = (uint32_t)pb[c] << 5;  // hx = 32 * q
-                        const int oa = o1 + c, ob = o1 + 3 + c;
-                        if (oa >= 0 && oa < twb) hrow[oa] = (uint16_t)(3u * A + B);
-                        if (ob >= 0 && ob < twb) hrow[ob] = (uint16_t)(A + 3u * B);
-                    }
-                }
-            }
-        } else {
-            const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + sh.lx_s0);
-            const uint32_t* lx_a = p.tab + sh.lx_a;
-            for (int jr = warp; jr < nj; jr += 8) {
-                const uint8_t* prow = P + jr * p.p_pitch;
-                uint16_t* hrow = hx + jr * kHxPitch;
-                for (int ob = lane; ob < twb; ob += 32) {
-                    const int o = b0 + ob;
-                    const int x = o / 3, c = o - 3 * x;
-                    const int s0 = lx_s0[x];
-                    const int s1 = min(s0 + 1, sh.nw - 1);
-                    hrow[ob] = (uint16_t)linear_h4(prow[(s0 - i_base) * 3 + c], prow[(s1 - i_base) * 3 + c], lx_a[x]);
-                }
-            }
+        // ---- phase C1: horizontal INTER_LINEAR pass -> hx[jr][ob] (u16), one thread per output byte column
+        for (int ob = threadIdx.x; ob < twb; ob += 256) {
+            const int o = b0 + ob;
+            const int x = o / 3, cch = o - 3 * x;
+            const int s0 = lx_s0[x];
+            const int s1 = min(s0 + 1, sh.nw - 1);
+            const uint32_t a = lx_a[x];
+            const uint8_t* pa = P + (s0 - i_lo) * 3 + cch;
+            const uint8_t* pb = P + (s1 - i_lo) * 3 + cch;
+            uint16_t* hrow = hx + ob;
+            for (int jr = 0; jr < nj; ++jr, pa += p.p_pitch, pb += p.p_pitch, hrow += kHxPitch)
+                *hrow = (uint16_t)linear_h4(*pa, *pb, a);
         }
         __syncthreads();
 
@@ -653,7 +647,9 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             p.half_rows = plan->lowres_half_rows;
             p.p_pitch = (3 * (plan->lowres_half_cols + 3) + 15) & ~15;
-            const size_t smem = (size_t)p.half_rows * p.p_pitch + (size_t)p.half_rows * kHxPitch * 2;
+            p.hb_pitch = 3 * plan->lowres_half_cols + 1;
+            const size_t un = std::max((size_t)plan->lowres_src_rows * p.hb_pitch * 4, (size_t)p.half_rows * kHxPitch * 2);
+            const size_t smem = (((size_t)p.half_rows * p.p_pitch + 15) & ~(size_t)15) + un + 16;
             if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
             ROD_CUDA(cudaFuncSetAttribute(lowres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));

@@ -37,7 +37,7 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     std::vector<uint32_t> blob;
     std::vector<DevShape> shapes(plan->shapes.size());
     bool all_identity = true;
-    int max_rows = 1, max_cols = 1;
+    int max_rows = 1, max_cols = 1, max_src_rows = 1;
     size_t x2_smem = 0;
     // tuning knobs (benchmarks only): CTA size, forced strip height, shared-memory budget per CTA
     const char* e_thr = getenv("ROD_X2_THREADS");
@@ -54,10 +54,11 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         all_identity = false;
         x2_smem = std::max(x2_smem, choose_strip_rows(&sh, blob.data(), x2_max_smem, x2_threads, x2_force_rows));
         if (sh.strip_rows > 0) continue;
-        int rows, cols;
-        lowres_tile_footprint(sh, blob.data(), kLowresTH, kLowresTWB, &rows, &cols);
+        int rows, cols, srows;
+        lowres_tile_footprint(sh, blob.data(), kLowresTH, kLowresTWB, &rows, &cols, &srows);
         max_rows = std::max(max_rows, rows);
         max_cols = std::max(max_cols, cols);
+        max_src_rows = std::max(max_src_rows, srows);
     }
     if (blob.empty()) blob.push_back(0);
     // warp-marching kernel: one tile = (band of rows, strip of 30 chunks); band height from the amount of work
@@ -125,6 +126,7 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     plan->lowres_all_identity = all_identity;
     plan->lowres_half_rows = max_rows;
     plan->lowres_half_cols = max_cols;
+    plan->lowres_src_rows = max_src_rows;
     return ROD_OK;
 }
 

@@ -72,6 +72,7 @@ struct rod_plan {
     uint32_t* d_tab = nullptr;
     bool lowres_all_identity = false;
     int lowres_half_rows = 0, lowres_half_cols = 0;  // worst-case low-res rows / cols one tile touches
+    int lowres_src_rows = 0;                          // worst-case source rows one generic tile reads
 
     // letterbox tables, rebuilt when (out_h, out_w) changes
     int lb_out_h = 0, lb_out_w = 0;

@@ -258,14 +258,20 @@ inline void build_grid_tiles(const std::vector<DevImage>& imgs, int th, int twb,
             for (int b = 0; b < 3 * imgs[i].w; b += twb) tiles.push_back(Tile{i, y, b, 0});
 }
 
-// Worst-case low-res footprint (rows, pixel columns) of one lowres tile of this shape.
-inline void lowres_tile_footprint(const DevShape& sh, const uint32_t* blob, int th, int twb, int* rows, int* cols) {
+// Worst-case low-res footprint (rows, pixel columns) and source-row footprint of one lowres tile of this shape.
+inline void lowres_tile_footprint(const DevShape& sh, const uint32_t* blob, int th, int twb, int* rows, int* cols,
+                                  int* src_rows = nullptr) {
     const int32_t* lx = (const int32_t*)(blob + sh.lx_s0);
     const uint32_t* ly = blob + sh.ly_s;
-    int mr = 1, mc = 1;
+    const int32_t* yf = (const int32_t*)(blob + sh.ay_first);
+    const int32_t* yc = (const int32_t*)(blob + sh.ay_count);
+    int mr = 1, mc = 1, ms = 1;
     for (int y0 = 0; y0 < sh.h; y0 += th) {
         const int y1 = std::min(sh.h, y0 + th) - 1;
-        mr = std::max(mr, (int)(ly[y1] >> 16) - (int)(ly[y0] & 0xFFFF) + 1);
+        const int j_lo = (int)(ly[y0] & 0xFFFF), j_hi = (int)(ly[y1] >> 16);
+        mr = std::max(mr, j_hi - j_lo + 1);
+        if (sh.area_mode == AREA_GENERAL) ms = std::max(ms, yf[j_hi] + yc[j_hi] - yf[j_lo]);
+        else ms = std::max(ms, (j_hi - j_lo + 1) * sh.iy);
     }
     for (int b0 = 0; b0 < 3 * sh.w; b0 += twb) {
         const int x0 = b0 / 3, x1 = (std::min(3 * sh.w, b0 + twb) - 1) / 3;
@@ -273,6 +279,7 @@ inline void lowres_tile_footprint(const DevShape& sh, const uint32_t* blob, int 
     }
     *rows = mr;
     *cols = mc;
+    if (src_rows) *src_rows = ms;
 }
 
 }  // namespace rod

@@ -77,6 +77,7 @@ extern "C" int emu_blur(const uint8_t* src, uint8_t* dst, int h, int w, long src
 // `src_phase`: emulated address phase of the source (the vector path needs 4-byte alignment).
 static int emu_lowres_generic(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
                               double factor, int src_phase) {
+    (void)src_phase;
     std::vector<uint32_t> blob;
     DevShape sh;
     if (!build_lowres_shape(h, w, factor, 8, blob, &sh)) return 2;
@@ -90,13 +91,22 @@ static int emu_lowres_generic(const uint8_t* src, uint8_t* dst, int h, int w, lo
     const uint32_t* lx_a = tab + sh.lx_a;
     const uint32_t* ly_s = tab + sh.ly_s;
     const uint32_t* ly_b = tab + sh.ly_b;
-    int half_rows, half_cols;
-    lowres_tile_footprint(sh, tab, kLowresTH, kLowresTWB, &half_rows, &half_cols);
+    const int32_t* xfirst = (const int32_t*)(tab + sh.ax_first);
+    const int32_t* xcount = (const int32_t*)(tab + sh.ax_count);
+    const float* xalpha = (const float*)(tab + sh.ax_alpha);
+    const int32_t* yfirst = (const int32_t*)(tab + sh.ay_first);
+    const int32_t* ycount = (const int32_t*)(tab + sh.ay_count);
+    const float* yalpha = (const float*)(tab + sh.ay_alpha);
+    int half_rows, half_cols, src_rows;
+    lowres_tile_footprint(sh, tab, kLowresTH, kLowresTWB, &half_rows, &half_cols, &src_rows);
     const int p_pitch = (3 * (half_cols + 3) + 15) & ~15;
     const int hx_pitch = kLowresTWB + 8;
+    const int hb_pitch = 3 * half_cols + 1;
     std::vector<uint8_t> P((size_t)half_rows * p_pitch);
     std::vector<uint16_t> hx((size_t)half_rows * hx_pitch);
+    std::vector<float> hbuf((size_t)src_rows * hb_pitch);
     const int n = 3 * w;
+    const bool general = sh.area_mode == AREA_GENERAL;
     for (int y0 = 0; y0 < h; y0 += kLowresTH)
         for (int b0 = 0; b0 < n; b0 += kLowresTWB) {
             const int th = std::min(kLowresTH, h - y0), twb = std::min(kLowresTWB, n - b0);
@@ -104,80 +114,78 @@ static int emu_lowres_generic(const uint8_t* src, uint8_t* dst, int h, int w, lo
             const int j_lo = (int)(ly_s[y0] & 0xFFFFu), j_hi = (int)(ly_s[y0 + th - 1] >> 16);
             const int nj = j_hi - j_lo + 1;
             if (nj > half_rows) return 3;
-            const bool x2 = sh.x2 != 0;
-            const bool vec = x2 && (sh.area_mode == AREA_FAST2 || sh.area_mode == AREA_GENERAL) &&
-                             (((long)src_phase | src_pitch) & 3) == 0 && (w & 3) == 0;
-            int i_lo, i_hi;
-            if (x2) {
-                i_lo = std::max(0, (x_first - 1) >> 1);
-                i_hi = std::min(std::max(0, (x_last - 1) >> 1) + 1, sh.nw - 1);
-            } else {
-                i_lo = lx_s0[x_first];
-                i_hi = std::min(lx_s0[x_last] + 1, sh.nw - 1);
-            }
-            const int i_base = vec ? (i_lo & ~1) : i_lo;
+            const int i_lo = lx_s0[x_first], i_hi = std::min(lx_s0[x_last] + 1, sh.nw - 1);
+            const int i_base = i_lo;
             if (i_hi - i_lo + 1 > half_cols) return 4;
+            const int ncol = 3 * (i_hi - i_lo + 1);
+            const int sy_lo = general ? yfirst[j_lo] : j_lo * sh.iy;
+            const int sy_hi = general ? yfirst[j_hi] + ycount[j_hi] - 1 : j_hi * sh.iy + sh.iy - 1;
+            const int nsr = sy_hi - sy_lo + 1;
+            if (nsr > src_rows || sy_hi >= h) return 5;
             std::fill(P.begin(), P.end(), 0xEE);
             std::fill(hx.begin(), hx.end(), 0xEEEE);
-            if (vec) {
-                const int u_lo = i_base >> 1, n_units = (i_hi >> 1) - u_lo + 1;
-                if (6 * n_units > p_pitch) return 5;
-                for (int jr = 0; jr < nj; ++jr)
-                    for (int u = 0; u < n_units; ++u) {
-                        const int sb = 12 * (u_lo + u);
-                        uint32_t o6[6];
+            std::fill(hbuf.begin(), hbuf.end(), -1e30f);
+            for (int o = 0; o < ncol; ++o) {  // B1
+                const int ir = o / 3, cch = o - 3 * ir, dx = i_lo + ir;
+                const int sx0 = general ? xfirst[dx] : dx * sh.ix;
+                const int nx = general ? xcount[dx] : sh.ix;
+                const uint8_t* sp = src + (long)sy_lo * src_pitch + 3 * sx0 + cch;
+                for (int sr = 0; sr < nsr; ++sr, sp += src_pitch) {
+                    float buf;
+                    if (general && nx <= 4) {
+                        float al[4];
+                        for (int q = 0; q < 4; ++q) al[q] = (q < nx) ? xalpha[dx * sh.xt + q] : 0.f;
+                        const int o1 = 3 * std::min(1, nx - 1), o2 = 3 * std::min(2, nx - 1), o3 = 3 * std::min(3, nx - 1);
+                        buf = fmul((float)sp[0], al[0]);
+                        buf = fadd(buf, fmul((float)sp[o1], al[1]));
+                        buf = fadd(buf, fmul((float)sp[o2], al[2]));
+                        buf = fadd(buf, fmul((float)sp[o3], al[3]));
+                    } else if (general) {
+                        buf = 0.f;
+                        for (int q = 0; q < nx; ++q) buf = fadd(buf, fmul((float)sp[3 * q], xalpha[dx * sh.xt + q]));
+                    } else {
+                        uint32_t sum = 0;
+                        for (int q = 0; q < nx; ++q) sum += sp[3 * q];
+                        buf = (float)sum;
+                    }
+                    hbuf[(size_t)sr * hb_pitch + o] = buf;
+                }
+            }
+            for (int o = 0; o < ncol; ++o)  // B2
+                for (int jr = 0; jr < nj; ++jr) {
+                    const int j = j_lo + jr;
+                    uint32_t v;
+                    if (general) {
+                        const float* be = yalpha + j * sh.yt;
+                        const float* hp = hbuf.data() + (size_t)(yfirst[j] - sy_lo) * hb_pitch + o;
+                        float sum = fmul(be[0], hp[0]);
+                        for (int q = 1; q < ycount[j]; ++q) sum = fadd(sum, fmul(be[q], hp[(size_t)q * hb_pitch]));
+                        float r = frint(sum);
+                        r = r < 0.f ? 0.f : (r > 255.f ? 255.f : r);
+                        v = (uint32_t)(int)r;
+                    } else {
+                        const float* hp = hbuf.data() + (size_t)(j * sh.iy - sy_lo) * hb_pitch + o;
+                        float sum = 0.f;
+                        for (int q = 0; q < sh.iy; ++q) sum += hp[(size_t)q * hb_pitch];
                         if (sh.area_mode == AREA_FAST2) {
-                            uint32_t ra[3], rb[3];
-                            memcpy(ra, src + (long)(2 * (j_lo + jr)) * src_pitch + sb, 12);
-                            memcpy(rb, src + (long)(2 * (j_lo + jr) + 1) * src_pitch + sb, 12);
-                            area_fast2_unit(ra, rb, o6);
+                            v = ((uint32_t)sum + 2u) >> 2;
                         } else {
-                            const int32_t* yfirst = (const int32_t*)(tab + sh.ay_first);
-                            const int32_t* ycount = (const int32_t*)(tab + sh.ay_count);
-                            const float* beta = (const float*)(tab + sh.ay_alpha) + (j_lo + jr) * sh.yt;
-                            float acc[6];
-                            for (int ty = 0; ty < ycount[j_lo + jr]; ++ty) {
-                                uint32_t rw[3];
-                                memcpy(rw, src + (long)(yfirst[j_lo + jr] + ty) * src_pitch + sb, 12);
-                                area_x2f_accumulate(rw, beta[ty], ty == 0, acc);
-                            }
-                            area_x2f_finish(acc, o6);
-                        }
-                        for (int q = 0; q < 6; ++q) P[jr * p_pitch + 6 * u + q] = (uint8_t)o6[q];
-                    }
-            } else {
-                const int ni3 = (i_hi - i_lo + 1) * 3;
-                for (int jr = 0; jr < nj; ++jr)
-                    for (int o = 0; o < ni3; ++o) {
-                        const int ir = o / 3, c = o - 3 * ir;
-                        P[jr * p_pitch + o] = (uint8_t)area_value(src, src_pitch, sh, tab, j_lo + jr, i_lo + ir, c);
-                    }
-            }
-            if (x2) {
-                const int i_a = ((x_first + 1) >> 1) - 1, i_b = ((x_last + 1) >> 1) - 1;
-                for (int jr = 0; jr < nj; ++jr)
-                    for (int i = i_a; i <= i_b; ++i) {
-                        const uint8_t* pa = P.data() + jr * p_pitch + 3 * (std::min(std::max(i, 0), sh.nw - 1) - i_base);
-                        const uint8_t* pb = P.data() + jr * p_pitch + 3 * (std::min(i + 1, sh.nw - 1) - i_base);
-                        const int o1 = 3 * (2 * i + 1) - b0;
-                        for (int c = 0; c < 3; ++c) {
-                            const uint32_t A = (uint32_t)pa[c] << 5, B = (uint32_t)pb[c] << 5;
-                            const int oa = o1 + c, ob = o1 + 3 + c;
-                            if (oa >= 0 && oa < twb) hx[jr * hx_pitch + oa] = (uint16_t)(3u * A + B);
-                            if (ob >= 0 && ob < twb) hx[jr * hx_pitch + ob] = (uint16_t)(A + 3u * B);
+                            float r = frint(fmul(sum, sh.inv_area));
+                            r = r < 0.f ? 0.f : (r > 255.f ? 255.f : r);
+                            v = (uint32_t)(int)r;
                         }
                     }
-            } else {
-                for (int jr = 0; jr < nj; ++jr)
-                    for (int ob = 0; ob < twb; ++ob) {
-                        const int o = b0 + ob;
-                        const int x = o / 3, c = o - 3 * x;
-                        const int s0 = lx_s0[x];
-                        const int s1 = std::min(s0 + 1, sh.nw - 1);
-                        const uint8_t* prow = P.data() + jr * p_pitch;
-                        hx[jr * hx_pitch + ob] = (uint16_t)linear_h4(prow[(s0 - i_base) * 3 + c], prow[(s1 - i_base) * 3 + c], lx_a[x]);
-                    }
-            }
+                    P[jr * p_pitch + o] = (uint8_t)v;
+                }
+            for (int jr = 0; jr < nj; ++jr)  // C1
+                for (int ob = 0; ob < twb; ++ob) {
+                    const int o = b0 + ob;
+                    const int x = o / 3, c = o - 3 * x;
+                    const int s0 = lx_s0[x];
+                    const int s1 = std::min(s0 + 1, sh.nw - 1);
+                    const uint8_t* prow = P.data() + jr * p_pitch;
+                    hx[jr * hx_pitch + ob] = (uint16_t)linear_h4(prow[(s0 - i_base) * 3 + c], prow[(s1 - i_base) * 3 + c], lx_a[x]);
+                }
             for (int tid = 0; tid < 256; ++tid) {
                 const int rg = tid >> 6, cc = tid & 63;
                 const int col = 8 * cc;
