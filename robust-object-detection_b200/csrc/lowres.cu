@@ -31,6 +31,7 @@ struct LowresParams {
     int half_rows;  // allocation (worst case over the plan): low-res rows one tile touches
     int p_pitch;    // bytes per low-res row in shared memory
     int hb_pitch;   // floats per source row of the horizontal INTER_AREA buffer
+    int union_bytes;  // size of the hbuf / hx union
 };
 
 constexpr int kHxPitch = kLowresTWB + 8;
@@ -65,6 +66,8 @@ __global__ void __launch_bounds__(256, 3) lowres_kernel(LowresParams p) {
     uint8_t* un = smem + (((size_t)p.half_rows * p.p_pitch + 15) & ~(size_t)15);
     float* hbuf = reinterpret_cast<float*>(un);       // phase B: horizontal INTER_AREA pass, [source row][low-res byte col]
     uint16_t* hx = reinterpret_cast<uint16_t*>(un);   // phase C: horizontal INTER_LINEAR pass (same bytes, later)
+    // per low-res row of the tile: {hbuf row offset of its first tap, tap count, weights[kMaxAreaTaps]}
+    uint32_t* ytab = reinterpret_cast<uint32_t*>(un + p.union_bytes);
 
     for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
         const Tile t = p.tiles[ti];
@@ -105,6 +108,15 @@ __global__ void __launch_bounds__(256, 3) lowres_kernel(LowresParams p) {
         const int sy_hi = general ? yfirst[j_hi] + ycount[j_hi] - 1 : j_hi * sh.iy + sh.iy - 1;
         const int nsr = sy_hi - sy_lo + 1;
 
+        if (general) {
+            for (int jr = threadIdx.x; jr < nj; jr += 256) {
+                uint32_t* e = ytab + jr * (2 + kMaxAreaTaps);
+                const int j = j_lo + jr;
+                e[0] = (uint32_t)((yfirst[j] - sy_lo) * p.hb_pitch);
+                e[1] = (uint32_t)ycount[j];
+                for (int q = 0; q < sh.yt; ++q) e[2 + q] = __float_as_uint(yalpha[j * sh.yt + q]);
+            }
+        }
         // ---- phase B1: horizontal INTER_AREA pass (OpenCV's resizeArea_ / resizeAreaFast_ row buffer), one thread
         //      per low-res byte column walking down the source rows: hbuf[sr][o]
         for (int o = threadIdx.x; o < ncol; o += 256) {
@@ -148,11 +160,11 @@ __global__ void __launch_bounds__(256, 3) lowres_kernel(LowresParams p) {
                 const int j = j_lo + jr;
                 uint32_t v;
                 if (general) {
-                    const int ny = ycount[j];
-                    const float* be = yalpha + j * sh.yt;
-                    const float* hp = hbuf + (yfirst[j] - sy_lo) * p.hb_pitch + o;
-                    float sum = fmul(be[0], hp[0]);
-                    for (int q = 1; q < ny; ++q) sum = fadd(sum, fmul(be[q], hp[q * p.hb_pitch]));
+                    const uint32_t* e = ytab + jr * (2 + kMaxAreaTaps);
+                    const int ny = (int)e[1];
+                    const float* hp = hbuf + e[0] + o;
+                    float sum = fmul(__uint_as_float(e[2]), hp[0]);
+                    for (int q = 1; q < ny; ++q) sum = fadd(sum, fmul(__uint_as_float(e[2 + q]), hp[q * p.hb_pitch]));
                     float r = frint(sum);
                     r = r < 0.f ? 0.f : (r > 255.f ? 255.f : r);
                     v = (uint32_t)(int)r;
@@ -648,8 +660,9 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.half_rows = plan->lowres_half_rows;
             p.p_pitch = (3 * (plan->lowres_half_cols + 3) + 15) & ~15;
             p.hb_pitch = 3 * plan->lowres_half_cols + 1;
-            const size_t un = std::max((size_t)plan->lowres_src_rows * p.hb_pitch * 4, (size_t)p.half_rows * kHxPitch * 2);
-            const size_t smem = (((size_t)p.half_rows * p.p_pitch + 15) & ~(size_t)15) + un + 16;
+            const size_t un = (std::max((size_t)plan->lowres_src_rows * p.hb_pitch * 4, (size_t)p.half_rows * kHxPitch * 2) + 15) & ~(size_t)15;
+            p.union_bytes = (int)un;
+            const size_t smem = (((size_t)p.half_rows * p.p_pitch + 15) & ~(size_t)15) + un + (size_t)p.half_rows * (2 + kMaxAreaTaps) * 4 + 16;
             if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
             ROD_CUDA(cudaFuncSetAttribute(lowres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));

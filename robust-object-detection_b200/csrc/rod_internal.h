@@ -13,7 +13,7 @@ namespace rod {
 constexpr int kNoiseSpan = 16384;  // elements (bytes) per noise work item
 constexpr int kBlurRowsPerTile = 8;  // one row per warp, 8 warps per CTA
 constexpr int kLowresTH = 32;      // output rows per lowres tile
-constexpr int kLowresTWB = 512;    // output BYTES per lowres tile row (tiles are cut in byte columns)
+constexpr int kLowresTWB = 480;    // output BYTES per lowres tile row (byte columns); its ~250 low-res byte columns fit one pass of 256 threads
 constexpr int kLbTH = 16;          // letterbox output tile
 constexpr int kLbTW = 64;
 constexpr int kMaxAreaTaps = 8;

@@ -14,7 +14,7 @@
 using namespace rod;
 
 static const int kBlurLeft = 64;
-static const int kLowresTH = 32, kLowresTWB = 512;
+static const int kLowresTH = 32, kLowresTWB = 480;
 
 // Replays blur_rows_kernel<9> / <0> for one image.  `dst_phase` shifts the destination (and
 // source) start address phase inside a 16-byte block, as an unaligned device buffer would.
