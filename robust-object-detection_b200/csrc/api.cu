@@ -41,6 +41,39 @@ int run_op(rod_plan* plan, int op, const uint8_t* src, uint8_t* dst, const float
     }
 }
 
+// The kernels of ops [op_lo, ROD_OP_LOWRES] of a mixed batch.  Each touches only the images of its own op-code, so
+// they are independent: for small batches (no single op fills the GPU) they run concurrently on two auxiliary
+// streams forked from / joined into `stream` with events (graph-capturable).
+int run_mixed_ops(rod_plan* plan, int op_lo, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes, const float* noise,
+                  float sigma, int k, double factor, uint64_t seed, uint64_t first_image, uint32_t offset,
+                  cudaStream_t stream) {
+    const bool fork = plan->n_images <= 128;
+    if (fork && plan->ev_fork == nullptr) {
+        for (auto& s : plan->aux_streams) ROD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        ROD_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+        for (auto& e : plan->ev_join) ROD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (fork) {
+        ROD_CUDA(cudaEventRecord(plan->ev_fork, stream));
+        for (auto& s : plan->aux_streams) ROD_CUDA(cudaStreamWaitEvent(s, plan->ev_fork, 0));
+    }
+    for (int op = op_lo; op <= ROD_OP_LOWRES; ++op) {
+        // lowres (the longest) stays on the caller's stream; blur and noise go to the auxiliary streams
+        cudaStream_t st = stream;
+        if (fork && op == ROD_OP_BLUR) st = plan->aux_streams[0];
+        if (fork && op == ROD_OP_NOISE) st = plan->aux_streams[1];
+        int rc = run_op(plan, op, src, dst, noise, sigma, k, factor, seed, first_image, offset, opcodes, st, 0, plan->n_images);
+        if (rc != ROD_OK) return rc;
+    }
+    if (fork) {
+        for (int i = 0; i < 2; ++i) {
+            ROD_CUDA(cudaEventRecord(plan->ev_join[i], plan->aux_streams[i]));
+            ROD_CUDA(cudaStreamWaitEvent(stream, plan->ev_join[i], 0));
+        }
+    }
+    return ROD_OK;
+}
+
 }  // namespace
 
 extern "C" const char* rod_version(void) { return "rod_b200 0.1.0 (sm_100a)"; }
@@ -73,7 +106,7 @@ extern "C" int rod_plan_launches(const rod_plan* plan, int op) {
     switch (op) {
         case ROD_OP_NONE: case ROD_OP_NOISE: case ROD_OP_BLUR: case ROD_OP_LOWRES: return 1;
         case 100: return 4;  // rod_corrupt_batch_u8: copy + noise + blur + lowres
-        case 101: return 5;  // rod_corrupt_letterbox_f16: the four above + letterbox
+        case 101: return 4;  // rod_corrupt_letterbox_f16: noise + blur + lowres + letterbox (clean images are read in place)
         default: return 0;
     }
 }
@@ -115,12 +148,11 @@ extern "C" int rod_corrupt_batch_u8(rod_plan* plan, const uint8_t* src, uint8_t*
                                     const float* noise, float sigma, int k, double factor, uint64_t seed,
                                     uint64_t first_image_index, uint32_t offset, void* stream) {
     if (plan == nullptr || src == nullptr || dst == nullptr || opcodes == nullptr) return ROD_ERR_INVALID_ARG;
-    for (int op = ROD_OP_NONE; op <= ROD_OP_LOWRES; ++op) {
-        int rc = run_op(plan, op, src, dst, noise, sigma, k, factor, seed, first_image_index, offset, opcodes,
-                        (cudaStream_t)stream, 0, plan->n_images);
-        if (rc != ROD_OK) return rc;
-    }
-    return ROD_OK;
+    int rc = run_op(plan, ROD_OP_NONE, src, dst, noise, sigma, k, factor, seed, first_image_index, offset, opcodes,
+                    (cudaStream_t)stream, 0, plan->n_images);
+    if (rc != ROD_OK) return rc;
+    return run_mixed_ops(plan, ROD_OP_NOISE, src, dst, opcodes, noise, sigma, k, factor, seed, first_image_index, offset,
+                         (cudaStream_t)stream);
 }
 
 extern "C" int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, const uint8_t* opcodes, void* out_f16,
@@ -137,10 +169,11 @@ extern "C" int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, con
         ROD_CUDA(cudaMalloc((void**)&plan->d_scratch, plan->dst_extent + 64));
         plan->scratch_bytes = plan->dst_extent;
     }
-    rc = rod_corrupt_batch_u8(plan, src, plan->d_scratch, opcodes, noise, sigma, k, factor, seed, first_image_index,
-                              offset, stream);
+    // images that stay clean are read from `src` by the letterbox kernel itself: no copy into the scratch
+    rc = run_mixed_ops(plan, ROD_OP_NOISE, src, plan->d_scratch, opcodes, noise, sigma, k, factor, seed, first_image_index,
+                       offset, (cudaStream_t)stream);
     if (rc != ROD_OK) return rc;
-    return launch_letterbox(plan, plan->d_scratch, out_f16, pad_value, (cudaStream_t)stream);
+    return launch_letterbox(plan, plan->d_scratch, src, opcodes, out_f16, pad_value, (cudaStream_t)stream);
 }
 
 // Host-buffer path: chunks of images are pipelined over three streams so the H2D copy of chunk

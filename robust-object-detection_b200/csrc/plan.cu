@@ -262,6 +262,11 @@ extern "C" void rod_plan_destroy(rod_plan* plan) {
         if (p) cudaFree(p);
     for (cudaStream_t s : plan->streams)
         if (s) cudaStreamDestroy(s);
+    for (cudaStream_t s : plan->aux_streams)
+        if (s) cudaStreamDestroy(s);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    for (cudaEvent_t e : plan->ev_join)
+        if (e) cudaEventDestroy(e);
     delete plan;
 }
 

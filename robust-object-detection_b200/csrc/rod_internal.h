@@ -14,7 +14,7 @@ constexpr int kNoiseSpan = 16384;  // elements (bytes) per noise work item
 constexpr int kBlurRowsPerTile = 8;  // one row per warp, 8 warps per CTA
 constexpr int kLowresTH = 32;      // output rows per lowres tile
 constexpr int kLowresTWB = 480;    // output BYTES per lowres tile row (byte columns); its ~250 low-res byte columns fit one pass of 256 threads
-constexpr int kLbTH = 16;          // letterbox output tile
+constexpr int kLbTH = 32;          // letterbox output tile
 constexpr int kLbTW = 64;
 constexpr int kMaxAreaTaps = 8;
 
@@ -89,6 +89,9 @@ struct rod_plan {
     float* d_stage_noise = nullptr;
     uint8_t* d_stage_ops = nullptr;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    // fork/join of the per-op kernels of a mixed batch (small batches do not fill the GPU one op at a time)
+    cudaStream_t aux_streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 namespace rod {
@@ -113,7 +116,8 @@ int launch_blur(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, c
                 cudaStream_t stream, int img_lo, int img_hi);
 int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
                   cudaStream_t stream, int img_lo, int img_hi);
-int launch_letterbox(const rod_plan* plan, const uint8_t* img, void* out_f16, int pad_value, cudaStream_t stream);
+int launch_letterbox(const rod_plan* plan, const uint8_t* img, const uint8_t* src, const uint8_t* opcodes, void* out_f16,
+                     int pad_value, cudaStream_t stream);
 
 int ensure_lowres_tables(rod_plan* plan, double factor);
 int ensure_letterbox_tables(rod_plan* plan, int out_h, int out_w);
