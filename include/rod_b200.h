@@ -96,6 +96,13 @@ ROD_API int rod_noise_field_f32(const rod_plan* plan, float* out_field, float si
 ROD_API int rod_blur_h_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, double angle_deg,
                   const uint8_t* opcodes, void* stream);
 
+/* a2+a3 at angle_deg != 0: install the k x k float32 kernel that
+ * _motion_blur_kernel(k, angle_deg) builds (augmentations.py:21-27; `kernel` is a HOST pointer, row-major).  While
+ * installed, every ROD_OP_BLUR of this plan (rod_blur_h_u8 with the same k, rod_corrupt_batch_u8, rod_apply_host,
+ * rod_corrupt_letterbox_f16) is cv2.filter2D(img, -1, kernel), bit-exact for k*k < 130 (OpenCV's direct filter
+ * engine; larger kernels use DFT-based convolution there and return ROD_ERR_UNSUPPORTED here).  NULL removes it. */
+ROD_API int rod_set_blur_kernel(rod_plan* plan, const float* kernel, int k);
+
 /* a4+a5: apply_lowres(img, factor) (augmentations.py:41-45): INTER_AREA down to
  * (max(1,int(W*factor)), max(1,int(H*factor))) then 8-bit INTER_LINEAR back, fused: the
  * low-resolution intermediate lives in shared memory only.  0 < factor <= 1. */

@@ -176,10 +176,54 @@ def motion_blur_taps(k: int, angle_deg: float) -> int:
     return int(k)
 
 
-def apply_motion_blur(img: np.ndarray, k: int, angle_deg: float) -> np.ndarray:
-    """cv2.filter2D(img, -1, kernel) with the angle-0 kernel: horizontal k-tap box,
-    BORDER_REFLECT_101, anchor k//2, result round(S/k).  S/k is never at a rounding
-    tie for odd k, so the float engine equals the integer form (2S + k) // (2k)."""
+DFT_FILTER_ELEMS = 130  # cv::filter2D switches 8U kernels with >= 130 elements to DFT-based convolution
+
+
+def filter2d(img: np.ndarray, kernel: np.ndarray) -> np.ndarray:
+    """cv2.filter2D(img, -1, kernel) for a small float32 kernel (fewer than 130 elements: the direct,
+    non-DFT FilterEngine of OpenCV 4.13.0, modules/imgproc/src/filter.simd.hpp Filter2D + FilterVec_8u),
+    as called by augmentations.py:38 with the rotated line kernel of augmentations.py:21-27.
+
+    Per output byte (channels interleaved, BORDER_REFLECT_101 on both axes): the non-zero taps are
+    accumulated in float32 in row-major kernel order starting from 0.  The vectorised part of each row
+    (flat byte index < 4 * (3W // 4)) uses fused multiply-add (v_muladd on an FMA3 host), the scalar tail
+    (the last 3W % 4 bytes of the row) a separate multiply and add; the sum is rounded half-to-even
+    (cvRound) and saturated.  Pinned by tests/golden/golden_angles.npz (outputs of the reference)."""
+    assert img.dtype == np.uint8 and img.ndim == 3
+    kernel = np.asarray(kernel, dtype=np.float32)
+    k = kernel.shape[0]
+    assert kernel.shape == (k, k) and k % 2 == 1 and k * k < DFT_FILTER_ELEMS
+    h, w, c = img.shape
+    pad = k // 2
+    ys = reflect101(np.arange(-pad, h + pad), h)
+    xs = reflect101(np.arange(-pad, w + pad), w)
+    src = img[ys][:, xs].astype(np.float32).reshape(h + 2 * pad, (w + 2 * pad) * c)
+    n = w * c
+    fma = np.zeros((h, n), np.float32)
+    sep = np.zeros((h, n), np.float32)
+    for dy in range(k):
+        for dx in range(k):
+            wgt = kernel[dy, dx]
+            if wgt == 0:
+                continue
+            v = src[dy:dy + h, c * dx:c * dx + n]
+            # float32 fma emulated in float64: the product is exact, the sum is rounded to float32 once
+            fma = (fma.astype(np.float64) + v.astype(np.float64) * np.float64(wgt)).astype(np.float32)
+            sep = sep + v * wgt
+    n_vec = n & ~3
+    s = np.concatenate([fma[:, :n_vec], sep[:, n_vec:]], axis=1)
+    return np.ascontiguousarray(np.clip(np.rint(s), 0, 255).astype(np.uint8).reshape(h, w, c))
+
+
+def apply_motion_blur(img: np.ndarray, k: int, angle_deg: float, kernel: np.ndarray = None) -> np.ndarray:
+    """cv2.filter2D(img, -1, kernel) with the kernel of augmentations.py:21-27.
+    angle 0: horizontal k-tap box, BORDER_REFLECT_101, out = (2S + k) // (2k) (integer; equals OpenCV's float
+    path because S/k is never within 1/(2k) of a tie).  Other angles: `kernel` must be the rotated k x k
+    float32 kernel (built by the caller with cv2, or taken from the golden file) -> filter2d()."""
+    if float(angle_deg) != 0.0 or kernel is not None:
+        if kernel is None:
+            raise ValueError("angle != 0 needs the rotated kernel (cv2.getRotationMatrix2D + warpAffine)")
+        return filter2d(img, kernel)
     k = motion_blur_taps(k, angle_deg)
     assert img.dtype == np.uint8 and img.ndim == 3
     h, w, c = img.shape

@@ -76,23 +76,32 @@ def _plan_for(h: int, w: int, pitch: int) -> CorruptionPlan:
 
 
 def _run(op: int, img_bgr: np.ndarray, *, noise=None, sigma=0.0, k=BLUR_KERNEL, factor=DOWNSCALE_FACTOR,
-         seed=0, index=0) -> np.ndarray:
+         seed=0, index=0, kernel=None) -> np.ndarray:
     img, pitch = _as_rows(img_bgr)
     h, w, _ = img.shape
     out = np.empty((h, w, 3), dtype=np.uint8)  # fresh, C-contiguous, caller-owned
-    _plan_for(h, w, pitch).apply_host(op, img, out, noise_host=noise, sigma=sigma, k=k, factor=factor, seed=seed,
-                                      first_image_index=index)
+    plan = _plan_for(h, w, pitch)
+    if op == N.OP_BLUR:
+        plan.set_blur_kernel(kernel)  # None: the angle-0 box
+    plan.apply_host(op, img, out, noise_host=noise, sigma=sigma, k=k, factor=factor, seed=seed, first_image_index=index)
     return out
 
 
 # ---- Low-level corruption functions ----
 def _motion_blur_kernel(k: int, angle_deg: float):
-    """The k x k float32 kernel of augmentations.py:21-27.  At angle 0 the warpAffine there is
-    the identity, so the kernel is row k//2 filled with float32(1)/float32(k)."""
-    if float(angle_deg) != 0.0:
-        raise NotImplementedError("only angle_deg == 0 is implemented (the reference never passes another value)")
+    """The k x k float32 kernel of augmentations.py:21-27.  At angle 0 the warpAffine there is the identity, so the
+    kernel is row k//2 filled with float32(1)/float32(k).  Other angles need the same host-side OpenCV calls as the
+    reference (cv2.getRotationMatrix2D + cv2.warpAffine on a k x k array, ~30 us): coefficient construction only --
+    every pixel is still filtered on the GPU."""
     kernel = np.zeros((k, k), dtype=np.float32)
     kernel[k // 2, :] = 1.0
+    if float(angle_deg) != 0.0:
+        try:
+            import cv2
+        except ImportError as e:  # pragma: no cover
+            raise NotImplementedError("angle_deg != 0 needs OpenCV on the host to rotate the k x k kernel") from e
+        center = (k / 2 - 0.5, k / 2 - 0.5)
+        kernel = cv2.warpAffine(kernel, cv2.getRotationMatrix2D(center, angle_deg, 1.0), (k, k))
     return kernel / (kernel.sum() + 1e-8)
 
 
@@ -108,11 +117,16 @@ def apply_noise(img_bgr: np.ndarray, sigma: float) -> np.ndarray:
 
 
 def apply_motion_blur(img_bgr: np.ndarray, k: int, angle_deg: float) -> np.ndarray:
-    if float(angle_deg) != 0.0:
-        raise NotImplementedError("apply_motion_blur: only angle_deg == 0 is implemented on the B200 path")
-    if int(k) != k or k < 1 or k % 2 == 0 or k > 31:
-        raise NotImplementedError("apply_motion_blur: k must be odd and in [1, 31] on the B200 path")
-    return _run(N.OP_BLUR, img_bgr, k=int(k))
+    if int(k) != k or k < 1 or k % 2 == 0:
+        raise NotImplementedError("apply_motion_blur: k must be odd on the B200 path")
+    if float(angle_deg) == 0.0:
+        if k > 31:
+            raise NotImplementedError("apply_motion_blur: k <= 31 at angle 0 on the B200 path")
+        return _run(N.OP_BLUR, img_bgr, k=int(k))
+    if k * k >= 130:
+        raise NotImplementedError("apply_motion_blur: at angle != 0 OpenCV filters kernels of 130+ elements (k >= 13) by "
+                                  "DFT, which cannot be reproduced bit-exactly; k <= 11 is implemented")
+    return _run(N.OP_BLUR, img_bgr, k=int(k), kernel=_motion_blur_kernel(int(k), angle_deg))
 
 
 def apply_lowres(img_bgr: np.ndarray, factor: float) -> np.ndarray:

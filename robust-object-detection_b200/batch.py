@@ -145,6 +145,17 @@ class CorruptionPlan:
         N.check(N.lib().rod_blur_h_u8(self._h, _ptr(src), _ptr(dst), int(k), float(angle_deg), _ptr(opcodes),
                                       _stream_handle(stream)), "rod_blur_h_u8")
 
+    def set_blur_kernel(self, kernel: Optional[np.ndarray]) -> None:
+        """Install the k x k float32 kernel of _motion_blur_kernel(k, angle != 0) for this plan's blur op
+        (cv2.filter2D semantics, k*k < 130), or None to return to the horizontal angle-0 box."""
+        if kernel is None:
+            N.check(N.lib().rod_set_blur_kernel(self._h, None, 0), "rod_set_blur_kernel")
+            return
+        kern = np.ascontiguousarray(kernel, dtype=np.float32)
+        if kern.ndim != 2 or kern.shape[0] != kern.shape[1]:
+            raise ValueError("kernel must be k x k")
+        N.check(N.lib().rod_set_blur_kernel(self._h, kern.ctypes.data, int(kern.shape[0])), "rod_set_blur_kernel")
+
     def lowres(self, src, dst, factor: float = DOWNSCALE_FACTOR, opcodes=None, stream=None) -> None:
         N.check(N.lib().rod_lowres_u8(self._h, _ptr(src), _ptr(dst), float(factor), _ptr(opcodes),
                                       _stream_handle(stream)), "rod_lowres_u8")

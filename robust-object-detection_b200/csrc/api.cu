@@ -23,6 +23,7 @@ int run_op(rod_plan* plan, int op, const uint8_t* src, uint8_t* dst, const float
             return launch_noise(plan, noise ? NOISE_COMPAT : NOISE_PHILOX, src, dst, noise, nullptr, sigma, seed,
                                 first_image, offset, opcodes, ROD_OP_NOISE, stream, img_lo, img_hi);
         case ROD_OP_BLUR:
+            if (plan->f2d_ntaps > 0) return launch_filter2d(plan, src, dst, opcodes, stream, img_lo, img_hi);
             if (!blur_supported(k, 0.0)) return ROD_ERR_UNSUPPORTED;
             if (k == 1)
                 return launch_noise(plan, NOISE_COPY, src, dst, nullptr, nullptr, 0.f, 0, 0, 0, opcodes, ROD_OP_BLUR,
@@ -132,7 +133,8 @@ extern "C" int rod_noise_field_f32(const rod_plan* plan, float* out_field, float
 extern "C" int rod_blur_h_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, double angle_deg,
                              const uint8_t* opcodes, void* stream) {
     if (plan == nullptr || src == nullptr || dst == nullptr) return ROD_ERR_INVALID_ARG;
-    if (!blur_supported(k, angle_deg)) return ROD_ERR_UNSUPPORTED;
+    // a general angle needs its rotated kernel installed with rod_set_blur_kernel (then k must match it)
+    if (plan->f2d_ntaps > 0 ? (k != plan->f2d_k) : !blur_supported(k, angle_deg)) return ROD_ERR_UNSUPPORTED;
     return run_op(const_cast<rod_plan*>(plan), ROD_OP_BLUR, src, dst, nullptr, 0.f, k, 0.0, 0, 0, 0, opcodes,
                   (cudaStream_t)stream, 0, plan->n_images);
 }
@@ -183,7 +185,7 @@ extern "C" int rod_apply_host(rod_plan* plan, int op, const uint8_t* src_host, u
                               uint64_t first_image_index, uint32_t offset) {
     if (plan == nullptr || src_host == nullptr || dst_host == nullptr) return ROD_ERR_INVALID_ARG;
     if (op < ROD_OP_NONE || op > ROD_OP_LOWRES) return ROD_ERR_INVALID_ARG;
-    if (op == ROD_OP_BLUR && !blur_supported(k, 0.0)) return ROD_ERR_UNSUPPORTED;
+    if (op == ROD_OP_BLUR && plan->f2d_ntaps == 0 && !blur_supported(k, 0.0)) return ROD_ERR_UNSUPPORTED;
     if (op == ROD_OP_LOWRES) {
         int rc = ensure_lowres_tables(plan, factor);
         if (rc != ROD_OK) return rc;

@@ -252,11 +252,53 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
     return ROD_OK;
 }
 
+// Installs (kernel != NULL) or removes (NULL) a general k x k float32 blur kernel: while installed, ROD_OP_BLUR runs
+// the 2-D filter (filter2d.cu) instead of the horizontal box.
+extern "C" int rod_set_blur_kernel(rod_plan* plan, const float* kernel, int k) {
+    if (plan == nullptr) return ROD_ERR_INVALID_ARG;
+    if (kernel == nullptr) {
+        plan->f2d_ntaps = 0;
+        plan->f2d_k = 0;
+        return ROD_OK;
+    }
+    if (k < 1 || (k & 1) == 0) return ROD_ERR_INVALID_ARG;
+    if (k * k >= kF2dMaxElems) return ROD_ERR_UNSUPPORTED;  // OpenCV's DFT path: not reproducible bit-exactly
+    std::vector<float4> taps;
+    for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) {
+            const float w = kernel[dy * k + dx];
+            if (w == 0.0f) continue;
+            float4 t;
+            const int dxb = 3 * dx;
+            memcpy(&t.x, &dy, 4);
+            memcpy(&t.y, &dxb, 4);
+            t.z = w;
+            t.w = 0.f;
+            taps.push_back(t);
+        }
+    if (taps.empty()) return ROD_ERR_INVALID_ARG;
+    if (plan->d_f2d_taps) { cudaFree(plan->d_f2d_taps); plan->d_f2d_taps = nullptr; }
+    int rc = upload(taps, &plan->d_f2d_taps);
+    if (rc != ROD_OK) return rc;
+    if (plan->d_f2d_tiles == nullptr) {
+        std::vector<Tile> tiles;
+        build_grid_tiles(plan->h_images, kF2dTH, kF2dTWB, tiles);
+        rc = upload(tiles, &plan->d_f2d_tiles);
+        if (rc != ROD_OK) return rc;
+        plan->n_f2d_tiles = (int)tiles.size();
+        tile_starts(tiles, plan->n_images, plan->f2d_tile_start);
+    }
+    plan->f2d_ntaps = (int)taps.size();
+    plan->f2d_k = k;
+    return ROD_OK;
+}
+
 extern "C" void rod_plan_destroy(rod_plan* plan) {
     if (plan == nullptr) return;
     void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles,
                     plan->d_lowres_x2w_tiles, plan->d_lowres_x2_rest_tiles, plan->d_shapes,
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
+                    plan->d_f2d_taps, plan->d_f2d_tiles,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};
     for (void* p : ptrs)
         if (p) cudaFree(p);

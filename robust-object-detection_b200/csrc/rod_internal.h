@@ -17,6 +17,9 @@ constexpr int kLowresTWB = 480;    // output BYTES per lowres tile row (byte col
 constexpr int kLbTH = 32;          // letterbox output tile
 constexpr int kLbTW = 64;
 constexpr int kMaxAreaTaps = 8;
+constexpr int kF2dTH = 16;         // general 2-D filter tile: rows x output bytes
+constexpr int kF2dTWB = 768;
+constexpr int kF2dMaxElems = 130;  // cv::filter2D uses DFT-based convolution from 130 kernel elements on (8U)
 
 struct HostShape {
     int h, w;
@@ -83,6 +86,13 @@ struct rod_plan {
     uint8_t* d_scratch = nullptr;  // corrupted full-res images for the letterbox path
     uint64_t scratch_bytes = 0;
 
+    // general 2-D blur kernel override (rod_set_blur_kernel): non-zero taps in row-major order
+    float4* d_f2d_taps = nullptr;
+    int f2d_ntaps = 0, f2d_k = 0;
+    rod::Tile* d_f2d_tiles = nullptr;
+    int n_f2d_tiles = 0;
+    std::vector<int> f2d_tile_start;
+
     // host-buffer (e2e) staging
     uint8_t* d_stage_src = nullptr;
     uint8_t* d_stage_dst = nullptr;
@@ -116,6 +126,8 @@ int launch_blur(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, c
                 cudaStream_t stream, int img_lo, int img_hi);
 int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
                   cudaStream_t stream, int img_lo, int img_hi);
+int launch_filter2d(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes, cudaStream_t stream,
+                    int img_lo, int img_hi);
 int launch_letterbox(const rod_plan* plan, const uint8_t* img, const uint8_t* src, const uint8_t* opcodes, void* out_f16,
                      int pad_value, cudaStream_t stream);
 

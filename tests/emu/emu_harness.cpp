@@ -443,6 +443,44 @@ extern "C" int emu_noise(const uint8_t* src, uint8_t* dst, const float* noise, f
     return 0;
 }
 
+// Replays filter2d_kernel: tiles of kF2dTH rows x kF2dTWB bytes staged with halo as floats (reflect-101 per pixel and
+// per row), taps in row-major order, fused multiply-add below 4 * (3w / 4), separate multiply / add in the row tail.
+extern "C" int emu_filter2d(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
+                            const float* kernel, int k) {
+    const int TH = 16, TWB = 768;
+    struct Tap { int dy, dxb; float w; };
+    std::vector<Tap> taps;
+    for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx)
+            if (kernel[dy * k + dx] != 0.0f) taps.push_back(Tap{dy, 3 * dx, kernel[dy * k + dx]});
+    const int r = k >> 1, n = 3 * w, tp = TWB + 3 * (k - 1), n_vec = n & ~3;
+    std::vector<float> tile((size_t)(TH + k - 1) * tp);
+    for (int y0 = 0; y0 < h; y0 += TH)
+        for (int b0 = 0; b0 < n; b0 += TWB) {
+            const int th = std::min(TH, h - y0), twb = std::min(TWB, n - b0);
+            std::fill(tile.begin(), tile.end(), -1e30f);
+            for (int rr = 0; rr < th + 2 * r; ++rr) {
+                const uint8_t* srow = src + (long)reflect101(y0 + rr - r, h) * src_pitch;
+                for (int ci = 0; ci < twb + 6 * r; ++ci) {
+                    const int i = b0 + ci, px = i / 3, c = i - 3 * px;
+                    tile[(size_t)rr * tp + ci] = (float)srow[3 * reflect101(px - r, w) + c];
+                }
+            }
+            for (int ry = 0; ry < th; ++ry)
+                for (int x = 0; x < twb; ++x) {
+                    float s = 0.f;
+                    for (const Tap& t : taps) {
+                        const float v = tile[(size_t)(ry + t.dy) * tp + x + t.dxb];
+                        s = (b0 + x >= n_vec) ? fadd(s, fmul(v, t.w)) : fmaf(v, t.w, s);
+                    }
+                    float v = frint(s);
+                    v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
+                    dst[(long)(y0 + ry) * dst_pitch + b0 + x] = (uint8_t)(int)v;
+                }
+        }
+    return 0;
+}
+
 // Letterbox tables + per-pixel arithmetic (replays lb_pixel); out is uint8 HWC canvas (pre-normalise).
 extern "C" int emu_letterbox_u8(const uint8_t* img, int h, int w, long pitch, uint8_t* canvas, int out_h, int out_w,
                                 int pad) {

@@ -138,5 +138,34 @@ def main():
     print("wrote", len(small), "arrays and", len(hashes["big"]), "big-case hashes")
 
 
+ANGLE_CASES = [(9, 45), (9, 135), (9, 30), (9, 90), (9, 179.5), (5, 60), (3, 45), (7, 33), (11, 45), (11, 100)]
+ANGLE_SHAPES = [(1, 1), (2, 3), (5, 4), (9, 13), (33, 47), (31, 100), (48, 129), (8, 6), (20, 46), (3, 2)]
+ANGLE_BIG = [("visdrone_765x1360", 12345, 765, 1360), ("tail3_540x961", 4001, 540, 961), ("tail2_301x402", 4002, 301, 402)]
+
+
+def make_angles():
+    """apply_motion_blur at angles other than 0 (general 2-D float kernel).  Stores the rotated
+    kernels the reference builds (cv2.getRotationMatrix2D + warpAffine, augmentations.py:21-27) and its outputs."""
+    sys.path.insert(0, REF_ROOT)
+    from scripts import augmentations as ref
+    arrs, hashes = {}, {}
+    for k, ang in ANGLE_CASES:
+        arrs[f"kernel_{k}_{ang}"] = ref._motion_blur_kernel(k, ang)
+        for i, (h, w) in enumerate(ANGLE_SHAPES):
+            for kind in ("uniform", "binary"):
+                img = synth(300 + i, h, w, kind)
+                arrs[f"out_{k}_{ang}_{kind}_{h}x{w}"] = ref.apply_motion_blur(img, k, ang)
+        for name, seed, h, w in ANGLE_BIG:
+            hashes[f"{k}_{ang}_{name}"] = sha(ref.apply_motion_blur(synth(seed, h, w), k, ang))
+    np.savez_compressed(os.path.join(HERE, "golden_angles.npz"), **arrs)
+    with open(os.path.join(HERE, "golden_angles.json"), "w") as f:
+        json.dump({"cases": ANGLE_CASES, "shapes": ANGLE_SHAPES, "big": ANGLE_BIG, "sha": hashes}, f, indent=1)
+    print("wrote", len(arrs), "angle arrays and", len(hashes), "hashes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "angles":
+        make_angles()
+    else:
+        main()
+        make_angles()

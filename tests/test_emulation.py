@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import corruption_oracle as orc
-from tests.helpers import synth
+from tests.helpers import sha, synth
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "emu_harness.cpp")
@@ -25,6 +25,7 @@ def emu(tmp_path_factory):
     lib.emu_blur.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int]
     lib.emu_lowres.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_int]
     lib.emu_lowres_tiled.argtypes = lib.emu_lowres.argtypes
+    lib.emu_filter2d.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, f32p, ctypes.c_int]
     lib.emu_lowres_x2w.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_int]
     lib.emu_noise.argtypes = [u8p, u8p, f32p, f32p, ctypes.c_long, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
     lib.emu_letterbox_u8.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -154,3 +155,25 @@ def test_emu_lowres_warp_marching(emu, band_rows):
         rc = emu.emu_lowres_x2w(_p(buf), _p(got), h, w, pitch, 3 * w, 0.5, band_rows)
         assert rc == 0, (h, w, rc)
         assert np.array_equal(got, want), (h, w, band_rows)
+
+
+def test_emu_filter2d_general_angles(emu):
+    """filter2d_kernel's tiling / halo / tap order / FMA-vs-tail arithmetic replayed on the CPU against the outputs
+    the reference produced at angles != 0 (tests/golden/golden_angles.npz)."""
+    import json
+    here = os.path.join(HERE, "golden")
+    g = np.load(os.path.join(here, "golden_angles.npz"))
+    meta = json.load(open(os.path.join(here, "golden_angles.json")))
+    for k, ang in meta["cases"]:
+        kern = np.ascontiguousarray(g[f"kernel_{k}_{ang}"], dtype=np.float32)
+        for i, (h, w) in enumerate(meta["shapes"]):
+            img = synth(300 + i, h, w)
+            got = np.zeros_like(img)
+            assert emu.emu_filter2d(_p(img), _p(got), h, w, 3 * w, 3 * w, _p(kern, ctypes.c_float), k) == 0
+            assert np.array_equal(got, g[f"out_{k}_{ang}_uniform_{h}x{w}"]), (k, ang, h, w)
+    name, seed, h, w = meta["big"][2]  # several tiles in x, 2-byte row tail
+    kern = np.ascontiguousarray(g["kernel_9_45"], dtype=np.float32)
+    img = synth(seed, h, w)
+    got = np.zeros_like(img)
+    emu.emu_filter2d(_p(img), _p(got), h, w, 3 * w, 3 * w, _p(kern, ctypes.c_float), 9)
+    assert sha(got) == meta["sha"][f"9_45_{name}"]

@@ -7,6 +7,8 @@ import random
 import sys
 import types
 
+import os
+
 import numpy as np
 import pytest
 
@@ -94,10 +96,43 @@ def test_lowres_shapes_and_factors_vs_oracle(aug):
             assert np.array_equal(aug.apply_lowres(img, f), orc.apply_lowres(img, f)), (h, w, f)
 
 
+def test_motion_blur_general_angles(aug, torch_):
+    """apply_motion_blur at angles != 0 (2-D float kernel, cv2.filter2D semantics incl. the
+    non-FMA scalar tail of each row) against outputs recorded from the unmodified reference."""
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(here, "golden_angles.npz"))
+    meta = json.load(open(os.path.join(here, "golden_angles.json")))
+    for k, ang in meta["cases"]:
+        assert np.array_equal(aug._motion_blur_kernel(k, ang), g[f"kernel_{k}_{ang}"]), (k, ang)
+        for i, (h, w) in enumerate(meta["shapes"]):
+            for kind in ("uniform", "binary"):
+                got = aug.apply_motion_blur(synth(300 + i, h, w, kind), k, ang)
+                assert np.array_equal(got, g[f"out_{k}_{ang}_{kind}_{h}x{w}"]), (k, ang, h, w, kind)
+        for name, seed, h, w in meta["big"]:
+            assert sha(aug.apply_motion_blur(synth(seed, h, w), k, ang)) == meta["sha"][f"{k}_{ang}_{name}"], (k, ang, name)
+    # the angle-0 box is back after a general kernel was used on the same cached plan
+    img = synth(300, 33, 47)
+    aug.apply_motion_blur(img, 9, 45)
+    assert np.array_equal(aug.apply_motion_blur(img, 9, 0), orc.apply_motion_blur(img, 9, 0))
+    # device-resident ragged batch with op-code masking
+    from robust_object_detection_b200.batch import CorruptionPlan
+    shapes = [(48, 129), (31, 100), (33, 47)]
+    imgs = [synth(300 + i, h, w) for i, (h, w) in zip((6, 5, 4), shapes)]
+    plan = CorruptionPlan.ragged(shapes)
+    plan.set_blur_kernel(g["kernel_9_45"])
+    src = torch_.from_numpy(plan.pack(imgs)).cuda()
+    dst = torch_.full_like(src, 5)
+    plan.blur(src, dst, k=9, opcodes=torch_.tensor([2, 0, 2], dtype=torch_.uint8, device="cuda"))
+    outs = plan.unpack(dst.cpu().numpy())
+    assert np.array_equal(outs[0], g["out_9_45_uniform_48x129"]) and np.array_equal(outs[2], g["out_9_45_uniform_33x47"])
+    assert (outs[1] == 5).all()
+
+
 def test_unsupported_parameters_raise(aug):
     img = synth(1, 16, 16)
     with pytest.raises(NotImplementedError):
-        aug.apply_motion_blur(img, 9, 30)
+        aug.apply_motion_blur(img, 13, 30)  # 169 kernel elements: OpenCV's DFT path, not reproducible bit-exactly
     with pytest.raises(NotImplementedError):
         aug.apply_motion_blur(img, 4, 0)
     with pytest.raises(NotImplementedError):

@@ -1,5 +1,6 @@
 """CPU: the oracle restatement vs golden vectors recorded from the unmodified reference
 (tests/golden/make_golden.py).  Bit-exact (integer/byte work)."""
+import os
 import random
 
 import numpy as np
@@ -78,3 +79,22 @@ def test_decisions_and_random_corruption(golden_hashes):
     np.random.seed(g["np_seed"])
     img = synth(g["img_seed"], g["h"], g["w"])
     assert [sha(orc.apply_random_corruption(img)) for _ in g["sha"]] == g["sha"]
+
+
+def test_general_angle_filter2d_vs_reference():
+    """the oracle's filter2d() against the reference's apply_motion_blur at angles != 0
+    (kernels and outputs recorded by tests/golden/make_golden.py from the unmodified reference)."""
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(here, "golden_angles.npz"))
+    meta = json.load(open(os.path.join(here, "golden_angles.json")))
+    for k, ang in meta["cases"]:
+        kern = g[f"kernel_{k}_{ang}"]
+        for i, (h, w) in enumerate(meta["shapes"]):
+            for kind in ("uniform", "binary"):
+                img = synth(300 + i, h, w, kind)
+                want = g[f"out_{k}_{ang}_{kind}_{h}x{w}"]
+                assert np.array_equal(orc.filter2d(img, kern), want), (k, ang, h, w, kind)
+        for name, seed, h, w in meta["big"]:
+            if (k, ang) in ((9, 45), (11, 45), (9, 179.5)) or name.startswith("tail2"):
+                assert sha(orc.filter2d(synth(seed, h, w), kern)) == meta["sha"][f"{k}_{ang}_{name}"], (k, ang, name)
