@@ -43,7 +43,7 @@ def traffic_from_profile(name):
     """dram bytes per launch from the committed ncu summary of this kernel, if any."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(name)
+            return float(json.load(f)[name]["dram_bytes"])
     except Exception:
         return None
 
@@ -279,7 +279,7 @@ def main():
                    "images_per_gpu": n, "l2": "inputs (799 MB in + 799 MB out per step) larger than the 126 MB L2",
                    "sharding": "image index, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic_from_profile("blur_rows_kernel<9>"), "peak_source": peak_src,
+                     "traffic": traffic_from_profile("bench:blur_rows_kernel<9>"), "peak_source": peak_src,
                      "kernel": "rod::blur_rows_kernel<9>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_IMAGE * n,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": IMG_BYTES * n, "d2h_bytes_per_step": IMG_BYTES * n,
@@ -326,8 +326,26 @@ def extras(torch, np, plan, src, dst, peak):
     rsrc = torch.randint(0, 256, (rp.src_bytes,), dtype=torch.uint8, device="cuda")
     rdst = torch.empty_like(rsrc)
     out["lowres_mixed_256"] = rate(lambda: rp.lowres(rsrc, rdst), 2 * rp.payload_bytes, 256)
+    out["lowres_mixed_256"]["shapes"] = "VisDrone set + odd-dimension variants (1361x765, 1917x1079, 1999x1499)"
     out["blur_mixed_256"] = rate(lambda: rp.blur(rsrc, rdst), 2 * rp.payload_bytes, 256)
-    del rsrc, rdst
+    del rsrc, rdst, rp
+    # config 4: build_corrupted_testsets equivalent -- Noise (Philox), Blur, LowRes over 1610 VisDrone-test-dev-shaped
+    # images (real VisDrone resolutions only); three corrupted outputs per image, counted as outputs/s
+    rng = np.random.default_rng(4000)
+    shapes = [pool[i] for i in rng.integers(0, 8, 1610)]
+    tp = CorruptionPlan.ragged(shapes)
+    tsrc = torch.randint(0, 256, (tp.src_bytes,), dtype=torch.uint8, device="cuda")
+    tdst = torch.empty_like(tsrc)
+
+    def testset():
+        tp.noise(tsrc, tdst, None, 15.0, seed=42)
+        tp.blur(tsrc, tdst)
+        tp.lowres(tsrc, tdst)
+
+    out["testset_1610x3"] = rate(testset, 3 * 2 * tp.payload_bytes, 3 * 1610, steps=3, warmup=1)
+    out["testset_1610x3"]["unit"] = "corrupted outputs/s (3 per image), one GPU"
+    out["lowres_visdrone_1610"] = rate(lambda: tp.lowres(tsrc, tdst), 2 * tp.payload_bytes, 1610, steps=3, warmup=1)
+    del tsrc, tdst, tp
     # config 5: random one-of-three + letterbox 640 + normalise -> fp16 NCHW, batch 16
     import random
     from robust_object_detection_b200.batch import draw_decisions

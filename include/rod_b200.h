@@ -125,6 +125,14 @@ ROD_API int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, const 
                               const float* noise, float sigma, int k, double factor, uint64_t seed,
                               uint64_t first_image_index, uint32_t offset, void* stream);
 
+/* SURVEY 8f rank 4 -- RestorationDataset.__getitem__ (scripts/train_restoration.py:104-129) for a batch of patches.
+ * The plan's source descriptors are the crops (offset + pitch into the device-resident images; one patch size per
+ * batch); flips[i] != 0 applies cv2.flip(patch, 1) first; opcodes[i] picks the corruption (1..3; 0 = none).
+ * Outputs are device float32 [n,3,P,P] RGB planes of value / 255.0f: the corrupted input and the clean target. */
+ROD_API int rod_restoration_pairs_f32(rod_plan* plan, const uint8_t* src, const uint8_t* flips, const uint8_t* opcodes,
+                              float* corrupted_out, float* clean_out, const float* noise, float sigma, int k,
+                              double factor, uint64_t seed, uint64_t first_image_index, uint32_t offset, void* stream);
+
 /* Host-buffer entry points (what a per-image Python/cgo/JNI caller binds): src/dst are HOST
  * pointers laid out by the plan's descriptors; the call stages through pinned memory,
  * overlaps H2D / kernel / D2H in chunks of images, and returns after dst is complete. */

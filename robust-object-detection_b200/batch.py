@@ -54,6 +54,22 @@ def draw_decisions(n: int, gate: str = "ultralytics", p: float = 0.5) -> np.ndar
     return ops
 
 
+def draw_restoration_decisions(h: int, w: int, size: int, is_train: bool = True):
+    """(y, x, flip, op) of one RestorationDataset.__getitem__ call (train_restoration.py:77-102,108-121), consuming
+    Python's global `random` in the reference's order: randint(0, h - size), randint(0, w - size), random() > 0.5,
+    random.choice([...]); validation items take the centre crop and no flip.  Needs h, w >= size."""
+    if h < size or w < size:
+        raise NotImplementedError("images smaller than the patch are resized first in the reference (not on this path)")
+    if is_train:
+        y = random.randint(0, h - size)
+        x = random.randint(0, w - size)
+        flip = random.random() > 0.5
+    else:
+        y, x, flip = (h - size) // 2, (w - size) // 2, False
+    op = 1 + ("noise", "blur", "lowres").index(random.choice(["noise", "blur", "lowres"]))
+    return y, x, flip, op
+
+
 class CorruptionPlan:
     """Descriptor table + tile lists + resize tables for one batch layout."""
 
@@ -177,6 +193,16 @@ class CorruptionPlan:
                                                   int(out_w), int(pad_value), _ptr(noise), float(sigma), int(k),
                                                   float(factor), int(seed), int(first_image_index), int(offset),
                                                   _stream_handle(stream)), "rod_corrupt_letterbox_f16")
+
+    def restoration_pairs(self, src, flips, opcodes, corrupted_out, clean_out, noise=None, sigma: float = NOISE_SIGMA,
+                          k: int = BLUR_KERNEL, factor: float = DOWNSCALE_FACTOR, seed: int = 0,
+                          first_image_index: int = 0, offset: int = 0, stream=None) -> None:
+        """RestorationDataset.__getitem__ (train_restoration.py:104-129) for a batch: this plan's source descriptors
+        are the crops; outputs are float32 [n,3,P,P] RGB in [0,1] (corrupted input, clean target)."""
+        N.check(N.lib().rod_restoration_pairs_f32(self._h, _ptr(src), _ptr(flips), _ptr(opcodes), _ptr(corrupted_out),
+                                                  _ptr(clean_out), _ptr(noise), float(sigma), int(k), float(factor),
+                                                  int(seed), int(first_image_index), int(offset), _stream_handle(stream)),
+                "rod_restoration_pairs_f32")
 
     # -- host-buffer path (H2D + kernel + D2H inside the call) ---------------------------
     def apply_host(self, op: int, src_host, dst_host, noise_host=None, sigma: float = NOISE_SIGMA,

@@ -1,5 +1,6 @@
 // api.cu -- extern "C" entry points of librod_b200.so (declared in include/rod_b200.h).
 #include <algorithm>
+#include <vector>
 
 #include "rod_internal.h"
 
@@ -176,6 +177,41 @@ extern "C" int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, con
                        offset, (cudaStream_t)stream);
     if (rc != ROD_OK) return rc;
     return launch_letterbox(plan, plan->d_scratch, src, opcodes, out_f16, pad_value, (cudaStream_t)stream);
+}
+
+// RestorationDataset.__getitem__ (train_restoration.py:104-129) for a batch of patches.
+extern "C" int rod_restoration_pairs_f32(rod_plan* plan, const uint8_t* src, const uint8_t* flips, const uint8_t* opcodes,
+                                         float* corrupted_out, float* clean_out, const float* noise, float sigma, int k,
+                                         double factor, uint64_t seed, uint64_t first_image_index, uint32_t offset,
+                                         void* stream) {
+    if (plan == nullptr || src == nullptr || opcodes == nullptr || corrupted_out == nullptr || clean_out == nullptr)
+        return ROD_ERR_INVALID_ARG;
+    const int n = plan->n_images;
+    for (int i = 1; i < n; ++i)  // one patch size per batch: the outputs are dense [N,3,P,P] tensors
+        if (plan->descs[i].height != plan->descs[0].height || plan->descs[i].width != plan->descs[0].width)
+            return ROD_ERR_INVALID_ARG;
+    if (plan->inner == nullptr) {
+        std::vector<rod_image_desc> d(n);
+        const uint64_t bytes = 3ull * plan->descs[0].height * plan->descs[0].width;
+        const uint64_t stride = (bytes + 255) / 256 * 256;
+        for (int i = 0; i < n; ++i) {
+            d[i].src_offset = d[i].dst_offset = i * stride;
+            d[i].height = plan->descs[0].height;
+            d[i].width = plan->descs[0].width;
+            d[i].src_pitch = d[i].dst_pitch = 3ll * d[i].width;
+        }
+        int rc = rod_plan_create(d.data(), n, &plan->inner);
+        if (rc != ROD_OK) return rc;
+        ROD_CUDA(cudaMalloc((void**)&plan->d_patch_clean, n * stride + 64));
+        ROD_CUDA(cudaMalloc((void**)&plan->d_patch_corrupted, n * stride + 64));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_gather_patches(plan, plan->inner, src, plan->d_patch_clean, flips, st);
+    if (rc != ROD_OK) return rc;
+    rc = rod_corrupt_batch_u8(plan->inner, plan->d_patch_clean, plan->d_patch_corrupted, opcodes, noise, sigma, k, factor,
+                              seed, first_image_index, offset, stream);
+    if (rc != ROD_OK) return rc;
+    return launch_format_pairs(plan->inner, plan->d_patch_clean, plan->d_patch_corrupted, clean_out, corrupted_out, st);
 }
 
 // Host-buffer path: chunks of images are pipelined over three streams so the H2D copy of chunk

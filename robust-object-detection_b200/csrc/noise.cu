@@ -95,7 +95,7 @@ __device__ __forceinline__ uint32_t philox_word(uint32_t word, const float* s, f
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, MODE == NOISE_PHILOX ? 5 : 4) noise_kernel(NoiseParams p) {
+__global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
     const float K = p.sigma * ROD_NOISE_K_PER_SIGMA;
     for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
         const Tile t = p.tiles[ti];

@@ -295,6 +295,9 @@ extern "C" int rod_set_blur_kernel(rod_plan* plan, const float* kernel, int k) {
 
 extern "C" void rod_plan_destroy(rod_plan* plan) {
     if (plan == nullptr) return;
+    if (plan->inner) rod_plan_destroy(plan->inner);
+    if (plan->d_patch_clean) cudaFree(plan->d_patch_clean);
+    if (plan->d_patch_corrupted) cudaFree(plan->d_patch_corrupted);
     void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles,
                     plan->d_lowres_x2w_tiles, plan->d_lowres_x2_rest_tiles, plan->d_shapes,
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,

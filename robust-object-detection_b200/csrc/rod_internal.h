@@ -93,6 +93,11 @@ struct rod_plan {
     int n_f2d_tiles = 0;
     std::vector<int> f2d_tile_start;
 
+    // restoration pairs (rod_restoration_pairs_f32): contiguous-patch plan + two uint8 patch buffers
+    rod_plan* inner = nullptr;
+    uint8_t* d_patch_clean = nullptr;
+    uint8_t* d_patch_corrupted = nullptr;
+
     // host-buffer (e2e) staging
     uint8_t* d_stage_src = nullptr;
     uint8_t* d_stage_dst = nullptr;
@@ -128,6 +133,10 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
                   cudaStream_t stream, int img_lo, int img_hi);
 int launch_filter2d(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes, cudaStream_t stream,
                     int img_lo, int img_hi);
+int launch_gather_patches(const rod_plan* plan, const rod_plan* inner, const uint8_t* src, uint8_t* clean,
+                          const uint8_t* flips, cudaStream_t stream);
+int launch_format_pairs(const rod_plan* inner, const uint8_t* clean, const uint8_t* corrupted, float* clean_out,
+                        float* corrupted_out, cudaStream_t stream);
 int launch_letterbox(const rod_plan* plan, const uint8_t* img, const uint8_t* src, const uint8_t* opcodes, void* out_f16,
                      int pad_value, cudaStream_t stream);
 

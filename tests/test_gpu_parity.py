@@ -428,3 +428,38 @@ def test_apply_host_chunked_pipeline(torch_):
     want = [orc.apply_lowres(imgs[i], 0.5) for i in range(4)]
     for i in range(n):
         assert np.array_equal(dst[i], want[i % 4]), i
+
+
+def test_restoration_pairs_fused(torch_):
+    """RestorationDataset.__getitem__ on device (crop view -> flip -> corrupt -> RGB f32 CHW / 255 for
+    the corrupted input and the clean target), decisions drawn in the reference's RNG order."""
+    from robust_object_detection_b200.batch import CorruptionPlan, draw_restoration_decisions
+    size = 64
+    shapes = [(120, 200), (97, 133), (64, 64), (300, 180), (81, 90), (200, 201)]
+    imgs = [synth(5000 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    base = CorruptionPlan.ragged(shapes)  # only used to pack the full images into one device buffer
+    src = torch_.from_numpy(base.pack(imgs)).cuda()
+    random.seed(11)
+    dec = [draw_restoration_decisions(h, w, size, is_train=(i != 2)) for i, (h, w) in enumerate(shapes)]
+    offs = [base.src_offsets[i] + y * 3 * shapes[i][1] + 3 * x for i, (y, x, _, _) in enumerate(dec)]
+    plan = CorruptionPlan([(size, size)] * len(shapes), offs, [0] * len(shapes), src_pitches=[3 * w for _, w in shapes])
+    flips = torch_.tensor([int(f) for _, _, f, _ in dec], dtype=torch_.uint8, device="cuda")
+    ops = torch_.tensor([o for _, _, _, o in dec], dtype=torch_.uint8, device="cuda")
+    np.random.seed(21)
+    fields = [orc.draw_noise_field((size, size, 3), 15) for _ in shapes]
+    nz = torch_.from_numpy(np.stack(fields).reshape(-1)).cuda()
+    corrupted = torch_.zeros((len(shapes), 3, size, size), dtype=torch_.float32, device="cuda")
+    clean = torch_.zeros_like(corrupted)
+    plan.restoration_pairs(src, flips, ops, corrupted, clean, noise=nz)
+    assert {o for _, _, _, o in dec} == {1, 2, 3} and any(f for _, _, f, _ in dec)
+    for i, (img, (y, x, flip, op)) in enumerate(zip(imgs, dec)):
+        patch = img[y:y + size, x:x + size]
+        if flip:
+            patch = patch[:, ::-1]
+        patch = np.ascontiguousarray(patch)
+        cor = {1: lambda p: orc.add_noise_field(p, fields[i]), 2: lambda p: orc.apply_motion_blur(p, 9, 0),
+               3: lambda p: orc.apply_lowres(p, 0.5)}[op](patch)
+        want_clean = (patch[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1)
+        want_cor = (cor[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1)
+        assert np.array_equal(clean[i].cpu().numpy(), want_clean), i
+        assert np.array_equal(corrupted[i].cpu().numpy(), want_cor), (i, op)

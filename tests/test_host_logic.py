@@ -48,7 +48,7 @@ def test_no_cpu_fallback_without_device(built):
 def test_argument_validation_precedes_device_work(built):
     from robust_object_detection_b200 import augmentations as aug
     with pytest.raises(NotImplementedError):
-        aug.apply_motion_blur(np.zeros((4, 4, 3), np.uint8), 9, 45)
+        aug.apply_motion_blur(np.zeros((4, 4, 3), np.uint8), 13, 45)  # DFT territory in OpenCV: rejected before any device work
     with pytest.raises(NotImplementedError):
         aug.apply_motion_blur(np.zeros((4, 4, 3), np.uint8), 8, 0)
     with pytest.raises(ValueError):

@@ -12,7 +12,10 @@ python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref_$tag.json
 python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/plain_bench_$tag.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches_$tag.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/ncu_launch_$tag.log 2>&1
+# the headline launch itself (256 images): DRAM traffic for bench.py's roofline.traffic
+ncu --set full --clock-control none --import-source on -k regex:blur -s 3 -c 1 -f -o $out/prof_bench_$tag \
+    python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/ncu_bench_$tag.log 2>&1
 python tools/profile_ops.py > $out/plain_profile_$tag.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'blur|noise|lowres|letterbox' -s 3 -c 22 -f \
+ncu --set full --clock-control none --import-source on -k regex:'blur|noise|lowres|letterbox' -s 3 -c 24 -f \
     -o $out/prof_$tag python tools/profile_ops.py > $out/ncu_full_$tag.log 2>&1
 echo "done"

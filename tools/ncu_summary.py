@@ -13,7 +13,8 @@ from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, rep = sys.argv[1], sys.argv[2]
-launches = sys.argv[3] if len(sys.argv) > 3 else None
+launches = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] != "-" else None
+prefix = sys.argv[4] if len(sys.argv) > 4 else ""  # e.g. "bench:" for the capture of the headline launch
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -25,7 +26,7 @@ rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 cols = [i for i, h in enumerate(hdr) if h in ("ID", "Kernel Name", "Block Size", "Grid Size") or "__" in h]
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-with open(os.path.join(ROOT, "profiles", f"{tag}_kernels.csv"), "w", newline="") as f:
+with open(os.path.join(ROOT, "profiles", f"{tag}_{'bench_' if prefix else ''}kernels.csv"), "w", newline="") as f:
     w = csv.writer(f)
     w.writerow([hdr[i] + (f" [{units[i]}]" if units[i] else "") for i in cols])
     for r in rows[2:]:
@@ -44,7 +45,7 @@ for r in rows[2:]:
     if b > best.get(name, (0,))[0]:
         best[name] = (b, to_bytes(r[ri], units[ri]), to_bytes(r[wi], units[wi]))
 for name, (b, rd, wr) in best.items():
-    traffic[name] = {"dram_bytes": b, "read": rd, "write": wr, "capture": f"{tag}: {os.path.basename(rep)}, largest launch of this kernel"}
+    traffic[prefix + name] = {"dram_bytes": b, "read": rd, "write": wr, "capture": f"{tag}: {os.path.basename(rep)}, largest launch of this kernel"}
 json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 
 if launches:
