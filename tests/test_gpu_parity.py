@@ -439,7 +439,7 @@ def test_restoration_pairs_fused(torch_):
     imgs = [synth(5000 + i, h, w) for i, (h, w) in enumerate(shapes)]
     base = CorruptionPlan.ragged(shapes)  # only used to pack the full images into one device buffer
     src = torch_.from_numpy(base.pack(imgs)).cuda()
-    random.seed(11)
+    random.seed(2)
     dec = [draw_restoration_decisions(h, w, size, is_train=(i != 2)) for i, (h, w) in enumerate(shapes)]
     offs = [base.src_offsets[i] + y * 3 * shapes[i][1] + 3 * x for i, (y, x, _, _) in enumerate(dec)]
     plan = CorruptionPlan([(size, size)] * len(shapes), offs, [0] * len(shapes), src_pitches=[3 * w for _, w in shapes])
