@@ -106,7 +106,13 @@ extern "C" const char* rod_status_string(int status) {
 extern "C" int rod_plan_launches(const rod_plan* plan, int op) {
     if (plan == nullptr) return 0;
     switch (op) {
-        case ROD_OP_NONE: case ROD_OP_NOISE: case ROD_OP_BLUR: case ROD_OP_LOWRES: return 1;
+        case ROD_OP_NONE: case ROD_OP_NOISE: case ROD_OP_BLUR: return 1;
+        case ROD_OP_LOWRES: {  // one launch per non-empty tile list (known once the resize tables exist)
+            if (plan->d_shapes == nullptr) return 1;
+            const int n = (plan->n_lowres_tiles > 0) + (plan->n_lowres_x2w_tiles > 0) + (plan->n_lowres_x2w4_tiles > 0) +
+                          (plan->n_lowres_x2_rest_tiles > 0);
+            return n > 0 ? n : 1;
+        }
         case 100: return 4;  // rod_corrupt_batch_u8: copy + noise + blur + lowres
         case 101: return 4;  // rod_corrupt_letterbox_f16: noise + blur + lowres + letterbox (clean images are read in place)
         default: return 0;

@@ -672,21 +672,24 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
         }
     }
     // exact-2x shapes: warp-marching kernel when the rows are 4-byte aligned, full-width strips otherwise
-    const bool use_bands = plan->n_lowres_x2w_tiles > 0 && (((uintptr_t)src) & 3) == 0;
+    const bool use_bands = (plan->n_lowres_x2w_tiles + plan->n_lowres_x2w4_tiles) > 0 && (((uintptr_t)src) & 3) == 0;
     if (use_bands) {
-        const int t_lo = plan->lowres_x2w_tile_start[img_lo], t_hi = plan->lowres_x2w_tile_start[img_hi];
-        if (t_hi > t_lo) {
+        const size_t smem = 4 * sizeof(X2wWarpTables);
+        for (int pass = 0; pass < 2; ++pass) {  // 0: images with 8-byte aligned rows (64-bit loads), 1: the others
+            const std::vector<int>& st = pass == 0 ? plan->lowres_x2w_tile_start : plan->lowres_x2w4_tile_start;
+            const Tile* tl = pass == 0 ? plan->d_lowres_x2w_tiles : plan->d_lowres_x2w4_tiles;
+            if ((pass == 0 ? plan->n_lowres_x2w_tiles : plan->n_lowres_x2w4_tiles) == 0) continue;
+            const int t_lo = st[img_lo], t_hi = st[img_hi];
+            if (t_hi <= t_lo) continue;
             LowresX2wParams p;
             p.images = plan->d_images;
-            p.tiles = plan->d_lowres_x2w_tiles + t_lo;
+            p.tiles = tl + t_lo;
             p.n_tiles = t_hi - t_lo;
             p.shapes = plan->d_shapes;
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             const int ctas = (p.n_tiles + 3) / 4;
-            // 64-bit source loads when every row of every image is 8-byte aligned
-            const size_t smem = 4 * sizeof(X2wWarpTables);
-            if (plan->x2w_all_al8 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, 4), 128, smem, stream>>>(p);
+            if (pass == 0 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, 4), 128, smem, stream>>>(p);
             else lowres_x2w_kernel<false><<<grid_for(plan, ctas, 4), 128, smem, stream>>>(p);
             ROD_CUDA(cudaGetLastError());
         }

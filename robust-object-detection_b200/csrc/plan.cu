@@ -69,6 +69,10 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         const DevImage& im = plan->h_images[i];
         return shapes[im.shape_id].x2w != 0 && (im.src_pitch & 3) == 0 && (im.src_off & 3) == 0;
     };
+    auto al8_image = [&](int i) {
+        const DevImage& im = plan->h_images[i];
+        return (im.src_pitch & 7) == 0 && (im.src_off & 7) == 0 && (im.w & 7) == 0;
+    };
     auto n_strips = [&](int w) { return ((w + 7) / 8 + 29) / 30; };
     int band_rows = 0;
     if (march) {
@@ -79,7 +83,7 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         band_rows = e_band ? atoi(e_band) : (int)(strip_rows / (64LL * plan->sm_count));
         band_rows = std::max(24, std::min(256, band_rows & ~7));  // <= kX2wMaxBandRows (per-warp shared tables)
     }
-    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2_rest_tiles;
+    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles;
     build_strip_tiles(plan->h_images, shapes, false, kLowresTH, kLowresTWB, gen_tiles);
     build_strip_tiles(plan->h_images, shapes, true, kLowresTH, kLowresTWB, x2_tiles);
     for (int i = 0; i < plan->n_images; ++i) {
@@ -88,39 +92,36 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         if (march && march_image(i)) {
             for (int y = 0; y < plan->h_images[i].h; y += band_rows)
                 for (int st = 0; st < n_strips(plan->h_images[i].w); ++st)
-                    x2w_tiles.push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows), st});
+                    (al8_image(i) ? x2w_tiles : x2w4_tiles).push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows), st});
         } else {
             for (int y = 0; y < plan->h_images[i].h; y += sh.strip_rows) x2_rest_tiles.push_back(Tile{i, y, 0, 0});
         }
     }
-    void* old[] = {plan->d_shapes, plan->d_tab, plan->d_lowres_tiles, plan->d_lowres_x2_tiles, plan->d_lowres_x2w_tiles,
+    void* old[] = {plan->d_shapes, plan->d_tab, plan->d_lowres_tiles, plan->d_lowres_x2_tiles, plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles,
                    plan->d_lowres_x2_rest_tiles};
     for (void* q : old)
         if (q) cudaFree(q);
     plan->d_shapes = nullptr; plan->d_tab = nullptr; plan->d_lowres_tiles = nullptr; plan->d_lowres_x2_tiles = nullptr;
-    plan->d_lowres_x2w_tiles = nullptr; plan->d_lowres_x2_rest_tiles = nullptr;
+    plan->d_lowres_x2w_tiles = nullptr; plan->d_lowres_x2w4_tiles = nullptr; plan->d_lowres_x2_rest_tiles = nullptr;
     int rc = upload(shapes, &plan->d_shapes);
     if (rc == ROD_OK) rc = upload(blob, &plan->d_tab);
     if (rc == ROD_OK) rc = upload(gen_tiles, &plan->d_lowres_tiles);
     if (rc == ROD_OK) rc = upload(x2_tiles, &plan->d_lowres_x2_tiles);
     if (rc == ROD_OK) rc = upload(x2w_tiles, &plan->d_lowres_x2w_tiles);
+    if (rc == ROD_OK) rc = upload(x2w4_tiles, &plan->d_lowres_x2w4_tiles);
     if (rc == ROD_OK) rc = upload(x2_rest_tiles, &plan->d_lowres_x2_rest_tiles);
     if (rc != ROD_OK) return rc;
     plan->n_lowres_tiles = (int)gen_tiles.size();
     plan->n_lowres_x2_tiles = (int)x2_tiles.size();
     plan->n_lowres_x2w_tiles = (int)x2w_tiles.size();
+    plan->n_lowres_x2w4_tiles = (int)x2w4_tiles.size();
+    tile_starts(x2w4_tiles, plan->n_images, plan->lowres_x2w4_tile_start);
     plan->n_lowres_x2_rest_tiles = (int)x2_rest_tiles.size();
     tile_starts(gen_tiles, plan->n_images, plan->lowres_tile_start);
     tile_starts(x2_tiles, plan->n_images, plan->lowres_x2_tile_start);
     tile_starts(x2w_tiles, plan->n_images, plan->lowres_x2w_tile_start);
     tile_starts(x2_rest_tiles, plan->n_images, plan->lowres_x2_rest_tile_start);
     plan->lowres_x2w_band_rows = band_rows;
-    plan->x2w_all_al8 = true;
-    for (int i = 0; i < plan->n_images; ++i)
-        if (march && march_image(i)) {
-            const DevImage& im = plan->h_images[i];
-            if ((im.src_pitch & 7) != 0 || (im.src_off & 7) != 0 || (im.w & 7) != 0) plan->x2w_all_al8 = false;
-        }
     plan->lowres_x2_smem = x2_smem;
     plan->lowres_factor = factor;
     plan->lowres_all_identity = all_identity;
@@ -299,7 +300,7 @@ extern "C" void rod_plan_destroy(rod_plan* plan) {
     if (plan->d_patch_clean) cudaFree(plan->d_patch_clean);
     if (plan->d_patch_corrupted) cudaFree(plan->d_patch_corrupted);
     void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles,
-                    plan->d_lowres_x2w_tiles, plan->d_lowres_x2_rest_tiles, plan->d_shapes,
+                    plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles, plan->d_lowres_x2_rest_tiles, plan->d_shapes,
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
                     plan->d_f2d_taps, plan->d_f2d_tiles,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};

@@ -61,12 +61,14 @@ struct rod_plan {
     int lowres_x2_threads = 128;  // CTA size of lowres_x2_kernel (ROD_X2_THREADS=128|256)
     // warp-marching x2 kernel (4-byte aligned rows of eligible exact-2x shapes): band x strip tiles; the strip-kernel
     // list restricted to the remaining exact-2x images
-    rod::Tile* d_lowres_x2w_tiles = nullptr;
+    rod::Tile* d_lowres_x2w_tiles = nullptr;    // images whose rows are 8-byte aligned and w % 8 == 0 (64-bit loads)
+    rod::Tile* d_lowres_x2w4_tiles = nullptr;   // the other eligible images (32-bit loads)
+    int n_lowres_x2w4_tiles = 0;
+    std::vector<int> lowres_x2w4_tile_start;
     rod::Tile* d_lowres_x2_rest_tiles = nullptr;
     int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
     std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
     int lowres_x2w_band_rows = 0;
-    bool x2w_all_al8 = false;  // every x2w image has 8-byte aligned rows and w % 8 == 0
     bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
 
     // lowres tables, rebuilt when the factor changes
