@@ -1,0 +1,151 @@
+"""Main-process training hook: corruption + detector-input formatting on the GPU, fed from
+pinned host memory, for the Ultralytics launchers of the reference.
+
+The reference runs the corruption inside 8 forked DataLoader workers
+(scripts/augmentations.py:91-95, scripts/train_yolo_augmented.py:33).  CUDA cannot be initialised in those forks,
+and per-image host calls would be PCIe-latency bound anyway, so the B200 path moves the hook to the main process,
+after collation: raw HWC BGR uint8 frames of one batch go through ONE pinned staging buffer and ONE H2D copy, the
+decisions are drawn from Python's `random` in the reference's order (random() < 0.5, then random.choice), and
+`rod_corrupt_letterbox_f16` produces the fp16 NCHW tensor the detector consumes.  Two staging slots and a copy
+stream let batch i+1 upload while batch i is being corrupted.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .batch import CorruptionPlan, draw_decisions
+
+
+class CorruptionBatcher:
+    """Double-buffered host->device pipeline around CorruptionPlan.corrupt_letterbox.
+
+        batcher = CorruptionBatcher(out_hw=(640, 640), seed=42)
+        for x in batcher.run(batches):      # batches: iterable of lists of HWC BGR uint8 arrays
+            loss = model(x)                 # x: torch.float16 [B,3,640,640] RGB in [0,1], on the GPU
+
+    Per batch: `draw_decisions(B, gate)` consumes the global `random` stream exactly as B consecutive calls of the
+    reference hook would; Philox noise is keyed by (seed, running global image index), so a run is reproducible
+    and independent of how images are grouped into batches.
+    """
+
+    def __init__(self, out_hw: Tuple[int, int] = (640, 640), pad_value: int = 114, gate: str = "ultralytics",
+                 seed: int = 0, max_cached_plans: int = 16):
+        import torch
+        self._torch = torch
+        self.out_h, self.out_w = int(out_hw[0]), int(out_hw[1])
+        self.pad_value, self.gate, self.seed = int(pad_value), gate, int(seed)
+        self._plans: dict = {}
+        self._max_plans = max_cached_plans
+        self._copy_stream = torch.cuda.Stream()
+        self._slots: List[dict] = [{}, {}]
+        self.images_seen = 0
+
+    # ------------------------------------------------------------------ internals
+    def _plan(self, shapes: Sequence[Tuple[int, int]]) -> CorruptionPlan:
+        key = tuple(shapes)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= self._max_plans:
+                self._plans.pop(next(iter(self._plans)))
+            plan = CorruptionPlan.ragged(shapes)
+            self._plans[key] = plan
+        return plan
+
+    def _stage(self, slot: dict, images: Sequence[np.ndarray], ops: Optional[np.ndarray]):
+        """Pack one batch into the slot's pinned buffer and start its H2D copy on the copy stream."""
+        torch = self._torch
+        shapes = [(int(im.shape[0]), int(im.shape[1])) for im in images]
+        plan = self._plan(shapes)
+        nbytes = plan.src_bytes
+        if slot.get("cap", 0) < nbytes:
+            cap = max(nbytes, 2 * slot.get("cap", 0))
+            slot["host"] = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            slot["dev"] = torch.empty(cap, dtype=torch.uint8, device="cuda")
+            slot["cap"] = cap
+        ev = slot.get("free")
+        if ev is not None:
+            ev.synchronize()  # the compute that last read this slot's device buffer has finished
+        hbuf = slot["host"].numpy()
+        for im, off, (h, w) in zip(images, plan.src_offsets, shapes):
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError("expected HWC uint8 BGR frames")
+            hbuf[off:off + 3 * h * w] = np.ascontiguousarray(im).reshape(-1)
+        if ops is None:
+            ops = draw_decisions(len(images), gate=self.gate)
+        n = len(images)
+        if slot.get("ops_cap", 0) < n:
+            slot["ops_host"] = torch.empty(max(n, 64), dtype=torch.uint8).pin_memory()
+            slot["ops_dev"] = torch.empty(max(n, 64), dtype=torch.uint8, device="cuda")
+            slot["ops_cap"] = max(n, 64)
+        slot["ops_host"][:n] = torch.from_numpy(np.asarray(ops, dtype=np.uint8))
+        with torch.cuda.stream(self._copy_stream):
+            slot["dev"][:nbytes].copy_(slot["host"][:nbytes], non_blocking=True)
+            slot["ops_dev"][:n].copy_(slot["ops_host"][:n], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        slot.update(plan=plan, n=n, ready=ready, ops=np.asarray(ops, dtype=np.uint8), first_index=self.images_seen)
+        self.images_seen += n
+
+    def _compute(self, slot: dict):
+        torch = self._torch
+        cur = torch.cuda.current_stream()
+        cur.wait_event(slot["ready"])
+        n = slot["n"]
+        out = torch.empty((n, 3, self.out_h, self.out_w), dtype=torch.float16, device="cuda")
+        slot["plan"].corrupt_letterbox(slot["dev"], slot["ops_dev"], out, self.out_h, self.out_w, self.pad_value,
+                                       seed=self.seed, first_image_index=slot["first_index"])
+        free = torch.cuda.Event()
+        free.record(cur)
+        slot["free"] = free
+        return out
+
+    # ------------------------------------------------------------------ public
+    def __call__(self, images: Sequence[np.ndarray], ops: Optional[np.ndarray] = None):
+        """One batch, no overlap: returns the fp16 [B,3,H,W] tensor (and leaves the drawn op-codes in .last_ops)."""
+        slot = self._slots[0]
+        self._stage(slot, images, ops)
+        self.last_ops = slot["ops"]
+        return self._compute(slot)
+
+    def run(self, batches: Iterable[Sequence[np.ndarray]]) -> Iterator:
+        """Pipelined: while batch i is corrupted on the current stream, batch i+1 is packed and uploaded."""
+        it = iter(batches)
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        k = 0
+        self._stage(self._slots[0], first, None)
+        while True:
+            cur = self._slots[k & 1]
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            if nxt is not None:
+                self._stage(self._slots[(k + 1) & 1], nxt, None)
+            self.last_ops = cur["ops"]
+            yield self._compute(cur)
+            if nxt is None:
+                return
+            k += 1
+
+
+def patch_ultralytics_trainer(trainer, batcher: Optional[CorruptionBatcher] = None):
+    """Optional glue for Ultralytics' trainer objects: replaces `trainer.preprocess_batch` so that a batch whose
+    "raw" entry holds the collated HWC BGR uint8 frames is corrupted + letterboxed + normalised on the GPU.
+    (Ultralytics is not installed in the build image; the contract is exercised with a stub in the tests.)"""
+    batcher = batcher or CorruptionBatcher()
+    orig = trainer.preprocess_batch
+
+    def _preprocess(batch):
+        raw = batch.get("raw")
+        if raw is None:
+            return orig(batch)
+        batch["img"] = batcher(raw).float() if getattr(trainer, "amp", True) is False else batcher(raw)
+        return batch
+
+    trainer.preprocess_batch = _preprocess
+    return batcher

@@ -463,3 +463,37 @@ def test_restoration_pairs_fused(torch_):
         want_cor = (cor[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1)
         assert np.array_equal(clean[i].cpu().numpy(), want_clean), i
         assert np.array_equal(corrupted[i].cpu().numpy(), want_cor), (i, op)
+
+
+def test_training_batcher_pinned_pipeline(torch_):
+    """main-process hook -- pinned staging + copy stream + corrupt_letterbox, decisions in the
+    reference's RNG order, Philox keyed by the running global image index (independent of batching)."""
+    from robust_object_detection_b200.training import CorruptionBatcher
+    shapes = [(765, 1360), (540, 960), (360, 480), (333, 517)]
+    frames = [synth(6000 + i, *shapes[i % 4]) for i in range(12)]
+    batches = [frames[0:4], frames[4:7], frames[7:12]]
+    random.seed(42)
+    want_ops = orc.draw_decisions(12, gate="ultralytics")
+    random.seed(42)
+    b = CorruptionBatcher(out_hw=(160, 160), seed=9)
+    outs, ops = [], []
+    for x in b.run(batches):
+        outs.append(x.cpu().numpy())
+        ops.extend(b.last_ops.tolist())
+    assert ops == list(want_ops) and len(set(ops)) == 4
+    got = np.concatenate(outs)
+    for i, (img, op) in enumerate(zip(frames, ops)):
+        if op == 1:
+            cor = orc.add_philox_noise(img, orc.philox_noise_field(img.size, 15.0, 9, i))
+        else:
+            cor = orc.apply_op(img, op)
+        want = orc.letterbox_norm_f16(cor, 160, 160)
+        if op == 1:
+            assert np.mean(got[i] != want) < 2e-3, i   # sin/cos/log approximations at truncation boundaries
+        else:
+            assert np.array_equal(got[i], want), (i, op)
+    # same frames, different batching, same result (global image index keys the noise)
+    random.seed(42)
+    b2 = CorruptionBatcher(out_hw=(160, 160), seed=9)
+    got2 = np.concatenate([x.cpu().numpy() for x in b2.run([frames[0:6], frames[6:12]])])
+    assert np.array_equal(got, got2)
