@@ -1,4 +1,6 @@
 // api.cu -- extern "C" entry points of librod_b200.so (declared in include/rod_b200.h).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -177,6 +179,20 @@ extern "C" int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, con
         plan->d_scratch = nullptr;
         ROD_CUDA(cudaMalloc((void**)&plan->d_scratch, plan->dst_extent + 64));
         plan->scratch_bytes = plan->dst_extent;
+    }
+    // Fused path: noise / blur / clean rows are produced inside the letterbox kernel (no full-resolution round trip);
+    // only LowRes images go through the scratch.  Needs plain linear letterboxes, the angle-0 blur and Philox sigma
+    // in range; ROD_FUSED_LETTERBOX=0 selects the unfused kernels (benchmark knob).
+    const char* e_fused = getenv("ROD_FUSED_LETTERBOX");
+    const bool fused = plan->lb_all_linear && plan->f2d_ntaps == 0 && blur_supported(k, 0.0) && k >= 3 &&
+                       (noise != nullptr || sigma <= kPhiloxMaxSigma) && !(e_fused && atoi(e_fused) == 0);
+    if (fused) {
+        rc = run_op(plan, ROD_OP_LOWRES, src, plan->d_scratch, noise, sigma, k, factor, seed, first_image_index, offset,
+                    opcodes, (cudaStream_t)stream, 0, plan->n_images);
+        if (rc != ROD_OK) return rc;
+        rc = launch_fused_letterbox(plan, src, plan->d_scratch, opcodes, noise, out_f16, pad_value, sigma, k, seed,
+                                    first_image_index, offset, (cudaStream_t)stream);
+        if (rc != ROD_ERR_UNSUPPORTED) return rc;  // rows too wide for the per-warp buffers: unfused path below
     }
     // images that stay clean are read from `src` by the letterbox kernel itself: no copy into the scratch
     rc = run_mixed_ops(plan, ROD_OP_NOISE, src, plan->d_scratch, opcodes, noise, sigma, k, factor, seed, first_image_index,

@@ -116,6 +116,226 @@ __global__ void __launch_bounds__(256) letterbox_kernel(LbParams p) {
     }
 }
 
+// =====================================================================================
+// Fused training path: corruption + letterbox + normalise in ONE pass over the source (BASELINE config 5).
+// A warp owns one output row.  It produces the (at most two) full-resolution CORRUPTED source rows that row blends
+// into its private shared-memory buffers -- clean rows are copied, noise rows get the Philox (or supplied) field,
+// blur rows are filtered from a staged raw row with reflected halo (same arithmetic as noise.cu / blur.cu) -- and
+// then resamples them.  With a down-scaling letterbox every source row is produced exactly once, so the corrupted
+// full-resolution image never exists in HBM.  Images whose op is LowRes are the exception: the resize kernels
+// write them to the scratch first and this kernel reads them from there like clean rows.
+// =====================================================================================
+struct FusedLbParams {
+    const DevImage* images;
+    const DevLetterbox* lb;
+    const uint32_t* tab;
+    int n_images;
+    const uint8_t* src;      // original images (src descriptors)
+    const uint8_t* scratch;  // LowRes-corrupted images (dst descriptors)
+    const uint8_t* opcodes;
+    const float* noise;      // supplied field (compat mode) or NULL (Philox)
+    __half* out;
+    int out_h, out_w, pad;
+    float K;                 // sigma * sqrt(2 ln 2)
+    uint32_t key0, key1, offset;
+    uint64_t first_image;
+    int k;                   // blur taps (odd)
+    int buf_bytes;           // bytes of one row buffer (16-byte multiple, >= 3 * max_w + 32)
+    int raw_bytes;           // bytes of the raw (blur staging) buffer
+};
+
+constexpr int kFusedLeft = 64;  // bytes in front of pixel 0 in every row buffer (halo of up to 15 pixels + window)
+
+__device__ __forceinline__ void fused_cp_async16(uint32_t smem_addr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+
+// start copying source row `srow` (n bytes) to row[0 .. n): 16-byte cp.async when the row is 16-byte aligned (whole
+// chunks; the last one may read up to 15 bytes past the row, inside the same 16-byte granule of the allocation),
+// plain 32-bit / byte loads otherwise.  Completion: cp.async.wait_group + __syncwarp by the caller.
+__device__ __forceinline__ void fused_stage_row(const uint8_t* srow, int n, uint8_t* row, int lane) {
+    if ((((uintptr_t)srow) & 15) == 0) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(row);
+        for (int j = lane; j < ((n + 15) >> 4); j += 32) fused_cp_async16(d + 16 * j, srow + 16 * j);
+    } else if (((((uintptr_t)srow) | (uintptr_t)n) & 3) == 0) {
+        for (int i = lane; i < (n >> 2); i += 32) reinterpret_cast<uint32_t*>(row)[i] = __ldg(reinterpret_cast<const uint32_t*>(srow) + i);
+    } else {
+        for (int i = lane; i < n; i += 32) row[i] = srow[i];
+    }
+}
+
+// in place: row := noise(row) for image row y (flat element index e0 = y * n of its first byte)
+__device__ __forceinline__ void fused_noise_row(const FusedLbParams& p, const DevImage& im, int img_index, int y, uint8_t* row,
+                                                int lane) {
+    const int n = 3 * im.w;
+    const uint32_t e0 = (uint32_t)y * (uint32_t)n;
+    if (p.noise != nullptr) {
+        const float* nz = p.noise + im.elem_base + e0;
+        for (int i = lane; i < n; i += 32) row[i] = (uint8_t)noise_px(__uint_as_float(0x4B000000u | row[i]) - 8388608.0f, nz[i]);
+        return;
+    }
+    const uint64_t ig = p.first_image + (uint64_t)img_index;
+    const uint32_t g_first = e0 >> 3, g_last = (e0 + (uint32_t)n - 1u) >> 3;
+    const bool words = ((e0 | (uint32_t)n) & 7u) == 0;  // the row is made of whole Philox groups (row buffers are 16-byte aligned)
+    for (uint32_t g = g_first + lane; g <= g_last; g += 32) {
+        uint32_t r[4];
+        float sf[8];
+        philox4x32_10(g, (uint32_t)ig, (uint32_t)(ig >> 32), p.offset, p.key0, p.key1, r);
+        if (philox_needs_tail(r)) {
+            uint32_t t[4];
+            philox4x32_10(g, (uint32_t)ig, (uint32_t)(ig >> 32) ^ ROD_PHILOX_TAIL_FLIP, p.offset, p.key0, p.key1, t);
+            gauss8(r, t, sf);
+        } else {
+            gauss8(r, nullptr, sf);
+        }
+        if (words) {
+            uint2* q = reinterpret_cast<uint2*>(row + (int)(8u * g - e0));
+            const uint2 v = *q;
+            *q = make_uint2(philox_word(v.x, sf, p.K), philox_word(v.y, sf + 4, p.K));
+            continue;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int x = (int)(8u * g + q - e0);
+            if (x >= 0 && x < n) row[x] = (uint8_t)noise_philox_px(row[x], sf[q], p.K);
+        }
+    }
+}
+
+// dst[0 .. n) := blur(row) where row (with kFusedLeft bytes of room in front and 64 behind) holds the raw image row
+__device__ __forceinline__ void fused_blur_row(const FusedLbParams& p, const DevImage& im, uint8_t* row, uint8_t* dst, int lane) {
+    const int n = 3 * im.w, halo = 3 * (p.k >> 1);
+    for (int q = lane; q < 2 * halo; q += 32) {
+        const int i = (q < halo) ? (q - halo) : (n + q - halo);
+        const int px = (i >= 0) ? i / 3 : -((-i + 2) / 3);
+        const int c = i - 3 * px;
+        row[i] = row[3 * reflect101(px, im.w) + c];
+    }
+    __syncwarp();
+    if (p.k == 9) {
+        for (int j = lane; j < ((n + 15) >> 4); j += 32) {
+            const uint4* wp = reinterpret_cast<const uint4*>(row + 16 * j - 16);
+            const uint4 a = wp[0], b = wp[1], c = wp[2];
+            const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+            uint32_t o[4];
+            blur9_chunk16(w, o);
+            *reinterpret_cast<uint4*>(dst + 16 * j) = make_uint4(o[0], o[1], o[2], o[3]);  // the tail beyond n is padding
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) dst[i] = (uint8_t)blur_byte_generic(row, i, p.k);
+    }
+}
+
+// six consecutive bytes of a shared-memory row buffer starting at byte offset `o` (buffers are padded: no bound check)
+__device__ __forceinline__ void load6_smem(const uint8_t* buf, int o, uint32_t& lo, uint32_t& hi) {
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(buf + (o & ~3));
+    const int sh = (o & 3) * 8;
+    const uint32_t w0 = a[0], w1 = a[1], w2 = a[2];
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
+__global__ void __launch_bounds__(256) fused_letterbox_kernel(FusedLbParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __half* lut = reinterpret_cast<__half*>(smem);  // 256 x half(v / 255)
+    lut[threadIdx.x] = __float2half_rn(__fdiv_rn((float)threadIdx.x, 255.0f));
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // three identical row buffers per warp: [kFusedLeft | row | 64]
+    uint8_t* X0 = smem + 512 + (size_t)warp * (3 * p.buf_bytes) + kFusedLeft;
+    uint8_t* X1 = X0 + p.buf_bytes;
+    uint8_t* X2 = X1 + p.buf_bytes;
+    const size_t plane = (size_t)p.out_h * p.out_w;
+    const __half padh = lut[p.pad];
+    const int groups = (p.out_h + 7) >> 3;
+    for (int ti = blockIdx.x; ti < p.n_images * groups; ti += gridDim.x) {
+        const int img = ti / groups;
+        const int Y = (ti - img * groups) * 8 + warp;
+        if (Y >= p.out_h) continue;
+        const DevImage im = p.images[img];
+        const DevLetterbox g = p.lb[im.shape_id];
+        __half* orow = p.out + (size_t)img * 3 * plane + (size_t)Y * p.out_w;
+        const int cy = Y - g.top;
+        if (cy < 0 || cy >= g.new_h) {
+            for (int X = lane; X < p.out_w; X += 32) { orow[X] = padh; orow[plane + X] = padh; orow[2 * plane + X] = padh; }
+            continue;
+        }
+        const int op = p.opcodes[img];
+        const bool pre = (op == ROD_OP_LOWRES);
+        const uint8_t* base = pre ? p.scratch + im.dst_off : p.src + im.src_off;
+        const int64_t pitch = pre ? im.dst_pitch : im.src_pitch;
+        const uint32_t ys = p.tab[g.ly_s + cy], yb = p.tab[g.ly_b + cy];
+        const int r0 = (int)(ys & 0xFFFFu), r1 = (int)(ys >> 16);
+        const int n = 3 * im.w;
+        const bool two = (r1 != r0);
+        const bool blur = (op == ROD_OP_BLUR);
+        // both source rows are requested before anything waits (blur filters out of place: X1 -> X0, X2 -> X1)
+        fused_stage_row(base + (int64_t)r0 * pitch, n, blur ? X1 : X0, lane);
+        if (two) fused_stage_row(base + (int64_t)r1 * pitch, n, blur ? X2 : X1, lane);
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (op == ROD_OP_NOISE) {
+            fused_noise_row(p, im, img, r0, X0, lane);
+            if (two) fused_noise_row(p, im, img, r1, X1, lane);
+        } else if (blur) {
+            fused_blur_row(p, im, X1, X0, lane);
+            __syncwarp();
+            if (two) fused_blur_row(p, im, X2, X1, lane);
+        }
+        const uint8_t* bufA = X0;
+        const uint8_t* rowB = two ? X1 : X0;
+        __syncwarp();
+        const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + g.lx_s0);
+        for (int X = lane; X < p.out_w; X += 32) {
+            const int cx = X - g.left;
+            __half h0 = padh, h1 = padh, h2 = padh;
+            if (cx >= 0 && cx < g.new_w) {
+                const int s0 = lx_s0[cx];
+                const uint32_t a = p.tab[g.lx_a + cx];
+                uint32_t lo0, hi0, lo1, hi1;
+                load6_smem(bufA, 3 * s0, lo0, hi0);
+                load6_smem(rowB, 3 * s0, lo1, hi1);
+                if (s0 + 1 > g.w - 1) {  // right border: both taps are the last pixel
+                    hi0 = __byte_perm(lo0, 0u, 0x4421); lo0 = __byte_perm(lo0, 0u, 0x0210);
+                    hi1 = __byte_perm(lo1, 0u, 0x4421); lo1 = __byte_perm(lo1, 0u, 0x0210);
+                }
+                const uint32_t g0[3] = {__byte_perm(lo0, hi0, 0x4430), __byte_perm(lo0, hi0, 0x4441), __byte_perm(lo0, hi0, 0x4452)};
+                const uint32_t g1[3] = {__byte_perm(lo1, hi1, 0x4430), __byte_perm(lo1, hi1, 0x4441), __byte_perm(lo1, hi1, 0x4452)};
+                uint32_t v[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = linear_v(dot2_lo(a, g0[c], 0u) >> 4, dot2_lo(a, g1[c], 0u) >> 4, yb);
+                h2 = lut[v[0]]; h1 = lut[v[1]]; h0 = lut[v[2]];  // BGR -> RGB
+            }
+            orow[X] = h0; orow[plane + X] = h1; orow[2 * plane + X] = h2;
+        }
+        __syncwarp();  // the row buffers are rewritten by this warp's next row
+    }
+}
+
+int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8_t* scratch, const uint8_t* opcodes,
+                           const float* noise, void* out_f16, int pad_value, float sigma, int k, uint64_t seed,
+                           uint64_t first_image, uint32_t offset, cudaStream_t stream) {
+    FusedLbParams p;
+    p.images = plan->d_images; p.lb = plan->d_lb; p.tab = plan->d_lb_tab; p.n_images = plan->n_images;
+    p.src = src; p.scratch = scratch; p.opcodes = opcodes; p.noise = noise;
+    p.out = reinterpret_cast<__half*>(out_f16);
+    p.out_h = plan->lb_out_h; p.out_w = plan->lb_out_w; p.pad = pad_value;
+    p.K = sigma * ROD_NOISE_K_PER_SIGMA;
+    p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32); p.offset = offset; p.first_image = first_image;
+    p.k = k;
+    p.buf_bytes = kFusedLeft + ((3 * plan->max_w + 15) & ~15) + 64;
+    p.raw_bytes = 0;
+    const size_t smem = 512 + 8 * (size_t)(3 * p.buf_bytes);
+    if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
+    ROD_CUDA(cudaFuncSetAttribute(fused_letterbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : per_sm;
+    const int tiles = plan->n_images * ((p.out_h + 7) / 8);
+    fused_letterbox_kernel<<<grid_for(plan, tiles, per_sm * 4), 256, smem, stream>>>(p);
+    ROD_CUDA(cudaGetLastError());
+    return ROD_OK;
+}
+
 int launch_letterbox(const rod_plan* plan, const uint8_t* img, const uint8_t* src, const uint8_t* opcodes, void* out_f16,
                      int pad_value, cudaStream_t stream) {
     if (plan->n_lb_tiles == 0) return ROD_OK;

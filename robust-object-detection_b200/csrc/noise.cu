@@ -86,16 +86,6 @@ __device__ __forceinline__ void group_gauss8(const NoiseParams& p, uint32_t ig_l
     }
 }
 
-// four pixels (one word) + four factors -> four output bytes: clamp(v + floor(K s), 0, 255)
-__device__ __forceinline__ uint32_t philox_word(uint32_t word, const float* s, float K) {
-    const uint32_t f01 = __byte_perm(noise_floor16(s[0], K), noise_floor16(s[1], K), 0x5410);
-    const uint32_t f23 = __byte_perm(noise_floor16(s[2], K), noise_floor16(s[3], K), 0x5410);
-    const uint32_t v01 = __byte_perm(word, 0u, 0x4140), v23 = __byte_perm(word, 0u, 0x4342);
-    const uint32_t q01 = __viaddmin_s16x2_relu(f01, v01, 0x00FF00FFu);
-    const uint32_t q23 = __viaddmin_s16x2_relu(f23, v23, 0x00FF00FFu);
-    return __byte_perm(q01, q23, 0x6420);
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
     const float K = p.sigma * ROD_NOISE_K_PER_SIGMA;

@@ -171,6 +171,9 @@ int ensure_letterbox_tables(rod_plan* plan, int out_h, int out_w) {
     rc = upload(tiles, &plan->d_lb_tiles);
     if (rc != ROD_OK) return rc;
     plan->n_lb_tiles = (int)tiles.size();
+    plan->lb_all_linear = true;
+    for (const DevLetterbox& g : lbs)
+        if (g.identity || g.area2) plan->lb_all_linear = false;
     plan->lb_out_h = out_h;
     plan->lb_out_w = out_w;
     return ROD_OK;

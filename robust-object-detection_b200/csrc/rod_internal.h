@@ -83,6 +83,7 @@ struct rod_plan {
     int lb_out_h = 0, lb_out_w = 0;
     rod::DevLetterbox* d_lb = nullptr;
     uint32_t* d_lb_tab = nullptr;
+    bool lb_all_linear = false;  // every shape is a plain INTER_LINEAR letterbox (fused kernel eligible)
     rod::Tile* d_lb_tiles = nullptr;
     int n_lb_tiles = 0;
     uint8_t* d_scratch = nullptr;  // corrupted full-res images for the letterbox path
@@ -139,6 +140,9 @@ int launch_gather_patches(const rod_plan* plan, const rod_plan* inner, const uin
                           const uint8_t* flips, cudaStream_t stream);
 int launch_format_pairs(const rod_plan* inner, const uint8_t* clean, const uint8_t* corrupted, float* clean_out,
                         float* corrupted_out, cudaStream_t stream);
+int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8_t* scratch, const uint8_t* opcodes,
+                           const float* noise, void* out_f16, int pad_value, float sigma, int k, uint64_t seed,
+                           uint64_t first_image, uint32_t offset, cudaStream_t stream);
 int launch_letterbox(const rod_plan* plan, const uint8_t* img, const uint8_t* src, const uint8_t* opcodes, void* out_f16,
                      int pad_value, cudaStream_t stream);
 
