@@ -140,8 +140,8 @@ struct FusedLbParams {
     uint32_t key0, key1, offset;
     uint64_t first_image;
     int k;                   // blur taps (odd)
-    int buf_bytes;           // bytes of one row buffer (16-byte multiple, >= 3 * max_w + 32)
-    int raw_bytes;           // bytes of the raw (blur staging) buffer
+    int buf_bytes;           // bytes of one row buffer (16-byte multiple)
+    int xtab_bytes;          // bytes of the per-CTA x table (16-byte multiple)
 };
 
 constexpr int kFusedLeft = 64;  // bytes in front of pixel 0 in every row buffer (halo of up to 15 pixels + window)
@@ -177,6 +177,7 @@ __device__ __forceinline__ void fused_noise_row(const FusedLbParams& p, const De
     const uint64_t ig = p.first_image + (uint64_t)img_index;
     const uint32_t g_first = e0 >> 3, g_last = (e0 + (uint32_t)n - 1u) >> 3;
     const bool words = ((e0 | (uint32_t)n) & 7u) == 0;  // the row is made of whole Philox groups (row buffers are 16-byte aligned)
+#pragma unroll 2
     for (uint32_t g = g_first + lane; g <= g_last; g += 32) {
         uint32_t r[4];
         float sf[8];
@@ -241,8 +242,12 @@ __global__ void __launch_bounds__(256) fused_letterbox_kernel(FusedLbParams p) {
     lut[threadIdx.x] = __float2half_rn(__fdiv_rn((float)threadIdx.x, 255.0f));
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-CTA copy of the x tables of the current shape: {3 * s0 (byte offset of the left tap), a0 | a1 << 16, right-border
+    // flag} per output column, read through the short scoreboard
+    uint2* xtab = reinterpret_cast<uint2*>(smem + 512);
+    int cached_shape = -1;
     // three identical row buffers per warp: [kFusedLeft | row | 64]
-    uint8_t* X0 = smem + 512 + (size_t)warp * (3 * p.buf_bytes) + kFusedLeft;
+    uint8_t* X0 = smem + 512 + (size_t)p.xtab_bytes + (size_t)warp * (3 * p.buf_bytes) + kFusedLeft;
     uint8_t* X1 = X0 + p.buf_bytes;
     uint8_t* X2 = X1 + p.buf_bytes;
     const size_t plane = (size_t)p.out_h * p.out_w;
@@ -251,9 +256,24 @@ __global__ void __launch_bounds__(256) fused_letterbox_kernel(FusedLbParams p) {
     for (int ti = blockIdx.x; ti < p.n_images * groups; ti += gridDim.x) {
         const int img = ti / groups;
         const int Y = (ti - img * groups) * 8 + warp;
-        if (Y >= p.out_h) continue;
         const DevImage im = p.images[img];
         const DevLetterbox g = p.lb[im.shape_id];
+        if (im.shape_id != cached_shape) {  // CTA-uniform: every warp walks the same tile sequence
+            __syncthreads();
+            const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + g.lx_s0);
+            for (int X = threadIdx.x; X < p.out_w; X += 256) {
+                const int cx = X - g.left;
+                uint2 e = make_uint2(0xFFFFFFFFu, 0u);  // padding column
+                if (cx >= 0 && cx < g.new_w) {
+                    const int s0 = lx_s0[cx];
+                    e = make_uint2((uint32_t)(3 * s0) | ((s0 + 1 > g.w - 1) ? 0x80000000u : 0u), p.tab[g.lx_a + cx]);
+                }
+                xtab[X] = e;
+            }
+            cached_shape = im.shape_id;
+            __syncthreads();
+        }
+        if (Y >= p.out_h) continue;
         __half* orow = p.out + (size_t)img * 3 * plane + (size_t)Y * p.out_w;
         const int cy = Y - g.top;
         if (cy < 0 || cy >= g.new_h) {
@@ -285,17 +305,17 @@ __global__ void __launch_bounds__(256) fused_letterbox_kernel(FusedLbParams p) {
         const uint8_t* bufA = X0;
         const uint8_t* rowB = two ? X1 : X0;
         __syncwarp();
-        const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + g.lx_s0);
+#pragma unroll 2
         for (int X = lane; X < p.out_w; X += 32) {
-            const int cx = X - g.left;
+            const uint2 xe = xtab[X];
             __half h0 = padh, h1 = padh, h2 = padh;
-            if (cx >= 0 && cx < g.new_w) {
-                const int s0 = lx_s0[cx];
-                const uint32_t a = p.tab[g.lx_a + cx];
+            if (xe.x != 0xFFFFFFFFu) {
+                const int o3 = (int)(xe.x & 0x7FFFFFFFu);
+                const uint32_t a = xe.y;
                 uint32_t lo0, hi0, lo1, hi1;
-                load6_smem(bufA, 3 * s0, lo0, hi0);
-                load6_smem(rowB, 3 * s0, lo1, hi1);
-                if (s0 + 1 > g.w - 1) {  // right border: both taps are the last pixel
+                load6_smem(bufA, o3, lo0, hi0);
+                load6_smem(rowB, o3, lo1, hi1);
+                if (xe.x & 0x80000000u) {  // right border: both taps are the last pixel
                     hi0 = __byte_perm(lo0, 0u, 0x4421); lo0 = __byte_perm(lo0, 0u, 0x0210);
                     hi1 = __byte_perm(lo1, 0u, 0x4421); lo1 = __byte_perm(lo1, 0u, 0x0210);
                 }
@@ -324,8 +344,8 @@ int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8
     p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32); p.offset = offset; p.first_image = first_image;
     p.k = k;
     p.buf_bytes = kFusedLeft + ((3 * plan->max_w + 15) & ~15) + 64;
-    p.raw_bytes = 0;
-    const size_t smem = 512 + 8 * (size_t)(3 * p.buf_bytes);
+    p.xtab_bytes = (p.out_w * 8 + 15) & ~15;
+    const size_t smem = 512 + (size_t)p.xtab_bytes + 8 * (size_t)(3 * p.buf_bytes);
     if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
     ROD_CUDA(cudaFuncSetAttribute(fused_letterbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((227 * 1024) / (smem + 1024));
