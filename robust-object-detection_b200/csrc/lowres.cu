@@ -569,7 +569,8 @@ struct X2wWarpTables {
     uint32_t ys[kX2wMaxBandRows]; // s0 | s1 << 16 per output row
 };
 
-template <bool AL8>  // 128 registers, 4 CTAs per SM; 96 registers / 5 CTAs spills and is 35 % slower (measured)
+template <bool AL8>  // 128 registers, 4 CTAs per SM.  Measured alternatives: 96 registers / 5 CTAs (spills) -35 %;
+                     // a 4-pixel-chunk variant with 80 registers / 6 CTAs -14 %: the kernel is issue-bound, not latency-bound
 __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -646,156 +647,6 @@ __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
     }
 }
 
-// =====================================================================================
-// 4-pixel-chunk variant of the warp-marching kernel: a lane holds 4 output pixels (12 bytes) = 2 low-res pixels =
-// 4 source pixels per tap row, so its state is half as large (~70 registers instead of 128) and seven CTAs of four
-// warps are resident per SM instead of four.  Same band x strip decomposition (30 chunks per strip, halo lanes 0 and
-// 31), same arithmetic.  w % 4 == 0 makes every chunk whole: no partial-chunk cases.
-// =====================================================================================
-__device__ __forceinline__ void x2v_expand(bool first_chunk, bool last_chunk, uint32_t o0, uint32_t o1, float x[12]) {
-    // own low-res bytes: o0 = bytes 0..3, o1 = bytes 4..5 (upper half unused)
-    const uint32_t last_px = __funnelshift_r(o0, o1, 24) & 0x00FFFFFFu;   // bytes 3..5
-    const uint32_t from_left = __shfl_up_sync(0xFFFFFFFFu, last_px, 1);
-    const uint32_t from_right = __shfl_down_sync(0xFFFFFFFFu, o0, 1) & 0x00FFFFFFu;
-    const uint32_t left = first_chunk ? (o0 & 0x00FFFFFFu) : from_left;     // P[-1] := P[0]
-    const uint32_t right = last_chunk ? last_px : from_right;              // P[nw] := P[nw-1]
-    // 12-byte window [left | own 6 bytes | right]
-    const uint32_t win[4] = {left | (o0 << 24), (o0 >> 8) | (o1 << 24), ((o1 >> 8) & 0xFFu) | (right << 8), 0u};
-    const uint32_t W31 = 6u | (2u << 16), W13 = 2u | (6u << 16), M = 0x4A800000u;
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {
-        const uint32_t g01 = x2_gather(win, 3 * m);
-        const uint32_t g2x = x2_gather(win, 3 * m + 2);
-        const int podd = 2 * m - 1, peven = 2 * m;
-        if (podd >= 0) {
-            x[3 * podd + 0] = bitsf(dot2_lo(W31, g01, M));
-            x[3 * podd + 1] = bitsf(dot2_hi(W31, g01, M));
-            x[3 * podd + 2] = bitsf(dot2_lo(W31, g2x, M));
-        }
-        if (peven < 4) {
-            x[3 * peven + 0] = bitsf(dot2_lo(W13, g01, M));
-            x[3 * peven + 1] = bitsf(dot2_hi(W13, g01, M));
-            x[3 * peven + 2] = bitsf(dot2_lo(W13, g2x, M));
-        }
-    }
-}
-
-__device__ __forceinline__ void x2v_emit(const float* xlo, const float* xhi, const X2Row& rc, uint8_t* dptr, bool store,
-                                         bool al4) {
-    uint32_t o[12];
-#pragma unroll
-    for (int t = 0; t < 12; ++t) o[t] = x2_vertical(xlo[t], xhi[t], rc);
-    uint32_t wds[3];
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-        const uint32_t lo = __byte_perm(o[4 * g], o[4 * g + 1], 0x0040);
-        const uint32_t hi = __byte_perm(o[4 * g + 2], o[4 * g + 3], 0x0040);
-        wds[g] = __byte_perm(lo, hi, 0x5410);
-    }
-    if (!store) return;
-    if (al4) {
-#pragma unroll
-        for (int g = 0; g < 3; ++g)
-            asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(dptr + 4 * g), "r"(wds[g]) : "memory");
-    } else {
-        for (int b = 0; b < 12; ++b) dptr[b] = (uint8_t)(wds[b >> 2] >> (8 * (b & 3)));
-    }
-}
-
-__global__ void __launch_bounds__(128, 6) lowres_x2v_kernel(LowresX2wParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    X2wWarpTables& tb = reinterpret_cast<X2wWarpTables*>(smem)[warp];
-    for (int ti = blockIdx.x * wpb + warp; ti < p.n_tiles; ti += gridDim.x * wpb) {
-        const Tile t = p.tiles[ti];
-        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
-        const DevImage im = p.images[t.img];
-        const DevShape sh = p.shapes[im.shape_id];
-        const uint8_t* simg = p.src + im.src_off;
-        uint8_t* dimg = p.dst + im.dst_off;
-        const int nchunks = im.w >> 2;
-        const int ch = kX2wChunksPerStrip * t.c - 1 + lane;
-        const bool cvalid = ch >= 0 && ch < nchunks;
-        const int cc = min(max(ch, 0), nchunks - 1);
-        const bool store = cvalid && lane >= 1 && lane <= kX2wChunksPerStrip;
-        const bool first_chunk = (cc == 0), last_chunk = (cc == nchunks - 1);
-        const bool fast2 = (sh.area_mode == AREA_FAST2);
-        const bool al4 = ((((uintptr_t)dimg) | (uintptr_t)im.dst_pitch) & 3) == 0;
-        const uint32_t* ly_s = p.tab + sh.ly_s;
-        const float4* ly_rc = reinterpret_cast<const float4*>(p.tab + sh.ly_rc);
-        const int Y0 = t.a, Y1 = t.b;
-        const int j_first = (int)(ly_s[Y0] & 0xFFFFu), j_last = (int)(ly_s[Y1 - 1] >> 16);
-        const uint8_t* scol = simg + 12 * cc;
-        const int64_t pitch = im.src_pitch;
-
-        __syncwarp();  // the previous band's tables are dead
-        for (int i = lane; i < Y1 - Y0; i += 32) {
-            tb.ys[i] = ly_s[Y0 + i];
-            tb.rc[i] = ly_rc[Y0 + i];
-        }
-        if (!fast2) {
-            const uint4* ypack = reinterpret_cast<const uint4*>(p.tab + sh.ay_pack);
-            for (int i = lane; i <= j_last - j_first; i += 32) tb.pk[i] = ypack[j_first + i];
-        }
-        __syncwarp();
-
-        uint32_t rw[3][3];
-        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-        auto prefetch = [&](int j) {
-            int sy0 = 2 * j;
-            if (!fast2) {
-                pk = tb.pk[j - j_first];
-                sy0 = (int)pk.x;
-            }
-            const uint8_t* r0 = scol + (int64_t)sy0 * pitch;
-            const uint8_t* r1 = r0 + pitch;
-            const uint8_t* r2 = scol + (int64_t)min(sy0 + 2, im.h - 1) * pitch;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                rw[0][q] = ldg_stream4(r0 + 4 * q);
-                rw[1][q] = ldg_stream4(r1 + 4 * q);
-                if (!fast2) rw[2][q] = ldg_stream4(r2 + 4 * q);
-            }
-        };
-        float xe[12], xo[12];
-        int have = j_first - 1;
-        prefetch(j_first);
-        uint8_t* dptr = dimg + (int64_t)Y0 * im.dst_pitch + 12 * cc;
-        for (int r = Y0; r < Y1; ++r, dptr += im.dst_pitch) {
-            const uint32_t ys = tb.ys[r - Y0];
-            const float4 rf = tb.rc[r - Y0];
-            const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
-            X2Row rc;
-            rc.c0s = rf.x; rc.c1s = rf.y; rc.k0 = rf.z; rc.k2 = rf.w;
-            while (have < s1) {
-                ++have;
-                uint32_t o6[6];
-                if (fast2) {
-                    area_fast2_unit(rw[0], rw[1], o6);
-                } else {
-                    float acc[6];
-                    area_x2f_accumulate(rw[0], __uint_as_float(pk.y), true, acc);
-                    area_x2f_accumulate(rw[1], __uint_as_float(pk.z), false, acc);
-                    area_x2f_accumulate(rw[2], __uint_as_float(pk.w), false, acc);
-                    area_x2f_finish(acc, o6);
-                }
-                const uint32_t a01 = __byte_perm(o6[0], o6[1], 0x0040), a23 = __byte_perm(o6[2], o6[3], 0x0040);
-                const uint32_t o0 = __byte_perm(a01, a23, 0x5410), o1 = __byte_perm(o6[4], o6[5], 0x0040) & 0xFFFFu;
-                if (have < j_last) prefetch(have + 1);
-                if (have & 1) x2v_expand(first_chunk, last_chunk, o0, o1, xo);
-                else x2v_expand(first_chunk, last_chunk, o0, o1, xe);
-            }
-            if (s0 & 1) {
-                if (s1 & 1) x2v_emit(xo, xo, rc, dptr, store, al4);
-                else x2v_emit(xo, xe, rc, dptr, store, al4);
-            } else {
-                if (s1 & 1) x2v_emit(xe, xo, rc, dptr, store, al4);
-                else x2v_emit(xe, xe, rc, dptr, store, al4);
-            }
-        }
-    }
-}
-
 int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
                   cudaStream_t stream, int img_lo, int img_hi) {
     // generic tiles (shapes that are not exact-2x in x)
@@ -844,8 +695,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             int per_sm = 4;  // benchmark knob: ROD_X2W_CTAS
             const char* e_ctas = getenv("ROD_X2W_CTAS");
             if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
-            if (plan->x2v) lowres_x2v_kernel<<<grid_for(plan, ctas, 6), 128, smem, stream>>>(p);
-            else if (pass == 0 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, per_sm), 128, smem, stream>>>(p);
+            if (pass == 0 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, per_sm), 128, smem, stream>>>(p);
             else lowres_x2w_kernel<false><<<grid_for(plan, ctas, per_sm), 128, smem, stream>>>(p);
             ROD_CUDA(cudaGetLastError());
         }

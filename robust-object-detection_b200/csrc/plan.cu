@@ -73,10 +73,7 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         const DevImage& im = plan->h_images[i];
         return (im.src_pitch & 7) == 0 && (im.src_off & 7) == 0 && (im.w & 7) == 0;
     };
-    const char* e_x2v = getenv("ROD_X2V");
-    plan->x2v = (e_x2v && atoi(e_x2v) == 1);
-    const bool x2v = plan->x2v;
-    auto n_strips = [&](int w) { return x2v ? (w / 4 + 29) / 30 : ((w + 7) / 8 + 29) / 30; };
+    auto n_strips = [&](int w) { return ((w + 7) / 8 + 29) / 30; };
     int band_rows = 0;
     if (march) {
         long long strip_rows = 0;

@@ -69,7 +69,6 @@ struct rod_plan {
     int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
     std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
     int lowres_x2w_band_rows = 0;
-    bool x2v = false;  // 4-pixel-chunk variant of the marching kernel (ROD_X2V=1)
     bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
 
     // lowres tables, rebuilt when the factor changes
