@@ -163,9 +163,41 @@ def make_angles():
     print("wrote", len(arrs), "angle arrays and", len(hashes), "hashes")
 
 
+def make_restoration():
+    """(corrupted, clean) pairs of the unmodified RestorationDataset.__getitem__
+    (scripts/train_restoration.py:104-129) on synthetic JPEG-free inputs: cv2.imread is replaced by a stub that
+    returns the synthetic frame, everything else (crop, flip, corruption choice, formatting) is the reference's."""
+    sys.path.insert(0, REF_ROOT)
+    import cv2
+    from pathlib import Path
+    from scripts import train_restoration as tr
+    shapes = [(120, 200), (97, 133), (64, 64), (300, 180), (81, 90), (200, 201)]
+    frames = {f"img{i}.jpg": synth(5000 + i, h, w) for i, (h, w) in enumerate(shapes)}
+    real_imread = cv2.imread
+    cv2.imread = lambda path, *a: frames[Path(path).name].copy()
+    try:
+        out = {}
+        for is_train in (True, False):
+            ds = tr.RestorationDataset(Path("/nonexistent"), patch_size=64, is_train=is_train)
+            ds.img_paths = [Path(n) for n in frames]
+            random.seed(2)
+            np.random.seed(21)
+            for i in range(len(frames)):
+                cor, clean = ds[i]
+                out[f"{'train' if is_train else 'val'}_cor_{i}"] = cor.numpy()
+                out[f"{'train' if is_train else 'val'}_clean_{i}"] = clean.numpy()
+    finally:
+        cv2.imread = real_imread
+    np.savez_compressed(os.path.join(HERE, "golden_restoration.npz"), **out)
+    print("wrote", len(out), "restoration arrays")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "angles":
+    if len(sys.argv) > 1 and sys.argv[1] == "restoration":
+        make_restoration()
+    elif len(sys.argv) > 1 and sys.argv[1] == "angles":
         make_angles()
     else:
         main()
         make_angles()
+        make_restoration()

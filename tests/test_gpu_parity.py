@@ -497,3 +497,27 @@ def test_training_batcher_pinned_pipeline(torch_):
     b2 = CorruptionBatcher(out_hw=(160, 160), seed=9)
     got2 = np.concatenate([x.cpu().numpy() for x in b2.run([frames[0:6], frames[6:12]])])
     assert np.array_equal(got, got2)
+
+
+@pytest.mark.parametrize("is_train", [True, False])
+def test_restoration_pairs_vs_reference_dataset_gpu(torch_, is_train):
+    """The fused device path against pairs produced by the unmodified RestorationDataset (golden_restoration.npz)."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    from tests.test_oracle_golden import RESTORATION_SHAPES, restoration_inputs
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_restoration.npz"))
+    frames, dec, fields = restoration_inputs(is_train)
+    base = CorruptionPlan.ragged(RESTORATION_SHAPES)
+    src = torch_.from_numpy(base.pack(frames)).cuda()
+    offs = [base.src_offsets[i] + y * 3 * RESTORATION_SHAPES[i][1] + 3 * x for i, (y, x, _, _) in enumerate(dec)]
+    n = len(frames)
+    plan = CorruptionPlan([(64, 64)] * n, offs, [0] * n, src_pitches=[3 * w for _, w in RESTORATION_SHAPES])
+    flips = torch_.tensor([int(f) for _, _, f, _ in dec], dtype=torch_.uint8, device="cuda")
+    ops = torch_.tensor([o for _, _, _, o in dec], dtype=torch_.uint8, device="cuda")
+    nz = torch_.from_numpy(np.stack(fields).reshape(-1)).cuda()
+    cor = torch_.zeros((n, 3, 64, 64), dtype=torch_.float32, device="cuda")
+    clean = torch_.zeros_like(cor)
+    plan.restoration_pairs(src, flips, ops, cor, clean, noise=nz)
+    tag = "train" if is_train else "val"
+    for i in range(n):
+        assert np.array_equal(clean[i].cpu().numpy(), g[f"{tag}_clean_{i}"]), i
+        assert np.array_equal(cor[i].cpu().numpy(), g[f"{tag}_cor_{i}"]), (i, dec[i])

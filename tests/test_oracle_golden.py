@@ -98,3 +98,36 @@ def test_general_angle_filter2d_vs_reference():
         for name, seed, h, w in meta["big"]:
             if (k, ang) in ((9, 45), (11, 45), (9, 179.5)) or name.startswith("tail2"):
                 assert sha(orc.filter2d(synth(seed, h, w), kern)) == meta["sha"][f"{k}_{ang}_{name}"], (k, ang, name)
+
+
+RESTORATION_SHAPES = [(120, 200), (97, 133), (64, 64), (300, 180), (81, 90), (200, 201)]
+
+
+def restoration_inputs(is_train):
+    """Decisions and noise fields of six RestorationDataset.__getitem__ calls, consuming `random` / `np.random` in the
+    reference's order (train_restoration.py:79-121, augmentations.py:31): returns (frames, decisions, fields)."""
+    from robust_object_detection_b200.batch import draw_restoration_decisions
+    frames = [synth(5000 + i, h, w) for i, (h, w) in enumerate(RESTORATION_SHAPES)]
+    random.seed(2)
+    np.random.seed(21)
+    dec, fields = [], []
+    for (h, w) in RESTORATION_SHAPES:
+        d = draw_restoration_decisions(h, w, 64, is_train=is_train)
+        dec.append(d)
+        fields.append(orc.draw_noise_field((64, 64, 3), 15) if d[3] == orc.OP_NOISE else np.zeros((64, 64, 3), np.float32))
+    return frames, dec, fields
+
+
+@pytest.mark.parametrize("is_train", [True, False])
+def test_restoration_pairs_vs_reference_dataset(is_train):
+    """crop / flip / choice order + the three corruptions + RGB f32 CHW / 255, against pairs produced
+    by the unmodified RestorationDataset (tests/golden/golden_restoration.npz)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_restoration.npz"))
+    frames, dec, fields = restoration_inputs(is_train)
+    tag = "train" if is_train else "val"
+    for i, (img, (y, x, flip, op)) in enumerate(zip(frames, dec)):
+        patch = img[y:y + 64, x:x + 64]
+        patch = np.ascontiguousarray(patch[:, ::-1] if flip else patch)
+        cor = orc.add_noise_field(patch, fields[i]) if op == orc.OP_NOISE else orc.apply_op(patch, op)
+        assert np.array_equal((patch[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1), g[f"{tag}_clean_{i}"]), i
+        assert np.array_equal((cor[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1), g[f"{tag}_cor_{i}"]), (i, op)
