@@ -465,16 +465,6 @@ __device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
-__device__ __forceinline__ uint32_t ldg_pinned4(const void* p) {
-    uint32_t r;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float4 ldg_pinned16f(const void* p) {
-    float4 r;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ void ldg_stream8(const void* p, uint32_t& a, uint32_t& b) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
 }
@@ -485,7 +475,7 @@ struct X2wCtx {
     const uint4* ypack;      // this warp's shared copy of the packed y table, entry 0 = low-res row j_first
     int j_first;
     int h;
-    bool fast2, al8, second_unit;  // second_unit: the chunk has four low-res pixels (else two: last chunk, w % 8 == 4)
+    bool fast2, second_unit;  // second_unit: the chunk has four low-res pixels (else two: last chunk, w % 8 == 4)
     bool first_chunk, last_chunk;
 };
 
@@ -598,7 +588,6 @@ __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
         c.j_first = j_first;
         c.h = im.h;
         c.fast2 = (sh.area_mode == AREA_FAST2);
-        c.al8 = AL8;
         c.second_unit = (nw - 4 * cc) >= 4;
         c.first_chunk = (cc == 0);
         c.last_chunk = (cc == nchunks - 1);

@@ -120,3 +120,27 @@ def test_two_rank_gloo_sharding(tmp_path):
     assert [r["rank"] for r in recs] == [0, 1]
     assert recs[0]["lo"] == 0 and recs[0]["hi"] == recs[1]["lo"] and recs[1]["hi"] == 1610
     assert max(r["ms"] for r in recs) == 2.0
+
+
+def test_trainer_patch_contract_with_stub():
+    """training.patch_ultralytics_trainer: batches without raw frames fall through to the trainer's own preprocess;
+    batches with raw frames are routed to the batcher (stubbed here: no GPU in this test)."""
+    from robust_object_detection_b200 import training
+
+    class Trainer:
+        amp = True
+
+        def preprocess_batch(self, batch):
+            batch["seen_by_original"] = True
+            return batch
+
+    class FakeBatcher:
+        def __call__(self, frames):
+            return ("device-tensor-for", len(frames))
+
+    t = Trainer()
+    got = training.patch_ultralytics_trainer(t, batcher=FakeBatcher())
+    assert isinstance(got, FakeBatcher)
+    assert t.preprocess_batch({"img": 1})["seen_by_original"] is True
+    out = t.preprocess_batch({"raw": [np.zeros((4, 4, 3), np.uint8)] * 3})
+    assert out["img"] == ("device-tensor-for", 3) and "seen_by_original" not in out
