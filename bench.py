@@ -171,6 +171,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_cpus(gpu_index):
+    """Pin this process to the CPUs NVML reports as local to its GPU (same NUMA node / PCIe root), so that the pinned
+    staging buffers of the e2e leg are allocated next to the GPU.  Best effort: returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = cpus & allowed
+        if pick and pick != allowed:
+            os.sched_setaffinity(0, pick)
+            return f"{len(pick)} of {len(allowed)} allowed CPUs (GPU-local)"
+        return f"unchanged ({len(allowed)} allowed CPUs, {len(cpus)} GPU-local)"
+    except Exception as e:  # NVML missing, cpuset restrictions, ...
+        return f"unavailable ({type(e).__name__})"
+
+
 def time_device(fn, steps, warmup, torch, dist=None):
     """W untimed + K timed calls of fn() bracketed by barrier + synchronize; CUDA events on the
     current stream; returns this rank's elapsed ms."""
@@ -220,6 +239,7 @@ def main():
     from robust_object_detection_b200.sharding import gather_records, shard_range
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else "not applied (single GPU)"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -287,6 +307,7 @@ def main():
         "gpu_launches": args.steps * plan.launches(N.OP_BLUR),
         "clocks": clocks,
         "per_rank_ms": [r["ms"] for r in rec],
+        "cpu_binding": numa,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
