@@ -412,6 +412,55 @@ def test_letterbox_fused_training_path(torch_):
         assert np.array_equal(got[i], want), (i, shapes[i])
 
 
+def test_fused_letterbox_kernel_paths(torch_):
+    """fused_letterbox_kernel (every shape a plain linear letterbox): 16-byte-aligned rows (cp.async staging), odd widths
+    (32-bit / byte staging, Philox groups straddling rows), supplied noise field, another blur size, and a pitched
+    source; all against the oracle, bit-exact except Philox noise (statistical mode)."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    shapes = [(765, 1360), (765, 1360), (540, 960), (333, 517), (401, 1001), (1079, 1917), (360, 480), (765, 1360)]
+    ops_host = np.array([1, 2, 3, 2, 1, 0, 1, 0], dtype=np.uint8)
+    imgs = [synth(5100 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    plan = CorruptionPlan.ragged(shapes)
+    src = torch_.from_numpy(plan.pack(imgs)).cuda()
+    ops = torch_.from_numpy(ops_host).cuda()
+    out = torch_.empty((len(shapes), 3, 320, 320), dtype=torch_.float16, device="cuda")
+    # (a) compat noise (supplied field), k = 9
+    np.random.seed(33)
+    fields = [orc.draw_noise_field(im.shape, 15) for im in imgs]
+    nz = torch_.from_numpy(np.concatenate([f.reshape(-1) for f in fields])).cuda()
+    plan.corrupt_letterbox(src, ops, out, 320, 320, 114, noise=nz)
+    got = out.cpu().numpy()
+    for i, img in enumerate(imgs):
+        op = int(ops_host[i])
+        cor = orc.add_noise_field(img, fields[i]) if op == 1 else orc.apply_op(img, op)
+        assert np.array_equal(got[i], orc.letterbox_norm_f16(cor, 320, 320, 114)), (i, shapes[i], op)
+    # (b) Philox noise keyed by a global index offset, blur k = 5
+    plan.corrupt_letterbox(src, ops, out, 320, 320, 114, k=5, seed=77, first_image_index=1000)
+    got = out.cpu().numpy()
+    for i, img in enumerate(imgs):
+        op = int(ops_host[i])
+        if op == 1:
+            want = orc.letterbox_norm_f16(orc.add_philox_noise(img, orc.philox_noise_field(img.size, 15.0, 77, 1000 + i)), 320, 320, 114)
+            assert np.mean(got[i] != want) < 2e-3, (i, shapes[i])
+        else:
+            cor = orc.apply_motion_blur(img, 5, 0) if op == 2 else orc.apply_op(img, op)
+            assert np.array_equal(got[i], orc.letterbox_norm_f16(cor, 320, 320, 114)), (i, shapes[i], op)
+    # (c) pitched source rows
+    sp = [3 * w + 12 for h, w in shapes]
+    so = np.concatenate([[0], np.cumsum([(h * q + 255) // 256 * 256 for (h, w), q in zip(shapes, sp)])])
+    planp = CorruptionPlan(shapes, so[:-1], plan.dst_offsets, src_pitches=sp)
+    hsrc = np.full(int(so[-1]), 0xAB, np.uint8)
+    for img, o, q in zip(imgs, so, sp):
+        h, w, _ = img.shape
+        hsrc[o:o + h * q].reshape(h, q)[:, :3 * w] = img.reshape(h, 3 * w)
+    ops2 = torch_.from_numpy(np.array([2, 0, 3, 2, 0, 2, 3, 0], dtype=np.uint8)).cuda()
+    planp.corrupt_letterbox(torch_.from_numpy(hsrc).cuda(), ops2, out, 320, 320, 114)
+    got = out.cpu().numpy()
+    for i, img in enumerate(imgs):
+        want = orc.letterbox_norm_f16(orc.apply_op(img, int(ops2[i].item())), 320, 320, 114)
+        assert np.array_equal(got[i], want), (i, shapes[i])
+
+
 def test_apply_host_chunked_pipeline(torch_):
     """Host-buffer entry point with enough payload for several H2D/kernel/D2H chunks."""
     from robust_object_detection_b200 import _native as N
