@@ -187,11 +187,18 @@ extern "C" int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, con
     const bool fused = plan->lb_all_linear && plan->f2d_ntaps == 0 && blur_supported(k, 0.0) && k >= 3 &&
                        (noise != nullptr || sigma <= kPhiloxMaxSigma) && !(e_fused && atoi(e_fused) == 0);
     if (fused) {
-        rc = run_op(plan, ROD_OP_LOWRES, src, plan->d_scratch, noise, sigma, k, factor, seed, first_image_index, offset,
-                    opcodes, (cudaStream_t)stream, 0, plan->n_images);
+        rc = ensure_lowres_tables(plan, factor);
         if (rc != ROD_OK) return rc;
+        // LowRes rows are produced inside the kernel as well when every shape is exact-2x (w % 4 == 0, 4-byte aligned
+        // rows); otherwise the resize kernels write the LowRes images to the scratch first
+        const bool in_kernel = plan->lowres_all_x2w && (((uintptr_t)src) & 3) == 0;
+        if (!in_kernel) {
+            rc = run_op(plan, ROD_OP_LOWRES, src, plan->d_scratch, noise, sigma, k, factor, seed, first_image_index, offset,
+                        opcodes, (cudaStream_t)stream, 0, plan->n_images);
+            if (rc != ROD_OK) return rc;
+        }
         rc = launch_fused_letterbox(plan, src, plan->d_scratch, opcodes, noise, out_f16, pad_value, sigma, k, seed,
-                                    first_image_index, offset, (cudaStream_t)stream);
+                                    first_image_index, offset, in_kernel, (cudaStream_t)stream);
         if (rc != ROD_ERR_UNSUPPORTED) return rc;  // rows too wide for the per-warp buffers: unfused path below
     }
     // images that stay clean are read from `src` by the letterbox kernel itself: no copy into the scratch

@@ -140,6 +140,9 @@ struct FusedLbParams {
     uint32_t key0, key1, offset;
     uint64_t first_image;
     int k;                   // blur taps (odd)
+    const DevShape* shapes;  // lowres tables (plan->d_shapes / d_tab), used when lowres_in_kernel
+    const uint32_t* ltab;
+    int lowres_in_kernel;    // 1: LowRes rows are produced in shared memory too (every LowRes-able shape is exact-2x)
     int buf_bytes;           // bytes of one row buffer (16-byte multiple)
     int xtab_bytes;          // bytes of the per-CTA x table (16-byte multiple)
 };
@@ -227,6 +230,90 @@ __device__ __forceinline__ void fused_blur_row(const FusedLbParams& p, const Dev
     }
 }
 
+// ---- LowRes rows in shared memory (exact-2x shapes, w % 4 == 0): same arithmetic as lowres.cu ----
+// low-res row j of the image -> prow (layout of the strip kernel: [1..3] = pixel 0 replicated, [4 + 3i + c], pixel nw-1 replicated)
+__device__ __forceinline__ void fused_lowres_prow(const DevImage& im, const DevShape& sh, const uint32_t* ltab,
+                                                  const uint8_t* simg, int j, uint8_t* prow, int lane) {
+    const int nw = sh.nw, n_units = nw >> 1;
+    const bool fast2 = (sh.area_mode == AREA_FAST2);
+    int sy0 = 2 * j;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    if (!fast2) {
+        const uint4 pk = reinterpret_cast<const uint4*>(ltab + sh.ay_pack)[j];
+        sy0 = (int)pk.x; b0 = __uint_as_float(pk.y); b1 = __uint_as_float(pk.z); b2 = __uint_as_float(pk.w);
+    }
+    const uint8_t* r0 = simg + (int64_t)sy0 * im.src_pitch;
+    const uint8_t* r1 = r0 + im.src_pitch;
+    const uint8_t* r2 = simg + (int64_t)min(sy0 + 2, im.h - 1) * im.src_pitch;
+    for (int u = lane; u < n_units; u += 32) {
+        const uint32_t* w0 = reinterpret_cast<const uint32_t*>(r0 + 12 * u);
+        const uint32_t* w1 = reinterpret_cast<const uint32_t*>(r1 + 12 * u);
+        const uint32_t ra[3] = {__ldg(w0), __ldg(w0 + 1), __ldg(w0 + 2)}, rb[3] = {__ldg(w1), __ldg(w1 + 1), __ldg(w1 + 2)};
+        uint32_t o6[6];
+        if (fast2) {
+            area_fast2_unit(ra, rb, o6);
+        } else {
+            const uint32_t* w2 = reinterpret_cast<const uint32_t*>(r2 + 12 * u);
+            const uint32_t rc[3] = {__ldg(w2), __ldg(w2 + 1), __ldg(w2 + 2)};
+            float acc[6];
+            area_x2f_accumulate(ra, b0, true, acc);
+            area_x2f_accumulate(rb, b1, false, acc);
+            area_x2f_accumulate(rc, b2, false, acc);
+            area_x2f_finish(acc, o6);
+        }
+        uint16_t* o16 = reinterpret_cast<uint16_t*>(prow + 4 + 6 * u);
+        o16[0] = (uint16_t)__byte_perm(o6[0], o6[1], 0x0040);
+        o16[1] = (uint16_t)__byte_perm(o6[2], o6[3], 0x0040);
+        o16[2] = (uint16_t)__byte_perm(o6[4], o6[5], 0x0040);
+        if (u == 0) { prow[1] = (uint8_t)o6[0]; prow[2] = (uint8_t)o6[1]; prow[3] = (uint8_t)o6[2]; }
+        if (u == n_units - 1) {
+            uint8_t* e = prow + 4 + 3 * nw;
+            e[0] = (uint8_t)o6[3]; e[1] = (uint8_t)o6[4]; e[2] = (uint8_t)o6[5];
+        }
+    }
+}
+
+// full-resolution row y of lowres(image) from the two resident low-res rows -> dst[0 .. 3w)
+__device__ __forceinline__ void fused_lowres_fullrow(const DevImage& im, const DevShape& sh, const uint32_t* ltab, int y,
+                                                     const uint8_t* pslots, int p_pitch, uint8_t* dst, int lane) {
+    const uint32_t ys = ltab[sh.ly_s + y];
+    const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+    const float4 rf = reinterpret_cast<const float4*>(ltab + sh.ly_rc)[y];
+    X2Row rc;
+    rc.c0s = rf.x; rc.c1s = rf.y; rc.k0 = rf.z; rc.k2 = rf.w;
+    const uint8_t* p0 = pslots + (s0 & 1) * p_pitch;
+    const uint8_t* p1 = pslots + (s1 & 1) * p_pitch;
+    const int n = 3 * im.w, nchunks = (im.w + 7) >> 3;
+    for (int ch = lane; ch < nchunks; ch += 32) {
+        float x0[24], x1[24];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(q ? p1 : p0) + 3 * ch;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5];
+            const uint32_t win[5] = {funnel_r(w0, w1, 8), funnel_r(w1, w2, 8), funnel_r(w2, w3, 8), funnel_r(w3, w4, 8),
+                                     funnel_r(w4, w5, 8)};
+            x2_expand24(win, q ? x1 : x0);
+        }
+        uint32_t o[24];
+#pragma unroll
+        for (int t = 0; t < 24; ++t) o[t] = x2_vertical(x0[t], x1[t], rc);
+        uint32_t wds[6];
+#pragma unroll
+        for (int g = 0; g < 6; ++g) {
+            const uint32_t lo = __byte_perm(o[4 * g], o[4 * g + 1], 0x0040);
+            const uint32_t hi = __byte_perm(o[4 * g + 2], o[4 * g + 3], 0x0040);
+            wds[g] = __byte_perm(lo, hi, 0x5410);
+        }
+        const int nvalid = min(24, n - 24 * ch);
+        uint2* d8 = reinterpret_cast<uint2*>(dst + 24 * ch);
+        if (nvalid == 24) {
+            d8[0] = make_uint2(wds[0], wds[1]); d8[1] = make_uint2(wds[2], wds[3]); d8[2] = make_uint2(wds[4], wds[5]);
+        } else {
+            for (int b = 0; b < nvalid; ++b) dst[24 * ch + b] = (uint8_t)(wds[b >> 2] >> (8 * (b & 3)));
+        }
+    }
+}
+
 // six consecutive bytes of a shared-memory row buffer starting at byte offset `o` (buffers are padded: no bound check)
 __device__ __forceinline__ void load6_smem(const uint8_t* buf, int o, uint32_t& lo, uint32_t& hi) {
     const uint32_t* a = reinterpret_cast<const uint32_t*>(buf + (o & ~3));
@@ -236,7 +323,7 @@ __device__ __forceinline__ void load6_smem(const uint8_t* buf, int o, uint32_t& 
     hi = __funnelshift_r(w1, w2, sh);
 }
 
-__global__ void __launch_bounds__(256) fused_letterbox_kernel(FusedLbParams p) {
+__global__ void __launch_bounds__(256, 2) fused_letterbox_kernel(FusedLbParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __half* lut = reinterpret_cast<__half*>(smem);  // 256 x half(v / 255)
     lut[threadIdx.x] = __float2half_rn(__fdiv_rn((float)threadIdx.x, 255.0f));
@@ -281,7 +368,8 @@ __global__ void __launch_bounds__(256) fused_letterbox_kernel(FusedLbParams p) {
             continue;
         }
         const int op = p.opcodes[img];
-        const bool pre = (op == ROD_OP_LOWRES);
+        const bool lowres_here = (op == ROD_OP_LOWRES) && p.lowres_in_kernel != 0 && p.shapes[im.shape_id].lin_identity == 0;
+        const bool pre = (op == ROD_OP_LOWRES) && p.lowres_in_kernel == 0;
         const uint8_t* base = pre ? p.scratch + im.dst_off : p.src + im.src_off;
         const int64_t pitch = pre ? im.dst_pitch : im.src_pitch;
         const uint32_t ys = p.tab[g.ly_s + cy], yb = p.tab[g.ly_b + cy];
@@ -289,6 +377,26 @@ __global__ void __launch_bounds__(256) fused_letterbox_kernel(FusedLbParams p) {
         const int n = 3 * im.w;
         const bool two = (r1 != r0);
         const bool blur = (op == ROD_OP_BLUR);
+        if (lowres_here) {
+            // rows r0, r1 of lowres(image): the (at most three) low-res rows they blend live two at a time in X2
+            const DevShape sh = p.shapes[im.shape_id];
+            const int p_pitch = (3 * sh.nw + 24 + 15) & ~15;
+            const uint32_t ya = p.ltab[sh.ly_s + r0];
+            const int a0 = (int)(ya & 0xFFFFu), a1 = (int)(ya >> 16);
+            fused_lowres_prow(im, sh, p.ltab, base, a0, X2 + (a0 & 1) * p_pitch, lane);
+            if (a1 != a0) fused_lowres_prow(im, sh, p.ltab, base, a1, X2 + (a1 & 1) * p_pitch, lane);
+            __syncwarp();
+            fused_lowres_fullrow(im, sh, p.ltab, r0, X2, p_pitch, X0, lane);
+            __syncwarp();
+            if (two) {
+                const uint32_t yb2 = p.ltab[sh.ly_s + r1];
+                const int b0 = (int)(yb2 & 0xFFFFu), b1 = (int)(yb2 >> 16);
+                if (b0 != a0 && b0 != a1) fused_lowres_prow(im, sh, p.ltab, base, b0, X2 + (b0 & 1) * p_pitch, lane);
+                if (b1 != a0 && b1 != a1 && b1 != b0) fused_lowres_prow(im, sh, p.ltab, base, b1, X2 + (b1 & 1) * p_pitch, lane);
+                __syncwarp();
+                fused_lowres_fullrow(im, sh, p.ltab, r1, X2, p_pitch, X1, lane);
+            }
+        } else {
         // both source rows are requested before anything waits (blur filters out of place: X1 -> X0, X2 -> X1)
         fused_stage_row(base + (int64_t)r0 * pitch, n, blur ? X1 : X0, lane);
         if (two) fused_stage_row(base + (int64_t)r1 * pitch, n, blur ? X2 : X1, lane);
@@ -301,6 +409,7 @@ __global__ void __launch_bounds__(256) fused_letterbox_kernel(FusedLbParams p) {
             fused_blur_row(p, im, X1, X0, lane);
             __syncwarp();
             if (two) fused_blur_row(p, im, X2, X1, lane);
+        }
         }
         const uint8_t* bufA = X0;
         const uint8_t* rowB = two ? X1 : X0;
@@ -334,8 +443,9 @@ __global__ void __launch_bounds__(256) fused_letterbox_kernel(FusedLbParams p) {
 
 int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8_t* scratch, const uint8_t* opcodes,
                            const float* noise, void* out_f16, int pad_value, float sigma, int k, uint64_t seed,
-                           uint64_t first_image, uint32_t offset, cudaStream_t stream) {
+                           uint64_t first_image, uint32_t offset, bool lowres_in_kernel, cudaStream_t stream) {
     FusedLbParams p;
+    p.shapes = plan->d_shapes; p.ltab = plan->d_tab; p.lowres_in_kernel = lowres_in_kernel ? 1 : 0;
     p.images = plan->d_images; p.lb = plan->d_lb; p.tab = plan->d_lb_tab; p.n_images = plan->n_images;
     p.src = src; p.scratch = scratch; p.opcodes = opcodes; p.noise = noise;
     p.out = reinterpret_cast<__half*>(out_f16);
@@ -343,7 +453,7 @@ int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8
     p.K = sigma * ROD_NOISE_K_PER_SIGMA;
     p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32); p.offset = offset; p.first_image = first_image;
     p.k = k;
-    p.buf_bytes = kFusedLeft + ((3 * plan->max_w + 15) & ~15) + 64;
+    p.buf_bytes = kFusedLeft + ((3 * plan->max_w + 15) & ~15) + 128;  // also holds two low-res rows (3 * max_w / 2 + 39 each)
     p.xtab_bytes = (p.out_w * 8 + 15) & ~15;
     const size_t smem = 512 + (size_t)p.xtab_bytes + 8 * (size_t)(3 * p.buf_bytes);
     if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;

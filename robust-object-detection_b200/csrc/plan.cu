@@ -125,6 +125,11 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     plan->lowres_x2_smem = x2_smem;
     plan->lowres_factor = factor;
     plan->lowres_all_identity = all_identity;
+    plan->lowres_all_x2w = true;
+    for (const DevShape& sh : shapes)
+        if (!sh.lin_identity && !sh.x2w) plan->lowres_all_x2w = false;
+    for (int i = 0; i < plan->n_images; ++i)  // 32-bit source loads in the fused kernel
+        if ((plan->h_images[i].src_pitch & 3) != 0 || (plan->h_images[i].src_off & 3) != 0) plan->lowres_all_x2w = false;
     plan->lowres_half_rows = max_rows;
     plan->lowres_half_cols = max_cols;
     plan->lowres_src_rows = max_src_rows;

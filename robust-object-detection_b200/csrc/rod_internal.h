@@ -76,6 +76,7 @@ struct rod_plan {
     rod::DevShape* d_shapes = nullptr;
     uint32_t* d_tab = nullptr;
     bool lowres_all_identity = false;
+    bool lowres_all_x2w = false;  // every shape is either an identity or eligible for the exact-2x in-register / in-smem path
     int lowres_half_rows = 0, lowres_half_cols = 0;  // worst-case low-res rows / cols one tile touches
     int lowres_src_rows = 0;                          // worst-case source rows one generic tile reads
 
@@ -142,7 +143,7 @@ int launch_format_pairs(const rod_plan* inner, const uint8_t* clean, const uint8
                         float* corrupted_out, cudaStream_t stream);
 int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8_t* scratch, const uint8_t* opcodes,
                            const float* noise, void* out_f16, int pad_value, float sigma, int k, uint64_t seed,
-                           uint64_t first_image, uint32_t offset, cudaStream_t stream);
+                           uint64_t first_image, uint32_t offset, bool lowres_in_kernel, cudaStream_t stream);
 int launch_letterbox(const rod_plan* plan, const uint8_t* img, const uint8_t* src, const uint8_t* opcodes, void* out_f16,
                      int pad_value, cudaStream_t stream);
 

@@ -461,6 +461,25 @@ def test_fused_letterbox_kernel_paths(torch_):
         assert np.array_equal(got[i], want), (i, shapes[i])
 
 
+def test_fused_letterbox_lowres_in_kernel(torch_):
+    """Every shape exact-2x (w % 4 == 0): the LowRes rows are produced inside fused_letterbox_kernel too (no scratch);
+    odd and even heights, a width with a two-pixel last chunk, several output sizes."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    shapes = [(765, 1360), (540, 960), (360, 480), (1080, 1920), (1050, 1400), (97, 1916), (131, 36), (765, 1360)]
+    ops_host = np.array([3, 3, 3, 3, 3, 3, 3, 2], dtype=np.uint8)
+    imgs = [synth(5200 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    plan = CorruptionPlan.ragged(shapes)
+    src = torch_.from_numpy(plan.pack(imgs)).cuda()
+    ops = torch_.from_numpy(ops_host).cuda()
+    want_cor = [orc.apply_op(im, int(o)) for im, o in zip(imgs, ops_host)]
+    for oh, ow in ((640, 640), (320, 416), (96, 96)):
+        out = torch_.empty((len(shapes), 3, oh, ow), dtype=torch_.float16, device="cuda")
+        plan.corrupt_letterbox(src, ops, out, oh, ow, 114)
+        got = out.cpu().numpy()
+        for i in range(len(shapes)):
+            assert np.array_equal(got[i], orc.letterbox_norm_f16(want_cor[i], oh, ow, 114)), (i, shapes[i], oh, ow)
+
+
 def test_apply_host_chunked_pipeline(torch_):
     """Host-buffer entry point with enough payload for several H2D/kernel/D2H chunks."""
     from robust_object_detection_b200 import _native as N
