@@ -456,6 +456,7 @@ struct LowresX2wParams {
     const uint8_t* src;
     uint8_t* dst;
     const uint8_t* opcodes;
+    unsigned int* counter;  // zeroed before the launch: next tile to hand out
 };
 
 constexpr int kX2wChunksPerStrip = 30;
@@ -565,7 +566,14 @@ __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     X2wWarpTables& tb = reinterpret_cast<X2wWarpTables*>(smem)[warp];
-    for (int ti = blockIdx.x * wpb + warp; ti < p.n_tiles; ti += gridDim.x * wpb) {
+    // tiles are handed out dynamically (one atomic per warp and tile): bands and strips differ in size, and a static
+    // round-robin leaves a tail
+    (void)wpb;
+    for (;;) {
+        int ti = 0;
+        if (lane == 0) ti = (int)atomicAdd(p.counter, 1u);
+        ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+        if (ti >= p.n_tiles) break;
         const Tile t = p.tiles[ti];
         if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
         const DevImage im = p.images[t.img];
@@ -680,6 +688,9 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.shapes = plan->d_shapes;
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
+            // a fresh counter per launch (ring of 256): launches of one plan may overlap on different streams
+            p.counter = plan->d_x2w_counter + (plan->x2w_launch_seq++ & 255u);
+            ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
             const int ctas = (p.n_tiles + 3) / 4;
             int per_sm = 4;  // benchmark knob: ROD_X2W_CTAS
             const char* e_ctas = getenv("ROD_X2W_CTAS");
