@@ -689,7 +689,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             // a fresh counter per launch (ring of 256): launches of one plan may overlap on different streams
-            p.counter = plan->d_x2w_counter + (plan->x2w_launch_seq++ & 255u);
+            p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
             ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
             const int ctas = (p.n_tiles + 3) / 4;
             int per_sm = 4;  // benchmark knob: ROD_X2W_CTAS

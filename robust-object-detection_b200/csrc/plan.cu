@@ -122,7 +122,6 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     tile_starts(x2w_tiles, plan->n_images, plan->lowres_x2w_tile_start);
     tile_starts(x2_rest_tiles, plan->n_images, plan->lowres_x2_rest_tile_start);
     plan->lowres_x2w_band_rows = band_rows;
-    if (plan->d_x2w_counter == nullptr) ROD_CUDA(cudaMalloc((void**)&plan->d_x2w_counter, 256 * sizeof(unsigned int)));
     plan->lowres_x2_smem = x2_smem;
     plan->lowres_factor = factor;
     plan->lowres_all_identity = all_identity;
@@ -254,6 +253,7 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
     }
     plan->n_noise_tiles = (int)nt.size();
     plan->n_blur_tiles = (int)bt.size();
+    if (cudaMalloc((void**)&plan->d_counters, 256 * sizeof(unsigned int)) != cudaSuccess) { rod_plan_destroy(plan); return ROD_ERR_OOM; }
     int rc = upload(plan->h_images, &plan->d_images);
     if (rc == ROD_OK) rc = upload(nt, &plan->d_noise_tiles);
     if (rc == ROD_OK) rc = upload(bt, &plan->d_blur_tiles);
@@ -311,7 +311,7 @@ extern "C" void rod_plan_destroy(rod_plan* plan) {
     void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles,
                     plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles, plan->d_lowres_x2_rest_tiles, plan->d_shapes,
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
-                    plan->d_f2d_taps, plan->d_f2d_tiles, plan->d_x2w_counter,
+                    plan->d_f2d_taps, plan->d_f2d_tiles, plan->d_counters,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};
     for (void* p : ptrs)
         if (p) cudaFree(p);

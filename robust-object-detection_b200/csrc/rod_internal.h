@@ -69,8 +69,8 @@ struct rod_plan {
     int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
     std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
     int lowres_x2w_band_rows = 0;
-    unsigned int* d_x2w_counter = nullptr;  // ring of 256 dynamic tile counters of the marching kernel (one per launch)
-    mutable unsigned int x2w_launch_seq = 0;
+    unsigned int* d_counters = nullptr;  // ring of 256 work counters for dynamically scheduled kernels (one per launch)
+    mutable unsigned int launch_seq = 0;
     bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
 
     // lowres tables, rebuilt when the factor changes
