@@ -7,6 +7,7 @@
 // half(float(u8) / 255.f).  One thread produces two horizontally adjacent output pixels
 // (3 channels each) and writes one half2 per colour plane.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "rod_internal.h"
 
@@ -143,6 +144,7 @@ struct FusedLbParams {
     const DevShape* shapes;  // lowres tables (plan->d_shapes / d_tab), used when lowres_in_kernel
     const uint32_t* ltab;
     int lowres_in_kernel;    // 1: LowRes rows are produced in shared memory too (every LowRes-able shape is exact-2x)
+    unsigned int* counter;   // zeroed before the launch: next tile to hand out
     int buf_bytes;           // bytes of one row buffer (16-byte multiple)
     int xtab_bytes;          // bytes of the per-CTA x table (16-byte multiple)
 };
@@ -323,10 +325,11 @@ __device__ __forceinline__ void load6_smem(const uint8_t* buf, int o, uint32_t& 
     hi = __funnelshift_r(w1, w2, sh);
 }
 
-__global__ void __launch_bounds__(256, 2) fused_letterbox_kernel(FusedLbParams p) {
+template <int NW>  // warps per CTA = output rows per tile
+__global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox_kernel(FusedLbParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __half* lut = reinterpret_cast<__half*>(smem);  // 256 x half(v / 255)
-    lut[threadIdx.x] = __float2half_rn(__fdiv_rn((float)threadIdx.x, 255.0f));
+    for (int v = threadIdx.x; v < 256; v += 32 * NW) lut[v] = __float2half_rn(__fdiv_rn((float)v, 255.0f));
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // per-CTA copy of the x tables of the current shape: {3 * s0 (byte offset of the left tap), a0 | a1 << 16, right-border
@@ -339,16 +342,24 @@ __global__ void __launch_bounds__(256, 2) fused_letterbox_kernel(FusedLbParams p
     uint8_t* X2 = X1 + p.buf_bytes;
     const size_t plane = (size_t)p.out_h * p.out_w;
     const __half padh = lut[p.pad];
-    const int groups = (p.out_h + 7) >> 3;
-    for (int ti = blockIdx.x; ti < p.n_images * groups; ti += gridDim.x) {
+    const int groups = (p.out_h + NW - 1) / NW;
+    // tiles (NW output rows of one image) are handed out dynamically: their cost differs by an order of magnitude
+    // (padding rows, clean rows, noise / blur / LowRes rows)
+    int* s_tile = reinterpret_cast<int*>(smem + 512 + p.xtab_bytes - 16);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) *s_tile = (int)atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const int ti = *s_tile;
+        if (ti >= p.n_images * groups) break;
         const int img = ti / groups;
-        const int Y = (ti - img * groups) * 8 + warp;
+        const int Y = (ti - img * groups) * NW + warp;
         const DevImage im = p.images[img];
         const DevLetterbox g = p.lb[im.shape_id];
         if (im.shape_id != cached_shape) {  // CTA-uniform: every warp walks the same tile sequence
             __syncthreads();
             const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + g.lx_s0);
-            for (int X = threadIdx.x; X < p.out_w; X += 256) {
+            for (int X = threadIdx.x; X < p.out_w; X += 32 * NW) {
                 const int cx = X - g.left;
                 uint2 e = make_uint2(0xFFFFFFFFu, 0u);  // padding column
                 if (cx >= 0 && cx < g.new_w) {
@@ -454,14 +465,26 @@ int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8
     p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32); p.offset = offset; p.first_image = first_image;
     p.k = k;
     p.buf_bytes = kFusedLeft + ((3 * plan->max_w + 15) & ~15) + 128;  // also holds two low-res rows (3 * max_w / 2 + 39 each)
-    p.xtab_bytes = (p.out_w * 8 + 15) & ~15;
-    const size_t smem = 512 + (size_t)p.xtab_bytes + 8 * (size_t)(3 * p.buf_bytes);
+    p.xtab_bytes = ((p.out_w * 8 + 15) & ~15) + 16;  // + the broadcast slot of the dynamic tile index
+    // 4 rows per tile: more, smaller tiles balance the expensive noise / blur / LowRes rows (measured 6 % faster than 8 at
+    // batch 64, equal at batch 16); knob ROD_FUSED_WARPS
+    const char* e_nw = getenv("ROD_FUSED_WARPS");
+    int nw = 4;
+    if (e_nw && (atoi(e_nw) == 4 || atoi(e_nw) == 8)) nw = atoi(e_nw);
+    const size_t smem = 512 + (size_t)p.xtab_bytes + (size_t)nw * (size_t)(3 * p.buf_bytes);
     if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
-    ROD_CUDA(cudaFuncSetAttribute(fused_letterbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : per_sm;
-    const int tiles = plan->n_images * ((p.out_h + 7) / 8);
-    fused_letterbox_kernel<<<grid_for(plan, tiles, per_sm * 4), 256, smem, stream>>>(p);
+    p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+    ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+    const int tiles = plan->n_images * ((p.out_h + nw - 1) / nw);
+    if (nw == 4) {
+        ROD_CUDA(cudaFuncSetAttribute(fused_letterbox_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fused_letterbox_kernel<4><<<grid_for(plan, tiles, per_sm), 128, smem, stream>>>(p);
+    } else {
+        ROD_CUDA(cudaFuncSetAttribute(fused_letterbox_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fused_letterbox_kernel<8><<<grid_for(plan, tiles, per_sm), 256, smem, stream>>>(p);
+    }
     ROD_CUDA(cudaGetLastError());
     return ROD_OK;
 }
