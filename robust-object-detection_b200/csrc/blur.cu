@@ -24,6 +24,7 @@ struct BlurParams {
     const uint8_t* opcodes;
     int k;
     int row_buf_bytes;  // shared bytes per warp
+    unsigned int* counter;  // zeroed before the launch
 };
 
 constexpr int kBlurLeft = 64;  // bytes in front of the 16-byte block that holds pixel 0 (>= 3*15 halo + 16)
@@ -49,12 +50,20 @@ __global__ void __launch_bounds__(256, 4) blur_rows_kernel(BlurParams p) {
     const int k = (K == 0) ? p.k : K;
     const int halo = 3 * (k >> 1);
 
-    for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
+    // each warp takes a whole tile (8 consecutive rows) at a time from a shared counter and filters its rows one by one
+    for (int sub = 8, ti = 0;;) {
+        if (sub >= 8) {
+            if (lane == 0) ti = (int)atomicAdd(p.counter, 1u);
+            ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+            sub = 0;
+        }
+        if (ti >= p.n_tiles) break;
         const Tile t = p.tiles[ti];
-        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_BLUR) continue;
-        if (warp >= t.b) continue;
+        const int wr = sub++;
+        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_BLUR) { sub = 8; continue; }
+        if (wr >= t.b) { sub = 8; continue; }
         const DevImage im = p.images[t.img];
-        const int y = t.a + warp;
+        const int y = t.a + wr;
         const int n = 3 * im.w;
         const uint8_t* srow = p.src + im.src_off + (int64_t)y * im.src_pitch;
         uint8_t* drow = p.dst + im.dst_off + (int64_t)y * im.dst_pitch;
@@ -166,7 +175,9 @@ int launch_blur(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, c
     if (ctas_per_sm > 4) ctas_per_sm = 4;
     const char* e_ctas = getenv("ROD_BLUR_CTAS");
     if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 4) ctas_per_sm = atoi(e_ctas);
-    const int grid = grid_for(plan, p.n_tiles, ctas_per_sm);
+    p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+    ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+    const int grid = grid_for(plan, (p.n_tiles + 7) / 8, ctas_per_sm);
     if (k == 9) {
         ROD_CUDA(cudaFuncSetAttribute(blur_rows_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         blur_rows_kernel<9><<<grid, 256, smem, stream>>>(p);
