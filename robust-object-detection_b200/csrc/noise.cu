@@ -29,6 +29,7 @@ struct NoiseParams {
     uint32_t offset;
     const uint8_t* opcodes;
     int my_op;
+    unsigned int* counter;  // zeroed before the launch
 };
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
@@ -89,9 +90,19 @@ __device__ __forceinline__ void group_gauss8(const NoiseParams& p, uint32_t ig_l
 template <int MODE>
 __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
     const float K = p.sigma * ROD_NOISE_K_PER_SIGMA;
-    for (int ti = blockIdx.x; ti < p.n_tiles; ti += gridDim.x) {
-        const Tile t = p.tiles[ti];
+    // a warp takes a quarter span (<= 4096 bytes) at a time from a shared counter: no tail, no block-level coupling
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t id = 0;
+        if (lane == 0) id = atomicAdd(p.counter, 1u);
+        id = __shfl_sync(0xFFFFFFFFu, id, 0);
+        if ((int)(id >> 2) >= p.n_tiles) break;
+        Tile t = p.tiles[id >> 2];
         if (p.opcodes != nullptr && p.opcodes[t.img] != p.my_op) continue;
+        const int piece0 = (int)(id & 3u) * (kNoiseSpan / 4);
+        if (piece0 >= t.b) continue;
+        t.a += piece0;
+        t.b = min(kNoiseSpan / 4, t.b - piece0);
         const DevImage im = p.images[t.img];
         const uint64_t img_global = p.first_image + (uint64_t)t.img;
         const uint32_t ig_lo = (uint32_t)img_global, ig_hi = (uint32_t)(img_global >> 32);
@@ -118,12 +129,12 @@ __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
             // coalesced (128 B of pixels, 512 B of field); four independent steps in flight per thread
             const bool vec4 = (e0 & 3u) == 0 && ((((uintptr_t)s) | ((uintptr_t)d)) & 3) == 0 && (((uintptr_t)nzp) & 15) == 0;
             const uint32_t nw = vec4 ? (n >> 2) : 0;
-            for (uint32_t base = threadIdx.x; base < nw; base += 4 * blockDim.x) {
+            for (uint32_t base = lane; base < nw; base += 4 * 32u) {
                 uint32_t px[4];
                 float4 f[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint32_t idx = base + u * blockDim.x;
+                    const uint32_t idx = base + u * 32u;
                     if (idx < nw) {
                         px[u] = ldg_stream4(s + 4 * idx);
                         f[u] = ldg_stream16f(nzp + 4 * idx);
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint32_t idx = base + u * blockDim.x;
+                    const uint32_t idx = base + u * 32u;
                     if (idx < nw) stg4(d + 4 * idx, noise_word(px[u], f[u].x, f[u].y, f[u].z, f[u].w));
                 }
             }
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
             if (MODE != NOISE_FIELD) vec = vec && ((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0;
             if (MODE == NOISE_FIELD) vec = vec && (((uintptr_t)fout) & 15) == 0;
             const uint32_t nvec = vec ? (n >> 4) : 0;
-            for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+            for (uint32_t i = lane; i < nvec; i += 32u) {
                 const uint32_t e = 16u * i;
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (MODE != NOISE_FIELD) v = ldg_stream16(s + e);
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
         if (r0 < n) {
             const uint32_t ea = e0 + r0, eb = e0 + n;      // absolute element range [ea, eb)
             const uint32_t g_first = ea >> 3, g_last = (eb - 1) >> 3;
-            for (uint32_t g = g_first + threadIdx.x; g <= g_last; g += blockDim.x) {
+            for (uint32_t g = g_first + lane; g <= g_last; g += 32u) {
                 float sf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (MODE == NOISE_PHILOX || MODE == NOISE_FIELD) group_gauss8(p, ig_lo, ig_hi, g, sf);
 #pragma unroll
@@ -210,10 +221,12 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
     p.first_image = first_image;
     p.offset = offset;
     p.opcodes = opcodes; p.my_op = my_op;
-    int per_sm = 32;  // CTAs per SM the grid is sized for: 4 are resident, a longer queue evens out the tail (knob: ROD_NOISE_CTAS)
+    p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+    ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+    int per_sm = 4;  // CTAs per SM the grid is sized for: 4 are resident, a longer queue evens out the tail (knob: ROD_NOISE_CTAS)
     const char* e_ctas = getenv("ROD_NOISE_CTAS");
     if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 64) per_sm = atoi(e_ctas);
-    const int grid = grid_for(plan, p.n_tiles, per_sm);
+    const int grid = grid_for(plan, (p.n_tiles + 1) / 2, per_sm);  // a CTA's 8 warps cover two spans at a time
     switch (mode) {
         case NOISE_COMPAT: noise_kernel<NOISE_COMPAT><<<grid, 256, 0, stream>>>(p); break;
         case NOISE_PHILOX: noise_kernel<NOISE_PHILOX><<<grid, 256, 0, stream>>>(p); break;
