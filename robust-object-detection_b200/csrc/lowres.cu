@@ -1,18 +1,16 @@
 // lowres.cu -- a4+a5: fused INTER_AREA downscale + 8-bit INTER_LINEAR upscale (sm_100a).
 //
-// Reference: scripts/augmentations.py:41-45 (apply_lowres): cv2.resize(img,(nw,nh),INTER_AREA)
-// followed by cv2.resize(small,(w,h),INTER_LINEAR).  The low-resolution intermediate of one
-// output tile (plus its one-pixel apron) is produced in shared memory and consumed from
-// there: it never exists in HBM.  A tile is kLowresTH output rows x kLowresTWB output BYTES
-// (tiles are cut in byte columns, not pixels: every stage is per byte, channel = byte % 3).
-//   phase B : low-res tile P (u8)    <- source pixels
-//             exact-2x widths: 12 source bytes (4 px) per row per thread with 32-bit loads,
-//             byte pairs summed with dp4a; integer (a+b+c+d+2)>>2 when both axes are exact
-//             2x (OpenCV's resizeAreaFast_), else OpenCV's float tables on the y axis.
-//             any other shape: per-byte generic path (rod_core.h area_value).
-//   phase C1: horizontal fixed-point pass  hx = (P[s0]*a0 + P[s1]*a1) >> 4   (u16, smem)
-//   phase C2: vertical pass + pack.  Each thread owns 8 byte columns and marches down 8 rows,
-//             keeping the two live hx rows in registers; one 64-bit store per row.
+// Reference: scripts/augmentations.py:41-45 (apply_lowres): cv2.resize(img,(nw,nh),INTER_AREA) followed by
+// cv2.resize(small,(w,h),INTER_LINEAR).  The low-resolution intermediate never exists in HBM.  Three kernels:
+//   lowres_x2w_kernel  exact-2x widths with w % 4 == 0 and 4-byte aligned rows (every VisDrone frame size): warp-marching,
+//                      the low-res rows live in registers (see the banner above the kernel)
+//   lowres_x2_kernel   exact-2x widths whose rows are not 4-byte aligned: full-width strips, low-res rows in shared memory
+//   lowres_kernel      any other shape (odd widths, other factors): tiles of kLowresTH rows x kLowresTWB output BYTES
+//                      (cut in byte columns: every stage is per byte, channel = byte % 3)
+//     phase B1/B2: separable INTER_AREA in OpenCV's operation order (resizeArea_ / resizeAreaFast_), horizontal pass
+//                  per source row into a float buffer, then the y taps -> low-res tile P (u8, shared)
+//     phase C1   : horizontal fixed-point pass  hx = (P[s0]*a0 + P[s1]*a1) >> 4   (u16, shared)
+//     phase C2   : vertical pass + pack; each thread owns 8 byte columns and marches down 8 rows
 #include <stdlib.h>
 
 #include <algorithm>
