@@ -11,6 +11,9 @@
  * (NULL = the legacy default stream).  All device work is stream-ordered and the
  * library never synchronises unless the function name ends in _host.
  *
+ * A rod_plan may be used from one host thread at a time (it caches tables, tile lists and scratch buffers lazily);
+ * launches issued from it on different streams may overlap on the device.  Different plans are independent.
+ *
  * Images are HWC uint8 with 3 interleaved channels (BGR for the reference's
  * callers; every operation is per channel).  A batch is described by a table of
  * rod_image_desc: byte offsets into one source and one destination buffer, so
