@@ -1,0 +1,152 @@
+"""Drop-in for scripts/build_corrupted_testsets.py of ysbbin/Robust-Object-Detection.
+
+Same module surface (constants, set_seed, build_yolo_testsets, build_coco_testsets, main), same on-disk result:
+for Test_Clean / Test_Noise / Test_Blur / Test_LowRes the images of `images/val` are read with cv2.imread, corrupted and
+written with cv2.imwrite under the same file name; labels / annotations are copied; data.yaml is written
+(build_corrupted_testsets.py:62-166).  The corruption itself runs on the GPU, one ragged batch at a time
+(rod_apply_host: pinned staging, chunked H2D / kernel / D2H), while JPEG decode and encode -- still the reference's
+OpenCV codec, so files are byte-identical to the reference's -- run on a host thread pool around it.
+
+RNG: Test_Noise draws each image's field with np.random.normal in glob order after np.random.seed(SEED), exactly like
+the reference, so the noisy files are byte-identical too (that draw is the slow part: ~100 ms per frame on one core).
+`NOISE_MODE = "philox"` generates the field on the GPU instead (statistically equivalent, not byte-identical).
+"""
+from __future__ import annotations
+
+import shutil
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+from . import _native as N
+from .augmentations import apply_lowres, apply_motion_blur, apply_noise  # noqa: F401  (same names as the reference)
+from .augmentations import _motion_blur_kernel as motion_blur_kernel  # noqa: F401
+from .batch import CorruptionPlan
+
+# ====== paths (same defaults as the reference, build_corrupted_testsets.py:8-10) ======
+YOLO_SRC = Path("data/processed/visdrone_yolo6")
+COCO_SRC = Path("data/processed/visdrone_coco6")
+OUT_ROOT = Path("data/testsets")
+
+# ====== corruption parameters (build_corrupted_testsets.py:13-23) ======
+SEED = 42
+NOISE_SIGMA = 15
+BLUR_KERNEL = 9
+BLUR_ANGLE_DEG = 0
+DOWNSCALE_FACTOR = 0.5
+
+# ====== B200 path knobs ======
+NOISE_MODE = "compat"      # "compat": host np.random stream (byte-identical) | "philox": in-kernel RNG
+PHILOX_SEED = SEED
+BATCH_BYTES = 512 << 20    # decoded source bytes per GPU batch
+IO_THREADS = 16
+
+VARIANTS = ["Test_Clean", "Test_Noise", "Test_Blur", "Test_LowRes"]
+_OPS = {"Test_Noise": N.OP_NOISE, "Test_Blur": N.OP_BLUR, "Test_LowRes": N.OP_LOWRES}
+
+
+def set_seed(seed: int):
+    np.random.seed(seed)
+
+
+def ensure_dir(p: Path):
+    p.mkdir(parents=True, exist_ok=True)
+
+
+def write_yolo_valonly_yaml(dst_root: Path):
+    """data.yaml that evaluates on this test set's val folder (build_corrupted_testsets.py:66-82)."""
+    lines = [f"path: {dst_root.as_posix()}", "train: images/val", "val: images/val", "", "names:",
+             "  0: pedestrian", "  1: car", "  2: van", "  3: truck", "  4: bus", "  5: motor"]
+    (dst_root / "data.yaml").write_text("\n".join(lines), encoding="utf-8")
+
+
+def _corrupt_batch(variant: str, images, philox_index: int):
+    """One ragged batch through the GPU; returns the corrupted arrays (views into one host buffer)."""
+    shapes = [(im.shape[0], im.shape[1]) for im in images]
+    plan = CorruptionPlan.ragged(shapes)
+    src = plan.pack(images)
+    dst = np.empty(plan.dst_bytes, dtype=np.uint8)
+    op = _OPS[variant]
+    noise = None
+    if variant == "Test_Noise" and NOISE_MODE == "compat":
+        # the draws of augmentations.py:31, one per image, in order
+        noise = np.concatenate([np.random.normal(0, NOISE_SIGMA, im.shape).astype(np.float32).reshape(-1) for im in images])
+    if variant == "Test_Blur" and float(BLUR_ANGLE_DEG) != 0.0:
+        plan.set_blur_kernel(motion_blur_kernel(BLUR_KERNEL, BLUR_ANGLE_DEG))
+    plan.apply_host(op, src, dst, noise_host=noise, sigma=float(NOISE_SIGMA), k=int(BLUR_KERNEL),
+                    factor=float(DOWNSCALE_FACTOR), seed=PHILOX_SEED, first_image_index=philox_index)
+    return plan.unpack(dst)
+
+
+def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str):
+    """The image loop of build_corrupted_testsets.py:108-124 / :148-164 for one variant, batched."""
+    import cv2
+    paths = list(src_img_dir.glob("*.*"))  # filesystem order, like the reference (it fixes the noise stream order)
+    philox_index = 0
+    with ThreadPoolExecutor(IO_THREADS) as pool:
+        i = 0
+        while i < len(paths):
+            # decode ahead until the batch is full (cv2 releases the GIL)
+            batch_paths, futs, nbytes = [], [], 0
+            while i < len(paths) and (nbytes < BATCH_BYTES or not futs):
+                futs.append(pool.submit(cv2.imread, str(paths[i])))
+                batch_paths.append(paths[i])
+                i += 1
+                nbytes += 6 << 20  # ~ a decoded VisDrone frame; the real size is known after decoding
+            decoded = [(p, f.result()) for p, f in zip(batch_paths, futs)]
+            decoded = [(p, im) for p, im in decoded if im is not None]  # unreadable files are skipped (reference :110-111)
+            if not decoded:
+                continue
+            images = [im for _, im in decoded]
+            if variant == "Test_Clean":
+                outs = images
+            else:
+                outs = _corrupt_batch(variant, images, philox_index)
+                philox_index += len(images)
+            list(pool.map(lambda po: cv2.imwrite(str(dst_img_dir / po[0].name), po[1]), zip((p for p, _ in decoded), outs)))
+
+
+def build_yolo_testsets():
+    src_img_dir = YOLO_SRC / "images" / "val"
+    src_lbl_dir = YOLO_SRC / "labels" / "val"
+    if not src_img_dir.exists() or not src_lbl_dir.exists():
+        raise FileNotFoundError("YOLO val images/labels not found. Check YOLO_SRC path.")
+    for v in VARIANTS:
+        dst_root = OUT_ROOT / "yolo6" / v
+        dst_img_dir = dst_root / "images" / "val"
+        dst_lbl_dir = dst_root / "labels" / "val"
+        ensure_dir(dst_img_dir)
+        ensure_dir(dst_lbl_dir)
+        for lbl in src_lbl_dir.glob("*.txt"):
+            shutil.copy2(lbl, dst_lbl_dir / lbl.name)
+        write_yolo_valonly_yaml(dst_root)
+        _process_images(src_img_dir, dst_img_dir, v)
+    print("YOLO test sets created:", (OUT_ROOT / "yolo6").resolve())
+
+
+def build_coco_testsets():
+    src_img_dir = COCO_SRC / "images" / "val"
+    src_ann = COCO_SRC / "annotations" / "instances_val.json"
+    if not src_img_dir.exists() or not src_ann.exists():
+        raise FileNotFoundError("COCO val images or instances_val.json not found. Check COCO_SRC path.")
+    for v in VARIANTS:
+        dst_root = OUT_ROOT / "coco6" / v
+        dst_img_dir = dst_root / "images" / "val"
+        dst_ann_dir = dst_root / "annotations"
+        ensure_dir(dst_img_dir)
+        ensure_dir(dst_ann_dir)
+        shutil.copy2(src_ann, dst_ann_dir / "instances_val.json")
+        _process_images(src_img_dir, dst_img_dir, v)
+    print("COCO test sets created:", (OUT_ROOT / "coco6").resolve())
+
+
+def main():
+    set_seed(SEED)
+    build_yolo_testsets()
+    build_coco_testsets()
+    print("\nAll corrupted test sets are ready under:", OUT_ROOT.resolve())
+
+
+if __name__ == "__main__":
+    main()

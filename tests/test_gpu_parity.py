@@ -589,3 +589,54 @@ def test_restoration_pairs_vs_reference_dataset_gpu(torch_, is_train):
     for i in range(n):
         assert np.array_equal(clean[i].cpu().numpy(), g[f"{tag}_clean_{i}"]), i
         assert np.array_equal(cor[i].cpu().numpy(), g[f"{tag}_cor_{i}"]), (i, dec[i])
+
+
+def test_build_corrupted_testsets_drop_in(tmp_path, monkeypatch):
+    """Row a9 end to end: the drop-in batch driver on a synthetic YOLO + COCO tree of JPEG files.  Every output file must
+    be byte-identical to what the reference loop produces: same cv2 codec, same glob order, same np.random stream for
+    Test_Noise (expected bytes are computed here with the oracle + cv2.imwrite in the same order)."""
+    import cv2
+    from robust_object_detection_b200 import build_corrupted_testsets as drv
+    shapes = [(120, 200), (97, 133), (64, 64), (300, 180), (81, 90), (200, 202), (765, 1360)]
+    for tree in ("yolo", "coco"):
+        img_dir = tmp_path / tree / "images" / "val"
+        img_dir.mkdir(parents=True)
+        for i, (h, w) in enumerate(shapes):
+            # smooth-ish content so the JPEG round trip is not pure noise
+            base = cv2.GaussianBlur(synth(7000 + i, h, w), (0, 0), 2.0)
+            cv2.imwrite(str(img_dir / f"frame_{i:03d}.jpg"), base)
+        (img_dir / "broken.jpg").write_bytes(b"not a jpeg")          # unreadable: skipped, consumes no RNG
+        (img_dir / "frame_png.png").write_bytes(cv2.imencode(".png", synth(7100, 50, 70))[1].tobytes())
+    (tmp_path / "yolo" / "labels" / "val").mkdir(parents=True)
+    for i in range(len(shapes)):
+        (tmp_path / "yolo" / "labels" / "val" / f"frame_{i:03d}.txt").write_text(f"0 0.5 0.5 0.1 0.{i + 1}\n")
+    (tmp_path / "coco" / "annotations").mkdir(parents=True)
+    (tmp_path / "coco" / "annotations" / "instances_val.json").write_text('{"images": [], "annotations": []}')
+    monkeypatch.setattr(drv, "YOLO_SRC", tmp_path / "yolo")
+    monkeypatch.setattr(drv, "COCO_SRC", tmp_path / "coco")
+    monkeypatch.setattr(drv, "OUT_ROOT", tmp_path / "out")
+    monkeypatch.setattr(drv, "BATCH_BYTES", 20 << 20)  # several GPU batches
+    drv.main()
+
+    # expected: the reference loop (build_corrupted_testsets.py:169-173, :85-166) restated with the oracle
+    np.random.seed(42)
+    ops = {"Test_Clean": 0, "Test_Noise": 1, "Test_Blur": 2, "Test_LowRes": 3}
+    n_files = 0
+    for tree, sub in (("yolo", "yolo6"), ("coco", "coco6")):
+        for v in ["Test_Clean", "Test_Noise", "Test_Blur", "Test_LowRes"]:
+            dst = tmp_path / "out" / sub / v
+            for p in (tmp_path / tree / "images" / "val").glob("*.*"):
+                img = cv2.imread(str(p))
+                if img is None:
+                    assert not (dst / "images" / "val" / p.name).exists()
+                    continue
+                want = orc.apply_op(img, ops[v])
+                ok, enc = cv2.imencode(p.suffix, want)
+                assert ok and (dst / "images" / "val" / p.name).read_bytes() == enc.tobytes(), (tree, v, p.name)
+                n_files += 1
+            if tree == "yolo":
+                assert (dst / "data.yaml").read_text().startswith(f"path: {dst.as_posix()}")
+                assert sorted(q.name for q in (dst / "labels" / "val").glob("*.txt")) == [f"frame_{i:03d}.txt" for i in range(len(shapes))]
+            else:
+                assert (dst / "annotations" / "instances_val.json").read_text() == '{"images": [], "annotations": []}'
+    assert n_files == 2 * 4 * (len(shapes) + 1)
