@@ -49,11 +49,23 @@ __global__ void __launch_bounds__(256) filter2d_kernel(Filter2dParams p) {
         for (int rr = warp; rr < th + 2 * r; rr += 8) {
             const uint8_t* srow = simg + (int64_t)reflect101(y0 + rr - r, im.h) * im.src_pitch;
             float* trow = tile + rr * tp;
+            // columns [c_lo, c_hi) lie inside the row: 32-bit loads over their 4-byte aligned middle, bytes at the ends;
+            // the columns outside are reflected border pixels (per pixel, not per byte)
+            const int c_lo = max(0, 3 * r - b0), c_hi = min(ncols, n + 3 * r - b0);
+            const uint8_t* s0 = srow + (b0 - 3 * r);  // s0[ci] is the source byte of column ci
+            const int c_al = min(c_hi, c_lo + (int)((4u - (uint32_t)((uintptr_t)(s0 + c_lo) & 3u)) & 3u));
+            const int n_words = (c_hi - c_al) >> 2;
+            for (int q = lane; q < n_words; q += 32) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(s0 + c_al) + q);
+                float* t4 = trow + c_al + 4 * q;
+                t4[0] = (float)(v & 0xFFu); t4[1] = (float)((v >> 8) & 0xFFu); t4[2] = (float)((v >> 16) & 0xFFu); t4[3] = (float)(v >> 24);
+            }
             for (int ci = lane; ci < ncols; ci += 32) {
+                if (ci >= c_al && ci < c_al + 4 * n_words) continue;  // done above
                 const int i = b0 + ci - 3 * r;  // byte position in the row
                 if (i >= 0 && i < n) {
                     trow[ci] = (float)srow[i];
-                } else {                        // reflected border pixel (per pixel, not per byte)
+                } else {
                     const int j = i + 3 * r, px = j / 3, c = j - 3 * px;  // j >= 0; pixel px - r
                     trow[ci] = (float)srow[3 * reflect101(px - r, im.w) + c];
                 }
