@@ -640,3 +640,38 @@ def test_build_corrupted_testsets_drop_in(tmp_path, monkeypatch):
             else:
                 assert (dst / "annotations" / "instances_val.json").read_text() == '{"images": [], "annotations": []}'
     assert n_files == 2 * 4 * (len(shapes) + 1)
+
+
+def test_random_shapes_stress(torch_):
+    """120 random shapes (1..320 x 1..420, biased to the kernels' corner cases: w % 4, w % 8, odd sizes, tiny images) in
+    ragged batches with 4-byte packing: blur, lowres and compat noise against the oracle, bit-exact."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    rng = np.random.default_rng(20240)
+    shapes = []
+    for i in range(120):
+        h = int(rng.integers(1, 321))
+        w = int(rng.integers(1, 421))
+        if i % 3 == 0:
+            w = max(4, w & ~3)          # exact-2x width, w % 4 == 0: the warp-marching kernel
+        if i % 9 == 0:
+            w = max(8, w & ~7)          # 8-byte-aligned rows
+        if i % 10 == 1:
+            h, w = int(rng.integers(1, 6)), int(rng.integers(1, 12))
+        shapes.append((h, w))
+    imgs = [synth(9000 + i, h, w, "binary" if i % 5 == 0 else "uniform") for i, (h, w) in enumerate(shapes)]
+    for lo in range(0, len(shapes), 40):
+        sh, im = shapes[lo:lo + 40], imgs[lo:lo + 40]
+        plan = CorruptionPlan.ragged(sh, align=4)
+        src = torch_.from_numpy(plan.pack(im)).cuda()
+        dst = torch_.zeros(plan.dst_bytes, dtype=torch_.uint8, device="cuda")
+        plan.blur(src, dst)
+        for i, out in enumerate(plan.unpack(dst.cpu().numpy())):
+            assert np.array_equal(out, orc.apply_motion_blur(im[i], 9, 0)), ("blur", sh[i])
+        plan.lowres(src, dst)
+        for i, out in enumerate(plan.unpack(dst.cpu().numpy())):
+            assert np.array_equal(out, orc.apply_lowres(im[i], 0.5)), ("lowres", sh[i])
+        np.random.seed(lo)
+        fields = [orc.draw_noise_field(x.shape, 15) for x in im]
+        plan.noise(src, dst, torch_.from_numpy(np.concatenate([f.reshape(-1) for f in fields])).cuda(), 15.0)
+        for i, out in enumerate(plan.unpack(dst.cpu().numpy())):
+            assert np.array_equal(out, orc.add_noise_field(im[i], fields[i])), ("noise", sh[i])
