@@ -675,3 +675,35 @@ def test_random_shapes_stress(torch_):
         plan.noise(src, dst, torch_.from_numpy(np.concatenate([f.reshape(-1) for f in fields])).cuda(), 15.0)
         for i, out in enumerate(plan.unpack(dst.cpu().numpy())):
             assert np.array_equal(out, orc.add_noise_field(im[i], fields[i])), ("noise", sh[i])
+
+
+def test_fused_letterbox_random_stress(torch_):
+    """Random shapes / ops / output sizes through corrupt_letterbox (fused kernel with in-kernel LowRes for the all-even
+    batch, scratch pre-pass for the mixed batch, unfused fallback when a letterbox degenerates), vs the oracle."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    rng = np.random.default_rng(777)
+    for trial in range(6):
+        n = 10
+        even = trial % 2 == 0
+        shapes = []
+        for i in range(n):
+            h, w = int(rng.integers(8, 260)), int(rng.integers(8, 340))
+            if even:
+                w = max(8, w & ~3)
+            shapes.append((h, w))
+        ops_host = rng.integers(0, 4, n).astype(np.uint8)
+        ops_host[ops_host == 1] = 2 if trial % 3 else 1   # compat noise only in some trials
+        oh, ow = [(96, 96), (128, 160), (64, 200)][trial % 3]
+        imgs = [synth(9500 + 16 * trial + i, h, w) for i, (h, w) in enumerate(shapes)]
+        plan = CorruptionPlan.ragged(shapes, align=4 if trial % 2 else 256)
+        src = torch_.from_numpy(plan.pack(imgs)).cuda()
+        np.random.seed(trial)
+        fields = [orc.draw_noise_field(im.shape, 15) for im in imgs]
+        nz = torch_.from_numpy(np.concatenate([f.reshape(-1) for f in fields])).cuda()
+        out = torch_.empty((n, 3, oh, ow), dtype=torch_.float16, device="cuda")
+        plan.corrupt_letterbox(src, torch_.from_numpy(ops_host).cuda(), out, oh, ow, 114, noise=nz)
+        got = out.cpu().numpy()
+        for i, img in enumerate(imgs):
+            op = int(ops_host[i])
+            cor = orc.add_noise_field(img, fields[i]) if op == 1 else orc.apply_op(img, op)
+            assert np.array_equal(got[i], orc.letterbox_norm_f16(cor, oh, ow, 114)), (trial, i, shapes[i], op)
