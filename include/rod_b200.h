@@ -80,10 +80,16 @@ ROD_API int  rod_plan_launches(const rod_plan* plan, int op);
  *   image in plan order, the H*W*3 field the reference would have drawn; result is
  *   uint8(trunc(clamp(float(src) + noise, 0, 255))) -- bit-exact with the reference.
  * philox mode (noise == NULL): the field is generated in registers: one Philox4x32-10 block
- *   (key = seed, counter = (element/8, first_image_index + i, offset)) feeds the Box-Muller pairs of
- *   8 consecutive elements (16-bit stratified radius with a 32-bit tail refinement, 16-bit angle);
+ *   (key = seed, counter = (element/8, first_image_index + i, offset)) serves 8 consecutive elements,
+ *   16 bits each.  Two Gaussian generators (csrc/rod_core.h defines both; the oracle restates both):
+ *     table      (sigma <= 29; default there): inverse-CDF lookup of floor(sigma z) in a 64 KB shared-memory table
+ *                (65535 strata of |z| < 4.30, tail refinement from a second Philox block up to 8.1 sigma);
+ *     Box-Muller (sigma <= 2048; default above 29, rod_plan_set_gaussian_generator(ROD_GAUSS_BOXMULLER), and always
+ *                on the training path rod_corrupt_letterbox_f16): 16-bit stratified radius with a 32-bit
+ *                tail refinement, 16-bit angle.
  *   result is clamp(src + floor(noise), 0, 255).  Reproducible for any batch split / GPU count;
- *   validated statistically (not bit-identical to NumPy's stream).  sigma <= 2048.
+ *   validated statistically (not bit-identical to NumPy's stream).  The first launch with a new sigma uploads
+ *   the table synchronously (do not issue it inside a stream capture).
  * opcodes (device uint8[n_images], may be NULL): when given, only images whose
  *   op-code equals ROD_OP_NOISE are processed; the others are left untouched. */
 ROD_API int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const float* noise,
@@ -92,6 +98,11 @@ ROD_API int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst,
 /* The float32 field philox mode adds (same layout as `noise` above); for tests/resume. */
 ROD_API int rod_noise_field_f32(const rod_plan* plan, float* out_field, float sigma, uint64_t seed,
                         uint64_t first_image_index, uint32_t offset, void* stream);
+/* Philox-mode Gaussian generator of this plan: ROD_GAUSS_AUTO (0, default: table when sigma <= 29, else
+ * Box-Muller) or ROD_GAUSS_BOXMULLER (1). */
+#define ROD_GAUSS_AUTO 0
+#define ROD_GAUSS_BOXMULLER 1
+ROD_API int rod_plan_set_gaussian_generator(rod_plan* plan, int generator);
 
 /* a2+a3: apply_motion_blur(img, k, angle_deg) (augmentations.py:21-38) for angle_deg == 0:
  * horizontal k-tap box, BORDER_REFLECT_101, out = (2S + k) / (2k).  k odd, 1 <= k <= 31;

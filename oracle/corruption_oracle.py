@@ -67,8 +67,8 @@ def apply_noise(img: np.ndarray, sigma: float) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------
-# Philox4x32-10 + Box-Muller (the GPU "philox" noise mode; no reference twin --
-# this restates OUR kernel's documented stream so tests can check it exactly).
+# Philox4x32-10 + inverse-CDF table / Box-Muller (the GPU "philox" noise mode; no reference twin --
+# this restates OUR kernels' documented streams so tests can check them exactly).
 # ----------------------------------------------------------------------------
 _PHILOX_M0 = np.uint64(0xD2511F53)
 _PHILOX_M1 = np.uint64(0xCD9E8D57)
@@ -103,9 +103,71 @@ _ANGLE_SCALE = float(np.float32(9.58737992428525768e-05))  # float32(2 pi / 6553
 _ANGLE_BIAS = float(np.float32(-804.2476806640625))        # float32((0.5 - 2^23) * 2 pi / 65536)
 
 
+GAUSS_TABLE_MAX_SIGMA = 29.0   # rod_core.h ROD_GAUSS_TABLE_MAX_SIGMA
+
+
+def gauss_table(sigma: float) -> np.ndarray:
+    """int64[65536]: T[h] = floor(float64(float32(sigma)) * Phi^-1(h / 65536)), h = 1..65535; T[0] unused
+    (rod_tables.h build_gauss_table).  scipy's ndtri is the independent inverse normal CDF here."""
+    from scipy.special import ndtri
+    t = np.zeros(65536, dtype=np.int64)
+    h = np.arange(1, 65536, dtype=np.float64)
+    t[1:] = np.floor(float(np.float32(sigma)) * ndtri(h / 65536.0)).astype(np.int64)
+    return t
+
+
+def philox_noise_field_table(n_elems: int, sigma: float, seed: int, image_index: int,
+                             offset: int = 0) -> np.ndarray:
+    """float64 restatement of the TABLE generator of Philox mode (rod_core.h / noise.cu noise_table_kernel),
+    the default for sigma <= 29.  Same Philox blocks as the Box-Muller generator below, but every 16-bit half is
+    one inverse-CDF draw: element 8g + 2p takes h = r_p & 0xffff, element 8g + 2p + 1 takes h = r_p >> 16;
+      h != 0: k = T[h]                                       (65535 equiprobable strata of |z| < 4.30)
+      h == 0: w = t_p (even element) or rotl(t_p, 16) (odd), t = Philox block at ctr[2] ^ 0x80000000;
+              z = -Phi^-1(((w >> 1) + 0.5) * 2^-48); k = floor(-sigma z) if w & 1 else floor(sigma z)
+    Returns k as float64 (already an integer: add_philox_noise's floor is then the identity)."""
+    from scipy.special import ndtri
+    n_groups = (n_elems + 7) // 8
+    g = np.arange(n_groups, dtype=np.uint64)
+    ctr = np.empty((n_groups, 4), dtype=np.uint32)
+    ctr[:, 0] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    ctr[:, 1] = np.uint32(image_index & 0xFFFFFFFF)
+    ctr[:, 2] = np.uint32((image_index >> 32) & 0xFFFFFFFF)
+    ctr[:, 3] = np.uint32(offset & 0xFFFFFFFF)
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    r = philox4x32_10(ctr, key)
+    ctr_t = ctr.copy()
+    ctr_t[:, 2] ^= np.uint32(_PHILOX_TAIL_FLIP)
+    tab = gauss_table(sigma)
+    sig = float(np.float32(sigma))
+    k = np.empty((n_groups, 8), dtype=np.float64)
+    h = np.empty((n_groups, 8), dtype=np.int64)
+    for p_ in range(4):
+        h[:, 2 * p_] = (r[:, p_] & np.uint32(0xFFFF)).astype(np.int64)
+        h[:, 2 * p_ + 1] = (r[:, p_] >> np.uint32(16)).astype(np.int64)
+    k[:] = tab[h]
+    rows, cols = np.nonzero(h == 0)
+    if rows.size:
+        t = philox4x32_10(ctr_t[rows], key).astype(np.uint64)
+        w = t[np.arange(rows.size), cols >> 1]
+        w = np.where(cols & 1, ((w << np.uint64(16)) | (w >> np.uint64(16))) & np.uint64(0xFFFFFFFF), w)
+        z = -ndtri(((w >> np.uint64(1)).astype(np.float64) + 0.5) * 2.0 ** -48)
+        k[rows, cols] = np.floor(np.where(w & np.uint64(1), -sig * z, sig * z))
+    return k.reshape(-1)[:n_elems]
+
+
 def philox_noise_field(n_elems: int, sigma: float, seed: int, image_index: int,
-                       offset: int = 0) -> np.ndarray:
-    """float64 restatement of the kernel's Philox-mode noise stream for one image
+                       offset: int = 0, generator: str = "auto") -> np.ndarray:
+    """The field Philox mode adds: generator "auto" (what rod_noise_u8 / rod_corrupt_batch_u8 use: the table
+    generator for sigma <= 29, else Box-Muller), "table", or "boxmuller" (always used by the training path,
+    rod_corrupt_letterbox_f16)."""
+    if generator == "table" or (generator == "auto" and float(np.float32(sigma)) <= GAUSS_TABLE_MAX_SIGMA):
+        return philox_noise_field_table(n_elems, sigma, seed, image_index, offset)
+    return philox_noise_field_boxmuller(n_elems, sigma, seed, image_index, offset)
+
+
+def philox_noise_field_boxmuller(n_elems: int, sigma: float, seed: int, image_index: int,
+                                 offset: int = 0) -> np.ndarray:
+    """float64 restatement of the Box-Muller generator of Philox mode for one image
     (robust-object-detection_b200/csrc/rod_core.h: philox4x32_10 + gauss8).
 
     Element e (flat HWC index) belongs to group g = e // 8; word p = (e % 8) // 2 of the

@@ -157,6 +157,11 @@ class CorruptionPlan:
         N.check(N.lib().rod_noise_field_f32(self._h, _ptr(out), float(sigma), int(seed), int(first_image_index),
                                             int(offset), _stream_handle(stream)), "rod_noise_field_f32")
 
+    def set_gaussian_generator(self, generator: int) -> None:
+        """Philox-mode Gaussian generator of this plan: 0 = auto (inverse-CDF table when sigma <= 29, else
+        Box-Muller), 1 = Box-Muller.  include/rod_b200.h rod_plan_set_gaussian_generator."""
+        N.check(N.lib().rod_plan_set_gaussian_generator(self._h, int(generator)), "rod_plan_set_gaussian_generator")
+
     def blur(self, src, dst, k: int = BLUR_KERNEL, angle_deg: float = BLUR_ANGLE_DEG, opcodes=None, stream=None) -> None:
         N.check(N.lib().rod_blur_h_u8(self._h, _ptr(src), _ptr(dst), int(k), float(angle_deg), _ptr(opcodes),
                                       _stream_handle(stream)), "rod_blur_h_u8")

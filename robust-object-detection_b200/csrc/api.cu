@@ -131,6 +131,13 @@ extern "C" int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* d
                         first_image_index, offset, opcodes, ROD_OP_NOISE, (cudaStream_t)stream, 0, plan->n_images);
 }
 
+extern "C" int rod_plan_set_gaussian_generator(rod_plan* plan, int generator) {
+    if (plan == nullptr || (generator != ROD_GAUSS_AUTO && generator != ROD_GAUSS_BOXMULLER)) return ROD_ERR_INVALID_ARG;
+    plan->gauss_generator = generator;
+    if (plan->inner != nullptr) plan->inner->gauss_generator = generator;
+    return ROD_OK;
+}
+
 extern "C" int rod_noise_field_f32(const rod_plan* plan, float* out_field, float sigma, uint64_t seed,
                                    uint64_t first_image_index, uint32_t offset, void* stream) {
     if (plan == nullptr || out_field == nullptr) return ROD_ERR_INVALID_ARG;
@@ -172,6 +179,13 @@ extern "C" int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, con
                                          void* stream) {
     if (plan == nullptr || src == nullptr || out_f16 == nullptr || opcodes == nullptr) return ROD_ERR_INVALID_ARG;
     if (pad_value < 0 || pad_value > 255) return ROD_ERR_INVALID_ARG;
+    // The training path always uses the Box-Muller generator: the fused kernel spends its shared memory on row
+    // buffers (no room for the 64 KB table), and the unfused fallback must produce the same bytes as the fused kernel.
+    struct GeneratorScope {
+        rod_plan* p; int saved;
+        explicit GeneratorScope(rod_plan* pl) : p(pl), saved(pl->gauss_generator) { p->gauss_generator = ROD_GAUSS_BOXMULLER; }
+        ~GeneratorScope() { p->gauss_generator = saved; }
+    } generator_scope(plan);
     int rc = ensure_letterbox_tables(plan, out_h, out_w);
     if (rc != ROD_OK) return rc;
     if (plan->d_scratch == nullptr || plan->scratch_bytes < plan->dst_extent) {
@@ -231,6 +245,7 @@ extern "C" int rod_restoration_pairs_f32(rod_plan* plan, const uint8_t* src, con
         }
         int rc = rod_plan_create(d.data(), n, &plan->inner);
         if (rc != ROD_OK) return rc;
+        plan->inner->gauss_generator = plan->gauss_generator;
         ROD_CUDA(cudaMalloc((void**)&plan->d_patch_clean, n * stride + 64));
         ROD_CUDA(cudaMalloc((void**)&plan->d_patch_corrupted, n * stride + 64));
     }

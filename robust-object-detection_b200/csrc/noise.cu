@@ -2,8 +2,11 @@
 //
 // Reference: scripts/augmentations.py:30-33 (apply_noise).  Two sources for the field:
 //   NOISE_COMPAT  a supplied float32 tensor (what np.random.normal(...).astype(f32) drew) -> bit-exact
-//   NOISE_PHILOX  Philox4x32-10 + Box-Muller generated in registers, keyed by
-//                 (seed, global image index, element/4, offset): no HBM traffic for the field
+//   NOISE_PHILOX  Philox4x32-10 keyed by (seed, global image index, element/8, offset), no HBM traffic for
+//                 the field; two Gaussian generators on the same Philox blocks (rod_core.h):
+//                   table      (sigma <= 29, noise_table_kernel): one shared-memory lookup per element in a
+//                              64 KB inverse-CDF table of floor(sigma z) -- no MUFU, ~10 instructions per byte
+//                   Box-Muller (any sigma <= 2048, noise_kernel<NOISE_PHILOX>): 4 MUFU per pair, XU-pipe bound
 // plus NOISE_COPY (ROD_OP_NONE images of a mixed batch) and NOISE_FIELD (dump the Philox field).
 //
 // HBM-bound elementwise op: one work item is a span of <= 16384 consecutive bytes; each
@@ -11,7 +14,11 @@
 // addresses are not 16-byte aligned (pitched rows of strided views) take a byte path.
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "rod_internal.h"
+#include "rod_tables.h"
 
 namespace rod {
 
@@ -25,11 +32,14 @@ struct NoiseParams {
     float* field_out;
     float sigma;
     uint32_t key0, key1;
+    PhiloxKeys keys;        // the ten round keys of (key0, key1)
     uint64_t first_image;
     uint32_t offset;
     const uint8_t* opcodes;
     int my_op;
     unsigned int* counter;  // zeroed before the launch
+    uint32_t two16;         // 65536 (see group_table8)
+    const int8_t* table;    // table generator: 65536 x int8 floor(sigma z) (device global; staged in shared memory)
 };
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
@@ -77,7 +87,7 @@ __device__ __forceinline__ uint32_t noise_word(uint32_t word, float n0, float n1
 __device__ __forceinline__ void group_gauss8(const NoiseParams& p, uint32_t ig_lo, uint32_t ig_hi, uint32_t g,
                                              float s[8]) {
     uint32_t r[4];
-    philox4x32_10(g, ig_lo, ig_hi, p.offset, p.key0, p.key1, r);
+    philox4x32_10_rk(g, ig_lo, ig_hi, p.offset, p.keys, r);
     if (philox_needs_tail(r)) {  // 2^-14 of the groups: refine the radius of the words whose high half is 0
         uint32_t t[4];
         philox4x32_10(g, ig_lo, ig_hi ^ ROD_PHILOX_TAIL_FLIP, p.offset, p.key0, p.key1, t);
@@ -205,10 +215,208 @@ __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Table generator (rod_core.h): k[0..7] of group g.  `tab` is the CTA's shared-memory copy of the table.
+// ---------------------------------------------------------------------------------------------------
+// Shared-memory layout of the table kernel: the 64 KB table sits at a 64 KB-ALIGNED shared address `tbase`, so
+// the address of a draw is one instruction per element: (r & 0xffff) | tbase (LOP3) for the low half and
+// hi(r * 2^16) + tbase (IMAD.HI, FMA pipe) for the high half.  Entries are stored biased, kb = k + 128 (uint8), so
+// two of them pack into an int16 pair with one IMAD; the pixel side carries the -128 (prmt sign replication).
+constexpr uint32_t kTabSmemBytes = 65536u + 65536u;  // table + slack to reach the next 64 KB boundary
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// f[i] = int16 pair (kb[2i], kb[2i+1]) of group g, kb = k + 128.  Half 0 of a word is a tail draw (2^-16 per element);
+// its table entry is the sentinel kb = 0 (real entries lie in [3, 253]), so the returned products -- the four
+// entries of two words multiplied together on the FMA pipe, < 2^32 -- are zero exactly when the group has one.  The
+// caller then redoes the group with table_group_slow after its loop, so the hot loop contains no call.
+__device__ __forceinline__ void group_table8(uint32_t tbase, const NoiseParams& p, uint32_t ig_lo, uint32_t ig_hi,
+                                             uint32_t g, uint32_t f[4], uint32_t* z01, uint32_t* z23) {
+    uint32_t r[4];
+    philox4x32_10_rk(g, ig_lo, ig_hi, p.offset, p.keys, r);
+    uint32_t z[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t alo, ahi;
+        asm("lop3.b32 %0, %1, 65535, %2, 0xEA;" : "=r"(alo) : "r"(r[q]), "r"(tbase));  // (r & 0xffff) | tbase
+        // 65536 comes from the parameter block so ptxas keeps the IMAD.HI (a literal power of two turns into LEA.HI, ALU pipe)
+        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(ahi) : "r"(r[q]), "r"(p.two16), "r"(tbase));
+        const uint32_t khi = lds_u8(ahi), klo = lds_u8(alo);
+        f[q] = khi * 65536u + klo;
+        z[q] = khi * klo;
+    }
+    *z01 = z[0] * z[1];
+    *z23 = z[2] * z[3];
+}
+
+// One group, element by element, restricted to the absolute element range [ea, eb), with the tail draws: the
+// remainder of unaligned spans and the redo of groups that group_table8 flagged.  e0 = element index of s[0] / d[0].
+template <int MODE>
+__device__ __noinline__ void table_group_slow(const NoiseParams& p, uint32_t tbase, uint32_t ig_lo, uint32_t ig_hi,
+                                              uint32_t g, uint32_t e0, uint32_t ea, uint32_t eb, const uint8_t* s,
+                                              uint8_t* d, float* fout) {
+    uint32_t r[4];
+    philox4x32_10_rk(g, ig_lo, ig_hi, p.offset, p.keys, r);
+    uint32_t t[4];
+    philox4x32_10_rk(g, ig_lo, ig_hi ^ ROD_PHILOX_TAIL_FLIP, p.offset, p.keys, t);
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t e = 8u * g + j;
+        if (e < ea || e >= eb) continue;
+        const uint32_t w = r[j >> 1];
+        const uint32_t h = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+        const int k = h != 0u ? (int)lds_u8(tbase + h) - 128 : gauss_tail_k(gauss_tail_word(t, j), p.sigma);
+        const uint32_t rel = e - e0;
+        if (MODE == NOISE_FIELD) fout[rel] = (float)k;
+        else d[rel] = (uint8_t)noise_table_px(s[rel], k);
+    }
+}
+__device__ __forceinline__ int table_k(const uint32_t f[4], int j) {  // element j of the group: k = kb - 128
+    return (int)(int16_t)(f[j >> 1] >> (16 * (j & 1))) - 128;
+}
+
+// four pixels (one word) + two packed pairs -> four output bytes: clamp((v - 128) + kb, 0, 255) = clamp(v + k, 0, 255)
+__device__ __forceinline__ uint32_t table_word(uint32_t word, uint32_t f01, uint32_t f23) {
+    const uint32_t w = word ^ 0x80808080u;  // int8(v ^ 0x80) = v - 128
+    const uint32_t v01 = prmt(w, 0u, 0x9180u), v23 = prmt(w, 0u, 0xB3A2u);  // sign-extended to int16 pairs
+    const uint32_t q01 = __viaddmin_s16x2_relu(f01, v01, 0x00FF00FFu);
+    const uint32_t q23 = __viaddmin_s16x2_relu(f23, v23, 0x00FF00FFu);
+    return __byte_perm(q01, q23, 0x6420);
+}
+
+// Same work hand-out as noise_kernel (warps take quarter spans from a shared counter); the CTA first stages the
+// 64 KB table in shared memory (from L2 after the first CTA of the launch).  MODE: NOISE_PHILOX or NOISE_FIELD.
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) noise_table_kernel(NoiseParams p) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(s_raw) + 0xFFFFu) & ~0xFFFFu;
+    for (int i = threadIdx.x; i < 4096; i += THREADS) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.table) + i);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tbase + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    // the next work item (counter value + its tile) is fetched while the current one is processed
+    uint32_t id_next = 0;
+    if (lane == 0) id_next = atomicAdd(p.counter, 1u);
+    id_next = __shfl_sync(0xFFFFFFFFu, id_next, 0);
+    Tile t_next = p.tiles[min((int)(id_next >> 2), p.n_tiles - 1)];
+    for (;;) {
+        const uint32_t id = id_next;
+        if ((int)(id >> 2) >= p.n_tiles) break;
+        Tile t = t_next;
+        if (lane == 0) id_next = atomicAdd(p.counter, 1u);
+        id_next = __shfl_sync(0xFFFFFFFFu, id_next, 0);
+        t_next = p.tiles[min((int)(id_next >> 2), p.n_tiles - 1)];
+        if (p.opcodes != nullptr && p.opcodes[t.img] != p.my_op) continue;
+        const int piece0 = (int)(id & 3u) * (kNoiseSpan / 4);
+        if (piece0 >= t.b) continue;
+        t.a += piece0;
+        t.b = min(kNoiseSpan / 4, t.b - piece0);
+        const DevImage im = p.images[t.img];
+        const uint64_t img_global = p.first_image + (uint64_t)t.img;
+        const uint32_t ig_lo = (uint32_t)img_global, ig_hi = (uint32_t)(img_global >> 32);
+        const uint8_t* s = nullptr;
+        uint8_t* d = nullptr;
+        uint32_t e0;  // element index (inside the image) of the span's first byte
+        if (t.c < 0) {
+            e0 = (uint32_t)t.a;
+            if (MODE != NOISE_FIELD) { s = p.src + im.src_off + e0; d = p.dst + im.dst_off + e0; }
+        } else {
+            e0 = (uint32_t)t.c * 3u * (uint32_t)im.w + (uint32_t)t.a;
+            if (MODE != NOISE_FIELD) {
+                s = p.src + im.src_off + (int64_t)t.c * im.src_pitch + t.a;
+                d = p.dst + im.dst_off + (int64_t)t.c * im.dst_pitch + t.a;
+            }
+        }
+        const uint32_t n = (uint32_t)t.b;
+        float* fout = (MODE == NOISE_FIELD) ? p.field_out + im.elem_base + e0 : nullptr;
+
+        // 16 bytes per thread step = two Philox groups: needs the span to start on a group boundary
+        bool vec = (e0 & 7u) == 0;
+        if (MODE != NOISE_FIELD) vec = vec && ((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0;
+        if (MODE == NOISE_FIELD) vec = vec && (((uintptr_t)fout) & 15) == 0;
+        const uint32_t nvec = vec ? (n >> 4) : 0;
+        uint32_t redo = 0;  // bit `step`: this lane's step has a tail draw and goes through the slow path (<= 8 steps per piece)
+#pragma unroll 2
+        for (uint32_t i = lane, bit = 1u; i < nvec; i += 32u, bit <<= 1) {
+            const uint32_t e = 16u * i;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (MODE != NOISE_FIELD) v = ldg_stream16(s + e);
+            uint32_t fa[4], fb[4], za, zb, zc, zd;
+            group_table8(tbase, p, ig_lo, ig_hi, (e0 + e) >> 3, fa, &za, &zb);
+            group_table8(tbase, p, ig_lo, ig_hi, ((e0 + e) >> 3) + 1u, fb, &zc, &zd);
+            if (min(min(za, zb), min(zc, zd)) == 0u) redo |= bit;
+            if (MODE == NOISE_FIELD) {
+                float4* fo = reinterpret_cast<float4*>(fout + e);
+                fo[0] = make_float4((float)table_k(fa, 0), (float)table_k(fa, 1), (float)table_k(fa, 2), (float)table_k(fa, 3));
+                fo[1] = make_float4((float)table_k(fa, 4), (float)table_k(fa, 5), (float)table_k(fa, 6), (float)table_k(fa, 7));
+                fo[2] = make_float4((float)table_k(fb, 0), (float)table_k(fb, 1), (float)table_k(fb, 2), (float)table_k(fb, 3));
+                fo[3] = make_float4((float)table_k(fb, 4), (float)table_k(fb, 5), (float)table_k(fb, 6), (float)table_k(fb, 7));
+            } else {
+                stg16(d + e, make_uint4(table_word(v.x, fa[0], fa[1]), table_word(v.y, fa[2], fa[3]),
+                                        table_word(v.z, fb[0], fb[1]), table_word(v.w, fb[2], fb[3])));
+            }
+        }
+        while (redo != 0u) {  // rare: rewrite the flagged steps element by element (this lane wrote them itself)
+            const uint32_t b = (uint32_t)__ffs((int)redo) - 1u;
+            redo &= redo - 1u;
+            const uint32_t g = (e0 + 16u * (lane + 32u * b)) >> 3;
+            table_group_slow<MODE>(p, tbase, ig_lo, ig_hi, g, e0, 8u * g, 8u * g + 8u, s, d, fout);
+            table_group_slow<MODE>(p, tbase, ig_lo, ig_hi, g + 1u, e0, 8u * g + 8u, 8u * g + 16u, s, d, fout);
+        }
+        // remainder (and the whole span when unaligned): one Philox group (<= 8 elements) per thread step
+        const uint32_t r0 = nvec << 4;
+        if (r0 < n) {
+            const uint32_t ea = e0 + r0, eb = e0 + n;  // absolute element range [ea, eb)
+            const uint32_t g_first = ea >> 3, g_last = (eb - 1) >> 3;
+            for (uint32_t g = g_first + lane; g <= g_last; g += 32u)
+                table_group_slow<MODE>(p, tbase, ig_lo, ig_hi, g, e0, ea, eb, s, d, fout);
+        }
+    }
+}
+
+// Device copies of the inverse-CDF table, one per (device, sigma), built on first use (synchronous upload: the
+// first Philox launch with a new sigma must not happen inside a stream capture).
+struct GaussTable {
+    int device;
+    uint32_t sigma_bits;
+    int8_t* d_tab;
+};
+static std::mutex g_tab_mutex;
+static std::vector<GaussTable> g_tabs;
+
+static int gauss_table_for(int device, float sigma, const int8_t** out) {
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    const uint32_t bits = fbits(sigma);
+    for (const GaussTable& t : g_tabs)
+        if (t.device == device && t.sigma_bits == bits) { *out = t.d_tab; return ROD_OK; }
+    std::vector<int8_t> h(65536);
+    build_gauss_table(sigma, h.data());
+    for (auto& b : h) b = (int8_t)(uint8_t)((int)b + 128);  // stored biased: kb = k + 128
+    h[0] = 0;                                                // the tail sentinel (real entries are >= 3)
+    int8_t* d = nullptr;
+    ROD_CUDA(cudaMalloc(&d, 65536));
+    cudaError_t e = cudaMemcpy(d, h.data(), 65536, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e); }
+    g_tabs.push_back(GaussTable{device, bits, d});
+    *out = d;
+    return ROD_OK;
+}
+
 int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* dst, const float* noise,
                  float* field_out, float sigma, uint64_t seed, uint64_t first_image, uint32_t offset,
-                 const uint8_t* opcodes, int my_op, cudaStream_t stream, int img_lo, int img_hi) {
+                 const uint8_t* opcodes, int my_op, cudaStream_t stream, int img_lo, int img_hi, int generator) {
     if (plan->n_noise_tiles == 0) return ROD_OK;
+    if (generator < 0) generator = plan->gauss_generator;
     NoiseParams p;
     p.images = plan->d_images;
     const int t_lo = plan->noise_tile_start[img_lo], t_hi = plan->noise_tile_start[img_hi];
@@ -218,14 +426,36 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
     p.src = src; p.dst = dst; p.noise = noise; p.field_out = field_out;
     p.sigma = sigma;
     p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32);
+    p.keys = philox_round_keys(p.key0, p.key1);
     p.first_image = first_image;
     p.offset = offset;
     p.opcodes = opcodes; p.my_op = my_op;
+    p.table = nullptr;
+    p.two16 = 65536u;
     p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
     ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     int per_sm = 4;  // CTAs per SM the grid is sized for: 4 are resident, a longer queue evens out the tail (knob: ROD_NOISE_CTAS)
     const char* e_ctas = getenv("ROD_NOISE_CTAS");
     if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 64) per_sm = atoi(e_ctas);
+    if ((mode == NOISE_PHILOX || mode == NOISE_FIELD) && generator == ROD_GAUSS_AUTO && sigma <= ROD_GAUSS_TABLE_MAX_SIGMA) {
+        int rc = gauss_table_for(plan->device, sigma, &p.table);
+        if (rc != ROD_OK) return rc;
+        // one 1024-thread CTA per SM, each with its own copy of the table; warps take quarter spans
+        const int ctas = grid_for(plan, (p.n_tiles * 4 + 23) / 24, 1);
+        static const int nthr = [] { const char* e = getenv("ROD_NOISE_THREADS"); return e ? atoi(e) : 768; }();
+#define ROD_TAB_LAUNCH(M, TH)                                                                                              \
+    do {                                                                                                                   \
+        ROD_CUDA(cudaFuncSetAttribute(noise_table_kernel<M, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmemBytes)); \
+        noise_table_kernel<M, TH><<<ctas, TH, kTabSmemBytes, stream>>>(p);                                                 \
+    } while (0)
+        if (mode == NOISE_FIELD) ROD_TAB_LAUNCH(NOISE_FIELD, 768);
+        else if (nthr == 1024) ROD_TAB_LAUNCH(NOISE_PHILOX, 1024);
+        else if (nthr == 896) ROD_TAB_LAUNCH(NOISE_PHILOX, 896);
+        else ROD_TAB_LAUNCH(NOISE_PHILOX, 768);
+#undef ROD_TAB_LAUNCH
+        ROD_CUDA(cudaGetLastError());
+        return ROD_OK;
+    }
     const int grid = grid_for(plan, (p.n_tiles + 1) / 2, per_sm);  // a CTA's 8 warps cover two spans at a time
     switch (mode) {
         case NOISE_COMPAT: noise_kernel<NOISE_COMPAT><<<grid, 256, 0, stream>>>(p); break;

@@ -131,6 +131,32 @@ ROD_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
 }
 
+// Same function with the 10 round keys precomputed (rk[2i] = k0 + i * 0x9E3779B9, rk[2i+1] = k1 + i * 0xBB67AE85):
+// in a kernel the keys are launch parameters, i.e. constant-bank operands of the XORs, and the per-round key
+// additions disappear from the instruction stream.
+struct PhiloxKeys {
+    uint32_t rk[20];
+};
+inline PhiloxKeys philox_round_keys(uint32_t k0, uint32_t k1) {
+    PhiloxKeys ks;
+    for (int i = 0; i < 10; ++i) {
+        ks.rk[2 * i] = k0 + (uint32_t)i * 0x9E3779B9u;
+        ks.rk[2 * i + 1] = k1 + (uint32_t)i * 0xBB67AE85u;
+    }
+    return ks;
+}
+ROD_HD void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& ks, uint32_t r[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ ks.rk[2 * i];
+        uint32_t n2 = hi0 ^ c3 ^ ks.rk[2 * i + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+
 // Philox-mode noise (rod_noise_u8 with noise == NULL).  One Philox block r[4] serves the GROUP of 8
 // consecutive elements e = 8g .. 8g+7 of an image (counter = (g, image lo, image hi, offset), key = seed);
 // word r[p] makes the Box-Muller pair (8g + 2p, 8g + 2p + 1):
@@ -152,33 +178,35 @@ ROD_HD bool philox_needs_tail(const uint32_t r[4]) {
     m = m < m2 ? m : m2;
     return m < 0x10000u;
 }
+// One Box-Muller pair from the word rw; tw is the tail word (used only when use_tail and rw < 2^16).
+ROD_HD void gauss2(uint32_t rw, bool use_tail, uint32_t tw, float* s0, float* s1) {
+#if defined(__CUDA_ARCH__)
+    // 2^23 + hi16 and 2^23 + lo16 assembled by byte permutes (no I2F)
+    const float xh = bitsf(__byte_perm(rw, 0x4B000000u, 0x7432));
+    const float xl = bitsf(__byte_perm(rw, 0x4B000000u, 0x7410));
+    float u = fmaf(xh, 1.52587890625e-05f, -127.99999237060546875f);  // (hi16 + 0.5) * 2^-16, exact
+    if (use_tail && rw < 0x10000u) u = fmaf((float)tw, 3.5527136788005009e-15f, 1.7763568394002505e-15f);
+    float l2, rad;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-l2));
+    const float th = fmaf(xl, ROD_ANGLE_SCALE, ROD_ANGLE_BIAS);
+    *s0 = rad * __cosf(th);
+    *s1 = rad * __sinf(th);
+#else
+    double u = ((double)(rw >> 16) + 0.5) * 1.52587890625e-05;
+    if (use_tail && rw < 0x10000u) u = ((double)tw + 0.5) * 3.5527136788005009e-15;
+    const double rad = sqrt(-log2(u));
+    const double th = (8388608.0 + (double)(rw & 0xFFFFu)) * (double)ROD_ANGLE_SCALE + (double)ROD_ANGLE_BIAS;
+    *s0 = (float)(rad * cos(th));
+    *s1 = (float)(rad * sin(th));
+#endif
+}
 // t may be NULL when !philox_needs_tail(r).
 ROD_HD void gauss8(const uint32_t r[4], const uint32_t* t, float s[8]) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        // 2^23 + hi16 and 2^23 + lo16 assembled by byte permutes (no I2F)
-        const float xh = bitsf(__byte_perm(r[p], 0x4B000000u, 0x7432));
-        const float xl = bitsf(__byte_perm(r[p], 0x4B000000u, 0x7410));
-        float u = fmaf(xh, 1.52587890625e-05f, -127.99999237060546875f);  // (hi16 + 0.5) * 2^-16, exact
-        if (t != nullptr && r[p] < 0x10000u) u = fmaf((float)t[p], 3.5527136788005009e-15f, 1.7763568394002505e-15f);
-        float l2, rad;
-        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-l2));
-        const float th = fmaf(xl, ROD_ANGLE_SCALE, ROD_ANGLE_BIAS);
-        s[2 * p] = rad * __cosf(th);
-        s[2 * p + 1] = rad * __sinf(th);
-    }
-#else
-    for (int p = 0; p < 4; ++p) {
-        double u = ((double)(r[p] >> 16) + 0.5) * 1.52587890625e-05;
-        if (t != nullptr && r[p] < 0x10000u) u = ((double)t[p] + 0.5) * 3.5527136788005009e-15;
-        const double rad = sqrt(-log2(u));
-        const double th = (8388608.0 + (double)(r[p] & 0xFFFFu)) * (double)ROD_ANGLE_SCALE + (double)ROD_ANGLE_BIAS;
-        s[2 * p] = (float)(rad * cos(th));
-        s[2 * p + 1] = (float)(rad * sin(th));
-    }
 #endif
+    for (int p = 0; p < 4; ++p) gauss2(r[p], t != nullptr, t != nullptr ? t[p] : 0u, &s[2 * p], &s[2 * p + 1]);
 }
 // int16 floor(K * s) in the low half of the result (two's complement), valid for |K s| < 32768:
 // fma rounded toward -inf onto the integer grid of [2^23, 2^24) (1.5 * 2^23 keeps negatives in the binade).
@@ -202,6 +230,79 @@ __device__ __forceinline__ uint32_t philox_word(uint32_t word, const float* s, f
 #endif
 ROD_HD uint32_t noise_philox_px(uint32_t v, float s, float K) {
     int x = (int)v + (int)(int16_t)(noise_floor16(s, K) & 0xFFFFu);
+    return (uint32_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
+}
+
+// Philox-mode noise, TABLE generator (noise.cu noise_table_kernel; used when sigma <= ROD_GAUSS_TABLE_MAX_SIGMA).
+// The same Philox block r[4] of group g, but each 16-bit half is one inverse-CDF draw instead of half a
+// Box-Muller pair: element 8g + 2p takes h = r[p] & 0xffff, element 8g + 2p + 1 takes h = r[p] >> 16, and
+//   h in 1..65535 : k = T[h] = floor(sigma * Phi^-1(h / 65536))      (65535 equiprobable strata of |z| < 4.30,
+//                                                                       T is a 64 KB int8 table in shared memory)
+//   h == 0        : (probability 2^-16 = the two-sided tail mass beyond the table) k = floor(+-sigma z),
+//                   z = -Phi^-1((m + 0.5) * 2^-48), m = w >> 1, sign = w & 1, w = t[p] (even element) or
+//                   rotl(t[p], 16) (odd element), t = the Philox block at counter (g, image lo, image hi ^ 0x80000000,
+//                   offset) -> reaches 8.1 sigma
+//   out = clamp(v + k, 0, 255)   (k is floor(noise), so this is the reference's truncation of the clipped sum).
+// One shared-memory byte load per element replaces the four MUFU operations per Box-Muller pair.
+#define ROD_GAUSS_TABLE_MAX_SIGMA 29.0f  // floor(sigma * 4.30) must fit int8
+#ifndef ROD_GAUSS_AUTO
+#define ROD_GAUSS_AUTO 0                 // table generator when sigma <= ROD_GAUSS_TABLE_MAX_SIGMA, else Box-Muller
+#define ROD_GAUSS_BOXMULLER 1
+#endif
+
+// Phi^-1 in double (Acklam's rational start + Halley steps on erfc): host only (table builder, emu harness).
+inline double ndtri_double(double p) {
+    if (p > 0.5) return -ndtri_double(1.0 - p);
+    static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                               1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                               6.680131188771972e+01, -1.328068155288572e+01};
+    static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                               -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+    static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                               3.754408661907416e+00};
+    double x;
+    if (p < 0.02425) {
+        const double q = sqrt(-2.0 * log(p));
+        x = (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+            ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
+    } else {
+        const double q = p - 0.5, r = q * q;
+        x = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+            (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1.0);
+    }
+    for (int it = 0; it < 3; ++it) {
+        const double e = 0.5 * erfc(-x * 0.70710678118654752440) - p;
+        const double u = e * 2.50662827463100050242 * exp(0.5 * x * x);
+        x -= u / (1.0 + 0.5 * x * u);
+    }
+    return x;
+}
+
+// The rare branch: tail draw from the 32-bit word w (see above).
+ROD_HD int gauss_tail_k(uint32_t w, float sigma) {
+#if defined(__CUDA_ARCH__)
+    // fp32: ln p = ln((m + 0.5) 2^-31) - 17 ln 2; Acklam's lower-region rational (|rel err| < 1.2e-9) gives -z
+    const float u = fmaf((float)(w >> 1), 4.656612873077393e-10f, 2.3283064365386963e-10f);
+    const float q = sqrtf(-2.0f * (logf(u) - 11.7835020695190700f));
+    const float num = fmaf(fmaf(fmaf(fmaf(fmaf(-7.784894002430293e-03f, q, -3.223964580411365e-01f), q,
+                                          -2.400758277161838e+00f), q, -2.549732539343734e+00f), q,
+                                4.374664141464968e+00f), q, 2.938163982698783e+00f);
+    const float den = fmaf(fmaf(fmaf(fmaf(7.784695709041462e-03f, q, 3.224671290700398e-01f), q,
+                                     2.445134137142996e+00f), q, 3.754408661907416e+00f), q, 1.0f);
+    const float z = -num / den;  // > 0
+    return (int)floorf((w & 1u) ? -sigma * z : sigma * z);
+#else
+    const double z = -ndtri_double(((double)(w >> 1) + 0.5) * 3.5527136788005009e-15);  // 2^-48
+    return (int)floor((w & 1u) ? -(double)sigma * z : (double)sigma * z);
+#endif
+}
+ROD_HD uint32_t gauss_tail_word(const uint32_t t[4], int j) {  // j = element inside the group, 0..7
+    const uint32_t w = t[j >> 1];
+    return (j & 1) ? ((w << 16) | (w >> 16)) : w;
+}
+ROD_HD uint32_t noise_table_px(uint32_t v, int k) {
+    const int x = (int)v + k;
     return (uint32_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
 }
 

@@ -72,6 +72,7 @@ struct rod_plan {
     unsigned int* d_counters = nullptr;  // ring of 256 work counters for dynamically scheduled kernels (one per launch)
     mutable unsigned int launch_seq = 0;
     bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
+    int gauss_generator = ROD_GAUSS_AUTO;  // Philox-mode Gaussian generator (rod_plan_set_gaussian_generator)
 
     // lowres tables, rebuilt when the factor changes
     double lowres_factor = -1.0;
@@ -132,7 +133,8 @@ int grid_for(const rod_plan* plan, int n_tiles, int ctas_per_sm);
 // kernel launchers (one per .cu)
 int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* dst, const float* noise,
                  float* field_out, float sigma, uint64_t seed, uint64_t first_image, uint32_t offset,
-                 const uint8_t* opcodes, int my_op, cudaStream_t stream, int img_lo, int img_hi);
+                 const uint8_t* opcodes, int my_op, cudaStream_t stream, int img_lo, int img_hi,
+                 int generator = -1 /* -1: plan->gauss_generator */);
 int launch_blur(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, const uint8_t* opcodes,
                 cudaStream_t stream, int img_lo, int img_hi);
 int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,

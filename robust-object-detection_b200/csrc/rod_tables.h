@@ -229,6 +229,13 @@ inline void letterbox_geometry(int h, int w, int out_h, int out_w, int* new_h, i
 }
 
 // Tile lists ---------------------------------------------------------------------------
+// Inverse-CDF table of the Philox TABLE generator (rod_core.h): T[h] = floor(sigma * Phi^-1(h / 65536)), h = 1..65535
+// (T[0] is the tail sentinel, unused).  sigma <= ROD_GAUSS_TABLE_MAX_SIGMA keeps every entry inside int8.
+inline void build_gauss_table(float sigma, int8_t* tab) {
+    tab[0] = 0;
+    for (int h = 1; h < 65536; ++h) tab[h] = (int8_t)floor((double)sigma * ndtri_double((double)h / 65536.0));
+}
+
 inline void build_noise_tiles(const std::vector<DevImage>& imgs, int span, std::vector<Tile>& tiles) {
     for (int i = 0; i < (int)imgs.size(); ++i) {
         const DevImage& im = imgs[i];

@@ -198,36 +198,78 @@ def test_ultralytics_patch_with_stub_module(aug, golden_hashes, monkeypatch):
 
 # ------------------------------------------------------------------ Philox mode
 def test_philox_field_and_fused_output(torch_):
+    """Both Gaussian generators of Philox mode against their restated streams: the table generator (default at
+    sigma <= 29) is integer-valued and matches exactly; Box-Muller (forced per plan, or sigma > 29) within float
+    tolerance."""
     from robust_object_detection_b200.batch import CorruptionPlan
     shapes = [(37, 53), (64, 64), (31, 45)]
     plan = CorruptionPlan.ragged(shapes)
     imgs = [synth(50 + i, h, w) for i, (h, w) in enumerate(shapes)]
     src = torch_.from_numpy(plan.pack(imgs)).cuda()
-    dst = torch_.zeros_like(src)
-    field = torch_.zeros(plan.payload_bytes, dtype=torch_.float32, device="cuda")
     seed, first, off = 0x1234567890ABCDEF, 5, 3
-    plan.noise_field(field, 15.0, seed, first, off)
-    plan.noise(src, dst, None, 15.0, seed, first, off)
-    f = field.cpu().numpy()
-    outs = plan.unpack(dst.cpu().numpy())
-    e = 0
-    for i, (img, (h, w)) in enumerate(zip(imgs, shapes)):
-        n = 3 * h * w
-        want = orc.philox_noise_field(n, 15.0, seed, first + i, off)
-        assert np.max(np.abs(f[e:e + n] - want)) < 2e-3, i
-        # the fused kernel adds the field it reports: clamp(v + floor(noise), 0, 255); the dumped field is the
-        # fp32-rounded product, the kernel floors the unrounded one, so a byte may differ only where noise is
-        # within an ulp of an integer
-        mism = outs[i] != orc.add_philox_noise(img, f[e:e + n])
-        assert mism.mean() < 1e-4, i
-        assert np.abs(outs[i].astype(int) - orc.add_philox_noise(img, want)).max() <= 1 and \
-            (outs[i] != orc.add_philox_noise(img, want)).mean() < 1e-3, i
-        e += n
-    # compat path on the dumped field (device-resident supplied-noise mode) agrees up to the reference's
-    # float32 rounding of v + noise
-    dst2 = torch_.zeros_like(src)
-    plan.noise(src, dst2, field, 15.0)
-    assert (dst != dst2).float().mean().item() < 1e-4
+    for generator, sigma in (("table", 15.0), ("table", 4.5), ("boxmuller", 15.0), ("auto-boxmuller", 40.0)):
+        plan.set_gaussian_generator(1 if generator == "boxmuller" else 0)
+        dst = torch_.zeros_like(src)
+        field = torch_.zeros(plan.payload_bytes, dtype=torch_.float32, device="cuda")
+        plan.noise_field(field, sigma, seed, first, off)
+        plan.noise(src, dst, None, sigma, seed, first, off)
+        f = field.cpu().numpy()
+        outs = plan.unpack(dst.cpu().numpy())
+        e = 0
+        for i, (img, (h, w)) in enumerate(zip(imgs, shapes)):
+            n = 3 * h * w
+            if generator == "table":
+                want = orc.philox_noise_field(n, sigma, seed, first + i, off)     # auto -> table
+                assert np.array_equal(f[e:e + n].astype(np.float64), want), (generator, sigma, i)
+                assert np.array_equal(outs[i], orc.add_philox_noise(img, want)), (generator, sigma, i)
+            else:
+                want = orc.philox_noise_field(n, sigma, seed, first + i, off, generator="boxmuller")
+                assert np.max(np.abs(f[e:e + n] - want)) < 2e-3 * sigma / 15.0, (generator, i)
+                # the kernel adds the field it reports: clamp(v + floor(noise), 0, 255); the dumped field is the
+                # fp32-rounded product, the kernel floors the unrounded one, so a byte may differ only where noise
+                # is within an ulp of an integer
+                assert (outs[i] != orc.add_philox_noise(img, f[e:e + n])).mean() < 1e-4, (generator, i)
+                assert np.abs(outs[i].astype(int) - orc.add_philox_noise(img, want)).max() <= 1 and \
+                    (outs[i] != orc.add_philox_noise(img, want)).mean() < 1e-3, (generator, i)
+            e += n
+        # compat path on the dumped field (device-resident supplied-noise mode) agrees up to the reference's
+        # float32 rounding of v + noise
+        dst2 = torch_.zeros_like(src)
+        plan.noise(src, dst2, field, sigma)
+        assert (dst != dst2).float().mean().item() < 1e-4
+    plan.set_gaussian_generator(0)
+
+
+def test_philox_table_tails_and_unaligned_spans(torch_):
+    """The table generator on a stream long enough to contain tail draws (2^-16 per element; the redo path of the
+    kernel), and on pitched rows / odd widths (the element-wise path): exact against the restated stream except
+    where the fp32 tail formula lands within ~1e-4 of an integer (never observed; bound 1e-6)."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    h, w = 765, 1360
+    plan = CorruptionPlan.uniform(2, h, w)
+    img = np.stack([synth(1234, h, w), synth(1235, h, w)])
+    src = torch_.from_numpy(img).cuda()
+    dst = torch_.empty_like(src)
+    plan.noise(src, dst, None, 15.0, seed=0xC0FFEE, first_image_index=3)
+    out = dst.cpu().numpy()
+    n_tail = 0
+    for i in range(2):
+        want = orc.philox_noise_field(img[i].size, 15.0, 0xC0FFEE, 3 + i)
+        n_tail += int((np.abs(want) > 64).sum())
+        assert np.mean(out[i] != orc.add_philox_noise(img[i], want)) < 1e-6, i
+    assert n_tail > 20      # ~95 expected over 6.2 M elements
+    # odd width + pitched source rows: spans that start off a group boundary / off 16-byte alignment
+    hh, ww = 45, 61
+    big = synth(77, hh + 4, ww + 6)
+    crop = big[2:2 + hh, 3:3 + ww]
+    from robust_object_detection_b200 import augmentations as aug
+    aug.set_noise_mode("philox", seed=31)
+    try:
+        got = aug.apply_noise(crop, 15.0)
+    finally:
+        aug.set_noise_mode("compat")
+    want = orc.philox_noise_field(crop.size, 15.0, 31, 0)
+    assert np.array_equal(got, orc.add_philox_noise(np.ascontiguousarray(crop), want))
 
 
 def test_philox_statistics_and_reproducibility(torch_):
@@ -301,8 +343,8 @@ def test_uniform_batch_all_ops(torch_):
     assert np.array_equal(out[1], imgs[1]) and np.array_equal(out[5], imgs[5])
     assert np.array_equal(out[2], orc.apply_motion_blur(imgs[2], 9, 0))
     assert np.array_equal(out[3], orc.apply_lowres(imgs[3], 0.5))
-    fld = orc.philox_noise_field(imgs[4].size, 15.0, 9, 4)
-    assert np.mean(out[4] != orc.add_philox_noise(imgs[4], fld)) < 1e-3  # float-vs-double field at .0 boundaries
+    fld = orc.philox_noise_field(imgs[4].size, 15.0, 9, 4)   # table generator: integer-valued, exact
+    assert np.mean(out[4] != orc.add_philox_noise(imgs[4], fld)) < 1e-6
 
 
 CONFIG3_SHAPES = [(765, 1360), (1050, 1400), (788, 1400), (1078, 1916), (1080, 1920), (1500, 2000), (540, 960),
@@ -440,7 +482,7 @@ def test_fused_letterbox_kernel_paths(torch_):
     for i, img in enumerate(imgs):
         op = int(ops_host[i])
         if op == 1:
-            want = orc.letterbox_norm_f16(orc.add_philox_noise(img, orc.philox_noise_field(img.size, 15.0, 77, 1000 + i)), 320, 320, 114)
+            want = orc.letterbox_norm_f16(orc.add_philox_noise(img, orc.philox_noise_field(img.size, 15.0, 77, 1000 + i, generator="boxmuller")), 320, 320, 114)
             assert np.mean(got[i] != want) < 2e-3, (i, shapes[i])
         else:
             cor = orc.apply_motion_blur(img, 5, 0) if op == 2 else orc.apply_op(img, op)
@@ -552,7 +594,7 @@ def test_training_batcher_pinned_pipeline(torch_):
     got = np.concatenate(outs)
     for i, (img, op) in enumerate(zip(frames, ops)):
         if op == 1:
-            cor = orc.add_philox_noise(img, orc.philox_noise_field(img.size, 15.0, 9, i))
+            cor = orc.add_philox_noise(img, orc.philox_noise_field(img.size, 15.0, 9, i, generator="boxmuller"))
         else:
             cor = orc.apply_op(img, op)
         want = orc.letterbox_norm_f16(cor, 160, 160)
