@@ -103,29 +103,28 @@ _ANGLE_SCALE = float(np.float32(9.58737992428525768e-05))  # float32(2 pi / 6553
 _ANGLE_BIAS = float(np.float32(-804.2476806640625))        # float32((0.5 - 2^23) * 2 pi / 65536)
 
 
-GAUSS_TABLE_MAX_SIGMA = 29.0   # rod_core.h ROD_GAUSS_TABLE_MAX_SIGMA
+GAUSS_TABLE_MAX_SIGMA = 21.0   # rod_core.h ROD_GAUSS_TABLE_MAX_SIGMA
+GAUSS_TABLE_BIAS = 16384
 
 
 def gauss_table(sigma: float) -> np.ndarray:
-    """int64[65536]: T[h] = floor(float64(float32(sigma)) * Phi^-1(h / 65536)), h = 1..65535; T[0] unused
-    (rod_tables.h build_gauss_table).  scipy's ndtri is the independent inverse normal CDF here."""
+    """int64[32768]: A[i] = round(256 * (float32(sigma) / sqrt 2) * Phi^-1((i + 0.5) / 32768)) + 16384, the biased
+    15-bit stratified quantile table of N(0, sigma^2 / 2) in 1/256 units (rod_tables.h build_gauss_table).
+    scipy's ndtri is the independent inverse normal CDF here."""
     from scipy.special import ndtri
-    t = np.zeros(65536, dtype=np.int64)
-    h = np.arange(1, 65536, dtype=np.float64)
-    t[1:] = np.floor(float(np.float32(sigma)) * ndtri(h / 65536.0)).astype(np.int64)
-    return t
+    scale = 256.0 * (float(np.float32(sigma)) / np.sqrt(2.0))
+    i = np.arange(32768, dtype=np.float64)
+    return np.floor(scale * ndtri((i + 0.5) / 32768.0) + 0.5).astype(np.int64) + GAUSS_TABLE_BIAS
 
 
 def philox_noise_field_table(n_elems: int, sigma: float, seed: int, image_index: int,
                              offset: int = 0) -> np.ndarray:
-    """float64 restatement of the TABLE generator of Philox mode (rod_core.h / noise.cu noise_table_kernel),
-    the default for sigma <= 29.  Same Philox blocks as the Box-Muller generator below, but every 16-bit half is
-    one inverse-CDF draw: element 8g + 2p takes h = r_p & 0xffff, element 8g + 2p + 1 takes h = r_p >> 16;
-      h != 0: k = T[h]                                       (65535 equiprobable strata of |z| < 4.30)
-      h == 0: w = t_p (even element) or rotl(t_p, 16) (odd), t = Philox block at ctr[2] ^ 0x80000000;
-              z = -Phi^-1(((w >> 1) + 0.5) * 2^-48); k = floor(-sigma z) if w & 1 else floor(sigma z)
-    Returns k as float64 (already an integer: add_philox_noise's floor is then the identity)."""
-    from scipy.special import ndtri
+    """Restatement of the TABLE generator of Philox mode (rod_core.h / noise.cu noise_table_kernel), the default
+    for sigma <= 21.  Same Philox blocks as the Box-Muller generator below, integer arithmetic only: word r_p of group
+    g gives two 15-bit draws a = A[(r_p & 0xffff) >> 1], b = A[r_p >> 17] and the 45-degree rotation of the pair
+      element 8g + 2p     : k = ((a + b) >> 8) - 128                = floor((x + y) / 256)
+      element 8g + 2p + 1 : k = ((a - b + 32768) >> 8) - 128        = floor((x - y) / 256)
+    (x, y the unbiased draws).  Returns k as float64 (an integer: add_philox_noise's floor is then the identity)."""
     n_groups = (n_elems + 7) // 8
     g = np.arange(n_groups, dtype=np.uint64)
     ctr = np.empty((n_groups, 4), dtype=np.uint32)
@@ -134,31 +133,20 @@ def philox_noise_field_table(n_elems: int, sigma: float, seed: int, image_index:
     ctr[:, 2] = np.uint32((image_index >> 32) & 0xFFFFFFFF)
     ctr[:, 3] = np.uint32(offset & 0xFFFFFFFF)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
-    r = philox4x32_10(ctr, key)
-    ctr_t = ctr.copy()
-    ctr_t[:, 2] ^= np.uint32(_PHILOX_TAIL_FLIP)
+    r = philox4x32_10(ctr, key).astype(np.int64)
     tab = gauss_table(sigma)
-    sig = float(np.float32(sigma))
+    a = tab[(r & 0xFFFF) >> 1]
+    b = tab[r >> 17]
     k = np.empty((n_groups, 8), dtype=np.float64)
-    h = np.empty((n_groups, 8), dtype=np.int64)
-    for p_ in range(4):
-        h[:, 2 * p_] = (r[:, p_] & np.uint32(0xFFFF)).astype(np.int64)
-        h[:, 2 * p_ + 1] = (r[:, p_] >> np.uint32(16)).astype(np.int64)
-    k[:] = tab[h]
-    rows, cols = np.nonzero(h == 0)
-    if rows.size:
-        t = philox4x32_10(ctr_t[rows], key).astype(np.uint64)
-        w = t[np.arange(rows.size), cols >> 1]
-        w = np.where(cols & 1, ((w << np.uint64(16)) | (w >> np.uint64(16))) & np.uint64(0xFFFFFFFF), w)
-        z = -ndtri(((w >> np.uint64(1)).astype(np.float64) + 0.5) * 2.0 ** -48)
-        k[rows, cols] = np.floor(np.where(w & np.uint64(1), -sig * z, sig * z))
+    k[:, 0::2] = ((a + b) >> 8) - 128
+    k[:, 1::2] = ((a - b + 32768) >> 8) - 128
     return k.reshape(-1)[:n_elems]
 
 
 def philox_noise_field(n_elems: int, sigma: float, seed: int, image_index: int,
                        offset: int = 0, generator: str = "auto") -> np.ndarray:
     """The field Philox mode adds: generator "auto" (what rod_noise_u8 / rod_corrupt_batch_u8 use: the table
-    generator for sigma <= 29, else Box-Muller), "table", or "boxmuller" (always used by the training path,
+    generator for sigma <= 21, else Box-Muller), "table", or "boxmuller" (always used by the training path,
     rod_corrupt_letterbox_f16)."""
     if generator == "table" or (generator == "auto" and float(np.float32(sigma)) <= GAUSS_TABLE_MAX_SIGMA):
         return philox_noise_field_table(n_elems, sigma, seed, image_index, offset)

@@ -4,8 +4,8 @@
 //   NOISE_COMPAT  a supplied float32 tensor (what np.random.normal(...).astype(f32) drew) -> bit-exact
 //   NOISE_PHILOX  Philox4x32-10 keyed by (seed, global image index, element/8, offset), no HBM traffic for
 //                 the field; two Gaussian generators on the same Philox blocks (rod_core.h):
-//                   table      (sigma <= 29, noise_table_kernel): one shared-memory lookup per element in a
-//                              64 KB inverse-CDF table of floor(sigma z) -- no MUFU, ~10 instructions per byte
+//                   table      (sigma <= 21, noise_table_kernel): two 15-bit draws from a 64 KB shared-memory quantile
+//                              table per Philox word, rotated by 45 degrees in integer arithmetic -- no MUFU
 //                   Box-Muller (any sigma <= 2048, noise_kernel<NOISE_PHILOX>): 4 MUFU per pair, XU-pipe bound
 // plus NOISE_COPY (ROD_OP_NONE images of a mixed batch) and NOISE_FIELD (dump the Philox field).
 //
@@ -38,8 +38,8 @@ struct NoiseParams {
     const uint8_t* opcodes;
     int my_op;
     unsigned int* counter;  // zeroed before the launch
-    uint32_t two16;         // 65536 (see group_table8)
-    const int8_t* table;    // table generator: 65536 x int8 floor(sigma z) (device global; staged in shared memory)
+    uint32_t two15;         // 32768 (see group_table8)
+    const uint16_t* table;  // table generator: 32768 x uint16 quantiles (device global; staged in shared memory)
 };
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
@@ -218,15 +218,14 @@ __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
 // ---------------------------------------------------------------------------------------------------
 // Table generator (rod_core.h): k[0..7] of group g.  `tab` is the CTA's shared-memory copy of the table.
 // ---------------------------------------------------------------------------------------------------
-// Shared-memory layout of the table kernel: the 64 KB table sits at a 64 KB-ALIGNED shared address `tbase`, so
-// the address of a draw is one instruction per element: (r & 0xffff) | tbase (LOP3) for the low half and
-// hi(r * 2^16) + tbase (IMAD.HI, FMA pipe) for the high half.  Entries are stored biased, kb = k + 128 (uint8), so
-// two of them pack into an int16 pair with one IMAD; the pixel side carries the -128 (prmt sign replication).
+// Shared-memory layout of the table kernel: the 64 KB table (32768 x uint16) sits at a 64 KB-ALIGNED shared address
+// `tbase`, so the address of the first draw of a word is one instruction, (r & 0xfffe) | tbase (LOP3); the second is
+// (r >> 17) * 2 + tbase as two integer multiply-adds on the FMA pipe (the ALU pipe is the busy one in this kernel).
 constexpr uint32_t kTabSmemBytes = 65536u + 65536u;  // table + slack to reach the next 64 KB boundary
 
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint32_t v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -235,45 +234,35 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return d;
 }
 
-// f[i] = int16 pair (kb[2i], kb[2i+1]) of group g, kb = k + 128.  Half 0 of a word is a tail draw (2^-16 per element);
-// its table entry is the sentinel kb = 0 (real entries lie in [3, 253]), so the returned products -- the four
-// entries of two words multiplied together on the FMA pipe, < 2^32 -- are zero exactly when the group has one.  The
-// caller then redoes the group with table_group_slow after its loop, so the hot loop contains no call.
+// f[q] = int16 pair (k + 128 of element 2q, k + 128 of element 2q + 1) of group g (rod_core.h gauss_pair_packed).
 __device__ __forceinline__ void group_table8(uint32_t tbase, const NoiseParams& p, uint32_t ig_lo, uint32_t ig_hi,
-                                             uint32_t g, uint32_t f[4], uint32_t* z01, uint32_t* z23) {
+                                             uint32_t g, uint32_t f[4]) {
     uint32_t r[4];
     philox4x32_10_rk(g, ig_lo, ig_hi, p.offset, p.keys, r);
-    uint32_t z[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        uint32_t alo, ahi;
-        asm("lop3.b32 %0, %1, 65535, %2, 0xEA;" : "=r"(alo) : "r"(r[q]), "r"(tbase));  // (r & 0xffff) | tbase
-        // 65536 comes from the parameter block so ptxas keeps the IMAD.HI (a literal power of two turns into LEA.HI, ALU pipe)
-        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(ahi) : "r"(r[q]), "r"(p.two16), "r"(tbase));
-        const uint32_t khi = lds_u8(ahi), klo = lds_u8(alo);
-        f[q] = khi * 65536u + klo;
-        z[q] = khi * klo;
+        uint32_t alo, ihi;
+        asm("lop3.b32 %0, %1, 0xFFFE, %2, 0xEA;" : "=r"(alo) : "r"(r[q]), "r"(tbase));  // (r & 0xfffe) | tbase
+        // 2^15 comes from the parameter block so ptxas keeps the IMAD.HI (a literal power of two becomes a shift, ALU pipe)
+        asm("mad.hi.u32 %0, %1, %2, 0;" : "=r"(ihi) : "r"(r[q]), "r"(p.two15));          // r >> 17
+        const uint32_t a = lds_u16(alo), b = lds_u16(ihi * 2u + tbase);
+        f[q] = prmt(gauss_pair_packed(a, b), 0u, 0x4341u);  // bytes 1 and 3 -> the two halves
     }
-    *z01 = z[0] * z[1];
-    *z23 = z[2] * z[3];
 }
 
-// One group, element by element, restricted to the absolute element range [ea, eb), with the tail draws: the
-// remainder of unaligned spans and the redo of groups that group_table8 flagged.  e0 = element index of s[0] / d[0].
+// One group, element by element, restricted to the absolute element range [ea, eb): the remainder of spans whose
+// start is not on a group boundary / not 16-byte aligned (pitched rows).  e0 = element index of s[0] / d[0].
 template <int MODE>
 __device__ __noinline__ void table_group_slow(const NoiseParams& p, uint32_t tbase, uint32_t ig_lo, uint32_t ig_hi,
                                               uint32_t g, uint32_t e0, uint32_t ea, uint32_t eb, const uint8_t* s,
                                               uint8_t* d, float* fout) {
     uint32_t r[4];
     philox4x32_10_rk(g, ig_lo, ig_hi, p.offset, p.keys, r);
-    uint32_t t[4];
-    philox4x32_10_rk(g, ig_lo, ig_hi ^ ROD_PHILOX_TAIL_FLIP, p.offset, p.keys, t);
     for (int j = 0; j < 8; ++j) {
         const uint32_t e = 8u * g + j;
         if (e < ea || e >= eb) continue;
         const uint32_t w = r[j >> 1];
-        const uint32_t h = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
-        const int k = h != 0u ? (int)lds_u8(tbase + h) - 128 : gauss_tail_k(gauss_tail_word(t, j), p.sigma);
+        const int k = gauss_pair_k(lds_u16(tbase + (w & 0xFFFEu)), lds_u16(tbase + 2u * (w >> 17)), j & 1);
         const uint32_t rel = e - e0;
         if (MODE == NOISE_FIELD) fout[rel] = (float)k;
         else d[rel] = (uint8_t)noise_table_px(s[rel], k);
@@ -294,7 +283,7 @@ __device__ __forceinline__ uint32_t table_word(uint32_t word, uint32_t f01, uint
 
 // Same work hand-out as noise_kernel (warps take quarter spans from a shared counter); the CTA first stages the
 // 64 KB table in shared memory (from L2 after the first CTA of the launch).  MODE: NOISE_PHILOX or NOISE_FIELD.
-template <int MODE, int THREADS>
+template <int MODE, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS, 1) noise_table_kernel(NoiseParams p) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(s_raw) + 0xFFFFu) & ~0xFFFFu;
@@ -345,16 +334,14 @@ __global__ void __launch_bounds__(THREADS, 1) noise_table_kernel(NoiseParams p) 
         if (MODE != NOISE_FIELD) vec = vec && ((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0;
         if (MODE == NOISE_FIELD) vec = vec && (((uintptr_t)fout) & 15) == 0;
         const uint32_t nvec = vec ? (n >> 4) : 0;
-        uint32_t redo = 0;  // bit `step`: this lane's step has a tail draw and goes through the slow path (<= 8 steps per piece)
-#pragma unroll 2
-        for (uint32_t i = lane, bit = 1u; i < nvec; i += 32u, bit <<= 1) {
+#pragma unroll UNROLL
+        for (uint32_t i = lane; i < nvec; i += 32u) {
             const uint32_t e = 16u * i;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (MODE != NOISE_FIELD) v = ldg_stream16(s + e);
-            uint32_t fa[4], fb[4], za, zb, zc, zd;
-            group_table8(tbase, p, ig_lo, ig_hi, (e0 + e) >> 3, fa, &za, &zb);
-            group_table8(tbase, p, ig_lo, ig_hi, ((e0 + e) >> 3) + 1u, fb, &zc, &zd);
-            if (min(min(za, zb), min(zc, zd)) == 0u) redo |= bit;
+            uint32_t fa[4], fb[4];
+            group_table8(tbase, p, ig_lo, ig_hi, (e0 + e) >> 3, fa);
+            group_table8(tbase, p, ig_lo, ig_hi, ((e0 + e) >> 3) + 1u, fb);
             if (MODE == NOISE_FIELD) {
                 float4* fo = reinterpret_cast<float4*>(fout + e);
                 fo[0] = make_float4((float)table_k(fa, 0), (float)table_k(fa, 1), (float)table_k(fa, 2), (float)table_k(fa, 3));
@@ -365,13 +352,6 @@ __global__ void __launch_bounds__(THREADS, 1) noise_table_kernel(NoiseParams p) 
                 stg16(d + e, make_uint4(table_word(v.x, fa[0], fa[1]), table_word(v.y, fa[2], fa[3]),
                                         table_word(v.z, fb[0], fb[1]), table_word(v.w, fb[2], fb[3])));
             }
-        }
-        while (redo != 0u) {  // rare: rewrite the flagged steps element by element (this lane wrote them itself)
-            const uint32_t b = (uint32_t)__ffs((int)redo) - 1u;
-            redo &= redo - 1u;
-            const uint32_t g = (e0 + 16u * (lane + 32u * b)) >> 3;
-            table_group_slow<MODE>(p, tbase, ig_lo, ig_hi, g, e0, 8u * g, 8u * g + 8u, s, d, fout);
-            table_group_slow<MODE>(p, tbase, ig_lo, ig_hi, g + 1u, e0, 8u * g + 8u, 8u * g + 16u, s, d, fout);
         }
         // remainder (and the whole span when unaligned): one Philox group (<= 8 elements) per thread step
         const uint32_t r0 = nvec << 4;
@@ -384,26 +364,24 @@ __global__ void __launch_bounds__(THREADS, 1) noise_table_kernel(NoiseParams p) 
     }
 }
 
-// Device copies of the inverse-CDF table, one per (device, sigma), built on first use (synchronous upload: the
-// first Philox launch with a new sigma must not happen inside a stream capture).
+// Device copies of the quantile table, one per (device, sigma), built on first use (synchronous upload: the first
+// Philox launch with a new sigma must not happen inside a stream capture).
 struct GaussTable {
     int device;
     uint32_t sigma_bits;
-    int8_t* d_tab;
+    uint16_t* d_tab;
 };
 static std::mutex g_tab_mutex;
 static std::vector<GaussTable> g_tabs;
 
-static int gauss_table_for(int device, float sigma, const int8_t** out) {
+static int gauss_table_for(int device, float sigma, const uint16_t** out) {
     std::lock_guard<std::mutex> lock(g_tab_mutex);
     const uint32_t bits = fbits(sigma);
     for (const GaussTable& t : g_tabs)
         if (t.device == device && t.sigma_bits == bits) { *out = t.d_tab; return ROD_OK; }
-    std::vector<int8_t> h(65536);
+    std::vector<uint16_t> h(32768);
     build_gauss_table(sigma, h.data());
-    for (auto& b : h) b = (int8_t)(uint8_t)((int)b + 128);  // stored biased: kb = k + 128
-    h[0] = 0;                                                // the tail sentinel (real entries are >= 3)
-    int8_t* d = nullptr;
+    uint16_t* d = nullptr;
     ROD_CUDA(cudaMalloc(&d, 65536));
     cudaError_t e = cudaMemcpy(d, h.data(), 65536, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e); }
@@ -431,7 +409,7 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
     p.offset = offset;
     p.opcodes = opcodes; p.my_op = my_op;
     p.table = nullptr;
-    p.two16 = 65536u;
+    p.two15 = 32768u;
     p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
     ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     int per_sm = 4;  // CTAs per SM the grid is sized for: 4 are resident, a longer queue evens out the tail (knob: ROD_NOISE_CTAS)
@@ -441,17 +419,21 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
         int rc = gauss_table_for(plan->device, sigma, &p.table);
         if (rc != ROD_OK) return rc;
         // one 1024-thread CTA per SM, each with its own copy of the table; warps take quarter spans
-        const int ctas = grid_for(plan, (p.n_tiles * 4 + 23) / 24, 1);
-        static const int nthr = [] { const char* e = getenv("ROD_NOISE_THREADS"); return e ? atoi(e) : 768; }();
-#define ROD_TAB_LAUNCH(M, TH)                                                                                              \
+        const int ctas = grid_for(plan, (p.n_tiles * 4 + 31) / 32, 1);
+        static const int nthr = [] { const char* e = getenv("ROD_NOISE_THREADS"); return e ? atoi(e) : 1024; }();
+        static const int unr = [] { const char* e = getenv("ROD_NOISE_UNROLL"); return e ? atoi(e) : 2; }();
+#define ROD_TAB_LAUNCH(M, TH, UN)                                                                                          \
     do {                                                                                                                   \
-        ROD_CUDA(cudaFuncSetAttribute(noise_table_kernel<M, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmemBytes)); \
-        noise_table_kernel<M, TH><<<ctas, TH, kTabSmemBytes, stream>>>(p);                                                 \
+        ROD_CUDA(cudaFuncSetAttribute(noise_table_kernel<M, TH, UN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmemBytes)); \
+        noise_table_kernel<M, TH, UN><<<ctas, TH, kTabSmemBytes, stream>>>(p);                                             \
     } while (0)
-        if (mode == NOISE_FIELD) ROD_TAB_LAUNCH(NOISE_FIELD, 768);
-        else if (nthr == 1024) ROD_TAB_LAUNCH(NOISE_PHILOX, 1024);
-        else if (nthr == 896) ROD_TAB_LAUNCH(NOISE_PHILOX, 896);
-        else ROD_TAB_LAUNCH(NOISE_PHILOX, 768);
+        if (mode == NOISE_FIELD) ROD_TAB_LAUNCH(NOISE_FIELD, 1024, 2);
+        else if (nthr == 768 && unr == 1) ROD_TAB_LAUNCH(NOISE_PHILOX, 768, 1);
+        else if (nthr == 768 && unr == 4) ROD_TAB_LAUNCH(NOISE_PHILOX, 768, 4);
+        else if (nthr == 768) ROD_TAB_LAUNCH(NOISE_PHILOX, 768, 2);
+        else if (unr == 1) ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 1);
+        else if (unr == 4) ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 4);
+        else ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 2);
 #undef ROD_TAB_LAUNCH
         ROD_CUDA(cudaGetLastError());
         return ROD_OK;

@@ -234,21 +234,33 @@ ROD_HD uint32_t noise_philox_px(uint32_t v, float s, float K) {
 }
 
 // Philox-mode noise, TABLE generator (noise.cu noise_table_kernel; used when sigma <= ROD_GAUSS_TABLE_MAX_SIGMA).
-// The same Philox block r[4] of group g, but each 16-bit half is one inverse-CDF draw instead of half a
-// Box-Muller pair: element 8g + 2p takes h = r[p] & 0xffff, element 8g + 2p + 1 takes h = r[p] >> 16, and
-//   h in 1..65535 : k = T[h] = floor(sigma * Phi^-1(h / 65536))      (65535 equiprobable strata of |z| < 4.30,
-//                                                                       T is a 64 KB int8 table in shared memory)
-//   h == 0        : (probability 2^-16 = the two-sided tail mass beyond the table) k = floor(+-sigma z),
-//                   z = -Phi^-1((m + 0.5) * 2^-48), m = w >> 1, sign = w & 1, w = t[p] (even element) or
-//                   rotl(t[p], 16) (odd element), t = the Philox block at counter (g, image lo, image hi ^ 0x80000000,
-//                   offset) -> reaches 8.1 sigma
+// The same Philox block r[4] of group g as the Box-Muller generator, but integer arithmetic only:
+//   A[i], i = 0..32767 : the 15-bit stratified quantile table of N(0, sigma^2 / 2) in 1/256 units, stored biased:
+//                        A[i] = round(256 * (sigma / sqrt 2) * Phi^-1((i + 0.5) / 32768)) + 16384      (uint16, < 32768)
+//   word r[p] -> a = A[(r[p] & 0xffff) >> 1],  b = A[r[p] >> 17]          (two independent draws; bits 0 and 16 unused)
+//   element 8g + 2p     : k0 = ((a + b) >> 8) - 128                       floor((x + y) / 256), x, y the unbiased draws
+//   element 8g + 2p + 1 : k1 = ((a - b + 32768) >> 8) - 128               floor((x - y) / 256)
 //   out = clamp(v + k, 0, 255)   (k is floor(noise), so this is the reference's truncation of the clipped sum).
-// One shared-memory byte load per element replaces the four MUFU operations per Box-Muller pair.
-#define ROD_GAUSS_TABLE_MAX_SIGMA 29.0f  // floor(sigma * 4.30) must fit int8
+// (x + y) and (x - y) are the 45-degree rotation of an independent Gaussian pair: again independent N(0, sigma^2),
+// each with ~2^30 distinct values and tails to 5.9 sigma, so no separate tail draw is needed.  On the device this is
+// two 16-bit shared-memory loads and integer multiply-adds per pair -- no MUFU, no floating point.
+#define ROD_GAUSS_TABLE_MAX_SIGMA 21.0f  // 256 * (sigma / sqrt 2) * 4.17 must stay below 16384
+#define ROD_GAUSS_TABLE_BIAS 16384
 #ifndef ROD_GAUSS_AUTO
 #define ROD_GAUSS_AUTO 0                 // table generator when sigma <= ROD_GAUSS_TABLE_MAX_SIGMA, else Box-Muller
 #define ROD_GAUSS_BOXMULLER 1
 #endif
+// Both elements of a pair as biased int16 halves: low = a + b = 256 x0 + 2 * 16384, high = a - b + 32768; byte 1 of
+// each half is k + 128.  Two multiply-adds: a * 0x10001 + b * (1 - 65536) + 0x80000000 (no carry between the halves).
+ROD_HD uint32_t gauss_pair_packed(uint32_t a, uint32_t b) { return a * 0x10001u + (b * 0xFFFF0001u + 0x80000000u); }
+ROD_HD int gauss_pair_k(uint32_t a, uint32_t b, int odd) {
+    const uint32_t p = gauss_pair_packed(a, b);
+    return (int)((odd ? (p >> 24) : (p >> 8)) & 0xFFu) - 128;
+}
+ROD_HD uint32_t noise_table_px(uint32_t v, int k) {
+    const int x = (int)v + k;
+    return (uint32_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
+}
 
 // Phi^-1 in double (Acklam's rational start + Halley steps on erfc): host only (table builder, emu harness).
 inline double ndtri_double(double p) {
@@ -277,33 +289,6 @@ inline double ndtri_double(double p) {
         x -= u / (1.0 + 0.5 * x * u);
     }
     return x;
-}
-
-// The rare branch: tail draw from the 32-bit word w (see above).
-ROD_HD int gauss_tail_k(uint32_t w, float sigma) {
-#if defined(__CUDA_ARCH__)
-    // fp32: ln p = ln((m + 0.5) 2^-31) - 17 ln 2; Acklam's lower-region rational (|rel err| < 1.2e-9) gives -z
-    const float u = fmaf((float)(w >> 1), 4.656612873077393e-10f, 2.3283064365386963e-10f);
-    const float q = sqrtf(-2.0f * (logf(u) - 11.7835020695190700f));
-    const float num = fmaf(fmaf(fmaf(fmaf(fmaf(-7.784894002430293e-03f, q, -3.223964580411365e-01f), q,
-                                          -2.400758277161838e+00f), q, -2.549732539343734e+00f), q,
-                                4.374664141464968e+00f), q, 2.938163982698783e+00f);
-    const float den = fmaf(fmaf(fmaf(fmaf(7.784695709041462e-03f, q, 3.224671290700398e-01f), q,
-                                     2.445134137142996e+00f), q, 3.754408661907416e+00f), q, 1.0f);
-    const float z = -num / den;  // > 0
-    return (int)floorf((w & 1u) ? -sigma * z : sigma * z);
-#else
-    const double z = -ndtri_double(((double)(w >> 1) + 0.5) * 3.5527136788005009e-15);  // 2^-48
-    return (int)floor((w & 1u) ? -(double)sigma * z : (double)sigma * z);
-#endif
-}
-ROD_HD uint32_t gauss_tail_word(const uint32_t t[4], int j) {  // j = element inside the group, 0..7
-    const uint32_t w = t[j >> 1];
-    return (j & 1) ? ((w << 16) | (w >> 16)) : w;
-}
-ROD_HD uint32_t noise_table_px(uint32_t v, int k) {
-    const int x = (int)v + k;
-    return (uint32_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
 }
 
 // ---------------------------------------------------------------------------------

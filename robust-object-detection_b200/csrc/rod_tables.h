@@ -229,11 +229,12 @@ inline void letterbox_geometry(int h, int w, int out_h, int out_w, int* new_h, i
 }
 
 // Tile lists ---------------------------------------------------------------------------
-// Inverse-CDF table of the Philox TABLE generator (rod_core.h): T[h] = floor(sigma * Phi^-1(h / 65536)), h = 1..65535
-// (T[0] is the tail sentinel, unused).  sigma <= ROD_GAUSS_TABLE_MAX_SIGMA keeps every entry inside int8.
-inline void build_gauss_table(float sigma, int8_t* tab) {
-    tab[0] = 0;
-    for (int h = 1; h < 65536; ++h) tab[h] = (int8_t)floor((double)sigma * ndtri_double((double)h / 65536.0));
+// Quantile table of the Philox TABLE generator (rod_core.h): A[i] = round(256 * (sigma / sqrt 2) * Phi^-1((i + 0.5) /
+// 32768)) + 16384, i = 0..32767.  sigma <= ROD_GAUSS_TABLE_MAX_SIGMA keeps every entry inside [0, 32767].
+inline void build_gauss_table(float sigma, uint16_t* tab) {
+    const double scale = 256.0 * ((double)sigma / sqrt(2.0));
+    for (int i = 0; i < 32768; ++i)
+        tab[i] = (uint16_t)((long)floor(scale * ndtri_double(((double)i + 0.5) / 32768.0) + 0.5) + ROD_GAUSS_TABLE_BIAS);
 }
 
 inline void build_noise_tiles(const std::vector<DevImage>& imgs, int span, std::vector<Tile>& tiles) {

@@ -443,29 +443,23 @@ extern "C" int emu_noise(const uint8_t* src, uint8_t* dst, const float* noise, f
     return 0;
 }
 
-// Replays noise_table_kernel (the TABLE generator of Philox mode): per group the Philox block, per element the
-// inverse-CDF lookup (table built by rod_tables.h build_gauss_table, stored biased + sentinel as on the device) or
-// the tail draw.  field_out receives k.
+// Replays noise_table_kernel (the TABLE generator of Philox mode): per group the Philox block, per word two 15-bit
+// table draws and their integer 45-degree rotation (rod_core.h gauss_pair_k).  field_out receives k.
 extern "C" int emu_noise_table(const uint8_t* src, uint8_t* dst, float* field_out, long n_elems, float sigma,
                                uint64_t seed, uint64_t image_index, uint32_t offset) {
     if (!(sigma <= ROD_GAUSS_TABLE_MAX_SIGMA)) return 1;
-    std::vector<int8_t> tab(65536);
+    std::vector<uint16_t> tab(32768);
     build_gauss_table(sigma, tab.data());
-    std::vector<uint8_t> kb(65536);
-    for (int h = 0; h < 65536; ++h) kb[h] = (uint8_t)((int)tab[h] + 128);
-    kb[0] = 0;  // sentinel
     const PhiloxKeys keys = philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32));
     const uint32_t ig_lo = (uint32_t)image_index, ig_hi = (uint32_t)(image_index >> 32);
     for (long g = 0; g < (n_elems + 7) / 8; ++g) {
-        uint32_t r[4], t[4];
+        uint32_t r[4];
         philox4x32_10_rk((uint32_t)g, ig_lo, ig_hi, offset, keys, r);
-        philox4x32_10_rk((uint32_t)g, ig_lo, ig_hi ^ ROD_PHILOX_TAIL_FLIP, offset, keys, t);
         for (int j = 0; j < 8; ++j) {
             const long e = 8 * g + j;
             if (e >= n_elems) break;
             const uint32_t w = r[j >> 1];
-            const uint32_t h = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
-            const int k = kb[h] != 0 ? (int)kb[h] - 128 : gauss_tail_k(gauss_tail_word(t, j), sigma);
+            const int k = gauss_pair_k(tab[(w & 0xFFFFu) >> 1], tab[w >> 17], j & 1);
             if (field_out) field_out[e] = (float)k;
             if (dst) dst[e] = (uint8_t)noise_table_px(src[e], k);
         }
@@ -474,7 +468,7 @@ extern "C" int emu_noise_table(const uint8_t* src, uint8_t* dst, float* field_ou
 }
 
 // The table itself, for a direct comparison with the oracle's scipy-based one.
-extern "C" int emu_gauss_table(float sigma, int8_t* out) {
+extern "C" int emu_gauss_table(float sigma, uint16_t* out) {
     build_gauss_table(sigma, out);
     return 0;
 }
