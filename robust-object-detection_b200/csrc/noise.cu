@@ -420,20 +420,14 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
         if (rc != ROD_OK) return rc;
         // one 1024-thread CTA per SM, each with its own copy of the table; warps take quarter spans
         const int ctas = grid_for(plan, (p.n_tiles * 4 + 31) / 32, 1);
-        static const int nthr = [] { const char* e = getenv("ROD_NOISE_THREADS"); return e ? atoi(e) : 1024; }();
-        static const int unr = [] { const char* e = getenv("ROD_NOISE_UNROLL"); return e ? atoi(e) : 2; }();
 #define ROD_TAB_LAUNCH(M, TH, UN)                                                                                          \
     do {                                                                                                                   \
         ROD_CUDA(cudaFuncSetAttribute(noise_table_kernel<M, TH, UN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmemBytes)); \
         noise_table_kernel<M, TH, UN><<<ctas, TH, kTabSmemBytes, stream>>>(p);                                             \
     } while (0)
+        // measured on a B200 (256 x 1360x765): 1024 threads x unroll 4: 3.63 TB/s; unroll 1 / 2: 3.61 / 3.57; 768 threads: 3.51-3.61
         if (mode == NOISE_FIELD) ROD_TAB_LAUNCH(NOISE_FIELD, 1024, 2);
-        else if (nthr == 768 && unr == 1) ROD_TAB_LAUNCH(NOISE_PHILOX, 768, 1);
-        else if (nthr == 768 && unr == 4) ROD_TAB_LAUNCH(NOISE_PHILOX, 768, 4);
-        else if (nthr == 768) ROD_TAB_LAUNCH(NOISE_PHILOX, 768, 2);
-        else if (unr == 1) ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 1);
-        else if (unr == 4) ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 4);
-        else ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 2);
+        else ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 4);
 #undef ROD_TAB_LAUNCH
         ROD_CUDA(cudaGetLastError());
         return ROD_OK;
