@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Table generator (rod_core.h): k[0..7] of group g.  `tab` is the CTA's shared-memory copy of the table.
+// Table generator of Philox mode (definition: rod_core.h).
 // ---------------------------------------------------------------------------------------------------
 // Shared-memory layout of the table kernel: the 64 KB table (32768 x uint16) sits at a 64 KB-ALIGNED shared address
 // `tbase`, so the address of the first draw of a word is one instruction, (r & 0xfffe) | tbase (LOP3); the second is
@@ -293,18 +293,12 @@ __global__ void __launch_bounds__(THREADS, 1) noise_table_kernel(NoiseParams p) 
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
-    // the next work item (counter value + its tile) is fetched while the current one is processed
-    uint32_t id_next = 0;
-    if (lane == 0) id_next = atomicAdd(p.counter, 1u);
-    id_next = __shfl_sync(0xFFFFFFFFu, id_next, 0);
-    Tile t_next = p.tiles[min((int)(id_next >> 2), p.n_tiles - 1)];
     for (;;) {
-        const uint32_t id = id_next;
+        uint32_t id = 0;
+        if (lane == 0) id = atomicAdd(p.counter, 1u);
+        id = __shfl_sync(0xFFFFFFFFu, id, 0);
         if ((int)(id >> 2) >= p.n_tiles) break;
-        Tile t = t_next;
-        if (lane == 0) id_next = atomicAdd(p.counter, 1u);
-        id_next = __shfl_sync(0xFFFFFFFFu, id_next, 0);
-        t_next = p.tiles[min((int)(id_next >> 2), p.n_tiles - 1)];
+        Tile t = p.tiles[id >> 2];
         if (p.opcodes != nullptr && p.opcodes[t.img] != p.my_op) continue;
         const int piece0 = (int)(id & 3u) * (kNoiseSpan / 4);
         if (piece0 >= t.b) continue;
