@@ -268,6 +268,41 @@ def test_philox_table_full_size_and_unaligned_spans(torch_):
     assert np.array_equal(got, orc.add_philox_noise(np.ascontiguousarray(crop), want))
 
 
+def test_philox_table_pitched_batch_guard_bytes(torch_):
+    """Table generator on a ragged batch with pitched source AND destination rows (every span is a row piece, most of
+    them off 16-byte alignment and off a Philox group boundary) plus op-code masking: image bytes bit-exact against
+    the restated stream, pitch padding / gaps / masked images untouched."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    shapes = [(37, 53), (64, 64), (31, 45), (3, 5), (1, 1), (90, 1366), (2, 6000)]
+    imgs = [synth(8100 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    sp = [3 * w + 20 for h, w in shapes]
+    dp = [3 * w + 9 for h, w in shapes]
+    so = np.concatenate([[0], np.cumsum([(h * q + 255) // 256 * 256 for (h, w), q in zip(shapes, sp)])])
+    do = np.concatenate([[0], np.cumsum([(h * q + 255) // 256 * 256 for (h, w), q in zip(shapes, dp)])])
+    plan = CorruptionPlan(shapes, so[:-1], do[:-1], src_pitches=sp, dst_pitches=dp)
+    hsrc = np.full(int(so[-1]), 0xAB, np.uint8)
+    for img, o, q in zip(imgs, so, sp):
+        h, w, _ = img.shape
+        hsrc[o:o + h * q].reshape(h, q)[:, :3 * w] = img.reshape(h, 3 * w)
+    src = torch_.from_numpy(hsrc).cuda()
+    dst = torch_.full((int(do[-1]),), 7, dtype=torch_.uint8, device="cuda")
+    ops = torch_.tensor([1, 1, 0, 1, 1, 1, 1], dtype=torch_.uint8, device="cuda")
+    plan.noise(src, dst, None, 15.0, seed=77, first_image_index=10, opcodes=ops)
+    hdst = dst.cpu().numpy()
+    covered = np.zeros(hdst.size, bool)
+    for i, (img, o, q) in enumerate(zip(imgs, do, dp)):
+        h, w, _ = img.shape
+        rows = hdst[o:o + h * q].reshape(h, q)
+        if i == 2:
+            assert (rows == 7).all()           # op-code 0: not a noise image
+            continue
+        want = orc.add_philox_noise(img, orc.philox_noise_field(img.size, 15.0, 77, 10 + i))
+        assert np.array_equal(rows[:, :3 * w].reshape(h, w, 3), want), (i, shapes[i])
+        cov = covered[o:o + h * q].reshape(h, q)
+        cov[:, :3 * w] = True
+    assert (hdst[~covered] == 7).all()         # padding, gaps between images, the masked image
+
+
 def test_philox_statistics_and_reproducibility(torch_):
     from robust_object_detection_b200.batch import CorruptionPlan
     h, w = 765, 1360
