@@ -5,7 +5,8 @@ for Test_Clean / Test_Noise / Test_Blur / Test_LowRes the images of `images/val`
 written with cv2.imwrite under the same file name; labels / annotations are copied; data.yaml is written
 (build_corrupted_testsets.py:62-166).  The corruption itself runs on the GPU, one ragged batch at a time
 (rod_apply_host: pinned staging, chunked H2D / kernel / D2H), while JPEG decode and encode -- still the reference's
-OpenCV codec, so files are byte-identical to the reference's -- run on a host thread pool around it.
+OpenCV codec, so files are byte-identical to the reference's -- run on a host thread pool around it (the next batch
+decodes and the previous one encodes while a batch is on the GPU; a tree's decoded frames are reused by its four variants).
 
 RNG: Test_Noise draws each image's field with np.random.normal in glob order after np.random.seed(SEED), exactly like
 the reference, so the noisy files are byte-identical too (that draw is the slow part: ~100 ms per frame on one core).
@@ -41,6 +42,7 @@ NOISE_MODE = "compat"      # "compat": host np.random stream (byte-identical) | 
 PHILOX_SEED = SEED
 BATCH_BYTES = 512 << 20    # decoded source bytes per GPU batch
 IO_THREADS = 16
+DECODE_CACHE_BYTES = 8 << 30  # decoded frames of one tree kept for its later variants (548 VisDrone val frames ~ 2.3 GB)
 
 VARIANTS = ["Test_Clean", "Test_Noise", "Test_Blur", "Test_LowRes"]
 _OPS = {"Test_Noise": N.OP_NOISE, "Test_Blur": N.OP_BLUR, "Test_LowRes": N.OP_LOWRES}
@@ -71,7 +73,11 @@ def _corrupt_batch(variant: str, images, philox_index: int):
     noise = None
     if variant == "Test_Noise" and NOISE_MODE == "compat":
         # the draws of augmentations.py:31, one per image, in order
-        noise = np.concatenate([np.random.normal(0, NOISE_SIGMA, im.shape).astype(np.float32).reshape(-1) for im in images])
+        noise = np.empty(sum(im.size for im in images), dtype=np.float32)
+        o = 0
+        for im in images:  # float64 draw, cast to float32 on assignment (== .astype(np.float32))
+            noise[o:o + im.size] = np.random.normal(0, NOISE_SIGMA, im.shape).reshape(-1)
+            o += im.size
     if variant == "Test_Blur" and float(BLUR_ANGLE_DEG) != 0.0:
         plan.set_blur_kernel(motion_blur_kernel(BLUR_KERNEL, BLUR_ANGLE_DEG))
     plan.apply_host(op, src, dst, noise_host=noise, sigma=float(NOISE_SIGMA), k=int(BLUR_KERNEL),
@@ -79,32 +85,80 @@ def _corrupt_batch(variant: str, images, philox_index: int):
     return plan.unpack(dst)
 
 
-def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str):
+class _TreeRun:
+    """Host-side pipeline state of one source tree (its four variants): the I/O thread pool, the decoded frames of the
+    tree (the reference re-reads every file for every variant, build_corrupted_testsets.py:109/:149; here variants 2-4
+    reuse the arrays of variant 1 while they fit DECODE_CACHE_BYTES) and the imwrite futures still in flight (encoding
+    of one batch overlaps decoding / corrupting the next; at most two batches of output buffers are alive)."""
+
+    def __init__(self):
+        # compat noise draws np.random.normal on the calling thread (the serial bottleneck of that mode): leave it a core
+        import os
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.pool = ThreadPoolExecutor(max(1, min(IO_THREADS, cores - 2)) if NOISE_MODE == "compat" else IO_THREADS)
+        self.cache = {}
+        self.cache_bytes = 0
+        self.pending = []  # one list of futures per batch in flight
+
+    def decode(self, path: Path):
+        import cv2
+        im = self.cache.get(path)
+        return im if im is not None else cv2.imread(str(path))
+
+    def remember(self, path: Path, im):
+        if path not in self.cache and self.cache_bytes + im.nbytes <= DECODE_CACHE_BYTES:
+            self.cache[path] = im
+            self.cache_bytes += im.nbytes
+
+    def drain(self, keep: int = 0):
+        while len(self.pending) > keep:
+            for f in self.pending.pop(0):
+                if not f.result():
+                    raise IOError("cv2.imwrite failed")
+
+    def close(self):
+        self.drain()
+        self.pool.shutdown()
+
+
+def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_TreeRun" = None):
     """The image loop of build_corrupted_testsets.py:108-124 / :148-164 for one variant, batched."""
     import cv2
+    own = run is None
+    if own:
+        run = _TreeRun()
     paths = list(src_img_dir.glob("*.*"))  # filesystem order, like the reference (it fixes the noise stream order)
     philox_index = 0
-    with ThreadPoolExecutor(IO_THREADS) as pool:
-        i = 0
-        while i < len(paths):
-            # decode ahead until the batch is full (cv2 releases the GIL)
-            batch_paths, futs, nbytes = [], [], 0
-            while i < len(paths) and (nbytes < BATCH_BYTES or not futs):
-                futs.append(pool.submit(cv2.imread, str(paths[i])))
-                batch_paths.append(paths[i])
-                i += 1
-                nbytes += 6 << 20  # ~ a decoded VisDrone frame; the real size is known after decoding
-            decoded = [(p, f.result()) for p, f in zip(batch_paths, futs)]
-            decoded = [(p, im) for p, im in decoded if im is not None]  # unreadable files are skipped (reference :110-111)
-            if not decoded:
-                continue
-            images = [im for _, im in decoded]
-            if variant == "Test_Clean":
-                outs = images
-            else:
-                outs = _corrupt_batch(variant, images, philox_index)
-                philox_index += len(images)
-            list(pool.map(lambda po: cv2.imwrite(str(dst_img_dir / po[0].name), po[1]), zip((p for p, _ in decoded), outs)))
+
+    def submit_decodes(i):
+        """decode ahead until the batch is full (cv2 releases the GIL)"""
+        batch_paths, futs, nbytes = [], [], 0
+        while i < len(paths) and (nbytes < BATCH_BYTES or not futs):
+            futs.append(run.pool.submit(run.decode, paths[i]))
+            batch_paths.append(paths[i])
+            i += 1
+            nbytes += 6 << 20  # ~ a decoded VisDrone frame; the real size is known after decoding
+        return i, batch_paths, futs
+
+    i, batch_paths, futs = submit_decodes(0)
+    while futs:
+        decoded = [(p, f.result()) for p, f in zip(batch_paths, futs)]
+        i, batch_paths, futs = submit_decodes(i)  # the next batch decodes while this one is corrupted and encoded
+        decoded = [(p, im) for p, im in decoded if im is not None]  # unreadable files are skipped (reference :110-111)
+        if not decoded:
+            continue
+        for p, im in decoded:
+            run.remember(p, im)
+        images = [im for _, im in decoded]
+        if variant == "Test_Clean":
+            outs = images
+        else:
+            outs = _corrupt_batch(variant, images, philox_index)
+            philox_index += len(images)
+        run.drain(keep=1)
+        run.pending.append([run.pool.submit(cv2.imwrite, str(dst_img_dir / p.name), o) for (p, _), o in zip(decoded, outs)])
+    if own:
+        run.close()
 
 
 def build_yolo_testsets():
@@ -112,6 +166,7 @@ def build_yolo_testsets():
     src_lbl_dir = YOLO_SRC / "labels" / "val"
     if not src_img_dir.exists() or not src_lbl_dir.exists():
         raise FileNotFoundError("YOLO val images/labels not found. Check YOLO_SRC path.")
+    run = _TreeRun()
     for v in VARIANTS:
         dst_root = OUT_ROOT / "yolo6" / v
         dst_img_dir = dst_root / "images" / "val"
@@ -121,7 +176,8 @@ def build_yolo_testsets():
         for lbl in src_lbl_dir.glob("*.txt"):
             shutil.copy2(lbl, dst_lbl_dir / lbl.name)
         write_yolo_valonly_yaml(dst_root)
-        _process_images(src_img_dir, dst_img_dir, v)
+        _process_images(src_img_dir, dst_img_dir, v, run)
+    run.close()
     print("YOLO test sets created:", (OUT_ROOT / "yolo6").resolve())
 
 
@@ -130,6 +186,7 @@ def build_coco_testsets():
     src_ann = COCO_SRC / "annotations" / "instances_val.json"
     if not src_img_dir.exists() or not src_ann.exists():
         raise FileNotFoundError("COCO val images or instances_val.json not found. Check COCO_SRC path.")
+    run = _TreeRun()
     for v in VARIANTS:
         dst_root = OUT_ROOT / "coco6" / v
         dst_img_dir = dst_root / "images" / "val"
@@ -137,7 +194,8 @@ def build_coco_testsets():
         ensure_dir(dst_img_dir)
         ensure_dir(dst_ann_dir)
         shutil.copy2(src_ann, dst_ann_dir / "instances_val.json")
-        _process_images(src_img_dir, dst_img_dir, v)
+        _process_images(src_img_dir, dst_img_dir, v, run)
+    run.close()
     print("COCO test sets created:", (OUT_ROOT / "coco6").resolve())
 
 

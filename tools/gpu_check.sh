@@ -18,4 +18,5 @@ ncu --set full --clock-control none --import-source on -k regex:blur -s 3 -c 1 -
 python tools/profile_ops.py > $out/plain_profile_$tag.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'blur|noise|lowres|letterbox' -s 3 -c 24 -f \
     -o $out/prof_$tag python tools/profile_ops.py > $out/ncu_full_$tag.log 2>&1
+python tools/time_testset_driver.py 64 > $out/testset_driver_$tag.json 2> $out/testset_driver_$tag.err; echo "driver timing exit $?"
 echo "done"
