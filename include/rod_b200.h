@@ -106,6 +106,14 @@ ROD_API int rod_noise_field_f32(const rod_plan* plan, float* out_field, float si
 #define ROD_GAUSS_BOXMULLER 1
 ROD_API int rod_plan_set_gaussian_generator(rod_plan* plan, int generator);
 
+/* The HOST side of compat mode: the field `np.random.normal(0, sigma, shape).astype(np.float32)` of augmentations.py:31,
+ * regenerated bit for bit from NumPy's legacy generator state (MT19937 + polar Gaussian) with the per-pair work spread
+ * over `threads` host threads (0 = all).  key[624], *pos, *has_gauss, *cached are np.random.get_state()[1:5] on entry
+ * and the state NumPy itself would have after the call on return (feed them to np.random.set_state), so later draws
+ * continue on the same stream.  Pure host code (no GPU work): the reference's own bottleneck, 104 of 137 ms per frame. */
+ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* cached, double sigma,
+                                uint64_t n, float* out, int threads);
+
 /* a2+a3: apply_motion_blur(img, k, angle_deg) (augmentations.py:21-38) for angle_deg == 0:
  * horizontal k-tap box, BORDER_REFLECT_101, out = (2S + k) / (2k).  k odd, 1 <= k <= 31;
  * anything else returns ROD_ERR_UNSUPPORTED (never an approximation). */

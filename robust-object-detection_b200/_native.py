@@ -40,6 +40,8 @@ SYMBOLS = {
     "rod_blur_h_u8": (_i, [_vp, _vp, _vp, _i, _d, _vp, _vp]),
     "rod_set_blur_kernel": (_i, [_vp, _vp, _i]),
     "rod_plan_set_gaussian_generator": (_i, [_vp, _i]),
+    "rod_numpy_legacy_normal_f32": (_i, [_vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                         ctypes.POINTER(ctypes.c_double), _d, _u64, _vp, _i]),
     "rod_lowres_u8": (_i, [_vp, _vp, _vp, _d, _vp, _vp]),
     "rod_corrupt_batch_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _d, _u64, _u64, _u32, _vp]),
     "rod_corrupt_letterbox_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _i, _d, _u64, _u64, _u32, _vp]),

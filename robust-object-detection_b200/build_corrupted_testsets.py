@@ -8,8 +8,9 @@ written with cv2.imwrite under the same file name; labels / annotations are copi
 OpenCV codec, so files are byte-identical to the reference's -- run on a host thread pool around it (the next batch
 decodes and the previous one encodes while a batch is on the GPU; a tree's decoded frames are reused by its four variants).
 
-RNG: Test_Noise draws each image's field with np.random.normal in glob order after np.random.seed(SEED), exactly like
-the reference, so the noisy files are byte-identical too (that draw is the slow part: ~100 ms per frame on one core).
+RNG: Test_Noise draws each image's field from NumPy's global legacy generator in glob order after np.random.seed(SEED)
+-- the same stream as the reference's np.random.normal calls, regenerated bit for bit by csrc/np_legacy_rng.cpp with the
+per-sample math on all host threads -- so the noisy files are byte-identical too.
 `NOISE_MODE = "philox"` generates the field on the GPU instead (statistically equivalent, not byte-identical).
 """
 from __future__ import annotations
@@ -22,6 +23,7 @@ import numpy as np
 
 from . import _native as N
 from .augmentations import apply_lowres, apply_motion_blur, apply_noise  # noqa: F401  (same names as the reference)
+from .augmentations import legacy_normal_f32
 from .augmentations import _motion_blur_kernel as motion_blur_kernel  # noqa: F401
 from .batch import CorruptionPlan
 
@@ -75,8 +77,8 @@ def _corrupt_batch(variant: str, images, philox_index: int):
         # the draws of augmentations.py:31, one per image, in order
         noise = np.empty(sum(im.size for im in images), dtype=np.float32)
         o = 0
-        for im in images:  # float64 draw, cast to float32 on assignment (== .astype(np.float32))
-            noise[o:o + im.size] = np.random.normal(0, NOISE_SIGMA, im.shape).reshape(-1)
+        for im in images:  # np.random.normal(0, NOISE_SIGMA, im.shape).astype(np.float32), bit for bit, multi-threaded
+            noise[o:o + im.size] = legacy_normal_f32(NOISE_SIGMA, im.shape).reshape(-1)
             o += im.size
     if variant == "Test_Blur" and float(BLUR_ANGLE_DEG) != 0.0:
         plan.set_blur_kernel(motion_blur_kernel(BLUR_KERNEL, BLUR_ANGLE_DEG))

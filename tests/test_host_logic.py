@@ -144,3 +144,37 @@ def test_trainer_patch_contract_with_stub():
     assert t.preprocess_batch({"img": 1})["seen_by_original"] is True
     out = t.preprocess_batch({"raw": [np.zeros((4, 4, 3), np.uint8)] * 3})
     assert out["img"] == ("device-tensor-for", 3) and "seen_by_original" not in out
+
+
+def test_numpy_legacy_normal_stream_bit_exact():
+    """csrc/np_legacy_rng.cpp (host code, no GPU): the compat-mode field generator must be NumPy's global legacy stream
+    bit for bit -- np.random.normal(0, sigma, shape).astype(float32) -- for any count (odd counts leave a cached
+    Gaussian), from any generator state (fresh seed: pos = 624; mid-block; with a cached Gaussian pending), and must
+    leave np.random in exactly the state the NumPy call would, so that mixed use continues on the same stream."""
+    from robust_object_detection_b200 import augmentations as aug
+    sizes = [1, 2, 3, 7, 155, 156, 157, 311, 312, 313, 1000, 4097, 65536, 100001, (37, 53, 3), (765, 1360, 3)]
+    for seed in (0, 42, 123456789):
+        np.random.seed(seed)
+        want = [np.random.normal(0, 15, s).astype(np.float32) for s in sizes]
+        want_tail = np.random.normal(0, 1, 9)
+        want_uni = np.random.random(5)
+        np.random.seed(seed)
+        got = [aug.legacy_normal_f32(15, s) for s in sizes]
+        assert all(g.dtype == np.float32 and g.shape == w.shape and np.array_equal(g, w) for g, w in zip(got, want)), seed
+        assert np.array_equal(np.random.normal(0, 1, 9), want_tail) and np.array_equal(np.random.random(5), want_uni)
+    # interleaved with other consumers of the global stream (uniforms move pos, standard_normal leaves a cached value)
+    np.random.seed(7)
+    a = [np.random.random(3), np.random.standard_normal(1), np.random.normal(0, 2.5, 11).astype(np.float32),
+         np.random.randint(0, 100, 5), np.random.normal(0, 15, 622).astype(np.float32), np.random.standard_normal(2)]
+    np.random.seed(7)
+    b = [np.random.random(3), np.random.standard_normal(1), aug.legacy_normal_f32(2.5, 11),
+         np.random.randint(0, 100, 5), aug.legacy_normal_f32(15, 622), np.random.standard_normal(2)]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # other sigmas, including 0 and a float32-inexact one
+    for sigma in (0.0, 1.0, 0.1, 33.3):
+        np.random.seed(5)
+        w = np.random.normal(0, sigma, 5001).astype(np.float32)
+        np.random.seed(5)
+        assert np.array_equal(aug.legacy_normal_f32(sigma, 5001), w), sigma
+    with pytest.raises(ValueError):
+        aug.legacy_normal_f32(-1.0, 4)
