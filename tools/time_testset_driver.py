@@ -65,7 +65,12 @@ def reference_loop(root: Path, out: Path):
 def run_driver(root: Path, out: Path, mode: str):
     from robust_object_detection_b200 import build_corrupted_testsets as drv
     drv.YOLO_SRC, drv.COCO_SRC, drv.OUT_ROOT, drv.NOISE_MODE = root / "yolo", root / "coco", out, mode
-    drv.main()
+    keep, sys.stdout = sys.stdout, open(os.devnull, "w")  # the driver prints the reference's progress lines
+    try:
+        drv.main()
+    finally:
+        sys.stdout.close()
+        sys.stdout = keep
 
 
 def main():
@@ -83,12 +88,7 @@ def main():
         res["reference_loop_s"] = time.perf_counter() - t0
         for mode in ("compat", "philox"):
             t0 = time.perf_counter()
-            sys.stdout, keep = open(os.devnull, "w"), sys.stdout  # the driver prints the reference's progress lines
-            try:
-                run_driver(base / "src", base / mode, mode)
-            finally:
-                sys.stdout.close()
-                sys.stdout = keep
+            run_driver(base / "src", base / mode, mode)
             res[f"driver_{mode}_s"] = time.perf_counter() - t0
         same = diff = 0
         for p in (base / "ref").rglob("*.jpg"):
