@@ -469,6 +469,65 @@ def test_full_size_config2_batch_by_replication(torch_):
         assert torch_.equal(dst.view(32, 8, h, w, 3), want.unsqueeze(0).expand(32, -1, -1, -1, -1)), op
 
 
+def test_full_size_config4_testset_by_replication_and_sharding(torch_):
+    """BASELINE config 4 at full size: 1610 VisDrone-shaped images (8 real frame sizes, same draw as bench.py) in one
+    ragged device-resident batch, the three corruptions of the test-set build.  Parity at this size rests on properties
+    that do not need 1610 oracle runs: (1) replication -- one distinct image per frame size, so every output must equal
+    the oracle's output for that size's image (blur, LowRes: bit-exact); (2) Philox noise is keyed by the global image
+    index -- three images are checked against the restated stream, and corrupting the batch as two image-index shards
+    (what two ranks would do, sharding.py) must give the same bytes as one batch; (3) image-index sharding of the other
+    two ops likewise."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    from robust_object_detection_b200.sharding import shard_range
+    pool = [(765, 1360), (1050, 1400), (788, 1400), (1078, 1916), (1080, 1920), (1500, 2000), (540, 960), (360, 480)]
+    kinds = np.random.default_rng(4000).integers(0, 8, 1610)
+    shapes = [pool[i] for i in kinds]
+    base = [synth(9000 + i, h, w) for i, (h, w) in enumerate(pool)]
+    dbase = [torch_.from_numpy(b.reshape(-1)).cuda() for b in base]
+    plan = CorruptionPlan.ragged(shapes)
+    src = torch_.zeros(plan.src_bytes, dtype=torch_.uint8, device="cuda")
+    for off, k in zip(plan.src_offsets, kinds):
+        src[off:off + dbase[k].numel()] = dbase[k]
+    dst = torch_.empty_like(src)
+
+    def image(buf, i):
+        h, w = shapes[i]
+        return buf[plan.dst_offsets[i]:plan.dst_offsets[i] + 3 * h * w]
+
+    full = {}
+    for op, fn in (("blur", lambda im: orc.apply_motion_blur(im, 9, 0)), ("lowres", lambda im: orc.apply_lowres(im, 0.5))):
+        dst.zero_()
+        getattr(plan, op)(src, dst)
+        want = [torch_.from_numpy(fn(b).reshape(-1)).cuda() for b in base]
+        assert all(torch_.equal(image(dst, i), want[kinds[i]]) for i in range(1610)), op
+        full[op] = dst.clone()
+    dst.zero_()
+    plan.noise(src, dst, None, 15.0, seed=42, first_image_index=0)
+    for i in (0, 807, 1609):
+        h, w = shapes[i]
+        fld = orc.philox_noise_field(3 * h * w, 15.0, 42, i)
+        assert np.array_equal(image(dst, i).cpu().numpy().reshape(h, w, 3), orc.add_philox_noise(base[kinds[i]], fld)), i
+    full["noise"] = dst.clone()
+    # the same work as two image-index shards (each shard: its own plan over its own images, global Philox index)
+    for rank in range(2):
+        lo, hi = shard_range(1610, rank, 2)
+        sp = CorruptionPlan.ragged(shapes[lo:hi])
+        b0 = plan.src_offsets[lo]
+        ssrc = src[b0:b0 + sp.src_bytes]
+        sdst = torch_.empty_like(ssrc)
+        for op in ("blur", "lowres", "noise"):
+            sdst.zero_()
+            if op == "noise":
+                sp.noise(ssrc, sdst, None, 15.0, seed=42, first_image_index=lo)
+            else:
+                getattr(sp, op)(ssrc, sdst)
+            for j in (0, (hi - lo) // 2, hi - lo - 1):
+                h, w = shapes[lo + j]
+                got = sdst[sp.dst_offsets[j]:sp.dst_offsets[j] + 3 * h * w]
+                assert torch_.equal(got, image(full[op], lo + j)), (rank, op, j)
+            assert torch_.equal(sdst[:sp.dst_offsets[-1]], full[op][b0:b0 + sp.dst_offsets[-1]]), (rank, op)
+
+
 def test_letterbox_fused_training_path(torch_):
     from robust_object_detection_b200.batch import CorruptionPlan
     shapes = [(765, 1360)] * 5 + [(720, 1280), (360, 480), (640, 640), (1079, 1917)]
