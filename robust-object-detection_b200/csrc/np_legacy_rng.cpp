@@ -102,7 +102,10 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
         *has_gauss = 0;
         *cached = 0.0;
     }
-    std::vector<uint32_t> words;   // tempered stream: leftover of the current block, then whole blocks
+    // tempered stream: leftover of the current block, then whole blocks.  Kept per calling thread between calls: a fresh
+    // 32 MB buffer per frame costs more in page faults than generating the words
+    static thread_local std::vector<uint32_t> tl_words;
+    std::vector<uint32_t>& words = tl_words;  // (a local reference: the worker lambdas must see THIS thread's buffer)
     std::vector<uint64_t> counts;
     while (done < n) {
         const uint64_t need_pairs = (n - done + 1) / 2;
