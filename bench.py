@@ -314,9 +314,36 @@ def main():
 
     if world == 1 and not args.no_extras:
         line["ops"] = extras(torch, np, plan, src, dst, peak)
+        if cpu is not None:
+            line["ops"]["drop_in_per_call_ms"] = per_call_latency(np)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def per_call_latency(np):
+    """One 1360x765 frame through the drop-in functions (host array in, fresh host array out: the call the training
+    scripts make), next to the reference's own library calls for the same frame (oracle/cv2_port.py: part of the CPU
+    baseline leg).  compat noise is bit-exact, i.e. it includes drawing NumPy's legacy normal stream."""
+    from oracle import cv2_port
+    from robust_object_detection_b200 import augmentations as aug
+    img = np.random.default_rng(7).integers(0, 256, (H, W, 3), dtype=np.uint8)
+
+    def ms(fn, reps):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return 1e3 * (time.perf_counter() - t0) / reps
+
+    out = {"apply_noise_compat": {"ours": ms(lambda: aug.apply_noise(img, 15), 10)},
+           "apply_motion_blur": {"ours": ms(lambda: aug.apply_motion_blur(img, 9, 0), 20)},
+           "apply_lowres": {"ours": ms(lambda: aug.apply_lowres(img, 0.5), 20)}}
+    if cv2_port.available():
+        out["apply_noise_compat"]["reference"] = ms(lambda: cv2_port.noise(img, 15), 3)
+        out["apply_motion_blur"]["reference"] = ms(lambda: cv2_port.blur(img, 9, 0), 10)
+        out["apply_lowres"]["reference"] = ms(lambda: cv2_port.lowres(img, 0.5), 10)
+    return out
 
 
 def extras(torch, np, plan, src, dst, peak):
