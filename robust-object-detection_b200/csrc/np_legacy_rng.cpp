@@ -5,10 +5,11 @@
 // (MT19937) feeding the legacy polar Gaussian (numpy/random/src/legacy/legacy-distributions.c legacy_gauss,
 // numpy/random/src/mt19937/mt19937.h mt19937_next_double), one scalar at a time.  In compat mode the GPU kernel
 // consumes that field bit for bit, so the field has to be this exact stream.  This file regenerates it faster without
-// changing a bit: the MT19937 word stream is produced sequentially (it is a linear recurrence), the polar method's
-// rejection test, log, sqrt and division -- independent per candidate pair -- run on all host threads, and the
-// generator state handed back (key, pos, has_gauss, cached gaussian) is exactly what NumPy's would be after the call,
-// so any later np.random use continues on the same stream.
+// changing a bit: the calling thread produces the MT19937 word stream (a linear recurrence: sequential) in 0.5 MB chunks
+// while the other host threads already run the polar method on the chunks that are ready -- rejection test, log, sqrt
+// and division are independent per candidate pair -- each chunk's accepted pairs are then compacted into the output
+// in order, and the generator state handed back (key, pos, has_gauss, cached gaussian) is exactly what NumPy's would
+// be after the call, so any later np.random use continues on the same stream.
 //
 // Bit-exactness rests on: identical integer stream; (a * 2^26 + b) / 2^53 and 2x - 1 exact in double; x1*x1 + x2*x2,
 // the division and sqrt are IEEE operations (this file is built with -ffp-contract=off: no FMA); log() is the same libm
@@ -19,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -102,71 +104,111 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
         *has_gauss = 0;
         *cached = 0.0;
     }
-    // tempered stream: leftover of the current block, then whole blocks.  Kept per calling thread between calls: a fresh
-    // 32 MB buffer per frame costs more in page faults than generating the words
+    // tempered stream: leftover of the current block, then whole blocks; and the accepted pairs of every chunk before
+    // they are compacted into `out`.  Kept per calling thread between calls: fresh 32 MB buffers per frame cost more in
+    // page faults than generating the words
     static thread_local std::vector<uint32_t> tl_words;
-    std::vector<uint32_t>& words = tl_words;  // (a local reference: the worker lambdas must see THIS thread's buffer)
-    std::vector<uint64_t> counts;
+    static thread_local std::vector<float> tl_pairs;
+    std::vector<uint32_t>& words = tl_words;  // (local references: the worker lambdas must see THIS thread's buffers)
+    std::vector<float>& pairs = tl_pairs;
+    constexpr uint64_t kChunk = 1u << 15;     // candidates per work item (128 K words, 0.5 MB)
     while (done < n) {
         const uint64_t need_pairs = (n - done + 1) / 2;
         // candidates to draw this round: expectation 4/pi per accepted pair, plus slack; bounded per round
         uint64_t cand = (uint64_t)((double)need_pairs * 1.2740) + 64;
         cand = std::min<uint64_t>(cand, 1ull << 24);
-        const uint64_t want_words = 4 * cand;
-        // the stream from the current position: rest of the present block, then as many fresh blocks as needed
-        words.clear();
-        words.reserve(want_words + kN);
         const int start_pos = *pos;
-        for (int i = start_pos; i < kN; ++i) words.push_back(temper(key[i]));
-        std::vector<uint32_t> block(key, key + kN);
-        while (words.size() < want_words) {
-            mt_regenerate(block.data());
-            const size_t o = words.size();
-            words.resize(o + kN);
-            for (int i = 0; i < kN; ++i) words[o + i] = temper(block[i]);
+        const uint64_t in_first = (uint64_t)(kN - start_pos);
+        const uint64_t fresh_blocks = (4 * cand > in_first) ? (4 * cand - in_first + kN - 1) / kN : 0;
+        const uint64_t total_words = in_first + fresh_blocks * kN;
+        cand = total_words / 4;
+        const uint64_t n_chunks = (cand + kChunk - 1) / kChunk;
+        if (words.size() < total_words) words.resize(total_words);
+        if (pairs.size() < 2 * cand) pairs.resize(2 * cand);
+        std::vector<uint32_t> chunk_count((size_t)n_chunks, 0);
+        std::atomic<uint64_t> words_ready{0}, next_chunk{0};
+
+        // one work item: the accepted pairs of chunk c, in order, as float32 outputs at pairs[2 * c * kChunk ...]
+        auto process_chunk = [&](uint64_t c) {
+            const uint64_t lo = c * kChunk, hi = std::min(cand, lo + kChunk);
+            float* dstp = &pairs[2 * lo];
+            uint32_t cnt = 0;
+            for (uint64_t i = lo; i < hi; ++i) {
+                const Candidate cd = candidate(&words[4 * i]);
+                if (!cd.ok) continue;
+                const double f = sqrt(-2.0 * log(cd.r2) / cd.r2);
+                dstp[2 * cnt] = (float)(0.0 + sigma * (f * cd.x2));      // returned first
+                dstp[2 * cnt + 1] = (float)(0.0 + sigma * (f * cd.x1));  // the "cached" second value
+                ++cnt;
+            }
+            chunk_count[(size_t)c] = cnt;
+        };
+        auto worker = [&]() {
+            for (;;) {
+                const uint64_t c = next_chunk.fetch_add(1, std::memory_order_relaxed);
+                if (c >= n_chunks) return;
+                const uint64_t need_words = 4 * std::min(cand, (c + 1) * kChunk);
+                while (words_ready.load(std::memory_order_acquire) < need_words) std::this_thread::yield();
+                process_chunk(c);
+            }
+        };
+        // the MT19937 word stream is sequential: this thread produces it while the others already consume it
+        const int n_workers = cand < 8192 ? 0 : (int)std::min<uint64_t>((uint64_t)std::max(0, threads - 1), n_chunks);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_workers; ++t) pool.emplace_back(worker);
+        {
+            uint64_t w = 0;
+            for (int i = start_pos; i < kN; ++i) words[w++] = temper(key[i]);
+            std::vector<uint32_t> block(key, key + kN);
+            uint64_t published = 0;
+            for (uint64_t b = 0; b < fresh_blocks; ++b) {
+                mt_regenerate(block.data());
+                for (int i = 0; i < kN; ++i) words[w + i] = temper(block[i]);
+                w += kN;
+                if (w - published >= 4 * kChunk / 2) { words_ready.store(w, std::memory_order_release); published = w; }
+            }
+            words_ready.store(w, std::memory_order_release);
         }
-        cand = words.size() / 4;
-        // pass 1: acceptance counts per range
-        int used_threads = 1;
-        counts.assign((size_t)threads + 1, 0);
-        parallel_ranges(cand, threads, [&](int t, uint64_t lo, uint64_t hi) {
-            uint64_t c = 0;
-            for (uint64_t i = lo; i < hi; ++i) c += candidate(&words[4 * i]).ok ? 1 : 0;
-            counts[(size_t)t + 1] = c;
-        });
-        used_threads = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (cand + 4095) / 4096));
-        for (int t = 0; t < used_threads; ++t) counts[(size_t)t + 1] += counts[(size_t)t];
-        const uint64_t accepted = counts[(size_t)used_threads];
+        worker();  // the producer helps with whatever is left (all of it when threads == 1)
+        for (auto& th : pool) th.join();
+
+        // compaction: chunk c's pairs go to out[done + 2 * prefix(c) ...]; the need_pairs-th accepted pair ends the round
+        std::vector<uint64_t> prefix((size_t)n_chunks + 1, 0);
+        for (uint64_t c = 0; c < n_chunks; ++c) prefix[(size_t)c + 1] = prefix[(size_t)c] + chunk_count[(size_t)c];
+        const uint64_t accepted = prefix[(size_t)n_chunks];
         const uint64_t take_pairs = std::min(accepted, need_pairs);
-        // pass 2: outputs of the first take_pairs accepted candidates; remember the index of the last one
-        std::vector<uint64_t> last_idx((size_t)used_threads, 0);
-        double tail_cached = 0.0;
-        bool tail_has = false;
-        parallel_ranges(cand, threads, [&](int t, uint64_t lo, uint64_t hi) {
-            uint64_t rank = counts[(size_t)t];
-            for (uint64_t i = lo; i < hi && rank < take_pairs; ++i) {
-                const Candidate c = candidate(&words[4 * i]);
-                if (!c.ok) continue;
-                const double f = sqrt(-2.0 * log(c.r2) / c.r2);
-                const double g_first = f * c.x2, g_second = f * c.x1;  // returned now / kept for the next call
-                const uint64_t o = done + 2 * rank;
-                out[o] = (float)(0.0 + sigma * g_first);
-                if (o + 1 < n) out[o + 1] = (float)(0.0 + sigma * g_second);
-                else { tail_cached = g_second; tail_has = true; }  // only the very last pair of an odd count
-                ++rank;
-                last_idx[(size_t)t] = i + 1;  // candidates consumed up to here (exclusive)
+        parallel_ranges(n_chunks, threads, [&](int, uint64_t clo, uint64_t chi) {
+            for (uint64_t c = clo; c < chi; ++c) {
+                const uint64_t p0 = prefix[(size_t)c];
+                if (p0 >= take_pairs) break;
+                const uint64_t np = std::min<uint64_t>(chunk_count[(size_t)c], take_pairs - p0);
+                const uint64_t o = done + 2 * p0;
+                const uint64_t nf = std::min<uint64_t>(2 * np, n - o);  // an odd count drops the very last second value
+                memcpy(out + o, &pairs[2 * c * kChunk], nf * sizeof(float));
             }
         });
         uint64_t consumed_cand = cand;  // all of them when this round did not reach the target
         if (take_pairs == need_pairs) {
-            consumed_cand = 0;
-            for (int t = 0; t < used_threads; ++t) consumed_cand = std::max(consumed_cand, last_idx[(size_t)t]);
+            // the candidate that produced the last pair: rescan its chunk
+            uint64_t c = 0;
+            while (prefix[(size_t)c + 1] < need_pairs) ++c;
+            uint64_t left = need_pairs - prefix[(size_t)c];
+            uint64_t i = c * kChunk;
+            Candidate last = candidate(&words[4 * i]);
+            for (;; ++i) {
+                last = candidate(&words[4 * i]);
+                if (last.ok && --left == 0) break;
+            }
+            consumed_cand = i + 1;
+            if (done + 2 * need_pairs > n) {  // odd count: the second value of the last pair stays cached, as a double
+                const double f = sqrt(-2.0 * log(last.r2) / last.r2);
+                *has_gauss = 1;
+                *cached = f * last.x1;
+            }
         }
         done = std::min<uint64_t>(n, done + 2 * take_pairs);
-        if (tail_has) { *has_gauss = 1; *cached = tail_cached; }
-        // generator state after consuming 4 * consumed_cand words from start_pos
         const uint64_t consumed_words = 4 * consumed_cand;
-        const uint64_t in_first = (uint64_t)(kN - start_pos);
+        // generator state after consuming those words from start_pos
         if (consumed_words <= in_first) {
             *pos = start_pos + (int)consumed_words;  // still inside the block the call started in: key unchanged
         } else {
