@@ -178,3 +178,21 @@ def test_numpy_legacy_normal_stream_bit_exact():
         assert np.array_equal(aug.legacy_normal_f32(sigma, 5001), w), sigma
     with pytest.raises(ValueError):
         aug.legacy_normal_f32(-1.0, 4)
+    # any thread count (1 = the calling thread alone produces and consumes) gives the same field and final state
+    import ctypes
+    from robust_object_detection_b200 import _native as N
+    np.random.seed(11)
+    n = 3 * 300 * 401 + 1
+    want = np.random.normal(0, 15, n).astype(np.float32)
+    want_state = np.random.get_state(legacy=True)
+    for threads in (1, 2, 3, 7):
+        np.random.seed(11)
+        st = np.random.get_state(legacy=True)
+        key = np.array(st[1], dtype=np.uint32)
+        pos, has, cached = ctypes.c_int32(st[2]), ctypes.c_int32(st[3]), ctypes.c_double(st[4])
+        out = np.empty(n, np.float32)
+        assert N.lib().rod_numpy_legacy_normal_f32(key.ctypes.data, ctypes.byref(pos), ctypes.byref(has), ctypes.byref(cached),
+                                                   15.0, n, out.ctypes.data, threads) == 0
+        assert np.array_equal(out, want), threads
+        assert np.array_equal(key, want_state[1]) and pos.value == want_state[2], threads
+        assert has.value == want_state[3] and cached.value == want_state[4], threads
