@@ -65,12 +65,24 @@ def write_yolo_valonly_yaml(dst_root: Path):
     (dst_root / "data.yaml").write_text("\n".join(lines), encoding="utf-8")
 
 
-def _corrupt_batch(variant: str, images, philox_index: int):
-    """One ragged batch through the GPU; returns the corrupted arrays (views into one host buffer)."""
+def _corrupt_batch(variant: str, images, philox_index: int, run: "_TreeRun" = None):
+    """One ragged batch through the GPU; returns the corrupted arrays (views into one host buffer).  With a _TreeRun the
+    batch is packed into / returned in page-locked buffers (packing spread over the I/O threads): pageable buffers cost
+    more in the two PCIe copies than the corruption itself."""
     shapes = [(im.shape[0], im.shape[1]) for im in images]
     plan = CorruptionPlan.ragged(shapes)
-    src = plan.pack(images)
-    dst = np.empty(plan.dst_bytes, dtype=np.uint8)
+    if run is not None:
+        src = run.pinned("src", plan.src_bytes)
+        dst = run.pinned_out(plan.dst_bytes)
+
+        def put(args):
+            im, off = args
+            src[off:off + im.size].reshape(im.shape)[...] = im
+
+        list(run.pool.map(put, zip(images, plan.src_offsets)))
+    else:
+        src = plan.pack(images)
+        dst = np.empty(plan.dst_bytes, dtype=np.uint8)
     op = _OPS[variant]
     noise = None
     if variant == "Test_Noise" and NOISE_MODE == "compat":
@@ -101,6 +113,22 @@ class _TreeRun:
         self.cache = {}
         self.cache_bytes = 0
         self.pending = []  # one list of futures per batch in flight
+        self._pinned = {}  # name -> page-locked torch uint8 tensor (grow-only)
+        self._out_turn = 0
+
+    def pinned(self, name: str, nbytes: int) -> np.ndarray:
+        """A page-locked host buffer of at least nbytes, kept for the run (pinning is slow: ~0.3 s per GB)."""
+        import torch
+        t = self._pinned.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8).pin_memory()
+            self._pinned[name] = t
+        return t.numpy()[:nbytes]
+
+    def pinned_out(self, nbytes: int) -> np.ndarray:
+        """Output buffers rotate over three slots: the imwrite futures of at most two batches still read theirs."""
+        self._out_turn = (self._out_turn + 1) % 3
+        return self.pinned(f"dst{self._out_turn}", nbytes)
 
     def decode(self, path: Path):
         import cv2
@@ -155,7 +183,8 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
         if variant == "Test_Clean":
             outs = images
         else:
-            outs = _corrupt_batch(variant, images, philox_index)
+            run.drain(keep=1)  # before the third output slot back is reused
+            outs = _corrupt_batch(variant, images, philox_index, run)
             philox_index += len(images)
         run.drain(keep=1)
         run.pending.append([run.pool.submit(cv2.imwrite, str(dst_img_dir / p.name), o) for (p, _), o in zip(decoded, outs)])
