@@ -170,20 +170,34 @@ def _apply_random_corruption(img_bgr: np.ndarray) -> np.ndarray:
 class RandomCorruption:
     """PIL Image transform that randomly applies one corruption (torchvision pipelines).
 
-    All three corruptions act per channel, so the RGB<->BGR swaps of the reference
-    (augmentations.py:72,74) only decide which noise plane meets which channel: the image is
-    reversed along the channel axis before and after, as the reference does."""
+    The reference converts RGB -> BGR, corrupts, converts back (augmentations.py:72-74).  Blur and LowRes act on each
+    channel separately and identically, so they are applied to the RGB array as it is (same bytes, no swaps); only
+    for noise does the channel order decide which plane of the field meets which channel, so only there is the image
+    swapped (cv2.cvtColor when OpenCV is importable, a NumPy reversal otherwise).  The `random` draws are the
+    reference's: random() for the gate, then random.choice inside _apply_random_corruption's dispatch."""
 
     def __init__(self, p: float = 0.5):
         self.p = p
+
+    @staticmethod
+    def _swap(arr: np.ndarray) -> np.ndarray:
+        try:
+            import cv2
+            return cv2.cvtColor(arr, cv2.COLOR_RGB2BGR)
+        except ImportError:  # pragma: no cover
+            return np.ascontiguousarray(arr[:, :, ::-1])
 
     def __call__(self, img):
         from PIL import Image
         if random.random() > self.p:
             return img
-        arr = np.array(img)[:, :, ::-1]          # RGB -> BGR (a strided view; compacted on upload)
-        arr = _apply_random_corruption(np.ascontiguousarray(arr))
-        return Image.fromarray(np.ascontiguousarray(arr[:, :, ::-1]))
+        rgb = np.array(img)
+        name = random.choice(["noise", "blur", "lowres"])  # the draw of _apply_random_corruption (augmentations.py:50)
+        if name == "noise":
+            out = self._swap(_DISPATCH[name](self._swap(rgb)))
+        else:
+            out = _DISPATCH[name](rgb)
+        return Image.fromarray(out)
 
 
 # ---- Ultralytics: monkey-patch Albumentations ----
