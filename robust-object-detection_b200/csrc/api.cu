@@ -279,14 +279,20 @@ extern "C" int rod_apply_host(rod_plan* plan, int op, const uint8_t* src_host, u
     if (compat && plan->d_stage_noise == nullptr)
         ROD_CUDA(cudaMalloc((void**)&plan->d_stage_noise, plan->payload_bytes * sizeof(float) + 64));
 
-    // chunking: ~32 MiB of payload per chunk when the layout allows per-chunk byte ranges
+    // chunking: ~16 MiB of payload per chunk when the layout allows per-chunk byte ranges (knob: ROD_HOST_CHUNK_MB;
+    // measured e2e on a B200 box: 16 MiB 13.9 k img/s, 32: 13.6, 64: 13.7, 128: 13.3)
+    static const uint64_t chunk_bytes = [] {
+        const char* e = getenv("ROD_HOST_CHUNK_MB");
+        const int mb = e ? atoi(e) : 16;
+        return (uint64_t)(mb >= 1 && mb <= 4096 ? mb : 16) << 20;
+    }();
     const int n = plan->n_images;
     std::vector<int> cuts{0};
     if (plan->monotonic && n > 1) {
         uint64_t acc = 0;
         for (int i = 0; i < n; ++i) {
             acc += 3ull * plan->descs[i].height * plan->descs[i].width;
-            if (acc >= (32ull << 20) && i + 1 < n) { cuts.push_back(i + 1); acc = 0; }
+            if (acc >= chunk_bytes && i + 1 < n) { cuts.push_back(i + 1); acc = 0; }
         }
     }
     cuts.push_back(n);
