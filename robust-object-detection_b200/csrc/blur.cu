@@ -167,8 +167,11 @@ int launch_blur(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, c
     // per-warp buffer: kBlurLeft | (shift + 3w rounded up to 16) | 16 (right window) + halo, 16-byte multiple
     const int row_bytes = 3 * plan->max_w;
     p.row_buf_bytes = kBlurLeft + ((15 + row_bytes + 15) & ~15) + 64;
-    const size_t smem = (size_t)p.row_buf_bytes * kBlurRowsPerTile;
-    if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;  // rows wider than ~9400 pixels
+    // one row buffer per warp: very wide rows run with fewer warps per CTA (the kernel has no block-level coupling)
+    int warps = kBlurRowsPerTile;
+    while (warps > 1 && (size_t)p.row_buf_bytes * warps > 227 * 1024) --warps;
+    const size_t smem = (size_t)p.row_buf_bytes * warps;
+    if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;  // a single row does not fit: wider than ~77 000 pixels
     int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     // measured on B200 (256 x 1360x765): 4 resident CTAs (32 warps) per SM -> 5.79 TB/s; 5 -> 5.62; 6 -> 5.57; 3 -> 5.66
@@ -177,13 +180,13 @@ int launch_blur(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, c
     if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 4) ctas_per_sm = atoi(e_ctas);
     p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
     ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
-    const int grid = grid_for(plan, (p.n_tiles + 7) / 8, ctas_per_sm);
+    const int grid = grid_for(plan, (p.n_tiles + warps - 1) / warps, ctas_per_sm);
     if (k == 9) {
         ROD_CUDA(cudaFuncSetAttribute(blur_rows_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        blur_rows_kernel<9><<<grid, 256, smem, stream>>>(p);
+        blur_rows_kernel<9><<<grid, 32 * warps, smem, stream>>>(p);
     } else {
         ROD_CUDA(cudaFuncSetAttribute(blur_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        blur_rows_kernel<0><<<grid, 256, smem, stream>>>(p);
+        blur_rows_kernel<0><<<grid, 32 * warps, smem, stream>>>(p);
     }
     ROD_CUDA(cudaGetLastError());
     return ROD_OK;

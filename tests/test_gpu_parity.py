@@ -454,6 +454,20 @@ def test_lowres_marching_kernel_alignments(torch_):
     assert np.array_equal(out[0], want[0]) and np.array_equal(out[2], want[0]) and (out[1] == 9).all()
 
 
+def test_very_wide_rows(aug):
+    """Rows far wider than any VisDrone frame (panoramas): the blur kernel keeps a whole row per warp in shared memory and
+    drops to fewer warps per CTA when 8 rows no longer fit; the other kernels tile in x.  Bit-exact vs the oracle."""
+    for h, w in [(3, 12000), (2, 30001), (5, 9500)]:
+        img = synth(9900 + h, h, w)
+        assert np.array_equal(aug.apply_motion_blur(img, 9, 0), orc.apply_motion_blur(img, 9, 0)), (h, w)
+        assert np.array_equal(aug.apply_motion_blur(img, 5, 0), orc.apply_motion_blur(img, 5, 0)), (h, w)
+        assert np.array_equal(aug.apply_lowres(img, 0.5), orc.apply_lowres(img, 0.5)), (h, w)
+        np.random.seed(3)
+        got = aug.apply_noise(img, 15)
+        np.random.seed(3)
+        assert np.array_equal(got, orc.apply_noise(img, 15)), (h, w)
+
+
 def test_full_size_config2_batch_by_replication(torch_):
     """BASELINE config 2 at full size (256 x 765x1360): 8 distinct images repeated 32 times; every
     replica must equal the oracle's output for its source image (bit-exact)."""
