@@ -95,8 +95,25 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(op="blur", budget_images=None):
     """The reference's CPU path for the same op on a bounded sample of the same workload."""
+    out = _cpu_baseline(op, budget_images)
+    out["cpu_model"] = cpu_model()
+    return out
+
+
+def _cpu_baseline(op="blur", budget_images=None):
     from oracle import cv2_port
     if not cv2_port.available():
         from oracle import corruption_oracle as orc
@@ -165,7 +182,8 @@ def run_reference(args):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "configs[1]: motion blur k=9 angle=0, 1360x765x3 uint8, bounded sample per step",
                        "sample": desc},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                             "cpu_model": cpu_model()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
