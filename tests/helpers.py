@@ -19,3 +19,20 @@ def sha(a):
 
 SMALL_SHAPES = [(1, 1), (1, 7), (7, 1), (2, 2), (2, 3), (3, 5), (4, 2), (5, 4), (8, 8), (9, 13),
                 (17, 9), (16, 48), (33, 47), (64, 64), (31, 100), (48, 129)]
+
+
+def spawn_worker_corrupt(args):
+    """Runs in a spawn()ed worker process (tests/test_gpu_parity.py::test_spawned_dataloader_workers): the drop-in
+    functions initialise CUDA in the calling process, like a DataLoader worker started with the spawn method."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import random
+    import numpy as np
+    from robust_object_detection_b200 import augmentations as aug
+    seed, h, w = args
+    img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    random.seed(seed)
+    np.random.seed(seed)
+    outs = [aug._apply_random_corruption(img) for _ in range(4)]
+    return seed, [o.tobytes() for o in outs]

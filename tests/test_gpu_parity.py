@@ -454,6 +454,24 @@ def test_lowres_marching_kernel_alignments(torch_):
     assert np.array_equal(out[0], want[0]) and np.array_equal(out[2], want[0]) and (out[1] == 9).all()
 
 
+def test_spawned_dataloader_workers(aug):
+    """The process model of INTEGRATION.md section 2: DataLoader-style workers started with the SPAWN method each
+    initialise CUDA on their own and run the per-image hook; every worker's outputs equal what the oracle gives for the
+    same seeds (random / np.random streams are per process, as in the reference's workers)."""
+    import multiprocessing as mp
+    from tests.helpers import spawn_worker_corrupt
+    jobs = [(101, 97, 133), (202, 120, 200), (303, 64, 64), (404, 81, 90)]
+    with mp.get_context("spawn").Pool(2) as pool:
+        results = dict(pool.map(spawn_worker_corrupt, jobs))
+    for seed, h, w in jobs:
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        random.seed(seed)
+        np.random.seed(seed)
+        want = [orc.apply_op(img, 1 + ("noise", "blur", "lowres").index(random.choice(["noise", "blur", "lowres"])))
+                for _ in range(4)]
+        assert [o.tobytes() for o in want] == results[seed], seed
+
+
 def test_very_wide_rows(aug):
     """Rows far wider than any VisDrone frame (panoramas): the blur kernel keeps a whole row per warp in shared memory and
     drops to fewer warps per CTA when 8 rows no longer fit; the other kernels tile in x.  Bit-exact vs the oracle."""
