@@ -139,6 +139,7 @@ struct FusedLbParams {
     int out_h, out_w, pad;
     float K;                 // sigma * sqrt(2 ln 2)
     uint32_t key0, key1, offset;
+    PhiloxKeys keys;  // the ten round keys of (key0, key1): constant-bank / uniform operands, no per-round key additions
     uint64_t first_image;
     int k;                   // blur taps (odd)
     const DevShape* shapes;  // lowres tables (plan->d_shapes / d_tab), used when lowres_in_kernel
@@ -186,7 +187,7 @@ __device__ __forceinline__ void fused_noise_row(const FusedLbParams& p, const De
     for (uint32_t g = g_first + lane; g <= g_last; g += 32) {
         uint32_t r[4];
         float sf[8];
-        philox4x32_10(g, (uint32_t)ig, (uint32_t)(ig >> 32), p.offset, p.key0, p.key1, r);
+        philox4x32_10_rk(g, (uint32_t)ig, (uint32_t)(ig >> 32), p.offset, p.keys, r);
         if (philox_needs_tail(r)) {
             uint32_t t[4];
             philox4x32_10(g, (uint32_t)ig, (uint32_t)(ig >> 32) ^ ROD_PHILOX_TAIL_FLIP, p.offset, p.key0, p.key1, t);
@@ -463,6 +464,7 @@ int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8
     p.out_h = plan->lb_out_h; p.out_w = plan->lb_out_w; p.pad = pad_value;
     p.K = sigma * ROD_NOISE_K_PER_SIGMA;
     p.key0 = (uint32_t)seed; p.key1 = (uint32_t)(seed >> 32); p.offset = offset; p.first_image = first_image;
+    p.keys = philox_round_keys(p.key0, p.key1);
     p.k = k;
     p.buf_bytes = kFusedLeft + ((3 * plan->max_w + 15) & ~15) + 128;  // also holds two low-res rows (3 * max_w / 2 + 39 each)
     p.xtab_bytes = ((p.out_w * 8 + 15) & ~15) + 16;  // + the broadcast slot of the dynamic tile index
