@@ -21,6 +21,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <new>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -127,8 +129,12 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
         const uint64_t total_words = in_first + fresh_blocks * kN;
         cand = total_words / 4;
         const uint64_t n_chunks = (cand + kChunk - 1) / kChunk;
-        if (words.size() < total_words) words.resize(total_words);
-        if (pairs.size() < 2 * cand) pairs.resize(2 * cand);
+        try {
+            if (words.size() < total_words) words.resize(total_words);
+            if (pairs.size() < 2 * cand) pairs.resize(2 * cand);
+        } catch (const std::bad_alloc&) {
+            return ROD_ERR_OOM;  // nothing consumed yet in this round: the generator state is still the caller's
+        }
         std::vector<uint32_t> chunk_count((size_t)n_chunks, 0);
         std::atomic<uint64_t> words_ready{0}, next_chunk{0};
 
@@ -159,7 +165,13 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
         // the MT19937 word stream is sequential: this thread produces it while the others already consume it
         const int n_workers = cand < 8192 ? 0 : (int)std::min<uint64_t>((uint64_t)std::max(0, threads - 1), n_chunks);
         std::vector<std::thread> pool;
-        for (int t = 0; t < n_workers; ++t) pool.emplace_back(worker);
+        for (int t = 0; t < n_workers; ++t) {
+            try {
+                pool.emplace_back(worker);
+            } catch (const std::system_error&) {
+                break;  // no more threads to be had: the ones running (and this one) do all chunks
+            }
+        }
         {
             uint64_t w = 0;
             for (int i = start_pos; i < kN; ++i) words[w++] = temper(key[i]);
