@@ -139,6 +139,22 @@ def test_unsupported_parameters_raise(aug):
         aug.apply_lowres(img, 1.5)
     with pytest.raises(NotImplementedError):
         aug.apply_lowres(synth(2, 64, 64), 0.05)  # > 8 area taps: outside the exact-parity domain
+    # C ABI argument checks of the newer entry points: status codes, never a crash
+    from robust_object_detection_b200 import _native as N
+    from robust_object_detection_b200.batch import CorruptionPlan
+    plan = CorruptionPlan.uniform(1, 16, 16)
+    assert N.lib().rod_plan_set_gaussian_generator(plan._h, 7) == N.ROD_ERR_INVALID_ARG
+    assert N.lib().rod_plan_set_gaussian_generator(None, 0) == N.ROD_ERR_INVALID_ARG
+    import ctypes
+    pos, has, cached = ctypes.c_int32(700), ctypes.c_int32(0), ctypes.c_double(0.0)
+    key = np.zeros(624, np.uint32)
+    out = np.zeros(4, np.float32)
+    assert N.lib().rod_numpy_legacy_normal_f32(key.ctypes.data, ctypes.byref(pos), ctypes.byref(has), ctypes.byref(cached),
+                                               1.0, 4, out.ctypes.data, 1) == N.ROD_ERR_INVALID_ARG   # pos > 624
+    with pytest.raises(NotImplementedError):
+        import torch
+        big = torch.zeros((1, 16, 16, 3), dtype=torch.uint8, device="cuda")
+        plan.noise(big, big.clone(), None, 5000.0)   # Philox sigma beyond int16 offsets
 
 
 # ------------------------------------------------------------------ random apply + adapters

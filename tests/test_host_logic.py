@@ -196,3 +196,35 @@ def test_numpy_legacy_normal_stream_bit_exact():
         assert np.array_equal(out, want), threads
         assert np.array_equal(key, want_state[1]) and pos.value == want_state[2], threads
         assert has.value == want_state[3] and cached.value == want_state[4], threads
+
+
+def test_numpy_legacy_normal_random_call_sequences():
+    """Property test (hypothesis): any interleaving of np.random consumers and legacy_normal_f32 calls of random sizes,
+    from any seed, produces the same values as the all-NumPy run and leaves the same generator state."""
+    from hypothesis import given, settings, strategies as st
+    from robust_object_detection_b200 import augmentations as aug
+
+    step = st.one_of(st.tuples(st.just("normal"), st.integers(1, 5000), st.sampled_from([15.0, 1.0, 2.5])),
+                     st.tuples(st.just("uniform"), st.integers(1, 700), st.just(0.0)),
+                     st.tuples(st.just("std"), st.integers(1, 9), st.just(0.0)))
+
+    @settings(max_examples=25, deadline=None)
+    @given(seed=st.integers(0, 2 ** 32 - 1), steps=st.lists(step, min_size=1, max_size=8))
+    def run(seed, steps):
+        def play(ours):
+            np.random.seed(seed)
+            out = []
+            for kind, n, sigma in steps:
+                if kind == "normal":
+                    out.append(aug.legacy_normal_f32(sigma, n) if ours else np.random.normal(0, sigma, n).astype(np.float32))
+                elif kind == "uniform":
+                    out.append(np.random.random(n))
+                else:
+                    out.append(np.random.standard_normal(n))
+            return out, np.random.get_state(legacy=True)
+        a, sa = play(False)
+        b, sb = play(True)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]
+
+    run()
