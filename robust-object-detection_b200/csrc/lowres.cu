@@ -38,6 +38,8 @@ constexpr int kHxPitch = kLowresTWB + 8;
 
 
 __device__ __forceinline__ uint32_t ldg32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+// exact float of a byte: 0x4B0000bb is 2^23 + bb
+__device__ __forceinline__ float u8f(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
 
 __device__ __forceinline__ void store_chunk8(uint8_t* p, uint32_t lo, uint32_t hi, int nvalid) {
     // p is the address of the chunk's first byte; alignment depends on the row (warp-uniform)
@@ -132,10 +134,11 @@ __global__ void __launch_bounds__(256, 3) lowres_kernel(LowresParams p) {
                 for (int q = 0; q < 4; ++q) al[q] = (q < nx) ? xalpha[dx * sh.xt + q] : 0.f;
                 const int o1 = 3 * min(1, nx - 1), o2 = 3 * min(2, nx - 1), o3 = 3 * min(3, nx - 1);
                 for (int sr = 0; sr < nsr; ++sr, sp += im.src_pitch, hb += p.hb_pitch) {
-                    float buf = fmul((float)sp[0], al[0]);
-                    buf = fadd(buf, fmul((float)sp[o1], al[1]));
-                    buf = fadd(buf, fmul((float)sp[o2], al[2]));
-                    buf = fadd(buf, fmul((float)sp[o3], al[3]));
+                    // byte -> float through the 2^23 mantissa trick (LOP3 + FADD) instead of I2F on the quarter-rate XU pipe
+                    float buf = fmul(u8f(sp[0]), al[0]);
+                    buf = fadd(buf, fmul(u8f(sp[o1]), al[1]));
+                    buf = fadd(buf, fmul(u8f(sp[o2]), al[2]));
+                    buf = fadd(buf, fmul(u8f(sp[o3]), al[3]));
                     *hb = buf;
                 }
             } else if (general) {
