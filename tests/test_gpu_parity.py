@@ -488,6 +488,41 @@ def test_spawned_dataloader_workers(aug):
         assert [o.tobytes() for o in want] == results[seed], seed
 
 
+def test_cuda_graph_capture_and_replay(torch_):
+    """The device-resident entry points are stream-ordered (memset of the work counter + kernels): a corrupt_batch and a
+    corrupt_letterbox call captured into a CUDA graph (after one eager call: resize tables, the noise quantile table and
+    the auxiliary streams are created on first use) replay to the same bytes on new input contents."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    n, h, w = 6, 360, 480
+    plan = CorruptionPlan.uniform(n, h, w)
+    ops = torch_.tensor([1, 2, 3, 0, 2, 1], dtype=torch_.uint8, device="cuda")
+    src = torch_.from_numpy(np.stack([synth(9500 + i, h, w) for i in range(n)])).cuda()
+    dst = torch_.zeros_like(src)
+    f16 = torch_.zeros((n, 3, 160, 160), dtype=torch_.float16, device="cuda")
+    plan.corrupt(src, dst, ops, seed=5)                       # eager warm-up
+    plan.corrupt_letterbox(src, ops, f16, 160, 160, 114, seed=5)
+    torch_.cuda.synchronize()
+    g = torch_.cuda.CUDAGraph()
+    with torch_.cuda.graph(g):
+        plan.corrupt(src, dst, ops, seed=5)
+        plan.corrupt_letterbox(src, ops, f16, 160, 160, 114, seed=5)
+    for rep in range(2):
+        new = np.stack([synth(9600 + 10 * rep + i, h, w) for i in range(n)])
+        src.copy_(torch_.from_numpy(new).cuda())
+        dst.zero_()
+        f16.zero_()
+        g.replay()
+        torch_.cuda.synchronize()
+        got, got16 = dst.cpu().numpy(), f16.cpu().numpy()
+        want = torch_.zeros_like(src)
+        want16 = torch_.zeros_like(f16)
+        plan.corrupt(src, want, ops, seed=5)
+        plan.corrupt_letterbox(src, ops, want16, 160, 160, 114, seed=5)
+        assert np.array_equal(got, want.cpu().numpy()) and np.array_equal(got16, want16.cpu().numpy()), rep
+        assert np.array_equal(got[1], orc.apply_motion_blur(new[1], 9, 0)) and np.array_equal(got[2], orc.apply_lowres(new[2], 0.5))
+        assert np.array_equal(got[3], new[3])
+
+
 def test_very_wide_rows(aug):
     """Rows far wider than any VisDrone frame (panoramas): the blur kernel keeps a whole row per warp in shared memory and
     drops to fewer warps per CTA when 8 rows no longer fit; the other kernels tile in x.  Bit-exact vs the oracle."""
