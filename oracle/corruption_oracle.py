@@ -67,7 +67,7 @@ def apply_noise(img: np.ndarray, sigma: float) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------
-# Philox4x32-10 + inverse-CDF table / Box-Muller (the GPU "philox" noise mode; no reference twin --
+# Philox4x32-10 + quantile-table pairs / Box-Muller (the GPU "philox" noise mode; no reference twin --
 # this restates OUR kernels' documented streams so tests can check them exactly).
 # ----------------------------------------------------------------------------
 _PHILOX_M0 = np.uint64(0xD2511F53)
