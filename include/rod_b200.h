@@ -82,11 +82,11 @@ ROD_API int  rod_plan_launches(const rod_plan* plan, int op);
  * philox mode (noise == NULL): the field is generated in registers: one Philox4x32-10 block
  *   (key = seed, counter = (element/8, first_image_index + i, offset)) serves 8 consecutive elements,
  *   16 bits each.  Two Gaussian generators (csrc/rod_core.h defines both; the oracle restates both):
- *     table      (sigma <= 21; default there): integer arithmetic only -- each Philox word gives two 15-bit draws
+ *     table      (1 <= sigma <= 21; default there): integer arithmetic only -- each Philox word gives two 15-bit draws
  *                from a 64 KB shared-memory quantile table of N(0, sigma^2/2) (1/256 units) and the pair is rotated
  *                by 45 degrees, k0 = floor((x + y)/256), k1 = floor((x - y)/256): independent, ~2^30 values each,
  *                tails to 5.9 sigma;
- *     Box-Muller (sigma <= 2048; default above 21, rod_plan_set_gaussian_generator(ROD_GAUSS_BOXMULLER), and always
+ *     Box-Muller (sigma <= 2048; default outside [1, 21], rod_plan_set_gaussian_generator(ROD_GAUSS_BOXMULLER), and always
  *                on the training path rod_corrupt_letterbox_f16): 16-bit stratified radius with a 32-bit
  *                tail refinement, 16-bit angle.
  *   result is clamp(src + floor(noise), 0, 255).  Reproducible for any batch split / GPU count;
@@ -100,7 +100,7 @@ ROD_API int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst,
 /* The float32 field philox mode adds (same layout as `noise` above); for tests/resume. */
 ROD_API int rod_noise_field_f32(const rod_plan* plan, float* out_field, float sigma, uint64_t seed,
                         uint64_t first_image_index, uint32_t offset, void* stream);
-/* Philox-mode Gaussian generator of this plan: ROD_GAUSS_AUTO (0, default: table when sigma <= 21, else
+/* Philox-mode Gaussian generator of this plan: ROD_GAUSS_AUTO (0, default: table when 1 <= sigma <= 21, else
  * Box-Muller) or ROD_GAUSS_BOXMULLER (1). */
 #define ROD_GAUSS_AUTO 0
 #define ROD_GAUSS_BOXMULLER 1

@@ -104,6 +104,7 @@ _ANGLE_BIAS = float(np.float32(-804.2476806640625))        # float32((0.5 - 2^23
 
 
 GAUSS_TABLE_MAX_SIGMA = 21.0   # rod_core.h ROD_GAUSS_TABLE_MAX_SIGMA
+GAUSS_TABLE_MIN_SIGMA = 1.0    # rod_core.h ROD_GAUSS_TABLE_MIN_SIGMA
 GAUSS_TABLE_BIAS = 16384
 
 
@@ -146,9 +147,10 @@ def philox_noise_field_table(n_elems: int, sigma: float, seed: int, image_index:
 def philox_noise_field(n_elems: int, sigma: float, seed: int, image_index: int,
                        offset: int = 0, generator: str = "auto") -> np.ndarray:
     """The field Philox mode adds: generator "auto" (what rod_noise_u8 / rod_corrupt_batch_u8 use: the table
-    generator for sigma <= 21, else Box-Muller), "table", or "boxmuller" (always used by the training path,
+    generator for 1 <= sigma <= 21, else Box-Muller), "table", or "boxmuller" (always used by the training path,
     rod_corrupt_letterbox_f16)."""
-    if generator == "table" or (generator == "auto" and float(np.float32(sigma)) <= GAUSS_TABLE_MAX_SIGMA):
+    if generator == "table" or (generator == "auto" and
+                                GAUSS_TABLE_MIN_SIGMA <= float(np.float32(sigma)) <= GAUSS_TABLE_MAX_SIGMA):
         return philox_noise_field_table(n_elems, sigma, seed, image_index, offset)
     return philox_noise_field_boxmuller(n_elems, sigma, seed, image_index, offset)
 

@@ -19,8 +19,8 @@ Noise modes.  'compat' (default) draws the field on the host with
 np.random.normal(0, sigma, shape).astype(float32) -- consuming NumPy's global legacy stream
 exactly like the reference -- and the GPU does the add/clip/truncate, so outputs are
 bit-identical to the reference under the same np.random.seed.  'philox' generates the field
-inside the kernel (Philox4x32-10 keyed by seed and a running image counter; for sigma <= 21 two 15-bit draws per
-Philox word from a 64 KB shared-memory quantile table, rotated by 45 degrees in integer arithmetic; Box-Muller above):
+inside the kernel (Philox4x32-10 keyed by seed and a running image counter; for 1 <= sigma <= 21 two 15-bit draws per
+Philox word from a 64 KB shared-memory quantile table, rotated by 45 degrees in integer arithmetic; Box-Muller otherwise):
 no host RNG work, statistically equivalent, not bit-identical.
 """
 from __future__ import annotations

@@ -158,7 +158,7 @@ class CorruptionPlan:
                                             int(offset), _stream_handle(stream)), "rod_noise_field_f32")
 
     def set_gaussian_generator(self, generator: int) -> None:
-        """Philox-mode Gaussian generator of this plan: 0 = auto (quantile table when sigma <= 21, else
+        """Philox-mode Gaussian generator of this plan: 0 = auto (quantile table when 1 <= sigma <= 21, else
         Box-Muller), 1 = Box-Muller.  include/rod_b200.h rod_plan_set_gaussian_generator."""
         N.check(N.lib().rod_plan_set_gaussian_generator(self._h, int(generator)), "rod_plan_set_gaussian_generator")
 

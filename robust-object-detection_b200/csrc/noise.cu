@@ -4,7 +4,7 @@
 //   NOISE_COMPAT  a supplied float32 tensor (what np.random.normal(...).astype(f32) drew) -> bit-exact
 //   NOISE_PHILOX  Philox4x32-10 keyed by (seed, global image index, element/8, offset), no HBM traffic for
 //                 the field; two Gaussian generators on the same Philox blocks (rod_core.h):
-//                   table      (sigma <= 21, noise_table_kernel): two 15-bit draws from a 64 KB shared-memory quantile
+//                   table      (1 <= sigma <= 21, noise_table_kernel): two 15-bit draws from a 64 KB shared-memory quantile
 //                              table per Philox word, rotated by 45 degrees in integer arithmetic -- no MUFU
 //                   Box-Muller (any sigma <= 2048, noise_kernel<NOISE_PHILOX>): 4 MUFU per pair, XU-pipe bound
 // plus NOISE_COPY (ROD_OP_NONE images of a mixed batch) and NOISE_FIELD (dump the Philox field).
@@ -409,7 +409,8 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
     int per_sm = 4;  // CTAs per SM the grid is sized for: 4 are resident, a longer queue evens out the tail (knob: ROD_NOISE_CTAS)
     const char* e_ctas = getenv("ROD_NOISE_CTAS");
     if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 64) per_sm = atoi(e_ctas);
-    if ((mode == NOISE_PHILOX || mode == NOISE_FIELD) && generator == ROD_GAUSS_AUTO && sigma <= ROD_GAUSS_TABLE_MAX_SIGMA) {
+    if ((mode == NOISE_PHILOX || mode == NOISE_FIELD) && generator == ROD_GAUSS_AUTO && sigma >= ROD_GAUSS_TABLE_MIN_SIGMA &&
+        sigma <= ROD_GAUSS_TABLE_MAX_SIGMA) {
         int rc = gauss_table_for(plan->device, sigma, &p.table);
         if (rc != ROD_OK) return rc;
         // one 1024-thread CTA per SM, each with its own copy of the table; warps take quarter spans

@@ -233,7 +233,8 @@ ROD_HD uint32_t noise_philox_px(uint32_t v, float s, float K) {
     return (uint32_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
 }
 
-// Philox-mode noise, TABLE generator (noise.cu noise_table_kernel; used when sigma <= ROD_GAUSS_TABLE_MAX_SIGMA).
+// Philox-mode noise, TABLE generator (noise.cu noise_table_kernel; used when ROD_GAUSS_TABLE_MIN_SIGMA <= sigma <=
+// ROD_GAUSS_TABLE_MAX_SIGMA).
 // The same Philox block r[4] of group g as the Box-Muller generator, but integer arithmetic only:
 //   A[i], i = 0..32767 : the 15-bit stratified quantile table of N(0, sigma^2 / 2) in 1/256 units, stored biased:
 //                        A[i] = round(256 * (sigma / sqrt 2) * Phi^-1((i + 0.5) / 32768)) + 16384      (uint16, < 32768)
@@ -245,6 +246,7 @@ ROD_HD uint32_t noise_philox_px(uint32_t v, float s, float K) {
 // each with ~2^30 distinct values and tails to 5.9 sigma, so no separate tail draw is needed.  On the device this is
 // two 16-bit shared-memory loads and integer multiply-adds per pair -- no MUFU, no floating point.
 #define ROD_GAUSS_TABLE_MAX_SIGMA 21.0f  // 256 * (sigma / sqrt 2) * 4.17 must stay below 16384
+#define ROD_GAUSS_TABLE_MIN_SIGMA 1.0f   // below, the 1/256 grid of the table is no longer fine against sigma (Box-Muller)
 #define ROD_GAUSS_TABLE_BIAS 16384
 #ifndef ROD_GAUSS_AUTO
 #define ROD_GAUSS_AUTO 0                 // table generator when sigma <= ROD_GAUSS_TABLE_MAX_SIGMA, else Box-Muller

@@ -215,15 +215,16 @@ def test_ultralytics_patch_with_stub_module(aug, golden_hashes, monkeypatch):
 # ------------------------------------------------------------------ Philox mode
 def test_philox_field_and_fused_output(torch_):
     """Both Gaussian generators of Philox mode against their restated streams: the table generator (default at
-    sigma <= 21) is integer arithmetic and matches exactly; Box-Muller (forced per plan, or sigma > 21) within float
-    tolerance."""
+    1 <= sigma <= 21) is integer arithmetic and matches exactly; Box-Muller (forced per plan, or sigma outside that
+    range) within float tolerance."""
     from robust_object_detection_b200.batch import CorruptionPlan
     shapes = [(37, 53), (64, 64), (31, 45)]
     plan = CorruptionPlan.ragged(shapes)
     imgs = [synth(50 + i, h, w) for i, (h, w) in enumerate(shapes)]
     src = torch_.from_numpy(plan.pack(imgs)).cuda()
     seed, first, off = 0x1234567890ABCDEF, 5, 3
-    for generator, sigma in (("table", 15.0), ("table", 4.5), ("boxmuller", 15.0), ("auto-boxmuller", 40.0)):
+    for generator, sigma in (("table", 15.0), ("table", 4.5), ("table", 1.0), ("boxmuller", 15.0), ("auto-boxmuller", 40.0),
+                             ("auto-boxmuller", 0.5)):
         plan.set_gaussian_generator(1 if generator == "boxmuller" else 0)
         dst = torch_.zeros_like(src)
         field = torch_.zeros(plan.payload_bytes, dtype=torch_.float32, device="cuda")
@@ -240,7 +241,7 @@ def test_philox_field_and_fused_output(torch_):
                 assert np.array_equal(outs[i], orc.add_philox_noise(img, want)), (generator, sigma, i)
             else:
                 want = orc.philox_noise_field(n, sigma, seed, first + i, off, generator="boxmuller")
-                assert np.max(np.abs(f[e:e + n] - want)) < 2e-3 * sigma / 15.0, (generator, i)
+                assert np.max(np.abs(f[e:e + n] - want)) < max(2e-3 * sigma / 15.0, 2e-5), (generator, sigma, i)
                 # the kernel adds the field it reports: clamp(v + floor(noise), 0, 255); the dumped field is the
                 # fp32-rounded product, the kernel floors the unrounded one, so a byte may differ only where noise
                 # is within an ulp of an integer
