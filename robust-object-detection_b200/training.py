@@ -143,6 +143,70 @@ class CorruptionBatcher:
             k += 1
 
 
+class RestorationPairBatcher:
+    """Host-level drop-in for the pair generation of RestorationDataset.__getitem__ (train_restoration.py:104-129), one
+    batch at a time: for every decoded frame (HWC BGR uint8, at least patch_size in both dimensions) the decisions are
+    drawn in the reference's order (random crop position, flip, random.choice of the corruption; centre crop and no
+    flip for validation), only the CROP is uploaded (the frame itself never leaves the host), and
+    rod_restoration_pairs_f32 produces both tensors on the device:
+
+        pairs = RestorationPairBatcher(patch_size=256, is_train=True)
+        corrupted, clean = pairs(frames)        # float32 [B,3,P,P] RGB in [0,1], on the GPU
+
+    noise="compat" draws each noise patch's field from NumPy's global legacy stream (bit-identical to the reference under
+    the same seeds: augmentations.legacy_normal_f32); noise="philox" generates it in the kernel, keyed by (seed, running
+    sample index)."""
+
+    def __init__(self, patch_size: int = 256, is_train: bool = True, noise: str = "compat", seed: int = 0):
+        import torch
+        if noise not in ("compat", "philox"):
+            raise ValueError("noise must be 'compat' or 'philox'")
+        self._torch = torch
+        self.size, self.is_train, self.noise, self.seed = int(patch_size), bool(is_train), noise, int(seed)
+        self._plans: dict = {}
+        self.samples_seen = 0
+        self.last_decisions: List[tuple] = []
+
+    def __call__(self, frames: Sequence[np.ndarray]):
+        from .augmentations import NOISE_SIGMA, legacy_normal_f32
+        from .batch import draw_restoration_decisions
+        torch, P, n = self._torch, self.size, len(frames)
+        if n not in self._plans:  # crops are staged back to back: one plan per batch size
+            offs = [i * 3 * P * P for i in range(n)]
+            self._plans[n] = (CorruptionPlan([(P, P)] * n, offs, [0] * n),
+                              torch.empty(n * 3 * P * P, dtype=torch.uint8).pin_memory())
+        plan, hbuf = self._plans[n]
+        crops = hbuf.numpy().reshape(n, P, P, 3)
+        dec, fields = [], []
+        for i, im in enumerate(frames):
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError("expected HWC uint8 BGR frames")
+            y, x, flip, op = draw_restoration_decisions(int(im.shape[0]), int(im.shape[1]), P, self.is_train)
+            crops[i] = im[y:y + P, x:x + P]
+            if op == 1 and self.noise == "compat":  # the draw of apply_noise on the (flipped) patch, in sample order
+                fields.append(legacy_normal_f32(NOISE_SIGMA, (P, P, 3)).reshape(-1))
+            elif self.noise == "compat":
+                fields.append(None)
+            dec.append((y, x, flip, op))
+        self.last_decisions = dec
+        src = hbuf.cuda()  # (synchronous for the host: the pinned crop buffer is rewritten by the next call)
+        flips = torch.tensor([int(d[2]) for d in dec], dtype=torch.uint8).cuda()
+        ops = torch.tensor([d[3] for d in dec], dtype=torch.uint8).cuda()
+        nz = None
+        if self.noise == "compat" and any(f is not None for f in fields):
+            host = np.zeros((n, 3 * P * P), dtype=np.float32)
+            for i, f in enumerate(fields):
+                if f is not None:
+                    host[i] = f
+            nz = torch.from_numpy(host.reshape(-1)).cuda()
+        corrupted = torch.empty((n, 3, P, P), dtype=torch.float32, device="cuda")
+        clean = torch.empty_like(corrupted)
+        plan.restoration_pairs(src, flips, ops, corrupted, clean, noise=nz, sigma=float(NOISE_SIGMA), seed=self.seed,
+                               first_image_index=self.samples_seen)
+        self.samples_seen += n
+        return corrupted, clean
+
+
 def patch_ultralytics_trainer(trainer, batcher: Optional[CorruptionBatcher] = None):
     """Optional glue for Ultralytics' trainer objects: replaces `trainer.preprocess_batch` so that a batch whose
     "raw" entry holds the collated HWC BGR uint8 frames is corrupted + letterboxed + normalised on the GPU.

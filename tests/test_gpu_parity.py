@@ -749,6 +749,44 @@ def test_restoration_pairs_fused(torch_):
         assert np.array_equal(corrupted[i].cpu().numpy(), want_cor), (i, op)
 
 
+def test_restoration_pair_batcher_host_level(torch_):
+    """training.RestorationPairBatcher: host frames in, (corrupted, clean) float32 batches on the device out, equal to the
+    reference dataset's per-item arithmetic (train_restoration.py:104-129 restated with the oracle) under the same
+    random / np.random seeds -- train mode (random crop, flip) and validation mode (centre crop)."""
+    from robust_object_detection_b200.training import RestorationPairBatcher
+    P = 64
+    shapes = [(120, 200), (97, 133), (64, 64), (300, 180), (81, 90), (200, 201), (765, 1360), (70, 64)]
+    frames = [synth(5600 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    for is_train in (True, False):
+        random.seed(8)
+        np.random.seed(9)
+        batcher = RestorationPairBatcher(patch_size=P, is_train=is_train)
+        got = [batcher(frames[:5]), batcher(frames[5:])]
+        cor = np.concatenate([g[0].cpu().numpy() for g in got])
+        clean = np.concatenate([g[1].cpu().numpy() for g in got])
+        random.seed(8)
+        np.random.seed(9)
+        ops_seen = set()
+        for i, img in enumerate(frames):
+            h, w = img.shape[:2]
+            if is_train:
+                y, x = random.randint(0, h - P), random.randint(0, w - P)
+                patch = img[y:y + P, x:x + P]
+                if random.random() > 0.5:
+                    patch = patch[:, ::-1]
+            else:
+                patch = img[(h - P) // 2:(h - P) // 2 + P, (w - P) // 2:(w - P) // 2 + P]
+            patch = np.ascontiguousarray(patch)
+            op = 1 + ("noise", "blur", "lowres").index(random.choice(["noise", "blur", "lowres"]))
+            ops_seen.add(op)
+            c = orc.apply_op(patch, op)   # noise: np.random.normal on the global stream, like the reference
+            assert np.array_equal(clean[i], (patch[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1)), (is_train, i)
+            assert np.array_equal(cor[i], (c[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1)), (is_train, i, op)
+        assert ops_seen == {1, 2, 3}
+    with pytest.raises(NotImplementedError):
+        RestorationPairBatcher(patch_size=P)([synth(1, 40, 80)])   # smaller than the patch: resized first in the reference
+
+
 def test_training_batcher_pinned_pipeline(torch_):
     """main-process hook -- pinned staging + copy stream + corrupt_letterbox, decisions in the
     reference's RNG order, Philox keyed by the running global image index (independent of batching)."""
