@@ -42,7 +42,7 @@ class CorruptionBatcher:
         from concurrent.futures import ThreadPoolExecutor
         import os
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        self._pack_pool = ThreadPoolExecutor(max(1, min(8, cores)))
+        self._pack_pool = ThreadPoolExecutor(max(1, min(int(os.environ.get("ROD_PACK_THREADS", "8")), cores)))
         self._slots: List[dict] = [{}, {}]
         self.images_seen = 0
 
