@@ -178,6 +178,15 @@ def test_numpy_legacy_normal_stream_bit_exact():
         assert np.array_equal(aug.legacy_normal_f32(sigma, 5001), w), sigma
     with pytest.raises(ValueError):
         aug.legacy_normal_f32(-1.0, 4)
+    # caller-provided (page-locked when a GPU is there) output buffer, as apply_noise uses it
+    np.random.seed(3)
+    w = np.random.normal(0, 15, (37, 53, 3)).astype(np.float32)
+    np.random.seed(3)
+    buf = aug._pinned_field(37 * 53 * 3)
+    got = aug.legacy_normal_f32(15, (37, 53, 3), out=buf)
+    assert np.array_equal(got, w) and np.shares_memory(got, buf) and aug._pinned_field(37 * 53 * 3) is buf
+    with pytest.raises(ValueError):
+        aug.legacy_normal_f32(15, (4,), out=np.zeros(5, np.float32))
     # any thread count (1 = the calling thread alone produces and consumes) gives the same field and final state
     import ctypes
     from robust_object_detection_b200 import _native as N
