@@ -43,6 +43,7 @@ DOWNSCALE_FACTOR = 0.5
 NOISE_MODE = "compat"      # "compat": host np.random stream (byte-identical) | "philox": in-kernel RNG
 PHILOX_SEED = SEED
 BATCH_BYTES = 512 << 20    # decoded source bytes per GPU batch
+NOISE_BATCH_BYTES = 128 << 20   # ... of a compat-noise batch (its float32 field is 4x that, page-locked)
 IO_THREADS = 16
 DECODE_CACHE_BYTES = 8 << 30  # decoded frames of one tree kept for its later variants (548 VisDrone val frames ~ 2.3 GB)
 
@@ -87,10 +88,13 @@ def _corrupt_batch(variant: str, images, philox_index: int, run: "_TreeRun" = No
     noise = None
     if variant == "Test_Noise" and NOISE_MODE == "compat":
         # the draws of augmentations.py:31, one per image, in order
-        noise = np.empty(sum(im.size for im in images), dtype=np.float32)
+        total = sum(im.size for im in images)
+        # drawn straight into a page-locked buffer kept for the run (a fresh pageable 4-bytes-per-pixel array costs
+        # more in page faults and in the upload than the GPU work)
+        noise = run.pinned("noise", 4 * total).view(np.float32) if run is not None else np.empty(total, dtype=np.float32)
         o = 0
         for im in images:  # np.random.normal(0, NOISE_SIGMA, im.shape).astype(np.float32), bit for bit, multi-threaded
-            noise[o:o + im.size] = legacy_normal_f32(NOISE_SIGMA, im.shape).reshape(-1)
+            legacy_normal_f32(NOISE_SIGMA, im.shape, out=noise[o:o + im.size])
             o += im.size
     if variant == "Test_Blur" and float(BLUR_ANGLE_DEG) != 0.0:
         plan.set_blur_kernel(motion_blur_kernel(BLUR_KERNEL, BLUR_ANGLE_DEG))
@@ -160,10 +164,13 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
     paths = list(src_img_dir.glob("*.*"))  # filesystem order, like the reference (it fixes the noise stream order)
     philox_index = 0
 
+    # compat noise carries a float32 field of 4 bytes per pixel byte through page-locked memory: smaller batches there
+    cap = min(BATCH_BYTES, NOISE_BATCH_BYTES) if (variant == "Test_Noise" and NOISE_MODE == "compat") else BATCH_BYTES
+
     def submit_decodes(i):
         """decode ahead until the batch is full (cv2 releases the GIL)"""
         batch_paths, futs, nbytes = [], [], 0
-        while i < len(paths) and (nbytes < BATCH_BYTES or not futs):
+        while i < len(paths) and (nbytes < cap or not futs):
             futs.append(run.pool.submit(run.decode, paths[i]))
             batch_paths.append(paths[i])
             i += 1
