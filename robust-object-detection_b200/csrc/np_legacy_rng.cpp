@@ -55,18 +55,6 @@ inline uint32_t temper(uint32_t y) {
     y ^= y >> 18;
     return y;
 }
-__attribute__((target_clones("avx2", "default"))) void temper_block(const uint32_t* mt, uint32_t* out) {
-    for (int i = 0; i < kN; ++i) out[i] = temper(mt[i]);
-}
-inline uint32_t untemper(uint32_t y) {  // inverse of temper(): recovers the raw state word
-    y ^= y >> 18;
-    y ^= (y << 15) & 0xefc60000u;
-    uint32_t t = y;
-    for (int i = 0; i < 4; ++i) t = y ^ ((t << 7) & 0x9d2c5680u);
-    y = t;
-    for (int i = 0; i < 2; ++i) t = y ^ (t >> 11);
-    return t;
-}
 // mt19937_next_double: 53-bit double in [0, 1) from two words
 inline double word_pair_to_double(uint32_t w0, uint32_t w1) {
     const int32_t a = (int32_t)(w0 >> 5), b = (int32_t)(w1 >> 6);
@@ -76,10 +64,10 @@ struct Candidate {
     double x1, x2, r2;
     bool ok;
 };
-inline Candidate candidate(const uint32_t* w) {
+inline Candidate candidate(const uint32_t* w) {  // w: four RAW state words (tempered here, on the worker threads)
     Candidate c;
-    c.x1 = 2.0 * word_pair_to_double(w[0], w[1]) - 1.0;
-    c.x2 = 2.0 * word_pair_to_double(w[2], w[3]) - 1.0;
+    c.x1 = 2.0 * word_pair_to_double(temper(w[0]), temper(w[1])) - 1.0;
+    c.x2 = 2.0 * word_pair_to_double(temper(w[2]), temper(w[3])) - 1.0;
     c.r2 = c.x1 * c.x1 + c.x2 * c.x2;
     c.ok = !(c.r2 >= 1.0 || c.r2 == 0.0);
     return c;
@@ -110,7 +98,7 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
         *has_gauss = 0;
         *cached = 0.0;
     }
-    // tempered stream: leftover of the current block, then whole blocks; and the accepted pairs of every chunk before
+    // raw MT19937 word stream: leftover of the current block, then whole blocks; and the accepted pairs of every chunk before
     // they are compacted into `out`.  Kept per calling thread between calls: fresh 32 MB buffers per frame cost more in
     // page faults than generating the words
     static thread_local std::vector<uint32_t> tl_words;
@@ -173,13 +161,16 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
             }
         }
         {
+            // raw state words: the rest of the present block, then each fresh block regenerated in place from a copy of
+            // its predecessor (the tempering is left to the consumers: this thread is the serial part)
             uint64_t w = 0;
-            for (int i = start_pos; i < kN; ++i) words[w++] = temper(key[i]);
-            std::vector<uint32_t> block(key, key + kN);
+            for (int i = start_pos; i < kN; ++i) words[w++] = key[i];
+            const uint32_t* prev = key;
             uint64_t published = 0;
             for (uint64_t b = 0; b < fresh_blocks; ++b) {
-                mt_regenerate(block.data());
-                temper_block(block.data(), &words[w]);
+                memcpy(&words[w], prev, sizeof(uint32_t) * kN);
+                mt_regenerate(&words[w]);
+                prev = &words[w];
                 w += kN;
                 if (w - published >= 4 * kChunk / 2) { words_ready.store(w, std::memory_order_release); published = w; }
             }
@@ -230,8 +221,7 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
         } else {
             const uint64_t beyond = consumed_words - in_first;         // words taken from fresh blocks
             const uint64_t blk = (beyond - 1) / kN;                    // 0-based fresh block holding the last word
-            const uint32_t* bw = &words[in_first + blk * kN];          // its tempered words -> raw state
-            for (int i = 0; i < kN; ++i) key[i] = untemper(bw[i]);
+            memcpy(key, &words[in_first + blk * kN], sizeof(uint32_t) * kN);  // its raw words are the state
             *pos = (int)(beyond - blk * kN);
         }
     }
