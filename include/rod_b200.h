@@ -79,19 +79,19 @@ ROD_API int  rod_plan_launches(const rod_plan* plan, int op);
  * compat mode (noise != NULL): `noise` is a device float32 array holding, image after
  *   image in plan order, the H*W*3 field the reference would have drawn; result is
  *   uint8(trunc(clamp(float(src) + noise, 0, 255))) -- bit-exact with the reference.
- * philox mode (noise == NULL): the field is generated in registers: one Philox4x32-10 block
- *   (key = seed, counter = (element/8, first_image_index + i, offset)) serves 8 consecutive elements,
- *   16 bits each.  Two Gaussian generators (csrc/rod_core.h defines both; the oracle restates both):
- *     table      (1 <= sigma <= 21; default there): integer arithmetic only -- each Philox word gives two 15-bit draws
- *                from a 64 KB shared-memory quantile table of N(0, sigma^2/2) (1/256 units) and the pair is rotated
- *                by 45 degrees, k0 = floor((x + y)/256), k1 = floor((x - y)/256): independent, ~2^30 values each,
- *                tails to 5.9 sigma;
- *     Box-Muller (sigma <= 2048; default outside [1, 21], rod_plan_set_gaussian_generator(ROD_GAUSS_BOXMULLER), and always
- *                on the training path rod_corrupt_letterbox_f16): 16-bit stratified radius with a 32-bit
- *                tail refinement, 16-bit angle.
+ * philox mode (noise == NULL): the field is generated in registers from Philox4x32-10 blocks
+ *   (key = seed, counter = (group, first_image_index + i, offset)).  Two Gaussian generators (csrc/rod_core.h defines
+ *   both; the oracle restates both):
+ *     table      (3 <= sigma <= 20; default there): integer arithmetic only -- one block serves a group of 16 consecutive
+ *                elements; each Philox word gives four 8-bit draws from a 256-entry table of N(0, sigma^2/4) (1/256
+ *                units; 2nd/4th/6th moments exact) and the four are mixed by a 4 x 4 Hadamard transform,
+ *                k = floor((xa +- xb +- xc +- xd) / 256): uncorrelated, 2^32 equally likely values each, tails to 6.2 sigma;
+ *     Box-Muller (sigma <= 2048; default outside [3, 20], rod_plan_set_gaussian_generator(ROD_GAUSS_BOXMULLER), and always
+ *                on the training path rod_corrupt_letterbox_f16): groups of 8 elements, 16-bit stratified radius with a
+ *                32-bit tail refinement, 16-bit angle.
  *   result is clamp(src + floor(noise), 0, 255).  Reproducible for any batch split / GPU count;
  *   validated statistically (not bit-identical to NumPy's stream).  The first launch with a new sigma uploads
- *   the table synchronously (do not issue it inside a stream capture).
+ *   the table synchronously: call rod_noise_prewarm(sigma) first when the launch is to be captured in a CUDA graph.
  * opcodes (device uint8[n_images], may be NULL): when given, only images whose
  *   op-code equals ROD_OP_NOISE are processed; the others are left untouched. */
 ROD_API int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const float* noise,
@@ -100,11 +100,19 @@ ROD_API int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* dst,
 /* The float32 field philox mode adds (same layout as `noise` above); for tests/resume. */
 ROD_API int rod_noise_field_f32(const rod_plan* plan, float* out_field, float sigma, uint64_t seed,
                         uint64_t first_image_index, uint32_t offset, void* stream);
-/* Philox-mode Gaussian generator of this plan: ROD_GAUSS_AUTO (0, default: table when 1 <= sigma <= 21, else
- * Box-Muller) or ROD_GAUSS_BOXMULLER (1). */
+/* Philox-mode Gaussian generator of this plan: ROD_GAUSS_AUTO (0, default: table when 3 <= sigma <= 20, else
+ * Box-Muller), ROD_GAUSS_BOXMULLER (1) or ROD_GAUSS_TABLE_PHILOX7 (2: like AUTO with the table generator on
+ * Philox4x32-7, the smallest round count that passes BigCrush in Salmon et al. 2011 -- a different, equally valid stream). */
 #define ROD_GAUSS_AUTO 0
 #define ROD_GAUSS_BOXMULLER 1
+#define ROD_GAUSS_TABLE_PHILOX7 2
 ROD_API int rod_plan_set_gaussian_generator(rod_plan* plan, int generator);
+/* Builds and uploads the table-generator table of `sigma` on `device` now (synchronous), so that later Philox-mode
+ * launches with this sigma issue no allocation or blocking copy and can be captured in a CUDA graph.  No-op for sigma
+ * outside the table generator's range.  (augmentations.py:30-33 has no such state: NumPy draws on the host.) */
+ROD_API int rod_noise_prewarm(int device, float sigma);
+/* The 256 entries of that table (int32, host pointer): for tests and for restating the stream. */
+ROD_API int rod_gauss_table_i32(float sigma, int32_t* out256);
 
 /* The HOST side of compat mode: the field `np.random.normal(0, sigma, shape).astype(np.float32)` of augmentations.py:31,
  * regenerated bit for bit from NumPy's legacy generator state (MT19937 + polar Gaussian) with the per-pair work spread

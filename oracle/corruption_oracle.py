@@ -76,13 +76,13 @@ _PHILOX_W0 = 0x9E3779B9
 _PHILOX_W1 = 0xBB67AE85
 
 
-def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
-    """ctr: uint32[N,4], key: uint32[N,2] (or [2]) -> uint32[N,4].  Salmon et al. 2011."""
+def philox4x32_10(ctr: np.ndarray, key: np.ndarray, rounds: int = 10) -> np.ndarray:
+    """ctr: uint32[N,4], key: uint32[N,2] (or [2]) -> uint32[N,4].  Salmon et al. 2011 (Philox4x32-`rounds`)."""
     c = ctr.astype(np.uint64).copy()
     k0 = np.broadcast_to(key[..., 0], (c.shape[0],)).astype(np.uint64).copy()
     k1 = np.broadcast_to(key[..., 1], (c.shape[0],)).astype(np.uint64).copy()
     mask = np.uint64(0xFFFFFFFF)
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = _PHILOX_M0 * c[:, 0]
         p1 = _PHILOX_M1 * c[:, 2]
         hi0, lo0 = p0 >> np.uint64(32), p0 & mask
@@ -103,30 +103,43 @@ _ANGLE_SCALE = float(np.float32(9.58737992428525768e-05))  # float32(2 pi / 6553
 _ANGLE_BIAS = float(np.float32(-804.2476806640625))        # float32((0.5 - 2^23) * 2 pi / 65536)
 
 
-GAUSS_TABLE_MAX_SIGMA = 21.0   # rod_core.h ROD_GAUSS_TABLE_MAX_SIGMA
-GAUSS_TABLE_MIN_SIGMA = 1.0    # rod_core.h ROD_GAUSS_TABLE_MIN_SIGMA
-GAUSS_TABLE_BIAS = 16384
+GAUSS_TABLE_MAX_SIGMA = 20.0   # rod_core.h ROD_GAUSS_TABLE_MAX_SIGMA
+GAUSS_TABLE_MIN_SIGMA = 3.0    # rod_core.h ROD_GAUSS_TABLE_MIN_SIGMA
+GAUSS_H4_STRETCH_A = -1.4657745851475e-3   # rod_core.h ROD_GAUSS_H4_STRETCH_A / _B
+GAUSS_H4_STRETCH_B = 2.4950155916569e-5
 
 
 def gauss_table(sigma: float) -> np.ndarray:
-    """int64[32768]: A[i] = round(256 * (float32(sigma) / sqrt 2) * Phi^-1((i + 0.5) / 32768)) + 16384, the biased
-    15-bit stratified quantile table of N(0, sigma^2 / 2) in 1/256 units (rod_tables.h build_gauss_table).
-    scipy's ndtri is the independent inverse normal CDF here."""
+    """int64[256]: X[i] = round(128 * float32(sigma) * y_i), the 256-point discretisation of N(0, (sigma/2)^2) in 1/256
+    pixel units of the table generator (rod_tables.h build_gauss_table): z_i = mean of N(0,1) over the i-th of 256
+    equiprobable cells, y_i = z_i (1 + A z_i^4 + B z_i^8) normalised to unit variance (A, B make the 4th and 6th
+    moments 3 and 15).  scipy's ndtri is the independent inverse normal CDF here."""
     from scipy.special import ndtri
-    scale = 256.0 * (float(np.float32(sigma)) / np.sqrt(2.0))
-    i = np.arange(32768, dtype=np.float64)
-    return np.floor(scale * ndtri((i + 0.5) / 32768.0) + 0.5).astype(np.int64) + GAUSS_TABLE_BIAS
+    q = ndtri(np.arange(128, 257, dtype=np.float64) / 256.0)      # cell edges of the upper half; q[0] = 0, q[128] = inf
+    q[0] = 0.0
+    ph = np.exp(-0.5 * q[:-1] ** 2) * 0.39894228040143267794
+    ph = np.concatenate([ph, [0.0]])
+    z = 256.0 * (ph[:-1] - ph[1:])
+    z4 = (z * z) * (z * z)
+    y = z * (1.0 + GAUSS_H4_STRETCH_A * z4 + GAUSS_H4_STRETCH_B * (z4 * z4))
+    norm = 128.0 * float(np.float32(sigma)) / np.sqrt(np.sum(y * y) / 128.0)
+    up = np.floor(norm * y + 0.5).astype(np.int64)
+    return np.concatenate([-up[::-1], up])
 
 
 def philox_noise_field_table(n_elems: int, sigma: float, seed: int, image_index: int,
-                             offset: int = 0) -> np.ndarray:
+                             offset: int = 0, rounds: int = 10) -> np.ndarray:
     """Restatement of the TABLE generator of Philox mode (rod_core.h / noise.cu noise_table_kernel), the default
-    for sigma <= 21.  Same Philox blocks as the Box-Muller generator below, integer arithmetic only: word r_p of group
-    g gives two 15-bit draws a = A[(r_p & 0xffff) >> 1], b = A[r_p >> 17] and the 45-degree rotation of the pair
-      element 8g + 2p     : k = ((a + b) >> 8) - 128                = floor((x + y) / 256)
-      element 8g + 2p + 1 : k = ((a - b + 32768) >> 8) - 128        = floor((x - y) / 256)
-    (x, y the unbiased draws).  Returns k as float64 (an integer: add_philox_noise's floor is then the identity)."""
-    n_groups = (n_elems + 7) // 8
+    for 3 <= sigma <= 20.  Integer arithmetic only; one Philox block per group of 16 elements (g = e >> 4, counter
+    (g, image lo, image hi, offset), key = seed); word r_q of the block gives four 8-bit draws
+    xa = X[r_q & 255], xb = X[(r_q >> 8) & 255], xc = X[(r_q >> 16) & 255], xd = X[r_q >> 24] and their Hadamard mix
+      element 16g + 4q + 0 : k = floor((xa + xb + xc + xd) / 256)
+      element 16g + 4q + 1 : k = floor((xa - xb + xc - xd) / 256)
+      element 16g + 4q + 2 : k = floor((xa + xb - xc - xd) / 256)
+      element 16g + 4q + 3 : k = floor((xa - xb - xc + xd) / 256)
+    Returns k as float64 (an integer: add_philox_noise's floor is then the identity).  rounds = 7 restates
+    ROD_GAUSS_TABLE_PHILOX7."""
+    n_groups = (n_elems + 15) // 16
     g = np.arange(n_groups, dtype=np.uint64)
     ctr = np.empty((n_groups, 4), dtype=np.uint32)
     ctr[:, 0] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)
@@ -134,24 +147,25 @@ def philox_noise_field_table(n_elems: int, sigma: float, seed: int, image_index:
     ctr[:, 2] = np.uint32((image_index >> 32) & 0xFFFFFFFF)
     ctr[:, 3] = np.uint32(offset & 0xFFFFFFFF)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
-    r = philox4x32_10(ctr, key).astype(np.int64)
-    tab = gauss_table(sigma)
-    a = tab[(r & 0xFFFF) >> 1]
-    b = tab[r >> 17]
-    k = np.empty((n_groups, 8), dtype=np.float64)
-    k[:, 0::2] = ((a + b) >> 8) - 128
-    k[:, 1::2] = ((a - b + 32768) >> 8) - 128
+    r = philox4x32_10(ctr, key, rounds).astype(np.int64)          # [n_groups, 4]
+    X = gauss_table(sigma)
+    xa, xb, xc, xd = X[r & 0xFF], X[(r >> 8) & 0xFF], X[(r >> 16) & 0xFF], X[r >> 24]
+    k = np.empty((n_groups, 4, 4), dtype=np.float64)
+    k[:, :, 0] = (xa + xb + xc + xd) >> 8
+    k[:, :, 1] = (xa - xb + xc - xd) >> 8
+    k[:, :, 2] = (xa + xb - xc - xd) >> 8
+    k[:, :, 3] = (xa - xb - xc + xd) >> 8
     return k.reshape(-1)[:n_elems]
 
 
 def philox_noise_field(n_elems: int, sigma: float, seed: int, image_index: int,
                        offset: int = 0, generator: str = "auto") -> np.ndarray:
     """The field Philox mode adds: generator "auto" (what rod_noise_u8 / rod_corrupt_batch_u8 use: the table
-    generator for 1 <= sigma <= 21, else Box-Muller), "table", or "boxmuller" (always used by the training path,
-    rod_corrupt_letterbox_f16)."""
-    if generator == "table" or (generator == "auto" and
-                                GAUSS_TABLE_MIN_SIGMA <= float(np.float32(sigma)) <= GAUSS_TABLE_MAX_SIGMA):
-        return philox_noise_field_table(n_elems, sigma, seed, image_index, offset)
+    generator for 3 <= sigma <= 20, else Box-Muller), "table", "table7" (ROD_GAUSS_TABLE_PHILOX7: like auto with the
+    table generator on Philox4x32-7) or "boxmuller" (always used by the training path, rod_corrupt_letterbox_f16)."""
+    in_range = GAUSS_TABLE_MIN_SIGMA <= float(np.float32(sigma)) <= GAUSS_TABLE_MAX_SIGMA
+    if generator == "table" or (generator in ("auto", "table7") and in_range):
+        return philox_noise_field_table(n_elems, sigma, seed, image_index, offset, 7 if generator == "table7" else 10)
     return philox_noise_field_boxmuller(n_elems, sigma, seed, image_index, offset)
 
 

@@ -40,6 +40,8 @@ SYMBOLS = {
     "rod_blur_h_u8": (_i, [_vp, _vp, _vp, _i, _d, _vp, _vp]),
     "rod_set_blur_kernel": (_i, [_vp, _vp, _i]),
     "rod_plan_set_gaussian_generator": (_i, [_vp, _i]),
+    "rod_noise_prewarm": (_i, [_i, ctypes.c_float]),
+    "rod_gauss_table_i32": (_i, [ctypes.c_float, ctypes.POINTER(ctypes.c_int32)]),
     "rod_numpy_legacy_normal_f32": (_i, [_vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                          ctypes.POINTER(ctypes.c_double), _d, _u64, _vp, _i]),
     "rod_lowres_u8": (_i, [_vp, _vp, _vp, _d, _vp, _vp]),

@@ -157,9 +157,19 @@ class CorruptionPlan:
         N.check(N.lib().rod_noise_field_f32(self._h, _ptr(out), float(sigma), int(seed), int(first_image_index),
                                             int(offset), _stream_handle(stream)), "rod_noise_field_f32")
 
+    @staticmethod
+    def prewarm_noise(sigma: float = NOISE_SIGMA, device: Optional[int] = None) -> None:
+        """Upload the table-generator table of `sigma` now, so that the first Philox-mode launch with this sigma does
+        no allocation / blocking copy (required before capturing it in a CUDA graph).  rod_noise_prewarm."""
+        if device is None:
+            import torch
+            device = torch.cuda.current_device()
+        N.check(N.lib().rod_noise_prewarm(int(device), float(sigma)), "rod_noise_prewarm")
+
     def set_gaussian_generator(self, generator: int) -> None:
-        """Philox-mode Gaussian generator of this plan: 0 = auto (quantile table when 1 <= sigma <= 21, else
-        Box-Muller), 1 = Box-Muller.  include/rod_b200.h rod_plan_set_gaussian_generator."""
+        """Philox-mode Gaussian generator of this plan: 0 = auto (256-entry table + Hadamard mix when 3 <= sigma <= 20,
+        else Box-Muller), 1 = Box-Muller, 2 = auto with the table generator on Philox4x32-7.  include/rod_b200.h
+        rod_plan_set_gaussian_generator."""
         N.check(N.lib().rod_plan_set_gaussian_generator(self._h, int(generator)), "rod_plan_set_gaussian_generator")
 
     def blur(self, src, dst, k: int = BLUR_KERNEL, angle_deg: float = BLUR_ANGLE_DEG, opcodes=None, stream=None) -> None:

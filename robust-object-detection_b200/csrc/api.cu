@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "rod_internal.h"
+#include "rod_tables.h"
 
 using namespace rod;
 
@@ -131,8 +132,25 @@ extern "C" int rod_noise_u8(const rod_plan* plan, const uint8_t* src, uint8_t* d
                         first_image_index, offset, opcodes, ROD_OP_NOISE, (cudaStream_t)stream, 0, plan->n_images);
 }
 
+extern "C" int rod_noise_prewarm(int device, float sigma) {
+    if (!(sigma >= ROD_GAUSS_TABLE_MIN_SIGMA && sigma <= ROD_GAUSS_TABLE_MAX_SIGMA)) return ROD_OK;
+    int prev = 0;
+    ROD_CUDA(cudaGetDevice(&prev));
+    ROD_CUDA(cudaSetDevice(device));
+    const int32_t* t = nullptr;
+    const int rc = rod::gauss_table_for(device, sigma, &t);
+    cudaSetDevice(prev);
+    return rc;
+}
+
+extern "C" int rod_gauss_table_i32(float sigma, int32_t* out256) {
+    if (out256 == nullptr || !(sigma >= ROD_GAUSS_TABLE_MIN_SIGMA && sigma <= ROD_GAUSS_TABLE_MAX_SIGMA)) return ROD_ERR_INVALID_ARG;
+    rod::build_gauss_table(sigma, out256);
+    return ROD_OK;
+}
+
 extern "C" int rod_plan_set_gaussian_generator(rod_plan* plan, int generator) {
-    if (plan == nullptr || (generator != ROD_GAUSS_AUTO && generator != ROD_GAUSS_BOXMULLER)) return ROD_ERR_INVALID_ARG;
+    if (plan == nullptr || (generator != ROD_GAUSS_AUTO && generator != ROD_GAUSS_BOXMULLER && generator != ROD_GAUSS_TABLE_PHILOX7)) return ROD_ERR_INVALID_ARG;
     plan->gauss_generator = generator;
     if (plan->inner != nullptr) plan->inner->gauss_generator = generator;
     return ROD_OK;

@@ -4,8 +4,9 @@
 //   NOISE_COMPAT  a supplied float32 tensor (what np.random.normal(...).astype(f32) drew) -> bit-exact
 //   NOISE_PHILOX  Philox4x32-10 keyed by (seed, global image index, element/8, offset), no HBM traffic for
 //                 the field; two Gaussian generators on the same Philox blocks (rod_core.h):
-//                   table      (1 <= sigma <= 21, noise_table_kernel): two 15-bit draws from a 64 KB shared-memory quantile
-//                              table per Philox word, rotated by 45 degrees in integer arithmetic -- no MUFU
+//                   table      (3 <= sigma <= 20, noise_table_kernel): four 8-bit draws per Philox word from a 256-entry
+//                              table in shared memory, mixed by a 4 x 4 Hadamard transform in integer arithmetic:
+//                              one Philox block per 16 elements, no MUFU, no bank conflicts
 //                   Box-Muller (any sigma <= 2048, noise_kernel<NOISE_PHILOX>): 4 MUFU per pair, XU-pipe bound
 // plus NOISE_COPY (ROD_OP_NONE images of a mixed batch) and NOISE_FIELD (dump the Philox field).
 //
@@ -38,8 +39,7 @@ struct NoiseParams {
     const uint8_t* opcodes;
     int my_op;
     unsigned int* counter;  // zeroed before the launch
-    uint32_t two15;         // 32768 (see group_table8)
-    const uint16_t* table;  // table generator: 32768 x uint16 quantiles (device global; staged in shared memory)
+    const int32_t* table;   // table generator: the 256 entries X[i] (device global; expanded into shared memory)
 };
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
@@ -218,14 +218,16 @@ __global__ void __launch_bounds__(256, 4) noise_kernel(NoiseParams p) {
 // ---------------------------------------------------------------------------------------------------
 // Table generator of Philox mode (definition: rod_core.h).
 // ---------------------------------------------------------------------------------------------------
-// Shared-memory layout of the table kernel: the 64 KB table (32768 x uint16) sits at a 64 KB-ALIGNED shared address
-// `tbase`, so the address of the first draw of a word is one instruction, (r & 0xfffe) | tbase (LOP3); the second is
-// (r >> 17) * 2 + tbase as two integer multiply-adds on the FMA pipe (the ALU pipe is the busy one in this kernel).
+// Shared-memory layout of the table kernel: 256 rows of 256 bytes at a 64 KB-ALIGNED shared address `tbase`; row i holds,
+// for each of the 32 lanes, the (x, x) form of entry i at byte 4 * lane and the (x, -x) form at byte 128 + 4 * lane.  The
+// address of a draw is therefore ONE byte permute -- byte 1 = the index byte of the Philox word, bytes 0, 2, 3 = the
+// lane's base -- and every lane reads its own bank: no conflicts, one wavefront per load (the 15-bit shared table this
+// replaces cost 3.6 wavefronts per random 16-bit load and had the LSU pipe at 82 %).
 constexpr uint32_t kTabSmemBytes = 65536u + 65536u;  // table + slack to reach the next 64 KB boundary
 
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -234,42 +236,15 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return d;
 }
 
-// f[q] = int16 pair (k + 128 of element 2q, k + 128 of element 2q + 1) of group g (rod_core.h gauss_pair_packed).
-__device__ __forceinline__ void group_table8(uint32_t tbase, const NoiseParams& p, uint32_t ig_lo, uint32_t ig_hi,
-                                             uint32_t g, uint32_t f[4]) {
-    uint32_t r[4];
-    philox4x32_10_rk(g, ig_lo, ig_hi, p.offset, p.keys, r);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint32_t alo, ihi;
-        asm("lop3.b32 %0, %1, 0xFFFE, %2, 0xEA;" : "=r"(alo) : "r"(r[q]), "r"(tbase));  // (r & 0xfffe) | tbase
-        // 2^15 comes from the parameter block so ptxas keeps the IMAD.HI (a literal power of two becomes a shift, ALU pipe)
-        asm("mad.hi.u32 %0, %1, %2, 0;" : "=r"(ihi) : "r"(r[q]), "r"(p.two15));          // r >> 17
-        const uint32_t a = lds_u16(alo), b = lds_u16(ihi * 2u + tbase);
-        f[q] = prmt(gauss_pair_packed(a, b), 0u, 0x4341u);  // bytes 1 and 3 -> the two halves
-    }
-}
-
-// One group, element by element, restricted to the absolute element range [ea, eb): the remainder of spans whose
-// start is not on a group boundary / not 16-byte aligned (pitched rows).  e0 = element index of s[0] / d[0].
-template <int MODE>
-__device__ __noinline__ void table_group_slow(const NoiseParams& p, uint32_t tbase, uint32_t ig_lo, uint32_t ig_hi,
-                                              uint32_t g, uint32_t e0, uint32_t ea, uint32_t eb, const uint8_t* s,
-                                              uint8_t* d, float* fout) {
-    uint32_t r[4];
-    philox4x32_10_rk(g, ig_lo, ig_hi, p.offset, p.keys, r);
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t e = 8u * g + j;
-        if (e < ea || e >= eb) continue;
-        const uint32_t w = r[j >> 1];
-        const int k = gauss_pair_k(lds_u16(tbase + (w & 0xFFFEu)), lds_u16(tbase + 2u * (w >> 17)), j & 1);
-        const uint32_t rel = e - e0;
-        if (MODE == NOISE_FIELD) fout[rel] = (float)k;
-        else d[rel] = (uint8_t)noise_table_px(s[rel], k);
-    }
-}
-__device__ __forceinline__ int table_k(const uint32_t f[4], int j) {  // element j of the group: k = kb - 128
-    return (int)(int16_t)(f[j >> 1] >> (16 * (j & 1))) - 128;
+// One Philox word -> the four elements it makes: f01 / f23 = int16 pairs (k + 128) of elements (0, 1) / (2, 3).
+// base_s / base_d: tbase + 4 * lane (+ 128): the lane's column of the (x, x) / (x, -x) forms.
+__device__ __forceinline__ void table_word4(uint32_t r, uint32_t base_s, uint32_t base_d, uint32_t& f01, uint32_t& f23) {
+    const uint32_t A = lds_u32(prmt(r, base_s, 0x7604u)), B = lds_u32(prmt(r, base_d, 0x7614u));
+    const uint32_t C = lds_u32(prmt(r, base_s, 0x7624u)), D = lds_u32(prmt(r, base_d, 0x7634u));
+    uint32_t e01, e23;
+    h4_combine(A, B, C, D, &e01, &e23);
+    f01 = prmt(e01, 0u, 0x4341u);  // bytes 1 and 3 -> the two halves
+    f23 = prmt(e23, 0u, 0x4341u);
 }
 
 // four pixels (one word) + two packed pairs -> four output bytes: clamp((v - 128) + kb, 0, 255) = clamp(v + k, 0, 255)
@@ -281,18 +256,45 @@ __device__ __forceinline__ uint32_t table_word(uint32_t word, uint32_t f01, uint
     return __byte_perm(q01, q23, 0x6420);
 }
 
-// Same work hand-out as noise_kernel (warps take quarter spans from a shared counter); the CTA first stages the
-// 64 KB table in shared memory (from L2 after the first CTA of the launch).  MODE: NOISE_PHILOX or NOISE_FIELD.
-template <int MODE, int THREADS, int UNROLL>
+// One group (16 elements), element by element, restricted to the absolute element range [ea, eb): the remainder of
+// spans whose start is not on a group boundary / not 16-byte aligned (pitched rows).  e0 = element index of s[0] / d[0].
+template <int MODE, int ROUNDS>
+__device__ __noinline__ void table_group_slow(const NoiseParams& p, uint32_t base_s, uint32_t base_d, uint32_t ig_lo,
+                                              uint32_t ig_hi, uint32_t g, uint32_t e0, uint32_t ea, uint32_t eb,
+                                              const uint8_t* s, uint8_t* d, float* fout) {
+    uint32_t r[4];
+    philox4x32_rk<ROUNDS>(g, ig_lo, ig_hi, p.offset, p.keys, r);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t f01, f23;
+        table_word4(r[q], base_s, base_d, f01, f23);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t e = 16u * g + 4u * q + j;
+            if (e < ea || e >= eb) continue;
+            const int k = (int)(((j & 2) ? f23 : f01) >> (16 * (j & 1)) & 0xFFFFu) - 128;
+            const uint32_t rel = e - e0;
+            if (MODE == NOISE_FIELD) fout[rel] = (float)k;
+            else d[rel] = (uint8_t)noise_table_px(s[rel], k);
+        }
+    }
+}
+
+// Same work hand-out as noise_kernel (warps take quarter spans from a shared counter); the CTA first expands the
+// 256-entry table (1 KB in global memory) into its lane-replicated two-form shared copy.  MODE: NOISE_PHILOX or NOISE_FIELD.
+template <int MODE, int THREADS, int UNROLL, int ROUNDS>
 __global__ void __launch_bounds__(THREADS, 1) noise_table_kernel(NoiseParams p) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(s_raw) + 0xFFFFu) & ~0xFFFFu;
-    for (int i = threadIdx.x; i < 4096; i += THREADS) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.table) + i);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tbase + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    for (int i = threadIdx.x; i < 256 * 64; i += THREADS) {
+        const int row = i >> 6, col = i & 63;  // col < 32: (x, x) form of lane col; else (x, -x) form of lane col - 32
+        const int32_t x = __ldg(p.table + row);
+        const uint32_t v = col < 32 ? h4_form_same(x) : h4_form_diff(x);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(tbase + 4u * (uint32_t)i), "r"(v) : "memory");
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t base_s = tbase + 4u * lane, base_d = base_s + 128u;
     for (;;) {
         uint32_t id = 0;
         if (lane == 0) id = atomicAdd(p.counter, 1u);
@@ -323,61 +325,63 @@ __global__ void __launch_bounds__(THREADS, 1) noise_table_kernel(NoiseParams p) 
         const uint32_t n = (uint32_t)t.b;
         float* fout = (MODE == NOISE_FIELD) ? p.field_out + im.elem_base + e0 : nullptr;
 
-        // 16 bytes per thread step = two Philox groups: needs the span to start on a group boundary
-        bool vec = (e0 & 7u) == 0;
+        // 16 bytes per thread step = one Philox group: needs the span to start on a group boundary
+        bool vec = (e0 & 15u) == 0;
         if (MODE != NOISE_FIELD) vec = vec && ((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0;
         if (MODE == NOISE_FIELD) vec = vec && (((uintptr_t)fout) & 15) == 0;
         const uint32_t nvec = vec ? (n >> 4) : 0;
+        const uint32_t g0 = e0 >> 4;
 #pragma unroll UNROLL
         for (uint32_t i = lane; i < nvec; i += 32u) {
             const uint32_t e = 16u * i;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (MODE != NOISE_FIELD) v = ldg_stream16(s + e);
-            uint32_t fa[4], fb[4];
-            group_table8(tbase, p, ig_lo, ig_hi, (e0 + e) >> 3, fa);
-            group_table8(tbase, p, ig_lo, ig_hi, ((e0 + e) >> 3) + 1u, fb);
+            uint32_t r[4], f[8];
+            philox4x32_rk<ROUNDS>(g0 + i, ig_lo, ig_hi, p.offset, p.keys, r);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) table_word4(r[q], base_s, base_d, f[2 * q], f[2 * q + 1]);
             if (MODE == NOISE_FIELD) {
                 float4* fo = reinterpret_cast<float4*>(fout + e);
-                fo[0] = make_float4((float)table_k(fa, 0), (float)table_k(fa, 1), (float)table_k(fa, 2), (float)table_k(fa, 3));
-                fo[1] = make_float4((float)table_k(fa, 4), (float)table_k(fa, 5), (float)table_k(fa, 6), (float)table_k(fa, 7));
-                fo[2] = make_float4((float)table_k(fb, 0), (float)table_k(fb, 1), (float)table_k(fb, 2), (float)table_k(fb, 3));
-                fo[3] = make_float4((float)table_k(fb, 4), (float)table_k(fb, 5), (float)table_k(fb, 6), (float)table_k(fb, 7));
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    fo[q] = make_float4((float)((int)(f[2 * q] & 0xFFFFu) - 128), (float)((int)(f[2 * q] >> 16) - 128),
+                                        (float)((int)(f[2 * q + 1] & 0xFFFFu) - 128), (float)((int)(f[2 * q + 1] >> 16) - 128));
             } else {
-                stg16(d + e, make_uint4(table_word(v.x, fa[0], fa[1]), table_word(v.y, fa[2], fa[3]),
-                                        table_word(v.z, fb[0], fb[1]), table_word(v.w, fb[2], fb[3])));
+                stg16(d + e, make_uint4(table_word(v.x, f[0], f[1]), table_word(v.y, f[2], f[3]),
+                                        table_word(v.z, f[4], f[5]), table_word(v.w, f[6], f[7])));
             }
         }
-        // remainder (and the whole span when unaligned): one Philox group (<= 8 elements) per thread step
+        // remainder (and the whole span when unaligned): one Philox group (<= 16 elements) per thread step
         const uint32_t r0 = nvec << 4;
         if (r0 < n) {
             const uint32_t ea = e0 + r0, eb = e0 + n;  // absolute element range [ea, eb)
-            const uint32_t g_first = ea >> 3, g_last = (eb - 1) >> 3;
+            const uint32_t g_first = ea >> 4, g_last = (eb - 1) >> 4;
             for (uint32_t g = g_first + lane; g <= g_last; g += 32u)
-                table_group_slow<MODE>(p, tbase, ig_lo, ig_hi, g, e0, ea, eb, s, d, fout);
+                table_group_slow<MODE, ROUNDS>(p, base_s, base_d, ig_lo, ig_hi, g, e0, ea, eb, s, d, fout);
         }
     }
 }
 
-// Device copies of the quantile table, one per (device, sigma), built on first use (synchronous upload: the first
-// Philox launch with a new sigma must not happen inside a stream capture).
+// Device copies of the 256-entry table, one per (device, sigma), built on first use.  rod_noise_prewarm() builds it ahead
+// of time (the upload is synchronous: the FIRST Philox launch with a new sigma must not happen inside a stream capture).
 struct GaussTable {
     int device;
     uint32_t sigma_bits;
-    uint16_t* d_tab;
+    int32_t* d_tab;
 };
 static std::mutex g_tab_mutex;
 static std::vector<GaussTable> g_tabs;
 
-static int gauss_table_for(int device, float sigma, const uint16_t** out) {
+int gauss_table_for(int device, float sigma, const int32_t** out) {
     std::lock_guard<std::mutex> lock(g_tab_mutex);
     const uint32_t bits = fbits(sigma);
     for (const GaussTable& t : g_tabs)
         if (t.device == device && t.sigma_bits == bits) { *out = t.d_tab; return ROD_OK; }
-    std::vector<uint16_t> h(32768);
-    build_gauss_table(sigma, h.data());
-    uint16_t* d = nullptr;
-    ROD_CUDA(cudaMalloc(&d, 65536));
-    cudaError_t e = cudaMemcpy(d, h.data(), 65536, cudaMemcpyHostToDevice);
+    int32_t h[256];
+    build_gauss_table(sigma, h);
+    int32_t* d = nullptr;
+    ROD_CUDA(cudaMalloc(&d, sizeof(h)));
+    cudaError_t e = cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e); }
     g_tabs.push_back(GaussTable{device, bits, d});
     *out = d;
@@ -403,26 +407,40 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
     p.offset = offset;
     p.opcodes = opcodes; p.my_op = my_op;
     p.table = nullptr;
-    p.two15 = 32768u;
     p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
     ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     int per_sm = 4;  // CTAs per SM the grid is sized for: 4 are resident, a longer queue evens out the tail (knob: ROD_NOISE_CTAS)
     const char* e_ctas = getenv("ROD_NOISE_CTAS");
     if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 64) per_sm = atoi(e_ctas);
-    if ((mode == NOISE_PHILOX || mode == NOISE_FIELD) && generator == ROD_GAUSS_AUTO && sigma >= ROD_GAUSS_TABLE_MIN_SIGMA &&
-        sigma <= ROD_GAUSS_TABLE_MAX_SIGMA) {
+    if ((mode == NOISE_PHILOX || mode == NOISE_FIELD) && (generator == ROD_GAUSS_AUTO || generator == ROD_GAUSS_TABLE_PHILOX7) &&
+        sigma >= ROD_GAUSS_TABLE_MIN_SIGMA && sigma <= ROD_GAUSS_TABLE_MAX_SIGMA) {
         int rc = gauss_table_for(plan->device, sigma, &p.table);
         if (rc != ROD_OK) return rc;
         // one 1024-thread CTA per SM, each with its own copy of the table; warps take quarter spans
-        const int ctas = grid_for(plan, (p.n_tiles * 4 + 31) / 32, 1);
-#define ROD_TAB_LAUNCH(M, TH, UN)                                                                                          \
+        int variant = 0;  // benchmark knob ROD_TAB_VARIANT: 0 = 1024 threads x unroll 2, 1 = unroll 4, 2 = unroll 1, 3 = 512 threads x unroll 2
+        const char* e_var = getenv("ROD_TAB_VARIANT");
+        if (e_var) variant = atoi(e_var);
+        const int threads = variant == 3 ? 512 : 1024;
+        const int ctas = grid_for(plan, (p.n_tiles * 4 + threads / 32 - 1) / (threads / 32), 1);
+#define ROD_TAB_LAUNCH(M, TH, UN, R)                                                                                       \
     do {                                                                                                                   \
-        ROD_CUDA(cudaFuncSetAttribute(noise_table_kernel<M, TH, UN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmemBytes)); \
-        noise_table_kernel<M, TH, UN><<<ctas, TH, kTabSmemBytes, stream>>>(p);                                             \
+        ROD_CUDA(cudaFuncSetAttribute(noise_table_kernel<M, TH, UN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmemBytes)); \
+        noise_table_kernel<M, TH, UN, R><<<ctas, TH, kTabSmemBytes, stream>>>(p);                                          \
     } while (0)
-        // measured on a B200 (256 x 1360x765): 1024 threads x unroll 4: 3.63 TB/s; unroll 1 / 2: 3.61 / 3.57; 768 threads: 3.51-3.61
-        if (mode == NOISE_FIELD) ROD_TAB_LAUNCH(NOISE_FIELD, 1024, 2);
-        else ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 4);
+        const bool r7 = generator == ROD_GAUSS_TABLE_PHILOX7;
+        if (mode == NOISE_FIELD) {
+            if (r7) ROD_TAB_LAUNCH(NOISE_FIELD, 1024, 2, 7); else ROD_TAB_LAUNCH(NOISE_FIELD, 1024, 2, 10);
+        } else if (r7) {
+            ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 2, 7);
+        } else if (variant == 1) {
+            ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 4, 10);
+        } else if (variant == 2) {
+            ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 1, 10);
+        } else if (variant == 3) {
+            ROD_TAB_LAUNCH(NOISE_PHILOX, 512, 2, 10);
+        } else {
+            ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 2, 10);
+        }
 #undef ROD_TAB_LAUNCH
         ROD_CUDA(cudaGetLastError());
         return ROD_OK;

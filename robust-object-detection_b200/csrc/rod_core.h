@@ -145,9 +145,12 @@ inline PhiloxKeys philox_round_keys(uint32_t k0, uint32_t k1) {
     }
     return ks;
 }
-ROD_HD void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& ks, uint32_t r[4]) {
+template <int ROUNDS>
+ROD_HD void philox4x32_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& ks, uint32_t r[4]) {
+#if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+#endif
+    for (int i = 0; i < ROUNDS; ++i) {
         uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         uint32_t n0 = hi1 ^ c1 ^ ks.rk[2 * i];
@@ -155,6 +158,9 @@ ROD_HD void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     }
     r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+ROD_HD void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& ks, uint32_t r[4]) {
+    philox4x32_rk<10>(c0, c1, c2, c3, ks, r);
 }
 
 // Philox-mode noise (rod_noise_u8 with noise == NULL).  One Philox block r[4] serves the GROUP of 8
@@ -234,30 +240,51 @@ ROD_HD uint32_t noise_philox_px(uint32_t v, float s, float K) {
 }
 
 // Philox-mode noise, TABLE generator (noise.cu noise_table_kernel; used when ROD_GAUSS_TABLE_MIN_SIGMA <= sigma <=
-// ROD_GAUSS_TABLE_MAX_SIGMA).
-// The same Philox block r[4] of group g as the Box-Muller generator, but integer arithmetic only:
-//   A[i], i = 0..32767 : the 15-bit stratified quantile table of N(0, sigma^2 / 2) in 1/256 units, stored biased:
-//                        A[i] = round(256 * (sigma / sqrt 2) * Phi^-1((i + 0.5) / 32768)) + 16384      (uint16, < 32768)
-//   word r[p] -> a = A[(r[p] & 0xffff) >> 1],  b = A[r[p] >> 17]          (two independent draws; bits 0 and 16 unused)
-//   element 8g + 2p     : k0 = ((a + b) >> 8) - 128                       floor((x + y) / 256), x, y the unbiased draws
-//   element 8g + 2p + 1 : k1 = ((a - b + 32768) >> 8) - 128               floor((x - y) / 256)
+// ROD_GAUSS_TABLE_MAX_SIGMA).  Integer arithmetic only, ONE Philox block per GROUP OF 16 elements:
+//   X[i], i = 0..255 : a 256-point equal-probability discretisation of N(0, (sigma/2)^2) in 1/256 pixel units
+//                      (rod_tables.h build_gauss_table: cell means of the 256 quantile cells, tails stretched so that
+//                      the 2nd, 4th and 6th moments are the Gaussian ones, rounded to integers)
+//   group g = e >> 4, block r[4] = Philox4x32-10(counter (g, image lo, image hi, offset), key seed)
+//   word r[q] -> four independent draws  xa = X[byte 0], xb = X[byte 1], xc = X[byte 2], xd = X[byte 3]  and their
+//   4 x 4 Hadamard transform (an orthogonal mix: four uncorrelated sums, each the sum of four N(0, sigma^2/4) draws)
+//     element 16g + 4q + 0 : k = floor((xa + xb + xc + xd) / 256)
+//     element 16g + 4q + 1 : k = floor((xa - xb + xc - xd) / 256)
+//     element 16g + 4q + 2 : k = floor((xa + xb - xc - xd) / 256)
+//     element 16g + 4q + 3 : k = floor((xa - xb - xc + xd) / 256)
 //   out = clamp(v + k, 0, 255)   (k is floor(noise), so this is the reference's truncation of the clipped sum).
-// (x + y) and (x - y) are the 45-degree rotation of an independent Gaussian pair: again independent N(0, sigma^2),
-// each with ~2^30 distinct values and tails to 5.9 sigma, so no separate tail draw is needed.  On the device this is
-// two 16-bit shared-memory loads and integer multiply-adds per pair -- no MUFU, no floating point.
-#define ROD_GAUSS_TABLE_MAX_SIGMA 21.0f  // 256 * (sigma / sqrt 2) * 4.17 must stay below 16384
-#define ROD_GAUSS_TABLE_MIN_SIGMA 1.0f   // below, the 1/256 grid of the table is no longer fine against sigma (Box-Muller)
-#define ROD_GAUSS_TABLE_BIAS 16384
+// The sum of four 256-level draws has 2^32 equally likely outcomes on the 1/256 grid and tails to 6.2 sigma; its
+// binned distribution is within 1e-3 relative of the Gaussian cell probabilities down to cells of 3e-6 (exact 4-fold
+// convolution, tests/test_emulation.py).  On the device the table lives in shared memory as two 32-bit forms per entry,
+// (x, x) and (x, -x) as 16-bit halves of one 32-bit integer, replicated per lane (bank = lane: conflict-free); the
+// Hadamard transform of a word is then four 32-bit integer additions that produce two elements each.
+#define ROD_GAUSS_TABLE_MAX_SIGMA 20.0f  // 4 * max |X| = 4 * 128 sigma * 3.0958 must stay below 32768
+#define ROD_GAUSS_TABLE_MIN_SIGMA 3.0f   // below, the 256-level draws are too coarse against 1-pixel cells (Box-Muller)
+#define ROD_GAUSS_H4_STRETCH_A (-1.4657745851475e-3)  // y = z (1 + A z^4 + B z^8): matches the 4th and 6th moments
+#define ROD_GAUSS_H4_STRETCH_B (2.4950155916569e-5)
 #ifndef ROD_GAUSS_AUTO
-#define ROD_GAUSS_AUTO 0                 // table generator when sigma <= ROD_GAUSS_TABLE_MAX_SIGMA, else Box-Muller
+#define ROD_GAUSS_AUTO 0                 // table generator when MIN <= sigma <= MAX, else Box-Muller
 #define ROD_GAUSS_BOXMULLER 1
+#define ROD_GAUSS_TABLE_PHILOX7 2        // like AUTO, but the table generator runs on Philox4x32-7 (Random123's fastest
+                                         // Crush-resistant round count) instead of Philox4x32-10
 #endif
-// Both elements of a pair as biased int16 halves: low = a + b = 256 x0 + 2 * 16384, high = a - b + 32768; byte 1 of
-// each half is k + 128.  Two multiply-adds: a * 0x10001 + b * (1 - 65536) + 0x80000000 (no carry between the halves).
-ROD_HD uint32_t gauss_pair_packed(uint32_t a, uint32_t b) { return a * 0x10001u + (b * 0xFFFF0001u + 0x80000000u); }
-ROD_HD int gauss_pair_k(uint32_t a, uint32_t b, int odd) {
-    const uint32_t p = gauss_pair_packed(a, b);
-    return (int)((odd ? (p >> 24) : (p >> 8)) & 0xFFu) - 128;
+// The two shared-memory forms of table entry x (as 32-bit integers; the 16-bit halves are x and +-x modulo carries
+// that cancel in the final sums because 32-bit addition is linear).
+ROD_HD uint32_t h4_form_same(int32_t x) { return (uint32_t)x * 0x00010001u; }
+ROD_HD uint32_t h4_form_diff(int32_t x) { return (uint32_t)x * 0xFFFF0001u; }
+// A, C: (x, x) forms of draws a, c;  B, D: (x, -x) forms of draws b, d.  e01 / e23: elements (0, 1) / (2, 3) of the word as
+// 16-bit halves 256 k + frac + 32768, i.e. byte 1 (byte 3) of each is k + 128.
+ROD_HD void h4_combine(uint32_t A, uint32_t B, uint32_t C, uint32_t D, uint32_t* e01, uint32_t* e23) {
+    const uint32_t u = A + B + 0x80008000u, v = C + D;
+    *e01 = u + v;
+    *e23 = u - v;
+}
+// element j (0..3) of Philox word w: k = floor(noise)
+ROD_HD int h4_word_k(uint32_t w, const int32_t* X, int j) {
+    uint32_t e01, e23;
+    h4_combine(h4_form_same(X[w & 0xFFu]), h4_form_diff(X[(w >> 8) & 0xFFu]), h4_form_same(X[(w >> 16) & 0xFFu]),
+               h4_form_diff(X[w >> 24]), &e01, &e23);
+    const uint32_t e = (j & 2) ? e23 : e01;
+    return (int)(((j & 1) ? (e >> 24) : (e >> 8)) & 0xFFu) - 128;
 }
 ROD_HD uint32_t noise_table_px(uint32_t v, int k) {
     const int x = (int)v + k;

@@ -151,6 +151,7 @@ int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8
 int launch_letterbox(const rod_plan* plan, const uint8_t* img, const uint8_t* src, const uint8_t* opcodes, void* out_f16,
                      int pad_value, cudaStream_t stream);
 
+int gauss_table_for(int device, float sigma, const int32_t** out);  // noise.cu: device copy of the Philox-mode table
 int ensure_lowres_tables(rod_plan* plan, double factor);
 int ensure_letterbox_tables(rod_plan* plan, int out_h, int out_w);
 

@@ -228,13 +228,29 @@ inline void letterbox_geometry(int h, int w, int out_h, int out_w, int* new_h, i
     *left = (int)nearbyint(dw - 0.1);
 }
 
-// Tile lists ---------------------------------------------------------------------------
-// Quantile table of the Philox TABLE generator (rod_core.h): A[i] = round(256 * (sigma / sqrt 2) * Phi^-1((i + 0.5) /
-// 32768)) + 16384, i = 0..32767.  sigma <= ROD_GAUSS_TABLE_MAX_SIGMA keeps every entry inside [0, 32767].
-inline void build_gauss_table(float sigma, uint16_t* tab) {
-    const double scale = 256.0 * ((double)sigma / sqrt(2.0));
-    for (int i = 0; i < 32768; ++i)
-        tab[i] = (uint16_t)((long)floor(scale * ndtri_double(((double)i + 0.5) / 32768.0) + 0.5) + ROD_GAUSS_TABLE_BIAS);
+// The 256-entry table of the Philox-mode table generator (rod_core.h): X[i] = round(128 sigma y_i) with
+//   z_i = 256 (phi(q_i) - phi(q_i+1)), q_i = Phi^-1(i / 256)      mean of N(0, 1) over the i-th of 256 equiprobable cells
+//   y_i = z_i (1 + A z_i^4 + B z_i^8) / sqrt(mean_j (z_j (1 + A z_j^4 + B z_j^8))^2)
+// (A, B = ROD_GAUSS_H4_STRETCH_*: unit variance, 4th moment 3, 6th moment 15).  Antisymmetric by construction:
+// X[255 - i] = -X[i] (the upper half is computed, the lower half mirrored), so the mean is exactly 0.
+inline void build_gauss_table(float sigma, int32_t* X) {
+    double y[256], q[257], ph[257];
+    for (int i = 128; i <= 256; ++i) {
+        q[i] = (i == 256) ? 0.0 : (i == 128 ? 0.0 : -ndtri_double((256 - i) / 256.0));
+        ph[i] = (i == 256) ? 0.0 : exp(-0.5 * q[i] * q[i]) * 0.39894228040143267794;
+    }
+    double m2 = 0.0;
+    for (int i = 128; i < 256; ++i) {
+        const double z = 256.0 * (ph[i] - ph[i + 1]);
+        const double z4 = (z * z) * (z * z);
+        y[i] = z * (1.0 + ROD_GAUSS_H4_STRETCH_A * z4 + ROD_GAUSS_H4_STRETCH_B * (z4 * z4));
+        m2 += y[i] * y[i];
+    }
+    const double norm = 128.0 * (double)sigma / sqrt(m2 / 128.0);
+    for (int i = 128; i < 256; ++i) {
+        X[i] = (int32_t)floor(norm * y[i] + 0.5);
+        X[255 - i] = -X[i];
+    }
 }
 
 inline void build_noise_tiles(const std::vector<DevImage>& imgs, int span, std::vector<Tile>& tiles) {

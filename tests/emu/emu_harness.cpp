@@ -443,23 +443,24 @@ extern "C" int emu_noise(const uint8_t* src, uint8_t* dst, const float* noise, f
     return 0;
 }
 
-// Replays noise_table_kernel (the TABLE generator of Philox mode): per group the Philox block, per word two 15-bit
-// table draws and their integer 45-degree rotation (rod_core.h gauss_pair_k).  field_out receives k.
+// Replays noise_table_kernel (the TABLE generator of Philox mode): per group of 16 elements the Philox block, per word
+// four 8-bit table draws and their integer Hadamard mix through the same 32-bit two-form arithmetic the kernel uses
+// (rod_core.h h4_word_k).  field_out receives k.  rounds: 10, or 7 (ROD_GAUSS_TABLE_PHILOX7).
 extern "C" int emu_noise_table(const uint8_t* src, uint8_t* dst, float* field_out, long n_elems, float sigma,
-                               uint64_t seed, uint64_t image_index, uint32_t offset) {
-    if (!(sigma <= ROD_GAUSS_TABLE_MAX_SIGMA)) return 1;
-    std::vector<uint16_t> tab(32768);
-    build_gauss_table(sigma, tab.data());
+                               uint64_t seed, uint64_t image_index, uint32_t offset, int rounds) {
+    if (!(sigma >= ROD_GAUSS_TABLE_MIN_SIGMA && sigma <= ROD_GAUSS_TABLE_MAX_SIGMA)) return 1;
+    int32_t X[256];
+    build_gauss_table(sigma, X);
     const PhiloxKeys keys = philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32));
     const uint32_t ig_lo = (uint32_t)image_index, ig_hi = (uint32_t)(image_index >> 32);
-    for (long g = 0; g < (n_elems + 7) / 8; ++g) {
+    for (long g = 0; g < (n_elems + 15) / 16; ++g) {
         uint32_t r[4];
-        philox4x32_10_rk((uint32_t)g, ig_lo, ig_hi, offset, keys, r);
-        for (int j = 0; j < 8; ++j) {
-            const long e = 8 * g + j;
+        if (rounds == 7) philox4x32_rk<7>((uint32_t)g, ig_lo, ig_hi, offset, keys, r);
+        else philox4x32_rk<10>((uint32_t)g, ig_lo, ig_hi, offset, keys, r);
+        for (int j = 0; j < 16; ++j) {
+            const long e = 16 * g + j;
             if (e >= n_elems) break;
-            const uint32_t w = r[j >> 1];
-            const int k = gauss_pair_k(tab[(w & 0xFFFFu) >> 1], tab[w >> 17], j & 1);
+            const int k = h4_word_k(r[j >> 2], X, j & 3);
             if (field_out) field_out[e] = (float)k;
             if (dst) dst[e] = (uint8_t)noise_table_px(src[e], k);
         }
@@ -468,7 +469,7 @@ extern "C" int emu_noise_table(const uint8_t* src, uint8_t* dst, float* field_ou
 }
 
 // The table itself, for a direct comparison with the oracle's scipy-based one.
-extern "C" int emu_gauss_table(float sigma, uint16_t* out) {
+extern "C" int emu_gauss_table(float sigma, int32_t* out) {
     build_gauss_table(sigma, out);
     return 0;
 }

@@ -28,8 +28,8 @@ def emu(tmp_path_factory):
     lib.emu_filter2d.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, f32p, ctypes.c_int]
     lib.emu_lowres_x2w.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_int]
     lib.emu_noise.argtypes = [u8p, u8p, f32p, f32p, ctypes.c_long, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
-    lib.emu_noise_table.argtypes = [u8p, u8p, f32p, ctypes.c_long, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
-    lib.emu_gauss_table.argtypes = [ctypes.c_float, ctypes.POINTER(ctypes.c_uint16)]
+    lib.emu_noise_table.argtypes = [u8p, u8p, f32p, ctypes.c_long, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int]
+    lib.emu_gauss_table.argtypes = [ctypes.c_float, ctypes.POINTER(ctypes.c_int32)]
     lib.emu_letterbox_u8.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_long, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return lib
 
@@ -97,24 +97,54 @@ def test_emu_noise_compat_and_philox(emu):
 
 
 def test_emu_noise_table_generator(emu):
-    """The TABLE generator (default for sigma <= 21): the C++ quantile table equals the oracle's scipy-based one entry
-    by entry, and the host replay of the kernel's integer definition equals the numpy restatement exactly."""
-    for sigma in (15.0, 1.0, 21.0, 7.25):
-        tab = np.zeros(32768, np.uint16)
-        assert emu.emu_gauss_table(ctypes.c_float(sigma), _p(tab, ctypes.c_uint16)) == 0
-        assert np.array_equal(tab.astype(np.int64), orc.gauss_table(sigma)), sigma
-        assert int(tab.max()) < 32768 and np.array_equal(tab.astype(np.int64) + tab[::-1].astype(np.int64),
-                                                          np.full(32768, 32768))   # antisymmetric about the bias
+    """The TABLE generator (default for 3 <= sigma <= 20): the C++ table equals the oracle's scipy-based one entry by
+    entry and has the designed moments; the host replay of the kernel's 32-bit two-form arithmetic equals the numpy
+    restatement exactly, for Philox4x32-10 and Philox4x32-7."""
+    for sigma in (15.0, 3.0, 20.0, 7.25, 4.5):
+        tab = np.zeros(256, np.int32)
+        assert emu.emu_gauss_table(ctypes.c_float(sigma), _p(tab, ctypes.c_int32)) == 0
+        X = orc.gauss_table(sigma)
+        assert np.array_equal(tab.astype(np.int64), X), sigma
+        assert np.array_equal(X, -X[::-1]) and np.all(np.diff(X) > 0) and 4 * int(X.max()) < 32768
+        y = X / (128.0 * sigma)          # unit-variance draws: 2nd / 4th / 6th moments of N(0, 1)
+        assert abs((y ** 2).mean() - 1) < 2e-4 and abs((y ** 4).mean() - 3) < 3e-3 and abs((y ** 6).mean() - 15) < 0.03, sigma
     n = 1 << 20
     img = np.random.default_rng(5).integers(0, 256, n, dtype=np.uint8)
     got = np.zeros_like(img)
     out = np.zeros(n, np.float32)
-    assert emu.emu_noise_table(_p(img), _p(got), _p(out, ctypes.c_float), n, ctypes.c_float(15.0), 0xABCDEF0123456789, 7, 2) == 0
-    want = orc.philox_noise_field(n, 15.0, 0xABCDEF0123456789, 7, 2)          # auto -> table
-    assert np.array_equal(want, orc.philox_noise_field_table(n, 15.0, 0xABCDEF0123456789, 7, 2))
-    assert np.array_equal(out.astype(np.float64), want)
-    assert np.array_equal(got, orc.add_philox_noise(img, want))
-    assert emu.emu_noise_table(_p(img), _p(got), None, 8, ctypes.c_float(22.0), 0, 0, 0) == 1   # out of the table's range
+    for rounds, gen in ((10, "auto"), (7, "table7")):
+        assert emu.emu_noise_table(_p(img), _p(got), _p(out, ctypes.c_float), n, ctypes.c_float(15.0), 0xABCDEF0123456789, 7, 2, rounds) == 0
+        want = orc.philox_noise_field(n, 15.0, 0xABCDEF0123456789, 7, 2, generator=gen)          # auto -> table
+        assert np.array_equal(want, orc.philox_noise_field_table(n, 15.0, 0xABCDEF0123456789, 7, 2, rounds))
+        assert np.array_equal(out.astype(np.float64), want)
+        assert np.array_equal(got, orc.add_philox_noise(img, want))
+    assert emu.emu_noise_table(_p(img), _p(got), None, 8, ctypes.c_float(22.0), 0, 0, 0, 10) == 1   # out of the table's range
+    assert emu.emu_noise_table(_p(img), _p(got), None, 8, ctypes.c_float(1.0), 0, 0, 0, 10) == 1
+
+
+def test_table_generator_exact_distribution():
+    """The exact law of one element of the table generator -- the 4-fold convolution of the 256-atom table law on
+    the 1/256 grid, floored -- against the cell probabilities of floor(N(0, sigma^2)): the chi-square non-centrality a
+    16.7 M-sample test would see stays far below its own standard deviation sqrt(2 * cells)."""
+    from scipy.special import ndtr
+    for sigma, bound in ((15.0, 6.0), (3.0, 12.0), (20.0, 6.0), (8.0, 8.0)):
+        X = orc.gauss_table(sigma)
+        off = 8192
+        p = np.zeros(16384)
+        np.add.at(p, X + off, 1.0 / 256)
+        s = np.fft.irfft(np.fft.rfft(p, 65536) ** 4, 65536)
+        s[s < 0] = 0
+        k = np.floor((np.arange(65536) - 4 * off) / 256.0).astype(int)
+        pk = np.bincount(k - k.min(), weights=s)
+        ks = np.arange(k.min(), k.max() + 1)
+        ideal = ndtr((ks + 1) / sigma) - ndtr(ks / sigma)
+        N = 16.7e6
+        big = ideal * N >= 50
+        ncp = N * ((pk[big] - ideal[big]) ** 2 / ideal[big]).sum()
+        assert ncp < bound, (sigma, ncp)
+        mean, var = (pk * ks).sum(), (pk * ks * ks).sum() - (pk * ks).sum() ** 2
+        assert abs(mean + 127.5 / 256) < 1e-4 and abs(np.sqrt(var) - np.sqrt(sigma ** 2 + 1 / 12)) < 4e-4 * sigma, sigma
+        assert np.abs(ks[pk > 0]).max() > 5.5 * sigma     # tails beyond 5.5 sigma exist
 
 
 def test_philox_known_answer():
@@ -160,14 +190,18 @@ def test_philox_stream_statistics_cpu():
     assert 0.020 < (out == 0).mean() < 0.029 and 0.020 < (out == 255).mean() < 0.029
 
 
-def test_philox_table_stream_statistics_cpu():
-    """Same checks for the TABLE generator (the default at sigma = 15): k = floor(noise) exactly, so the moments are
-    those of floor(N(0, sigma^2)): mean -0.5, variance sigma^2 + 1/12; the histogram of k out to 4.1 sigma against
-    the exact cell probabilities Phi((k+1)/sigma) - Phi(k/sigma) (chi-square, 8 M samples); the two elements of a
-    rotated pair and neighbouring groups uncorrelated (also in their squares); tails beyond 4.5 sigma present."""
+@pytest.mark.parametrize("generator", ["auto", "table7"])
+def test_philox_table_stream_statistics_cpu(generator):
+    """Same checks for the TABLE generator (the default at sigma = 15; Philox4x32-10 and -7): k = floor(noise) exactly,
+    so the moments are those of floor(N(0, sigma^2)): mean -0.5, variance sigma^2 + 1/12; the histogram of k out to
+    4.1 sigma against the exact cell probabilities Phi((k+1)/sigma) - Phi(k/sigma) (chi-square, 8 M samples); tails
+    beyond 4.5 sigma present.  JOINT behaviour of the four elements one Philox word makes (a Hadamard mix of four
+    draws) and of neighbouring words / groups: lag-1..16 autocorrelation, correlation of squares for every pair inside
+    a word, and a coarse 2-D chi-square of (element 4q, element 4q+1) and (element 4q, element 4q+2) against the
+    product of the marginals."""
     from scipy import stats
     n = 1 << 23
-    k = orc.philox_noise_field(n, 15.0, 42, 0)
+    k = orc.philox_noise_field(n, 15.0, 42, 0, generator=generator)
     assert np.array_equal(k, np.floor(k))
     assert abs(k.mean() + 0.5) < 4 * 15 / np.sqrt(n) and abs(k.std() - np.sqrt(225 + 1 / 12)) < 0.02
     z = (k + 0.5) / 15.0
@@ -177,8 +211,23 @@ def test_philox_table_stream_statistics_cpu():
     obs = np.array([(k == c).sum() for c in cells], dtype=np.float64)
     chi2 = ((obs - expect) ** 2 / expect).sum()
     assert chi2 < stats.chi2.ppf(1 - 1e-4, len(cells)), chi2
-    assert abs(np.corrcoef(k[0::2], k[1::2])[0, 1]) < 3e-3 and abs(np.corrcoef(k[:-8], k[8:])[0, 1]) < 3e-3
-    assert abs(np.corrcoef(z[0::2] ** 2, z[1::2] ** 2)[0, 1]) < 3e-3      # the rotated pair is independent, not just uncorrelated
+    tol = 4.0 / np.sqrt(n / 4)                                   # 4 sigma of a sample correlation over n/4 pairs
+    for lag in (1, 2, 3, 4, 8, 16):
+        assert abs(np.corrcoef(z[:-lag], z[lag:])[0, 1]) < tol, lag
+        assert abs(np.corrcoef(z[:-lag] ** 2, z[lag:] ** 2)[0, 1]) < tol, lag
+    w = z.reshape(-1, 4)                                         # the four elements of one Philox word
+    for a in range(4):
+        for b in range(a + 1, 4):
+            assert abs(np.corrcoef(w[:, a], w[:, b])[0, 1]) < tol, (a, b)
+            assert abs(np.corrcoef(w[:, a] ** 2, w[:, b] ** 2)[0, 1]) < tol, (a, b)      # independent, not just uncorrelated
+            assert abs(np.corrcoef(np.abs(w[:, a]), np.abs(w[:, b]))[0, 1]) < tol, (a, b)
+    edges = stats.norm.ppf(np.linspace(0, 1, 13))[1:-1]          # 12 x 12 equiprobable cells
+    for a, b in ((0, 1), (0, 2), (1, 3), (2, 3)):
+        ia, ib = np.searchsorted(edges, w[:, a]), np.searchsorted(edges, w[:, b])
+        tab2 = np.bincount(ia * 12 + ib, minlength=144).reshape(12, 12).astype(np.float64)
+        exp2 = np.outer(tab2.sum(1), tab2.sum(0)) / tab2.sum()
+        chi2d = ((tab2 - exp2) ** 2 / exp2).sum()
+        assert chi2d < stats.chi2.ppf(1 - 1e-4, 121), (a, b, chi2d)
     assert abs((np.abs(z) > 4.0).mean() - 2 * stats.norm.sf(4.0)) < 2e-5 and np.abs(z).max() > 4.5
     img = synth(1000, 256, 1024)
     out = orc.add_philox_noise(img, k[:img.size]).astype(np.int32)

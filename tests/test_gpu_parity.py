@@ -215,17 +215,17 @@ def test_ultralytics_patch_with_stub_module(aug, golden_hashes, monkeypatch):
 # ------------------------------------------------------------------ Philox mode
 def test_philox_field_and_fused_output(torch_):
     """Both Gaussian generators of Philox mode against their restated streams: the table generator (default at
-    1 <= sigma <= 21) is integer arithmetic and matches exactly; Box-Muller (forced per plan, or sigma outside that
-    range) within float tolerance."""
+    3 <= sigma <= 20; on Philox4x32-10 or, selectable, -7) is integer arithmetic and matches exactly; Box-Muller (forced
+    per plan, or sigma outside that range) within float tolerance."""
     from robust_object_detection_b200.batch import CorruptionPlan
     shapes = [(37, 53), (64, 64), (31, 45)]
     plan = CorruptionPlan.ragged(shapes)
     imgs = [synth(50 + i, h, w) for i, (h, w) in enumerate(shapes)]
     src = torch_.from_numpy(plan.pack(imgs)).cuda()
     seed, first, off = 0x1234567890ABCDEF, 5, 3
-    for generator, sigma in (("table", 15.0), ("table", 4.5), ("table", 1.0), ("boxmuller", 15.0), ("auto-boxmuller", 40.0),
-                             ("auto-boxmuller", 0.5)):
-        plan.set_gaussian_generator(1 if generator == "boxmuller" else 0)
+    for generator, sigma in (("table", 15.0), ("table", 4.5), ("table", 3.0), ("table", 20.0), ("table7", 15.0),
+                             ("boxmuller", 15.0), ("auto-boxmuller", 40.0), ("auto-boxmuller", 1.0), ("auto-boxmuller", 0.5)):
+        plan.set_gaussian_generator({"boxmuller": 1, "table7": 2}.get(generator, 0))
         dst = torch_.zeros_like(src)
         field = torch_.zeros(plan.payload_bytes, dtype=torch_.float32, device="cuda")
         plan.noise_field(field, sigma, seed, first, off)
@@ -235,8 +235,9 @@ def test_philox_field_and_fused_output(torch_):
         e = 0
         for i, (img, (h, w)) in enumerate(zip(imgs, shapes)):
             n = 3 * h * w
-            if generator == "table":
-                want = orc.philox_noise_field(n, sigma, seed, first + i, off)     # auto -> table
+            if generator in ("table", "table7"):
+                want = orc.philox_noise_field(n, sigma, seed, first + i, off,     # auto -> table
+                                              generator="table7" if generator == "table7" else "auto")
                 assert np.array_equal(f[e:e + n].astype(np.float64), want), (generator, sigma, i)
                 assert np.array_equal(outs[i], orc.add_philox_noise(img, want)), (generator, sigma, i)
             else:
