@@ -645,6 +645,224 @@ __global__ void __launch_bounds__(128, 4) lowres_x2w_kernel(LowresX2wParams p) {
     }
 }
 
+// =====================================================================================
+// Packed-integer kernel for shapes that are exact 2x in BOTH axes (even w and h at factor 0.5, w % 4 == 0, 4-byte aligned
+// source and destination rows): 7 of the 8 VisDrone frame sizes.  Same work split as lowres_x2w_kernel (a warp owns a
+// band of output rows x a strip of 30 chunks of 8 output pixels, lanes 0 and 31 are halo lanes), but
+//   * the whole pipeline is integer arithmetic on packed 16-bit halves (rod_core.h x2p_*): per low-res row a lane forms
+//     its twelve low-res values (resizeAreaFast_), the horizontal 2x stage and the two vertical-stage terms A / B' of
+//     its 24 output byte columns; an output row is then ONE packed add per two bytes plus one byte permute per four.
+//     No tables (the row pairs and the (1536, 512) y coefficients follow from the row parity), no floating point:
+//     ~4.5 instructions per output byte where the float kernel needs 13.7;
+//   * global memory is only touched by fully coalesced warp-wide copies: the two source rows of a low-res row are
+//     staged in the warp's shared-memory ring by 16-byte cp.async copies (three stages in flight: the copies of low-res
+//     rows j+1 and j+2 overlap the arithmetic of row j), and finished output rows leave through a shared staging
+//     buffer as 16-byte stores.  (The first version had every lane load and store its own 24-byte chunk: 8 bytes of
+//     every 32-byte sector per instruction, 3.6x / 3.0x the ideal sector count at L1 / L2 and 4.0 TB/s at 33 % issue
+//     utilisation.)  Only __syncwarp() is used: warps never share data.
+// =====================================================================================
+constexpr int kX2pStages = 3;
+constexpr int kX2pRowBytes = 32 * 24 + 32;  // staged source bytes of one row: 32 chunks + 16-byte phase + slack
+constexpr int kX2pOutBytes = 30 * 24 + 32;  // one output row of the strip
+struct alignas(16) X2pWarpSmem {
+    uint8_t in[kX2pStages][2][kX2pRowBytes];
+    uint8_t out[2][kX2pOutBytes];
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void stg4s(void* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stg16s(void* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Warp-cooperative copies between a global row segment and the warp's shared buffer.  Every lane moves the units
+// lane, lane + 32, lane + 64, ... of the segment (unit = 16 bytes when the image qualifies: width a multiple of 16
+// pixels and 16-byte aligned rows, so that every strip segment starts on a 16-byte boundary; else 4 bytes), so a lane's
+// addresses are ONE running pointer (global base + unit * lane, advanced by the pitch per row) plus compile-time
+// offsets, and a row costs two address instructions plus one copy per unit.
+template <int U>
+__device__ __forceinline__ void cp_async_u(uint32_t sm, const void* g) {
+    if (U == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sm), "l"(g) : "memory");
+    else if (U == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sm), "l"(g) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sm), "l"(g) : "memory");
+}
+template <int U>
+__device__ __forceinline__ void x2p_copy_in(uint32_t sm_lane, const uint8_t* g_lane, int lane, int nunits) {
+    constexpr int K = (kX2pRowBytes / U + 31) / 32;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if (lane + 32 * k < nunits) cp_async_u<U>(sm_lane + 32 * U * k, g_lane + 32 * U * k);
+}
+template <int U>
+__device__ __forceinline__ void x2p_copy_out(const uint8_t* sm_lane, uint8_t* g_lane, int lane, int nunits) {
+    constexpr int K = (kX2wChunksPerStrip * 24 / U + 31) / 32;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (lane + 32 * k < nunits) {
+            if (U == 16) stg16s(g_lane + 32 * U * k, *reinterpret_cast<const uint4*>(sm_lane + 32 * U * k));
+            else if (U == 8) { const uint2 v = *reinterpret_cast<const uint2*>(sm_lane + 32 * U * k); stg8(g_lane + 32 * U * k, v.x, v.y); }
+            else stg4s(g_lane + 32 * U * k, *reinterpret_cast<const uint32_t*>(sm_lane + 32 * U * k));
+        }
+    }
+}
+
+struct X2pLane {
+    int soff;             // byte offset of this lane's chunk inside a staged source row
+    bool second;          // the chunk has four low-res pixels (else two: last chunk when w % 8 == 4)
+    bool first, last;     // the chunk touches the left / right image border
+};
+
+// the lane's 24 source bytes of both rows of a ring slot (the staged chunk is 8-byte aligned)
+__device__ __forceinline__ void x2p_read_stage(const uint8_t* st, int off, uint32_t rw[2][6]) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const uint2* r = reinterpret_cast<const uint2*>(st + t * kX2pRowBytes + off);
+        const uint2 a = r[0], b = r[1], c = r[2];
+        rw[t][0] = a.x; rw[t][1] = a.y; rw[t][2] = b.x; rw[t][3] = b.y; rw[t][4] = c.x; rw[t][5] = c.y;
+    }
+}
+
+// the lane's low-res row from its source words: A / B' of its 24 output byte columns
+__device__ __forceinline__ void x2p_finish(const X2pLane& c, uint32_t b[6], uint32_t A[12], uint32_t Bp[12]) {
+    if (!c.second) x2p_patch_two_pixel(b);
+    const uint32_t left_n9 = __shfl_up_sync(0xFFFFFFFFu, b[3], 1), left_n10 = __shfl_up_sync(0xFFFFFFFFu, x2p_n10(b), 1);
+    const uint32_t right_b4 = __shfl_down_sync(0xFFFFFFFFu, b[4], 1), right_b0 = __shfl_down_sync(0xFFFFFFFFu, b[0], 1);
+    x2p_build(b, left_n9, left_n10, right_b4, right_b0, c.first, c.last, A, Bp);
+}
+
+// one output row of the strip: every storing lane puts its 24 bytes into the staging buffer (8-byte aligned there), then
+// the warp copies the row segment out with coalesced stores.  ooff < 0: this lane stores nothing.
+template <int U>
+__device__ __forceinline__ void x2p_store_row(uint8_t* ob, int ooff, const uint32_t* near_bp, const uint32_t* far_a,
+                                              uint8_t* g_lane, int lane, int nunits) {
+    if (ooff >= 0) {
+        uint32_t w[6];
+        x2p_emit(near_bp, far_a, w);
+        uint2* o = reinterpret_cast<uint2*>(ob + ooff);
+        o[0] = make_uint2(w[0], w[1]);
+        o[1] = make_uint2(w[2], w[3]);
+        o[2] = make_uint2(w[4], w[5]);
+    }
+    __syncwarp();
+    x2p_copy_out<U>(ob + U * lane, g_lane, lane, nunits);
+}
+
+template <int U>
+__device__ __forceinline__ void x2p_tile(const LowresX2wParams& p, const Tile& t, const DevImage& im, X2pWarpSmem& ws, int lane) {
+    constexpr bool M16 = (U == 16);
+    const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(&ws.in[0][0][0]) + U * lane;
+    const uint8_t* simg = p.src + im.src_off;
+    uint8_t* dimg = p.dst + im.dst_off;
+    const int n = 3 * im.w, nw = im.w >> 1, H = im.h, nh = H >> 1;
+    const int nchunks = (im.w + 7) >> 3;
+    const int c0 = kX2wChunksPerStrip * t.c;                     // first chunk this strip stores
+    const int ch = c0 - 1 + lane;
+    const int cc = min(max(ch, 0), nchunks - 1);
+    // staged source segment: chunks [cs, ce]: the strip and one halo chunk either side, clipped to the row (16-byte
+    // mode starts one chunk earlier so that 24 * cs is a multiple of 16)
+    const int cs = max(c0 - (M16 ? 2 : 1), 0), ce = min(c0 + kX2wChunksPerStrip, nchunks - 1);
+    const int in_units = (min(24 * (ce + 1), n) - 24 * cs + U - 1) / U;
+    const int out_units = (min(24 * (c0 + kX2wChunksPerStrip), n) - 24 * c0) / U;   // chunks [c0, c0 + 30): a multiple of U
+    X2pLane c;
+    c.soff = 24 * (cc - cs);
+    c.second = (nw - 4 * cc) >= 4;
+    c.first = (cc == 0);
+    c.last = (cc == nchunks - 1);
+    const bool stores = ch >= 0 && ch < nchunks && lane >= 1 && lane <= kX2wChunksPerStrip;
+    const int ooff = stores ? 24 * (lane - 1) : -1;
+    const int Y0 = t.a, Y1 = t.b;                 // Y0 is even; Y1 is even or H (H is even)
+    const int j0 = Y0 >> 1;
+    const int jfirst = max(j0 - 1, 0), jlast = min(Y1 >> 1, nh - 1);
+    const int64_t sp = im.src_pitch, dp = im.dst_pitch;
+    const uint8_t* gin = simg + 24 * cs + U * lane + (int64_t)(2 * jfirst) * sp;   // this lane's unit 0 of the next row to stage
+    uint8_t* gout = dimg + 24 * c0 + U * lane;                                     // ... of output row 0
+
+    __syncwarp();  // the previous tile's reads of the ring are done
+    // prologue: low-res rows jfirst .. jfirst + stages - 2 in flight
+    int jn = jfirst;       // next low-res row to stage
+    uint32_t sn = 0;       // its ring slot
+#pragma unroll
+    for (int q = 0; q < kX2pStages - 1; ++q) {
+        if (jn <= jlast) {
+            x2p_copy_in<U>(in_s + sn * (2 * kX2pRowBytes), gin, lane, in_units);
+            x2p_copy_in<U>(in_s + sn * (2 * kX2pRowBytes) + kX2pRowBytes, gin + sp, lane, in_units);
+            gin += 2 * sp;
+        }
+        cp_async_commit();
+        ++jn;
+        sn = (sn + 1 == kX2pStages) ? 0 : sn + 1;
+    }
+    uint32_t Ae[12], Be[12], Ao[12], Bo[12];      // A / B' of the latest even / odd low-res row
+    int obuf = 0;
+    uint32_t sc = 0;       // ring slot of low-res row j
+    // low-res row j completes output rows 2j-1 (near row j-1, far row j) and 2j (near row j, far row j-1)
+    for (int j = jfirst; j <= jlast; ++j) {
+        if (jn <= jlast) {  // refill the slot that row j-1 used
+            x2p_copy_in<U>(in_s + sn * (2 * kX2pRowBytes), gin, lane, in_units);
+            x2p_copy_in<U>(in_s + sn * (2 * kX2pRowBytes) + kX2pRowBytes, gin + sp, lane, in_units);
+            gin += 2 * sp;
+        }
+        cp_async_commit();
+        ++jn;
+        sn = (sn + 1 == kX2pStages) ? 0 : sn + 1;
+        cp_async_wait<kX2pStages - 1>();  // this lane's copies of row j have landed ...
+        __syncwarp();                     // ... and so have everybody else's
+        uint32_t rw[2][6], b[6];
+        x2p_read_stage(&ws.in[sc][0][0], c.soff, rw);
+        sc = (sc + 1 == kX2pStages) ? 0 : sc + 1;
+        x2p_area(rw[0], rw[1], b);
+        const bool up = j > j0, down = j >= j0 && 2 * j < Y1;
+        uint8_t* g1 = gout + (int64_t)(2 * j - 1) * dp;
+        if (j & 1) {
+            x2p_finish(c, b, Ao, Bo);
+            if (up) { x2p_store_row<U>(ws.out[obuf], ooff, Be, Ao, g1, lane, out_units); obuf ^= 1; }
+            if (down) { x2p_store_row<U>(ws.out[obuf], ooff, Bo, Ae, g1 + dp, lane, out_units); obuf ^= 1; }
+        } else {
+            x2p_finish(c, b, Ae, Be);
+            if (up) { x2p_store_row<U>(ws.out[obuf], ooff, Bo, Ae, g1, lane, out_units); obuf ^= 1; }
+            if (down) {
+                if (j == 0) x2p_store_row<U>(ws.out[obuf], ooff, Be, Ae, gout, lane, out_units);   // row 0 blends low-res row 0 with itself
+                else x2p_store_row<U>(ws.out[obuf], ooff, Be, Ao, g1 + dp, lane, out_units);
+                obuf ^= 1;
+            }
+        }
+        __syncwarp();  // all lanes have read their slot before the next iteration refills the one before it
+    }
+    if (Y1 == H) {  // the last image row blends low-res row nh-1 with itself
+        if ((nh - 1) & 1) x2p_store_row<U>(ws.out[obuf], ooff, Bo, Ao, gout + (int64_t)(H - 1) * dp, lane, out_units);
+        else x2p_store_row<U>(ws.out[obuf], ooff, Be, Ae, gout + (int64_t)(H - 1) * dp, lane, out_units);
+    }
+    cp_async_wait<0>();
+}
+
+// U: copy unit in bytes (16: image width a multiple of 16 and 16-byte aligned rows; 8; 4)
+template <int U, int MINB>
+__global__ void __launch_bounds__(128, MINB) lowres_x2p_kernel(LowresX2wParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    X2pWarpSmem& ws = reinterpret_cast<X2pWarpSmem*>(smem)[threadIdx.x >> 5];
+    for (;;) {
+        int ti = 0;
+        if (lane == 0) ti = (int)atomicAdd(p.counter, 1u);
+        ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+        if (ti >= p.n_tiles) break;
+        const Tile t = p.tiles[ti];
+        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
+        const DevImage im = p.images[t.img];
+        x2p_tile<U>(p, t, im, ws, lane);
+    }
+}
+
 int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
                   cudaStream_t stream, int img_lo, int img_hi) {
     // generic tiles (shapes that are not exact-2x in x)
@@ -673,7 +891,48 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
         }
     }
     // exact-2x shapes: warp-marching kernel when the rows are 4-byte aligned, full-width strips otherwise
-    const bool use_bands = (plan->n_lowres_x2w_tiles + plan->n_lowres_x2w4_tiles) > 0 && (((uintptr_t)src) & 3) == 0;
+    const int n_packed = plan->n_lowres_x2p_tiles[0] + plan->n_lowres_x2p_tiles[1] + plan->n_lowres_x2p_tiles[2];
+    const bool use_bands = (plan->n_lowres_x2w_tiles + plan->n_lowres_x2w4_tiles + n_packed) > 0 &&
+                           (((uintptr_t)src) & 3) == 0 && (n_packed == 0 || (((uintptr_t)dst) & 3) == 0);
+    for (int u = 0; u < 3 && use_bands; ++u) {
+        if (plan->n_lowres_x2p_tiles[u] == 0) continue;
+        const int t_lo = plan->lowres_x2p_tile_start[u][img_lo], t_hi = plan->lowres_x2p_tile_start[u][img_hi];
+        if (t_hi <= t_lo) continue;
+        LowresX2wParams p;
+        p.images = plan->d_images;
+        p.tiles = plan->d_lowres_x2p_tiles[u] + t_lo;
+        p.n_tiles = t_hi - t_lo;
+        p.shapes = plan->d_shapes;
+        p.tab = plan->d_tab;
+        p.src = src; p.dst = dst; p.opcodes = opcodes;
+        p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+        ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+        const int ctas = (p.n_tiles + 3) / 4;
+        int per_sm = 3;  // measured on a B200 (128 x 1920x1080): 3 CTAs/SM 5.86 TB/s, 4 CTAs/SM (128 registers) 5.68; knob ROD_X2P_CTAS
+        const char* e_ctas = getenv("ROD_X2P_CTAS");
+        if (e_ctas && atoi(e_ctas) >= 2 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
+        // the list's copy unit holds for offsets and pitches; the base pointers may be less aligned
+        const uintptr_t base = (uintptr_t)src | (uintptr_t)dst;
+        const int unit = std::min(u == 0 ? 16 : (u == 1 ? 8 : 4), (base & 15) == 0 ? 16 : ((base & 7) == 0 ? 8 : 4));
+        const size_t smem = 4 * sizeof(X2pWarpSmem);
+#define ROD_X2P_LAUNCH(U, B)                                                                                              \
+    do {                                                                                                                  \
+        ROD_CUDA(cudaFuncSetAttribute(lowres_x2p_kernel<U, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        lowres_x2p_kernel<U, B><<<grid_for(plan, ctas, B), 128, smem, stream>>>(p);                                       \
+    } while (0)
+#define ROD_X2P_LAUNCH_U(U)                                                      \
+    do {                                                                         \
+        if (per_sm == 2) ROD_X2P_LAUNCH(U, 2);                                   \
+        else if (per_sm == 4) ROD_X2P_LAUNCH(U, 4);                              \
+        else ROD_X2P_LAUNCH(U, 3);                                               \
+    } while (0)
+        if (unit == 16) ROD_X2P_LAUNCH_U(16);
+        else if (unit == 8) ROD_X2P_LAUNCH_U(8);
+        else ROD_X2P_LAUNCH_U(4);
+#undef ROD_X2P_LAUNCH_U
+#undef ROD_X2P_LAUNCH
+        ROD_CUDA(cudaGetLastError());
+    }
     if (use_bands) {
         const size_t smem = 4 * sizeof(X2wWarpTables);
         for (int pass = 0; pass < 2; ++pass) {  // 0: images with 8-byte aligned rows (64-bit loads), 1: the others

@@ -39,6 +39,7 @@ struct NoiseParams {
     const uint8_t* opcodes;
     int my_op;
     unsigned int* counter;  // zeroed before the launch
+    int piece_shift;        // table kernel: a work item is 1 / (1 << piece_shift) of a span
     const int32_t* table;   // table generator: the 256 entries X[i] (device global; expanded into shared memory)
 };
 
@@ -295,17 +296,21 @@ __global__ void __launch_bounds__(THREADS, 1) noise_table_kernel(NoiseParams p) 
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t base_s = tbase + 4u * lane, base_d = base_s + 128u;
+    // a warp takes a piece (a span, or a half / quarter of one: p.piece_shift) at a time from a shared counter
+    // (prefetching the next counter value during the current piece measured +-1 %: not done)
+    const uint32_t pmask = (1u << p.piece_shift) - 1u;
+    const int piece_len = kNoiseSpan >> p.piece_shift;
     for (;;) {
         uint32_t id = 0;
         if (lane == 0) id = atomicAdd(p.counter, 1u);
         id = __shfl_sync(0xFFFFFFFFu, id, 0);
-        if ((int)(id >> 2) >= p.n_tiles) break;
-        Tile t = p.tiles[id >> 2];
+        if ((int)(id >> p.piece_shift) >= p.n_tiles) break;
+        Tile t = p.tiles[id >> p.piece_shift];
         if (p.opcodes != nullptr && p.opcodes[t.img] != p.my_op) continue;
-        const int piece0 = (int)(id & 3u) * (kNoiseSpan / 4);
+        const int piece0 = (int)(id & pmask) * piece_len;
         if (piece0 >= t.b) continue;
         t.a += piece0;
-        t.b = min(kNoiseSpan / 4, t.b - piece0);
+        t.b = min(piece_len, t.b - piece0);
         const DevImage im = p.images[t.img];
         const uint64_t img_global = p.first_image + (uint64_t)t.img;
         const uint32_t ig_lo = (uint32_t)img_global, ig_hi = (uint32_t)(img_global >> 32);
@@ -416,12 +421,16 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
         sigma >= ROD_GAUSS_TABLE_MIN_SIGMA && sigma <= ROD_GAUSS_TABLE_MAX_SIGMA) {
         int rc = gauss_table_for(plan->device, sigma, &p.table);
         if (rc != ROD_OK) return rc;
-        // one 1024-thread CTA per SM, each with its own copy of the table; warps take quarter spans
-        int variant = 0;  // benchmark knob ROD_TAB_VARIANT: 0 = 1024 threads x unroll 2, 1 = unroll 4, 2 = unroll 1, 3 = 512 threads x unroll 2
-        const char* e_var = getenv("ROD_TAB_VARIANT");
-        if (e_var) variant = atoi(e_var);
-        const int threads = variant == 3 ? 512 : 1024;
-        const int ctas = grid_for(plan, (p.n_tiles * 4 + threads / 32 - 1) / (threads / 32), 1);
+        // one 1024-thread CTA per SM, each with its own copy of the table; warps take pieces of spans
+        // Work item = a whole span when there are plenty (>= 8 per resident warp), else a half / quarter span so that
+        // small batches still spread over all warps.  Measured on a B200, sigma 15, 1360x765: 256 images 5.10 TB/s with
+        // whole spans vs 4.87 with quarter spans (fewer atomic -> tile -> image dependency chains); 16 images 2.74 TB/s
+        // with quarter spans vs 2.38 with whole spans.  Knob: ROD_NOISE_PIECE_SHIFT = 0 | 1 | 2.
+        const long warps = 32L * plan->sm_count;
+        p.piece_shift = p.n_tiles >= 8 * warps ? 0 : (2L * p.n_tiles >= 8 * warps ? 1 : 2);
+        const char* e_ps = getenv("ROD_NOISE_PIECE_SHIFT");
+        if (e_ps && atoi(e_ps) >= 0 && atoi(e_ps) <= 2) p.piece_shift = atoi(e_ps);
+        const int ctas = grid_for(plan, ((p.n_tiles << p.piece_shift) + 31) / 32, 1);
 #define ROD_TAB_LAUNCH(M, TH, UN, R)                                                                                       \
     do {                                                                                                                   \
         ROD_CUDA(cudaFuncSetAttribute(noise_table_kernel<M, TH, UN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmemBytes)); \
@@ -432,12 +441,6 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
             if (r7) ROD_TAB_LAUNCH(NOISE_FIELD, 1024, 2, 7); else ROD_TAB_LAUNCH(NOISE_FIELD, 1024, 2, 10);
         } else if (r7) {
             ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 2, 7);
-        } else if (variant == 1) {
-            ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 4, 10);
-        } else if (variant == 2) {
-            ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 1, 10);
-        } else if (variant == 3) {
-            ROD_TAB_LAUNCH(NOISE_PHILOX, 512, 2, 10);
         } else {
             ROD_TAB_LAUNCH(NOISE_PHILOX, 1024, 2, 10);
         }

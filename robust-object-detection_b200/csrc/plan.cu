@@ -83,7 +83,21 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         band_rows = e_band ? atoi(e_band) : (int)(strip_rows / (80LL * plan->sm_count));  // ~5 tiles per resident warp (measured best on B200)
         band_rows = std::max(24, std::min(256, band_rows & ~7));  // <= kX2wMaxBandRows (per-warp shared tables)
     }
-    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles;
+    // packed-integer kernel (exact 2x in both axes): additionally needs 4-byte aligned destination rows (32 / 64-bit stores)
+    const char* e_packed = getenv("ROD_X2_PACKED");
+    const bool packed_on = !(e_packed && atoi(e_packed) == 0);
+    auto packed_image = [&](int i) {
+        const DevImage& im = plan->h_images[i];
+        return packed_on && shapes[im.shape_id].x2p != 0 && (im.dst_pitch & 3) == 0 && (im.dst_off & 3) == 0;
+    };
+    auto packed_class = [&](int i) {  // 0: 16-byte copy units, 1: 8-byte, 2: 4-byte
+        const DevImage& im = plan->h_images[i];
+        const uint64_t a = (uint64_t)im.src_pitch | (uint64_t)im.dst_pitch | im.src_off | im.dst_off;
+        if ((im.w & 15) == 0 && (a & 15) == 0) return 0;
+        if ((im.w & 7) == 0 && (a & 7) == 0) return 1;
+        return 2;
+    };
+    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles, x2p_tiles[3];
     build_strip_tiles(plan->h_images, shapes, false, kLowresTH, kLowresTWB, gen_tiles);
     build_strip_tiles(plan->h_images, shapes, true, kLowresTH, kLowresTWB, x2_tiles);
     for (int i = 0; i < plan->n_images; ++i) {
@@ -92,18 +106,22 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         if (march && march_image(i)) {
             for (int y = 0; y < plan->h_images[i].h; y += band_rows)
                 for (int st = 0; st < n_strips(plan->h_images[i].w); ++st)
-                    (al8_image(i) ? x2w_tiles : x2w4_tiles).push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows), st});
+                    (packed_image(i) ? x2p_tiles[packed_class(i)] : al8_image(i) ? x2w_tiles : x2w4_tiles).push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows), st});
         } else {
             for (int y = 0; y < plan->h_images[i].h; y += sh.strip_rows) x2_rest_tiles.push_back(Tile{i, y, 0, 0});
         }
     }
     void* old[] = {plan->d_shapes, plan->d_tab, plan->d_lowres_tiles, plan->d_lowres_x2_tiles, plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles,
-                   plan->d_lowres_x2_rest_tiles};
+                   plan->d_lowres_x2_rest_tiles, plan->d_lowres_x2p_tiles[0], plan->d_lowres_x2p_tiles[1], plan->d_lowres_x2p_tiles[2]};
     for (void* q : old)
         if (q) cudaFree(q);
     plan->d_shapes = nullptr; plan->d_tab = nullptr; plan->d_lowres_tiles = nullptr; plan->d_lowres_x2_tiles = nullptr;
     plan->d_lowres_x2w_tiles = nullptr; plan->d_lowres_x2w4_tiles = nullptr; plan->d_lowres_x2_rest_tiles = nullptr;
     int rc = upload(shapes, &plan->d_shapes);
+    for (int u = 0; u < 3; ++u) {
+        plan->d_lowres_x2p_tiles[u] = nullptr;
+        if (rc == ROD_OK) rc = upload(x2p_tiles[u], &plan->d_lowres_x2p_tiles[u]);
+    }
     if (rc == ROD_OK) rc = upload(blob, &plan->d_tab);
     if (rc == ROD_OK) rc = upload(gen_tiles, &plan->d_lowres_tiles);
     if (rc == ROD_OK) rc = upload(x2_tiles, &plan->d_lowres_x2_tiles);
@@ -115,6 +133,10 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     plan->n_lowres_x2_tiles = (int)x2_tiles.size();
     plan->n_lowres_x2w_tiles = (int)x2w_tiles.size();
     plan->n_lowres_x2w4_tiles = (int)x2w4_tiles.size();
+    for (int u = 0; u < 3; ++u) {
+        plan->n_lowres_x2p_tiles[u] = (int)x2p_tiles[u].size();
+        tile_starts(x2p_tiles[u], plan->n_images, plan->lowres_x2p_tile_start[u]);
+    }
     tile_starts(x2w4_tiles, plan->n_images, plan->lowres_x2w4_tile_start);
     plan->n_lowres_x2_rest_tiles = (int)x2_rest_tiles.size();
     tile_starts(gen_tiles, plan->n_images, plan->lowres_tile_start);
@@ -310,6 +332,7 @@ extern "C" void rod_plan_destroy(rod_plan* plan) {
     if (plan->d_patch_corrupted) cudaFree(plan->d_patch_corrupted);
     void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles,
                     plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles, plan->d_lowres_x2_rest_tiles, plan->d_shapes,
+                    plan->d_lowres_x2p_tiles[0], plan->d_lowres_x2p_tiles[1], plan->d_lowres_x2p_tiles[2],
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
                     plan->d_f2d_taps, plan->d_f2d_tiles, plan->d_counters,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};

@@ -65,6 +65,7 @@ struct DevShape {
     int32_t ay_packed;          // 1 when ay_pack is valid
     uint32_t ly_rc;             // float4 per output row: the vertical-stage constants (X2Row) of the exact-2x kernels
     int32_t x2w;                // 1: eligible for the warp-marching exact-2x kernel (lowres_x2w_kernel)
+    int32_t x2p;                // 1: exact 2x in both axes, w % 4 == 0: the packed-integer kernel (lowres_x2p_kernel)
 };
 
 // ---------------------------------------------------------------------------------
@@ -576,6 +577,113 @@ ROD_HD uint32_t x2_vertical(float x0, float x1, const X2Row& r) {
     const double y2 = floor((double)x1 * r.c1s + y1);
     return fbits((float)floor(y2 * 0.25 + r.k2));
 #endif
+}
+
+// ---------------------------------------------------------------------------------
+// a4 + a5 for shapes that are exact 2x in BOTH axes (w = 2 nw, h = 2 nh, i.e. even w and h at factor 0.5): an
+// all-integer pipeline on packed 16-bit halves, two values per 32-bit word (lowres.cu lowres_x2p_kernel).
+//   INTER_AREA is resizeAreaFast_:  P = (s00 + s01 + s10 + s11 + 2) >> 2.
+//   INTER_LINEAR x: with q = 3 N + F (N / F = the nearer / farther low-res pixel of the output pixel; at the image
+//     border F := N, OpenCV's (2048, 0) coefficients) the horizontal stage is hx = 512 q and (hx >> 4) = 32 q.
+//   INTER_LINEAR y: the two coefficients are exactly (1536, 512) with the heavier one on the nearer low-res row, so
+//     out = (((1536 * 32 qn) >> 16) + ((512 * 32 qf) >> 16) + 2) >> 2 = (floor(3 qn / 4) + floor(qf / 4) + 2) >> 2.
+//   Every low-res row therefore publishes, per output byte column, A = 64 floor(q / 4) and B' = 64 (floor(3 q / 4) + 2)
+//   (each < 2^16), and an output row is  byte 1 of (B'[near row] + A[far row])  -- one packed add per two bytes.
+// A lane owns a chunk of 8 output pixels = low-res pixels P0..P3 (+ the halo pixels P-1, P4 of its neighbours); packed
+// word t of a row holds the values of output bytes (2t, 2t+1) of the chunk, t = 0..11.
+// ---------------------------------------------------------------------------------
+template <int I0, int I1>
+ROD_HD uint32_t pk2(uint32_t w) {  // (byte I0 of w) | (byte I1 of w) << 16
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, I0 | (4 << 4) | (I1 << 8) | (4 << 12));
+#else
+    return ((w >> (8 * I0)) & 0xFFu) | (((w >> (8 * I1)) & 0xFFu) << 16);
+#endif
+}
+template <int SEL>
+ROD_HD uint32_t perm(uint32_t a, uint32_t b) {  // prmt.b32 in its default mode, selector nibbles 0..7
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, SEL);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((SEL >> (4 * i)) & 7))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+// The lane's twelve low-res values of one low-res row from its 24 source bytes of the two source rows, as raw sums
+// s00 + s01 + s10 + s11 + 2 in six packed words, then scaled to 16 P = ((sum) & 0x3FC) << 2.  Value (pixel p, channel c)
+// sits in: (0,0) b4.lo  (0,1) b0.lo  (0,2) b0.hi  (1,0) b1.lo  (1,1) b1.hi  (1,2) b4.hi
+//          (2,0) b5.lo  (2,1) b2.lo  (2,2) b2.hi  (3,0) b3.lo  (3,1) b3.hi  (3,2) b5.hi
+// (pairs chosen so that the two left bytes, and the two right bytes, of a word's values share one source word).
+ROD_HD void x2p_area(const uint32_t r0[6], const uint32_t r1[6], uint32_t b[6]) {
+    const uint32_t two = 0x00020002u;
+    b[0] = pk2<1, 2>(r0[0]) + pk2<0, 1>(r0[1]) + (pk2<1, 2>(r1[0]) + pk2<0, 1>(r1[1]) + two);
+    b[1] = pk2<2, 3>(r0[1]) + pk2<1, 2>(r0[2]) + (pk2<2, 3>(r1[1]) + pk2<1, 2>(r1[2]) + two);
+    b[2] = pk2<1, 2>(r0[3]) + pk2<0, 1>(r0[4]) + (pk2<1, 2>(r1[3]) + pk2<0, 1>(r1[4]) + two);
+    b[3] = pk2<2, 3>(r0[4]) + pk2<1, 2>(r0[5]) + (pk2<2, 3>(r1[4]) + pk2<1, 2>(r1[5]) + two);
+    b[4] = perm<0x5410>(sum_b0_b3(r1[0], sum_b0_b3(r0[0], 2u)), sum_b0_b3(r1[2], sum_b0_b3(r0[2], 2u)));
+    b[5] = perm<0x5410>(sum_b0_b3(r1[3], sum_b0_b3(r0[3], 2u)), sum_b0_b3(r1[5], sum_b0_b3(r0[5], 2u)));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; ++i) b[i] = (b[i] & 0x03FC03FCu) << 2;
+}
+// A chunk with two low-res pixels only (the last chunk of a row when w % 8 == 4): P2 := P1 (OpenCV's clamped right tap).
+ROD_HD void x2p_patch_two_pixel(uint32_t b[6]) {
+    b[2] = perm<0x7632>(b[1], b[4]);  // (P2.c1, P2.c2) := (P1.c1, P1.c2)
+    b[5] = b[1];                      // P2.c0 := P1.c0 (low half)
+}
+ROD_HD uint32_t x2p_n10(const uint32_t b[6]) { return perm<0x5432>(b[5], b[3]); }  // (P3.c2, P3.c0)
+// left_n9 / left_n10: the left neighbour lane's b[3] = (P3.c0, P3.c1) and x2p_n10(); right_b4 / right_b0: the right
+// neighbour's b[4] (low half P0.c0) and b[0] = (P0.c1, P0.c2).  first / last: the chunk touches the image border.
+ROD_HD void x2p_build(const uint32_t b[6], uint32_t left_n9, uint32_t left_n10, uint32_t right_b4, uint32_t right_b0,
+                      bool first, bool last, uint32_t A[12], uint32_t Bp[12]) {
+    uint32_t N[12], F[12];
+    N[0] = perm<0x5410>(b[4], b[0]);   // (P0.c0, P0.c1)
+    N[1] = perm<0x5432>(b[0], b[4]);   // (P0.c2, P0.c0)
+    N[2] = b[0];                       // (P0.c1, P0.c2)
+    N[3] = b[1];                       // (P1.c0, P1.c1)
+    N[4] = perm<0x5432>(b[4], b[1]);   // (P1.c2, P1.c0)
+    N[5] = perm<0x7632>(b[1], b[4]);   // (P1.c1, P1.c2)
+    N[6] = perm<0x5410>(b[5], b[2]);   // (P2.c0, P2.c1)
+    N[7] = perm<0x5432>(b[2], b[5]);   // (P2.c2, P2.c0)
+    N[8] = b[2];                       // (P2.c1, P2.c2)
+    N[9] = b[3];                       // (P3.c0, P3.c1)
+    N[10] = x2p_n10(b);                // (P3.c2, P3.c0)
+    N[11] = perm<0x7632>(b[3], b[5]);  // (P3.c1, P3.c2)
+    const uint32_t lc01 = first ? N[0] : left_n9;    // (P-1.c0, P-1.c1)
+    const uint32_t lc2 = first ? N[1] : left_n10;    // low half: P-1.c2
+    const uint32_t rc0 = last ? b[3] : right_b4;     // low half: P4.c0
+    const uint32_t rc12 = last ? N[11] : right_b0;   // (P4.c1, P4.c2)
+    F[0] = lc01;
+    F[1] = perm<0x5410>(lc2, b[1]);    // (P-1.c2, P1.c0)
+    F[2] = N[5];
+    F[3] = N[0];
+    F[4] = perm<0x5432>(b[0], b[5]);   // (P0.c2, P2.c0)
+    F[5] = N[8];
+    F[6] = N[3];
+    F[7] = perm<0x5432>(b[4], b[3]);   // (P1.c2, P3.c0)
+    F[8] = N[11];
+    F[9] = N[6];
+    F[10] = perm<0x5432>(b[2], rc0);   // (P2.c2, P4.c0)
+    F[11] = rc12;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int t = 0; t < 12; ++t) {
+        const uint32_t q16 = N[t] * 3u + F[t];               // 16 q per half, q = 3 N + F <= 1020
+        A[t] = q16 & 0xFFC0FFC0u;                            // 64 floor(q / 4)
+        Bp[t] = (q16 * 3u + 0x00800080u) & 0xFFC0FFC0u;      // 64 (floor(3 q / 4) + 2)
+    }
+}
+// One output row of the chunk: 24 bytes in six words.
+ROD_HD void x2p_emit(const uint32_t near_bp[12], const uint32_t far_a[12], uint32_t w[6]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int g = 0; g < 6; ++g)
+        w[g] = perm<0x7531>(near_bp[2 * g] + far_a[2 * g], near_bp[2 * g + 1] + far_a[2 * g + 1]);
 }
 
 // Detector-input normalisation: half(float(u8) / 255.f) is done with __float2half_rn on

@@ -66,6 +66,11 @@ struct rod_plan {
     int n_lowres_x2w4_tiles = 0;
     std::vector<int> lowres_x2w4_tile_start;
     rod::Tile* d_lowres_x2_rest_tiles = nullptr;
+    // exact 2x in both axes (packed-integer kernel), same band x strip tiles; three lists by the copy unit the image
+    // allows: [0] 16 bytes (w % 16 == 0, 16-byte aligned rows), [1] 8 bytes (w % 8 == 0, 8-byte aligned rows), [2] 4 bytes
+    rod::Tile* d_lowres_x2p_tiles[3] = {nullptr, nullptr, nullptr};
+    int n_lowres_x2p_tiles[3] = {0, 0, 0};
+    std::vector<int> lowres_x2p_tile_start[3];
     int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
     std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
     int lowres_x2w_band_rows = 0;

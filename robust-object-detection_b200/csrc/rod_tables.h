@@ -164,6 +164,16 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
             }
             sh.ly_rc = blob_push(blob, rc);
             sh.x2w = ((w & 3) == 0 && h >= 2 && (sh.area_mode == AREA_FAST2 || (sh.area_mode == AREA_GENERAL && sh.ay_packed))) ? 1 : 0;
+            // packed-integer kernel: exact 2x in both axes; it derives the row pairs and the (1536, 512) / (512, 1536) y
+            // coefficients from the row parity, so check that OpenCV's tables say the same
+            bool packed = sh.x2w && sh.area_mode == AREA_FAST2;
+            for (int y = 0; y < h && packed; ++y) {
+                const int s0 = (y & 1) ? (y - 1) / 2 : std::max(y / 2 - 1, 0);
+                const int s1 = (y & 1) ? std::min(s0 + 1, sh.nh - 1) : y / 2;
+                const uint32_t coef = (y & 1) ? (1536u | (512u << 16)) : (512u | (1536u << 16));
+                packed = (ly.s0[y] == s0 && ly.s1[y] == s1 && ly.coef[y] == coef);
+            }
+            sh.x2p = packed ? 1 : 0;
         }
     }
     *out = sh;

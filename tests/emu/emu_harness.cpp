@@ -393,6 +393,70 @@ extern "C" int emu_lowres_x2w(const uint8_t* src, uint8_t* dst, int h, int w, lo
     return 0;
 }
 
+// Replays lowres_x2p_kernel (packed-integer pipeline for shapes that are exact 2x in both axes): the same band x strip
+// tiles and 32-lane strips as lowres_x2w_kernel; per low-res row every lane forms its packed words (rod_core.h x2p_*),
+// the neighbour words arrive by "shuffle" (lane 0 / 31 get their own value back, like shfl.up / shfl.down).
+extern "C" int emu_lowres_x2p(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch, int band_rows) {
+    std::vector<uint32_t> blob;
+    DevShape sh;
+    if (!build_lowres_shape(h, w, 0.5, 8, blob, &sh)) return 2;
+    if (!sh.x2p) return 3;
+    const int n = 3 * w, nw = w >> 1, nh = h >> 1;
+    const int nchunks = (w + 7) >> 3, nstrips = (nchunks + 29) / 30;
+    struct Slot { uint32_t A[12], Bp[12]; };
+    for (int Y0 = 0; Y0 < h; Y0 += band_rows)
+        for (int st = 0; st < nstrips; ++st) {
+            const int Y1 = std::min(h, Y0 + band_rows);
+            const int j0 = Y0 >> 1, jfirst = std::max(j0 - 1, 0), jlast = std::min(Y1 >> 1, nh - 1);
+            std::vector<Slot> even(32), odd(32);
+            memset(even.data(), 0xCD, sizeof(Slot) * 32);  // poison
+            memset(odd.data(), 0xCD, sizeof(Slot) * 32);
+            auto store = [&](int y, const std::vector<Slot>& nearS, const std::vector<Slot>& farS) {
+                for (int l = 1; l <= 30; ++l) {
+                    const int ch = 30 * st - 1 + l;
+                    if (ch < 0 || ch >= nchunks) continue;
+                    const int nvalid = std::min(24, n - 24 * ch);
+                    uint32_t wds[6];
+                    x2p_emit(nearS[l].Bp, farS[l].A, wds);
+                    memcpy(dst + (long)y * dst_pitch + 24 * ch, wds, nvalid);
+                }
+            };
+            for (int j = jfirst; j <= jlast; ++j) {
+                uint32_t b[32][6];
+                for (int l = 0; l < 32; ++l) {
+                    const int ch = 30 * st - 1 + l;
+                    const int cc = std::min(std::max(ch, 0), nchunks - 1);
+                    const bool second = (nw - 4 * cc) >= 4;
+                    uint32_t rw[2][6];
+                    for (int t = 0; t < 2; ++t) {
+                        const uint8_t* rp = src + (long)(2 * j + t) * src_pitch + 24 * cc;
+                        memcpy(&rw[t][0], rp, 12);
+                        memcpy(&rw[t][3], rp + (second ? 12 : 0), 12);
+                    }
+                    x2p_area(rw[0], rw[1], b[l]);
+                    if (!second) x2p_patch_two_pixel(b[l]);
+                }
+                std::vector<Slot>& cur = (j & 1) ? odd : even;
+                for (int l = 0; l < 32; ++l) {
+                    const int ch = 30 * st - 1 + l;
+                    const int cc = std::min(std::max(ch, 0), nchunks - 1);
+                    const int ll = l > 0 ? l - 1 : l, lr = l < 31 ? l + 1 : l;
+                    x2p_build(b[l], b[ll][3], x2p_n10(b[ll]), b[lr][4], b[lr][0], cc == 0, cc == nchunks - 1, cur[l].A, cur[l].Bp);
+                }
+                const bool up = j > j0, down = j >= j0 && 2 * j < Y1;
+                if (j & 1) {
+                    if (up) store(2 * j - 1, even, odd);
+                    if (down) store(2 * j, odd, even);
+                } else {
+                    if (up) store(2 * j - 1, odd, even);
+                    if (down) store(2 * j, even, j == 0 ? even : odd);
+                }
+            }
+            if (Y1 == h) store(h - 1, ((nh - 1) & 1) ? odd : even, ((nh - 1) & 1) ? odd : even);
+        }
+    return 0;
+}
+
 extern "C" int emu_lowres(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
                           double factor, int src_phase) {
     std::vector<uint32_t> blob;

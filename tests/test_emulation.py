@@ -257,6 +257,35 @@ def test_emu_lowres_warp_marching(emu, band_rows):
         assert np.array_equal(got, want), (h, w, band_rows)
 
 
+X2P_SHAPES = [(360, 480), (100, 8), (2, 4), (4, 4), (64, 64), (130, 36), (200, 1400), (96, 1916), (540, 960), (34, 2000), (40, 20),
+              (76, 1364), (50, 240), (52, 244), (52, 248), (1078, 1916), (1050, 1400)]
+
+
+@pytest.mark.parametrize("band_rows", [24, 56, 512])
+def test_emu_lowres_packed_kernel(emu, band_rows):
+    """lowres_x2p_kernel (even w and h: the all-integer packed pipeline) replayed lane by lane on the CPU against the
+    oracle: halo lanes, neighbour words by shuffle, border replication, two-pixel last chunks (w % 8 == 4), band
+    boundaries, pitched rows; uniform and binary {0, 255} content (every rounding boundary of the >> 2 stages)."""
+    emu.emu_lowres_x2p.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_long, ctypes.c_long, ctypes.c_int]
+    for i, (h, w) in enumerate(X2P_SHAPES):
+        if band_rows != 56 and h * w > 600000:
+            continue
+        img = synth(900 + i, h, w)
+        if i % 4 == 1:
+            img = (img > 127).astype(np.uint8) * 255
+        want = orc.apply_lowres(img, 0.5)
+        pitch = 3 * w + (0 if i % 3 else 20)
+        buf = np.full((h, pitch), 0xAB, np.uint8)
+        buf[:, :3 * w] = img.reshape(h, 3 * w)
+        got = np.zeros_like(img)
+        rc = emu.emu_lowres_x2p(_p(buf), _p(got), h, w, pitch, 3 * w, band_rows)
+        assert rc == 0, (h, w, rc)
+        assert np.array_equal(got, want), (h, w, band_rows, int((got != want).sum()))
+    assert emu.emu_lowres_x2p(_p(buf), _p(got), 765, 1360, 4080, 4080, 56) == 3      # odd height: not this kernel's
+    assert emu.emu_lowres_x2p(_p(buf), _p(got), 100, 1362, 4086, 4086, 56) == 3      # w % 4 != 0
+
+
 def test_emu_filter2d_general_angles(emu):
     """filter2d_kernel's tiling / halo / tap order / FMA-vs-tail arithmetic replayed on the CPU against the outputs
     the reference produced at angles != 0 (tests/golden/golden_angles.npz)."""

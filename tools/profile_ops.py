@@ -22,6 +22,13 @@ for _ in range(3):
         plan.noise(src, dst, None, 15.0, seed=1)
     if "lowres" in which:
         plan.lowres(src, dst)
+if "lowres1080" in which:   # even x even shape: the packed-integer kernel
+    p2 = CorruptionPlan.uniform(48, 1080, 1920)
+    s2 = torch.randint(0, 256, (48, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
+    d2 = torch.empty_like(s2)
+    for _ in range(3):
+        p2.lowres(s2, d2)
+    del s2, d2
 if "letterbox" in which:
     import random
     random.seed(42)

@@ -1,0 +1,61 @@
+"""Times the fused LowRes kernels on a B200 (device-resident batches), with the packed-integer kernel on / off and its
+residency knob.  Usage: python tools/sweep_lowres.py [quick]"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from robust_object_detection_b200.batch import CorruptionPlan
+
+torch.cuda.set_device(0)
+POOL = [(765, 1360), (1050, 1400), (788, 1400), (1078, 1916), (1080, 1920), (1500, 2000), (540, 960), (360, 480),
+        (765, 1361), (1079, 1917), (1499, 1999)]
+
+
+def rate(fn, nbytes, steps=8, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return round(nbytes / (e0.elapsed_time(e1) / steps) / 1e6, 1)
+
+
+def workloads():
+    yield "1360x765_x256", [(765, 1360)] * 256
+    yield "1920x1080_x128", [(1080, 1920)] * 128
+    yield "1916x1078_x128", [(1078, 1916)] * 128
+    yield "1400x1050_x128", [(1050, 1400)] * 128
+    rng = np.random.default_rng(3000)
+    yield "mixed_256", [POOL[i] for i in rng.integers(0, len(POOL), 256)]
+    rng = np.random.default_rng(4000)
+    yield "visdrone_1610", [POOL[i] for i in rng.integers(0, 8, 1610)]
+    yield "odd_only_96", [POOL[8 + i % 3] for i in range(96)]
+
+
+settings = [("packed_4", {"ROD_X2P_CTAS": "4"}), ("packed_3", {"ROD_X2P_CTAS": "3"}), ("packed_2", {"ROD_X2P_CTAS": "2"})]
+extra = [kv.split("=") for kv in sys.argv[1:] if "=" in kv]
+if extra:
+    settings = [("custom", dict(extra))]
+out = {}
+for wname, shapes in workloads():
+    src = dst = None
+    for sname, env in settings:
+        for k in ("ROD_X2_PACKED", "ROD_X2P_CTAS"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        plan = CorruptionPlan.ragged(shapes)
+        if src is None:
+            src = torch.randint(0, 256, (plan.src_bytes,), dtype=torch.uint8, device="cuda")
+            dst = torch.empty_like(src)
+        out[f"{wname}:{sname}"] = rate(lambda: plan.lowres(src, dst), 2 * plan.payload_bytes)
+        del plan
+    del src, dst
+    print(json.dumps(out), flush=True)
