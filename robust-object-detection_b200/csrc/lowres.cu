@@ -863,6 +863,196 @@ __global__ void __launch_bounds__(128, MINB) lowres_x2p_kernel(LowresX2wParams p
     }
 }
 
+// =====================================================================================
+// Float-tap kernel for exact-2x WIDTHS whose height is not exact 2x (odd h at factor 0.5, e.g. 1360 x 765 -- the
+// BASELINE frame size): INTER_AREA runs OpenCV's general path (x taps (0.5, 0.5), two or three float y taps per low-res
+// row) and the INTER_LINEAR y coefficients are general.  Same strips, bands, halo lanes and shared-memory staging as
+// lowres_x2p_kernel (coalesced cp.async in, coalesced stores out); the arithmetic is lowres_x2w_kernel's, trimmed:
+//   * every SOURCE ROW is staged once in a ring of 8 rows and its pair sums are formed once: the last tap row of
+//     low-res row j is the first tap row of row j+1 and its sums are carried in registers (x2w loaded and reduced
+//     three tap rows per low-res row);
+//   * the vertical stage is 2 FFMA.RZ per byte + a packed integer finish (rod_core.h x2_vertical_pair) instead of
+//     3 FFMA.RZ + a byte pack;
+//   * per-row constants come from the global tables through L1 one row ahead (nothing else is in flight on the
+//     long scoreboard, the pixels arrive by cp.async), so no per-warp shared tables.
+// =====================================================================================
+constexpr int kX2fRing = 8;  // staged source rows per warp (power of two); eligibility (plan.cu): h <= 8 or h / nh <= 2.25
+struct alignas(16) X2fWarpSmem {
+    uint8_t in[kX2fRing][kX2pRowBytes];
+    uint8_t out[2][kX2pOutBytes];
+};
+
+// own 12 low-res bytes + the neighbouring pixels (by shuffle, or replicated at the image border) -> 24 horizontal-stage floats
+__device__ __forceinline__ void x2f_expand(const X2pLane& c, const uint32_t own[3], float x[24]) {
+    const uint32_t from_left = __shfl_up_sync(0xFFFFFFFFu, own[2], 1);     // left lane's last pixel = its bytes 9..11
+    const uint32_t from_right = __shfl_down_sync(0xFFFFFFFFu, own[0], 1);  // right lane's first pixel = its bytes 0..2
+    const uint32_t w0 = c.first ? (own[0] << 8) : (from_left & 0xFFFFFF00u);
+    const uint32_t w4 = c.last ? (own[2] >> 8) : (from_right & 0x00FFFFFFu);
+    const uint32_t win[5] = {funnel_r(w0, own[0], 8), funnel_r(own[0], own[1], 8), funnel_r(own[1], own[2], 8),
+                             funnel_r(own[2], w4, 8), w4 >> 8};
+    x2_expand24(win, x);
+}
+
+// one output row: 24 bytes per lane from the horizontal stages of the two low-res rows it blends
+template <int U>
+__device__ __forceinline__ void x2f_store_row(uint8_t* ob, int ooff, const float* xlo, const float* xhi, float c0s, float c1s,
+                                              float k0p, uint32_t cfix, uint8_t* g_lane, int lane, int nunits) {
+    if (ooff >= 0) {
+        uint32_t pr[12];
+#pragma unroll
+        for (int t = 0; t < 12; ++t)
+            pr[t] = x2_vertical_pair(xlo[2 * t], xhi[2 * t], xlo[2 * t + 1], xhi[2 * t + 1], c0s, c1s, k0p, cfix);
+        uint2* o = reinterpret_cast<uint2*>(ob + ooff);
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+            o[g] = make_uint2(perm<0x7531>(pr[4 * g], pr[4 * g + 1]), perm<0x7531>(pr[4 * g + 2], pr[4 * g + 3]));
+    }
+    __syncwarp();
+    x2p_copy_out<U>(ob + U * lane, g_lane, lane, nunits);
+}
+
+template <int U>
+__device__ __forceinline__ void x2f_tile(const LowresX2wParams& p, const Tile& t, const DevImage& im, const DevShape& sh,
+                                         X2fWarpSmem& ws, int lane) {
+    constexpr bool M16 = (U == 16);
+    const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(&ws.in[0][0]) + U * lane;
+    const uint8_t* simg = p.src + im.src_off;
+    uint8_t* dimg = p.dst + im.dst_off;
+    const int n = 3 * im.w, nw = sh.nw, H = im.h;
+    const int nchunks = (im.w + 7) >> 3;
+    const int c0 = kX2wChunksPerStrip * t.c;
+    const int ch = c0 - 1 + lane;
+    const int cc = min(max(ch, 0), nchunks - 1);
+    const int cs = max(c0 - (M16 ? 2 : 1), 0), ce = min(c0 + kX2wChunksPerStrip, nchunks - 1);
+    const int in_units = (min(24 * (ce + 1), n) - 24 * cs + U - 1) / U;
+    const int out_units = (min(24 * (c0 + kX2wChunksPerStrip), n) - 24 * c0) / U;
+    X2pLane c;
+    c.soff = 24 * (cc - cs);
+    c.second = (nw - 4 * cc) >= 4;
+    c.first = (cc == 0);
+    c.last = (cc == nchunks - 1);
+    const bool stores = ch >= 0 && ch < nchunks && lane >= 1 && lane <= kX2wChunksPerStrip;
+    const int ooff = stores ? 24 * (lane - 1) : -1;
+    const int64_t sp = im.src_pitch, dp = im.dst_pitch;
+    const uint8_t* gin = simg + 24 * cs + U * lane;    // this lane's unit 0 of source row 0
+    uint8_t* gout = dimg + 24 * c0 + U * lane;         // ... of output row 0
+    const uint32_t* ly_s = p.tab + sh.ly_s;
+    const uint4* ypack = reinterpret_cast<const uint4*>(p.tab + sh.ay_pack);
+    const int Y0 = t.a, Y1 = t.b;
+    const int j_first = (int)(__ldg(ly_s + Y0) & 0xFFFFu), j_last = (int)(__ldg(ly_s + Y1 - 1) >> 16);
+
+    // ---- staging: source rows are issued in increasing order, each once; one commit group per low-res row
+    int next_row = (int)__ldg(ypack + j_first).x;
+    const uint8_t* gnext = gin + (int64_t)next_row * sp;                           // this lane's unit 0 of source row next_row
+    uint32_t snext = in_s + (uint32_t)((next_row & (kX2fRing - 1)) * kX2pRowBytes);  // its ring slot
+    const uint32_t ring_end = in_s + kX2fRing * kX2pRowBytes;
+    auto stage_for = [&](int jt) {   // make sure the tap rows of low-res row jt are on their way
+        __syncwarp();                // nobody still reads the ring slots that are about to be refilled
+        if (jt <= j_last) {
+            const int target = min((int)__ldg(&ypack[jt].x) + 2, H - 1);
+            while (next_row <= target) {
+                x2p_copy_in<U>(snext, gnext, lane, in_units);
+                gnext += sp;
+                snext = (snext + kX2pRowBytes == ring_end) ? in_s : snext + kX2pRowBytes;
+                ++next_row;
+            }
+        }
+        cp_async_commit();
+    };
+    stage_for(j_first);
+    stage_for(j_first + 1);
+
+    float xe[24], xo[24];        // horizontal stage of the even / odd low-res row currently held
+    uint32_t carry[12];          // pair sums of source row carry_row (the last tap row of the previous low-res row)
+    int carry_row = -1;
+    int have = j_first - 1;      // highest low-res row produced so far
+    uint8_t* ob0 = ws.out[0];
+    uint8_t* ob1 = ws.out[1];
+    const uint8_t* in0 = &ws.in[0][c.soff];
+    // per-row constants {c0s, c1s, k0 + 2, cfix} and row pairs, fetched one output row ahead through L1
+    const float4* p_rc = reinterpret_cast<const float4*>(p.tab + sh.ly_rc2) + Y0;
+    const uint32_t* p_ys = ly_s + Y0;
+    uint32_t ys = __ldg(p_ys);
+    float4 rf = __ldg(p_rc);
+    uint4 pk = __ldg(ypack + j_first);   // {first tap row, beta0, beta1, beta2} of the next low-res row to produce
+    uint8_t* grow = gout + (int64_t)Y0 * dp;
+    for (int r = Y0; r < Y1; ++r, grow += dp) {
+        const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+        const float c0s = rf.x, c1s = rf.y, k0p = rf.z;
+        const uint32_t cfix = __float_as_uint(rf.w);
+        if (r + 1 < Y1) { ys = __ldg(++p_ys); rf = __ldg(++p_rc); }
+        while (have < s1) {
+            ++have;
+            stage_for(have + 2);
+            cp_async_wait<2>();   // this lane's copies for low-res row `have` have landed ...
+            __syncwarp();         // ... and so have everybody else's
+            const int sy0 = (int)pk.x;
+            const float b0 = __uint_as_float(pk.y), b1 = __uint_as_float(pk.z), b2 = __uint_as_float(pk.w);
+            if (have < j_last) pk = __ldg(ypack + have + 1);
+            float acc[12];
+#pragma unroll
+            for (int tp = 0; tp < 3; ++tp) {
+                const int row = (tp == 2) ? min(sy0 + 2, H - 1) : sy0 + tp;
+                if (!(tp == 0 && row == carry_row)) {   // (warp-uniform) the first tap row is usually the carried one
+                    const uint2* rp = reinterpret_cast<const uint2*>(in0 + (row & (kX2fRing - 1)) * kX2pRowBytes);
+                    const uint2 a = rp[0], b = rp[1], d = rp[2];
+                    const uint32_t rw[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
+                    x2f_pairsums(rw, carry);
+                }
+                x2f_mac(carry, tp == 0 ? b0 : (tp == 1 ? b1 : b2), tp == 0, acc);
+                carry_row = row;
+            }
+            uint32_t o6[2][6];
+            area_x2f_finish(acc, o6[0]);
+            area_x2f_finish(acc + 6, o6[1]);
+            uint32_t own[3];
+            {
+                const uint32_t a01 = __byte_perm(o6[0][0], o6[0][1], 0x0040), a23 = __byte_perm(o6[0][2], o6[0][3], 0x0040);
+                const uint32_t a45 = __byte_perm(o6[0][4], o6[0][5], 0x0040);
+                const uint32_t c01 = __byte_perm(o6[1][0], o6[1][1], 0x0040), c23 = __byte_perm(o6[1][2], o6[1][3], 0x0040);
+                const uint32_t c45 = __byte_perm(o6[1][4], o6[1][5], 0x0040);
+                own[0] = __byte_perm(a01, a23, 0x5410);
+                own[1] = __byte_perm(a45, c01, 0x5410);
+                own[2] = __byte_perm(c23, c45, 0x5410);
+                if (!c.second) {  // two-pixel last chunk: pixel 2 := pixel 1 (OpenCV's clamped right tap P[nw] = P[nw-1])
+                    own[2] = __byte_perm(own[1], 0u, 0x4441);
+                    own[1] = __byte_perm(own[0], own[1], 0x4354);
+                }
+            }
+            if (have & 1) x2f_expand(c, own, xo);
+            else x2f_expand(c, own, xe);
+        }
+        // s1 is s0 + 1 except on the first / last image rows (s1 == s0): the parity of s0 picks the slots
+        if (s1 != s0) {
+            if (s0 & 1) x2f_store_row<U>(ob0, ooff, xo, xe, c0s, c1s, k0p, cfix, grow, lane, out_units);
+            else x2f_store_row<U>(ob0, ooff, xe, xo, c0s, c1s, k0p, cfix, grow, lane, out_units);
+        } else {
+            if (s0 & 1) x2f_store_row<U>(ob0, ooff, xo, xo, c0s, c1s, k0p, cfix, grow, lane, out_units);
+            else x2f_store_row<U>(ob0, ooff, xe, xe, c0s, c1s, k0p, cfix, grow, lane, out_units);
+        }
+        uint8_t* tswap = ob0; ob0 = ob1; ob1 = tswap;
+    }
+    cp_async_wait<0>();
+}
+
+template <int U, int MINB>
+__global__ void __launch_bounds__(128, MINB) lowres_x2f_kernel(LowresX2wParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    X2fWarpSmem& ws = reinterpret_cast<X2fWarpSmem*>(smem)[threadIdx.x >> 5];
+    for (;;) {
+        int ti = 0;
+        if (lane == 0) ti = (int)atomicAdd(p.counter, 1u);
+        ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+        if (ti >= p.n_tiles) break;
+        const Tile t = p.tiles[ti];
+        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
+        const DevImage im = p.images[t.img];
+        const DevShape sh = p.shapes[im.shape_id];
+        x2f_tile<U>(p, t, im, sh, ws, lane);
+    }
+}
+
 int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
                   cudaStream_t stream, int img_lo, int img_hi) {
     // generic tiles (shapes that are not exact-2x in x)
@@ -891,47 +1081,60 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
         }
     }
     // exact-2x shapes: warp-marching kernel when the rows are 4-byte aligned, full-width strips otherwise
-    const int n_packed = plan->n_lowres_x2p_tiles[0] + plan->n_lowres_x2p_tiles[1] + plan->n_lowres_x2p_tiles[2];
+    const int n_packed = plan->n_lowres_x2p_tiles[0] + plan->n_lowres_x2p_tiles[1] + plan->n_lowres_x2p_tiles[2] +
+                         plan->n_lowres_x2f_tiles[0] + plan->n_lowres_x2f_tiles[1] + plan->n_lowres_x2f_tiles[2];
     const bool use_bands = (plan->n_lowres_x2w_tiles + plan->n_lowres_x2w4_tiles + n_packed) > 0 &&
                            (((uintptr_t)src) & 3) == 0 && (n_packed == 0 || (((uintptr_t)dst) & 3) == 0);
-    for (int u = 0; u < 3 && use_bands; ++u) {
-        if (plan->n_lowres_x2p_tiles[u] == 0) continue;
-        const int t_lo = plan->lowres_x2p_tile_start[u][img_lo], t_hi = plan->lowres_x2p_tile_start[u][img_hi];
-        if (t_hi <= t_lo) continue;
-        LowresX2wParams p;
-        p.images = plan->d_images;
-        p.tiles = plan->d_lowres_x2p_tiles[u] + t_lo;
-        p.n_tiles = t_hi - t_lo;
-        p.shapes = plan->d_shapes;
-        p.tab = plan->d_tab;
-        p.src = src; p.dst = dst; p.opcodes = opcodes;
-        p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
-        ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
-        const int ctas = (p.n_tiles + 3) / 4;
-        int per_sm = 3;  // measured on a B200 (128 x 1920x1080): 3 CTAs/SM 5.86 TB/s, 4 CTAs/SM (128 registers) 5.68; knob ROD_X2P_CTAS
-        const char* e_ctas = getenv("ROD_X2P_CTAS");
-        if (e_ctas && atoi(e_ctas) >= 2 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
-        // the list's copy unit holds for offsets and pitches; the base pointers may be less aligned
-        const uintptr_t base = (uintptr_t)src | (uintptr_t)dst;
-        const int unit = std::min(u == 0 ? 16 : (u == 1 ? 8 : 4), (base & 15) == 0 ? 16 : ((base & 7) == 0 ? 8 : 4));
-        const size_t smem = 4 * sizeof(X2pWarpSmem);
-#define ROD_X2P_LAUNCH(U, B)                                                                                              \
-    do {                                                                                                                  \
-        ROD_CUDA(cudaFuncSetAttribute(lowres_x2p_kernel<U, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        lowres_x2p_kernel<U, B><<<grid_for(plan, ctas, B), 128, smem, stream>>>(p);                                       \
+    // staged kernels (packed-integer: exact 2x in both axes; float taps: exact-2x width only), one launch per copy-unit class
+    for (int kind = 0; kind < 2 && use_bands; ++kind) {
+        for (int u = 0; u < 3; ++u) {
+            const int n_list = kind == 0 ? plan->n_lowres_x2p_tiles[u] : plan->n_lowres_x2f_tiles[u];
+            if (n_list == 0) continue;
+            const std::vector<int>& st = kind == 0 ? plan->lowres_x2p_tile_start[u] : plan->lowres_x2f_tile_start[u];
+            const int t_lo = st[img_lo], t_hi = st[img_hi];
+            if (t_hi <= t_lo) continue;
+            LowresX2wParams p;
+            p.images = plan->d_images;
+            p.tiles = (kind == 0 ? plan->d_lowres_x2p_tiles[u] : plan->d_lowres_x2f_tiles[u]) + t_lo;
+            p.n_tiles = t_hi - t_lo;
+            p.shapes = plan->d_shapes;
+            p.tab = plan->d_tab;
+            p.src = src; p.dst = dst; p.opcodes = opcodes;
+            p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+            ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+            const int ctas = (p.n_tiles + 3) / 4;
+            // measured on a B200 (128 x 1920x1080, packed): 3 CTAs/SM 5.88 TB/s, 4: 5.79, 2: 5.17; knobs ROD_X2P_CTAS / ROD_X2F_CTAS
+            int per_sm = kind == 0 ? 3 : 4;  // the float-tap kernel is issue-bound: more warps win (4: 3.69, 3: 3.34, 2: 2.74 TB/s)
+            const char* e_ctas = getenv(kind == 0 ? "ROD_X2P_CTAS" : "ROD_X2F_CTAS");
+            if (e_ctas && atoi(e_ctas) >= 2 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
+            // the list's copy unit holds for offsets and pitches; the base pointers may be less aligned
+            const uintptr_t base = (uintptr_t)src | (uintptr_t)dst;
+            const int unit = std::min(u == 0 ? 16 : (u == 1 ? 8 : 4), (base & 15) == 0 ? 16 : ((base & 7) == 0 ? 8 : 4));
+            const size_t smem = 4 * (kind == 0 ? sizeof(X2pWarpSmem) : sizeof(X2fWarpSmem));
+#define ROD_STAGED_LAUNCH(K, U, B)                                                                         \
+    do {                                                                                                   \
+        ROD_CUDA(cudaFuncSetAttribute(K<U, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        K<U, B><<<grid_for(plan, ctas, B), 128, smem, stream>>>(p);                                        \
     } while (0)
-#define ROD_X2P_LAUNCH_U(U)                                                      \
-    do {                                                                         \
-        if (per_sm == 2) ROD_X2P_LAUNCH(U, 2);                                   \
-        else if (per_sm == 4) ROD_X2P_LAUNCH(U, 4);                              \
-        else ROD_X2P_LAUNCH(U, 3);                                               \
+#define ROD_STAGED_LAUNCH_B(K, U)                                 \
+    do {                                                          \
+        if (per_sm == 2) ROD_STAGED_LAUNCH(K, U, 2);              \
+        else if (per_sm == 4) ROD_STAGED_LAUNCH(K, U, 4);         \
+        else ROD_STAGED_LAUNCH(K, U, 3);                          \
     } while (0)
-        if (unit == 16) ROD_X2P_LAUNCH_U(16);
-        else if (unit == 8) ROD_X2P_LAUNCH_U(8);
-        else ROD_X2P_LAUNCH_U(4);
-#undef ROD_X2P_LAUNCH_U
-#undef ROD_X2P_LAUNCH
-        ROD_CUDA(cudaGetLastError());
+#define ROD_STAGED_LAUNCH_U(K)                                    \
+    do {                                                          \
+        if (unit == 16) ROD_STAGED_LAUNCH_B(K, 16);               \
+        else if (unit == 8) ROD_STAGED_LAUNCH_B(K, 8);            \
+        else ROD_STAGED_LAUNCH_B(K, 4);                           \
+    } while (0)
+            if (kind == 0) ROD_STAGED_LAUNCH_U(lowres_x2p_kernel);
+            else ROD_STAGED_LAUNCH_U(lowres_x2f_kernel);
+#undef ROD_STAGED_LAUNCH_U
+#undef ROD_STAGED_LAUNCH_B
+#undef ROD_STAGED_LAUNCH
+            ROD_CUDA(cudaGetLastError());
+        }
     }
     if (use_bands) {
         const size_t smem = 4 * sizeof(X2wWarpTables);

@@ -66,6 +66,7 @@ struct DevShape {
     uint32_t ly_rc;             // float4 per output row: the vertical-stage constants (X2Row) of the exact-2x kernels
     int32_t x2w;                // 1: eligible for the warp-marching exact-2x kernel (lowres_x2w_kernel)
     int32_t x2p;                // 1: exact 2x in both axes, w % 4 == 0: the packed-integer kernel (lowres_x2p_kernel)
+    uint32_t ly_rc2;            // float4 per output row {c0s, c1s, k0 + 2, bits of x2_vertical_cfix}: lowres_x2f_kernel
 };
 
 // ---------------------------------------------------------------------------------
@@ -684,6 +685,43 @@ ROD_HD void x2p_emit(const uint32_t near_bp[12], const uint32_t far_a[12], uint3
 #endif
     for (int g = 0; g < 6; ++g)
         w[g] = perm<0x7531>(near_bp[2 * g] + far_a[2 * g], near_bp[2 * g + 1] + far_a[2 * g + 1]);
+}
+
+// Two outputs of the float vertical stage at once (lowres_x2f_kernel): the same two round-toward-zero multiply-adds
+// per byte as x2_vertical, y2 = 2^23 + b1 * 2048 + F0 + F1 + 2 (k0p = X2Row.k0 + 2), but the final (.. + 2) >> 2 is done
+// for a PAIR in integer arithmetic: the low 16 bits of y2's bit pattern are Dl + v with Dl = (b1 & 31) * 2048 and
+// v = F0 + F1 + 2 <= 1022 (no wrap: Dl + v < 2^16), so (packed pair) * 64 + cfix, cfix = -64 * Dl * 0x10001 (mod 2^32),
+// leaves 64 v in each half and byte 1 / byte 3 of the result are v >> 2 -- 2 FFMA + 1 PRMT/2 + 1 IMAD/2 per byte
+// instead of 3 FFMA, and the bytes are already in place for the final byte permute.
+ROD_HD uint32_t x2_vertical_cfix(uint32_t b_packed) { return (0u - (((b_packed >> 16) & 31u) << 17)) * 0x00010001u; }
+ROD_HD uint32_t x2_vertical_pair(float x0a, float x1a, float x0b, float x1b, float c0s, float c1s, float k0p, uint32_t cfix) {
+#if defined(__CUDA_ARCH__)
+    const float ya = __fmaf_rz(x1a, c1s, __fmaf_rz(x0a, c0s, k0p));
+    const float yb = __fmaf_rz(x1b, c1s, __fmaf_rz(x0b, c0s, k0p));
+    return __byte_perm(__float_as_uint(ya), __float_as_uint(yb), 0x5410) * 64u + cfix;
+#else
+    const double ya = floor((double)x1a * c1s + floor((double)x0a * c0s + k0p));
+    const double yb = floor((double)x1b * c1s + floor((double)x0b * c0s + k0p));
+    return ((fbits((float)ya) & 0xFFFFu) | (fbits((float)yb) << 16)) * 64u + cfix;
+#endif
+}
+// Pair sums of one source row for the float INTER_AREA y taps: s[k] = float bits of 2^23 + (byte k + byte k+3) for the
+// lane's twelve low-res byte columns (two 12-byte units), and the tap product / accumulation on them
+// (see area_x2f_accumulate: fma(x, beta, -beta * 2^23) == fl(beta * S) exactly).
+ROD_HD void x2f_pairsums(const uint32_t rw[6], uint32_t s[12]) {
+    const uint32_t magic[6] = {0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u, 0x4B000000u};
+    pair_sums12(rw[0], rw[1], rw[2], magic, s);
+    pair_sums12(rw[3], rw[4], rw[5], magic, s + 6);
+}
+ROD_HD void x2f_mac(const uint32_t s[12], float beta, bool first, float acc[12]) {
+    const float nb = fmul(beta, -8388608.0f);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 12; ++q) {
+        const float prod = fmaf(bitsf(s[q]), beta, nb);
+        acc[q] = first ? prod : fadd(acc[q], prod);
+    }
 }
 
 // Detector-input normalisation: half(float(u8) / 255.f) is done with __float2half_rn on

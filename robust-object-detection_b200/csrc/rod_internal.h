@@ -71,6 +71,10 @@ struct rod_plan {
     rod::Tile* d_lowres_x2p_tiles[3] = {nullptr, nullptr, nullptr};
     int n_lowres_x2p_tiles[3] = {0, 0, 0};
     std::vector<int> lowres_x2p_tile_start[3];
+    // exact-2x widths with float y taps (odd heights): lowres_x2f_kernel, same tiles and unit classes
+    rod::Tile* d_lowres_x2f_tiles[3] = {nullptr, nullptr, nullptr};
+    int n_lowres_x2f_tiles[3] = {0, 0, 0};
+    std::vector<int> lowres_x2f_tile_start[3];
     int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
     std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
     int lowres_x2w_band_rows = 0;

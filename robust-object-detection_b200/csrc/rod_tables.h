@@ -163,6 +163,14 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
                 rc[4 * y] = r.c0s; rc[4 * y + 1] = r.c1s; rc[4 * y + 2] = r.k0; rc[4 * y + 3] = r.k2;
             }
             sh.ly_rc = blob_push(blob, rc);
+            std::vector<uint32_t> rc2((size_t)h * 4);
+            for (int y = 0; y < h; ++y) {
+                const X2Row r = x2_row_consts(ly.coef[y]);
+                const float k0p = r.k0 + 2.0f;
+                memcpy(&rc2[4 * y], &r.c0s, 4); memcpy(&rc2[4 * y + 1], &r.c1s, 4); memcpy(&rc2[4 * y + 2], &k0p, 4);
+                rc2[4 * y + 3] = x2_vertical_cfix(ly.coef[y]);
+            }
+            sh.ly_rc2 = blob_push(blob, rc2);
             sh.x2w = ((w & 3) == 0 && h >= 2 && (sh.area_mode == AREA_FAST2 || (sh.area_mode == AREA_GENERAL && sh.ay_packed))) ? 1 : 0;
             // packed-integer kernel: exact 2x in both axes; it derives the row pairs and the (1536, 512) / (512, 1536) y
             // coefficients from the row parity, so check that OpenCV's tables say the same

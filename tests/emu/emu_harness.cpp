@@ -393,6 +393,99 @@ extern "C" int emu_lowres_x2w(const uint8_t* src, uint8_t* dst, int h, int w, lo
     return 0;
 }
 
+// Replays lowres_x2f_kernel: the strips / bands / halo lanes of lowres_x2w_kernel with its own arithmetic pieces -- pair sums
+// formed once per source row and carried from the last tap row of one low-res row to the first of the next
+// (x2f_pairsums / x2f_mac), and the paired vertical stage (x2_vertical_pair).
+extern "C" int emu_lowres_x2f(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
+                              double factor, int band_rows) {
+    std::vector<uint32_t> blob;
+    DevShape sh;
+    if (!build_lowres_shape(h, w, factor, 8, blob, &sh)) return 2;
+    if (blob.empty()) blob.push_back(0);
+    if (!sh.x2w) return 3;
+    const uint32_t* tab = blob.data();
+    const int n = 3 * w, nw = sh.nw;
+    const bool fast2 = sh.area_mode == AREA_FAST2;
+    const uint32_t* ypack = tab + sh.ay_pack;
+    const uint32_t* ly_s = tab + sh.ly_s;
+    const float* ly_rc = (const float*)(tab + sh.ly_rc);
+    const uint32_t* ly_b = tab + sh.ly_b;
+    const int nchunks = (w + 7) >> 3, nstrips = (nchunks + 29) / 30;
+    for (int Y0 = 0; Y0 < h; Y0 += band_rows)
+        for (int st = 0; st < nstrips; ++st) {
+            const int Y1 = std::min(h, Y0 + band_rows);
+            const int j_first = (int)(ly_s[Y0] & 0xFFFFu);
+            float xe[32][24], xo[32][24];
+            for (int l = 0; l < 32; ++l) for (int q = 0; q < 24; ++q) xe[l][q] = xo[l][q] = -1e30f;  // poison
+            int have = j_first - 1;
+            uint32_t carry[32][12];
+            int carry_row[32];
+            for (int l = 0; l < 32; ++l) carry_row[l] = -1;
+            for (int r = Y0; r < Y1; ++r) {
+                const uint32_t ys = ly_s[r];
+                const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+                while (have < s1) {
+                    ++have;
+                    const int j = have;
+                    uint32_t own[32][3];
+                    for (int l = 0; l < 32; ++l) {
+                        const int ch = 30 * st - 1 + l;
+                        const int cc = std::min(std::max(ch, 0), nchunks - 1);
+                        const bool second = (nw - 4 * cc) >= 4;
+                        const int sy0 = fast2 ? 2 * j : (int)ypack[4 * j];
+                        const int rows[3] = {sy0, sy0 + 1, std::min(sy0 + 2, h - 1)};
+                        uint32_t rw[3][6];
+                        for (int t = 0; t < 3; ++t) {
+                            const uint8_t* rp = src + (long)rows[t] * src_pitch + 24 * cc;
+                            memcpy(&rw[t][0], rp, 12);
+                            memcpy(&rw[t][3], rp + (second ? 12 : 0), 12);
+                        }
+                        uint32_t o6[2][6];
+                        if (fast2) return 4;
+                        float acc[12];
+                        for (int t = 0; t < 3; ++t) {
+                            if (!(t == 0 && rows[0] == carry_row[l])) x2f_pairsums(rw[t], carry[l]);
+                            x2f_mac(carry[l], bitsf(ypack[4 * j + 1 + t]), t == 0, acc);
+                            carry_row[l] = rows[t];
+                        }
+                        area_x2f_finish(acc, o6[0]);
+                        area_x2f_finish(acc + 6, o6[1]);
+                        uint8_t b[12];
+                        for (int q = 0; q < 6; ++q) { b[q] = (uint8_t)o6[0][q]; b[6 + q] = (uint8_t)o6[1][q]; }
+                        if (!second) { b[6] = b[3]; b[7] = b[4]; b[8] = b[5]; b[9] = b[10] = b[11] = 0; }
+                        memcpy(own[l], b, 12);
+                    }
+                    for (int l = 0; l < 32; ++l) {
+                        const int ch = 30 * st - 1 + l;
+                        const int cc = std::min(std::max(ch, 0), nchunks - 1);
+                        const uint32_t from_left = own[l > 0 ? l - 1 : l][2], from_right = own[l < 31 ? l + 1 : l][0];
+                        const uint32_t w0 = (cc == 0) ? (own[l][0] << 8) : (from_left & 0xFFFFFF00u);
+                        const uint32_t w4 = (cc == nchunks - 1) ? (own[l][2] >> 8) : (from_right & 0x00FFFFFFu);
+                        const uint32_t win[5] = {funnel_r(w0, own[l][0], 8), funnel_r(own[l][0], own[l][1], 8),
+                                                 funnel_r(own[l][1], own[l][2], 8), funnel_r(own[l][2], w4, 8), w4 >> 8};
+                        x2_expand24(win, (j & 1) ? xo[l] : xe[l]);
+                    }
+                }
+                X2Row rc;
+                rc.c0s = ly_rc[4 * r]; rc.c1s = ly_rc[4 * r + 1]; rc.k0 = ly_rc[4 * r + 2]; rc.k2 = ly_rc[4 * r + 3];
+                for (int l = 1; l <= 30; ++l) {
+                    const int ch = 30 * st - 1 + l;
+                    if (ch < 0 || ch >= nchunks) continue;
+                    const int nvalid = std::min(24, n - 24 * ch);
+                    const float* xlo = (s0 & 1) ? xo[l] : xe[l];
+                    const float* xhi = (s1 & 1) ? xo[l] : xe[l];
+                    const uint32_t cfix = x2_vertical_cfix(ly_b[r]);
+                    for (int q = 0; q < nvalid; q += 2) {
+                        const uint32_t pr = x2_vertical_pair(xlo[q], xhi[q], xlo[q + 1], xhi[q + 1], rc.c0s, rc.c1s, rc.k0 + 2.0f, cfix);
+                        dst[(long)r * dst_pitch + 24 * ch + q] = (uint8_t)(pr >> 8);
+                        dst[(long)r * dst_pitch + 24 * ch + q + 1] = (uint8_t)(pr >> 24);
+                    }
+                }
+            }
+        }
+    return 0;
+}
+
 // Replays lowres_x2p_kernel (packed-integer pipeline for shapes that are exact 2x in both axes): the same band x strip
 // tiles and 32-lane strips as lowres_x2w_kernel; per low-res row every lane forms its packed words (rod_core.h x2p_*),
 // the neighbour words arrive by "shuffle" (lane 0 / 31 get their own value back, like shfl.up / shfl.down).

@@ -257,6 +257,30 @@ def test_emu_lowres_warp_marching(emu, band_rows):
         assert np.array_equal(got, want), (h, w, band_rows)
 
 
+@pytest.mark.parametrize("band_rows", [24, 56, 512])
+def test_emu_lowres_float_staged_kernel(emu, band_rows):
+    """lowres_x2f_kernel's arithmetic (carried pair sums, paired vertical stage with the packed integer finish) replayed on
+    the CPU against the oracle on the odd-height shapes of X2W_SHAPES."""
+    emu.emu_lowres_x2f.argtypes = emu.emu_lowres_x2w.argtypes
+    n_run = 0
+    for i, (h, w) in enumerate(X2W_SHAPES):
+        if h % 2 == 0:
+            continue
+        img = synth(700 + i, h, w)
+        if i % 2:
+            img = (img > 127).astype(np.uint8) * 255
+        want = orc.apply_lowres(img, 0.5)
+        pitch = 3 * w + (0 if i % 3 else 20)
+        buf = np.full((h, pitch), 0xAB, np.uint8)
+        buf[:, :3 * w] = img.reshape(h, 3 * w)
+        got = np.zeros_like(img)
+        rc = emu.emu_lowres_x2f(_p(buf), _p(got), h, w, pitch, 3 * w, 0.5, band_rows)
+        assert rc == 0, (h, w, rc)
+        assert np.array_equal(got, want), (h, w, band_rows, int((got != want).sum()))
+        n_run += 1
+    assert n_run >= 6
+
+
 X2P_SHAPES = [(360, 480), (100, 8), (2, 4), (4, 4), (64, 64), (130, 36), (200, 1400), (96, 1916), (540, 960), (34, 2000), (40, 20),
               (76, 1364), (50, 240), (52, 244), (52, 248), (1078, 1916), (1050, 1400)]
 

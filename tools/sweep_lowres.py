@@ -30,9 +30,8 @@ def rate(fn, nbytes, steps=8, warmup=3):
 
 def workloads():
     yield "1360x765_x256", [(765, 1360)] * 256
-    yield "1920x1080_x128", [(1080, 1920)] * 128
-    yield "1916x1078_x128", [(1078, 1916)] * 128
-    yield "1400x1050_x128", [(1050, 1400)] * 128
+    yield "1400x787_x128", [(787, 1400)] * 128
+    yield "1916x1079_x128", [(1079, 1916)] * 128
     rng = np.random.default_rng(3000)
     yield "mixed_256", [POOL[i] for i in rng.integers(0, len(POOL), 256)]
     rng = np.random.default_rng(4000)
@@ -40,7 +39,7 @@ def workloads():
     yield "odd_only_96", [POOL[8 + i % 3] for i in range(96)]
 
 
-settings = [("packed_4", {"ROD_X2P_CTAS": "4"}), ("packed_3", {"ROD_X2P_CTAS": "3"}), ("packed_2", {"ROD_X2P_CTAS": "2"})]
+settings = [("f4", {"ROD_X2F_CTAS": "4"}), ("f3", {"ROD_X2F_CTAS": "3"})]
 extra = [kv.split("=") for kv in sys.argv[1:] if "=" in kv]
 if extra:
     settings = [("custom", dict(extra))]
@@ -48,7 +47,7 @@ out = {}
 for wname, shapes in workloads():
     src = dst = None
     for sname, env in settings:
-        for k in ("ROD_X2_PACKED", "ROD_X2P_CTAS"):
+        for k in ("ROD_X2_PACKED", "ROD_X2P_CTAS", "ROD_X2_FLOAT_STAGED", "ROD_X2F_CTAS"):
             os.environ.pop(k, None)
         os.environ.update(env)
         plan = CorruptionPlan.ragged(shapes)
