@@ -50,9 +50,14 @@ def _pool_init():
     cv2.setNumThreads(1)
 
 
+_POOL_IMAGES = {}  # per worker process: the synthetic input stays resident between tasks (like a decoded frame)
+
+
 def _pool_task(args):
     op, seed, h, w, reps = args
-    img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img = _POOL_IMAGES.get((seed, h, w))
+    if img is None:
+        img = _POOL_IMAGES[(seed, h, w)] = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
     np.random.seed(seed)
     fn = OPS[op]
     import time

@@ -19,13 +19,23 @@ Noise modes.  'compat' (default) draws the field on the host with
 np.random.normal(0, sigma, shape).astype(float32) -- consuming NumPy's global legacy stream
 exactly like the reference -- and the GPU does the add/clip/truncate, so outputs are
 bit-identical to the reference under the same np.random.seed.  'philox' generates the field
-inside the kernel (Philox4x32-10 keyed by seed and a running image counter; for 1 <= sigma <= 21 two 15-bit draws per
-Philox word from a 64 KB shared-memory quantile table, rotated by 45 degrees in integer arithmetic; Box-Muller otherwise):
+inside the kernel (Philox4x32-10 keyed by seed and a running image counter; for 3 <= sigma <= 20 four 8-bit draws per
+Philox word from a 256-entry table, mixed by a 4 x 4 Hadamard transform in integer arithmetic; Box-Muller otherwise):
 no host RNG work, statistically equivalent, not bit-identical.
+
+Process and thread model.  The functions are re-entrant: a module lock serialises the short critical section
+(plan cache, the shared page-locked noise buffer, the launch) so concurrent threads corrupting same-shaped images get
+the right bytes; the GPU runs one call at a time anyway.  In DataLoader WORKER PROCESSES each process needs its own
+CUDA context, which only the 'spawn' (or 'forkserver') start method gives: patch_ultralytics_augmentations() therefore
+switches multiprocessing to 'spawn' (the reference's launchers already call the patch at import time precisely so that
+spawned workers re-apply it, train_yolo_augmented.py:16-19).  A fork()ed child of a process that has used CUDA cannot
+use it: calling into this module from such a child raises a RuntimeError that names the fix instead of a raw CUDA error.
 """
 from __future__ import annotations
 
+import os
 import random
+import threading
 
 import numpy as np
 
@@ -43,6 +53,33 @@ _philox_seed = 0
 _philox_counter = 0
 _plans: dict = {}
 _PLAN_CACHE_MAX = 64
+_lock = threading.RLock()     # plan cache, pinned noise buffers, Philox counter, launch: one call at a time
+_owner_pid = None             # the process that first ran a corruption through this module (owns the CUDA context)
+
+
+def _check_process() -> None:
+    """Fail clearly in a fork()ed child of a process that already uses CUDA (the reference's hook runs inside DataLoader
+    workers, train_yolo_augmented.py:33 workers=8): CUDA cannot be re-initialised there and there is no CPU fallback."""
+    global _owner_pid
+    pid = os.getpid()
+    if _owner_pid == pid:
+        return
+    bad = _owner_pid is not None          # this module already ran in the parent, and we are a fork of it
+    if not bad:
+        try:  # the parent initialised CUDA through torch before forking (the usual Ultralytics situation)
+            import sys
+            torch = sys.modules.get("torch")
+            bad = bool(torch is not None and torch.cuda._is_in_bad_fork())
+        except Exception:
+            bad = False
+    if bad:
+        raise RuntimeError(
+            "robust_object_detection_b200: this process was fork()ed from a parent that already uses CUDA, and CUDA cannot "
+            "be initialised in such a child (there is no CPU fallback).  Start DataLoader workers with the 'spawn' start "
+            "method -- patch_ultralytics_augmentations() selects it; or torch.multiprocessing.set_start_method('spawn') / "
+            "DataLoader(multiprocessing_context='spawn') -- or use workers=0, or the main-process batch driver "
+            "robust_object_detection_b200.training.CorruptionBatcher.")
+    _owner_pid = pid
 
 
 def set_noise_mode(mode: str, seed: int = 0) -> None:
@@ -81,10 +118,12 @@ def _run(op: int, img_bgr: np.ndarray, *, noise=None, sigma=0.0, k=BLUR_KERNEL, 
     img, pitch = _as_rows(img_bgr)
     h, w, _ = img.shape
     out = np.empty((h, w, 3), dtype=np.uint8)  # fresh, C-contiguous, caller-owned
-    plan = _plan_for(h, w, pitch)
-    if op == N.OP_BLUR:
-        plan.set_blur_kernel(kernel)  # None: the angle-0 box
-    plan.apply_host(op, img, out, noise_host=noise, sigma=sigma, k=k, factor=factor, seed=seed, first_image_index=index)
+    with _lock:  # the cached plan (its staging buffers, its installed blur kernel) is shared by all threads
+        _check_process()
+        plan = _plan_for(h, w, pitch)
+        if op == N.OP_BLUR:
+            plan.set_blur_kernel(kernel)  # None: the angle-0 box
+        plan.apply_host(op, img, out, noise_host=noise, sigma=sigma, k=k, factor=factor, seed=seed, first_image_index=index)
     return out
 
 
@@ -150,14 +189,19 @@ def legacy_normal_f32(sigma: float, shape, out: np.ndarray = None) -> np.ndarray
 def apply_noise(img_bgr: np.ndarray, sigma: float) -> np.ndarray:
     global _philox_counter
     if _noise_mode == "compat":
-        # the exact draw of augmentations.py:31 (global legacy NumPy RNG, float64 -> float32)
-        if float(sigma) >= 0.0:
-            noise = legacy_normal_f32(sigma, img_bgr.shape, out=_pinned_field(int(np.prod(img_bgr.shape))))
-        else:
-            noise = legacy_normal_f32(sigma, img_bgr.shape)  # raises like the reference
-        return _run(N.OP_NOISE, img_bgr, noise=noise, sigma=float(sigma))
-    idx = _philox_counter
-    _philox_counter += 1
+        # the exact draw of augmentations.py:31 (global legacy NumPy RNG, float64 -> float32).  The draw goes into a
+        # page-locked buffer shared by all calls of this size, so draw + upload are one critical section (like the
+        # reference, whose np.random.normal holds NumPy's own lock for the draw).
+        with _lock:
+            _check_process()
+            if float(sigma) >= 0.0:
+                noise = legacy_normal_f32(sigma, img_bgr.shape, out=_pinned_field(int(np.prod(img_bgr.shape))))
+            else:
+                noise = legacy_normal_f32(sigma, img_bgr.shape)  # raises like the reference
+            return _run(N.OP_NOISE, img_bgr, noise=noise, sigma=float(sigma))
+    with _lock:
+        idx = _philox_counter
+        _philox_counter += 1
     return _run(N.OP_NOISE, img_bgr, sigma=float(sigma), seed=_philox_seed, index=idx)
 
 
@@ -195,11 +239,13 @@ def _apply_random_corruption(img_bgr: np.ndarray) -> np.ndarray:
 class RandomCorruption:
     """PIL Image transform that randomly applies one corruption (torchvision pipelines).
 
-    The reference converts RGB -> BGR, corrupts, converts back (augmentations.py:72-74).  Blur and LowRes act on each
-    channel separately and identically, so they are applied to the RGB array as it is (same bytes, no swaps); only
-    for noise does the channel order decide which plane of the field meets which channel, so only there is the image
-    swapped (cv2.cvtColor when OpenCV is importable, a NumPy reversal otherwise).  The `random` draws are the
-    reference's: random() for the gate, then random.choice inside _apply_random_corruption's dispatch."""
+    The reference converts RGB -> BGR, corrupts, converts back (augmentations.py:72-74).  The angle-0 blur and LowRes act
+    on each channel separately and identically, so they are applied to the RGB array as it is (same bytes, no swaps).
+    The image IS swapped for noise (the channel order decides which plane of the field meets which channel) and for a
+    blur at BLUR_ANGLE_DEG != 0 (the general 2-D filter mirrors OpenCV's FMA body / non-FMA row tail split, which is a
+    function of the byte position, so the channel order can move a rounding tie): cv2.cvtColor when OpenCV is importable,
+    a NumPy reversal otherwise.  The `random` draws are the reference's: random() for the gate, then random.choice
+    inside _apply_random_corruption's dispatch."""
 
     def __init__(self, p: float = 0.5):
         self.p = p
@@ -218,7 +264,7 @@ class RandomCorruption:
             return img
         rgb = np.array(img)
         name = random.choice(["noise", "blur", "lowres"])  # the draw of _apply_random_corruption (augmentations.py:50)
-        if name == "noise":
+        if name == "noise" or (name == "blur" and float(BLUR_ANGLE_DEG) != 0.0):
             out = self._swap(_DISPATCH[name](self._swap(rgb)))
         else:
             out = _DISPATCH[name](rgb)
@@ -227,12 +273,21 @@ class RandomCorruption:
 
 # ---- Ultralytics: monkey-patch Albumentations ----
 def patch_ultralytics_augmentations():
-    """Inject the corruption into Ultralytics' Albumentations transform (call ONCE before
-    model.train()).  With DataLoader workers > 0 the hook runs inside worker processes; CUDA
-    cannot be initialised in a fork()ed child of a process that already uses it, so use
-    workers=0 / the 'spawn' start method, or the batched main-process driver
-    (robust_object_detection_b200.batch.CorruptionPlan.corrupt_letterbox) instead."""
+    """Inject the corruption into Ultralytics' Albumentations transform (call ONCE before model.train()), like
+    augmentations.py:78-98.
+
+    With DataLoader workers > 0 (the reference launchers use workers=8, train_yolo_augmented.py:33) the hook runs inside
+    worker processes, and each needs its own CUDA context: the multiprocessing start method is switched to 'spawn'
+    here, before Ultralytics builds its DataLoader (the launchers call this function at import time, so spawned workers
+    re-import the launcher and re-apply the patch -- the Windows behaviour the reference was written for).  Set
+    ROD_KEEP_START_METHOD=1 to leave the start method alone; a fork()ed worker then raises the RuntimeError of
+    _check_process() on its first image."""
     from ultralytics.data import augment as _augment
+
+    if os.environ.get("ROD_KEEP_START_METHOD", "0") != "1":
+        import multiprocessing
+        if multiprocessing.get_start_method(allow_none=True) != "spawn":
+            multiprocessing.set_start_method("spawn", force=True)
 
     _OrigCall = _augment.Albumentations.__call__
 

@@ -52,31 +52,54 @@ int run_op(rod_plan* plan, int op, const uint8_t* src, uint8_t* dst, const float
 int run_mixed_ops(rod_plan* plan, int op_lo, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes, const float* noise,
                   float sigma, int k, double factor, uint64_t seed, uint64_t first_image, uint32_t offset,
                   cudaStream_t stream) {
+    // validate every op's parameters BEFORE anything is launched or forked: an unsupported k / factor / sigma must not
+    // leave the auxiliary streams un-joined (stream capture, ordering) or dst half written
+    if (noise == nullptr && sigma > kPhiloxMaxSigma) return ROD_ERR_UNSUPPORTED;
+    if (plan->f2d_ntaps == 0 && !blur_supported(k, 0.0)) return ROD_ERR_UNSUPPORTED;
+    {
+        const int rc = ensure_lowres_tables(plan, factor);
+        if (rc != ROD_OK) return rc;
+    }
     const bool fork = plan->n_images <= 128;
-    if (fork && plan->ev_fork == nullptr) {
-        for (auto& s : plan->aux_streams) ROD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        ROD_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
-        for (auto& e : plan->ev_join) ROD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (fork && plan->ev_fork == nullptr) {  // created as a whole or not at all (a failed creation is retried next call)
+        cudaStream_t s2[2] = {nullptr, nullptr};
+        cudaEvent_t ef = nullptr, ej[2] = {nullptr, nullptr};
+        cudaError_t e = cudaSuccess;
+        for (auto& s : s2)
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ef, cudaEventDisableTiming);
+        for (auto& ev : ej)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            for (auto& s : s2) if (s) cudaStreamDestroy(s);
+            if (ef) cudaEventDestroy(ef);
+            for (auto& ev : ej) if (ev) cudaEventDestroy(ev);
+            return cuda_fail(e);
+        }
+        plan->aux_streams[0] = s2[0]; plan->aux_streams[1] = s2[1];
+        plan->ev_join[0] = ej[0]; plan->ev_join[1] = ej[1];
+        plan->ev_fork = ef;
     }
     if (fork) {
         ROD_CUDA(cudaEventRecord(plan->ev_fork, stream));
         for (auto& s : plan->aux_streams) ROD_CUDA(cudaStreamWaitEvent(s, plan->ev_fork, 0));
     }
-    for (int op = op_lo; op <= ROD_OP_LOWRES; ++op) {
+    int first_rc = ROD_OK;
+    for (int op = op_lo; op <= ROD_OP_LOWRES && first_rc == ROD_OK; ++op) {
         // lowres (the longest) stays on the caller's stream; blur and noise go to the auxiliary streams
         cudaStream_t st = stream;
         if (fork && op == ROD_OP_BLUR) st = plan->aux_streams[0];
         if (fork && op == ROD_OP_NOISE) st = plan->aux_streams[1];
-        int rc = run_op(plan, op, src, dst, noise, sigma, k, factor, seed, first_image, offset, opcodes, st, 0, plan->n_images);
-        if (rc != ROD_OK) return rc;
+        first_rc = run_op(plan, op, src, dst, noise, sigma, k, factor, seed, first_image, offset, opcodes, st, 0, plan->n_images);
     }
-    if (fork) {
+    if (fork) {  // the join is executed on every path, also after a failed launch
         for (int i = 0; i < 2; ++i) {
-            ROD_CUDA(cudaEventRecord(plan->ev_join[i], plan->aux_streams[i]));
-            ROD_CUDA(cudaStreamWaitEvent(stream, plan->ev_join[i], 0));
+            cudaError_t e = cudaEventRecord(plan->ev_join[i], plan->aux_streams[i]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, plan->ev_join[i], 0);
+            if (e != cudaSuccess && first_rc == ROD_OK) first_rc = cuda_fail(e);
         }
     }
-    return ROD_OK;
+    return first_rc;
 }
 
 }  // namespace
@@ -186,8 +209,13 @@ extern "C" int rod_corrupt_batch_u8(rod_plan* plan, const uint8_t* src, uint8_t*
                                     const float* noise, float sigma, int k, double factor, uint64_t seed,
                                     uint64_t first_image_index, uint32_t offset, void* stream) {
     if (plan == nullptr || src == nullptr || dst == nullptr || opcodes == nullptr) return ROD_ERR_INVALID_ARG;
-    int rc = run_op(plan, ROD_OP_NONE, src, dst, noise, sigma, k, factor, seed, first_image_index, offset, opcodes,
-                    (cudaStream_t)stream, 0, plan->n_images);
+    // parameters are validated before the first launch (run_mixed_ops repeats the check for its other callers)
+    if (noise == nullptr && sigma > kPhiloxMaxSigma) return ROD_ERR_UNSUPPORTED;
+    if (plan->f2d_ntaps == 0 && !blur_supported(k, 0.0)) return ROD_ERR_UNSUPPORTED;
+    int rc = ensure_lowres_tables(plan, factor);
+    if (rc != ROD_OK) return rc;
+    rc = run_op(plan, ROD_OP_NONE, src, dst, noise, sigma, k, factor, seed, first_image_index, offset, opcodes,
+                (cudaStream_t)stream, 0, plan->n_images);
     if (rc != ROD_OK) return rc;
     return run_mixed_ops(plan, ROD_OP_NOISE, src, dst, opcodes, noise, sigma, k, factor, seed, first_image_index, offset,
                          (cudaStream_t)stream);
@@ -253,7 +281,7 @@ extern "C" int rod_restoration_pairs_f32(rod_plan* plan, const uint8_t* src, con
     for (int i = 1; i < n; ++i)  // one patch size per batch: the outputs are dense [N,3,P,P] tensors
         if (plan->descs[i].height != plan->descs[0].height || plan->descs[i].width != plan->descs[0].width)
             return ROD_ERR_INVALID_ARG;
-    if (plan->inner == nullptr) {
+    if (plan->inner == nullptr) {  // built as a whole or not at all: nothing is committed to the plan until every piece exists
         std::vector<rod_image_desc> d(n);
         const uint64_t bytes = 3ull * plan->descs[0].height * plan->descs[0].width;
         const uint64_t stride = (bytes + 255) / 256 * 256;
@@ -263,11 +291,21 @@ extern "C" int rod_restoration_pairs_f32(rod_plan* plan, const uint8_t* src, con
             d[i].width = plan->descs[0].width;
             d[i].src_pitch = d[i].dst_pitch = 3ll * d[i].width;
         }
-        int rc = rod_plan_create(d.data(), n, &plan->inner);
+        rod_plan* inner = nullptr;
+        int rc = rod_plan_create(d.data(), n, &inner);
         if (rc != ROD_OK) return rc;
-        plan->inner->gauss_generator = plan->gauss_generator;
-        ROD_CUDA(cudaMalloc((void**)&plan->d_patch_clean, n * stride + 64));
-        ROD_CUDA(cudaMalloc((void**)&plan->d_patch_corrupted, n * stride + 64));
+        uint8_t *pc = nullptr, *pp = nullptr;
+        cudaError_t e = cudaMalloc((void**)&pc, n * stride + 64);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&pp, n * stride + 64);
+        if (e != cudaSuccess) {
+            if (pc) cudaFree(pc);
+            rod_plan_destroy(inner);
+            return cuda_fail(e);
+        }
+        inner->gauss_generator = plan->gauss_generator;
+        plan->d_patch_clean = pc;
+        plan->d_patch_corrupted = pp;
+        plan->inner = inner;
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_gather_patches(plan, plan->inner, src, plan->d_patch_clean, flips, st);
@@ -290,10 +328,22 @@ extern "C" int rod_apply_host(rod_plan* plan, int op, const uint8_t* src_host, u
         int rc = ensure_lowres_tables(plan, factor);
         if (rc != ROD_OK) return rc;
     }
-    if (plan->d_stage_src == nullptr) {
-        ROD_CUDA(cudaMalloc((void**)&plan->d_stage_src, plan->src_extent + 64));
-        ROD_CUDA(cudaMalloc((void**)&plan->d_stage_dst, plan->dst_extent + 64));
-        for (auto& s : plan->streams) ROD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    if (plan->d_stage_dst == nullptr) {  // staging buffers + streams: committed to the plan only when all of them exist
+        uint8_t *ss = nullptr, *sd = nullptr;
+        cudaStream_t st3[3] = {nullptr, nullptr, nullptr};
+        cudaError_t e = cudaMalloc((void**)&ss, plan->src_extent + 64);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&sd, plan->dst_extent + 64);
+        for (auto& s : st3)
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            if (ss) cudaFree(ss);
+            if (sd) cudaFree(sd);
+            for (auto& s : st3) if (s) cudaStreamDestroy(s);
+            return cuda_fail(e);
+        }
+        plan->d_stage_src = ss;
+        for (int i = 0; i < 3; ++i) plan->streams[i] = st3[i];
+        plan->d_stage_dst = sd;
     }
     const bool compat = (op == ROD_OP_NOISE && noise_host != nullptr);
     if (compat && plan->d_stage_noise == nullptr)
@@ -322,32 +372,42 @@ extern "C" int rod_apply_host(rod_plan* plan, int op, const uint8_t* src_host, u
         if (d.dst_pitch != 3ll * d.width) dst_packed = false;
         if (i + 1 < n && plan->descs[i + 1].dst_offset != d.dst_offset + 3ull * d.width * d.height) dst_packed = false;
     }
+    // every CUDA call below records its error and falls through to the stream synchronisation at the end: copies into
+    // the caller's buffers may be in flight, so no early return
     int rc = ROD_OK;
+    auto cu = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == ROD_OK) rc = cuda_fail(e);
+        return e == cudaSuccess;
+    };
     for (size_t c = 0; c + 1 < cuts.size() && rc == ROD_OK; ++c) {
         const int lo = cuts[c], hi = cuts[c + 1];
         cudaStream_t st = plan->streams[c % 3];
         const rod_image_desc& a = plan->descs[lo];
         const rod_image_desc& b = plan->descs[hi - 1];
-        const uint64_t s_lo = a.src_offset, s_hi = b.src_offset + (uint64_t)(b.height - 1) * b.src_pitch + 3ull * b.width;
+        // byte range of the chunk's images.  A monotonic plan has increasing disjoint extents, so [first image start,
+        // last image end) covers exactly the chunk; any other plan (reversed, shuffled or aliased offsets: one chunk)
+        // uploads the whole span the descriptors touch.
+        const uint64_t s_lo = plan->monotonic ? a.src_offset : plan->src_min_offset;
+        const uint64_t s_hi = plan->monotonic ? b.src_offset + (uint64_t)(b.height - 1) * b.src_pitch + 3ull * b.width : plan->src_extent;
         const uint64_t d_lo = a.dst_offset, d_hi = b.dst_offset + (uint64_t)(b.height - 1) * b.dst_pitch + 3ull * b.width;
-        ROD_CUDA(cudaMemcpyAsync(plan->d_stage_src + s_lo, src_host + s_lo, s_hi - s_lo, cudaMemcpyHostToDevice, st));
+        if (!cu(cudaMemcpyAsync(plan->d_stage_src + s_lo, src_host + s_lo, s_hi - s_lo, cudaMemcpyHostToDevice, st))) break;
         if (compat) {
             const uint64_t e_lo = plan->h_images[lo].elem_base;
             const uint64_t e_hi = plan->h_images[hi - 1].elem_base + 3ull * b.height * b.width;
-            ROD_CUDA(cudaMemcpyAsync(plan->d_stage_noise + e_lo, noise_host + e_lo, (e_hi - e_lo) * sizeof(float),
-                                     cudaMemcpyHostToDevice, st));
+            if (!cu(cudaMemcpyAsync(plan->d_stage_noise + e_lo, noise_host + e_lo, (e_hi - e_lo) * sizeof(float),
+                                    cudaMemcpyHostToDevice, st))) break;
         }
         rc = run_op(plan, op, plan->d_stage_src, plan->d_stage_dst, compat ? plan->d_stage_noise : nullptr, sigma, k,
                     factor, seed, first_image_index, offset, nullptr, st, lo, hi);
         if (rc != ROD_OK) break;
         if (dst_packed) {
-            ROD_CUDA(cudaMemcpyAsync(dst_host + d_lo, plan->d_stage_dst + d_lo, d_hi - d_lo, cudaMemcpyDeviceToHost, st));
+            if (!cu(cudaMemcpyAsync(dst_host + d_lo, plan->d_stage_dst + d_lo, d_hi - d_lo, cudaMemcpyDeviceToHost, st))) break;
         } else {  // never write the caller's pitch padding / gaps: one 2-D copy per image
             for (int i = lo; i < hi; ++i) {
                 const rod_image_desc& d = plan->descs[i];
-                ROD_CUDA(cudaMemcpy2DAsync(dst_host + d.dst_offset, (size_t)d.dst_pitch, plan->d_stage_dst + d.dst_offset,
-                                           (size_t)d.dst_pitch, 3ull * d.width, (size_t)d.height,
-                                           cudaMemcpyDeviceToHost, st));
+                if (!cu(cudaMemcpy2DAsync(dst_host + d.dst_offset, (size_t)d.dst_pitch, plan->d_stage_dst + d.dst_offset,
+                                          (size_t)d.dst_pitch, 3ull * d.width, (size_t)d.height, cudaMemcpyDeviceToHost, st)))
+                    break;
             }
         }
     }

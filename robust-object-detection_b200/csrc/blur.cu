@@ -178,7 +178,7 @@ int launch_blur(const rod_plan* plan, const uint8_t* src, uint8_t* dst, int k, c
     if (ctas_per_sm > 4) ctas_per_sm = 4;
     const char* e_ctas = getenv("ROD_BLUR_CTAS");
     if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 4) ctas_per_sm = atoi(e_ctas);
-    p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+    p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
     ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     const int grid = grid_for(plan, (p.n_tiles + warps - 1) / warps, ctas_per_sm);
     if (k == 9) {

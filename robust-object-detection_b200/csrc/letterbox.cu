@@ -477,7 +477,7 @@ int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8
     if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : per_sm;
-    p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+    p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
     ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     const int tiles = plan->n_images * ((p.out_h + nw - 1) / nw);
     if (nw == 4) {

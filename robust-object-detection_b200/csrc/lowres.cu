@@ -1100,7 +1100,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.shapes = plan->d_shapes;
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
-            p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+            p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
             ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
             const int ctas = (p.n_tiles + 3) / 4;
             // measured on a B200 (128 x 1920x1080, packed): 3 CTAs/SM 5.88 TB/s, 4: 5.79, 2: 5.17; knobs ROD_X2P_CTAS / ROD_X2F_CTAS
@@ -1152,7 +1152,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             // a fresh counter per launch (ring of 256): launches of one plan may overlap on different streams
-            p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+            p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
             ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
             const int ctas = (p.n_tiles + 3) / 4;
             int per_sm = 4;  // benchmark knob: ROD_X2W_CTAS

@@ -412,7 +412,7 @@ int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* ds
     p.offset = offset;
     p.opcodes = opcodes; p.my_op = my_op;
     p.table = nullptr;
-    p.counter = plan->d_counters + (plan->launch_seq++ & 255u);
+    p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
     ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     int per_sm = 4;  // CTAs per SM the grid is sized for: 4 are resident, a longer queue evens out the tail (knob: ROD_NOISE_CTAS)
     const char* e_ctas = getenv("ROD_NOISE_CTAS");

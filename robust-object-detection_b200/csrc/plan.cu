@@ -267,6 +267,7 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
         im.shape_id = it->second;
         plan->max_w = std::max(plan->max_w, d.width);
         plan->all_contiguous = plan->all_contiguous && im.contiguous;
+        plan->src_min_offset = (i == 0) ? d.src_offset : std::min<uint64_t>(plan->src_min_offset, d.src_offset);
         plan->src_extent = std::max<uint64_t>(plan->src_extent, d.src_offset + (uint64_t)(d.height - 1) * d.src_pitch + 3ull * d.width);
         plan->dst_extent = std::max<uint64_t>(plan->dst_extent, d.dst_offset + (uint64_t)(d.height - 1) * d.dst_pitch + 3ull * d.width);
     }
@@ -290,7 +291,7 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
     }
     plan->n_noise_tiles = (int)nt.size();
     plan->n_blur_tiles = (int)bt.size();
-    if (cudaMalloc((void**)&plan->d_counters, 256 * sizeof(unsigned int)) != cudaSuccess) { rod_plan_destroy(plan); return ROD_ERR_OOM; }
+    if (cudaMalloc((void**)&plan->d_counters, kCounterRing * sizeof(unsigned int)) != cudaSuccess) { rod_plan_destroy(plan); return ROD_ERR_OOM; }
     int rc = upload(plan->h_images, &plan->d_images);
     if (rc == ROD_OK) rc = upload(nt, &plan->d_noise_tiles);
     if (rc == ROD_OK) rc = upload(bt, &plan->d_blur_tiles);

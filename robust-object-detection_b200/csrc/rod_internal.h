@@ -2,12 +2,15 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <vector>
 
 #include "../../include/rod_b200.h"
 #include "rod_core.h"
 
 namespace rod {
+
+constexpr unsigned int kCounterRing = 4096;  // rod_plan::d_counters
 
 // Tile geometry shared by the host tile builders and the kernels.
 constexpr int kNoiseSpan = 16384;  // elements (bytes) per noise work item
@@ -47,6 +50,7 @@ struct rod_plan {
     int max_w = 0;
     bool all_contiguous = true;
     uint64_t src_extent = 0, dst_extent = 0;  // bytes spanned by the descriptors in src / dst
+    uint64_t src_min_offset = 0;               // smallest src_offset (start of the span a host upload must cover)
 
     rod::DevImage* d_images = nullptr;
     rod::Tile* d_noise_tiles = nullptr;
@@ -78,8 +82,11 @@ struct rod_plan {
     int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
     std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
     int lowres_x2w_band_rows = 0;
-    unsigned int* d_counters = nullptr;  // ring of 256 work counters for dynamically scheduled kernels (one per launch)
-    mutable unsigned int launch_seq = 0;
+    // ring of work counters for dynamically scheduled kernels, one per launch: launches of one plan may be in flight
+    // on several streams / from several host threads, so the slot index is taken atomically and the ring is long
+    // enough (4096 launches) that a slot is never reused while its launch is still pending
+    unsigned int* d_counters = nullptr;
+    mutable std::atomic<unsigned int> launch_seq{0};
     bool monotonic = true;  // image extents are disjoint and increasing in both src and dst
     int gauss_generator = ROD_GAUSS_AUTO;  // Philox-mode Gaussian generator (rod_plan_set_gaussian_generator)
 

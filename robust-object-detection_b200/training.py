@@ -1,10 +1,10 @@
 """Main-process training hook: corruption + detector-input formatting on the GPU, fed from
 pinned host memory, for the Ultralytics launchers of the reference.
 
-The reference runs the corruption inside 8 forked DataLoader workers
-(scripts/augmentations.py:91-95, scripts/train_yolo_augmented.py:33).  CUDA cannot be initialised in those forks,
-and per-image host calls would be PCIe-latency bound anyway, so the B200 path moves the hook to the main process,
-after collation: raw HWC BGR uint8 frames of one batch go through ONE pinned staging buffer and ONE H2D copy, the
+The reference runs the corruption inside 8 DataLoader workers (scripts/augmentations.py:91-95,
+scripts/train_yolo_augmented.py:33).  The unmodified launchers keep working through the per-image drop-in functions in
+spawned workers (augmentations.patch_ultralytics_augmentations selects the start method); per-image host calls are
+PCIe-latency bound, though, so for custom training loops this module offers the batch form in the main process: raw HWC BGR uint8 frames of one batch go through ONE pinned staging buffer and ONE H2D copy, the
 decisions are drawn from Python's `random` in the reference's order (random() < 0.5, then random.choice), and
 `rod_corrupt_letterbox_f16` produces the fp16 NCHW tensor the detector consumes.  Two staging slots and a copy
 stream let batch i+1 upload while batch i is being corrupted.
@@ -68,6 +68,9 @@ class CorruptionBatcher:
             slot["host"] = torch.empty(cap, dtype=torch.uint8).pin_memory()
             slot["dev"] = torch.empty(cap, dtype=torch.uint8, device="cuda")
             slot["cap"] = cap
+            # the caching allocator may hand out a block whose last use (a previous step's output, activations) is still
+            # pending on the compute stream; the copy stream must not write it before that work has finished
+            self._copy_stream.wait_stream(torch.cuda.current_stream())
         ev = slot.get("free")
         if ev is not None:
             ev.synchronize()  # the compute that last read this slot's device buffer has finished
@@ -89,6 +92,7 @@ class CorruptionBatcher:
             slot["ops_host"] = torch.empty(max(n, 64), dtype=torch.uint8).pin_memory()
             slot["ops_dev"] = torch.empty(max(n, 64), dtype=torch.uint8, device="cuda")
             slot["ops_cap"] = max(n, 64)
+            self._copy_stream.wait_stream(torch.cuda.current_stream())
         slot["ops_host"][:n] = torch.from_numpy(np.asarray(ops, dtype=np.uint8))
         with torch.cuda.stream(self._copy_stream):
             slot["dev"][:nbytes].copy_(slot["host"][:nbytes], non_blocking=True)
@@ -205,21 +209,3 @@ class RestorationPairBatcher:
                                first_image_index=self.samples_seen)
         self.samples_seen += n
         return corrupted, clean
-
-
-def patch_ultralytics_trainer(trainer, batcher: Optional[CorruptionBatcher] = None):
-    """Optional glue for Ultralytics' trainer objects: replaces `trainer.preprocess_batch` so that a batch whose
-    "raw" entry holds the collated HWC BGR uint8 frames is corrupted + letterboxed + normalised on the GPU.
-    (Ultralytics is not installed in the build image; the contract is exercised with a stub in the tests.)"""
-    batcher = batcher or CorruptionBatcher()
-    orig = trainer.preprocess_batch
-
-    def _preprocess(batch):
-        raw = batch.get("raw")
-        if raw is None:
-            return orig(batch)
-        batch["img"] = batcher(raw).float() if getattr(trainer, "amp", True) is False else batcher(raw)
-        return batch
-
-    trainer.preprocess_batch = _preprocess
-    return batcher

@@ -103,10 +103,10 @@ def main():
             "lowres": sha(ref.apply_lowres(img, 0.5)),
             "noise_seed42": sha(ref.apply_noise(img, 15)),
         }
-    # config 1: 4 sequential apply_noise calls after one np.random.seed(42)
+    # config 1: all 64 sequential apply_noise calls after one np.random.seed(42) (BASELINE.json configs[0])
     np.random.seed(42)
     seq = []
-    for i in range(4):
+    for i in range(64):
         seq.append(sha(ref.apply_noise(synth(1000 + i, 765, 1360), 15)))
     hashes["noise_sequence"] = {"seed": 42, "first_image_seed": 1000, "sha": seq}
     # random-apply decisions (a6-a8): which op each of 64 consecutive calls picks
@@ -163,6 +163,40 @@ def make_angles():
     print("wrote", len(arrs), "angle arrays and", len(hashes), "hashes")
 
 
+LETTERBOX_CASES = [  # (seed, h, w, out_h, out_w)
+    (6000, 765, 1360, 640, 640), (6001, 1080, 1920, 640, 640), (6002, 360, 480, 320, 320), (6003, 640, 640, 640, 640),
+    (6004, 500, 375, 640, 640), (6005, 1050, 1400, 1024, 1024), (6006, 97, 133, 64, 96), (6007, 720, 1280, 640, 640),
+    (6008, 1078, 1916, 640, 640), (6009, 31, 45, 64, 64)]
+
+
+def make_letterbox():
+    """Config 5's formatting stage (Ultralytics LetterBox + Format + preprocess_batch) is not in /root/reference and
+    Ultralytics is not installable here, so it cannot be pinned to Ultralytics itself.  These vectors pin it to LIVE
+    OpenCV PRIMITIVES instead -- cv2.resize(INTER_LINEAR) to the documented LetterBox size, cv2.copyMakeBorder with
+    value (114, 114, 114) and the documented rounding of the padding, BGR -> RGB, HWC -> CHW, / 255 -> float16 -- so the
+    oracle's letterbox_norm_f16 (a NumPy restatement) and the GPU kernel are no longer only checked against each other.
+    The GEOMETRY formula (r = min(oh/h, ow/w); new = round(w r), round(h r); top = round(dh - 0.1)) is recalled from
+    Ultralytics 8.3.x and remains unverified against it."""
+    import cv2
+    out = {}
+    for seed, h, w, oh, ow in LETTERBOX_CASES:
+        img = synth(seed, h, w)
+        r = min(oh / h, ow / w)
+        new_w, new_h = int(round(w * r)), int(round(h * r))
+        dw, dh = (ow - new_w) / 2, (oh - new_h) / 2
+        res = img if (h, w) == (new_h, new_w) else cv2.resize(img, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
+        top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+        left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+        canvas = cv2.copyMakeBorder(res, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))
+        assert canvas.shape[:2] == (oh, ow), (canvas.shape, oh, ow)
+        chw = np.ascontiguousarray(canvas[:, :, ::-1].transpose(2, 0, 1))
+        f16 = (chw.astype(np.float32) / np.float32(255.0)).astype(np.float16)
+        out[f"{seed}_{h}x{w}_{oh}x{ow}"] = sha(f16)
+    with open(os.path.join(HERE, "golden_letterbox.json"), "w") as f:
+        json.dump({"cases": LETTERBOX_CASES, "sha": out, "cv2": cv2.__version__}, f, indent=1)
+    print("wrote", len(out), "letterbox hashes")
+
+
 def make_restoration():
     """(corrupted, clean) pairs of the unmodified RestorationDataset.__getitem__
     (scripts/train_restoration.py:104-129) on synthetic JPEG-free inputs: cv2.imread is replaced by a stub that
@@ -197,7 +231,10 @@ if __name__ == "__main__":
         make_restoration()
     elif len(sys.argv) > 1 and sys.argv[1] == "angles":
         make_angles()
+    elif len(sys.argv) > 1 and sys.argv[1] == "letterbox":
+        make_letterbox()
     else:
         main()
         make_angles()
         make_restoration()
+        make_letterbox()

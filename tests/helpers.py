@@ -36,3 +36,28 @@ def spawn_worker_corrupt(args):
     np.random.seed(seed)
     outs = [aug._apply_random_corruption(img) for _ in range(4)]
     return seed, [o.tobytes() for o in outs]
+
+
+class CorruptDataset:
+    """A torch-style map dataset whose __getitem__ runs the per-image drop-in hook, i.e. what the reference's DataLoader
+    workers do (tests/test_gpu_parity.py::test_dataloader_workers_fork_and_spawn).  Module-level so that spawned workers can
+    unpickle it."""
+
+    def __init__(self, jobs):
+        self.jobs = jobs
+
+    def __len__(self):
+        return len(self.jobs)
+
+    def __getitem__(self, i):
+        import os
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import random
+        import numpy as np
+        from robust_object_detection_b200 import augmentations as aug
+        seed, h, w = self.jobs[i]
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        random.seed(seed)
+        np.random.seed(seed)
+        return seed, aug._apply_random_corruption(img).tobytes()

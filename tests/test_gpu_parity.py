@@ -75,10 +75,13 @@ def test_big_cases_sha(aug, golden_hashes):
 
 
 def test_noise_sequence_config1(aug, golden_hashes):
+    """BASELINE.json configs[0] at full size: all 64 sequential apply_noise calls after one np.random.seed(42), against the
+    sha256 of the unmodified reference's 64 outputs."""
     g = golden_hashes["noise_sequence"]
+    assert len(g["sha"]) == 64
     np.random.seed(g["seed"])
     for i, want in enumerate(g["sha"]):
-        assert sha(aug.apply_noise(synth(g["first_image_seed"] + i, 765, 1360), 15)) == want
+        assert sha(aug.apply_noise(synth(g["first_image_seed"] + i, 765, 1360), 15)) == want, i
 
 
 @pytest.mark.parametrize("k", [1, 3, 7, 9, 13, 21, 31])
@@ -490,6 +493,163 @@ def test_spawned_dataloader_workers(aug):
         assert [o.tobytes() for o in want] == results[seed], seed
 
 
+def test_dataloader_workers_fork_and_spawn(aug, torch_):
+    """A real torch.utils.data.DataLoader(num_workers=2) around the per-image hook, under both start methods
+    (train_yolo_augmented.py:33 runs the hook in 8 DataLoader workers).  spawn: every worker owns a CUDA context and
+    the outputs equal the oracle's for the same seeds.  fork: this process has used CUDA, so a forked worker cannot --
+    the drop-in raises a RuntimeError naming the fix (not a raw CUDA error); the DataLoader re-raises it here."""
+    from torch.utils.data import DataLoader
+    from tests.helpers import CorruptDataset
+    aug.apply_lowres(synth(1, 8, 8), 0.5)       # this process owns a CUDA context now
+    jobs = [(501, 97, 133), (502, 120, 200), (503, 64, 64), (504, 81, 90), (505, 33, 47), (506, 40, 56)]
+    got = {}
+    for seed, data in DataLoader(CorruptDataset(jobs), batch_size=None, num_workers=2, multiprocessing_context="spawn"):
+        got[int(seed)] = data
+    for seed, h, w in jobs:
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        random.seed(seed)
+        np.random.seed(seed)
+        op = 1 + ("noise", "blur", "lowres").index(random.choice(["noise", "blur", "lowres"]))
+        assert got[seed] == orc.apply_op(img, op).tobytes(), seed
+    with pytest.raises(RuntimeError, match="spawn"):
+        for _ in DataLoader(CorruptDataset(jobs), batch_size=None, num_workers=2, multiprocessing_context="fork"):
+            pass
+
+
+def test_threads_sharing_shapes(aug):
+    """The per-image functions are re-entrant: threads corrupting same-shaped images concurrently -- they
+    share the cached plan, its staging buffers and, for the two blur variants, its installed kernel -- all get the
+    reference's bytes."""
+    import threading
+    img = [synth(7000 + i, 120, 200) for i in range(4)]
+    want = {"blur": [orc.apply_motion_blur(x, 9, 0) for x in img], "lowres": [orc.apply_lowres(x, 0.5) for x in img],
+            "blur5": [orc.apply_motion_blur(x, 5, 0) for x in img]}
+    kern = aug._motion_blur_kernel(5, 45.0)
+    want["blur45"] = [orc.apply_motion_blur(x, 5, 45.0, kernel=kern) for x in img]
+    errors = []
+
+    def work(t):
+        try:
+            for it in range(25):
+                i = (t + it) % 4
+                for name, fn in (("blur", lambda x: aug.apply_motion_blur(x, 9, 0)), ("lowres", lambda x: aug.apply_lowres(x, 0.5)),
+                                 ("blur45", lambda x: aug.apply_motion_blur(x, 5, 45.0)), ("blur5", lambda x: aug.apply_motion_blur(x, 5, 0))):
+                    if not np.array_equal(fn(img[i]), want[name][i]):
+                        errors.append((t, it, name))
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors[:5]
+
+
+def test_apply_host_non_monotonic_plan(torch_):
+    """rod_apply_host on plans whose images are NOT laid out in increasing order (reversed and shuffled offsets, which
+    rod_plan_create accepts): the host upload must cover every image, not the span between the first and last descriptor."""
+    from robust_object_detection_b200 import _native as N
+    from robust_object_detection_b200.batch import CorruptionPlan
+    shapes = [(37, 53), (64, 64), (31, 45), (20, 100)]
+    sizes = [3 * h * w for h, w in shapes]
+    imgs = [synth(8300 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    for order in ([3, 2, 1, 0], [2, 0, 3, 1]):
+        offs = [0] * 4
+        cur = 0
+        for i in order:                      # image i sits at the position `order` gives it
+            offs[i] = cur
+            cur += (sizes[i] + 255) // 256 * 256
+        plan = CorruptionPlan(shapes, offs, offs)
+        src = np.full(cur, 0xEE, np.uint8)
+        for i in range(4):
+            src[offs[i]:offs[i] + sizes[i]] = imgs[i].reshape(-1)
+        for op, fn in ((N.OP_BLUR, lambda x: orc.apply_motion_blur(x, 9, 0)), (N.OP_LOWRES, lambda x: orc.apply_lowres(x, 0.5))):
+            dst = np.zeros(cur, np.uint8)
+            plan.apply_host(op, src, dst)
+            for i, (h, w) in enumerate(shapes):
+                assert np.array_equal(dst[offs[i]:offs[i] + sizes[i]].reshape(h, w, 3), fn(imgs[i])), (order, op, i)
+
+
+def test_torch_library_ops_parity(torch_):
+    """The torch.library layer (torch.ops.rod.*) on CUDA uint8 tensors, current stream, against the oracle."""
+    import robust_object_detection_b200.torch_ops  # noqa: F401
+    rod = torch_.ops.rod
+    n, h, w = 5, 97, 133
+    imgs = np.stack([synth(8400 + i, h, w) for i in range(n)])
+    x = torch_.from_numpy(imgs).cuda()
+    assert np.array_equal(rod.blur(x, 9, 0.0).cpu().numpy(), np.stack([orc.apply_motion_blur(i, 9, 0) for i in imgs]))
+    assert np.array_equal(rod.lowres(x, 0.5).cpu().numpy(), np.stack([orc.apply_lowres(i, 0.5) for i in imgs]))
+    assert np.array_equal(rod.lowres(x[0], 0.5).cpu().numpy(), orc.apply_lowres(imgs[0], 0.5))          # [H,W,3] form
+    kern = orc_kernel = None
+    from robust_object_detection_b200.augmentations import _motion_blur_kernel
+    kern = _motion_blur_kernel(5, 60.0)
+    assert np.array_equal(rod.blur(x, 5, 60.0).cpu().numpy(), np.stack([orc.apply_motion_blur(i, 5, 60.0, kernel=kern) for i in imgs]))
+    assert np.array_equal(rod.blur(x, 9, 0.0).cpu().numpy(), np.stack([orc.apply_motion_blur(i, 9, 0) for i in imgs]))  # back to the box
+    np.random.seed(5)
+    field = np.random.normal(0, 15, imgs.shape).astype(np.float32)
+    got = rod.noise(x, 15.0, 0, 0, torch_.from_numpy(field).cuda()).cpu().numpy()
+    assert np.array_equal(got, np.stack([orc.add_noise_field(i, f) for i, f in zip(imgs, field)]))
+    got = rod.noise(x, 15.0, 77, 3).cpu().numpy()                                                  # Philox mode
+    for i in range(n):
+        assert np.array_equal(got[i], orc.add_philox_noise(imgs[i], orc.philox_noise_field(imgs[i].size, 15.0, 77, 3 + i)))
+    ops = np.array([0, 1, 2, 3, 2], np.uint8)
+    got = rod.corrupt_batch(x, torch_.from_numpy(ops).cuda(), 15.0, 9, 0.5, 9, 100).cpu().numpy()
+    assert np.array_equal(got[0], imgs[0]) and np.array_equal(got[2], orc.apply_motion_blur(imgs[2], 9, 0))
+    assert np.array_equal(got[3], orc.apply_lowres(imgs[3], 0.5)) and np.array_equal(got[4], orc.apply_motion_blur(imgs[4], 9, 0))
+    assert np.array_equal(got[1], orc.add_philox_noise(imgs[1], orc.philox_noise_field(imgs[1].size, 15.0, 9, 101)))
+    f16 = rod.corrupt_letterbox(x, torch_.from_numpy(ops).cuda(), 64, 96, 114, 15.0, 9, 0.5, 9, 100)
+    assert f16.shape == (n, 3, 64, 96) and f16.dtype == torch_.float16
+    assert np.array_equal(f16[2].cpu().numpy(), orc.letterbox_norm_f16(orc.apply_motion_blur(imgs[2], 9, 0), 64, 96))
+    assert np.array_equal(f16[0].cpu().numpy(), orc.letterbox_norm_f16(imgs[0], 64, 96))
+    # stream semantics: the ops run on the current stream
+    s = torch_.cuda.Stream()
+    with torch_.cuda.stream(s):
+        y = rod.lowres(x, 0.5)
+    s.synchronize()
+    assert np.array_equal(y.cpu().numpy(), np.stack([orc.apply_lowres(i, 0.5) for i in imgs]))
+    with pytest.raises(Exception):
+        rod.blur(x.cpu(), 9, 0.0)
+
+
+def test_letterbox_vs_cv2_primitive_golden(torch_):
+    """The fused corrupt + letterbox kernel with every image clean, against the vectors built from live cv2.resize +
+    cv2.copyMakeBorder (tests/golden/golden_letterbox.json): the formatting stage is pinned to OpenCV primitives, not only
+    to the builder's NumPy restatement."""
+    import json
+    from robust_object_detection_b200.batch import CorruptionPlan
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_letterbox.json")))
+    for seed, h, w, oh, ow in g["cases"]:
+        img = synth(seed, h, w)
+        plan = CorruptionPlan.uniform(1, h, w)
+        src = torch_.from_numpy(img[None]).cuda()
+        out = torch_.zeros((1, 3, oh, ow), dtype=torch_.float16, device="cuda")
+        plan.corrupt_letterbox(src, torch_.zeros(1, dtype=torch_.uint8, device="cuda"), out, oh, ow, 114)
+        assert sha(out[0].cpu().numpy()) == g["sha"][f"{seed}_{h}x{w}_{oh}x{ow}"], (h, w, oh, ow)
+
+
+def test_noise_prewarm_then_first_launch_in_graph(torch_):
+    """rod_noise_prewarm: after it, the FIRST Philox launch with a new sigma does no allocation / blocking copy and can
+    be captured in a CUDA graph."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    sigma = 7.625                                        # not used by any other test in this process
+    n, h, w = 3, 64, 80
+    plan = CorruptionPlan.uniform(n, h, w)
+    imgs = np.stack([synth(8500 + i, h, w) for i in range(n)])
+    src = torch_.from_numpy(imgs).cuda()
+    dst = torch_.zeros_like(src)
+    plan.blur(src, dst)                                  # (warm-up of unrelated lazy state)
+    CorruptionPlan.prewarm_noise(sigma)
+    torch_.cuda.synchronize()
+    g = torch_.cuda.CUDAGraph()
+    with torch_.cuda.graph(g):
+        plan.noise(src, dst, None, sigma, seed=11)
+    g.replay()
+    torch_.cuda.synchronize()
+    out = dst.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(out[i], orc.add_philox_noise(imgs[i], orc.philox_noise_field(imgs[i].size, sigma, 11, i)))
+
+
 def test_cuda_graph_capture_and_replay(torch_):
     """The device-resident entry points are stream-ordered (memset of the work counter + kernels): a corrupt_batch and a
     corrupt_letterbox call captured into a CUDA graph (after one eager call: resize tables, the noise quantile table and
@@ -552,6 +712,60 @@ def test_full_size_config2_batch_by_replication(torch_):
         getattr(plan, op)(src, dst)
         want = torch_.from_numpy(np.stack([fn(im) for im in base])).cuda()
         assert torch_.equal(dst.view(32, 8, h, w, 3), want.unsqueeze(0).expand(32, -1, -1, -1, -1)), op
+
+
+def test_full_size_config3_mixed_256_by_replication(torch_):
+    """BASELINE config 3 at full size: 256 mixed-resolution images (the 11 shapes of bench.py's draw, incl. the
+    odd-dimension variants) in one ragged batch -- one seeded image per shape, replicated according to the draw; every
+    replica must equal the oracle's fused LowRes output for its source image (0 mismatching bytes)."""
+    from robust_object_detection_b200.batch import CorruptionPlan
+    rng = np.random.default_rng(3000)
+    idx = rng.integers(0, len(CONFIG3_SHAPES), 256)
+    shapes = [CONFIG3_SHAPES[i] for i in idx]
+    plan = CorruptionPlan.ragged(shapes)
+    base = [synth(3300 + k, h, w) for k, (h, w) in enumerate(CONFIG3_SHAPES)]
+    want = [torch_.from_numpy(orc.apply_lowres(b, 0.5)).cuda() for b in base]
+    dev = [torch_.from_numpy(b).cuda() for b in base]
+    src = torch_.zeros(plan.src_bytes, dtype=torch_.uint8, device="cuda")
+    for i, k in enumerate(idx):
+        h, w = shapes[i]
+        src[plan.src_offsets[i]:plan.src_offsets[i] + 3 * h * w] = dev[k].reshape(-1)
+    dst = torch_.zeros_like(src)
+    plan.lowres(src, dst)
+    assert len(set(int(k) for k in idx)) == len(CONFIG3_SHAPES)
+    for i, k in enumerate(idx):
+        h, w = shapes[i]
+        got = dst[plan.dst_offsets[i]:plan.dst_offsets[i] + 3 * h * w].view(h, w, 3)
+        mism = int((got != want[k]).sum().item())
+        assert mism == 0, (i, shapes[i], mism)
+
+
+def test_config5_batch16_seed42(torch_):
+    """BASELINE config 5 as one case: batch 16 of 765x1360 frames, decisions drawn on the host with random.seed(42) in
+    the reference's order (random() < 0.5, then random.choice: golden 'ultralytics' stream), fused corrupt + letterbox 640
+    + normalise -> fp16 NCHW.  Non-noise images are bit-exact against oracle corruption + letterbox (itself pinned to the
+    cv2-primitive golden); noise images (Box-Muller Philox on this path) against the restated stream up to its float
+    tolerance."""
+    from robust_object_detection_b200.batch import CorruptionPlan, draw_decisions
+    n, h, w = 16, 765, 1360
+    random.seed(42)
+    ops_host = draw_decisions(n)
+    assert [int(o) for o in ops_host] == [0, 2, 1, 0, 0, 0, 2, 1, 3, 0, 0, 0, 0, 2, 0, 0]     # SURVEY section 4
+    imgs = np.stack([synth(5200 + i, h, w) for i in range(n)])
+    plan = CorruptionPlan.uniform(n, h, w)
+    src = torch_.from_numpy(imgs).cuda()
+    out = torch_.zeros((n, 3, 640, 640), dtype=torch_.float16, device="cuda")
+    plan.corrupt_letterbox(src, torch_.from_numpy(ops_host).cuda(), out, 640, 640, 114, seed=42)
+    got = out.cpu().numpy()
+    for i in range(n):
+        if ops_host[i] == 1:
+            cor = orc.add_philox_noise(imgs[i], orc.philox_noise_field(imgs[i].size, 15.0, 42, i, generator="boxmuller"))
+            want = orc.letterbox_norm_f16(cor, 640, 640, 114).astype(np.float32)
+            assert np.mean(np.abs(got[i].astype(np.float32) - want) > 1e-6) < 2e-3, i
+        else:
+            want = orc.letterbox_norm_f16(orc.apply_op(imgs[i], int(ops_host[i])), 640, 640, 114)
+            assert np.array_equal(got[i], want), (i, int(ops_host[i]))
+    assert np.all(got[:, :, :140, :] == np.float16(114 / 255)) and np.all(got[:, :, 500:, :] == np.float16(114 / 255))
 
 
 def test_full_size_config4_testset_by_replication_and_sharding(torch_):

@@ -122,28 +122,63 @@ def test_two_rank_gloo_sharding(tmp_path):
     assert max(r["ms"] for r in recs) == 2.0
 
 
-def test_trainer_patch_contract_with_stub():
-    """training.patch_ultralytics_trainer: batches without raw frames fall through to the trainer's own preprocess;
-    batches with raw frames are routed to the batcher (stubbed here: no GPU in this test)."""
-    from robust_object_detection_b200 import training
+def test_forked_child_guard_and_spawn_switch(monkeypatch):
+    """Process model of the reference's callers (train_yolo_augmented.py:16-19,33: the hook runs in workers=8 DataLoader
+    processes).  (1) A process whose pid differs from the one that first ran a corruption here -- a fork()ed worker --
+    gets a RuntimeError that names the fix, before any CUDA call.  (2) patch_ultralytics_augmentations() switches
+    multiprocessing to 'spawn' (each worker then owns a CUDA context), unless ROD_KEEP_START_METHOD=1.  No GPU needed."""
+    import multiprocessing
+    import sys
+    import types
+    from robust_object_detection_b200 import augmentations as aug
+    monkeypatch.setattr(aug, "_owner_pid", 1)           # "the parent"
+    with pytest.raises(RuntimeError, match="spawn"):
+        aug._check_process()
+    with pytest.raises(RuntimeError, match="fork"):
+        aug.apply_motion_blur(np.zeros((4, 4, 3), np.uint8), 9, 0)
+    monkeypatch.setattr(aug, "_owner_pid", None)
 
-    class Trainer:
-        amp = True
+    class Albumentations:
+        def __call__(self, labels):
+            return labels
 
-        def preprocess_batch(self, batch):
-            batch["seen_by_original"] = True
-            return batch
+    mod = types.ModuleType("ultralytics.data.augment")
+    mod.Albumentations = Albumentations
+    pkg, data = types.ModuleType("ultralytics"), types.ModuleType("ultralytics.data")
+    pkg.data, data.augment = data, mod
+    for name, m in (("ultralytics", pkg), ("ultralytics.data", data), ("ultralytics.data.augment", mod)):
+        monkeypatch.setitem(sys.modules, name, m)
+    before = multiprocessing.get_start_method(allow_none=True)
+    try:
+        monkeypatch.setenv("ROD_KEEP_START_METHOD", "1")
+        multiprocessing.set_start_method("fork", force=True)
+        aug.patch_ultralytics_augmentations()
+        assert multiprocessing.get_start_method() == "fork"
+        monkeypatch.setenv("ROD_KEEP_START_METHOD", "0")
+        aug.patch_ultralytics_augmentations()
+        assert multiprocessing.get_start_method() == "spawn"
+    finally:
+        multiprocessing.set_start_method(before, force=True)
 
-    class FakeBatcher:
-        def __call__(self, frames):
-            return ("device-tensor-for", len(frames))
 
-    t = Trainer()
-    got = training.patch_ultralytics_trainer(t, batcher=FakeBatcher())
-    assert isinstance(got, FakeBatcher)
-    assert t.preprocess_batch({"img": 1})["seen_by_original"] is True
-    out = t.preprocess_batch({"raw": [np.zeros((4, 4, 3), np.uint8)] * 3})
-    assert out["img"] == ("device-tensor-for", 3) and "seen_by_original" not in out
+def test_torch_library_ops_are_registered_and_traceable(built):
+    """rod::noise / blur / lowres / corrupt_batch / corrupt_letterbox exist as torch.library custom ops, trace through
+    their fake implementations (shapes / dtypes), and have no CPU kernel."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import robust_object_detection_b200.torch_ops  # noqa: F401
+    for name in ("noise", "blur", "lowres", "corrupt_batch", "corrupt_letterbox"):
+        assert hasattr(torch.ops.rod, name), name
+    with FakeTensorMode():
+        x = torch.empty((2, 8, 12, 3), dtype=torch.uint8, device="cuda")
+        ops = torch.empty(2, dtype=torch.uint8, device="cuda")
+        for y in (torch.ops.rod.noise(x, 15.0, 1, 0), torch.ops.rod.blur(x, 9, 0.0), torch.ops.rod.lowres(x, 0.5),
+                  torch.ops.rod.corrupt_batch(x, ops, 15.0, 9, 0.5, 1, 0)):
+            assert y.shape == x.shape and y.dtype == torch.uint8 and y.device.type == "cuda"
+        z = torch.ops.rod.corrupt_letterbox(x, ops, 64, 96, 114, 15.0, 9, 0.5, 1, 0)
+        assert z.shape == (2, 3, 64, 96) and z.dtype == torch.float16
+    with pytest.raises(NotImplementedError):
+        torch.ops.rod.blur(torch.zeros((4, 4, 3), dtype=torch.uint8), 9, 0.0)
 
 
 def test_numpy_legacy_normal_stream_bit_exact():

@@ -70,6 +70,20 @@ def test_noise_sequence_config1(golden_hashes):
         assert sha(orc.apply_noise(synth(g["first_image_seed"] + i, 765, 1360), 15)) == want
 
 
+def test_letterbox_oracle_vs_cv2_primitive_golden():
+    """The formatting stage of config 5 (no reference code: it lives in Ultralytics) -- the oracle's NumPy restatement
+    against vectors built in the build container from LIVE cv2.resize + cv2.copyMakeBorder(value=114) + / 255 -> float16
+    (tests/golden/make_golden.py make_letterbox).  Pins the arithmetic to OpenCV primitives; the LetterBox geometry
+    formula itself stays unverified against Ultralytics."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_letterbox.json")))
+    for seed, h, w, oh, ow in g["cases"]:
+        got = orc.letterbox_norm_f16(synth(seed, h, w), oh, ow)
+        assert got.dtype == np.float16 and got.shape == (3, oh, ow)
+        assert sha(got) == g["sha"][f"{seed}_{h}x{w}_{oh}x{ow}"], (h, w, oh, ow)
+
+
 def test_decisions_and_random_corruption(golden_hashes):
     for gate in ("ultralytics", "pil"):
         random.seed(42)
