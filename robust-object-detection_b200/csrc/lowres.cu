@@ -1053,6 +1053,225 @@ __global__ void __launch_bounds__(128, MINB) lowres_x2f_kernel(LowresX2wParams p
     }
 }
 
+// =====================================================================================
+// Odd-width kernel (w = 2 nw + 1 at factor 0.5; any height; rows at ANY byte alignment -- 3 w is odd, so consecutive rows
+// of a contiguous image cycle through all four 4-byte phases).  Same strips, bands, halo lanes, source-row ring and carried
+// tap row as lowres_x2f_kernel; what differs (rod_core.h x2g_*):
+//   * staging copies whole aligned 4-byte words (cp.async) from the word that holds the segment's first byte, so a staged
+//     row sits at its global phase (0..3) in the ring slot; a lane reads 8 aligned words and funnel-shifts them by that
+//     (warp-uniform) phase into its 27-byte window (9 source pixels);
+//   * the horizontal INTER_AREA stage is OpenCV's float pass with three taps per low-res column (per-column weights in
+//     registers), the vertical one works on those floats;
+//   * the INTER_LINEAR x stage uses the per-pixel coefficients and the per-pixel slip flag, the y stage the general
+//     3 x FFMA.RZ form;
+//   * output rows are byte aligned too: every lane shifts its 24 bytes by the row's destination phase (taking the
+//     spill-over of its left neighbour by shuffle), so the staging buffer mirrors the global 4-byte words; the row leaves
+//     as aligned 32-bit stores plus at most three byte stores at either end.
+// This replaces the tiled lowres_kernel for these shapes (it ran at 0.7 TB/s: scalar byte loads per tap, three block
+// barriers per tile).
+// =====================================================================================
+struct X2gLane {
+    int soff;          // byte offset of this lane's window inside a staged source row (without the phase)
+    int valid;         // valid low-res pixels of the chunk: min(4, nw - 4 * chunk), possibly <= 0
+    bool first, last;  // the chunk touches the left / right image border
+    uint32_t slip;     // bit k: odd output pixel 2k+1 of the chunk blends (P[k-1], P[k])
+};
+
+__device__ __forceinline__ void x2g_expand(const X2gLane& c, uint32_t own[3], const uint32_t coef[8], float x[24]) {
+    const uint32_t from_left = __shfl_up_sync(0xFFFFFFFFu, own[2], 1);     // left lane's last pixel = its bytes 9..11
+    if (c.valid < 4) x2g_replicate(own, max(c.valid, 0), from_left);
+    const uint32_t from_right = __shfl_down_sync(0xFFFFFFFFu, own[0], 1);  // right lane's first pixel = its bytes 0..2
+    const uint32_t w0 = c.first ? (own[0] << 8) : (from_left & 0xFFFFFF00u);
+    const uint32_t w4 = c.last ? (own[2] >> 8) : (from_right & 0x00FFFFFFu);
+    const uint32_t win[5] = {funnel_r(w0, own[0], 8), funnel_r(own[0], own[1], 8), funnel_r(own[1], own[2], 8),
+                             funnel_r(own[2], w4, 8), w4 >> 8};
+    x2g_expand24(win, coef, c.slip, x);
+}
+
+// one output row: the lane's 24 bytes, shifted to the destination row's 4-byte phase `ph`, into the staging buffer; then
+// the warp stores the row segment [grow, grow + olen): head bytes, aligned words, tail bytes
+__device__ __forceinline__ void x2g_store_row(uint8_t* ob, bool stores, const float* xlo, const float* xhi, const X2Row& rc,
+                                              uint8_t* grow, int olen, int lane) {
+    uint32_t o[24];
+#pragma unroll
+    for (int t = 0; t < 24; ++t) o[t] = x2_vertical(xlo[t], xhi[t], rc);
+    uint32_t w[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g)
+        w[g] = __byte_perm(__byte_perm(o[4 * g], o[4 * g + 1], 0x0040), __byte_perm(o[4 * g + 2], o[4 * g + 3], 0x0040), 0x5410);
+    const int ph = (int)((uintptr_t)grow & 3);
+    // buffer word 6 (lane - 1) + k = bytes [24 (lane - 1) + 4k - ph, +4) of the strip's output row: the last `ph` bytes of
+    // the left neighbour's chunk, then own bytes
+    const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, w[5], 1);
+    const int sh = 32 - 8 * ph;  // ph == 0: funnel by 32 = the high word, i.e. w[k] itself
+    uint32_t v[6];
+    v[0] = ph ? __funnelshift_r(prev, w[0], sh) : w[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) v[k] = ph ? __funnelshift_r(w[k - 1], w[k], sh) : w[k];
+    if (lane >= 1) {  // (lane 31's words carry the spill-over of lane 30)
+        uint2* q = reinterpret_cast<uint2*>(ob + 24 * (lane - 1));
+        q[0] = make_uint2(v[0], v[1]); q[1] = make_uint2(v[2], v[3]); q[2] = make_uint2(v[4], v[5]);
+    }
+    (void)stores;
+    __syncwarp();
+    // buffer byte ph + i = output byte i of the segment
+    const int head = min((4 - ph) & 3, olen);          // bytes before the first aligned global word
+    const int nbody = (olen - head) >> 2;
+    const int tail = olen - head - 4 * nbody;
+    if (lane < head) grow[lane] = ob[ph + lane];
+    if (lane >= 8 && lane - 8 < tail) grow[head + 4 * nbody + lane - 8] = ob[ph + head + 4 * nbody + lane - 8];
+    const uint32_t* sb = reinterpret_cast<const uint32_t*>(ob + ph + head);   // 4-byte aligned: ph + head is 0 or 4
+    uint32_t* gb = reinterpret_cast<uint32_t*>(grow + head);
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        if (lane + 32 * k < nbody) stg4s(gb + lane + 32 * k, sb[lane + 32 * k]);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) lowres_x2g_kernel(LowresX2wParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    X2fWarpSmem& ws = reinterpret_cast<X2fWarpSmem*>(smem)[threadIdx.x >> 5];
+    const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(&ws.in[0][0]) + 4 * lane;
+    for (;;) {
+        int ti = 0;
+        if (lane == 0) ti = (int)atomicAdd(p.counter, 1u);
+        ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+        if (ti >= p.n_tiles) break;
+        const Tile t = p.tiles[ti];
+        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
+        const DevImage im = p.images[t.img];
+        const DevShape sh = p.shapes[im.shape_id];
+        const uint8_t* simg = p.src + im.src_off;
+        uint8_t* dimg = p.dst + im.dst_off;
+        const int n = 3 * im.w, nw = sh.nw, H = im.h, W = im.w;
+        const int nchunks = (W + 7) >> 3;
+        const int c0 = kX2wChunksPerStrip * t.c;
+        const int ch = c0 - 1 + lane;
+        const int cc = min(max(ch, 0), nchunks - 1);
+        const int cs = max(c0 - 1, 0), ce = min(c0 + kX2wChunksPerStrip, nchunks - 1);
+        const int slen = min(24 * (ce + 1) + 3, n) - 24 * cs;          // staged bytes of a row: + the ninth pixel of chunk ce
+        const int olen = min(24 * (c0 + kX2wChunksPerStrip), n) - 24 * c0;
+        X2gLane c;
+        c.soff = 24 * (cc - cs);
+        c.valid = nw - 4 * cc;
+        c.first = (cc == 0);
+        c.last = (cc == nchunks - 1);
+        const bool stores = ch >= 0 && ch < nchunks && lane >= 1 && lane <= kX2wChunksPerStrip;
+        const int64_t sp = im.src_pitch, dp = im.dst_pitch;
+        const uint8_t* sseg = simg + 24 * cs;
+        uint8_t* dseg = dimg + 24 * c0;
+        // per-lane column constants: area weights of its four low-res pixels, linear coefficients and slip flags of its
+        // eight output pixels
+        float al[12];
+        uint32_t coef[8];
+        {
+            const float* xalpha = reinterpret_cast<const float*>(p.tab + sh.ax_alpha);
+            const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + sh.lx_s0);
+            const uint32_t* lx_a = p.tab + sh.lx_a;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int dx = min(4 * cc + q, nw - 1);
+#pragma unroll
+                for (int tp = 0; tp < 3; ++tp) al[3 * q + tp] = __ldg(xalpha + 3 * dx + tp);
+            }
+            c.slip = 0;
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                const int xa = min(8 * cc + x, W - 1);
+                coef[x] = __ldg(lx_a + xa);
+                if ((x & 1) && __ldg(lx_s0 + xa) == ((xa - 1) >> 1) - 1) c.slip |= 1u << (x >> 1);
+            }
+        }
+        const uint32_t* ly_s = p.tab + sh.ly_s;
+        const uint4* ypack = reinterpret_cast<const uint4*>(p.tab + sh.ay_pack);
+        const int Y0 = t.a, Y1 = t.b;
+        const int j_first = (int)(__ldg(ly_s + Y0) & 0xFFFFu), j_last = (int)(__ldg(ly_s + Y1 - 1) >> 16);
+
+        // ---- staging: whole aligned words from the word that holds the segment's first byte; a row's ring slot then
+        // holds it at its global phase
+        int next_row = (int)__ldg(ypack + j_first).x;
+        const uint8_t* gnext = sseg + (int64_t)next_row * sp;
+        uint32_t snext = in_s + (uint32_t)((next_row & (kX2fRing - 1)) * kX2pRowBytes);
+        const uint32_t ring_end = in_s + kX2fRing * kX2pRowBytes;
+        auto stage_for = [&](int jt) {
+            __syncwarp();
+            if (jt <= j_last) {
+                const int target = min((int)__ldg(&ypack[jt].x) + 2, H - 1);
+                while (next_row <= target) {
+                    const int ph = (int)((uintptr_t)gnext & 3);
+                    x2p_copy_in<4>(snext, gnext - ph + 4 * lane, lane, (slen + ph + 3) >> 2);
+                    gnext += sp;
+                    snext = (snext + kX2pRowBytes == ring_end) ? in_s : snext + kX2pRowBytes;
+                    ++next_row;
+                }
+            }
+            cp_async_commit();
+        };
+        stage_for(j_first);
+        stage_for(j_first + 1);
+
+        float xe[24], xo[24];
+        float carry[12];             // horizontal INTER_AREA values of source row carry_row
+        int carry_row = -1;
+        int have = j_first - 1;
+        uint8_t* ob0 = ws.out[0];
+        uint8_t* ob1 = ws.out[1];
+        const uint8_t* in0 = &ws.in[0][c.soff];
+        const float4* p_rc = reinterpret_cast<const float4*>(p.tab + sh.ly_rc3) + Y0;
+        const uint32_t* p_ys = ly_s + Y0;
+        uint32_t ys = __ldg(p_ys);
+        float4 rf = __ldg(p_rc);
+        uint4 pk = __ldg(ypack + j_first);
+        uint8_t* grow = dseg + (int64_t)Y0 * dp;
+        for (int r = Y0; r < Y1; ++r, grow += dp) {
+            const int s0 = (int)(ys & 0xFFFFu), s1 = (int)(ys >> 16);
+            X2Row rc;
+            rc.c0s = rf.x; rc.c1s = rf.y; rc.k0 = rf.z; rc.k2 = rf.w;
+            if (r + 1 < Y1) { ys = __ldg(++p_ys); rf = __ldg(++p_rc); }
+            while (have < s1) {
+                ++have;
+                stage_for(have + 2);
+                cp_async_wait<2>();
+                __syncwarp();
+                const int sy0 = (int)pk.x;
+                const float b0 = __uint_as_float(pk.y), b1 = __uint_as_float(pk.z), b2 = __uint_as_float(pk.w);
+                if (have < j_last) pk = __ldg(ypack + have + 1);
+                float acc[12];
+#pragma unroll
+                for (int tp = 0; tp < 3; ++tp) {
+                    const int row = (tp == 2) ? min(sy0 + 2, H - 1) : sy0 + tp;
+                    if (!(tp == 0 && row == carry_row)) {
+                        const int ph = (int)((uintptr_t)(sseg + (int64_t)row * sp) & 3);   // the staged row's phase (warp-uniform)
+                        const uint2* rp = reinterpret_cast<const uint2*>(in0 + (row & (kX2fRing - 1)) * kX2pRowBytes);
+                        const uint2 a = rp[0], b = rp[1], d = rp[2], e = rp[3];
+                        const uint32_t raw[8] = {a.x, a.y, b.x, b.y, d.x, d.y, e.x, e.y};
+                        uint32_t wn[7];
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) wn[k] = __funnelshift_r(raw[k], raw[k + 1], 8 * ph);
+                        x2g_hrow(wn, al, carry);
+                    }
+                    x2g_vmac(carry, tp == 0 ? b0 : (tp == 1 ? b1 : b2), tp == 0, acc);
+                    carry_row = row;
+                }
+                uint32_t own[3];
+                x2g_round12(acc, own);
+                if (have & 1) x2g_expand(c, own, coef, xo);
+                else x2g_expand(c, own, coef, xe);
+            }
+            if (s1 != s0) {
+                if (s0 & 1) x2g_store_row(ob0, stores, xo, xe, rc, grow, olen, lane);
+                else x2g_store_row(ob0, stores, xe, xo, rc, grow, olen, lane);
+            } else {
+                if (s0 & 1) x2g_store_row(ob0, stores, xo, xo, rc, grow, olen, lane);
+                else x2g_store_row(ob0, stores, xe, xe, rc, grow, olen, lane);
+            }
+            uint8_t* tswap = ob0; ob0 = ob1; ob1 = tswap;
+        }
+        cp_async_wait<0>();
+    }
+}
+
 int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
                   cudaStream_t stream, int img_lo, int img_hi) {
     // generic tiles (shapes that are not exact-2x in x)
@@ -1077,6 +1296,36 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
             ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 3 ? 3 : ctas_per_sm);
             lowres_kernel<<<grid_for(plan, p.n_tiles, ctas_per_sm), 256, smem, stream>>>(p);
+            ROD_CUDA(cudaGetLastError());
+        }
+    }
+    // odd widths at factor 0.5: the staged odd-width kernel (no alignment requirement)
+    if (plan->n_lowres_x2g_tiles > 0) {
+        const int t_lo = plan->lowres_x2g_tile_start[img_lo], t_hi = plan->lowres_x2g_tile_start[img_hi];
+        if (t_hi > t_lo) {
+            LowresX2wParams p;
+            p.images = plan->d_images;
+            p.tiles = plan->d_lowres_x2g_tiles + t_lo;
+            p.n_tiles = t_hi - t_lo;
+            p.shapes = plan->d_shapes;
+            p.tab = plan->d_tab;
+            p.src = src; p.dst = dst; p.opcodes = opcodes;
+            p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
+            ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+            const int ctas = (p.n_tiles + 3) / 4;
+            const size_t smem = 4 * sizeof(X2fWarpSmem);
+            int per_sm = 3;  // knob ROD_X2G_CTAS = 2 | 3 | 4
+            const char* e_ctas = getenv("ROD_X2G_CTAS");
+            if (e_ctas && atoi(e_ctas) >= 2 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
+#define ROD_X2G_LAUNCH(B)                                                                                              \
+    do {                                                                                                               \
+        ROD_CUDA(cudaFuncSetAttribute(lowres_x2g_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        lowres_x2g_kernel<B><<<grid_for(plan, ctas, B), 128, smem, stream>>>(p);                                       \
+    } while (0)
+            if (per_sm == 2) ROD_X2G_LAUNCH(2);
+            else if (per_sm == 4) ROD_X2G_LAUNCH(4);
+            else ROD_X2G_LAUNCH(3);
+#undef ROD_X2G_LAUNCH
             ROD_CUDA(cudaGetLastError());
         }
     }

@@ -107,11 +107,33 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         return x2f_on && sh.x2w != 0 && sh.area_mode == AREA_GENERAL && sh.ay_packed && (im.dst_pitch & 3) == 0 &&
                (im.dst_off & 3) == 0 && (sh.h <= 8 || 4LL * sh.h <= 9LL * sh.nh);
     };
-    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles, x2p_tiles[3], x2f_tiles[3];
-    build_strip_tiles(plan->h_images, shapes, false, kLowresTH, kLowresTWB, gen_tiles);
+    // odd-width staged kernel: regular 3-tap / one-slip shapes whose y scale fits the ring of 8 source rows
+    const char* e_x2g = getenv("ROD_X2_ODD_STAGED");
+    const bool x2g_on = !(e_x2g && atoi(e_x2g) == 0);
+    auto odd_image = [&](int i) {
+        const DevShape& sh = shapes[plan->h_images[i].shape_id];
+        return x2g_on && sh.x2g != 0 && (sh.h <= 8 || 4LL * sh.h <= 9LL * sh.nh);
+    };
+    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles, x2p_tiles[3], x2f_tiles[3], x2g_tiles, gen_all;
+    build_strip_tiles(plan->h_images, shapes, false, kLowresTH, kLowresTWB, gen_all);
+    for (const Tile& t : gen_all)
+        if (!odd_image(t.img)) gen_tiles.push_back(t);
     build_strip_tiles(plan->h_images, shapes, true, kLowresTH, kLowresTWB, x2_tiles);
+    int band_rows_odd = 0;
+    {
+        long long strip_rows = 0;
+        for (int i = 0; i < plan->n_images; ++i)
+            if (odd_image(i)) strip_rows += (long long)plan->h_images[i].h * n_strips(plan->h_images[i].w);
+        band_rows_odd = std::max(24, std::min(256, (int)(strip_rows / (60LL * plan->sm_count)) & ~7));
+    }
     for (int i = 0; i < plan->n_images; ++i) {
         const DevShape& sh = shapes[plan->h_images[i].shape_id];
+        if (odd_image(i)) {
+            for (int y = 0; y < plan->h_images[i].h; y += band_rows_odd)
+                for (int st = 0; st < n_strips(plan->h_images[i].w); ++st)
+                    x2g_tiles.push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows_odd), st});
+            continue;
+        }
         if (sh.strip_rows <= 0) continue;
         if (march && march_image(i)) {
             for (int y = 0; y < plan->h_images[i].h; y += band_rows)
@@ -123,12 +145,14 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     }
     void* old[] = {plan->d_shapes, plan->d_tab, plan->d_lowres_tiles, plan->d_lowres_x2_tiles, plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles,
                    plan->d_lowres_x2_rest_tiles, plan->d_lowres_x2p_tiles[0], plan->d_lowres_x2p_tiles[1], plan->d_lowres_x2p_tiles[2],
-                   plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2]};
+                   plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2], plan->d_lowres_x2g_tiles};
     for (void* q : old)
         if (q) cudaFree(q);
     plan->d_shapes = nullptr; plan->d_tab = nullptr; plan->d_lowres_tiles = nullptr; plan->d_lowres_x2_tiles = nullptr;
     plan->d_lowres_x2w_tiles = nullptr; plan->d_lowres_x2w4_tiles = nullptr; plan->d_lowres_x2_rest_tiles = nullptr;
     int rc = upload(shapes, &plan->d_shapes);
+    plan->d_lowres_x2g_tiles = nullptr;
+    if (rc == ROD_OK) rc = upload(x2g_tiles, &plan->d_lowres_x2g_tiles);
     for (int u = 0; u < 3; ++u) {
         plan->d_lowres_x2p_tiles[u] = nullptr;
         if (rc == ROD_OK) rc = upload(x2p_tiles[u], &plan->d_lowres_x2p_tiles[u]);
@@ -146,6 +170,8 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     plan->n_lowres_x2_tiles = (int)x2_tiles.size();
     plan->n_lowres_x2w_tiles = (int)x2w_tiles.size();
     plan->n_lowres_x2w4_tiles = (int)x2w4_tiles.size();
+    plan->n_lowres_x2g_tiles = (int)x2g_tiles.size();
+    tile_starts(x2g_tiles, plan->n_images, plan->lowres_x2g_tile_start);
     for (int u = 0; u < 3; ++u) {
         plan->n_lowres_x2p_tiles[u] = (int)x2p_tiles[u].size();
         tile_starts(x2p_tiles[u], plan->n_images, plan->lowres_x2p_tile_start[u]);
@@ -349,7 +375,7 @@ extern "C" void rod_plan_destroy(rod_plan* plan) {
     void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles,
                     plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles, plan->d_lowres_x2_rest_tiles, plan->d_shapes,
                     plan->d_lowres_x2p_tiles[0], plan->d_lowres_x2p_tiles[1], plan->d_lowres_x2p_tiles[2],
-                    plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2],
+                    plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2], plan->d_lowres_x2g_tiles,
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
                     plan->d_f2d_taps, plan->d_f2d_tiles, plan->d_counters,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};

@@ -67,6 +67,8 @@ struct DevShape {
     int32_t x2w;                // 1: eligible for the warp-marching exact-2x kernel (lowres_x2w_kernel)
     int32_t x2p;                // 1: exact 2x in both axes, w % 4 == 0: the packed-integer kernel (lowres_x2p_kernel)
     uint32_t ly_rc2;            // float4 per output row {c0s, c1s, k0 + 2, bits of x2_vertical_cfix}: lowres_x2f_kernel
+    uint32_t ly_rc3;            // float4 per output row: x2g_row_consts (general horizontal stage): lowres_x2g_kernel
+    int32_t x2g;                // 1: odd width at factor 0.5 with the regular 3-tap / one-slip structure (lowres_x2g_kernel)
 };
 
 // ---------------------------------------------------------------------------------
@@ -722,6 +724,136 @@ ROD_HD void x2f_mac(const uint32_t s[12], float beta, bool first, float acc[12])
         const float prod = fmaf(bitsf(s[q]), beta, nb);
         acc[q] = first ? prod : fadd(acc[q], prod);
     }
+}
+
+// ---------------------------------------------------------------------------------
+// a4 + a5 for ODD widths at factor 0.5 (w = 2 nw + 1: lowres_x2g_kernel).  OpenCV's general INTER_AREA path then has,
+// for EVERY low-res column dx, exactly three x taps on source pixels 2dx, 2dx+1, 2dx+2 (weights from the table, all
+// different per column), and the INTER_LINEAR x axis has general 11-bit coefficients with ONE slip: output pixel
+// x = 2i+2 always blends low-res pixels (i, i+1); x = 2i+1 blends (i, i+1) left of the slip column and (i-1, i) from
+// it on.  A lane owns a chunk of 8 output pixels = low-res pixels P0..P3 = source pixels 0..8 of its 27-byte window.
+// ---------------------------------------------------------------------------------
+// One source row of the lane's window (7 aligned words = bytes 0..27) -> the horizontal INTER_AREA values of its twelve
+// low-res byte columns, hb[3p + c] = fl(fl(S[6p+c] a0 + S[6p+3+c] a1) + S[6p+6+c] a2) in OpenCV's operation order
+// (buf = 0; buf += S * alpha per tap: separate multiply and add).  al[3p + t] = weight of tap t of low-res pixel p.
+ROD_HD float byte_magic(const uint32_t* w, int i) {  // float 2^23 + (byte i of the window)
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w[i >> 2], 0x4B000000u, 0x7440 | (i & 3)));
+#else
+    return bitsf(0x4B000000u | ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu));
+#endif
+}
+ROD_HD void x2g_hrow(const uint32_t w[7], const float al[12], float hb[12]) {
+    float x[27];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 27; ++i) x[i] = byte_magic(w, i);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int p = 0; p < 4; ++p) {
+        // fma(2^23 + S, a, -2^23 a) == fl(S a) exactly (2^23 a is exact, one rounding)
+        const float n0 = fmul(al[3 * p], -8388608.0f), n1 = fmul(al[3 * p + 1], -8388608.0f), n2 = fmul(al[3 * p + 2], -8388608.0f);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int c = 0; c < 3; ++c) {
+            const float t0 = fmaf(x[6 * p + c], al[3 * p], n0);
+            const float t1 = fmaf(x[6 * p + 3 + c], al[3 * p + 1], n1);
+            const float t2 = fmaf(x[6 * p + 6 + c], al[3 * p + 2], n2);
+            hb[3 * p + c] = fadd(fadd(t0, t1), t2);
+        }
+    }
+}
+// vertical INTER_AREA tap on those values: first tap sum = beta * buf, later taps sum = sum + beta * buf
+ROD_HD void x2g_vmac(const float hb[12], float beta, bool first, float acc[12]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 12; ++q) {
+        const float prod = fmul(beta, hb[q]);
+        acc[q] = first ? prod : fadd(acc[q], prod);
+    }
+}
+// saturate_cast<uchar>(rint(sum)) of the twelve sums -> the lane's 12 low-res bytes in three words.  (The weights are
+// positive and sum to 1 +- 1e-6, so the sum lies in [0, 255.001]: the magic-number rint needs no clamp.)
+ROD_HD void x2g_round12(const float acc[12], uint32_t own[3]) {
+    uint32_t b[12];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 12; ++q) b[q] = fbits(fadd(acc[q], 12582912.0f));  // result in the low byte
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 3; ++k)
+        own[k] = perm<0x5410>(perm<0x0040>(b[4 * k], b[4 * k + 1]), perm<0x0040>(b[4 * k + 2], b[4 * k + 3]));
+}
+// A chunk at the right image border with fewer than four valid low-res pixels: the missing ones replicate the last
+// valid pixel (OpenCV clamps the second x tap to nw - 1).  valid = 0..3; for valid == 0 all four become the left
+// neighbour's last pixel, passed in bytes 1..3 of `left_px`.
+ROD_HD void x2g_replicate(uint32_t own[3], int valid, uint32_t left_px) {
+    if (valid >= 4) return;
+    if (valid <= 1) {
+        const uint32_t p = valid == 0 ? (left_px >> 8) : own[0];   // the pixel in bytes 0..2
+        own[0] = perm<0x0210>(p, p);
+        own[1] = perm<0x1021>(p, p);
+        own[2] = perm<0x2102>(p, p);
+    } else if (valid == 2) {                                      // pixel 1 = bytes 3..5
+        const uint32_t o1 = own[1];
+        own[1] = perm<0x4354>(own[0], o1);
+        own[2] = perm<0x5435>(own[0], o1);
+    } else {                                                      // pixel 2 = bytes 6..8
+        own[2] = perm<0x4324>(own[1], own[2]);
+    }
+}
+// Horizontal INTER_LINEAR stage of one low-res row for the chunk: win[] = the 18 bytes of P[-1..4] (as in x2_expand24),
+// coef[x] = a0 | a1 << 16 of output pixel x, slip bit x>>1 of `slip` set = odd pixel x blends (P[k-1], P[k]) instead of
+// (P[k], P[k+1]), k = x >> 1.  x[t] = float 2^23 + ((L a0 + R a1) >> 4) for output byte t = 3 * pixel + channel.
+ROD_HD void x2g_expand24(const uint32_t win[5], const uint32_t coef[8], uint32_t slip, float x[24]) {
+    const uint32_t M = 0x4B000000u;
+    uint32_t g01[5], g2x[5];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m = 0; m < 5; ++m) { g01[m] = x2_gather(win, 3 * m); g2x[m] = x2_gather(win, 3 * m + 2); }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int px = 0; px < 8; ++px) {
+        const int k = px >> 1;
+        uint32_t a = g01[k], b = g2x[k];               // even pixels, and slipped odd pixels: pair k = (P[k-1], P[k])
+        if (px & 1) {
+            const bool sl = (slip >> k) & 1u;
+            a = sl ? g01[k] : g01[k + 1];
+            b = sl ? g2x[k] : g2x[k + 1];
+        }
+        const uint32_t h0 = dot2_lo(coef[px], a, M), h1 = dot2_hi(coef[px], a, M), h2 = dot2_lo(coef[px], b, M);
+        // 2^23 + H -> 2^23 + (H >> 4): one multiply-add rounded toward zero
+#if defined(__CUDA_ARCH__)
+        x[3 * px + 0] = __fmaf_rz(bitsf(h0), 0.0625f, 7864320.0f);
+        x[3 * px + 1] = __fmaf_rz(bitsf(h1), 0.0625f, 7864320.0f);
+        x[3 * px + 2] = __fmaf_rz(bitsf(h2), 0.0625f, 7864320.0f);
+#else
+        x[3 * px + 0] = (float)(8388608.0 + (double)((h0 - M) >> 4));
+        x[3 * px + 1] = (float)(8388608.0 + (double)((h1 - M) >> 4));
+        x[3 * px + 2] = (float)(8388608.0 + (double)((h2 - M) >> 4));
+#endif
+    }
+}
+// Vertical-stage constants for x = 2^23 + hx (general horizontal stage): x2_vertical(x0, x1, r) then gives
+// (((b0 * hx0) >> 16) + ((b1 * hx1) >> 16) + 2) >> 2 in its low byte:
+//   y1 = x0 * b0/65536 + (2^23 - 128 b0) = 2^23 + F0;  y2 = x1 * b1/65536 + y1 = 2^23 + 128 b1 + F0 + F1 (< 2^24);
+//   o = y2 / 4 + (2^23 - 2^21 - 32 b1 + 0.5) = 2^23 + ((F0 + F1 + 2) >> 2), every step rounded toward zero.
+ROD_HD X2Row x2g_row_consts(uint32_t b_packed) {
+    X2Row r;
+    const float b0 = (float)(b_packed & 0xFFFFu), b1 = (float)(b_packed >> 16);
+    r.c0s = b0 * 1.52587890625e-05f;
+    r.c1s = b1 * 1.52587890625e-05f;
+    r.k0 = 8388608.0f - b0 * 128.0f;
+    r.k2 = 6291456.5f - b1 * 32.0f;
+    return r;
 }
 
 // Detector-input normalisation: half(float(u8) / 255.f) is done with __float2half_rn on

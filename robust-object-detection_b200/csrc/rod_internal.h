@@ -79,6 +79,10 @@ struct rod_plan {
     rod::Tile* d_lowres_x2f_tiles[3] = {nullptr, nullptr, nullptr};
     int n_lowres_x2f_tiles[3] = {0, 0, 0};
     std::vector<int> lowres_x2f_tile_start[3];
+    // odd widths at factor 0.5: lowres_x2g_kernel (any byte alignment), same band x strip tiles
+    rod::Tile* d_lowres_x2g_tiles = nullptr;
+    int n_lowres_x2g_tiles = 0;
+    std::vector<int> lowres_x2g_tile_start;
     int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
     std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
     int lowres_x2w_band_rows = 0;

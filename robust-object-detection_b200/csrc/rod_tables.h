@@ -156,6 +156,27 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
         sh.lx_a = blob_push(blob, lx.coef);
         sh.ly_s = blob_push(blob, ys);
         sh.ly_b = blob_push(blob, ly.coef);
+        // odd widths at factor 0.5 (lowres_x2g_kernel): every low-res column has the three x taps 2dx, 2dx+1, 2dx+2; even
+        // output pixels x blend low-res (x/2 - 1, x/2), odd ones ((x-1)/2, +1) or, from the slip column on, ((x-1)/2 - 1, +1)
+        if (sh.area_mode == AREA_GENERAL && sh.ay_packed && sh.xt == 3 && w == 2 * sh.nw + 1 && sh.nw >= 1 && h >= 2) {
+            const int32_t* xf = (const int32_t*)(blob.data() + sh.ax_first);
+            const int32_t* xc = (const int32_t*)(blob.data() + sh.ax_count);
+            bool ok = true;
+            for (int dx = 0; dx < sh.nw && ok; ++dx) ok = (xf[dx] == 2 * dx && xc[dx] == 3);
+            for (int x = 0; x < w && ok; ++x) {
+                const int i = (x & 1) ? (x - 1) / 2 : x / 2 - 1;
+                ok = (x & 1) ? (lx.s0[x] == i || (i >= 1 && lx.s0[x] == i - 1)) : (lx.s0[x] == std::max(i, 0));
+            }
+            if (ok) {
+                std::vector<float> rc3((size_t)h * 4);
+                for (int y = 0; y < h; ++y) {
+                    const X2Row r = x2g_row_consts(ly.coef[y]);
+                    rc3[4 * y] = r.c0s; rc3[4 * y + 1] = r.c1s; rc3[4 * y + 2] = r.k0; rc3[4 * y + 3] = r.k2;
+                }
+                sh.ly_rc3 = blob_push(blob, rc3);
+                sh.x2g = 1;
+            }
+        }
         if (sh.x2) {  // vertical-stage constants of the exact-2x kernels, one float4 per output row
             std::vector<float> rc((size_t)h * 4);
             for (int y = 0; y < h; ++y) {

@@ -281,6 +281,39 @@ def test_emu_lowres_float_staged_kernel(emu, band_rows):
     assert n_run >= 6
 
 
+X2G_SHAPES = [(765, 1361), (360, 481), (100, 9), (9, 5), (2, 3), (5, 13), (64, 65), (65, 129), (131, 37), (201, 1401), (97, 1917),
+              (540, 961), (33, 1999), (40, 21), (77, 1363), (50, 241), (51, 243), (52, 247), (8, 7), (3, 11), (10, 15), (64, 17)]
+
+
+@pytest.mark.parametrize("band_rows", [24, 56, 512])
+def test_emu_lowres_odd_width_kernel(emu, band_rows):
+    """lowres_x2g_kernel's arithmetic (odd widths at factor 0.5: three-tap float INTER_AREA x pass, carried tap row,
+    border replication for chunks with 0..3 valid low-res pixels, coefficient + slip driven INTER_LINEAR x stage, general
+    y stage) replayed lane by lane on the CPU against the oracle; odd and even heights, uniform and binary content."""
+    emu.emu_lowres_x2g.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_long, ctypes.c_long, ctypes.c_int]
+    n_run = 0
+    for i, (h, w) in enumerate(X2G_SHAPES):
+        if band_rows != 56 and h * w > 300000:
+            continue
+        img = synth(1100 + i, h, w)
+        if i % 4 == 1:
+            img = (img > 127).astype(np.uint8) * 255
+        want = orc.apply_lowres(img, 0.5)
+        pitch = 3 * w + (0 if i % 3 else 7)
+        buf = np.full((h, pitch), 0xAB, np.uint8)
+        buf[:, :3 * w] = img.reshape(h, 3 * w)
+        got = np.zeros_like(img)
+        rc = emu.emu_lowres_x2g(_p(buf), _p(got), h, w, pitch, 3 * w, band_rows)
+        if rc == 3 and min(h, w) <= 3:
+            continue                      # integer-scale corner cases (resizeAreaFast_) are not this kernel's
+        assert rc == 0, (h, w, rc)
+        assert np.array_equal(got, want), (h, w, band_rows, int((got != want).sum()))
+        n_run += 1
+    assert n_run >= (19 if band_rows == 56 else 14)
+    assert emu.emu_lowres_x2g(_p(buf), _p(got), 64, 64, 192, 192, 56) == 3      # even width: not this kernel's
+
+
 X2P_SHAPES = [(360, 480), (100, 8), (2, 4), (4, 4), (64, 64), (130, 36), (200, 1400), (96, 1916), (540, 960), (34, 2000), (40, 20),
               (76, 1364), (50, 240), (52, 244), (52, 248), (1078, 1916), (1050, 1400)]
 

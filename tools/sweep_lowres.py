@@ -29,17 +29,15 @@ def rate(fn, nbytes, steps=8, warmup=3):
 
 
 def workloads():
-    yield "1360x765_x256", [(765, 1360)] * 256
-    yield "1400x787_x128", [(787, 1400)] * 128
-    yield "1916x1079_x128", [(1079, 1916)] * 128
+    yield "1361x765_x128", [(765, 1361)] * 128
+    yield "1999x1499_x48", [(1499, 1999)] * 48
+    yield "1917x1080_x64", [(1080, 1917)] * 64
     rng = np.random.default_rng(3000)
     yield "mixed_256", [POOL[i] for i in rng.integers(0, len(POOL), 256)]
-    rng = np.random.default_rng(4000)
-    yield "visdrone_1610", [POOL[i] for i in rng.integers(0, 8, 1610)]
     yield "odd_only_96", [POOL[8 + i % 3] for i in range(96)]
 
 
-settings = [("f4", {"ROD_X2F_CTAS": "4"}), ("f3", {"ROD_X2F_CTAS": "3"})]
+settings = [("g_off", {"ROD_X2_ODD_STAGED": "0"}), ("g3", {"ROD_X2G_CTAS": "3"}), ("g4", {"ROD_X2G_CTAS": "4"}), ("g2", {"ROD_X2G_CTAS": "2"})]
 extra = [kv.split("=") for kv in sys.argv[1:] if "=" in kv]
 if extra:
     settings = [("custom", dict(extra))]
@@ -47,7 +45,7 @@ out = {}
 for wname, shapes in workloads():
     src = dst = None
     for sname, env in settings:
-        for k in ("ROD_X2_PACKED", "ROD_X2P_CTAS", "ROD_X2_FLOAT_STAGED", "ROD_X2F_CTAS"):
+        for k in ("ROD_X2_PACKED", "ROD_X2P_CTAS", "ROD_X2_FLOAT_STAGED", "ROD_X2F_CTAS", "ROD_X2_ODD_STAGED", "ROD_X2G_CTAS"):
             os.environ.pop(k, None)
         os.environ.update(env)
         plan = CorruptionPlan.ragged(shapes)
