@@ -124,7 +124,9 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         long long strip_rows = 0;
         for (int i = 0; i < plan->n_images; ++i)
             if (odd_image(i)) strip_rows += (long long)plan->h_images[i].h * n_strips(plan->h_images[i].w);
-        band_rows_odd = std::max(24, std::min(256, (int)(strip_rows / (60LL * plan->sm_count)) & ~7));
+        const char* e_band = getenv("ROD_X2G_BAND_DIV");  // tiles per SM the band height aims at (benchmark knob)
+        const long long div = e_band && atoi(e_band) >= 4 ? atoi(e_band) : 60;
+        band_rows_odd = std::max(24, std::min(256, (int)(strip_rows / (div * plan->sm_count)) & ~7));
     }
     for (int i = 0; i < plan->n_images; ++i) {
         const DevShape& sh = shapes[plan->h_images[i].shape_id];

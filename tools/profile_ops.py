@@ -29,6 +29,13 @@ if "lowres1080" in which:   # even x even shape: the packed-integer kernel
     for _ in range(3):
         p2.lowres(s2, d2)
     del s2, d2
+if "lowresodd" in which:   # odd width: the staged odd-width kernel
+    p3 = CorruptionPlan.uniform(48, 1079, 1917)
+    s3 = torch.randint(0, 256, (48, 1079, 1917, 3), dtype=torch.uint8, device="cuda")
+    d3 = torch.empty_like(s3)
+    for _ in range(3):
+        p3.lowres(s3, d3)
+    del s3, d3
 if "letterbox" in which:
     import random
     random.seed(42)

@@ -37,7 +37,7 @@ def workloads():
     yield "odd_only_96", [POOL[8 + i % 3] for i in range(96)]
 
 
-settings = [("g_off", {"ROD_X2_ODD_STAGED": "0"}), ("g3", {"ROD_X2G_CTAS": "3"}), ("g4", {"ROD_X2G_CTAS": "4"}), ("g2", {"ROD_X2G_CTAS": "2"})]
+settings = [("g3", {"ROD_X2G_CTAS": "3"}), ("g4", {"ROD_X2G_CTAS": "4"}), ("g3_b30", {"ROD_X2G_CTAS": "3", "ROD_X2G_BAND_DIV": "30"}), ("g3_b120", {"ROD_X2G_CTAS": "3", "ROD_X2G_BAND_DIV": "120"})]
 extra = [kv.split("=") for kv in sys.argv[1:] if "=" in kv]
 if extra:
     settings = [("custom", dict(extra))]
@@ -45,7 +45,7 @@ out = {}
 for wname, shapes in workloads():
     src = dst = None
     for sname, env in settings:
-        for k in ("ROD_X2_PACKED", "ROD_X2P_CTAS", "ROD_X2_FLOAT_STAGED", "ROD_X2F_CTAS", "ROD_X2_ODD_STAGED", "ROD_X2G_CTAS"):
+        for k in ("ROD_X2_PACKED", "ROD_X2P_CTAS", "ROD_X2_FLOAT_STAGED", "ROD_X2F_CTAS", "ROD_X2_ODD_STAGED", "ROD_X2G_CTAS", "ROD_X2G_BAND_DIV"):
             os.environ.pop(k, None)
         os.environ.update(env)
         plan = CorruptionPlan.ragged(shapes)
