@@ -1054,6 +1054,208 @@ __global__ void __launch_bounds__(128, MINB) lowres_x2f_kernel(LowresX2wParams p
 }
 
 // =====================================================================================
+// Regular three-tap kernel for exact-2x widths with h = 2 nh + 1 (DevShape::x2h: low-res row j reads source rows 2j, 2j+1,
+// 2j+2 -- 1360 x 765, the BASELINE frame size).  Same arithmetic, strips, bands, halo lanes and coalesced staging as
+// lowres_x2f_kernel, but the control flow is static so that the instruction stream is (almost) only arithmetic:
+//   * the loop runs over LOW-RES rows, unrolled by parity (the even row's horizontal stage lives in xe, the odd row's in
+//     xo: no register moves, no parity dispatch); a per-low-res-row table entry {beta0, beta1, beta2, first output row, nA,
+//     nB} says which output rows leave once the row exists;
+//   * source rows are staged as fixed pairs (2j+1, 2j+2) in a ring of four stages, one commit group per stage and one
+//     __syncwarp per low-res row; row 2j is the previous stage's second row, whose pair sums are carried in registers;
+//   * the per-output-row constants run two rows ahead in registers.
+// (lowres_x2f_kernel spends 40 % of its instructions on ring / row bookkeeping: 317 warp instructions per output row of a
+// strip where the arithmetic needs ~190.)
+// =====================================================================================
+constexpr int kX2hStages = 4;
+struct alignas(16) X2hWarpSmem {
+    uint8_t in[kX2hStages][2][kX2pRowBytes];
+    uint8_t out[2][kX2pOutBytes];
+};
+
+template <int U>
+struct X2hState {
+    // staging
+    uint32_t in_s;            // shared address of this lane's copy unit 0 in stage 0, row 0
+    const uint8_t* gnext;     // this lane's unit 0 of the next source row to stage
+    int64_t sp, dp;
+    int in_units, out_units;
+    int next_stage, n_stages;
+    // reading
+    const uint8_t* in0;       // this lane's chunk in stage 0, row 0
+    // emission
+    uint8_t* grow;            // this lane's copy unit 0 of the next output row
+    uint8_t* ob0; uint8_t* ob1;
+    int ooff;
+    const float4* rc_tab;
+    float4 rcA, rcB;          // constants of output rows r and r + 1
+    int r, H;
+    int lane;
+};
+
+template <int U>
+__device__ __forceinline__ void x2h_issue(X2hState<U>& s) {   // stage `next_stage`: source rows 2 jj + 1, 2 jj + 2
+    if (s.next_stage < s.n_stages) {
+        const uint32_t slot = s.in_s + (uint32_t)((s.next_stage & (kX2hStages - 1)) * (2 * kX2pRowBytes));
+        x2p_copy_in<U>(slot, s.gnext, s.lane, s.in_units);
+        x2p_copy_in<U>(slot + kX2pRowBytes, s.gnext + s.sp, s.lane, s.in_units);
+        s.gnext += 2 * s.sp;
+    }
+    cp_async_commit();
+    ++s.next_stage;
+}
+
+template <int U>
+__device__ __forceinline__ void x2h_emit_row(X2hState<U>& s, const float* xlo, const float* xhi) {
+    const float4 rf = s.rcA;
+    s.rcA = s.rcB;
+    s.rcB = __ldg(s.rc_tab + min(s.r + 2, s.H - 1));
+    x2f_store_row<U>(s.ob0, s.ooff, xlo, xhi, rf.x, rf.y, rf.z, __float_as_uint(rf.w), s.grow, s.lane, s.out_units);
+    uint8_t* tswap = s.ob0; s.ob0 = s.ob1; s.ob1 = tswap;
+    s.grow += s.dp;
+    ++s.r;
+}
+
+// low-res row j: stage index st = j - j_first + 1.  xnew receives its horizontal stage, xprev holds row j - 1's.
+template <int U>
+__device__ __forceinline__ void x2h_row(X2hState<U>& s, const X2pLane& c, int st, uint4& hp_next, const uint4* hp_fetch,
+                                        uint32_t carry[12], float* xnew, const float* xprev, int Y0, int Y1) {
+    cp_async_wait<kX2hStages - 2>();   // this lane's copies of stage st have landed ...
+    __syncwarp();                      // ... and everybody else's; all lanes are done with the stage before it
+    uint32_t ra[6], rb[6];
+    {
+        const uint8_t* sl = s.in0 + (st & (kX2hStages - 1)) * (2 * kX2pRowBytes);
+        const uint2* pa = reinterpret_cast<const uint2*>(sl);
+        const uint2* pb = reinterpret_cast<const uint2*>(sl + kX2pRowBytes);
+        const uint2 a0 = pa[0], a1 = pa[1], a2 = pa[2], b0 = pb[0], b1 = pb[1], b2 = pb[2];
+        ra[0] = a0.x; ra[1] = a0.y; ra[2] = a1.x; ra[3] = a1.y; ra[4] = a2.x; ra[5] = a2.y;
+        rb[0] = b0.x; rb[1] = b0.y; rb[2] = b1.x; rb[3] = b1.y; rb[4] = b2.x; rb[5] = b2.y;
+    }
+    x2h_issue<U>(s);                   // refills the slot that was read one row ago
+    const uint4 hp = hp_next;
+    hp_next = __ldg(hp_fetch);
+    float acc[12];
+    x2f_mac(carry, __uint_as_float(hp.x), true, acc);
+    {
+        uint32_t sa[12];
+        x2f_pairsums(ra, sa);
+        x2f_mac(sa, __uint_as_float(hp.y), false, acc);
+    }
+    x2f_pairsums(rb, carry);           // source row 2j + 2: also the first tap row of low-res row j + 1
+    x2f_mac(carry, __uint_as_float(hp.z), false, acc);
+    uint32_t o6[2][6];
+    area_x2f_finish(acc, o6[0]);
+    area_x2f_finish(acc + 6, o6[1]);
+    uint32_t own[3];
+    {
+        const uint32_t a01 = __byte_perm(o6[0][0], o6[0][1], 0x0040), a23 = __byte_perm(o6[0][2], o6[0][3], 0x0040);
+        const uint32_t a45 = __byte_perm(o6[0][4], o6[0][5], 0x0040);
+        const uint32_t c01 = __byte_perm(o6[1][0], o6[1][1], 0x0040), c23 = __byte_perm(o6[1][2], o6[1][3], 0x0040);
+        const uint32_t c45 = __byte_perm(o6[1][4], o6[1][5], 0x0040);
+        own[0] = __byte_perm(a01, a23, 0x5410);
+        own[1] = __byte_perm(a45, c01, 0x5410);
+        own[2] = __byte_perm(c23, c45, 0x5410);
+        if (!c.second) {  // two-pixel last chunk: pixel 2 := pixel 1 (OpenCV's clamped right tap P[nw] = P[nw-1])
+            own[2] = __byte_perm(own[1], 0u, 0x4441);
+            own[1] = __byte_perm(own[0], own[1], 0x4354);
+        }
+    }
+    x2f_expand(c, own, xnew);
+    // output rows whose lower tap row is j: [r0, r0 + nA) blend (j - 1, j), [r0 + nA, r0 + nA + nB) blend (j, j)
+    const int r0 = (int)(hp.w & 0xFFFFu), ra_end = r0 + (int)((hp.w >> 16) & 0xFFu), rb_end = ra_end + (int)(hp.w >> 24);
+    const int a_end = min(ra_end, Y1), b_end = min(rb_end, Y1);
+#pragma unroll 1
+    while (s.r < a_end) x2h_emit_row<U>(s, xprev, xnew);    // (s.r >= max(r0, Y0) by construction)
+#pragma unroll 1
+    while (s.r < b_end) x2h_emit_row<U>(s, xnew, xnew);
+}
+
+template <int U>
+__device__ __forceinline__ void x2h_tile(const LowresX2wParams& p, const Tile& t, const DevImage& im, const DevShape& sh,
+                                         X2hWarpSmem& ws, int lane) {
+    constexpr bool M16 = (U == 16);
+    const uint8_t* simg = p.src + im.src_off;
+    uint8_t* dimg = p.dst + im.dst_off;
+    const int n = 3 * im.w, nw = sh.nw, H = im.h;
+    const int nchunks = (im.w + 7) >> 3;
+    const int c0 = kX2wChunksPerStrip * t.c;
+    const int ch = c0 - 1 + lane;
+    const int cc = min(max(ch, 0), nchunks - 1);
+    const int cs = max(c0 - (M16 ? 2 : 1), 0), ce = min(c0 + kX2wChunksPerStrip, nchunks - 1);
+    X2pLane c;
+    c.soff = 24 * (cc - cs);
+    c.second = (nw - 4 * cc) >= 4;
+    c.first = (cc == 0);
+    c.last = (cc == nchunks - 1);
+    const bool stores = ch >= 0 && ch < nchunks && lane >= 1 && lane <= kX2wChunksPerStrip;
+    const uint32_t* ly_s = p.tab + sh.ly_s;
+    const uint4* hyp = reinterpret_cast<const uint4*>(p.tab + sh.hy_pack);
+    const int Y0 = t.a, Y1 = t.b;
+    const int j_first = (int)(__ldg(ly_s + Y0) & 0xFFFFu), j_last = (int)(__ldg(ly_s + Y1 - 1) >> 16);
+
+    X2hState<U> s;
+    s.lane = lane;
+    s.in_s = (uint32_t)__cvta_generic_to_shared(&ws.in[0][0][0]) + U * lane;
+    s.sp = im.src_pitch; s.dp = im.dst_pitch;
+    s.in_units = (min(24 * (ce + 1), n) - 24 * cs + U - 1) / U;
+    s.out_units = (min(24 * (c0 + kX2wChunksPerStrip), n) - 24 * c0) / U;
+    s.in0 = &ws.in[0][0][c.soff];
+    s.ooff = stores ? 24 * (lane - 1) : -1;
+    s.ob0 = ws.out[0]; s.ob1 = ws.out[1];
+    s.grow = dimg + 24 * c0 + U * lane + (int64_t)Y0 * s.dp;
+    s.rc_tab = reinterpret_cast<const float4*>(p.tab + sh.ly_rc2);
+    s.r = Y0; s.H = H;
+    s.rcA = __ldg(s.rc_tab + Y0);
+    s.rcB = __ldg(s.rc_tab + min(Y0 + 1, H - 1));
+    // stage 0 holds source row 2 j_first alone (in its second row slot); stage st >= 1 rows 2 j + 1, 2 j + 2, j = j_first + st - 1
+    s.n_stages = j_last - j_first + 2;
+    s.gnext = simg + 24 * cs + U * lane + (int64_t)(2 * j_first) * s.sp;
+    __syncwarp();  // the previous tile's reads of the ring are done
+    x2p_copy_in<U>(s.in_s + kX2pRowBytes, s.gnext, lane, s.in_units);
+    s.gnext += s.sp;
+    cp_async_commit();
+    s.next_stage = 1;
+#pragma unroll
+    for (int q = 1; q < kX2hStages - 1; ++q) x2h_issue<U>(s);
+    uint4 hp_next = __ldg(hyp + j_first);
+
+    float xe[24], xo[24];
+    uint32_t carry[12];
+    {   // stage 0: the pair sums of source row 2 j_first
+        cp_async_wait<kX2hStages - 2>();
+        __syncwarp();
+        const uint2* pb = reinterpret_cast<const uint2*>(s.in0 + kX2pRowBytes);
+        const uint2 b0 = pb[0], b1 = pb[1], b2 = pb[2];
+        const uint32_t rb[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+        x2h_issue<U>(s);
+        x2f_pairsums(rb, carry);
+    }
+#pragma unroll 1
+    for (int jj = j_first & ~1; jj <= j_last; jj += 2) {
+        if (jj >= j_first) x2h_row<U>(s, c, jj - j_first + 1, hp_next, hyp + min(jj + 1, j_last), carry, xe, xo, Y0, Y1);
+        if (jj + 1 <= j_last) x2h_row<U>(s, c, jj - j_first + 2, hp_next, hyp + min(jj + 2, j_last), carry, xo, xe, Y0, Y1);
+    }
+    cp_async_wait<0>();
+}
+
+template <int U, int MINB>
+__global__ void __launch_bounds__(128, MINB) lowres_x2h_kernel(LowresX2wParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    X2hWarpSmem& ws = reinterpret_cast<X2hWarpSmem*>(smem)[threadIdx.x >> 5];
+    for (;;) {
+        int ti = 0;
+        if (lane == 0) ti = (int)atomicAdd(p.counter, 1u);
+        ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+        if (ti >= p.n_tiles) break;
+        const Tile t = p.tiles[ti];
+        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
+        const DevImage im = p.images[t.img];
+        const DevShape sh = p.shapes[im.shape_id];
+        x2h_tile<U>(p, t, im, sh, ws, lane);
+    }
+}
+
+// =====================================================================================
 // Odd-width kernel (w = 2 nw + 1 at factor 0.5; any height; rows at ANY byte alignment -- 3 w is odd, so consecutive rows
 // of a contiguous image cycle through all four 4-byte phases).  Same strips, bands, halo lanes, source-row ring and carried
 // tap row as lowres_x2f_kernel; what differs (rod_core.h x2g_*):
@@ -1331,20 +1533,21 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
     }
     // exact-2x shapes: warp-marching kernel when the rows are 4-byte aligned, full-width strips otherwise
     const int n_packed = plan->n_lowres_x2p_tiles[0] + plan->n_lowres_x2p_tiles[1] + plan->n_lowres_x2p_tiles[2] +
-                         plan->n_lowres_x2f_tiles[0] + plan->n_lowres_x2f_tiles[1] + plan->n_lowres_x2f_tiles[2];
+                         plan->n_lowres_x2f_tiles[0] + plan->n_lowres_x2f_tiles[1] + plan->n_lowres_x2f_tiles[2] +
+                         plan->n_lowres_x2h_tiles[0] + plan->n_lowres_x2h_tiles[1] + plan->n_lowres_x2h_tiles[2];
     const bool use_bands = (plan->n_lowres_x2w_tiles + plan->n_lowres_x2w4_tiles + n_packed) > 0 &&
                            (((uintptr_t)src) & 3) == 0 && (n_packed == 0 || (((uintptr_t)dst) & 3) == 0);
     // staged kernels (packed-integer: exact 2x in both axes; float taps: exact-2x width only), one launch per copy-unit class
-    for (int kind = 0; kind < 2 && use_bands; ++kind) {
+    for (int kind = 0; kind < 3 && use_bands; ++kind) {   // 0: packed-integer, 1: float taps, 2: regular three-tap
         for (int u = 0; u < 3; ++u) {
-            const int n_list = kind == 0 ? plan->n_lowres_x2p_tiles[u] : plan->n_lowres_x2f_tiles[u];
+            const int n_list = kind == 0 ? plan->n_lowres_x2p_tiles[u] : kind == 1 ? plan->n_lowres_x2f_tiles[u] : plan->n_lowres_x2h_tiles[u];
             if (n_list == 0) continue;
-            const std::vector<int>& st = kind == 0 ? plan->lowres_x2p_tile_start[u] : plan->lowres_x2f_tile_start[u];
+            const std::vector<int>& st = kind == 0 ? plan->lowres_x2p_tile_start[u] : kind == 1 ? plan->lowres_x2f_tile_start[u] : plan->lowres_x2h_tile_start[u];
             const int t_lo = st[img_lo], t_hi = st[img_hi];
             if (t_hi <= t_lo) continue;
             LowresX2wParams p;
             p.images = plan->d_images;
-            p.tiles = (kind == 0 ? plan->d_lowres_x2p_tiles[u] : plan->d_lowres_x2f_tiles[u]) + t_lo;
+            p.tiles = (kind == 0 ? plan->d_lowres_x2p_tiles[u] : kind == 1 ? plan->d_lowres_x2f_tiles[u] : plan->d_lowres_x2h_tiles[u]) + t_lo;
             p.n_tiles = t_hi - t_lo;
             p.shapes = plan->d_shapes;
             p.tab = plan->d_tab;
@@ -1354,12 +1557,12 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             const int ctas = (p.n_tiles + 3) / 4;
             // measured on a B200 (128 x 1920x1080, packed): 3 CTAs/SM 5.88 TB/s, 4: 5.79, 2: 5.17; knobs ROD_X2P_CTAS / ROD_X2F_CTAS
             int per_sm = kind == 0 ? 3 : 4;  // the float-tap kernel is issue-bound: more warps win (4: 3.69, 3: 3.34, 2: 2.74 TB/s)
-            const char* e_ctas = getenv(kind == 0 ? "ROD_X2P_CTAS" : "ROD_X2F_CTAS");
+            const char* e_ctas = getenv(kind == 0 ? "ROD_X2P_CTAS" : kind == 1 ? "ROD_X2F_CTAS" : "ROD_X2H_CTAS");
             if (e_ctas && atoi(e_ctas) >= 2 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
             // the list's copy unit holds for offsets and pitches; the base pointers may be less aligned
             const uintptr_t base = (uintptr_t)src | (uintptr_t)dst;
             const int unit = std::min(u == 0 ? 16 : (u == 1 ? 8 : 4), (base & 15) == 0 ? 16 : ((base & 7) == 0 ? 8 : 4));
-            const size_t smem = 4 * (kind == 0 ? sizeof(X2pWarpSmem) : sizeof(X2fWarpSmem));
+            const size_t smem = 4 * (kind == 0 ? sizeof(X2pWarpSmem) : kind == 1 ? sizeof(X2fWarpSmem) : sizeof(X2hWarpSmem));
 #define ROD_STAGED_LAUNCH(K, U, B)                                                                         \
     do {                                                                                                   \
         ROD_CUDA(cudaFuncSetAttribute(K<U, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
@@ -1378,7 +1581,8 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
         else ROD_STAGED_LAUNCH_B(K, 4);                           \
     } while (0)
             if (kind == 0) ROD_STAGED_LAUNCH_U(lowres_x2p_kernel);
-            else ROD_STAGED_LAUNCH_U(lowres_x2f_kernel);
+            else if (kind == 1) ROD_STAGED_LAUNCH_U(lowres_x2f_kernel);
+            else ROD_STAGED_LAUNCH_U(lowres_x2h_kernel);
 #undef ROD_STAGED_LAUNCH_U
 #undef ROD_STAGED_LAUNCH_B
 #undef ROD_STAGED_LAUNCH

@@ -107,6 +107,9 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         return x2f_on && sh.x2w != 0 && sh.area_mode == AREA_GENERAL && sh.ay_packed && (im.dst_pitch & 3) == 0 &&
                (im.dst_off & 3) == 0 && (sh.h <= 8 || 4LL * sh.h <= 9LL * sh.nh);
     };
+    const char* e_x2h = getenv("ROD_X2_REGULAR");
+    const bool x2h_on = !(e_x2h && atoi(e_x2h) == 0);
+    auto regular_image = [&](int i) { return x2h_on && float_image(i) && shapes[plan->h_images[i].shape_id].x2h != 0; };
     // odd-width staged kernel: regular 3-tap / one-slip shapes whose y scale fits the ring of 8 source rows
     const char* e_x2g = getenv("ROD_X2_ODD_STAGED");
     const bool x2g_on = !(e_x2g && atoi(e_x2g) == 0);
@@ -114,7 +117,7 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         const DevShape& sh = shapes[plan->h_images[i].shape_id];
         return x2g_on && sh.x2g != 0 && (sh.h <= 8 || 4LL * sh.h <= 9LL * sh.nh);
     };
-    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles, x2p_tiles[3], x2f_tiles[3], x2g_tiles, gen_all;
+    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles, x2p_tiles[3], x2f_tiles[3], x2h_tiles[3], x2g_tiles, gen_all;
     build_strip_tiles(plan->h_images, shapes, false, kLowresTH, kLowresTWB, gen_all);
     for (const Tile& t : gen_all)
         if (!odd_image(t.img)) gen_tiles.push_back(t);
@@ -140,14 +143,15 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         if (march && march_image(i)) {
             for (int y = 0; y < plan->h_images[i].h; y += band_rows)
                 for (int st = 0; st < n_strips(plan->h_images[i].w); ++st)
-                    (packed_image(i) ? x2p_tiles[packed_class(i)] : float_image(i) ? x2f_tiles[packed_class(i)] : al8_image(i) ? x2w_tiles : x2w4_tiles).push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows), st});
+                    (packed_image(i) ? x2p_tiles[packed_class(i)] : regular_image(i) ? x2h_tiles[packed_class(i)] : float_image(i) ? x2f_tiles[packed_class(i)] : al8_image(i) ? x2w_tiles : x2w4_tiles).push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows), st});
         } else {
             for (int y = 0; y < plan->h_images[i].h; y += sh.strip_rows) x2_rest_tiles.push_back(Tile{i, y, 0, 0});
         }
     }
     void* old[] = {plan->d_shapes, plan->d_tab, plan->d_lowres_tiles, plan->d_lowres_x2_tiles, plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles,
                    plan->d_lowres_x2_rest_tiles, plan->d_lowres_x2p_tiles[0], plan->d_lowres_x2p_tiles[1], plan->d_lowres_x2p_tiles[2],
-                   plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2], plan->d_lowres_x2g_tiles};
+                   plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2], plan->d_lowres_x2g_tiles,
+                   plan->d_lowres_x2h_tiles[0], plan->d_lowres_x2h_tiles[1], plan->d_lowres_x2h_tiles[2]};
     for (void* q : old)
         if (q) cudaFree(q);
     plan->d_shapes = nullptr; plan->d_tab = nullptr; plan->d_lowres_tiles = nullptr; plan->d_lowres_x2_tiles = nullptr;
@@ -160,6 +164,8 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         if (rc == ROD_OK) rc = upload(x2p_tiles[u], &plan->d_lowres_x2p_tiles[u]);
         plan->d_lowres_x2f_tiles[u] = nullptr;
         if (rc == ROD_OK) rc = upload(x2f_tiles[u], &plan->d_lowres_x2f_tiles[u]);
+        plan->d_lowres_x2h_tiles[u] = nullptr;
+        if (rc == ROD_OK) rc = upload(x2h_tiles[u], &plan->d_lowres_x2h_tiles[u]);
     }
     if (rc == ROD_OK) rc = upload(blob, &plan->d_tab);
     if (rc == ROD_OK) rc = upload(gen_tiles, &plan->d_lowres_tiles);
@@ -179,6 +185,8 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         tile_starts(x2p_tiles[u], plan->n_images, plan->lowres_x2p_tile_start[u]);
         plan->n_lowres_x2f_tiles[u] = (int)x2f_tiles[u].size();
         tile_starts(x2f_tiles[u], plan->n_images, plan->lowres_x2f_tile_start[u]);
+        plan->n_lowres_x2h_tiles[u] = (int)x2h_tiles[u].size();
+        tile_starts(x2h_tiles[u], plan->n_images, plan->lowres_x2h_tile_start[u]);
     }
     tile_starts(x2w4_tiles, plan->n_images, plan->lowres_x2w4_tile_start);
     plan->n_lowres_x2_rest_tiles = (int)x2_rest_tiles.size();
@@ -378,6 +386,7 @@ extern "C" void rod_plan_destroy(rod_plan* plan) {
                     plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles, plan->d_lowres_x2_rest_tiles, plan->d_shapes,
                     plan->d_lowres_x2p_tiles[0], plan->d_lowres_x2p_tiles[1], plan->d_lowres_x2p_tiles[2],
                     plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2], plan->d_lowres_x2g_tiles,
+                    plan->d_lowres_x2h_tiles[0], plan->d_lowres_x2h_tiles[1], plan->d_lowres_x2h_tiles[2],
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
                     plan->d_f2d_taps, plan->d_f2d_tiles, plan->d_counters,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};

@@ -69,6 +69,8 @@ struct DevShape {
     uint32_t ly_rc2;            // float4 per output row {c0s, c1s, k0 + 2, bits of x2_vertical_cfix}: lowres_x2f_kernel
     uint32_t ly_rc3;            // float4 per output row: x2g_row_consts (general horizontal stage): lowres_x2g_kernel
     int32_t x2g;                // 1: odd width at factor 0.5 with the regular 3-tap / one-slip structure (lowres_x2g_kernel)
+    uint32_t hy_pack;           // uint4 per low-res row {beta0, beta1, beta2, r0 | nA << 16 | nB << 24}: lowres_x2h_kernel
+    int32_t x2h;                // 1: exact-2x width whose low-res row j has the three y taps 2j, 2j+1, 2j+2 (h = 2 nh + 1)
 };
 
 // ---------------------------------------------------------------------------------

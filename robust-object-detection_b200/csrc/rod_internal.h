@@ -79,6 +79,10 @@ struct rod_plan {
     rod::Tile* d_lowres_x2f_tiles[3] = {nullptr, nullptr, nullptr};
     int n_lowres_x2f_tiles[3] = {0, 0, 0};
     std::vector<int> lowres_x2f_tile_start[3];
+    // ... of those, the shapes with the regular three-tap structure (DevShape::x2h): lowres_x2h_kernel
+    rod::Tile* d_lowres_x2h_tiles[3] = {nullptr, nullptr, nullptr};
+    int n_lowres_x2h_tiles[3] = {0, 0, 0};
+    std::vector<int> lowres_x2h_tile_start[3];
     // odd widths at factor 0.5: lowres_x2g_kernel (any byte alignment), same band x strip tiles
     rod::Tile* d_lowres_x2g_tiles = nullptr;
     int n_lowres_x2g_tiles = 0;

@@ -203,6 +203,32 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
                 packed = (ly.s0[y] == s0 && ly.s1[y] == s1 && ly.coef[y] == coef);
             }
             sh.x2p = packed ? 1 : 0;
+            // regular three-tap kernel (lowres_x2h_kernel): low-res row j reads source rows 2j, 2j+1, 2j+2 (every h = 2 nh + 1
+            // up to ~2000), so row 2j+2 is shared with row j+1 and the source rows can be staged as fixed pairs.  Its row
+            // schedule: after low-res row j exists, the output rows whose lower tap row is j leave -- first those that blend
+            // (j-1, j) [nA of them], then those that blend (j, j) [nB: only at the top and bottom of the image].
+            if (sh.x2w && sh.area_mode == AREA_GENERAL && sh.ay_packed && sh.yt == 3 && h >= 3) {
+                const int32_t* yf = (const int32_t*)(blob.data() + sh.ay_first);
+                const int32_t* yc = (const int32_t*)(blob.data() + sh.ay_count);
+                bool ok = true;
+                for (int j = 0; j < sh.nh && ok; ++j) ok = (yf[j] == 2 * j && yc[j] == 3 && 2 * j + 2 <= h - 1);
+                std::vector<uint32_t> hp((size_t)sh.nh * 4, 0u);
+                int r = 0;
+                for (int j = 0; j < sh.nh && ok; ++j) {
+                    const int r0 = r;
+                    int na = 0, nb = 0;
+                    while (r < h && ly.s1[r] == j && ly.s0[r] == j - 1) { ++na; ++r; }
+                    while (r < h && ly.s1[r] == j && ly.s0[r] == j) { ++nb; ++r; }
+                    ok = (na < 256 && nb < 256 && r0 < 65536);
+                    const uint32_t* pk = blob.data() + sh.ay_pack + 4 * (size_t)j;
+                    hp[4 * j] = pk[1]; hp[4 * j + 1] = pk[2]; hp[4 * j + 2] = pk[3];
+                    hp[4 * j + 3] = (uint32_t)r0 | ((uint32_t)na << 16) | ((uint32_t)nb << 24);
+                }
+                if (ok && r == h) {
+                    sh.hy_pack = blob_push(blob, hp);
+                    sh.x2h = 1;
+                }
+            }
         }
     }
     *out = sh;

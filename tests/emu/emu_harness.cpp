@@ -486,6 +486,102 @@ extern "C" int emu_lowres_x2f(const uint8_t* src, uint8_t* dst, int h, int w, lo
     return 0;
 }
 
+// Replays lowres_x2h_kernel (exact-2x widths with h = 2 nh + 1): the loop over LOW-RES rows of a band, source rows 2j+1 and
+// 2j+2 read as a pair with row 2j's pair sums carried, and the per-low-res-row emission schedule of DevShape::hy_pack
+// (rows that blend (j-1, j), then rows that blend (j, j)), clipped to the band.  Returns 3 if the shape is not eligible.
+extern "C" int emu_lowres_x2h(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch,
+                              double factor, int band_rows) {
+    std::vector<uint32_t> blob;
+    DevShape sh;
+    if (!build_lowres_shape(h, w, factor, 8, blob, &sh)) return 2;
+    if (blob.empty()) blob.push_back(0);
+    if (!sh.x2h) return 3;
+    const uint32_t* tab = blob.data();
+    const int n = 3 * w, nw = sh.nw;
+    const uint32_t* hyp = tab + sh.hy_pack;
+    const uint32_t* ly_s = tab + sh.ly_s;
+    const uint32_t* rc2 = tab + sh.ly_rc2;
+    const int nchunks = (w + 7) >> 3, nstrips = (nchunks + 29) / 30;
+    for (int Y0 = 0; Y0 < h; Y0 += band_rows)
+        for (int st = 0; st < nstrips; ++st) {
+            const int Y1 = std::min(h, Y0 + band_rows);
+            const int j_first = (int)(ly_s[Y0] & 0xFFFFu), j_last = (int)(ly_s[Y1 - 1] >> 16);
+            float xe[32][24], xo[32][24];
+            for (int l = 0; l < 32; ++l) for (int q = 0; q < 24; ++q) xe[l][q] = xo[l][q] = -1e30f;  // poison
+            uint32_t carry[32][12];
+            auto lane_words = [&](int l, int row, uint32_t rw[6]) {
+                const int cc = std::min(std::max(30 * st - 1 + l, 0), nchunks - 1);
+                const bool second = (nw - 4 * cc) >= 4;
+                const uint8_t* rp = src + (long)row * src_pitch + 24 * cc;
+                memcpy(&rw[0], rp, 12);
+                memcpy(&rw[3], rp + (second ? 12 : 0), 12);
+            };
+            for (int l = 0; l < 32; ++l) { uint32_t rw[6]; lane_words(l, 2 * j_first, rw); x2f_pairsums(rw, carry[l]); }
+            int r = Y0;
+            for (int j = j_first; j <= j_last; ++j) {
+                if (2 * j + 2 > h - 1) return 5;
+                const uint32_t* hp = hyp + 4 * j;
+                uint32_t own[32][3];
+                for (int l = 0; l < 32; ++l) {
+                    const int cc = std::min(std::max(30 * st - 1 + l, 0), nchunks - 1);
+                    const bool second = (nw - 4 * cc) >= 4;
+                    uint32_t ra[6], rb[6], sa[12];
+                    lane_words(l, 2 * j + 1, ra);
+                    lane_words(l, 2 * j + 2, rb);
+                    float acc[12];
+                    x2f_mac(carry[l], bitsf(hp[0]), true, acc);
+                    x2f_pairsums(ra, sa);
+                    x2f_mac(sa, bitsf(hp[1]), false, acc);
+                    x2f_pairsums(rb, carry[l]);
+                    x2f_mac(carry[l], bitsf(hp[2]), false, acc);
+                    uint32_t o6[2][6];
+                    area_x2f_finish(acc, o6[0]);
+                    area_x2f_finish(acc + 6, o6[1]);
+                    uint8_t b[12];
+                    for (int q = 0; q < 6; ++q) { b[q] = (uint8_t)o6[0][q]; b[6 + q] = (uint8_t)o6[1][q]; }
+                    if (!second) { b[6] = b[3]; b[7] = b[4]; b[8] = b[5]; b[9] = b[10] = b[11] = 0; }
+                    memcpy(own[l], b, 12);
+                }
+                float (*xnew)[24] = (j & 1) ? xo : xe;
+                float (*xprev)[24] = (j & 1) ? xe : xo;
+                for (int l = 0; l < 32; ++l) {
+                    const int cc = std::min(std::max(30 * st - 1 + l, 0), nchunks - 1);
+                    const uint32_t from_left = own[l > 0 ? l - 1 : l][2], from_right = own[l < 31 ? l + 1 : l][0];
+                    const uint32_t w0 = (cc == 0) ? (own[l][0] << 8) : (from_left & 0xFFFFFF00u);
+                    const uint32_t w4 = (cc == nchunks - 1) ? (own[l][2] >> 8) : (from_right & 0x00FFFFFFu);
+                    const uint32_t win[5] = {funnel_r(w0, own[l][0], 8), funnel_r(own[l][0], own[l][1], 8),
+                                             funnel_r(own[l][1], own[l][2], 8), funnel_r(own[l][2], w4, 8), w4 >> 8};
+                    x2_expand24(win, xnew[l]);
+                }
+                const int r0 = (int)(hp[3] & 0xFFFFu), ra_end = r0 + (int)((hp[3] >> 16) & 0xFFu), rb_end = ra_end + (int)(hp[3] >> 24);
+                const int a_end = std::min(ra_end, Y1), b_end = std::min(rb_end, Y1);
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int end = pass == 0 ? a_end : b_end;
+                    for (; r < end; ++r) {
+                        if (r < r0) return 6;   // the schedule must never skip a row
+                        float c0s, c1s, k0p;
+                        memcpy(&c0s, &rc2[4 * r], 4); memcpy(&c1s, &rc2[4 * r + 1], 4); memcpy(&k0p, &rc2[4 * r + 2], 4);
+                        const uint32_t cfix = rc2[4 * r + 3];
+                        for (int l = 1; l <= 30; ++l) {
+                            const int ch = 30 * st - 1 + l;
+                            if (ch < 0 || ch >= nchunks) continue;
+                            const int nvalid = std::min(24, n - 24 * ch);
+                            const float* xlo = pass == 0 ? xprev[l] : xnew[l];
+                            const float* xhi = xnew[l];
+                            for (int q = 0; q < nvalid; q += 2) {
+                                const uint32_t pr = x2_vertical_pair(xlo[q], xhi[q], xlo[q + 1], xhi[q + 1], c0s, c1s, k0p, cfix);
+                                dst[(long)r * dst_pitch + 24 * ch + q] = (uint8_t)(pr >> 8);
+                                dst[(long)r * dst_pitch + 24 * ch + q + 1] = (uint8_t)(pr >> 24);
+                            }
+                        }
+                    }
+                }
+            }
+            if (r != Y1) return 7;
+        }
+    return 0;
+}
+
 // Replays lowres_x2g_kernel (odd widths at factor 0.5): strips of 30 chunks with halo lanes; per lane the 27-byte source
 // window, the three-tap float INTER_AREA x pass (x2g_hrow) on each tap row with the last tap row carried to the next
 // low-res row, the float y pass, border replication of missing low-res pixels (x2g_replicate), the coefficient /

@@ -281,6 +281,31 @@ def test_emu_lowres_float_staged_kernel(emu, band_rows):
     assert n_run >= 6
 
 
+@pytest.mark.parametrize("band_rows", [24, 56, 512])
+def test_emu_lowres_regular_three_tap_kernel(emu, band_rows):
+    """lowres_x2h_kernel's loop over low-res rows (fixed source-row pairs, carried pair sums, the per-low-res-row emission
+    schedule clipped to the band) replayed on the CPU against the oracle on odd heights; every row is written exactly once."""
+    emu.emu_lowres_x2h.argtypes = emu.emu_lowres_x2w.argtypes
+    n_run = 0
+    shapes = [s for s in X2W_SHAPES if s[0] % 2 == 1] + [(3, 8), (5, 244), (7, 36), (765, 1360), (1079, 1916), (1999, 16), (2001, 8)]
+    for i, (h, w) in enumerate(shapes):
+        img = synth(900 + i, h, w)
+        if i % 2:
+            img = (img > 127).astype(np.uint8) * 255
+        pitch = 3 * w + (0 if i % 3 else 20)
+        buf = np.full((h, pitch), 0xAB, np.uint8)
+        buf[:, :3 * w] = img.reshape(h, 3 * w)
+        got = np.full_like(img, 0x5A)
+        rc = emu.emu_lowres_x2h(_p(buf), _p(got), h, w, pitch, 3 * w, 0.5, band_rows)
+        if rc == 3:     # not eligible (h < 3, or tap rows outside the regular pattern): the float-tap kernel takes it
+            continue
+        assert rc == 0, (h, w, rc)
+        want = orc.apply_lowres(img, 0.5)
+        assert np.array_equal(got, want), (h, w, band_rows, int((got != want).sum()))
+        n_run += 1
+    assert n_run >= 8
+
+
 X2G_SHAPES = [(765, 1361), (360, 481), (100, 9), (9, 5), (2, 3), (5, 13), (64, 65), (65, 129), (131, 37), (201, 1401), (97, 1917),
               (540, 961), (33, 1999), (40, 21), (77, 1363), (50, 241), (51, 243), (52, 247), (8, 7), (3, 11), (10, 15), (64, 17)]
 

@@ -1,5 +1,5 @@
-"""Times the fused LowRes kernels on a B200 (device-resident batches), with the packed-integer kernel on / off and its
-residency knob.  Usage: python tools/sweep_lowres.py [quick]"""
+"""Times the fused LowRes kernels on a B200 (device-resident batches) under different benchmark knobs.
+Usage: python tools/sweep_lowres.py <workload,...> <name:KNOB=V,KNOB=V> ...   (see WORKLOADS / KNOBS below)"""
 import json
 import os
 import sys
@@ -28,24 +28,34 @@ def rate(fn, nbytes, steps=8, warmup=3):
     return round(nbytes / (e0.elapsed_time(e1) / steps) / 1e6, 1)
 
 
-def workloads():
-    yield "1361x765_x128", [(765, 1361)] * 128
-    yield "1999x1499_x48", [(1499, 1999)] * 48
-    yield "1917x1080_x64", [(1080, 1917)] * 64
-    rng = np.random.default_rng(3000)
-    yield "mixed_256", [POOL[i] for i in rng.integers(0, len(POOL), 256)]
-    yield "odd_only_96", [POOL[8 + i % 3] for i in range(96)]
+WORKLOADS = {
+    "1360x765_x256": [(765, 1360)] * 256,
+    "1360x765_x64": [(765, 1360)] * 64,
+    "1916x1079_x64": [(1079, 1916)] * 64,
+    "1361x765_x128": [(765, 1361)] * 128,
+    "1999x1499_x48": [(1499, 1999)] * 48,
+    "1917x1080_x64": [(1080, 1917)] * 64,
+    "1920x1080_x128": [(1080, 1920)] * 128,
+    "mixed_256": [POOL[i] for i in np.random.default_rng(3000).integers(0, len(POOL), 256)],
+    "odd_only_96": [POOL[8 + i % 3] for i in range(96)],
+}
+KNOBS = ("ROD_X2_PACKED", "ROD_X2P_CTAS", "ROD_X2_FLOAT_STAGED", "ROD_X2F_CTAS", "ROD_X2_ODD_STAGED", "ROD_X2G_CTAS",
+         "ROD_X2G_BAND_DIV", "ROD_X2_REGULAR", "ROD_X2H_CTAS", "ROD_X2_BAND")
 
-
-settings = [("g3", {"ROD_X2G_CTAS": "3"}), ("g4", {"ROD_X2G_CTAS": "4"}), ("g3_b30", {"ROD_X2G_CTAS": "3", "ROD_X2G_BAND_DIV": "30"}), ("g3_b120", {"ROD_X2G_CTAS": "3", "ROD_X2G_BAND_DIV": "120"})]
-extra = [kv.split("=") for kv in sys.argv[1:] if "=" in kv]
-if extra:
-    settings = [("custom", dict(extra))]
+# usage: sweep_lowres.py <workload,workload,...> <name:K=V,K=V> <name:K=V> ...   (a bare "name:" is the default setting)
+names = sys.argv[1].split(",") if len(sys.argv) > 1 else list(WORKLOADS)
+settings = []
+for a in sys.argv[2:]:
+    sname, _, kvs = a.partition(":")
+    settings.append((sname, dict(kv.split("=") for kv in kvs.split(",") if kv)))
+if not settings:
+    settings = [("default", {})]
 out = {}
-for wname, shapes in workloads():
+for wname in names:
+    shapes = WORKLOADS[wname]
     src = dst = None
     for sname, env in settings:
-        for k in ("ROD_X2_PACKED", "ROD_X2P_CTAS", "ROD_X2_FLOAT_STAGED", "ROD_X2F_CTAS", "ROD_X2_ODD_STAGED", "ROD_X2G_CTAS", "ROD_X2G_BAND_DIV"):
+        for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)
         plan = CorruptionPlan.ragged(shapes)
