@@ -139,7 +139,8 @@ extern "C" int rod_plan_launches(const rod_plan* plan, int op) {
                           (plan->n_lowres_x2_rest_tiles > 0) + (plan->n_lowres_x2p_tiles[0] > 0) + (plan->n_lowres_x2p_tiles[1] > 0) +
                           (plan->n_lowres_x2p_tiles[2] > 0) + (plan->n_lowres_x2f_tiles[0] > 0) + (plan->n_lowres_x2f_tiles[1] > 0) +
                           (plan->n_lowres_x2f_tiles[2] > 0) + (plan->n_lowres_x2g_tiles > 0) + (plan->n_lowres_x2h_tiles[0] > 0) +
-                          (plan->n_lowres_x2h_tiles[1] > 0) + (plan->n_lowres_x2h_tiles[2] > 0);
+                          (plan->n_lowres_x2h_tiles[1] > 0) + (plan->n_lowres_x2h_tiles[2] > 0) + (plan->n_lowres_x2i_tiles[0] > 0) +
+                          (plan->n_lowres_x2i_tiles[1] > 0);
             return n > 0 ? n : 1;
         }
         case 100: return 4;  // rod_corrupt_batch_u8: copy + noise + blur + lowres

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "rod_internal.h"
 
@@ -1067,6 +1068,11 @@ __global__ void __launch_bounds__(128, MINB) lowres_x2f_kernel(LowresX2wParams p
 // strip where the arithmetic needs ~190.)
 // =====================================================================================
 constexpr int kX2hStages = 4;
+__device__ __forceinline__ float4 ldg_early16(const void* p) {   // a read-only 16-byte load that stays where it is written
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 struct alignas(16) X2hWarpSmem {
     uint8_t in[kX2hStages][2][kX2pRowBytes];
     uint8_t out[2][kX2pOutBytes];
@@ -1084,10 +1090,9 @@ struct X2hState {
     const uint8_t* in0;       // this lane's chunk in stage 0, row 0
     // emission
     uint8_t* grow;            // this lane's copy unit 0 of the next output row
-    uint8_t* ob0; uint8_t* ob1;
-    int ooff;
+    uint32_t ob_s, ob_flip;   // shared address of the current output staging buffer; xor mask to the other one
+    int ooff, loff;           // byte offsets in the staging buffer: this lane's chunk (< 0: stores nothing), its copy unit 0
     const float4* rc_tab;
-    float4 rcA, rcB;          // constants of output rows r and r + 1
     int r, H;
     int lane;
 };
@@ -1104,13 +1109,43 @@ __device__ __forceinline__ void x2h_issue(X2hState<U>& s) {   // stage `next_sta
     ++s.next_stage;
 }
 
+// one output row: 24 bytes per lane into the staging buffer, then the warp copies the row segment out with coalesced stores
 template <int U>
-__device__ __forceinline__ void x2h_emit_row(X2hState<U>& s, const float* xlo, const float* xhi) {
-    const float4 rf = s.rcA;
-    s.rcA = s.rcB;
-    s.rcB = __ldg(s.rc_tab + min(s.r + 2, s.H - 1));
-    x2f_store_row<U>(s.ob0, s.ooff, xlo, xhi, rf.x, rf.y, rf.z, __float_as_uint(rf.w), s.grow, s.lane, s.out_units);
-    uint8_t* tswap = s.ob0; s.ob0 = s.ob1; s.ob1 = tswap;
+__device__ __forceinline__ void x2h_emit_row(X2hState<U>& s, const float* xlo, const float* xhi, const float4 rf) {
+    if (s.ooff >= 0) {
+        const uint32_t cfix = __float_as_uint(rf.w);
+        uint32_t pr[12];
+#pragma unroll
+        for (int t = 0; t < 12; ++t)
+            pr[t] = x2_vertical_pair(xlo[2 * t], xhi[2 * t], xlo[2 * t + 1], xhi[2 * t + 1], rf.x, rf.y, rf.z, cfix);
+        const uint32_t a = s.ob_s + (uint32_t)s.ooff;
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a + 8 * g), "r"(perm<0x7531>(pr[4 * g], pr[4 * g + 1])),
+                         "r"(perm<0x7531>(pr[4 * g + 2], pr[4 * g + 3])) : "memory");
+    }
+    __syncwarp();
+    constexpr int K = (kX2wChunksPerStrip * 24 / U + 31) / 32;
+    const uint32_t l = s.ob_s + (uint32_t)s.loff;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (s.lane + 32 * k < s.out_units) {
+            if (U == 16) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(l + 32 * U * k));
+                stg16s(s.grow + 32 * U * k, v);
+            } else if (U == 8) {
+                uint2 v;
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(l + 32 * U * k));
+                stg8(s.grow + 32 * U * k, v.x, v.y);
+            } else {
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(l + 32 * U * k));
+                stg4s(s.grow + 32 * U * k, v);
+            }
+        }
+    }
+    s.ob_s ^= s.ob_flip;
     s.grow += s.dp;
     ++s.r;
 }
@@ -1118,7 +1153,7 @@ __device__ __forceinline__ void x2h_emit_row(X2hState<U>& s, const float* xlo, c
 // low-res row j: stage index st = j - j_first + 1.  xnew receives its horizontal stage, xprev holds row j - 1's.
 template <int U>
 __device__ __forceinline__ void x2h_row(X2hState<U>& s, const X2pLane& c, int st, uint4& hp_next, const uint4* hp_fetch,
-                                        uint32_t carry[12], float* xnew, const float* xprev, int Y0, int Y1) {
+                                        uint32_t carry[12], float* xnew, const float* xprev, int Y1) {
     cp_async_wait<kX2hStages - 2>();   // this lane's copies of stage st have landed ...
     __syncwarp();                      // ... and everybody else's; all lanes are done with the stage before it
     uint32_t ra[6], rb[6];
@@ -1132,7 +1167,16 @@ __device__ __forceinline__ void x2h_row(X2hState<U>& s, const X2pLane& c, int st
     }
     x2h_issue<U>(s);                   // refills the slot that was read one row ago
     const uint4 hp = hp_next;
-    hp_next = __ldg(hp_fetch);
+    {
+        const float4 t = ldg_early16(hp_fetch);
+        hp_next = make_uint4(__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w));
+    }
+    // output rows whose lower tap row is j: [r0, r0 + nA) blend (j - 1, j), [r0 + nA, r0 + nA + nB) blend (j, j); the rows
+    // before s.r have left already (s.r >= r0 by construction).  Constants of the first two, fetched before the arithmetic.
+    const int ra_end = (int)(hp.w & 0xFFFFu) + (int)((hp.w >> 16) & 0xFFu);
+    const int na = min(ra_end, Y1) - s.r, b_end = min(ra_end + (int)(hp.w >> 24), Y1);
+    // (volatile: the compiler would otherwise sink these loads to their first use, after ~200 instructions of arithmetic)
+    const float4 rc0 = ldg_early16(s.rc_tab + min(s.r, s.H - 1)), rc1 = ldg_early16(s.rc_tab + min(s.r + 1, s.H - 1));
     float acc[12];
     x2f_mac(carry, __uint_as_float(hp.x), true, acc);
     {
@@ -1160,13 +1204,16 @@ __device__ __forceinline__ void x2h_row(X2hState<U>& s, const X2pLane& c, int st
         }
     }
     x2f_expand(c, own, xnew);
-    // output rows whose lower tap row is j: [r0, r0 + nA) blend (j - 1, j), [r0 + nA, r0 + nA + nB) blend (j, j)
-    const int r0 = (int)(hp.w & 0xFFFFu), ra_end = r0 + (int)((hp.w >> 16) & 0xFFu), rb_end = ra_end + (int)(hp.w >> 24);
-    const int a_end = min(ra_end, Y1), b_end = min(rb_end, Y1);
+    if (na >= 1) {
+        x2h_emit_row<U>(s, xprev, xnew, rc0);
+        if (na >= 2) {
+            x2h_emit_row<U>(s, xprev, xnew, rc1);
 #pragma unroll 1
-    while (s.r < a_end) x2h_emit_row<U>(s, xprev, xnew);    // (s.r >= max(r0, Y0) by construction)
+            for (int k = 2; k < na; ++k) x2h_emit_row<U>(s, xprev, xnew, __ldg(s.rc_tab + s.r));
+        }
+    }
 #pragma unroll 1
-    while (s.r < b_end) x2h_emit_row<U>(s, xnew, xnew);
+    while (s.r < b_end) x2h_emit_row<U>(s, xnew, xnew, __ldg(s.rc_tab + s.r));   // top / bottom rows of the image only
 }
 
 template <int U>
@@ -1200,12 +1247,12 @@ __device__ __forceinline__ void x2h_tile(const LowresX2wParams& p, const Tile& t
     s.out_units = (min(24 * (c0 + kX2wChunksPerStrip), n) - 24 * c0) / U;
     s.in0 = &ws.in[0][0][c.soff];
     s.ooff = stores ? 24 * (lane - 1) : -1;
-    s.ob0 = ws.out[0]; s.ob1 = ws.out[1];
+    s.loff = U * lane;
+    s.ob_s = (uint32_t)__cvta_generic_to_shared(ws.out[0]);
+    s.ob_flip = s.ob_s ^ (uint32_t)__cvta_generic_to_shared(ws.out[1]);
     s.grow = dimg + 24 * c0 + U * lane + (int64_t)Y0 * s.dp;
     s.rc_tab = reinterpret_cast<const float4*>(p.tab + sh.ly_rc2);
     s.r = Y0; s.H = H;
-    s.rcA = __ldg(s.rc_tab + Y0);
-    s.rcB = __ldg(s.rc_tab + min(Y0 + 1, H - 1));
     // stage 0 holds source row 2 j_first alone (in its second row slot); stage st >= 1 rows 2 j + 1, 2 j + 2, j = j_first + st - 1
     s.n_stages = j_last - j_first + 2;
     s.gnext = simg + 24 * cs + U * lane + (int64_t)(2 * j_first) * s.sp;
@@ -1231,8 +1278,8 @@ __device__ __forceinline__ void x2h_tile(const LowresX2wParams& p, const Tile& t
     }
 #pragma unroll 1
     for (int jj = j_first & ~1; jj <= j_last; jj += 2) {
-        if (jj >= j_first) x2h_row<U>(s, c, jj - j_first + 1, hp_next, hyp + min(jj + 1, j_last), carry, xe, xo, Y0, Y1);
-        if (jj + 1 <= j_last) x2h_row<U>(s, c, jj - j_first + 2, hp_next, hyp + min(jj + 2, j_last), carry, xo, xe, Y0, Y1);
+        if (jj >= j_first) x2h_row<U>(s, c, jj - j_first + 1, hp_next, hyp + min(jj + 1, j_last), carry, xe, xo, Y1);
+        if (jj + 1 <= j_last) x2h_row<U>(s, c, jj - j_first + 2, hp_next, hyp + min(jj + 2, j_last), carry, xo, xe, Y1);
     }
     cp_async_wait<0>();
 }
@@ -1474,13 +1521,342 @@ __global__ void __launch_bounds__(128, MINB) lowres_x2g_kernel(LowresX2wParams p
     }
 }
 
-int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
-                  cudaStream_t stream, int img_lo, int img_hi) {
+// =====================================================================================
+// Odd widths with a regular y axis (DevShape::x2i): lowres_x2g_kernel's arithmetic and byte-phase staging inside
+// lowres_x2h_kernel's control structure -- a loop over low-res rows unrolled by parity, source rows staged as fixed pairs
+// (CARRY, odd h: rows 2j+1, 2j+2 with row 2j's horizontal pass carried; else even h: rows 2j, 2j+1), the emission schedule
+// of DevShape::hy_pack.  (lowres_x2g_kernel: 473 warp instructions per output row of a strip, ~290 of them arithmetic.)
+// =====================================================================================
+struct alignas(16) X2iWarpSmem {
+    uint8_t in[kX2hStages][2][kX2pRowBytes];
+    uint8_t out[2][kX2pOutBytes];
+    float4 lc[8][32];   // per-lane column constants of the tile: [0..2] area weights, [3..5] -2^23 * weights, [6..7] linear coefficients
+};
+struct X2iState {
+    uint32_t in_s;            // shared address of this lane's 16-byte unit 0 in stage 0, row 0
+    const uint8_t* gnext;     // first byte of the strip's segment in the next source row to stage
+    const uint8_t* gread;     // ... in the next source row to read from the ring (its low four bits place the row in its slot)
+    int64_t sp, dp;
+    int slen, olen;
+    int next_stage, n_stages;
+    uint32_t in0;             // shared address of this lane's window in stage 0, row 0 (without the row's 16-byte phase)
+    uint8_t* grow;            // first byte of the strip's segment in the next output row
+    uint32_t ob_s, ob_flip;   // shared address of the current output staging buffer; xor mask to the other one
+    uint32_t lc_s;            // shared address of this lane's first constant vector (the others follow at 512-byte steps)
+    bool first_strip, last_strip;
+    const float4* rc_tab;
+    int r, H;
+    int lane;
+};
+
+// A source row is staged with 16-byte copies from the 16-byte block that holds the segment's first byte, so it sits in its
+// ring slot at its global phase (0..15); the last unit copies only the bytes up to the segment's end (the rest is zero-filled).
+__device__ __forceinline__ void x2i_stage_row(X2iState& s, uint32_t slot) {
+    const int ph = (int)((uintptr_t)s.gnext & 15);
+    const uint8_t* g = s.gnext - ph + 16 * s.lane;
+    const int total = ph + s.slen;                      // bytes from the aligned start to the segment's end
+    constexpr int K = (kX2pRowBytes / 16 + 31) / 32;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int left = total - 16 * (s.lane + 32 * k);
+        if (left > 0)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + 512 * k), "l"(g + 512 * k), "r"(min(left, 16)) : "memory");
+    }
+    s.gnext += s.sp;
+}
+__device__ __forceinline__ void x2i_issue(X2iState& s) {
+    if (s.next_stage < s.n_stages) {
+        const uint32_t slot = s.in_s + (uint32_t)((s.next_stage & (kX2hStages - 1)) * (2 * kX2pRowBytes));
+        x2i_stage_row(s, slot);
+        x2i_stage_row(s, slot + kX2pRowBytes);
+    }
+    cp_async_commit();
+    ++s.next_stage;
+}
+// the lane's 27-byte window of the next source row to read (ring row at shared address `rowp`), shifted by the row's phase
+__device__ __forceinline__ void x2i_window(X2iState& s, uint32_t rowp, uint32_t wn[7]) {
+    const uint32_t ph = (uint32_t)((uintptr_t)s.gread & 15);
+    s.gread += s.sp;
+    const uint32_t a = rowp + (ph & ~3u);
+    uint32_t raw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw[k]) : "r"(a + 4 * k));
+#pragma unroll
+    for (int k = 0; k < 7; ++k) wn[k] = __funnelshift_r(raw[k], raw[k + 1], 8 * (ph & 3u));
+}
+// One output row.  Every lane shifts its 24 bytes by the destination row's 4-byte phase (taking the spill-over of its left
+// neighbour by shuffle), so that the staging buffer mirrors the global 4-byte words: buffer word 0 = the aligned word that
+// holds the segment's first byte.  The halo lanes' bytes are valid output too, so a segment that is not at the image border
+// leaves as WHOLE aligned words (the two words it shares with the neighbouring strips are written by both, with the same
+// bytes); only the first / last strip of a row finish with byte stores.
+__device__ __forceinline__ void x2i_emit_row(X2iState& s, const float* xlo, const float* xhi, const float4 rf) {
+    X2Row rc;
+    rc.c0s = rf.x; rc.c1s = rf.y; rc.k0 = rf.z; rc.k2 = rf.w;
+    uint32_t o[24];
+#pragma unroll
+    for (int t = 0; t < 24; ++t) o[t] = x2_vertical(xlo[t], xhi[t], rc);
+    uint32_t w[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g)
+        w[g] = __byte_perm(__byte_perm(o[4 * g], o[4 * g + 1], 0x0040), __byte_perm(o[4 * g + 2], o[4 * g + 3], 0x0040), 0x5410);
+    const int ph = (int)((uintptr_t)s.grow & 3);
+    const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, w[5], 1);
+    uint32_t v[6];   // (w[k] << 8 ph) | (w[k-1] >> (32 - 8 ph)); ph == 0: the word itself
+    v[0] = __funnelshift_l(prev, w[0], 8 * ph);
+#pragma unroll
+    for (int k = 1; k < 6; ++k) v[k] = __funnelshift_l(w[k - 1], w[k], 8 * ph);
+    if (s.lane >= 1) {
+        const uint32_t a = s.ob_s + 24u * (uint32_t)(s.lane - 1);
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a + 8 * g), "r"(v[2 * g]), "r"(v[2 * g + 1]) : "memory");
+    }
+    __syncwarp();
+    // buffer byte ph + i = output byte i of the segment; buffer word q <-> the aligned global word at grow - ph + 4 q
+    const int tot = ph + s.olen;
+    int w_lo = 0, w_hi = (tot + 3) >> 2;
+    if (s.first_strip | s.last_strip) {  // (warp-uniform, constant over the tile)
+        if (s.first_strip && ph != 0) {  // the word before the row's first byte belongs to the previous row
+            w_lo = 1;
+            if (s.lane < 4 - ph && s.lane < s.olen) {
+                uint32_t b;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(s.ob_s + ph + s.lane));
+                s.grow[s.lane] = (uint8_t)b;
+            }
+        }
+        if (s.last_strip) {              // ... and the bytes after the row's last one to the next row
+            w_hi = tot >> 2;
+            const int tail = tot & 3, q = 4 * w_hi - ph + (s.lane - 8);   // output byte handled by lanes 8..10
+            if (s.lane >= 8 && s.lane - 8 < tail && q >= 0 && !(w_lo == 1 && w_hi == 0)) {
+                uint32_t b;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(s.ob_s + ph + q));
+                s.grow[q] = (uint8_t)b;
+            }
+        }
+    }
+    uint8_t* gb = s.grow - ph + 4 * s.lane;
+    const uint32_t sb = s.ob_s + 4u * (uint32_t)s.lane;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int q = s.lane + 32 * k;
+        if (q >= w_lo && q < w_hi) {
+            uint32_t b;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b) : "r"(sb + 128 * k));
+            stg4s(gb + 128 * k, b);
+        }
+    }
+    s.ob_s ^= s.ob_flip;
+    s.grow += s.dp;
+    ++s.r;
+}
+
+__device__ __forceinline__ void x2i_lane_consts(uint32_t lc_s, float al[12], float nal[12]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(al[4 * k]), "=f"(al[4 * k + 1]), "=f"(al[4 * k + 2]), "=f"(al[4 * k + 3]) : "r"(lc_s + 512u * k));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(nal[4 * k]), "=f"(nal[4 * k + 1]), "=f"(nal[4 * k + 2]), "=f"(nal[4 * k + 3]) : "r"(lc_s + 512u * (3 + k)));
+    }
+}
+
+template <bool CARRY>
+__device__ __forceinline__ void x2i_row(X2iState& s, X2gLane& c, int st, uint4& hp_next, const uint4* hp_fetch,
+                                        float carry[12], float* xnew, const float* xprev, int Y1) {
+    cp_async_wait<kX2hStages - 2>();
+    __syncwarp();
+    uint32_t wa[7], wb[7];
+    {
+        const uint32_t sl = s.in0 + (uint32_t)((st & (kX2hStages - 1)) * (2 * kX2pRowBytes));
+        x2i_window(s, sl, wa);
+        x2i_window(s, sl + kX2pRowBytes, wb);
+    }
+    x2i_issue(s);
+    const uint4 hp = hp_next;
+    hp_next = __ldg(hp_fetch);
+    const int ra_end = (int)(hp.w & 0xFFFFu) + (int)((hp.w >> 16) & 0xFFu);
+    const int na = min(ra_end, Y1) - s.r, b_end = min(ra_end + (int)(hp.w >> 24), Y1);
+    const float4 rc0 = ldg_early16(s.rc_tab + min(s.r, s.H - 1)), rc1 = ldg_early16(s.rc_tab + min(s.r + 1, s.H - 1));
+    float acc[12];
+    {
+        float al[12], nal[12];
+        x2i_lane_consts(s.lc_s, al, nal);
+        if (CARRY) {
+            x2g_vmac(carry, __uint_as_float(hp.x), true, acc);
+            {
+                float ha[12];
+                x2g_hrow_pre(wa, al, nal, ha);
+                x2g_vmac(ha, __uint_as_float(hp.y), false, acc);
+            }
+            x2g_hrow_pre(wb, al, nal, carry);   // source row 2j + 2: also the first tap row of low-res row j + 1
+            x2g_vmac(carry, __uint_as_float(hp.z), false, acc);
+        } else {
+            float ha[12];
+            x2g_hrow_pre(wa, al, nal, ha);
+            x2g_vmac(ha, __uint_as_float(hp.x), true, acc);
+            x2g_hrow_pre(wb, al, nal, ha);
+            x2g_vmac(ha, __uint_as_float(hp.y), false, acc);
+        }
+    }
+    uint32_t own[3];
+    x2g_round12(acc, own);
+    {
+        uint32_t coef[8];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(coef[4 * k]), "=r"(coef[4 * k + 1]), "=r"(coef[4 * k + 2]), "=r"(coef[4 * k + 3])
+                         : "r"(s.lc_s + 512u * (6 + k)));
+        x2g_expand(c, own, coef, xnew);
+    }
+    if (na >= 1) {
+        x2i_emit_row(s, xprev, xnew, rc0);
+        if (na >= 2) {
+            x2i_emit_row(s, xprev, xnew, rc1);
+#pragma unroll 1
+            for (int k = 2; k < na; ++k) x2i_emit_row(s, xprev, xnew, __ldg(s.rc_tab + s.r));
+        }
+    }
+#pragma unroll 1
+    while (s.r < b_end) x2i_emit_row(s, xnew, xnew, __ldg(s.rc_tab + s.r));
+}
+
+template <bool CARRY>
+__device__ __forceinline__ void x2i_tile(const LowresX2wParams& p, const Tile& t, const DevImage& im, const DevShape& sh,
+                                         X2iWarpSmem& ws, int lane) {
+    constexpr int PRE = CARRY ? 1 : 0;
+    const uint8_t* simg = p.src + im.src_off;
+    uint8_t* dimg = p.dst + im.dst_off;
+    const int n = 3 * im.w, nw = sh.nw, H = im.h, W = im.w;
+    const int nchunks = (W + 7) >> 3;
+    const int c0 = kX2wChunksPerStrip * t.c;
+    const int cc = min(max(c0 - 1 + lane, 0), nchunks - 1);
+    const int cs = max(c0 - 1, 0), ce = min(c0 + kX2wChunksPerStrip, nchunks - 1);
+    X2gLane c;
+    c.soff = 24 * (cc - cs);
+    c.valid = nw - 4 * cc;
+    c.first = (cc == 0);
+    c.last = (cc == nchunks - 1);
+    __syncwarp();  // the previous tile's reads of the ring and of the lane constants are done
+    {
+        float al[12];
+        uint32_t coef[8];
+        const float* xalpha = reinterpret_cast<const float*>(p.tab + sh.ax_alpha);
+        const int32_t* lx_s0 = reinterpret_cast<const int32_t*>(p.tab + sh.lx_s0);
+        const uint32_t* lx_a = p.tab + sh.lx_a;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int dx = min(4 * cc + q, nw - 1);
+#pragma unroll
+            for (int tp = 0; tp < 3; ++tp) al[3 * q + tp] = __ldg(xalpha + 3 * dx + tp);
+        }
+        c.slip = 0;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const int xa = min(8 * cc + x, W - 1);
+            coef[x] = __ldg(lx_a + xa);
+            if ((x & 1) && __ldg(lx_s0 + xa) == ((xa - 1) >> 1) - 1) c.slip |= 1u << (x >> 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ws.lc[k][lane] = make_float4(al[4 * k], al[4 * k + 1], al[4 * k + 2], al[4 * k + 3]);
+            ws.lc[3 + k][lane] = make_float4(fmul(al[4 * k], -8388608.0f), fmul(al[4 * k + 1], -8388608.0f),
+                                             fmul(al[4 * k + 2], -8388608.0f), fmul(al[4 * k + 3], -8388608.0f));
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            ws.lc[6 + k][lane] = make_float4(__uint_as_float(coef[4 * k]), __uint_as_float(coef[4 * k + 1]),
+                                             __uint_as_float(coef[4 * k + 2]), __uint_as_float(coef[4 * k + 3]));
+    }
+    const uint32_t* ly_s = p.tab + sh.ly_s;
+    const uint4* hyp = reinterpret_cast<const uint4*>(p.tab + sh.hy_pack);
+    const int Y0 = t.a, Y1 = t.b;
+    const int j_first = (int)(__ldg(ly_s + Y0) & 0xFFFFu), j_last = (int)(__ldg(ly_s + Y1 - 1) >> 16);
+
+    X2iState s;
+    s.lc_s = (uint32_t)__cvta_generic_to_shared(&ws.lc[0][lane]);
+    s.lane = lane;
+    s.in_s = (uint32_t)__cvta_generic_to_shared(&ws.in[0][0][0]) + 16 * lane;
+    s.sp = im.src_pitch; s.dp = im.dst_pitch;
+    s.slen = min(24 * (ce + 1) + 3, n) - 24 * cs;          // staged bytes of a row: + the ninth pixel of chunk ce
+    s.olen = min(24 * (c0 + kX2wChunksPerStrip), n) - 24 * c0;
+    s.in0 = (uint32_t)__cvta_generic_to_shared(&ws.in[0][0][0]) + (uint32_t)c.soff;
+    s.ob_s = (uint32_t)__cvta_generic_to_shared(ws.out[0]);
+    s.ob_flip = s.ob_s ^ (uint32_t)__cvta_generic_to_shared(ws.out[1]);
+    s.first_strip = (c0 == 0);
+    s.last_strip = (c0 + kX2wChunksPerStrip >= nchunks);
+    s.grow = dimg + 24 * c0 + (int64_t)Y0 * s.dp;
+    s.rc_tab = reinterpret_cast<const float4*>(p.tab + sh.ly_rc3);
+    s.r = Y0; s.H = H;
+    // CARRY: stage 0 holds source row 2 j_first alone (second row slot), stage st >= 1 rows 2j + 1, 2j + 2 (j = j_first + st - 1);
+    // else stage st holds rows 2j, 2j + 1 (j = j_first + st)
+    s.n_stages = j_last - j_first + 1 + PRE;
+    s.gnext = simg + 24 * cs + (int64_t)(2 * j_first) * s.sp;
+    s.gread = s.gnext;
+    __syncwarp();  // the previous tile's reads of the ring are done
+    s.next_stage = 0;
+    if (CARRY) {
+        x2i_stage_row(s, s.in_s + kX2pRowBytes);
+        cp_async_commit();
+        s.next_stage = 1;
+    }
+#pragma unroll
+    for (int q = PRE; q < kX2hStages - 1; ++q) x2i_issue(s);
+    uint4 hp_next = __ldg(hyp + j_first);
+
+    float xe[24], xo[24];
+    float carry[12];
+    if (CARRY) {   // stage 0: the horizontal pass of source row 2 j_first
+        cp_async_wait<kX2hStages - 2>();
+        __syncwarp();
+        uint32_t wb[7];
+        x2i_window(s, s.in0 + (uint32_t)kX2pRowBytes, wb);
+        x2i_issue(s);
+        float al[12], nal[12];
+        x2i_lane_consts(s.lc_s, al, nal);
+        x2g_hrow_pre(wb, al, nal, carry);
+    }
+#pragma unroll 1
+    for (int jj = j_first & ~1; jj <= j_last; jj += 2) {
+        if (jj >= j_first) x2i_row<CARRY>(s, c, jj - j_first + PRE, hp_next, hyp + min(jj + 1, j_last), carry, xe, xo, Y1);
+        if (jj + 1 <= j_last) x2i_row<CARRY>(s, c, jj - j_first + 1 + PRE, hp_next, hyp + min(jj + 2, j_last), carry, xo, xe, Y1);
+    }
+    cp_async_wait<0>();
+}
+
+template <bool CARRY, int MINB>
+__global__ void __launch_bounds__(128, MINB) lowres_x2i_kernel(LowresX2wParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    X2iWarpSmem& ws = reinterpret_cast<X2iWarpSmem*>(smem)[threadIdx.x >> 5];
+    for (;;) {
+        int ti = 0;
+        if (lane == 0) ti = (int)atomicAdd(p.counter, 1u);
+        ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+        if (ti >= p.n_tiles) break;
+        const Tile t = p.tiles[ti];
+        if (p.opcodes != nullptr && p.opcodes[t.img] != ROD_OP_LOWRES) continue;
+        const DevImage im = p.images[t.img];
+        const DevShape sh = p.shapes[im.shape_id];
+        x2i_tile<CARRY>(p, t, im, sh, ws, lane);
+    }
+}
+
+namespace {
+// The launches of one LowRes call touch disjoint images, so they may run concurrently: with more than one non-empty
+// tile list they are spread over the caller's stream and two plan-owned streams forked from / joined into it (events:
+// capturable), so that the persistent CTAs of the next kernel move in while the last tiles of the previous one finish.
+struct LrStreams {
+    cudaStream_t s[3];
+    int n, i;
+    cudaStream_t pick() { const cudaStream_t r = s[i]; i = (i + 1) % n; return r; }
+};
+
+int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes, LrStreams& ls,
+                        int img_lo, int img_hi) {
     // generic tiles (shapes that are not exact-2x in x)
     {
         const int t_lo = plan->lowres_tile_start[img_lo], t_hi = plan->lowres_tile_start[img_hi];
         if (t_hi > t_lo) {
             LowresParams p;
+            const cudaStream_t lst = ls.pick();
             p.images = plan->d_images;
             p.tiles = plan->d_lowres_tiles + t_lo;
             p.n_tiles = t_hi - t_lo;
@@ -1497,7 +1873,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             ROD_CUDA(cudaFuncSetAttribute(lowres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
             ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 3 ? 3 : ctas_per_sm);
-            lowres_kernel<<<grid_for(plan, p.n_tiles, ctas_per_sm), 256, smem, stream>>>(p);
+            lowres_kernel<<<grid_for(plan, p.n_tiles, ctas_per_sm), 256, smem, lst>>>(p);
             ROD_CUDA(cudaGetLastError());
         }
     }
@@ -1506,6 +1882,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
         const int t_lo = plan->lowres_x2g_tile_start[img_lo], t_hi = plan->lowres_x2g_tile_start[img_hi];
         if (t_hi > t_lo) {
             LowresX2wParams p;
+            const cudaStream_t lst = ls.pick();
             p.images = plan->d_images;
             p.tiles = plan->d_lowres_x2g_tiles + t_lo;
             p.n_tiles = t_hi - t_lo;
@@ -1513,7 +1890,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
-            ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+            ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), lst));
             const int ctas = (p.n_tiles + 3) / 4;
             const size_t smem = 4 * sizeof(X2fWarpSmem);
             int per_sm = 3;  // knob ROD_X2G_CTAS = 2 | 3 | 4
@@ -1522,7 +1899,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
 #define ROD_X2G_LAUNCH(B)                                                                                              \
     do {                                                                                                               \
         ROD_CUDA(cudaFuncSetAttribute(lowres_x2g_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        lowres_x2g_kernel<B><<<grid_for(plan, ctas, B), 128, smem, stream>>>(p);                                       \
+        lowres_x2g_kernel<B><<<grid_for(plan, ctas, B), 128, smem, lst>>>(p);                                       \
     } while (0)
             if (per_sm == 2) ROD_X2G_LAUNCH(2);
             else if (per_sm == 4) ROD_X2G_LAUNCH(4);
@@ -1530,6 +1907,43 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
 #undef ROD_X2G_LAUNCH
             ROD_CUDA(cudaGetLastError());
         }
+    }
+    // ... and of those, the shapes with a regular y axis: the low-res-row loop kernel ([0]: odd h, carried tap row; [1]: even h)
+    for (int u = 0; u < 2; ++u) {
+        if (plan->n_lowres_x2i_tiles[u] == 0) continue;
+        const int t_lo = plan->lowres_x2i_tile_start[u][img_lo], t_hi = plan->lowres_x2i_tile_start[u][img_hi];
+        if (t_hi <= t_lo) continue;
+        LowresX2wParams p;
+        const cudaStream_t lst = ls.pick();
+        p.images = plan->d_images;
+        p.tiles = plan->d_lowres_x2i_tiles[u] + t_lo;
+        p.n_tiles = t_hi - t_lo;
+        p.shapes = plan->d_shapes;
+        p.tab = plan->d_tab;
+        p.src = src; p.dst = dst; p.opcodes = opcodes;
+        p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
+        ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), lst));
+        const int ctas = (p.n_tiles + 3) / 4;
+        const size_t smem = 4 * sizeof(X2iWarpSmem);
+        int per_sm = 3;  // knob ROD_X2I_CTAS = 2 | 3 | 4
+        const char* e_ctas = getenv("ROD_X2I_CTAS");
+        if (e_ctas && atoi(e_ctas) >= 2 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
+#define ROD_X2I_LAUNCH(C, B)                                                                                              \
+    do {                                                                                                                  \
+        ROD_CUDA(cudaFuncSetAttribute(lowres_x2i_kernel<C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        lowres_x2i_kernel<C, B><<<grid_for(plan, ctas, B), 128, smem, lst>>>(p);                                       \
+    } while (0)
+        if (u == 0) {
+            if (per_sm == 2) ROD_X2I_LAUNCH(true, 2);
+            else if (per_sm == 4) ROD_X2I_LAUNCH(true, 4);
+            else ROD_X2I_LAUNCH(true, 3);
+        } else {
+            if (per_sm == 2) ROD_X2I_LAUNCH(false, 2);
+            else if (per_sm == 4) ROD_X2I_LAUNCH(false, 4);
+            else ROD_X2I_LAUNCH(false, 3);
+        }
+#undef ROD_X2I_LAUNCH
+        ROD_CUDA(cudaGetLastError());
     }
     // exact-2x shapes: warp-marching kernel when the rows are 4-byte aligned, full-width strips otherwise
     const int n_packed = plan->n_lowres_x2p_tiles[0] + plan->n_lowres_x2p_tiles[1] + plan->n_lowres_x2p_tiles[2] +
@@ -1546,6 +1960,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             const int t_lo = st[img_lo], t_hi = st[img_hi];
             if (t_hi <= t_lo) continue;
             LowresX2wParams p;
+            const cudaStream_t lst = ls.pick();
             p.images = plan->d_images;
             p.tiles = (kind == 0 ? plan->d_lowres_x2p_tiles[u] : kind == 1 ? plan->d_lowres_x2f_tiles[u] : plan->d_lowres_x2h_tiles[u]) + t_lo;
             p.n_tiles = t_hi - t_lo;
@@ -1553,7 +1968,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.tab = plan->d_tab;
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
-            ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+            ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), lst));
             const int ctas = (p.n_tiles + 3) / 4;
             // measured on a B200 (128 x 1920x1080, packed): 3 CTAs/SM 5.88 TB/s, 4: 5.79, 2: 5.17; knobs ROD_X2P_CTAS / ROD_X2F_CTAS
             int per_sm = kind == 0 ? 3 : 4;  // the float-tap kernel is issue-bound: more warps win (4: 3.69, 3: 3.34, 2: 2.74 TB/s)
@@ -1566,7 +1981,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
 #define ROD_STAGED_LAUNCH(K, U, B)                                                                         \
     do {                                                                                                   \
         ROD_CUDA(cudaFuncSetAttribute(K<U, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        K<U, B><<<grid_for(plan, ctas, B), 128, smem, stream>>>(p);                                        \
+        K<U, B><<<grid_for(plan, ctas, B), 128, smem, lst>>>(p);                                        \
     } while (0)
 #define ROD_STAGED_LAUNCH_B(K, U)                                 \
     do {                                                          \
@@ -1598,6 +2013,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             const int t_lo = st[img_lo], t_hi = st[img_hi];
             if (t_hi <= t_lo) continue;
             LowresX2wParams p;
+            const cudaStream_t lst = ls.pick();
             p.images = plan->d_images;
             p.tiles = tl + t_lo;
             p.n_tiles = t_hi - t_lo;
@@ -1606,13 +2022,13 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             p.src = src; p.dst = dst; p.opcodes = opcodes;
             // a fresh counter per launch (ring of 256): launches of one plan may overlap on different streams
             p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
-            ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+            ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), lst));
             const int ctas = (p.n_tiles + 3) / 4;
             int per_sm = 4;  // benchmark knob: ROD_X2W_CTAS
             const char* e_ctas = getenv("ROD_X2W_CTAS");
             if (e_ctas && atoi(e_ctas) >= 1 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
-            if (pass == 0 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, per_sm), 128, smem, stream>>>(p);
-            else lowres_x2w_kernel<false><<<grid_for(plan, ctas, per_sm), 128, smem, stream>>>(p);
+            if (pass == 0 && (((uintptr_t)src) & 7) == 0) lowres_x2w_kernel<true><<<grid_for(plan, ctas, per_sm), 128, smem, lst>>>(p);
+            else lowres_x2w_kernel<false><<<grid_for(plan, ctas, per_sm), 128, smem, lst>>>(p);
             ROD_CUDA(cudaGetLastError());
         }
     }
@@ -1622,6 +2038,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
         const int t_lo = starts[img_lo], t_hi = starts[img_hi];
         if (t_hi > t_lo) {
             LowresX2Params p;
+            const cudaStream_t lst = ls.pick();
             p.images = plan->d_images;
             p.tiles = tiles + t_lo;
             p.n_tiles = t_hi - t_lo;
@@ -1633,15 +2050,65 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
             ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm;
             if (plan->lowres_x2_threads == 128) {
                 ROD_CUDA(cudaFuncSetAttribute(lowres_x2_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                lowres_x2_kernel<128, 4><<<grid_for(plan, p.n_tiles, ctas_per_sm > 4 ? 4 : ctas_per_sm), 128, smem, stream>>>(p);
+                lowres_x2_kernel<128, 4><<<grid_for(plan, p.n_tiles, ctas_per_sm > 4 ? 4 : ctas_per_sm), 128, smem, lst>>>(p);
             } else {
                 ROD_CUDA(cudaFuncSetAttribute(lowres_x2_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                lowres_x2_kernel<256, 2><<<grid_for(plan, p.n_tiles, ctas_per_sm > 2 ? 2 : ctas_per_sm), 256, smem, stream>>>(p);
+                lowres_x2_kernel<256, 2><<<grid_for(plan, p.n_tiles, ctas_per_sm > 2 ? 2 : ctas_per_sm), 256, smem, lst>>>(p);
             }
             ROD_CUDA(cudaGetLastError());
         }
     }
     return ROD_OK;
+}
+}  // namespace
+
+int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes,
+                  cudaStream_t stream, int img_lo, int img_hi) {
+    auto in_range = [&](int n, const std::vector<int>& st) { return n > 0 && st[img_hi] > st[img_lo]; };
+    int n_lists = in_range(plan->n_lowres_tiles, plan->lowres_tile_start) + in_range(plan->n_lowres_x2g_tiles, plan->lowres_x2g_tile_start) +
+                  in_range(plan->n_lowres_x2w_tiles, plan->lowres_x2w_tile_start) + in_range(plan->n_lowres_x2w4_tiles, plan->lowres_x2w4_tile_start) +
+                  in_range(plan->n_lowres_x2_rest_tiles, plan->lowres_x2_rest_tile_start);
+    for (int u = 0; u < 3; ++u)
+        n_lists += in_range(plan->n_lowres_x2p_tiles[u], plan->lowres_x2p_tile_start[u]) + in_range(plan->n_lowres_x2f_tiles[u], plan->lowres_x2f_tile_start[u]) +
+                   in_range(plan->n_lowres_x2h_tiles[u], plan->lowres_x2h_tile_start[u]);
+    for (int u = 0; u < 2; ++u) n_lists += in_range(plan->n_lowres_x2i_tiles[u], plan->lowres_x2i_tile_start[u]);
+    const char* e_conc = getenv("ROD_LOWRES_CONCURRENT");
+    LrStreams ls;
+    ls.s[0] = stream; ls.s[1] = ls.s[2] = nullptr;
+    ls.n = 1; ls.i = 0;
+    if (n_lists < 2 || (e_conc && atoi(e_conc) == 0)) return launch_lowres_lists(plan, src, dst, opcodes, ls, img_lo, img_hi);
+    // the fork / join of one call must not interleave with another host thread's on the same plan
+    std::lock_guard<std::mutex> lock(plan->lr_mutex);
+    if (plan->lr_ev_fork == nullptr) {  // created as a whole or not at all
+        cudaStream_t s2[2] = {nullptr, nullptr};
+        cudaEvent_t ef = nullptr, ej[2] = {nullptr, nullptr};
+        cudaError_t e = cudaSuccess;
+        for (auto& s : s2)
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ef, cudaEventDisableTiming);
+        for (auto& ev : ej)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            for (auto& s : s2) if (s) cudaStreamDestroy(s);
+            if (ef) cudaEventDestroy(ef);
+            for (auto& ev : ej) if (ev) cudaEventDestroy(ev);
+            return cuda_fail(e);
+        }
+        plan->lr_streams[0] = s2[0]; plan->lr_streams[1] = s2[1];
+        plan->lr_ev_join[0] = ej[0]; plan->lr_ev_join[1] = ej[1];
+        plan->lr_ev_fork = ef;
+    }
+    ROD_CUDA(cudaEventRecord(plan->lr_ev_fork, stream));
+    for (auto& s : plan->lr_streams) ROD_CUDA(cudaStreamWaitEvent(s, plan->lr_ev_fork, 0));
+    ls.s[1] = plan->lr_streams[0]; ls.s[2] = plan->lr_streams[1];
+    ls.n = 3;
+    int rc = launch_lowres_lists(plan, src, dst, opcodes, ls, img_lo, img_hi);
+    for (int i = 0; i < 2; ++i) {  // the join is executed on every path
+        cudaError_t e = cudaEventRecord(plan->lr_ev_join[i], plan->lr_streams[i]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, plan->lr_ev_join[i], 0);
+        if (e != cudaSuccess && rc == ROD_OK) rc = cuda_fail(e);
+    }
+    return rc;
 }
 
 }  // namespace rod

@@ -117,7 +117,9 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
         const DevShape& sh = shapes[plan->h_images[i].shape_id];
         return x2g_on && sh.x2g != 0 && (sh.h <= 8 || 4LL * sh.h <= 9LL * sh.nh);
     };
-    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles, x2p_tiles[3], x2f_tiles[3], x2h_tiles[3], x2g_tiles, gen_all;
+    const char* e_x2i = getenv("ROD_X2_ODD_REGULAR");
+    const bool x2i_on = !(e_x2i && atoi(e_x2i) == 0);
+    std::vector<Tile> gen_tiles, x2_tiles, x2w_tiles, x2w4_tiles, x2_rest_tiles, x2p_tiles[3], x2f_tiles[3], x2h_tiles[3], x2g_tiles, x2i_tiles[2], gen_all;
     build_strip_tiles(plan->h_images, shapes, false, kLowresTH, kLowresTWB, gen_all);
     for (const Tile& t : gen_all)
         if (!odd_image(t.img)) gen_tiles.push_back(t);
@@ -134,9 +136,10 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     for (int i = 0; i < plan->n_images; ++i) {
         const DevShape& sh = shapes[plan->h_images[i].shape_id];
         if (odd_image(i)) {
+            std::vector<Tile>& list = (x2i_on && sh.x2i != 0) ? x2i_tiles[sh.x2i - 1] : x2g_tiles;
             for (int y = 0; y < plan->h_images[i].h; y += band_rows_odd)
                 for (int st = 0; st < n_strips(plan->h_images[i].w); ++st)
-                    x2g_tiles.push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows_odd), st});
+                    list.push_back(Tile{i, y, std::min(plan->h_images[i].h, y + band_rows_odd), st});
             continue;
         }
         if (sh.strip_rows <= 0) continue;
@@ -151,7 +154,8 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     void* old[] = {plan->d_shapes, plan->d_tab, plan->d_lowres_tiles, plan->d_lowres_x2_tiles, plan->d_lowres_x2w_tiles, plan->d_lowres_x2w4_tiles,
                    plan->d_lowres_x2_rest_tiles, plan->d_lowres_x2p_tiles[0], plan->d_lowres_x2p_tiles[1], plan->d_lowres_x2p_tiles[2],
                    plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2], plan->d_lowres_x2g_tiles,
-                   plan->d_lowres_x2h_tiles[0], plan->d_lowres_x2h_tiles[1], plan->d_lowres_x2h_tiles[2]};
+                   plan->d_lowres_x2h_tiles[0], plan->d_lowres_x2h_tiles[1], plan->d_lowres_x2h_tiles[2],
+                   plan->d_lowres_x2i_tiles[0], plan->d_lowres_x2i_tiles[1]};
     for (void* q : old)
         if (q) cudaFree(q);
     plan->d_shapes = nullptr; plan->d_tab = nullptr; plan->d_lowres_tiles = nullptr; plan->d_lowres_x2_tiles = nullptr;
@@ -159,6 +163,10 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     int rc = upload(shapes, &plan->d_shapes);
     plan->d_lowres_x2g_tiles = nullptr;
     if (rc == ROD_OK) rc = upload(x2g_tiles, &plan->d_lowres_x2g_tiles);
+    for (int u = 0; u < 2; ++u) {
+        plan->d_lowres_x2i_tiles[u] = nullptr;
+        if (rc == ROD_OK) rc = upload(x2i_tiles[u], &plan->d_lowres_x2i_tiles[u]);
+    }
     for (int u = 0; u < 3; ++u) {
         plan->d_lowres_x2p_tiles[u] = nullptr;
         if (rc == ROD_OK) rc = upload(x2p_tiles[u], &plan->d_lowres_x2p_tiles[u]);
@@ -180,6 +188,10 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
     plan->n_lowres_x2w4_tiles = (int)x2w4_tiles.size();
     plan->n_lowres_x2g_tiles = (int)x2g_tiles.size();
     tile_starts(x2g_tiles, plan->n_images, plan->lowres_x2g_tile_start);
+    for (int u = 0; u < 2; ++u) {
+        plan->n_lowres_x2i_tiles[u] = (int)x2i_tiles[u].size();
+        tile_starts(x2i_tiles[u], plan->n_images, plan->lowres_x2i_tile_start[u]);
+    }
     for (int u = 0; u < 3; ++u) {
         plan->n_lowres_x2p_tiles[u] = (int)x2p_tiles[u].size();
         tile_starts(x2p_tiles[u], plan->n_images, plan->lowres_x2p_tile_start[u]);
@@ -387,6 +399,7 @@ extern "C" void rod_plan_destroy(rod_plan* plan) {
                     plan->d_lowres_x2p_tiles[0], plan->d_lowres_x2p_tiles[1], plan->d_lowres_x2p_tiles[2],
                     plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2], plan->d_lowres_x2g_tiles,
                     plan->d_lowres_x2h_tiles[0], plan->d_lowres_x2h_tiles[1], plan->d_lowres_x2h_tiles[2],
+                    plan->d_lowres_x2i_tiles[0], plan->d_lowres_x2i_tiles[1],
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
                     plan->d_f2d_taps, plan->d_f2d_tiles, plan->d_counters,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};
@@ -396,6 +409,11 @@ extern "C" void rod_plan_destroy(rod_plan* plan) {
         if (s) cudaStreamDestroy(s);
     for (cudaStream_t s : plan->aux_streams)
         if (s) cudaStreamDestroy(s);
+    for (cudaStream_t s : plan->lr_streams)
+        if (s) cudaStreamDestroy(s);
+    if (plan->lr_ev_fork) cudaEventDestroy(plan->lr_ev_fork);
+    for (cudaEvent_t e : plan->lr_ev_join)
+        if (e) cudaEventDestroy(e);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     for (cudaEvent_t e : plan->ev_join)
         if (e) cudaEventDestroy(e);

@@ -71,6 +71,7 @@ struct DevShape {
     int32_t x2g;                // 1: odd width at factor 0.5 with the regular 3-tap / one-slip structure (lowres_x2g_kernel)
     uint32_t hy_pack;           // uint4 per low-res row {beta0, beta1, beta2, r0 | nA << 16 | nB << 24}: lowres_x2h_kernel
     int32_t x2h;                // 1: exact-2x width whose low-res row j has the three y taps 2j, 2j+1, 2j+2 (h = 2 nh + 1)
+    int32_t x2i;                // odd width (x2g) with a regular y axis: 1 = taps 2j, 2j+1, 2j+2 (odd h), 2 = taps 2j, 2j+1 (even h)
 };
 
 // ---------------------------------------------------------------------------------
@@ -764,6 +765,28 @@ ROD_HD void x2g_hrow(const uint32_t w[7], const float al[12], float hb[12]) {
             const float t0 = fmaf(x[6 * p + c], al[3 * p], n0);
             const float t1 = fmaf(x[6 * p + 3 + c], al[3 * p + 1], n1);
             const float t2 = fmaf(x[6 * p + 6 + c], al[3 * p + 2], n2);
+            hb[3 * p + c] = fadd(fadd(t0, t1), t2);
+        }
+    }
+}
+// The same with the products -2^23 * weight supplied (nal[i] = fmul(al[i], -8388608.0f): constant per lane and tile).
+ROD_HD void x2g_hrow_pre(const uint32_t w[7], const float al[12], const float nal[12], float hb[12]) {
+    float x[27];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 27; ++i) x[i] = byte_magic(w, i);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int p = 0; p < 4; ++p) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int c = 0; c < 3; ++c) {
+            const float t0 = fmaf(x[6 * p + c], al[3 * p], nal[3 * p]);
+            const float t1 = fmaf(x[6 * p + 3 + c], al[3 * p + 1], nal[3 * p + 1]);
+            const float t2 = fmaf(x[6 * p + 6 + c], al[3 * p + 2], nal[3 * p + 2]);
             hb[3 * p + c] = fadd(fadd(t0, t1), t2);
         }
     }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/rod_b200.h"
@@ -87,6 +88,10 @@ struct rod_plan {
     rod::Tile* d_lowres_x2g_tiles = nullptr;
     int n_lowres_x2g_tiles = 0;
     std::vector<int> lowres_x2g_tile_start;
+    // ... of those, the shapes with a regular y axis (DevShape::x2i = 1: odd h, [0]; 2: even h, [1]): lowres_x2i_kernel
+    rod::Tile* d_lowres_x2i_tiles[2] = {nullptr, nullptr};
+    int n_lowres_x2i_tiles[2] = {0, 0};
+    std::vector<int> lowres_x2i_tile_start[2];
     int n_lowres_x2w_tiles = 0, n_lowres_x2_rest_tiles = 0;
     std::vector<int> lowres_x2w_tile_start, lowres_x2_rest_tile_start;
     int lowres_x2w_band_rows = 0;
@@ -138,6 +143,10 @@ struct rod_plan {
     // fork/join of the per-op kernels of a mixed batch (small batches do not fill the GPU one op at a time)
     cudaStream_t aux_streams[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    // fork/join of the LowRes launches of one call (several tile lists: lowres.cu launch_lowres); created on first use
+    mutable std::mutex lr_mutex;
+    mutable cudaStream_t lr_streams[2] = {nullptr, nullptr};
+    mutable cudaEvent_t lr_ev_fork = nullptr, lr_ev_join[2] = {nullptr, nullptr};
 };
 
 namespace rod {

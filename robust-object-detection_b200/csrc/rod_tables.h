@@ -156,6 +156,33 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
         sh.lx_a = blob_push(blob, lx.coef);
         sh.ly_s = blob_push(blob, ys);
         sh.ly_b = blob_push(blob, ly.coef);
+        // Row schedule of the kernels that loop over LOW-RES rows (lowres_x2h_kernel, lowres_x2i_kernel), one uint4 per
+        // low-res row j: {beta0, beta1, beta2, r0 | nA << 16 | nB << 24}.  Once row j exists, the output rows whose lower
+        // tap row is j leave: first the nA rows that blend (j-1, j), then the nB rows that blend (j, j) (top and bottom of
+        // the image only); r0 is the first of them.  Requires the regular y taps first[j] = 2j, count[j] = taps.
+        auto build_row_schedule = [&](int taps) -> bool {
+            if (sh.hy_pack != 0) return true;
+            if (sh.area_mode != AREA_GENERAL || !sh.ay_packed || h < taps) return false;
+            const int32_t* yf = (const int32_t*)(blob.data() + sh.ay_first);
+            const int32_t* yc = (const int32_t*)(blob.data() + sh.ay_count);
+            for (int j = 0; j < sh.nh; ++j)
+                if (yf[j] != 2 * j || yc[j] != taps || 2 * j + taps - 1 > h - 1) return false;
+            std::vector<uint32_t> hp((size_t)sh.nh * 4, 0u);
+            int r = 0;
+            for (int j = 0; j < sh.nh; ++j) {
+                const int r0 = r;
+                int na = 0, nb = 0;
+                while (r < h && ly.s1[r] == j && ly.s0[r] == j - 1) { ++na; ++r; }
+                while (r < h && ly.s1[r] == j && ly.s0[r] == j) { ++nb; ++r; }
+                if (na > 255 || nb > 255 || r0 > 65535) return false;
+                const uint32_t* pk = blob.data() + sh.ay_pack + 4 * (size_t)j;
+                hp[4 * j] = pk[1]; hp[4 * j + 1] = pk[2]; hp[4 * j + 2] = pk[3];
+                hp[4 * j + 3] = (uint32_t)r0 | ((uint32_t)na << 16) | ((uint32_t)nb << 24);
+            }
+            if (r != h) return false;
+            sh.hy_pack = blob_push(blob, hp);
+            return true;
+        };
         // odd widths at factor 0.5 (lowres_x2g_kernel): every low-res column has the three x taps 2dx, 2dx+1, 2dx+2; even
         // output pixels x blend low-res (x/2 - 1, x/2), odd ones ((x-1)/2, +1) or, from the slip column on, ((x-1)/2 - 1, +1)
         if (sh.area_mode == AREA_GENERAL && sh.ay_packed && sh.xt == 3 && w == 2 * sh.nw + 1 && sh.nw >= 1 && h >= 2) {
@@ -175,6 +202,8 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
                 }
                 sh.ly_rc3 = blob_push(blob, rc3);
                 sh.x2g = 1;
+                if (build_row_schedule(3)) sh.x2i = 1;
+                else if (build_row_schedule(2)) sh.x2i = 2;
             }
         }
         if (sh.x2) {  // vertical-stage constants of the exact-2x kernels, one float4 per output row
@@ -204,31 +233,8 @@ inline bool build_lowres_shape(int h, int w, double factor, int max_taps, std::v
             }
             sh.x2p = packed ? 1 : 0;
             // regular three-tap kernel (lowres_x2h_kernel): low-res row j reads source rows 2j, 2j+1, 2j+2 (every h = 2 nh + 1
-            // up to ~2000), so row 2j+2 is shared with row j+1 and the source rows can be staged as fixed pairs.  Its row
-            // schedule: after low-res row j exists, the output rows whose lower tap row is j leave -- first those that blend
-            // (j-1, j) [nA of them], then those that blend (j, j) [nB: only at the top and bottom of the image].
-            if (sh.x2w && sh.area_mode == AREA_GENERAL && sh.ay_packed && sh.yt == 3 && h >= 3) {
-                const int32_t* yf = (const int32_t*)(blob.data() + sh.ay_first);
-                const int32_t* yc = (const int32_t*)(blob.data() + sh.ay_count);
-                bool ok = true;
-                for (int j = 0; j < sh.nh && ok; ++j) ok = (yf[j] == 2 * j && yc[j] == 3 && 2 * j + 2 <= h - 1);
-                std::vector<uint32_t> hp((size_t)sh.nh * 4, 0u);
-                int r = 0;
-                for (int j = 0; j < sh.nh && ok; ++j) {
-                    const int r0 = r;
-                    int na = 0, nb = 0;
-                    while (r < h && ly.s1[r] == j && ly.s0[r] == j - 1) { ++na; ++r; }
-                    while (r < h && ly.s1[r] == j && ly.s0[r] == j) { ++nb; ++r; }
-                    ok = (na < 256 && nb < 256 && r0 < 65536);
-                    const uint32_t* pk = blob.data() + sh.ay_pack + 4 * (size_t)j;
-                    hp[4 * j] = pk[1]; hp[4 * j + 1] = pk[2]; hp[4 * j + 2] = pk[3];
-                    hp[4 * j + 3] = (uint32_t)r0 | ((uint32_t)na << 16) | ((uint32_t)nb << 24);
-                }
-                if (ok && r == h) {
-                    sh.hy_pack = blob_push(blob, hp);
-                    sh.x2h = 1;
-                }
-            }
+            // up to ~2000), so row 2j+2 is shared with row j+1 and the source rows can be staged as fixed pairs
+            if (sh.x2w && sh.area_mode == AREA_GENERAL && sh.ay_packed && build_row_schedule(3)) sh.x2h = 1;
         }
     }
     *out = sh;

@@ -681,6 +681,115 @@ extern "C" int emu_lowres_x2g(const uint8_t* src, uint8_t* dst, int h, int w, lo
     return 0;
 }
 
+// Replays lowres_x2i_kernel (odd widths with a regular y axis): lowres_x2g_kernel's per-lane arithmetic inside the loop over
+// LOW-RES rows -- fixed source-row pairs (odd h: rows 2j+1, 2j+2 with row 2j's horizontal pass carried; even h: rows 2j,
+// 2j+1) and the emission schedule of DevShape::hy_pack clipped to the band.  Returns 3 if the shape is not eligible.
+extern "C" int emu_lowres_x2i(const uint8_t* src, uint8_t* dst, int h, int w, long src_pitch, long dst_pitch, int band_rows) {
+    std::vector<uint32_t> blob;
+    DevShape sh;
+    if (!build_lowres_shape(h, w, 0.5, 8, blob, &sh)) return 2;
+    if (!sh.x2g || !sh.x2i) return 3;
+    const bool carry_mode = sh.x2i == 1;
+    const uint32_t* tab = blob.data();
+    const int n = 3 * w, nw = sh.nw;
+    const uint32_t* hyp = tab + sh.hy_pack;
+    const uint32_t* ly_s = tab + sh.ly_s;
+    const float* ly_rc = (const float*)(tab + sh.ly_rc3);
+    const float* xalpha = (const float*)(tab + sh.ax_alpha);
+    const int32_t* lx_s0 = (const int32_t*)(tab + sh.lx_s0);
+    const uint32_t* lx_a = tab + sh.lx_a;
+    const int nchunks = (w + 7) >> 3, nstrips = (nchunks + 29) / 30;
+    for (int Y0 = 0; Y0 < h; Y0 += band_rows)
+        for (int st = 0; st < nstrips; ++st) {
+            const int Y1 = std::min(h, Y0 + band_rows);
+            const int j_first = (int)(ly_s[Y0] & 0xFFFFu), j_last = (int)(ly_s[Y1 - 1] >> 16);
+            float xe[32][24], xo[32][24], carry[32][12];
+            for (int l = 0; l < 32; ++l) for (int q = 0; q < 24; ++q) xe[l][q] = xo[l][q] = -1e30f;
+            auto hrow = [&](int l, int row, float out[12]) {
+                const int cc = std::min(std::max(30 * st - 1 + l, 0), nchunks - 1);
+                float al[12];
+                for (int q = 0; q < 4; ++q)
+                    for (int tp = 0; tp < 3; ++tp) al[3 * q + tp] = xalpha[3 * std::min(4 * cc + q, nw - 1) + tp];
+                uint8_t win[28];
+                for (int k = 0; k < 28; ++k) {
+                    const int col = 24 * cc + k;
+                    win[k] = col < n ? src[(long)row * src_pitch + col] : (uint8_t)0xEE;  // beyond the row: garbage
+                }
+                uint32_t wn[7];
+                memcpy(wn, win, 28);
+                x2g_hrow(wn, al, out);
+            };
+            if (carry_mode)
+                for (int l = 0; l < 32; ++l) hrow(l, 2 * j_first, carry[l]);
+            int r = Y0;
+            for (int j = j_first; j <= j_last; ++j) {
+                const uint32_t* hp = hyp + 4 * j;
+                if ((carry_mode ? 2 * j + 2 : 2 * j + 1) > h - 1) return 5;
+                uint32_t own[32][3];
+                for (int l = 0; l < 32; ++l) {
+                    float acc[12], ha[12];
+                    if (carry_mode) {
+                        x2g_vmac(carry[l], bitsf(hp[0]), true, acc);
+                        hrow(l, 2 * j + 1, ha);
+                        x2g_vmac(ha, bitsf(hp[1]), false, acc);
+                        hrow(l, 2 * j + 2, carry[l]);
+                        x2g_vmac(carry[l], bitsf(hp[2]), false, acc);
+                    } else {
+                        hrow(l, 2 * j, ha);
+                        x2g_vmac(ha, bitsf(hp[0]), true, acc);
+                        hrow(l, 2 * j + 1, ha);
+                        x2g_vmac(ha, bitsf(hp[1]), false, acc);
+                    }
+                    x2g_round12(acc, own[l]);
+                }
+                uint32_t from_left[32];
+                for (int l = 0; l < 32; ++l) from_left[l] = own[l > 0 ? l - 1 : l][2];
+                for (int l = 0; l < 32; ++l) {
+                    const int cc = std::min(std::max(30 * st - 1 + l, 0), nchunks - 1);
+                    const int valid = nw - 4 * cc;
+                    if (valid < 4) x2g_replicate(own[l], std::max(valid, 0), from_left[l]);
+                }
+                float (*xnew)[24] = (j & 1) ? xo : xe;
+                float (*xprev)[24] = (j & 1) ? xe : xo;
+                for (int l = 0; l < 32; ++l) {
+                    const int cc = std::min(std::max(30 * st - 1 + l, 0), nchunks - 1);
+                    uint32_t coef[8], slip = 0;
+                    for (int x = 0; x < 8; ++x) {
+                        const int xa = std::min(8 * cc + x, w - 1);
+                        coef[x] = lx_a[xa];
+                        if ((x & 1) && lx_s0[xa] == ((xa - 1) >> 1) - 1) slip |= 1u << (x >> 1);
+                    }
+                    const uint32_t from_right = own[l < 31 ? l + 1 : l][0];
+                    const uint32_t w0 = (cc == 0) ? (own[l][0] << 8) : (from_left[l] & 0xFFFFFF00u);
+                    const uint32_t w4 = (cc == nchunks - 1) ? (own[l][2] >> 8) : (from_right & 0x00FFFFFFu);
+                    const uint32_t win[5] = {funnel_r(w0, own[l][0], 8), funnel_r(own[l][0], own[l][1], 8),
+                                             funnel_r(own[l][1], own[l][2], 8), funnel_r(own[l][2], w4, 8), w4 >> 8};
+                    x2g_expand24(win, coef, slip, xnew[l]);
+                }
+                const int r0 = (int)(hp[3] & 0xFFFFu), ra_end = r0 + (int)((hp[3] >> 16) & 0xFFu), rb_end = ra_end + (int)(hp[3] >> 24);
+                const int a_end = std::min(ra_end, Y1), b_end = std::min(rb_end, Y1);
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int end = pass == 0 ? a_end : b_end;
+                    for (; r < end; ++r) {
+                        if (r < r0) return 6;
+                        X2Row rc;
+                        rc.c0s = ly_rc[4 * r]; rc.c1s = ly_rc[4 * r + 1]; rc.k0 = ly_rc[4 * r + 2]; rc.k2 = ly_rc[4 * r + 3];
+                        for (int l = 1; l <= 30; ++l) {
+                            const int ch = 30 * st - 1 + l;
+                            if (ch < 0 || ch >= nchunks) continue;
+                            const int nvalid = std::min(24, n - 24 * ch);
+                            const float* xlo = pass == 0 ? xprev[l] : xnew[l];
+                            for (int q = 0; q < nvalid; ++q)
+                                dst[(long)r * dst_pitch + 24 * ch + q] = (uint8_t)(x2_vertical(xlo[q], xnew[l][q], rc) & 0xFFu);
+                        }
+                    }
+                }
+            }
+            if (r != Y1) return 7;
+        }
+    return 0;
+}
+
 // Replays lowres_x2p_kernel (packed-integer pipeline for shapes that are exact 2x in both axes): the same band x strip
 // tiles and 32-lane strips as lowres_x2w_kernel; per low-res row every lane forms its packed words (rod_core.h x2p_*),
 // the neighbour words arrive by "shuffle" (lane 0 / 31 get their own value back, like shfl.up / shfl.down).

@@ -344,6 +344,32 @@ X2P_SHAPES = [(360, 480), (100, 8), (2, 4), (4, 4), (64, 64), (130, 36), (200, 1
 
 
 @pytest.mark.parametrize("band_rows", [24, 56, 512])
+def test_emu_lowres_odd_width_regular_kernel(emu, band_rows):
+    """lowres_x2i_kernel: the odd-width arithmetic inside the loop over low-res rows (odd heights: carried tap row; even
+    heights: two fresh tap rows) with the per-low-res-row emission schedule, replayed on the CPU against the oracle."""
+    emu.emu_lowres_x2i.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_long, ctypes.c_long, ctypes.c_int]
+    n_carry = n_plain = 0
+    for i, (h, w) in enumerate(X2G_SHAPES):
+        img = synth(1100 + i, h, w)
+        if i % 2:
+            img = (img > 127).astype(np.uint8) * 255
+        pitch = 3 * w + (0 if i % 3 else 13)
+        buf = np.full((h, pitch), 0xAB, np.uint8)
+        buf[:, :3 * w] = img.reshape(h, 3 * w)
+        got = np.full_like(img, 0x5A)
+        rc = emu.emu_lowres_x2i(_p(buf), _p(got), h, w, pitch, 3 * w, band_rows)
+        if rc == 3:
+            continue
+        assert rc == 0, (h, w, rc)
+        want = orc.apply_lowres(img, 0.5)
+        assert np.array_equal(got, want), (h, w, band_rows, int((got != want).sum()))
+        n_carry += h % 2
+        n_plain += 1 - h % 2
+    assert n_carry >= 5 and n_plain >= 5
+
+
+@pytest.mark.parametrize("band_rows", [24, 56, 512])
 def test_emu_lowres_packed_kernel(emu, band_rows):
     """lowres_x2p_kernel (even w and h: the all-integer packed pipeline) replayed lane by lane on the CPU against the
     oracle: halo lanes, neighbour words by shuffle, border replication, two-pixel last chunks (w % 8 == 4), band

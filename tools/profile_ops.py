@@ -9,7 +9,7 @@ import torch
 
 from robust_object_detection_b200.batch import CorruptionPlan, draw_decisions
 
-n, h, w = 64, 765, 1360
+n, h, w = int(os.environ.get("ROD_PROFILE_N", "64")), 765, 1360
 torch.cuda.set_device(0)
 src = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
 dst = torch.empty_like(src)

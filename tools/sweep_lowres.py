@@ -36,11 +36,18 @@ WORKLOADS = {
     "1999x1499_x48": [(1499, 1999)] * 48,
     "1917x1080_x64": [(1080, 1917)] * 64,
     "1920x1080_x128": [(1080, 1920)] * 128,
+    "1400x1050_x96": [(1050, 1400)] * 96,
+    "1400x788_x128": [(788, 1400)] * 128,
+    "1916x1078_x64": [(1078, 1916)] * 64,
+    "2000x1500_x48": [(1500, 2000)] * 48,
+    "960x540_x256": [(540, 960)] * 256,
+    "480x360_x512": [(360, 480)] * 512,
+    "visdrone_256": [POOL[i] for i in np.random.default_rng(3001).integers(0, 8, 256)],
     "mixed_256": [POOL[i] for i in np.random.default_rng(3000).integers(0, len(POOL), 256)],
     "odd_only_96": [POOL[8 + i % 3] for i in range(96)],
 }
 KNOBS = ("ROD_X2_PACKED", "ROD_X2P_CTAS", "ROD_X2_FLOAT_STAGED", "ROD_X2F_CTAS", "ROD_X2_ODD_STAGED", "ROD_X2G_CTAS",
-         "ROD_X2G_BAND_DIV", "ROD_X2_REGULAR", "ROD_X2H_CTAS", "ROD_X2_BAND")
+         "ROD_X2G_BAND_DIV", "ROD_X2_REGULAR", "ROD_X2H_CTAS", "ROD_X2_BAND", "ROD_X2_ODD_REGULAR", "ROD_X2I_CTAS")
 
 # usage: sweep_lowres.py <workload,workload,...> <name:K=V,K=V> <name:K=V> ...   (a bare "name:" is the default setting)
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else list(WORKLOADS)
