@@ -453,6 +453,187 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox_kernel(Fused
     }
 }
 
+// =====================================================================================
+// Version 2 of the fused training path (even out_w): the same row producers, but
+//   * every WARP takes single output rows from the counter on its own (no block barrier, no per-CTA table): rows are handed
+//     out centre-out and image-minor, so the expensive rows (content of noise / blur / LowRes images) of all images run
+//     first, spread evenly, and the cheap padding rows fill the tail;
+//   * the resampling loop makes two adjacent output columns per lane and step: x taps from a per-shape table in global
+//     memory (one 16-byte load through L1), the horizontal stage as dp2a onto the 2^23 float grid, the vertical stage as the
+//     three round-toward-zero FMAs of the resize kernels, half(v / 255) as one more FMA (== the 256-entry table of
+//     version 1 for every byte value) and a packed half2 conversion; three 4-byte stores per step;
+//   * padding rows leave as 16-byte stores.
+// Version 1 spent 55 % of its instructions in the resampling loop (~95 per output column; here ~50).
+// =====================================================================================
+__device__ __forceinline__ void fused_column(const uint8_t* bufA, const uint8_t* rowB, uint32_t o3, uint32_t a, const X2Row& rc,
+                                             float c255, float nc255, float out[3]) {
+    uint32_t lo0, hi0, lo1, hi1;
+    load6_smem(bufA, (int)o3, lo0, hi0);
+    load6_smem(rowB, (int)o3, lo1, hi1);
+    // at the right border both taps are the last pixel: OpenCV's coefficients there are (2048, 0), so whatever the second
+    // tap reads (row padding) is multiplied by zero
+    const uint32_t g0[3] = {__byte_perm(lo0, hi0, 0x4430), __byte_perm(lo0, hi0, 0x4441), __byte_perm(lo0, hi0, 0x4452)};
+    const uint32_t g1[3] = {__byte_perm(lo1, hi1, 0x4430), __byte_perm(lo1, hi1, 0x4441), __byte_perm(lo1, hi1, 0x4452)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // 2^23 + H (H = tap0 * a0 + tap1 * a1 < 2^23) -> 2^23 + (H >> 4): one multiply-add rounded toward zero
+        const float x0 = __fmaf_rz(__uint_as_float(dot2_lo(a, g0[c], 0x4B000000u)), 0.0625f, 7864320.0f);
+        const float x1 = __fmaf_rz(__uint_as_float(dot2_lo(a, g1[c], 0x4B000000u)), 0.0625f, 7864320.0f);
+        const float y = __uint_as_float(x2_vertical(x0, x1, rc));   // 2^23 + v
+        out[c] = __fmaf_rn(y, c255, nc255);                          // fl(v * fl(1 / 255)); its half is half(float(v) / 255.f)
+    }
+}
+
+constexpr int kFusedMaxSorted = 256;   // batches up to this size are walked most-expensive-op first
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox2_kernel(FusedLbParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // image order: by op class, the most expensive rows first (noise, LowRes, blur, clean), so that the cheap rows fill
+    // the tail of the launch; every CTA derives the same permutation from the op-codes
+    uint16_t* perm = reinterpret_cast<uint16_t*>(smem);   // [kFusedMaxSorted] + class starts
+    int* cls = reinterpret_cast<int*>(smem + 2 * kFusedMaxSorted);   // cls[c] = first sorted position of class c, cls[4] = n
+    const bool sorted = p.n_images <= kFusedMaxSorted;
+    if (sorted) {
+        auto rank_of = [](int op) { return op == ROD_OP_NOISE ? 0 : op == ROD_OP_LOWRES ? 1 : op == ROD_OP_BLUR ? 2 : 3; };
+        for (int i = threadIdx.x; i < p.n_images; i += 32 * NW) {
+            const int r = rank_of(p.opcodes[i]);
+            int pos = 0;
+            for (int j = 0; j < p.n_images; ++j) {
+                const int rj = rank_of(p.opcodes[j]);
+                pos += (rj < r || (rj == r && j < i)) ? 1 : 0;
+            }
+            perm[pos] = (uint16_t)i;
+        }
+        if (threadIdx.x < 5) {
+            int c = 0;
+            for (int j = 0; j < p.n_images; ++j) c += rank_of(p.opcodes[j]) < (int)threadIdx.x ? 1 : 0;
+            cls[threadIdx.x] = c;
+        }
+    }
+    __syncthreads();
+    const size_t buf0 = 2 * kFusedMaxSorted + 32;
+    uint8_t* X0 = smem + buf0 + (size_t)warp * (3 * p.buf_bytes) + kFusedLeft;   // three identical row buffers per warp: [kFusedLeft | row | 64]
+    uint8_t* X1 = X0 + p.buf_bytes;
+    uint8_t* X2 = X1 + p.buf_bytes;
+    const size_t plane = (size_t)p.out_h * p.out_w;
+    const float c255 = __fdiv_rn(1.0f, 255.0f), nc255 = -8388608.0f * c255;
+    const float padf = __fmul_rn((float)p.pad, c255);
+    const __half2 pad2 = __floats2half2_rn(padf, padf);
+    const int total = p.n_images * p.out_h, mid = p.out_h >> 1;
+    const int half_w = p.out_w >> 1;
+    int ti = 0;
+    if (lane == 0) ti = (int)atomicAdd(p.counter, 1u);
+    ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+    while (ti < total) {
+        int ti_next = 0;
+        if (lane == 0) ti_next = (int)atomicAdd(p.counter, 1u);   // the next row's index arrives while this row is processed
+        // row order inside a class block: centre-out (mid, mid-1, mid+1, ...: a bijection onto [0, out_h)), image-minor
+        int img, kk;
+        if (sorted) {
+            const int c1 = cls[1] * p.out_h, c2 = cls[2] * p.out_h, c3 = cls[3] * p.out_h;
+            const int c = (ti >= c1) + (ti >= c2) + (ti >= c3);
+            const int first = cls[c], cnt = cls[c + 1] - first;
+            const int local = ti - first * p.out_h;
+            kk = local / cnt;
+            img = perm[first + (local - kk * cnt)];
+        } else {
+            kk = ti / p.n_images;
+            img = ti - kk * p.n_images;
+        }
+        const int d = (kk + 1) >> 1;
+        const int Y = (kk & 1) ? mid - d : mid + d;
+        const DevImage im = p.images[img];
+        const DevLetterbox g = p.lb[im.shape_id];
+        __half* orow = p.out + (size_t)img * 3 * plane + (size_t)Y * p.out_w;
+        const int cy = Y - g.top;
+        if (cy < 0 || cy >= g.new_h) {
+            if ((p.out_w & 7) == 0 && (((uintptr_t)p.out) & 15) == 0) {
+                const uint32_t pw = *reinterpret_cast<const uint32_t*>(&pad2);
+                const uint4 v = make_uint4(pw, pw, pw, pw);
+                for (int q = lane; q < (p.out_w >> 3); q += 32) {
+                    reinterpret_cast<uint4*>(orow)[q] = v;
+                    reinterpret_cast<uint4*>(orow + plane)[q] = v;
+                    reinterpret_cast<uint4*>(orow + 2 * plane)[q] = v;
+                }
+            } else {
+                for (int q = lane; q < half_w; q += 32) {
+                    reinterpret_cast<__half2*>(orow)[q] = pad2;
+                    reinterpret_cast<__half2*>(orow + plane)[q] = pad2;
+                    reinterpret_cast<__half2*>(orow + 2 * plane)[q] = pad2;
+                }
+            }
+            ti = __shfl_sync(0xFFFFFFFFu, ti_next, 0);
+            continue;
+        }
+        const int op = p.opcodes[img];
+        const bool lowres_here = (op == ROD_OP_LOWRES) && p.lowres_in_kernel != 0 && p.shapes[im.shape_id].lin_identity == 0;
+        const bool pre = (op == ROD_OP_LOWRES) && p.lowres_in_kernel == 0;
+        const uint8_t* base = pre ? p.scratch + im.dst_off : p.src + im.src_off;
+        const int64_t pitch = pre ? im.dst_pitch : im.src_pitch;
+        const uint32_t ys = p.tab[g.ly_s + cy], yb = p.tab[g.ly_b + cy];
+        const int r0 = (int)(ys & 0xFFFFu), r1 = (int)(ys >> 16);
+        const int n = 3 * im.w;
+        const bool two = (r1 != r0);
+        const bool blur = (op == ROD_OP_BLUR);
+        const uint4* xt = reinterpret_cast<const uint4*>(p.tab + g.lx_pack);
+        uint4 e = __ldg(xt + min(lane, half_w - 1));   // x taps of this lane's first column pair: needed after the row producers
+        __syncwarp();  // the previous row's reads of the buffers are done
+        if (lowres_here) {
+            const DevShape sh = p.shapes[im.shape_id];
+            const int p_pitch = (3 * sh.nw + 24 + 15) & ~15;
+            const uint32_t ya = p.ltab[sh.ly_s + r0];
+            const int a0 = (int)(ya & 0xFFFFu), a1 = (int)(ya >> 16);
+            fused_lowres_prow(im, sh, p.ltab, base, a0, X2 + (a0 & 1) * p_pitch, lane);
+            if (a1 != a0) fused_lowres_prow(im, sh, p.ltab, base, a1, X2 + (a1 & 1) * p_pitch, lane);
+            __syncwarp();
+            fused_lowres_fullrow(im, sh, p.ltab, r0, X2, p_pitch, X0, lane);
+            __syncwarp();
+            if (two) {
+                const uint32_t yb2 = p.ltab[sh.ly_s + r1];
+                const int b0 = (int)(yb2 & 0xFFFFu), b1 = (int)(yb2 >> 16);
+                if (b0 != a0 && b0 != a1) fused_lowres_prow(im, sh, p.ltab, base, b0, X2 + (b0 & 1) * p_pitch, lane);
+                if (b1 != a0 && b1 != a1 && b1 != b0) fused_lowres_prow(im, sh, p.ltab, base, b1, X2 + (b1 & 1) * p_pitch, lane);
+                __syncwarp();
+                fused_lowres_fullrow(im, sh, p.ltab, r1, X2, p_pitch, X1, lane);
+            }
+        } else {
+            fused_stage_row(base + (int64_t)r0 * pitch, n, blur ? X1 : X0, lane);
+            if (two) fused_stage_row(base + (int64_t)r1 * pitch, n, blur ? X2 : X1, lane);
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            if (op == ROD_OP_NOISE) {
+                fused_noise_row(p, im, img, r0, X0, lane);
+                if (two) fused_noise_row(p, im, img, r1, X1, lane);
+            } else if (blur) {
+                fused_blur_row(p, im, X1, X0, lane);
+                __syncwarp();
+                if (two) fused_blur_row(p, im, X2, X1, lane);
+            }
+        }
+        const uint8_t* bufA = X0;
+        const uint8_t* rowB = two ? X1 : X0;
+        const X2Row rc = x2g_row_consts(yb);
+        __half2* o0 = reinterpret_cast<__half2*>(orow);
+        __half2* o1 = reinterpret_cast<__half2*>(orow + plane);
+        __half2* o2 = reinterpret_cast<__half2*>(orow + 2 * plane);
+        __syncwarp();
+#pragma unroll 1
+        for (int q = lane; q < half_w; q += 32) {
+            const uint4 en = __ldg(xt + min(q + 32, half_w - 1));   // next step's x taps, in flight during this step
+            float fa[3] = {padf, padf, padf}, fb[3] = {padf, padf, padf};
+            if (e.x != 0xFFFFFFFFu) fused_column(bufA, rowB, e.x, e.y, rc, c255, nc255, fa);
+            if (e.z != 0xFFFFFFFFu) fused_column(bufA, rowB, e.z, e.w, rc, c255, nc255, fb);
+            o0[q] = __floats2half2_rn(fa[2], fb[2]);   // BGR -> RGB planes
+            o1[q] = __floats2half2_rn(fa[1], fb[1]);
+            o2[q] = __floats2half2_rn(fa[0], fb[0]);
+            e = en;
+        }
+        ti = __shfl_sync(0xFFFFFFFFu, ti_next, 0);
+    }
+}
+
 int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8_t* scratch, const uint8_t* opcodes,
                            const float* noise, void* out_f16, int pad_value, float sigma, int k, uint64_t seed,
                            uint64_t first_image, uint32_t offset, bool lowres_in_kernel, cudaStream_t stream) {
@@ -473,12 +654,29 @@ int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8
     const char* e_nw = getenv("ROD_FUSED_WARPS");
     int nw = 4;
     if (e_nw && (atoi(e_nw) == 4 || atoi(e_nw) == 8)) nw = atoi(e_nw);
-    const size_t smem = 512 + (size_t)p.xtab_bytes + (size_t)nw * (size_t)(3 * p.buf_bytes);
+    // version 2 (row per warp, two columns per lane) from 32 images on: measured on a B200 with 1360x765 sources and the
+    // seed-42 mix, batch 64: 147 us (version 1: 161 us), batch 16: 46-49 us (version 1: 42 us -- with ~4 rows per resident warp
+    // the per-row descriptor loads of version 2 are not amortised).  Knob ROD_FUSED_V2 = 0 | 1 forces either.
+    const char* e_v2 = getenv("ROD_FUSED_V2");
+    const bool v2 = (p.out_w & 1) == 0 && (e_v2 ? atoi(e_v2) != 0 : plan->n_images >= 32);
+    const size_t smem = v2 ? (size_t)(2 * kFusedMaxSorted + 32) + (size_t)nw * (size_t)(3 * p.buf_bytes) : 512 + (size_t)p.xtab_bytes + (size_t)nw * (size_t)(3 * p.buf_bytes);
     if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : per_sm;
     p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
     ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
+    if (v2) {   // one output row per warp and counter value
+        const int ctas = (plan->n_images * p.out_h + nw - 1) / nw;
+        if (nw == 4) {
+            ROD_CUDA(cudaFuncSetAttribute(fused_letterbox2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fused_letterbox2_kernel<4><<<grid_for(plan, ctas, per_sm), 128, smem, stream>>>(p);
+        } else {
+            ROD_CUDA(cudaFuncSetAttribute(fused_letterbox2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fused_letterbox2_kernel<8><<<grid_for(plan, ctas, per_sm), 256, smem, stream>>>(p);
+        }
+        ROD_CUDA(cudaGetLastError());
+        return ROD_OK;
+    }
     const int tiles = plan->n_images * ((p.out_h + nw - 1) / nw);
     if (nw == 4) {
         ROD_CUDA(cudaFuncSetAttribute(fused_letterbox_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -243,6 +243,14 @@ int ensure_letterbox_tables(rod_plan* plan, int out_h, int out_w) {
             g.lx_a = blob_push(blob, lx.coef);
             g.ly_s = blob_push(blob, ys);
             g.ly_b = blob_push(blob, ly.coef);
+            std::vector<uint32_t> pack((size_t)2 * out_w);
+            for (int X = 0; X < out_w; ++X) {
+                const int cx = X - g.left;
+                const bool in = cx >= 0 && cx < g.new_w;
+                pack[2 * X] = in ? (uint32_t)(3 * lx.s0[cx]) : 0xFFFFFFFFu;
+                pack[2 * X + 1] = in ? lx.coef[cx] : 0u;
+            }
+            g.lx_pack = blob_push(blob, pack);
         }
         lbs[s] = g;
     }

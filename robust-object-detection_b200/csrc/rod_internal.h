@@ -36,6 +36,7 @@ struct DevLetterbox {
     int32_t identity;          // 1: new size == source size
     uint32_t lx_s0, lx_a;      // int32 s0[new_w], uint32 (a0 | a1<<16)[new_w]
     uint32_t ly_s, ly_b;       // uint32 (s0 | s1<<16)[new_h], uint32 (b0 | b1<<16)[new_h]
+    uint32_t lx_pack;          // uint2 per OUTPUT column X of the padded row: {3 * s0 (0xFFFFFFFF: padding column), a0 | a1<<16}
 };
 
 }  // namespace rod

@@ -40,6 +40,8 @@ if "letterbox" in which:
     import random
     random.seed(42)
     ops = torch.from_numpy(draw_decisions(n)).cuda()
+    if os.environ.get("ROD_PROFILE_OP"):   # every image on the same op
+        ops = torch.full((n,), int(os.environ["ROD_PROFILE_OP"]), dtype=torch.uint8, device="cuda")
     f16 = torch.empty((n, 3, 640, 640), dtype=torch.float16, device="cuda")
     for _ in range(2):
         plan.corrupt_letterbox(src, ops, f16, 640, 640, 114, seed=1)
