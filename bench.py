@@ -471,7 +471,7 @@ def extras(torch, np, plan, src, dst, peak):
     out = {}
     n = src.shape[0]
 
-    def rate(fn, bytes_per_call, images, steps=5, warmup=2):
+    def rate(fn, bytes_per_call, images, steps=10, warmup=3):
         ms = time_device(fn, steps, warmup, torch) / steps
         gbs = bytes_per_call / (ms / 1e3) / 1e9
         return {"images_per_s": images / (ms / 1e3), "ms": ms, "GB/s": gbs, "frac_of_measured_peak": gbs / peak}
@@ -502,7 +502,7 @@ def extras(torch, np, plan, src, dst, peak):
     tp = CorruptionPlan.ragged(shapes)
     tsrc = torch.randint(0, 256, (tp.src_bytes,), dtype=torch.uint8, device="cuda")
     tdst = torch.empty_like(tsrc)
-    out["lowres_visdrone_1610"] = rate(lambda: tp.lowres(tsrc, tdst), 2 * tp.payload_bytes, 1610, steps=3, warmup=2)
+    out["lowres_visdrone_1610"] = rate(lambda: tp.lowres(tsrc, tdst), 2 * tp.payload_bytes, 1610, steps=4, warmup=2)
     del tsrc, tdst, tp
     torch.cuda.empty_cache()
     # even x even frame (the packed-integer kernel) and batch 64 of the training path
@@ -511,6 +511,12 @@ def extras(torch, np, plan, src, dst, peak):
     d1080 = torch.empty_like(s1080)
     out["lowres_1920x1080_128"] = rate(lambda: p1080.lowres(s1080, d1080), 2 * s1080.numel(), 128)
     del s1080, d1080, p1080
+    # odd width and height (the odd-width kernel: general INTER_AREA taps in both axes, rows at every byte phase)
+    podd = CorruptionPlan.uniform(64, 1079, 1917)
+    sodd = torch.randint(0, 256, (64, 1079, 1917, 3), dtype=torch.uint8, device="cuda")
+    dodd = torch.empty_like(sodd)
+    out["lowres_1917x1079_64"] = rate(lambda: podd.lowres(sodd, dodd), 2 * sodd.numel(), 64)
+    del sodd, dodd, podd
     import random
     from robust_object_detection_b200.batch import draw_decisions
     random.seed(42)

@@ -165,6 +165,13 @@ ROD_API int rod_restoration_pairs_f32(rod_plan* plan, const uint8_t* src, const 
                               float* corrupted_out, float* clean_out, const float* noise, float sigma, int k,
                               double factor, uint64_t seed, uint64_t first_image_index, uint32_t offset, void* stream);
 
+/* The resize-first branch of RestorationDataset._random_crop / _center_crop (scripts/train_restoration.py:79-81,
+ * 88-90): frames smaller than the patch are enlarged with cv2.resize(img, (max(w, size), max(h, size))), i.e. OpenCV's
+ * 8-bit fixed-point INTER_LINEAR, before the crop.  One HWC uint8 image, device pointers, pitches in bytes; (nh, nw) must
+ * not be smaller than (h, w) in either axis (a 2x reduction would switch OpenCV to INTER_AREA: ROD_ERR_UNSUPPORTED). */
+ROD_API int rod_resize_linear_u8(const uint8_t* src, int h, int w, int64_t src_pitch, uint8_t* dst, int nh, int nw,
+                         int64_t dst_pitch, void* stream);
+
 /* Host-buffer entry points (what a per-image Python/cgo/JNI caller binds): src/dst are HOST
  * pointers laid out by the plan's descriptors; the call stages through pinned memory,
  * overlaps H2D / kernel / D2H in chunks of images, and returns after dst is complete. */

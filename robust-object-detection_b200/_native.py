@@ -48,6 +48,7 @@ SYMBOLS = {
     "rod_corrupt_batch_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _d, _u64, _u64, _u32, _vp]),
     "rod_corrupt_letterbox_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _i, _d, _u64, _u64, _u32, _vp]),
     "rod_restoration_pairs_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _d, _u64, _u64, _u32, _vp]),
+    "rod_resize_linear_u8": (_i, [_vp, _i, _i, ctypes.c_int64, _vp, _i, _i, ctypes.c_int64, _vp]),
     "rod_apply_host": (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _d, _u64, _u64, _u32]),
 }
 

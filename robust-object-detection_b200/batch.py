@@ -54,12 +54,28 @@ def draw_decisions(n: int, gate: str = "ultralytics", p: float = 0.5) -> np.ndar
     return ops
 
 
+def resize_linear_u8(img: np.ndarray, nh: int, nw: int) -> np.ndarray:
+    """cv2.resize(img, (nw, nh)) with the default INTER_LINEAR for an HWC uint8 frame that is enlarged (or kept) in both
+    axes, computed on the GPU (rod_resize_linear_u8; bit-exact against OpenCV's 8-bit fixed-point path).  The
+    resize-first branch of RestorationDataset._random_crop / _center_crop (train_restoration.py:79-81,88-90)."""
+    import torch
+    N.require_device()
+    if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+        raise ValueError("expected an HWC uint8 image")
+    h, w = int(img.shape[0]), int(img.shape[1])
+    src = torch.from_numpy(np.ascontiguousarray(img)).cuda()
+    dst = torch.empty((int(nh), int(nw), 3), dtype=torch.uint8, device="cuda")
+    N.check(N.lib().rod_resize_linear_u8(_ptr(src), h, w, 3 * w, _ptr(dst), int(nh), int(nw), 3 * int(nw), _stream_handle()),
+            "rod_resize_linear_u8")
+    return dst.cpu().numpy()
+
+
 def draw_restoration_decisions(h: int, w: int, size: int, is_train: bool = True):
     """(y, x, flip, op) of one RestorationDataset.__getitem__ call (train_restoration.py:77-102,108-121), consuming
     Python's global `random` in the reference's order: randint(0, h - size), randint(0, w - size), random() > 0.5,
-    random.choice([...]); validation items take the centre crop and no flip.  Needs h, w >= size."""
-    if h < size or w < size:
-        raise NotImplementedError("images smaller than the patch are resized first in the reference (not on this path)")
+    random.choice([...]); validation items take the centre crop and no flip.  A frame smaller than the patch is first
+    enlarged to (max(h, size), max(w, size)) in the reference (:79-81, 88-90); the positions are drawn for that size."""
+    h, w = max(h, size), max(w, size)
     if is_train:
         y = random.randint(0, h - size)
         x = random.randint(0, w - size)

@@ -272,6 +272,15 @@ extern "C" int rod_corrupt_letterbox_f16(rod_plan* plan, const uint8_t* src, con
     return launch_letterbox(plan, plan->d_scratch, src, opcodes, out_f16, pad_value, (cudaStream_t)stream);
 }
 
+extern "C" int rod_resize_linear_u8(const uint8_t* src, int h, int w, int64_t src_pitch, uint8_t* dst, int nh, int nw,
+                                    int64_t dst_pitch, void* stream) {
+    if (src == nullptr || dst == nullptr || h < 1 || w < 1 || nh < 1 || nw < 1 || src_pitch < 3LL * w || dst_pitch < 3LL * nw ||
+        h > 65535 || w > 65535 || nh > 65535 || nw > 65535)
+        return ROD_ERR_INVALID_ARG;
+    if (nh < h || nw < w) return ROD_ERR_UNSUPPORTED;  // reductions: OpenCV may switch to INTER_AREA (exact 2x); not this entry point
+    return launch_resize_linear(src, h, w, src_pitch, dst, nh, nw, dst_pitch, (cudaStream_t)stream);
+}
+
 // RestorationDataset.__getitem__ (train_restoration.py:104-129) for a batch of patches.
 extern "C" int rod_restoration_pairs_f32(rod_plan* plan, const uint8_t* src, const uint8_t* flips, const uint8_t* opcodes,
                                          float* corrupted_out, float* clean_out, const float* noise, float sigma, int k,

@@ -523,12 +523,13 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox2_kernel(Fuse
     const __half2 pad2 = __floats2half2_rn(padf, padf);
     const int total = p.n_images * p.out_h, mid = p.out_h >> 1;
     const int half_w = p.out_w >> 1;
-    int ti = 0;
-    if (lane == 0) ti = (int)atomicAdd(p.counter, 1u);
+    // row indices are fetched two rows ahead (lane 0 holds them): a padding row is too short to cover the atomic's latency
+    int ti = 0, ti_next = 0;
+    if (lane == 0) { ti = (int)atomicAdd(p.counter, 1u); ti_next = (int)atomicAdd(p.counter, 1u); }
     ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
     while (ti < total) {
-        int ti_next = 0;
-        if (lane == 0) ti_next = (int)atomicAdd(p.counter, 1u);   // the next row's index arrives while this row is processed
+        int ti_next2 = 0;
+        if (lane == 0) ti_next2 = (int)atomicAdd(p.counter, 1u);
         // row order inside a class block: centre-out (mid, mid-1, mid+1, ...: a bijection onto [0, out_h)), image-minor
         int img, kk;
         if (sorted) {
@@ -565,6 +566,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox2_kernel(Fuse
                 }
             }
             ti = __shfl_sync(0xFFFFFFFFu, ti_next, 0);
+            ti_next = ti_next2;
             continue;
         }
         const int op = p.opcodes[img];
@@ -631,6 +633,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox2_kernel(Fuse
             e = en;
         }
         ti = __shfl_sync(0xFFFFFFFFu, ti_next, 0);
+        ti_next = ti_next2;
     }
 }
 

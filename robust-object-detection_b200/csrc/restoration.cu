@@ -68,6 +68,65 @@ __global__ void __launch_bounds__(256) format_pairs_kernel(FormatParams p) {
     }
 }
 
+// ---- resize-first branch (train_restoration.py:79-81, 88-90): cv2.resize(img, (nw, nh)) with the default INTER_LINEAR
+// on 8-bit data = fixed-point coefficients (11 bits) per axis, horizontal stage (S0 a0 + S1 a1) >> 4, vertical stage
+// (((b0 h0) >> 16) + ((b1 h1) >> 16) + 2) >> 2 (rod_core.h linear_h4 / linear_v).  The per-axis coefficients are
+// computed in the kernel exactly as rod_tables.h build_linear_axis does on the host (double scale, float fraction,
+// round-half-even to 11 bits; x: index and fraction clamped at both ends, y: fraction kept, indices clipped).
+struct ResizeParams {
+    const uint8_t* src;
+    uint8_t* dst;
+    int h, w, nh, nw;
+    int64_t src_pitch, dst_pitch;
+    double scale_x, scale_y;  // 1.0 / ((double)dsize / (double)ssize)
+};
+
+__device__ __forceinline__ void linear_axis_entry(int d, double scale, int ssize, bool clamp_x, int* s0, int* s1, uint32_t* coef) {
+    float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+    int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (clamp_x) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+    }
+    const float c0 = __fsub_rn(1.f, f);
+    const int a0 = __float2int_rn(__fmul_rn(c0, 2048.f)), a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+    *s0 = min(max(s, 0), ssize - 1);
+    *s1 = min(max(s + 1, 0), ssize - 1);
+    *coef = (uint32_t)(a0 & 0xFFFF) | ((uint32_t)(a1 & 0xFFFF) << 16);
+}
+
+__global__ void __launch_bounds__(256) resize_linear_kernel(ResizeParams p) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= p.nw || y >= p.nh) return;
+    int xs0, xs1, ys0, ys1;
+    uint32_t xa, yb;
+    linear_axis_entry(x, p.scale_x, p.w, true, &xs0, &xs1, &xa);
+    linear_axis_entry(y, p.scale_y, p.h, false, &ys0, &ys1, &yb);
+    const uint8_t* r0 = p.src + (int64_t)ys0 * p.src_pitch;
+    const uint8_t* r1 = p.src + (int64_t)ys1 * p.src_pitch;
+    uint8_t* o = p.dst + (int64_t)y * p.dst_pitch + 3 * x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t h0 = linear_h4(r0[3 * xs0 + c], r0[3 * xs1 + c], xa);
+        const uint32_t h1 = linear_h4(r1[3 * xs0 + c], r1[3 * xs1 + c], xa);
+        o[c] = (uint8_t)linear_v(h0, h1, yb);
+    }
+}
+
+int launch_resize_linear(const uint8_t* src, int h, int w, int64_t src_pitch, uint8_t* dst, int nh, int nw, int64_t dst_pitch,
+                         cudaStream_t stream) {
+    ResizeParams p;
+    p.src = src; p.dst = dst; p.h = h; p.w = w; p.nh = nh; p.nw = nw; p.src_pitch = src_pitch; p.dst_pitch = dst_pitch;
+    p.scale_x = 1.0 / ((double)nw / (double)w);
+    p.scale_y = 1.0 / ((double)nh / (double)h);
+    const dim3 grid((unsigned)((nw + 31) / 32), (unsigned)((nh + 7) / 8));
+    resize_linear_kernel<<<grid, 256, 0, stream>>>(p);
+    ROD_CUDA(cudaGetLastError());
+    return ROD_OK;
+}
+
 int launch_gather_patches(const rod_plan* plan, const rod_plan* inner, const uint8_t* src, uint8_t* clean,
                           const uint8_t* flips, cudaStream_t stream) {
     GatherParams p;

@@ -177,6 +177,8 @@ int launch_filter2d(const rod_plan* plan, const uint8_t* src, uint8_t* dst, cons
                     int img_lo, int img_hi);
 int launch_gather_patches(const rod_plan* plan, const rod_plan* inner, const uint8_t* src, uint8_t* clean,
                           const uint8_t* flips, cudaStream_t stream);
+int launch_resize_linear(const uint8_t* src, int h, int w, int64_t src_pitch, uint8_t* dst, int nh, int nw, int64_t dst_pitch,
+                         cudaStream_t stream);
 int launch_format_pairs(const rod_plan* inner, const uint8_t* clean, const uint8_t* corrupted, float* clean_out,
                         float* corrupted_out, cudaStream_t stream);
 int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8_t* scratch, const uint8_t* opcodes,

@@ -149,7 +149,7 @@ class CorruptionBatcher:
 
 class RestorationPairBatcher:
     """Host-level drop-in for the pair generation of RestorationDataset.__getitem__ (train_restoration.py:104-129), one
-    batch at a time: for every decoded frame (HWC BGR uint8, at least patch_size in both dimensions) the decisions are
+    batch at a time: for every decoded frame (HWC BGR uint8; smaller than patch_size: enlarged first like the reference) the decisions are
     drawn in the reference's order (random crop position, flip, random.choice of the corruption; centre crop and no
     flip for validation), only the CROP is uploaded (the frame itself never leaves the host), and
     rod_restoration_pairs_f32 produces both tensors on the device:
@@ -173,7 +173,7 @@ class RestorationPairBatcher:
 
     def __call__(self, frames: Sequence[np.ndarray]):
         from .augmentations import NOISE_SIGMA, legacy_normal_f32
-        from .batch import draw_restoration_decisions
+        from .batch import draw_restoration_decisions, resize_linear_u8
         torch, P, n = self._torch, self.size, len(frames)
         if n not in self._plans:  # crops are staged back to back: one plan per batch size
             offs = [i * 3 * P * P for i in range(n)]
@@ -185,6 +185,8 @@ class RestorationPairBatcher:
         for i, im in enumerate(frames):
             if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
                 raise ValueError("expected HWC uint8 BGR frames")
+            if im.shape[0] < P or im.shape[1] < P:  # the reference enlarges such a frame first (train_restoration.py:79-81)
+                im = resize_linear_u8(im, max(int(im.shape[0]), P), max(int(im.shape[1]), P))
             y, x, flip, op = draw_restoration_decisions(int(im.shape[0]), int(im.shape[1]), P, self.is_train)
             crops[i] = im[y:y + P, x:x + P]
             if op == 1 and self.noise == "compat":  # the draw of apply_noise on the (flipped) patch, in sample order

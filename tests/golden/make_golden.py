@@ -224,6 +224,25 @@ def make_restoration():
         cv2.imread = real_imread
     np.savez_compressed(os.path.join(HERE, "golden_restoration.npz"), **out)
     print("wrote", len(out), "restoration arrays")
+    # frames smaller than the patch: the resize-first branch (train_restoration.py:79-81, 88-90)
+    small = [(40, 80), (100, 50), (30, 30), (64, 20), (70, 64), (63, 65)]
+    frames = {f"img{i}.jpg": synth(5100 + i, h, w) for i, (h, w) in enumerate(small)}
+    cv2.imread = lambda path, *a: frames[Path(path).name].copy()
+    try:
+        out = {}
+        for is_train in (True, False):
+            ds = tr.RestorationDataset(Path("/nonexistent"), patch_size=64, is_train=is_train)
+            ds.img_paths = [Path(n) for n in frames]
+            random.seed(4)
+            np.random.seed(41)
+            for i in range(len(frames)):
+                cor, clean = ds[i]
+                out[f"{'train' if is_train else 'val'}_cor_{i}"] = cor.numpy()
+                out[f"{'train' if is_train else 'val'}_clean_{i}"] = clean.numpy()
+    finally:
+        cv2.imread = real_imread
+    np.savez_compressed(os.path.join(HERE, "golden_restoration_small.npz"), **out)
+    print("wrote", len(out), "restoration arrays (frames smaller than the patch)")
 
 
 if __name__ == "__main__":

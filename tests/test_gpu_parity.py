@@ -1004,8 +1004,34 @@ def test_restoration_pair_batcher_host_level(torch_):
             assert np.array_equal(clean[i], (patch[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1)), (is_train, i)
             assert np.array_equal(cor[i], (c[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1)), (is_train, i, op)
         assert ops_seen == {1, 2, 3}
+
+
+def test_restoration_resize_first_branch(torch_):
+    """Frames smaller than the patch (train_restoration.py:79-81, 88-90): rod_resize_linear_u8 against live
+    cv2.resize(INTER_LINEAR) for enlargements in one or both axes, and RestorationPairBatcher on such frames against the
+    pairs of the unmodified RestorationDataset (golden_restoration_small.npz; compat noise: bit-exact)."""
+    import cv2
+    from robust_object_detection_b200.batch import resize_linear_u8
+    from robust_object_detection_b200.training import RestorationPairBatcher
+    for i, (h, w, nh, nw) in enumerate([(40, 80, 64, 80), (100, 50, 100, 64), (30, 30, 64, 64), (64, 20, 64, 64), (63, 65, 64, 65),
+                                        (7, 5, 256, 256), (1, 1, 3, 2), (200, 255, 256, 256), (97, 133, 97, 133), (120, 77, 333, 190)]):
+        img = synth(5300 + i, h, w)
+        want = img if (nh, nw) == (h, w) else cv2.resize(img, (nw, nh))
+        assert np.array_equal(resize_linear_u8(img, nh, nw), want), (h, w, nh, nw)
     with pytest.raises(NotImplementedError):
-        RestorationPairBatcher(patch_size=P)([synth(1, 40, 80)])   # smaller than the patch: resized first in the reference
+        resize_linear_u8(synth(1, 40, 80), 20, 80)   # reductions are not this entry point's job
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_restoration_small.npz"))
+    small = [(40, 80), (100, 50), (30, 30), (64, 20), (70, 64), (63, 65)]
+    frames = [synth(5100 + i, h, w) for i, (h, w) in enumerate(small)]
+    for is_train in (True, False):
+        random.seed(4)
+        np.random.seed(41)
+        tag = "train" if is_train else "val"
+        pairs = RestorationPairBatcher(patch_size=64, is_train=is_train)
+        for i, fr in enumerate(frames):   # one frame per call: the reference draws crop / flip / op / noise per item, in this order
+            cor, clean = pairs([fr])
+            assert np.array_equal(clean[0].cpu().numpy(), g[f"{tag}_clean_{i}"]), (tag, i)
+            assert np.array_equal(cor[0].cpu().numpy(), g[f"{tag}_cor_{i}"]), (tag, i, pairs.last_decisions)
 
 
 def test_training_batcher_pinned_pipeline(torch_):

@@ -145,3 +145,28 @@ def test_restoration_pairs_vs_reference_dataset(is_train):
         cor = orc.add_noise_field(patch, fields[i]) if op == orc.OP_NOISE else orc.apply_op(patch, op)
         assert np.array_equal((patch[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1), g[f"{tag}_clean_{i}"]), i
         assert np.array_equal((cor[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1), g[f"{tag}_cor_{i}"]), (i, op)
+
+
+RESTORATION_SMALL_SHAPES = [(40, 80), (100, 50), (30, 30), (64, 20), (70, 64), (63, 65)]
+
+
+@pytest.mark.parametrize("is_train", [True, False])
+def test_restoration_resize_first_branch_vs_reference_dataset(is_train):
+    """Frames smaller than the patch (train_restoration.py:79-81, 88-90): the oracle's INTER_LINEAR enlargement, then
+    the usual crop / flip / choice / corruption order, against pairs of the unmodified RestorationDataset
+    (tests/golden/golden_restoration_small.npz)."""
+    from robust_object_detection_b200.batch import draw_restoration_decisions
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_restoration_small.npz"))
+    random.seed(4)
+    np.random.seed(41)
+    tag = "train" if is_train else "val"
+    for i, (h, w) in enumerate(RESTORATION_SMALL_SHAPES):
+        img = synth(5100 + i, h, w)
+        if h < 64 or w < 64:
+            img = orc.resize_linear(img, max(h, 64), max(w, 64))
+        y, x, flip, op = draw_restoration_decisions(h, w, 64, is_train=is_train)
+        patch = img[y:y + 64, x:x + 64]
+        patch = np.ascontiguousarray(patch[:, ::-1] if flip else patch)
+        cor = orc.apply_op(patch, op)   # noise draws from np.random's global stream, like the reference
+        assert np.array_equal((patch[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1), g[f"{tag}_clean_{i}"]), i
+        assert np.array_equal((cor[:, :, ::-1].astype(np.float32) / 255.0).transpose(2, 0, 1), g[f"{tag}_cor_{i}"]), (i, op)
