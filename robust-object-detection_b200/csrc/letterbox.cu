@@ -455,9 +455,9 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox_kernel(Fused
 
 // =====================================================================================
 // Version 2 of the fused training path (even out_w): the same row producers, but
-//   * every WARP takes single output rows from the counter on its own (no block barrier, no per-CTA table): rows are handed
-//     out centre-out and image-minor, so the expensive rows (content of noise / blur / LowRes images) of all images run
-//     first, spread evenly, and the cheap padding rows fill the tail;
+//   * every WARP works on single output rows on its own (no block barrier, no per-CTA table).  Rows are ordered by op class
+//     (noise, LowRes, blur, clean), centre-out and image-minor, and dealt round-robin to the resident warps: the expensive
+//     rows of all images run first, spread evenly, and the cheap padding rows fill the tail;
 //   * the resampling loop makes two adjacent output columns per lane and step: x taps from a per-shape table in global
 //     memory (one 16-byte load through L1), the horizontal stage as dp2a onto the 2^23 float grid, the vertical stage as the
 //     three round-toward-zero FMAs of the resize kernels, half(v / 255) as one more FMA (== the 256-entry table of
@@ -523,13 +523,11 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox2_kernel(Fuse
     const __half2 pad2 = __floats2half2_rn(padf, padf);
     const int total = p.n_images * p.out_h, mid = p.out_h >> 1;
     const int half_w = p.out_w >> 1;
-    // row indices are fetched two rows ahead (lane 0 holds them): a padding row is too short to cover the atomic's latency
-    int ti = 0, ti_next = 0;
-    if (lane == 0) { ti = (int)atomicAdd(p.counter, 1u); ti_next = (int)atomicAdd(p.counter, 1u); }
-    ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
-    while (ti < total) {
-        int ti_next2 = 0;
-        if (lane == 0) ti_next2 = (int)atomicAdd(p.counter, 1u);
+    // rows are dealt round-robin to the resident warps, in the cost-sorted order above: consecutive indices cost about the
+    // same, so every warp gets the same mix.  (A dynamic counter does not pay here: ptxas turns a single-lane atomicAdd
+    // into its warp-aggregated form, whose broadcast shuffle waits for the atomic on the spot -- 0.45 us per row.)
+    const int stride = (int)gridDim.x * NW;
+    for (int ti = (int)blockIdx.x * NW + warp; ti < total; ti += stride) {
         // row order inside a class block: centre-out (mid, mid-1, mid+1, ...: a bijection onto [0, out_h)), image-minor
         int img, kk;
         if (sorted) {
@@ -565,8 +563,6 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox2_kernel(Fuse
                     reinterpret_cast<__half2*>(orow + 2 * plane)[q] = pad2;
                 }
             }
-            ti = __shfl_sync(0xFFFFFFFFu, ti_next, 0);
-            ti_next = ti_next2;
             continue;
         }
         const int op = p.opcodes[img];
@@ -632,8 +628,6 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox2_kernel(Fuse
             o2[q] = __floats2half2_rn(fa[0], fb[0]);
             e = en;
         }
-        ti = __shfl_sync(0xFFFFFFFFu, ti_next, 0);
-        ti_next = ti_next2;
     }
 }
 
@@ -657,18 +651,19 @@ int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8
     const char* e_nw = getenv("ROD_FUSED_WARPS");
     int nw = 4;
     if (e_nw && (atoi(e_nw) == 4 || atoi(e_nw) == 8)) nw = atoi(e_nw);
-    // version 2 (row per warp, two columns per lane) from 32 images on: measured on a B200 with 1360x765 sources and the
-    // seed-42 mix, batch 64: 147 us (version 1: 161 us), batch 16: 46-49 us (version 1: 42 us -- with ~4 rows per resident warp
-    // the per-row descriptor loads of version 2 are not amortised).  Knob ROD_FUSED_V2 = 0 | 1 forces either.
+    // version 2 (row per warp, two columns per lane) whenever out_w is even.  Measured on a B200 (1360x765 sources, seed-42
+    // mix): batch 64 152 us (version 1: 161 us), batch 16 43.5 us (43.1 us).  Knob ROD_FUSED_V2 = 0 forces version 1.
+    // (Tried and dropped: a version 3 that keeps the NEXT row's source rows in flight during the resampling loop -- four row
+    // buffers per warp, 12 warps per SM: 171 us at batch 64.  The loop is bound by its shared-memory reads, not by the
+    // source-row latency: at scale 2.125 the six-byte windows of every fifth column pair fall into the same bank.)
     const char* e_v2 = getenv("ROD_FUSED_V2");
-    const bool v2 = (p.out_w & 1) == 0 && (e_v2 ? atoi(e_v2) != 0 : plan->n_images >= 32);
+    const bool v2 = (p.out_w & 1) == 0 && !(e_v2 && atoi(e_v2) == 0);
     const size_t smem = v2 ? (size_t)(2 * kFusedMaxSorted + 32) + (size_t)nw * (size_t)(3 * p.buf_bytes) : 512 + (size_t)p.xtab_bytes + (size_t)nw * (size_t)(3 * p.buf_bytes);
     if (smem > 227 * 1024) return ROD_ERR_UNSUPPORTED;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : per_sm;
-    p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
-    ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
-    if (v2) {   // one output row per warp and counter value
+    p.counter = nullptr;
+    if (v2) {   // one output row per warp, dealt round-robin (no work counter: one launch, nothing else on the stream)
         const int ctas = (plan->n_images * p.out_h + nw - 1) / nw;
         if (nw == 4) {
             ROD_CUDA(cudaFuncSetAttribute(fused_letterbox2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -680,6 +675,8 @@ int launch_fused_letterbox(const rod_plan* plan, const uint8_t* src, const uint8
         ROD_CUDA(cudaGetLastError());
         return ROD_OK;
     }
+    p.counter = plan->d_counters + (plan->launch_seq.fetch_add(1u) & (kCounterRing - 1u));
+    ROD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     const int tiles = plan->n_images * ((p.out_h + nw - 1) / nw);
     if (nw == 4) {
         ROD_CUDA(cudaFuncSetAttribute(fused_letterbox_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

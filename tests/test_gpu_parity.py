@@ -827,9 +827,9 @@ def test_full_size_config4_testset_by_replication_and_sharding(torch_):
             assert torch_.equal(sdst[:sp.dst_offsets[-1]], full[op][b0:b0 + sp.dst_offsets[-1]]), (rank, op)
 
 
-@pytest.mark.parametrize("fused_version", ["0", "1"])
+@pytest.mark.parametrize("fused_version", ["1", "2"])
 def test_letterbox_fused_training_path(torch_, monkeypatch, fused_version):
-    monkeypatch.setenv("ROD_FUSED_V2", fused_version)   # 0: block-per-four-rows kernel, 1: row-per-warp kernel (default from 32 images on)
+    monkeypatch.setenv("ROD_FUSED_V2", "0" if fused_version == "1" else "1")   # 1: block-per-four-rows kernel, 2: row-per-warp kernel (default)
     from robust_object_detection_b200.batch import CorruptionPlan
     shapes = [(765, 1360)] * 5 + [(720, 1280), (360, 480), (640, 640), (1079, 1917)]
     plan = CorruptionPlan.ragged(shapes)
@@ -845,9 +845,9 @@ def test_letterbox_fused_training_path(torch_, monkeypatch, fused_version):
         assert np.array_equal(got[i], want), (i, shapes[i])
 
 
-@pytest.mark.parametrize("fused_version", ["0", "1"])
+@pytest.mark.parametrize("fused_version", ["1", "2"])
 def test_fused_letterbox_kernel_paths(torch_, monkeypatch, fused_version):
-    monkeypatch.setenv("ROD_FUSED_V2", fused_version)   # 0: block-per-four-rows kernel, 1: row-per-warp kernel (default from 32 images on)
+    monkeypatch.setenv("ROD_FUSED_V2", "0" if fused_version == "1" else "1")   # 1: block-per-four-rows kernel, 2: row-per-warp kernel (default)
     """fused_letterbox_kernel (every shape a plain linear letterbox): 16-byte-aligned rows (cp.async staging), odd widths
     (32-bit / byte staging, Philox groups straddling rows), supplied noise field, another blur size, and a pitched
     source; all against the oracle, bit-exact except Philox noise (statistical mode)."""
@@ -896,9 +896,9 @@ def test_fused_letterbox_kernel_paths(torch_, monkeypatch, fused_version):
         assert np.array_equal(got[i], want), (i, shapes[i])
 
 
-@pytest.mark.parametrize("fused_version", ["0", "1"])
+@pytest.mark.parametrize("fused_version", ["1", "2"])
 def test_fused_letterbox_lowres_in_kernel(torch_, monkeypatch, fused_version):
-    monkeypatch.setenv("ROD_FUSED_V2", fused_version)   # 0: block-per-four-rows kernel, 1: row-per-warp kernel (default from 32 images on)
+    monkeypatch.setenv("ROD_FUSED_V2", "0" if fused_version == "1" else "1")   # 1: block-per-four-rows kernel, 2: row-per-warp kernel (default)
     """Every shape exact-2x (w % 4 == 0): the LowRes rows are produced inside fused_letterbox_kernel too (no scratch);
     odd and even heights, a width with a two-pixel last chunk, several output sizes."""
     from robust_object_detection_b200.batch import CorruptionPlan
