@@ -15,8 +15,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-fil
 # the headline launch itself (256 images): DRAM traffic for bench.py's roofline.traffic
 ncu --set full --clock-control none --import-source on -k regex:blur -s 3 -c 1 -f -o $out/prof_bench_$tag \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/ncu_bench_$tag.log 2>&1
-python tools/profile_ops.py > $out/plain_profile_$tag.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'blur|noise|lowres|letterbox' -s 3 -c 24 -f \
-    -o $out/prof_$tag python tools/profile_ops.py > $out/ncu_full_$tag.log 2>&1
+ops="blur noise lowres lowres1080 lowresodd letterbox mixed"
+python tools/profile_ops.py $ops > $out/plain_profile_$tag.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'blur|noise|lowres|letterbox' -s 3 -c 40 -f \
+    -o $out/prof_$tag python tools/profile_ops.py $ops > $out/ncu_full_$tag.log 2>&1
 python tools/time_testset_driver.py 64 > $out/testset_driver_$tag.json 2> $out/testset_driver_$tag.err; echo "driver timing exit $?"
 echo "done"
