@@ -576,7 +576,11 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox2_kernel(Fuse
         const bool two = (r1 != r0);
         const bool blur = (op == ROD_OP_BLUR);
         const uint4* xt = reinterpret_cast<const uint4*>(p.tab + g.lx_pack);
-        uint4 e = __ldg(xt + min(lane, half_w - 1));   // x taps of this lane's first column pair: needed after the row producers
+        // step order of this lane: groups of lane_group lanes start one step apart (their windows would otherwise fall into
+        // the same shared-memory bank, see plan.cu); every lane still visits all steps
+        const int n_it = (half_w + 31) >> 5;
+        int itt = (g.lane_group > 0 ? lane / g.lane_group : 0) % n_it;
+        uint4 e = __ldg(xt + min(lane + 32 * itt, half_w - 1));   // x taps of this lane's first column pair: needed after the row producers
         __syncwarp();  // the previous row's reads of the buffers are done
         if (lowres_here) {
             const DevShape sh = p.shapes[im.shape_id];
@@ -618,14 +622,18 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) fused_letterbox2_kernel(Fuse
         __half2* o2 = reinterpret_cast<__half2*>(orow + 2 * plane);
         __syncwarp();
 #pragma unroll 1
-        for (int q = lane; q < half_w; q += 32) {
-            const uint4 en = __ldg(xt + min(q + 32, half_w - 1));   // next step's x taps, in flight during this step
-            float fa[3] = {padf, padf, padf}, fb[3] = {padf, padf, padf};
-            if (e.x != 0xFFFFFFFFu) fused_column(bufA, rowB, e.x, e.y, rc, c255, nc255, fa);
-            if (e.z != 0xFFFFFFFFu) fused_column(bufA, rowB, e.z, e.w, rc, c255, nc255, fb);
-            o0[q] = __floats2half2_rn(fa[2], fb[2]);   // BGR -> RGB planes
-            o1[q] = __floats2half2_rn(fa[1], fb[1]);
-            o2[q] = __floats2half2_rn(fa[0], fb[0]);
+        for (int it = 0; it < n_it; ++it) {
+            const int q = lane + 32 * itt;
+            itt = (itt + 1 == n_it) ? 0 : itt + 1;
+            const uint4 en = __ldg(xt + min(lane + 32 * itt, half_w - 1));   // next step's x taps, in flight during this step
+            if (q < half_w) {
+                float fa[3] = {padf, padf, padf}, fb[3] = {padf, padf, padf};
+                if (e.x != 0xFFFFFFFFu) fused_column(bufA, rowB, e.x, e.y, rc, c255, nc255, fa);
+                if (e.z != 0xFFFFFFFFu) fused_column(bufA, rowB, e.z, e.w, rc, c255, nc255, fb);
+                o0[q] = __floats2half2_rn(fa[2], fb[2]);   // BGR -> RGB planes
+                o1[q] = __floats2half2_rn(fa[1], fb[1]);
+                o2[q] = __floats2half2_rn(fa[0], fb[0]);
+            }
             e = en;
         }
     }

@@ -251,6 +251,15 @@ int ensure_letterbox_tables(rod_plan* plan, int out_h, int out_w) {
                 pack[2 * X + 1] = in ? lx.coef[cx] : 0u;
             }
             g.lx_pack = blob_push(blob, pack);
+            // The fused kernel's lane l resamples output columns 2l, 2l+1 (+64 per step) from six-byte windows that lie
+            // 2 * 3 * (w / new_w) bytes apart.  If p lanes further the window is a multiple of 128 bytes away (within a word),
+            // lanes l, l+p, l+2p, ... hit the same bank: the kernel then shifts every such group by one step.
+            const double stride_words = 2.0 * 3.0 * ((double)g.w / (double)g.new_w) / 4.0;
+            g.lane_group = 0;
+            for (int pp = 2; pp <= 16; ++pp) {
+                const double x = pp * stride_words / 32.0;
+                if (fabs(x - nearbyint(x)) * 32.0 < 1.0) { g.lane_group = pp; break; }
+            }
         }
         lbs[s] = g;
     }

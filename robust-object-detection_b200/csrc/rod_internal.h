@@ -37,6 +37,7 @@ struct DevLetterbox {
     uint32_t lx_s0, lx_a;      // int32 s0[new_w], uint32 (a0 | a1<<16)[new_w]
     uint32_t ly_s, ly_b;       // uint32 (s0 | s1<<16)[new_h], uint32 (b0 | b1<<16)[new_h]
     uint32_t lx_pack;          // uint2 per OUTPUT column X of the padded row: {3 * s0 (0xFFFFFFFF: padding column), a0 | a1<<16}
+    int32_t lane_group;        // fused kernel: lanes l and l + lane_group would read the same shared-memory bank (0: no such period)
 };
 
 }  // namespace rod
