@@ -172,6 +172,26 @@ ROD_API int rod_restoration_pairs_f32(rod_plan* plan, const uint8_t* src, const 
 ROD_API int rod_resize_linear_u8(const uint8_t* src, int h, int w, int64_t src_pitch, uint8_t* dst, int nh, int nw,
                          int64_t dst_pitch, void* stream);
 
+/* SURVEY 8f rank 1 -- `cv2.imwrite(str(dst_img_dir / img_path.name), out)` (scripts/build_corrupted_testsets.py:124, :164)
+ * for a device-resident batch: baseline JPEG encoding whose bytes equal OpenCV 4.13.0's (libjpeg-turbo defaults: YCbCr
+ * 4:2:0, quality 95, standard Huffman tables, islow DCT).  `images`: the pixels to encode (src_offset / src_pitch /
+ * height / width; HWC BGR uint8).  `header`: the bytes SOI .. SOS OpenCV itself writes with the wanted parameters (any
+ * image size): its DQT / DHT segments define the tables; ROD_ERR_UNSUPPORTED unless it is baseline 4:2:0 without restart
+ * markers.  After rod_jpeg_encode() the device array rod_jpeg_stream_base() + rod_jpeg_stream_offset(i) holds the
+ * entropy-coded segment + EOI of image i and rod_jpeg_stream_lengths()[i] (device uint32) its length, 0xFFFFFFFF if it did
+ * not fit its buffer; the file is OpenCV's header for that image size followed by those bytes. */
+typedef struct rod_jpeg_encoder rod_jpeg_encoder;
+ROD_API int rod_jpeg_create(const rod_image_desc* images, int n_images, const uint8_t* header, uint64_t header_len,
+                    rod_jpeg_encoder** out_enc);
+ROD_API void rod_jpeg_destroy(rod_jpeg_encoder* enc);
+ROD_API int rod_jpeg_encode(rod_jpeg_encoder* enc, const uint8_t* pixels, void* stream);
+ROD_API uint64_t rod_jpeg_stream_offset(const rod_jpeg_encoder* enc, int i);
+ROD_API const uint8_t* rod_jpeg_stream_base(const rod_jpeg_encoder* enc);
+ROD_API const uint32_t* rod_jpeg_stream_lengths(const rod_jpeg_encoder* enc);
+/* lengths and streams to the host: host_len[n_images]; image i's bytes at host_out + rod_jpeg_stream_offset(enc, i)
+ * (host_out holds rod_jpeg_stream_offset(enc, n_images) bytes); returns when the copies are complete */
+ROD_API int rod_jpeg_download(rod_jpeg_encoder* enc, uint8_t* host_out, uint32_t* host_len, void* stream);
+
 /* Host-buffer entry points (what a per-image Python/cgo/JNI caller binds): src/dst are HOST
  * pointers laid out by the plan's descriptors; the call stages through pinned memory,
  * overlaps H2D / kernel / D2H in chunks of images, and returns after dst is complete. */

@@ -49,6 +49,13 @@ SYMBOLS = {
     "rod_corrupt_letterbox_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _i, _d, _u64, _u64, _u32, _vp]),
     "rod_restoration_pairs_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _d, _u64, _u64, _u32, _vp]),
     "rod_resize_linear_u8": (_i, [_vp, _i, _i, ctypes.c_int64, _vp, _i, _i, ctypes.c_int64, _vp]),
+    "rod_jpeg_create": (_i, [ctypes.POINTER(ImageDesc), _i, _vp, _u64, ctypes.POINTER(_vp)]),
+    "rod_jpeg_destroy": (None, [_vp]),
+    "rod_jpeg_encode": (_i, [_vp, _vp, _vp]),
+    "rod_jpeg_stream_offset": (_u64, [_vp, _i]),
+    "rod_jpeg_stream_base": (_vp, [_vp]),
+    "rod_jpeg_stream_lengths": (_vp, [_vp]),
+    "rod_jpeg_download": (_i, [_vp, _vp, _vp, _vp]),
     "rod_apply_host": (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _d, _u64, _u64, _u32]),
 }
 

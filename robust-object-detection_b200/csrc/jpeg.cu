@@ -1,0 +1,426 @@
+// jpeg.cu -- SURVEY 8f rank 1: baseline JPEG encoding of a device-resident batch whose bytes equal cv2.imwrite's
+// (OpenCV 4.13.0 = libjpeg-turbo 3.1.2 defaults: YCbCr 4:2:0, quality 95, standard Huffman tables, islow DCT).
+//
+// Reference: scripts/build_corrupted_testsets.py:124 / :164 (`cv2.imwrite(str(dst_img_dir / img_path.name), out)`): the
+// JPEG files are what the evaluation scripts read, so their bytes are part of the test-set semantics.  The arithmetic is
+// rod_jpeg.h (shared with the CPU check against cv2.imencode in tests/emu); this file is its parallel schedule:
+//   jpeg_coef_kernel    one thread per 8x8 block: colour conversion (+ h2v2 chroma), islow DCT, reciprocal quantisation,
+//                       zigzag -> int16 coefficients [MCU][6][64]
+//   jpeg_dummy_kernel   libjpeg's dummy blocks of partial MCUs at the right / bottom edge (DC of the preceding block)
+//   jpeg_bits_kernel    one thread per MCU: bit length of its entropy-coded segment
+//   jpeg_scan_kernel    one CTA per image: exclusive prefix sum of the MCU bit lengths
+//   jpeg_write_kernel   one thread per MCU: its bits at its absolute bit offset of a zeroed big-endian stream (whole 32-bit
+//                       words stored, the two boundary words OR-ed atomically)
+//   jpeg_stuff_kernel   one CTA per image: pad the last byte with ones, insert 0x00 after every 0xFF, append EOI
+// The header (SOI .. SOS) is OpenCV's own for that image size and is prepended on the host.
+#include <algorithm>
+#include <new>
+
+#include "rod_internal.h"
+#include "rod_jpeg_host.h"
+
+namespace rod {
+
+struct JpegImage {
+    uint64_t img_off;        // byte offset of the image in the pixel buffer
+    int64_t pitch;
+    int32_t h, w;
+    int32_t mcu_w, n_mcu;
+    uint32_t mcu_first;      // index of the image's first MCU in the batch-wide MCU arrays
+    uint32_t pad_;
+    uint64_t raw_off, raw_cap;   // unstuffed stream (bytes, 4-byte aligned offset)
+    uint64_t out_off, out_cap;   // stuffed stream + EOI
+};
+
+struct JpegParams {
+    const JpegImage* images;
+    int n_images;
+    const uint8_t* pixels;
+    const jpeg::Tables* tables;
+    int16_t* coef;           // [total MCUs][6][64], zigzag order
+    uint32_t* mcu_bits;      // [total MCUs]: bit length, then (after the scan) bit offset inside the image's stream
+    uint32_t* total_bits;    // [n_images]
+    uint8_t* raw;            // unstuffed streams
+    uint8_t* out;            // stuffed streams
+    uint32_t* out_len;       // [n_images] bytes written to out (incl. EOI); 0xFFFFFFFF: a buffer was too small
+    const uint32_t* mcu_image;   // [total MCUs / 64 + 1]: image of every 64th MCU (search start)
+    uint32_t total_mcu;
+};
+
+__device__ __forceinline__ int jpeg_image_of(const JpegParams& p, uint32_t m) {
+    int i = (int)p.mcu_image[m >> 6];
+    while (i + 1 < p.n_images && p.images[i + 1].mcu_first <= m) ++i;
+    return i;
+}
+
+__global__ void __launch_bounds__(128) jpeg_coef_kernel(JpegParams p) {
+    const uint32_t t = blockIdx.x * 128u + threadIdx.x;
+    const uint32_t m = t / 6u;
+    if (m >= p.total_mcu) return;
+    const int blk = (int)(t - 6u * m);
+    const JpegImage im = p.images[jpeg_image_of(p, m)];
+    const int lm = (int)(m - im.mcu_first), my = lm / im.mcu_w, mx = lm - my * im.mcu_w;
+    const jpeg::Geometry g = jpeg::geometry(im.h, im.w);
+    int16_t* zz = p.coef + ((size_t)m * 6 + blk) * 64;
+    const bool real = blk >= 4 || (2 * mx + (blk & 1) < g.yblk_w && 2 * my + (blk >> 1) < g.yblk_h);
+    if (!real) {
+        for (int z = 0; z < 64; ++z) zz[z] = 0;   // DC set by jpeg_dummy_kernel
+        return;
+    }
+    int d[64];
+    jpeg::block_samples(p.pixels + im.img_off, (long)im.pitch, g, mx, my, blk, d);
+    jpeg::fdct_islow(d);
+    const int tq = blk < 4 ? 0 : 1;
+    const jpeg::Tables& tb = *p.tables;
+#pragma unroll
+    for (int z = 0; z < 64; ++z) {
+        const int nat = jpeg::natural_order(z);
+        zz[z] = (int16_t)jpeg::quantize(d[nat], tb.recip[tq][nat], tb.corr[tq][nat], tb.shift[tq][nat]);
+    }
+}
+
+// jccoefct.c compress_data: dummy blocks of a partial MCU carry the DC of the block before them (in MCU order), AC zero.
+__global__ void __launch_bounds__(128) jpeg_dummy_kernel(JpegParams p) {
+    const uint32_t m = blockIdx.x * 128u + threadIdx.x;
+    if (m >= p.total_mcu) return;
+    const JpegImage im = p.images[jpeg_image_of(p, m)];
+    const int lm = (int)(m - im.mcu_first), my = lm / im.mcu_w, mx = lm - my * im.mcu_w;
+    const jpeg::Geometry g = jpeg::geometry(im.h, im.w);
+    if (2 * mx + 1 < g.yblk_w && 2 * my + 1 < g.yblk_h) return;   // all four luma blocks are real
+    int16_t* mc = p.coef + (size_t)m * 6 * 64;
+    for (int blk = 1; blk < 4; ++blk) {
+        const bool real = 2 * mx + (blk & 1) < g.yblk_w && 2 * my + (blk >> 1) < g.yblk_h;
+        if (!real) mc[64 * blk] = mc[64 * (blk - 1)];
+    }
+}
+
+struct GlobalBitWriter {   // MSB-first bits into a zeroed big-endian stream; whole words stored, boundary words OR-ed
+    uint32_t* words;       // the image's stream as 32-bit words (device memory is little-endian: words are byte-swapped)
+    uint64_t acc;          // pending bits, left-aligned below bit (64 - fill) ... kept in the high `fill` bits
+    int fill;              // pending bit count (< 32 after a flush)
+    uint32_t widx;         // index of the word the pending bits start in
+    bool first;            // the next flushed word may be shared with the previous MCU
+    __device__ __forceinline__ void init(uint8_t* stream, uint32_t bitpos) {
+        words = reinterpret_cast<uint32_t*>(stream);
+        widx = bitpos >> 5;
+        fill = (int)(bitpos & 31u);   // the leading bits of the first word belong to the previous MCU: zeros here
+        acc = 0;
+        first = true;
+    }
+    __device__ __forceinline__ void put(uint32_t code, int size) {
+        acc |= (uint64_t)code << (64 - fill - size);
+        fill += size;
+        if (fill >= 32) {
+            const uint32_t w = (uint32_t)(acc >> 32);
+            const uint32_t be = __byte_perm(w, 0u, 0x0123);
+            if (first) { atomicOr(words + widx, be); first = false; }
+            else words[widx] = be;
+            ++widx;
+            acc <<= 32;
+            fill -= 32;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (fill > 0) atomicOr(words + widx, __byte_perm((uint32_t)(acc >> 32), 0u, 0x0123));
+    }
+};
+
+template <typename Sink>
+__device__ __forceinline__ void jpeg_encode_mcu(const JpegParams& p, const JpegImage& im, uint32_t m, Sink& sink) {
+    const int16_t* mc = p.coef + (size_t)m * 6 * 64;
+    const jpeg::Tables& tb = *p.tables;
+    const bool first_mcu = (m == im.mcu_first);
+#pragma unroll 1
+    for (int blk = 0; blk < 6; ++blk) {
+        int last;
+        if (blk >= 1 && blk <= 3) last = mc[64 * (blk - 1)];
+        else if (first_mcu) last = 0;
+        else last = (mc - 6 * 64)[64 * (blk == 0 ? 3 : blk)];
+        const int hs = blk < 4 ? 0 : 1;
+        jpeg::encode_block(mc + 64 * blk, last, tb.ehufco[hs], tb.ehufsi[hs], tb.ehufco[2 + hs], tb.ehufsi[2 + hs], sink);
+    }
+}
+
+__global__ void __launch_bounds__(128) jpeg_bits_kernel(JpegParams p) {
+    const uint32_t m = blockIdx.x * 128u + threadIdx.x;
+    if (m >= p.total_mcu) return;
+    const JpegImage im = p.images[jpeg_image_of(p, m)];
+    jpeg::BitCounter bc;
+    jpeg_encode_mcu(p, im, m, bc);
+    p.mcu_bits[m] = bc.bits;
+}
+
+// one CTA per image: mcu_bits := exclusive prefix sum; total_bits[image] := sum
+__global__ void __launch_bounds__(1024) jpeg_scan_kernel(JpegParams p) {
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry_s;
+    const JpegImage im = p.images[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < im.n_mcu; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        const uint32_t v = i < im.n_mcu ? p.mcu_bits[im.mcu_first + i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t s = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sum[lane] = s;   // inclusive sums of the warps
+        }
+        __syncthreads();
+        const uint32_t before = carry_s + (warp > 0 ? warp_sum[warp - 1] : 0u) + (x - v);
+        if (i < im.n_mcu) p.mcu_bits[im.mcu_first + i] = before;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += warp_sum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) p.total_bits[blockIdx.x] = carry_s;
+}
+
+__global__ void __launch_bounds__(128) jpeg_write_kernel(JpegParams p) {
+    const uint32_t m = blockIdx.x * 128u + threadIdx.x;
+    if (m >= p.total_mcu) return;
+    const int ii = jpeg_image_of(p, m);
+    const JpegImage im = p.images[ii];
+    if (((uint64_t)p.total_bits[ii] + 7) / 8 + 8 > im.raw_cap) return;   // too small: reported by jpeg_stuff_kernel
+    GlobalBitWriter w;
+    w.init(p.raw + im.raw_off, p.mcu_bits[m]);
+    jpeg_encode_mcu(p, im, m, w);
+    w.finish();
+}
+
+// one CTA per image: out := stuffed(raw, padded with ones to a byte) + EOI
+__global__ void __launch_bounds__(1024) jpeg_stuff_kernel(JpegParams p) {
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry_s;
+    const JpegImage im = p.images[blockIdx.x];
+    const uint32_t bits = p.total_bits[blockIdx.x];
+    const uint32_t nbytes = (bits + 7u) >> 3;
+    if ((uint64_t)nbytes + 8 > im.raw_cap) {
+        if (threadIdx.x == 0) p.out_len[blockIdx.x] = 0xFFFFFFFFu;
+        return;
+    }
+    uint8_t* raw = p.raw + im.raw_off;
+    uint8_t* out = p.out + im.out_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        carry_s = 0;
+        if (bits & 7u) raw[nbytes - 1] |= (uint8_t)(0xFFu >> (bits & 7u));   // flush_bits: the last byte is padded with ones
+    }
+    __syncthreads();
+    bool overflow = false;
+    for (uint32_t base = 0; base < nbytes; base += 1024u * 16u) {
+        // 16 bytes per thread: count the 0xFF bytes, scan, then copy with the inserted zeros
+        const uint32_t b0 = base + 16u * threadIdx.x;
+        uint32_t wds[4] = {0u, 0u, 0u, 0u};
+        int n_here = 0;
+        if (b0 < nbytes) {
+            n_here = (int)min(16u, nbytes - b0);
+            const uint4 v = *reinterpret_cast<const uint4*>(raw + b0);   // raw_off is 16-byte aligned and raw_cap padded
+            wds[0] = v.x; wds[1] = v.y; wds[2] = v.z; wds[3] = v.w;
+        }
+        uint32_t nff = 0;
+        for (int k = 0; k < n_here; ++k) nff += ((wds[k >> 2] >> (8 * (k & 3))) & 0xFFu) == 0xFFu ? 1u : 0u;
+        uint32_t x = nff;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t s = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sum[lane] = s;
+        }
+        __syncthreads();
+        const uint32_t ff_before = carry_s + (warp > 0 ? warp_sum[warp - 1] : 0u) + (x - nff);
+        uint64_t o = (uint64_t)b0 + ff_before;
+        if (o + (uint64_t)n_here + nff + 2 > im.out_cap) overflow = overflow || n_here > 0;
+        else
+            for (int k = 0; k < n_here; ++k) {
+                const uint8_t b = (uint8_t)(wds[k >> 2] >> (8 * (k & 3)));
+                out[o++] = b;
+                if (b == 0xFF) out[o++] = 0;
+            }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += warp_sum[31];
+        __syncthreads();
+    }
+    const int any_overflow = __syncthreads_or(overflow ? 1 : 0);
+    if (threadIdx.x == 0) {
+        const uint64_t end = (uint64_t)nbytes + carry_s;
+        if (any_overflow || end + 2 > im.out_cap) p.out_len[blockIdx.x] = 0xFFFFFFFFu;
+        else {
+            out[end] = 0xFF; out[end + 1] = 0xD9;
+            p.out_len[blockIdx.x] = (uint32_t)(end + 2);
+        }
+    }
+}
+
+}  // namespace rod
+
+using namespace rod;
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+struct rod_jpeg_encoder {
+    int n_images = 0;
+    std::vector<JpegImage> h_images;
+    std::vector<uint32_t> h_mcu_image;
+    uint32_t total_mcu = 0;
+    uint64_t raw_bytes = 0, out_bytes = 0;
+    JpegImage* d_images = nullptr;
+    uint32_t* d_mcu_image = nullptr;
+    jpeg::Tables* d_tables = nullptr;
+    int16_t* d_coef = nullptr;
+    uint32_t* d_mcu_bits = nullptr;
+    uint32_t* d_total_bits = nullptr;
+    uint8_t* d_raw = nullptr;
+    uint8_t* d_out = nullptr;
+    uint32_t* d_out_len = nullptr;
+    std::vector<uint64_t> out_off;
+};
+
+extern "C" void rod_jpeg_destroy(rod_jpeg_encoder* e) {
+    if (e == nullptr) return;
+    void* ptrs[] = {e->d_images, e->d_mcu_image, e->d_tables, e->d_coef, e->d_mcu_bits, e->d_total_bits, e->d_raw, e->d_out, e->d_out_len};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    delete e;
+}
+
+// `images`: n descriptors (src_offset / src_pitch / height / width describe the pixels to encode; the dst_* fields are
+// ignored).  `header`: the bytes SOI .. SOS OpenCV writes with the wanted parameters (any image size): its DQT / DHT
+// segments define the tables.  Output streams are laid out back to back; rod_jpeg_stream_offset tells where.
+extern "C" int rod_jpeg_create(const rod_image_desc* images, int n_images, const uint8_t* header, uint64_t header_len,
+                               rod_jpeg_encoder** out_enc) {
+    if (out_enc == nullptr) return ROD_ERR_INVALID_ARG;
+    *out_enc = nullptr;
+    if (images == nullptr || n_images < 1 || header == nullptr) return ROD_ERR_INVALID_ARG;
+    jpeg::HeaderInfo info;
+    jpeg::Tables tb;
+    if (!jpeg::parse_header(header, (size_t)header_len, &info, &tb)) return ROD_ERR_UNSUPPORTED;
+    rod_jpeg_encoder* e = new (std::nothrow) rod_jpeg_encoder();
+    if (e == nullptr) return ROD_ERR_OOM;
+    e->n_images = n_images;
+    e->h_images.resize(n_images);
+    e->out_off.resize(n_images + 1);
+    uint64_t mcu = 0, raw = 0, out = 0;
+    for (int i = 0; i < n_images; ++i) {
+        const rod_image_desc& d = images[i];
+        if (d.height < 1 || d.width < 1 || d.height > 65535 || d.width > 65535 || d.src_pitch < 3LL * d.width) {
+            delete e;
+            return ROD_ERR_INVALID_ARG;
+        }
+        JpegImage& im = e->h_images[i];
+        im.img_off = d.src_offset; im.pitch = d.src_pitch; im.h = d.height; im.w = d.width;
+        im.mcu_w = (d.width + 15) / 16;
+        im.n_mcu = im.mcu_w * ((d.height + 15) / 16);
+        im.mcu_first = (uint32_t)mcu;
+        im.pad_ = 0;
+        // an MCU of uniform noise codes to ~0.6 of its 768 raw bytes at quality 95; 1.25x raw + 4 KB leaves ample room and is
+        // checked on the device (out_len = 0xFFFFFFFF: the caller falls back to its own encoder for that image)
+        const uint64_t cap = ((uint64_t)im.n_mcu * 960 + 4096 + 15) & ~(uint64_t)15;
+        im.raw_off = raw; im.raw_cap = cap;
+        im.out_off = out; im.out_cap = cap + cap / 8;
+        e->out_off[i] = out;
+        raw += cap;
+        out += (im.out_cap + 15) & ~(uint64_t)15;
+        mcu += (uint64_t)im.n_mcu;
+        if (mcu > 0x7FFFFFFFull) { delete e; return ROD_ERR_UNSUPPORTED; }
+    }
+    e->out_off[n_images] = out;
+    e->total_mcu = (uint32_t)mcu;
+    e->raw_bytes = raw; e->out_bytes = out;
+    e->h_mcu_image.resize(e->total_mcu / 64 + 2);
+    {
+        int img = 0;
+        for (uint32_t b = 0; b < e->h_mcu_image.size(); ++b) {
+            const uint64_t m = (uint64_t)b * 64;
+            while (img + 1 < n_images && e->h_images[img + 1].mcu_first <= m) ++img;
+            e->h_mcu_image[b] = (uint32_t)img;
+        }
+    }
+    cudaError_t err = cudaSuccess;
+    auto alloc = [&](void** p, size_t n) { if (err == cudaSuccess) err = cudaMalloc(p, n); };
+    alloc((void**)&e->d_images, sizeof(JpegImage) * n_images);
+    alloc((void**)&e->d_mcu_image, sizeof(uint32_t) * e->h_mcu_image.size());
+    alloc((void**)&e->d_tables, sizeof(jpeg::Tables));
+    alloc((void**)&e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
+    alloc((void**)&e->d_mcu_bits, sizeof(uint32_t) * (size_t)e->total_mcu);
+    alloc((void**)&e->d_total_bits, sizeof(uint32_t) * n_images);
+    alloc((void**)&e->d_raw, e->raw_bytes + 64);
+    alloc((void**)&e->d_out, e->out_bytes + 64);
+    alloc((void**)&e->d_out_len, sizeof(uint32_t) * n_images);
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_images, e->h_images.data(), sizeof(JpegImage) * n_images, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_mcu_image, e->h_mcu_image.data(), sizeof(uint32_t) * e->h_mcu_image.size(), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_tables, &tb, sizeof(tb), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        const int rc = cuda_fail(err);
+        rod_jpeg_destroy(e);
+        return rc;
+    }
+    *out_enc = e;
+    return ROD_OK;
+}
+
+extern "C" uint64_t rod_jpeg_stream_offset(const rod_jpeg_encoder* e, int i) {
+    return (e != nullptr && i >= 0 && i <= e->n_images) ? e->out_off[i] : 0;
+}
+extern "C" const uint8_t* rod_jpeg_stream_base(const rod_jpeg_encoder* e) { return e ? e->d_out : nullptr; }
+extern "C" const uint32_t* rod_jpeg_stream_lengths(const rod_jpeg_encoder* e) { return e ? e->d_out_len : nullptr; }
+
+// Encode every image of `pixels` (device pointer, laid out by the descriptors given at creation).  Afterwards the device
+// arrays rod_jpeg_stream_base() + rod_jpeg_stream_offset(i) hold the entropy-coded segment + EOI of image i and
+// rod_jpeg_stream_lengths()[i] its length (0xFFFFFFFF: did not fit); the file is OpenCV's header for that size + those bytes.
+extern "C" int rod_jpeg_encode(rod_jpeg_encoder* e, const uint8_t* pixels, void* stream_) {
+    if (e == nullptr || pixels == nullptr) return ROD_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    JpegParams p;
+    p.images = e->d_images; p.n_images = e->n_images; p.pixels = pixels; p.tables = e->d_tables; p.coef = e->d_coef;
+    p.mcu_bits = e->d_mcu_bits; p.total_bits = e->d_total_bits; p.raw = e->d_raw; p.out = e->d_out; p.out_len = e->d_out_len;
+    p.mcu_image = e->d_mcu_image; p.total_mcu = e->total_mcu;
+    ROD_CUDA(cudaMemsetAsync(e->d_raw, 0, e->raw_bytes + 64, stream));
+    const unsigned mcu_blocks = (e->total_mcu + 127u) / 128u;
+    const unsigned blk_blocks = (unsigned)(((uint64_t)e->total_mcu * 6 + 127) / 128);
+    jpeg_coef_kernel<<<blk_blocks, 128, 0, stream>>>(p);
+    jpeg_dummy_kernel<<<mcu_blocks, 128, 0, stream>>>(p);
+    jpeg_bits_kernel<<<mcu_blocks, 128, 0, stream>>>(p);
+    jpeg_scan_kernel<<<e->n_images, 1024, 0, stream>>>(p);
+    jpeg_write_kernel<<<mcu_blocks, 128, 0, stream>>>(p);
+    jpeg_stuff_kernel<<<e->n_images, 1024, 0, stream>>>(p);
+    ROD_CUDA(cudaGetLastError());
+    return ROD_OK;
+}
+
+// Copy the lengths and the encoded streams to the host: host_len[n_images]; image i's bytes land at
+// host_out + rod_jpeg_stream_offset(i) (host_out: rod_jpeg_stream_offset(n_images) bytes, ideally page-locked).
+// Returns after the copies are complete.  Images whose length is 0xFFFFFFFF are skipped.
+extern "C" int rod_jpeg_download(rod_jpeg_encoder* e, uint8_t* host_out, uint32_t* host_len, void* stream_) {
+    if (e == nullptr || host_out == nullptr || host_len == nullptr) return ROD_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ROD_CUDA(cudaMemcpyAsync(host_len, e->d_out_len, sizeof(uint32_t) * e->n_images, cudaMemcpyDeviceToHost, stream));
+    ROD_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < e->n_images; ++i) {
+        if (host_len[i] == 0xFFFFFFFFu || host_len[i] == 0) continue;
+        ROD_CUDA(cudaMemcpyAsync(host_out + e->out_off[i], e->d_out + e->out_off[i], host_len[i], cudaMemcpyDeviceToHost, stream));
+    }
+    ROD_CUDA(cudaStreamSynchronize(stream));
+    return ROD_OK;
+}

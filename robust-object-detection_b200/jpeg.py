@@ -1,0 +1,98 @@
+"""Device-side JPEG encoding whose files equal cv2.imwrite's byte for byte.
+
+`cv2.imwrite(str(dst_img_dir / img_path.name), out)` (scripts/build_corrupted_testsets.py:124, :164) is the last step of
+the test-set build; with the corruption on the GPU it is what the build spends its time in.  JpegEncoder encodes a
+device-resident batch (HWC BGR uint8, the layout of a CorruptionPlan) with rod_jpeg_encode: OpenCV 4.13's own parameters
+(libjpeg-turbo defaults: YCbCr 4:2:0, quality 95, standard Huffman tables, islow DCT), its own header bytes (taken from
+cv2.imencode on the host, per image size) and entropy-coded data that is bit-identical to libjpeg-turbo's.  No CPU
+fallback inside: an image whose stream does not fit its device buffer comes back as None and the caller decides."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .batch import _ptr, _stream_handle
+
+_HEADER_TEMPLATE = None
+
+
+def _header_template() -> bytes:
+    """SOI .. SOS as OpenCV writes them with its default parameters (the tables do not depend on the image size)."""
+    global _HEADER_TEMPLATE
+    if _HEADER_TEMPLATE is None:
+        import cv2
+        ok, buf = cv2.imencode(".jpg", np.zeros((16, 16, 3), np.uint8))
+        if not ok:
+            raise RuntimeError("cv2.imencode failed")
+        b = buf.tobytes()
+        i = 2
+        while True:
+            if b[i] != 0xFF:
+                raise RuntimeError("unexpected JPEG header layout")
+            seg = (b[i + 2] << 8) | b[i + 3]
+            if b[i + 1] == 0xDA:
+                _HEADER_TEMPLATE = b[:i + 2 + seg]
+                break
+            i += 2 + seg
+    return _HEADER_TEMPLATE
+
+
+def header_for(h: int, w: int) -> bytes:
+    """The template with the frame size of SOF0 set to h x w."""
+    t = bytearray(_header_template())
+    i = 2
+    while t[i + 1] != 0xC0:
+        i += 2 + ((t[i + 2] << 8) | t[i + 3])
+    t[i + 5:i + 9] = bytes([h >> 8, h & 255, w >> 8, w & 255])
+    return bytes(t)
+
+
+class JpegEncoder:
+    """Encoder for one batch layout: images of `shapes` at byte `offsets` (row pitch 3 * w unless `pitches` is given)."""
+
+    def __init__(self, shapes: Sequence[Tuple[int, int]], offsets: Sequence[int], pitches: Optional[Sequence[int]] = None):
+        N.require_device()
+        n = len(shapes)
+        descs = (N.ImageDesc * n)()
+        for i, (h, w) in enumerate(shapes):
+            descs[i].src_offset = descs[i].dst_offset = int(offsets[i])
+            descs[i].height, descs[i].width = int(h), int(w)
+            descs[i].src_pitch = descs[i].dst_pitch = int(pitches[i]) if pitches is not None else 3 * int(w)
+        hdr = _header_template()
+        hbuf = (ctypes.c_uint8 * len(hdr)).from_buffer_copy(hdr)
+        handle = ctypes.c_void_p()
+        N.check(N.lib().rod_jpeg_create(descs, n, hbuf, len(hdr), ctypes.byref(handle)), "rod_jpeg_create")
+        self._h = handle
+        self.shapes = [(int(h), int(w)) for h, w in shapes]
+        self.n_images = n
+        self._off = [int(N.lib().rod_jpeg_stream_offset(handle, i)) for i in range(n + 1)]
+        self._host = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                N.lib().rod_jpeg_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def encode(self, pixels, stream=None) -> List[Optional[bytes]]:
+        """pixels: CUDA uint8 tensor holding the batch.  Returns one complete JPEG file (bytes) per image, None where the
+        encoded stream did not fit its device buffer."""
+        import torch
+        st = _stream_handle(stream)
+        N.check(N.lib().rod_jpeg_encode(self._h, _ptr(pixels), st), "rod_jpeg_encode")
+        if self._host is None:
+            self._host = torch.empty(max(self._off[-1], 16), dtype=torch.uint8).pin_memory()
+        lens = np.zeros(self.n_images, dtype=np.uint32)
+        N.check(N.lib().rod_jpeg_download(self._h, self._host.data_ptr(), lens.ctypes.data, st), "rod_jpeg_download")
+        host = self._host.numpy()
+        out: List[Optional[bytes]] = []
+        for i, (h, w) in enumerate(self.shapes):
+            n = int(lens[i])
+            out.append(None if n == 0xFFFFFFFF else header_for(h, w) + host[self._off[i]:self._off[i] + n].tobytes())
+        return out

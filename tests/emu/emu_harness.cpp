@@ -1007,3 +1007,93 @@ extern "C" int emu_letterbox_u8(const uint8_t* img, int h, int w, long pitch, ui
         }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// JPEG: sequential replay of the device encoder (csrc/jpeg.cu) from the same rod_jpeg.h arithmetic, in the same
+// passes: (1) quantised coefficients of every block incl. libjpeg's dummy blocks at the right / bottom edge,
+// (2) bit length of every MCU, (3) prefix sum, (4) every MCU written at its bit offset, (5) final 1-padding, 0xFF
+// stuffing, EOI.  `header` = the bytes SOI .. SOS that OpenCV writes for this size.  Returns the file length, or < 0.
+#include "../../robust-object-detection_b200/csrc/rod_jpeg_host.h"
+
+namespace {
+struct WordWriter {   // MSB-first bits into a zero-initialised big-endian byte stream, at an absolute bit offset
+    uint8_t* buf;
+    uint64_t pos;
+    void put(uint32_t code, int size) {
+        for (int b = size - 1; b >= 0; --b, ++pos)
+            if ((code >> b) & 1u) buf[pos >> 3] |= (uint8_t)(0x80u >> (pos & 7));
+    }
+};
+}  // namespace
+
+extern "C" long emu_jpeg_encode(const uint8_t* bgr, int h, int w, long pitch, const uint8_t* header, long header_len,
+                                uint8_t* out, long out_cap) {
+    using namespace rod::jpeg;
+    HeaderInfo info;
+    Tables tb;
+    if (!parse_header(header, (size_t)header_len, &info, &tb)) return -1;
+    if (info.height != h || info.width != w) return -2;
+    const Geometry g = geometry(h, w);
+    const int n_mcu = g.mcu_w * g.mcu_h;
+    std::vector<int16_t> coef((size_t)n_mcu * 6 * 64);
+    // pass 1: coefficients (zigzag order); dummy luma blocks: zero AC, DC of the preceding block of the MCU
+    for (int my = 0; my < g.mcu_h; ++my)
+        for (int mx = 0; mx < g.mcu_w; ++mx) {
+            int16_t* mc = coef.data() + ((size_t)my * g.mcu_w + mx) * 6 * 64;
+            for (int blk = 0; blk < 6; ++blk) {
+                int16_t* zz = mc + 64 * blk;
+                const bool real = blk >= 4 || (2 * mx + (blk & 1) < g.yblk_w && 2 * my + (blk >> 1) < g.yblk_h);
+                if (!real) {
+                    memset(zz, 0, 128);
+                    zz[0] = (zz - 64)[0];
+                    continue;
+                }
+                int d[64];
+                block_samples(bgr, pitch, g, mx, my, blk, d);
+                fdct_islow(d);
+                const int t = blk < 4 ? 0 : 1;
+                for (int z = 0; z < 64; ++z) {
+                    const int nat = natural_order(z);
+                    zz[z] = (int16_t)quantize(d[nat], tb.recip[t][nat], tb.corr[t][nat], tb.shift[t][nat]);
+                }
+            }
+        }
+    // pass 2 + 3: bit length per MCU, offsets.  DC predictor of a block = DC of the previous block of its component.
+    auto encode_mcu = [&](int m, auto& sink) {
+        const int16_t* mc = coef.data() + (size_t)m * 6 * 64;
+        for (int blk = 0; blk < 6; ++blk) {
+            int last;
+            if (blk >= 1 && blk <= 3) last = mc[64 * (blk - 1)];
+            else if (m == 0) last = 0;
+            else last = (mc - 6 * 64)[64 * (blk == 0 ? 3 : blk)];
+            const int hs = blk < 4 ? 0 : 1;
+            encode_block(mc + 64 * blk, last, tb.ehufco[hs], tb.ehufsi[hs], tb.ehufco[2 + hs], tb.ehufsi[2 + hs], sink);
+        }
+    };
+    std::vector<uint64_t> off((size_t)n_mcu + 1, 0);
+    for (int m = 0; m < n_mcu; ++m) {
+        BitCounter bc;
+        encode_mcu(m, bc);
+        off[m + 1] = off[m] + bc.bits;
+    }
+    const uint64_t total_bits = off[n_mcu];
+    const size_t raw_bytes = (size_t)((total_bits + 7) >> 3);
+    std::vector<uint8_t> raw(raw_bytes + 8, 0);
+    for (int m = 0; m < n_mcu; ++m) {
+        WordWriter ww{raw.data(), off[m]};
+        encode_mcu(m, ww);
+    }
+    if (total_bits & 7) raw[raw_bytes - 1] |= (uint8_t)(0xFFu >> (total_bits & 7));   // flush_bits: pad with ones
+    // pass 5: stuffing
+    long o = 0;
+    if (header_len > out_cap) return -3;
+    memcpy(out, header, (size_t)header_len);
+    o = header_len;
+    for (size_t i = 0; i < raw_bytes; ++i) {
+        if (o + 4 > out_cap) return -3;
+        out[o++] = raw[i];
+        if (raw[i] == 0xFF) out[o++] = 0x00;
+    }
+    out[o++] = 0xFF; out[o++] = 0xD9;
+    return o;
+}

@@ -414,3 +414,46 @@ def test_emu_filter2d_general_angles(emu):
     got = np.zeros_like(img)
     emu.emu_filter2d(_p(img), _p(got), h, w, 3 * w, 3 * w, _p(kern, ctypes.c_float), 9)
     assert sha(got) == meta["sha"][f"9_45_{name}"]
+
+
+def jpeg_header(h, w):
+    """The bytes SOI .. SOS that OpenCV writes for an h x w BGR image with its default parameters."""
+    import cv2
+    ok, buf = cv2.imencode(".jpg", np.zeros((h, w, 3), np.uint8))
+    assert ok
+    b = buf.tobytes()
+    i = 2
+    while True:
+        assert b[i] == 0xFF
+        L = (b[i + 2] << 8) | b[i + 3]
+        if b[i + 1] == 0xDA:
+            return b[:i + 2 + L]
+        i += 2 + L
+
+
+def test_emu_jpeg_encoder_matches_cv2(emu):
+    """The encoder arithmetic of csrc/rod_jpeg.h (colour conversion, h2v2 chroma, islow DCT, reciprocal quantisation,
+    Huffman coding with libjpeg's dummy blocks, stuffing) replayed on the CPU: the file must equal cv2.imencode's byte for
+    byte -- sizes that are not multiples of 8 / 16, uniform noise (every coefficient busy), smooth and constant content."""
+    import cv2
+    emu.emu_jpeg_encode.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_long,
+                                    ctypes.POINTER(ctypes.c_uint8), ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.c_long]
+    emu.emu_jpeg_encode.restype = ctypes.c_long
+    shapes = [(16, 16), (8, 8), (1, 1), (37, 53), (64, 48), (17, 33), (100, 9), (9, 100), (120, 200), (97, 133), (765, 1360), (38, 40)]
+    for i, (h, w) in enumerate(shapes):
+        variants = [synth(8000 + i, h, w)]
+        if h * w < 100000:
+            variants += [cv2.GaussianBlur(synth(8100 + i, h, w), (0, 0), 2.5), np.full((h, w, 3), 255 if i % 2 else 0, np.uint8),
+                         (synth(8200 + i, h, w) > 127).astype(np.uint8) * 255]
+        hdr = np.frombuffer(jpeg_header(h, w), np.uint8).copy()
+        for v, img in enumerate(variants):
+            want = cv2.imencode(".jpg", img)[1].tobytes()
+            pitch = 3 * w + (0 if v % 2 else 7)
+            buf = np.full((h, pitch), 0xAB, np.uint8)
+            buf[:, :3 * w] = img.reshape(h, 3 * w)
+            out = np.zeros(3 * h * w + 4096, np.uint8)
+            n = emu.emu_jpeg_encode(_p(buf), h, w, pitch, _p(hdr), len(hdr), _p(out), len(out))
+            assert n > 0, (h, w, v, n)
+            got = out[:n].tobytes()
+            assert len(got) == len(want) and got == want, (h, w, v, len(got), len(want),
+                                                           next((k for k in range(min(len(got), len(want))) if got[k] != want[k]), -1))

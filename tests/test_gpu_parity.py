@@ -1208,3 +1208,43 @@ def test_fused_letterbox_random_stress(torch_):
             op = int(ops_host[i])
             cor = orc.add_noise_field(img, fields[i]) if op == 1 else orc.apply_op(img, op)
             assert np.array_equal(got[i], orc.letterbox_norm_f16(cor, oh, ow, 114)), (trial, i, shapes[i], op)
+
+
+def test_jpeg_encoder_matches_cv2(torch_):
+    """the device JPEG encoder (rod_jpeg_encode) against cv2.imencode, byte for byte: a ragged batch of
+    sizes that are not multiples of 8 / 16 (libjpeg's dummy blocks), uniform noise (long streams, 0xFF stuffing), smooth
+    and constant content, a pitched layout, and the BASELINE frame size."""
+    import cv2
+    from robust_object_detection_b200.batch import CorruptionPlan
+    from robust_object_detection_b200.jpeg import JpegEncoder
+    shapes = [(16, 16), (8, 8), (1, 1), (37, 53), (64, 48), (17, 33), (100, 9), (9, 100), (120, 200), (97, 133), (38, 40),
+              (765, 1360), (360, 480), (540, 960)]
+    imgs = []
+    for i, (h, w) in enumerate(shapes):
+        kind = i % 4
+        if kind == 0 or h * w > 100000:
+            imgs.append(synth(9000 + i, h, w))
+        elif kind == 1:
+            imgs.append(cv2.GaussianBlur(synth(9100 + i, h, w), (0, 0), 2.5))
+        elif kind == 2:
+            imgs.append(np.full((h, w, 3), 255 if i % 8 == 2 else 0, np.uint8))
+        else:
+            imgs.append((synth(9200 + i, h, w) > 127).astype(np.uint8) * 255)
+    plan = CorruptionPlan.ragged(shapes)
+    dev = torch_.from_numpy(plan.pack(imgs)).cuda()
+    enc = JpegEncoder(shapes, plan.src_offsets)
+    for rep in range(2):   # a second run reuses the zeroed stream buffers
+        files = enc.encode(dev)
+        for i, (img, got) in enumerate(zip(imgs, files)):
+            want = cv2.imencode(".jpg", img)[1].tobytes()
+            assert got is not None and got == want, (rep, i, shapes[i], None if got is None else len(got), len(want))
+    # pitched rows
+    pitches = [3 * w + 5 for _, w in shapes]
+    offs = np.concatenate([[0], np.cumsum([(h * q + 255) // 256 * 256 for (h, _), q in zip(shapes, pitches)])])
+    host = np.full(int(offs[-1]), 0xAB, np.uint8)
+    for img, o, q in zip(imgs, offs, pitches):
+        h, w, _ = img.shape
+        host[o:o + h * q].reshape(h, q)[:, :3 * w] = img.reshape(h, 3 * w)
+    files = JpegEncoder(shapes, offs[:-1], pitches).encode(torch_.from_numpy(host).cuda())
+    for i, (img, got) in enumerate(zip(imgs, files)):
+        assert got == cv2.imencode(".jpg", img)[1].tobytes(), (i, shapes[i])
