@@ -183,7 +183,8 @@ ROD_API int rod_resize_linear_u8(const uint8_t* src, int h, int w, int64_t src_p
 typedef struct rod_jpeg_encoder rod_jpeg_encoder;
 ROD_API int rod_jpeg_create(const rod_image_desc* images, int n_images, const uint8_t* header, uint64_t header_len,
                     rod_jpeg_encoder** out_enc);
-ROD_API void rod_jpeg_destroy(rod_jpeg_encoder* enc);
+ROD_API void rod_jpeg_destroy(rod_jpeg_encoder* enc);   /* its large device buffers go to a cache for the next encoder */
+ROD_API void rod_jpeg_trim(void);                         /* frees that cache */
 ROD_API int rod_jpeg_encode(rod_jpeg_encoder* enc, const uint8_t* pixels, void* stream);
 ROD_API uint64_t rod_jpeg_stream_offset(const rod_jpeg_encoder* enc, int i);
 ROD_API const uint8_t* rod_jpeg_stream_base(const rod_jpeg_encoder* enc);

@@ -51,6 +51,7 @@ SYMBOLS = {
     "rod_resize_linear_u8": (_i, [_vp, _i, _i, ctypes.c_int64, _vp, _i, _i, ctypes.c_int64, _vp]),
     "rod_jpeg_create": (_i, [ctypes.POINTER(ImageDesc), _i, _vp, _u64, ctypes.POINTER(_vp)]),
     "rod_jpeg_destroy": (None, [_vp]),
+    "rod_jpeg_trim": (None, []),
     "rod_jpeg_encode": (_i, [_vp, _vp, _vp]),
     "rod_jpeg_stream_offset": (_u64, [_vp, _i]),
     "rod_jpeg_stream_base": (_vp, [_vp]),

@@ -4,9 +4,12 @@ Same module surface (constants, set_seed, build_yolo_testsets, build_coco_testse
 for Test_Clean / Test_Noise / Test_Blur / Test_LowRes the images of `images/val` are read with cv2.imread, corrupted and
 written with cv2.imwrite under the same file name; labels / annotations are copied; data.yaml is written
 (build_corrupted_testsets.py:62-166).  The corruption itself runs on the GPU, one ragged batch at a time
-(rod_apply_host: pinned staging, chunked H2D / kernel / D2H), while JPEG decode and encode -- still the reference's
-OpenCV codec, so files are byte-identical to the reference's -- run on a host thread pool around it (the next batch
-decodes and the previous one encodes while a batch is on the GPU; a tree's decoded frames are reused by its four variants).
+while JPEG decoding -- the reference's OpenCV codec -- runs on a host thread pool around it (the next batch decodes
+while a batch is on the GPU; a tree's decoded frames are reused by its four variants).  JPEG ENCODING runs on the GPU too
+(`ENCODER = "gpu"`: rod_jpeg_encode, libjpeg-turbo's integer algorithms restated in CUDA, the header bytes taken from
+OpenCV itself): the corrupted frames never leave the device, only the compressed streams do, and the files are
+byte-identical to cv2.imwrite's (tested).  `ENCODER = "host"` keeps cv2.imwrite on the I/O threads (rod_apply_host:
+pinned staging, chunked H2D / kernel / D2H); other file types than .jpg / .jpeg always take that route.
 
 RNG: Test_Noise draws each image's field from NumPy's global legacy generator in glob order after np.random.seed(SEED)
 -- the same stream as the reference's np.random.normal calls, regenerated bit for bit by csrc/np_legacy_rng.cpp with the
@@ -45,7 +48,9 @@ PHILOX_SEED = SEED
 BATCH_BYTES = 512 << 20    # decoded source bytes per GPU batch
 NOISE_BATCH_BYTES = 128 << 20   # ... of a compat-noise batch (its float32 field is 4x that, page-locked)
 IO_THREADS = 16
+ENCODER = "gpu"            # "gpu": device JPEG encoder for .jpg / .jpeg outputs (same bytes as cv2.imwrite) | "host": cv2.imwrite
 DECODE_CACHE_BYTES = 8 << 30  # decoded frames of one tree kept for its later variants (548 VisDrone val frames ~ 2.3 GB)
+DEVICE_CACHE_BYTES = 8 << 30   # ... and their uploaded batches kept on the GPU with their JPEG encoders (ENCODER = "gpu"; ~5 bytes of device memory per cached byte)
 
 VARIANTS = ["Test_Clean", "Test_Noise", "Test_Blur", "Test_LowRes"]
 _OPS = {"Test_Noise": N.OP_NOISE, "Test_Blur": N.OP_BLUR, "Test_LowRes": N.OP_LOWRES}
@@ -103,6 +108,71 @@ def _corrupt_batch(variant: str, images, philox_index: int, run: "_TreeRun" = No
     return plan.unpack(dst)
 
 
+def _write_bytes(path: str, data: bytes) -> bool:
+    with open(path, "wb") as f:
+        f.write(data)
+    return True
+
+
+def _corrupt_encode_batch(variant: str, decoded, philox_index: int, run: "_TreeRun"):
+    """One ragged batch on the device: upload, corrupt (Test_Clean: nothing), JPEG-encode; returns the write jobs
+    [(function, path, payload)] -- encoded files as bytes, everything that is not a .jpg / .jpeg (or did not fit the
+    encoder's buffers) as a decoded array for cv2.imwrite."""
+    import cv2
+    import torch
+    from .jpeg import JpegEncoder
+    images = [im for _, im in decoded]
+    shapes = [(im.shape[0], im.shape[1]) for im in images]
+    key = tuple(p for p, _ in decoded)
+    hit = run.dev_cache.get(key)
+    if hit is not None:   # the batch was uploaded for an earlier variant of this tree: it is still on the device
+        plan, src_dev, enc = hit
+    else:
+        plan = CorruptionPlan.ragged(shapes)
+        src = run.pinned("src", plan.src_bytes)
+
+        def put(args):
+            im, off = args
+            src[off:off + im.size].reshape(im.shape)[...] = im
+
+        list(run.pool.map(put, zip(images, plan.src_offsets)))
+        src_dev = run.pinned_tensor("src", plan.src_bytes).cuda(non_blocking=True)
+        enc = JpegEncoder(shapes, plan.dst_offsets)
+        if run.dev_cache_bytes + plan.src_bytes <= DEVICE_CACHE_BYTES:
+            run.dev_cache[key] = (plan, src_dev, enc)
+            run.dev_cache_bytes += plan.src_bytes
+    if variant == "Test_Clean":
+        pix = src_dev
+    else:
+        pix = torch.empty(plan.dst_bytes, dtype=torch.uint8, device="cuda")
+        if variant == "Test_Noise":
+            field = None
+            if NOISE_MODE == "compat":   # the draws of augmentations.py:31, one per image, in order
+                total = sum(im.size for im in images)
+                noise = run.pinned("noise", 4 * total).view(np.float32)
+                o = 0
+                for im in images:
+                    legacy_normal_f32(NOISE_SIGMA, im.shape, out=noise[o:o + im.size])
+                    o += im.size
+                # (indexed by the plan's packed element index -- images back to back -- as rod_noise_u8 expects)
+                field = run.pinned_tensor("noise", 4 * total).view(torch.float32).cuda(non_blocking=True)
+            plan.noise(src_dev, pix, field, float(NOISE_SIGMA), seed=PHILOX_SEED, first_image_index=philox_index)
+        elif variant == "Test_Blur":
+            if float(BLUR_ANGLE_DEG) != 0.0:
+                plan.set_blur_kernel(motion_blur_kernel(BLUR_KERNEL, BLUR_ANGLE_DEG))
+            plan.blur(src_dev, pix, int(BLUR_KERNEL), float(BLUR_ANGLE_DEG))
+        else:
+            plan.lowres(src_dev, pix, float(DOWNSCALE_FACTOR))
+    files = enc.encode(pix)
+    jobs = []
+    for (p, _), data, off, (h, w) in zip(decoded, files, plan.dst_offsets, shapes):
+        if data is not None and p.suffix.lower() in (".jpg", ".jpeg"):
+            jobs.append((_write_bytes, p, data))
+        else:
+            jobs.append((cv2.imwrite, p, pix[off:off + 3 * h * w].cpu().numpy().reshape(h, w, 3)))
+    return jobs
+
+
 class _TreeRun:
     """Host-side pipeline state of one source tree (its four variants): the I/O thread pool, the decoded frames of the
     tree (the reference re-reads every file for every variant, build_corrupted_testsets.py:109/:149; here variants 2-4
@@ -116,6 +186,8 @@ class _TreeRun:
         self.pool = ThreadPoolExecutor(max(1, min(IO_THREADS, cores - 2)) if NOISE_MODE == "compat" else IO_THREADS)
         self.cache = {}
         self.cache_bytes = 0
+        self.dev_cache = {}    # batch (tuple of paths) -> (plan, uploaded source batch, JPEG encoder)
+        self.dev_cache_bytes = 0
         self.pending = []  # one list of futures per batch in flight
         self._pinned = {}  # name -> page-locked torch uint8 tensor (grow-only)
         self._out_turn = 0
@@ -128,6 +200,10 @@ class _TreeRun:
             t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8).pin_memory()
             self._pinned[name] = t
         return t.numpy()[:nbytes]
+
+    def pinned_tensor(self, name: str, nbytes: int):
+        """The page-locked torch tensor behind pinned(name, ...) (for asynchronous uploads)."""
+        return self._pinned[name][:nbytes]
 
     def pinned_out(self, nbytes: int) -> np.ndarray:
         """Output buffers rotate over three slots: the imwrite futures of at most two batches still read theirs."""
@@ -187,6 +263,13 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
         for p, im in decoded:
             run.remember(p, im)
         images = [im for _, im in decoded]
+        if ENCODER == "gpu":
+            run.drain(keep=1)  # the pinned source buffer is repacked below: the previous batch's uploads are complete (encode synchronises)
+            jobs = _corrupt_encode_batch(variant, decoded, philox_index, run)
+            if variant != "Test_Clean":
+                philox_index += len(images)
+            run.pending.append([run.pool.submit(fn, str(dst_img_dir / p.name), payload) for fn, p, payload in jobs])
+            continue
         if variant == "Test_Clean":
             outs = images
         else:

@@ -279,6 +279,46 @@ __global__ void __launch_bounds__(1024) jpeg_stuff_kernel(JpegParams p) {
 using namespace rod;
 
 // ---- host side -------------------------------------------------------------------------------------------------------
+// Encoders are created per batch layout; their (large) device buffers come from a small cache of blocks keyed by rounded
+// size, so that building one encoder per batch does not pay cudaMalloc / cudaFree (a device-wide synchronisation) each time.
+#include <map>
+#include <mutex>
+namespace {
+std::mutex g_cache_mutex;
+std::multimap<std::pair<int, size_t>, void*> g_cache;   // (device, rounded size) -> free block
+size_t round_block(size_t n) {
+    size_t r = 1 << 20;
+    while (r < n) r <<= 1;
+    if (r > (64u << 20)) r = (n + (64u << 20) - 1) / (64u << 20) * (64u << 20);   // large blocks: multiples of 64 MiB
+    return r;
+}
+cudaError_t cached_alloc(void** p, size_t n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t r = round_block(n);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        auto it = g_cache.find({dev, r});
+        if (it != g_cache.end()) { *p = it->second; g_cache.erase(it); return cudaSuccess; }
+    }
+    return cudaMalloc(p, r);
+}
+void cached_free(void* p, size_t n) {
+    if (p == nullptr) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    g_cache.insert({{dev, round_block(n)}, p});
+}
+}  // namespace
+
+// releases the cached device blocks of destroyed encoders
+extern "C" void rod_jpeg_trim(void) {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (auto& kv : g_cache) cudaFree(kv.second);
+    g_cache.clear();
+}
+
 struct rod_jpeg_encoder {
     int n_images = 0;
     std::vector<JpegImage> h_images;
@@ -299,9 +339,15 @@ struct rod_jpeg_encoder {
 
 extern "C" void rod_jpeg_destroy(rod_jpeg_encoder* e) {
     if (e == nullptr) return;
-    void* ptrs[] = {e->d_images, e->d_mcu_image, e->d_tables, e->d_coef, e->d_mcu_bits, e->d_total_bits, e->d_raw, e->d_out, e->d_out_len};
-    for (void* q : ptrs)
+    // (the stream-ordered work of the last rod_jpeg_encode is complete: rod_jpeg_download synchronises; a caller that
+    // never downloaded must synchronise its stream before destroying the encoder)
+    void* small[] = {e->d_images, e->d_mcu_image, e->d_tables, e->d_total_bits, e->d_out_len};
+    for (void* q : small)
         if (q) cudaFree(q);
+    cached_free(e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
+    cached_free(e->d_mcu_bits, sizeof(uint32_t) * (size_t)e->total_mcu);
+    cached_free(e->d_raw, e->raw_bytes + 64);
+    cached_free(e->d_out, e->out_bytes + 64);
     delete e;
 }
 
@@ -362,11 +408,12 @@ extern "C" int rod_jpeg_create(const rod_image_desc* images, int n_images, const
     alloc((void**)&e->d_images, sizeof(JpegImage) * n_images);
     alloc((void**)&e->d_mcu_image, sizeof(uint32_t) * e->h_mcu_image.size());
     alloc((void**)&e->d_tables, sizeof(jpeg::Tables));
-    alloc((void**)&e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
-    alloc((void**)&e->d_mcu_bits, sizeof(uint32_t) * (size_t)e->total_mcu);
+    auto calloc_ = [&](void** p, size_t n) { if (err == cudaSuccess) err = cached_alloc(p, n); };
+    calloc_((void**)&e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
+    calloc_((void**)&e->d_mcu_bits, sizeof(uint32_t) * (size_t)e->total_mcu);
     alloc((void**)&e->d_total_bits, sizeof(uint32_t) * n_images);
-    alloc((void**)&e->d_raw, e->raw_bytes + 64);
-    alloc((void**)&e->d_out, e->out_bytes + 64);
+    calloc_((void**)&e->d_raw, e->raw_bytes + 64);
+    calloc_((void**)&e->d_out, e->out_bytes + 64);
     alloc((void**)&e->d_out_len, sizeof(uint32_t) * n_images);
     if (err == cudaSuccess) err = cudaMemcpy(e->d_images, e->h_images.data(), sizeof(JpegImage) * n_images, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMemcpy(e->d_mcu_image, e->h_mcu_image.data(), sizeof(uint32_t) * e->h_mcu_image.size(), cudaMemcpyHostToDevice);

@@ -9,6 +9,7 @@ fallback inside: an image whose stream does not fit its device buffer comes back
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -17,6 +18,16 @@ from . import _native as N
 from .batch import _ptr, _stream_handle
 
 _HEADER_TEMPLATE = None
+_TLS = threading.local()   # per-thread page-locked download buffer, grow-only (pinning costs ~0.3 s per GB)
+
+
+def _download_buffer(nbytes: int):
+    import torch
+    t = getattr(_TLS, "buf", None)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes) * 5 // 4, 1 << 20), dtype=torch.uint8).pin_memory()
+        _TLS.buf = t
+    return t
 
 
 def _header_template() -> bytes:
@@ -69,7 +80,6 @@ class JpegEncoder:
         self.shapes = [(int(h), int(w)) for h, w in shapes]
         self.n_images = n
         self._off = [int(N.lib().rod_jpeg_stream_offset(handle, i)) for i in range(n + 1)]
-        self._host = None
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -83,14 +93,12 @@ class JpegEncoder:
     def encode(self, pixels, stream=None) -> List[Optional[bytes]]:
         """pixels: CUDA uint8 tensor holding the batch.  Returns one complete JPEG file (bytes) per image, None where the
         encoded stream did not fit its device buffer."""
-        import torch
         st = _stream_handle(stream)
         N.check(N.lib().rod_jpeg_encode(self._h, _ptr(pixels), st), "rod_jpeg_encode")
-        if self._host is None:
-            self._host = torch.empty(max(self._off[-1], 16), dtype=torch.uint8).pin_memory()
+        hbuf = _download_buffer(self._off[-1])
         lens = np.zeros(self.n_images, dtype=np.uint32)
-        N.check(N.lib().rod_jpeg_download(self._h, self._host.data_ptr(), lens.ctypes.data, st), "rod_jpeg_download")
-        host = self._host.numpy()
+        N.check(N.lib().rod_jpeg_download(self._h, hbuf.data_ptr(), lens.ctypes.data, st), "rod_jpeg_download")
+        host = hbuf.numpy()
         out: List[Optional[bytes]] = []
         for i, (h, w) in enumerate(self.shapes):
             n = int(lens[i])
