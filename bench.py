@@ -533,6 +533,23 @@ def extras(torch, np, plan, src, dst, peak):
     dodd = torch.empty_like(sodd)
     out["lowres_1917x1079_64"] = rate(lambda: podd.lowres(sodd, dodd), 2 * sodd.numel(), 64)
     del sodd, dodd, podd
+    # device JPEG encoder (files byte-identical to cv2.imwrite's) on 64 frames of the batch; bytes = pixels
+    # read + stream written.  Content: uniform noise (the worst case for a JPEG encoder: every coefficient is coded).
+    try:
+        from robust_object_detection_b200 import _native as N
+        from robust_object_detection_b200.batch import _ptr
+        from robust_object_detection_b200.jpeg import JpegEncoder
+        nj = min(64, n)
+        enc = JpegEncoder([(H, W)] * nj, [i * IMG_BYTES for i in range(nj)])
+        files = enc.encode(src[:nj])
+        stream_bytes = sum(len(f) for f in files if f is not None)
+        r = rate(lambda: N.check(N.lib().rod_jpeg_encode(enc._h, _ptr(src), None), "rod_jpeg_encode"), IMG_BYTES * nj + stream_bytes, nj)
+        r["compressed_bytes_per_image"] = stream_bytes // nj
+        r["content"] = "uniform noise"
+        out["jpeg_encode_64"] = r
+        del enc
+    except Exception as e:  # cv2 (for the header template) is the only extra dependency
+        print(f"[bench] JPEG encoder line skipped: {e}", file=sys.stderr)
     import random
     from robust_object_detection_b200.batch import draw_decisions
     random.seed(42)

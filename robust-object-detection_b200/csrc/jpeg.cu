@@ -4,8 +4,9 @@
 // Reference: scripts/build_corrupted_testsets.py:124 / :164 (`cv2.imwrite(str(dst_img_dir / img_path.name), out)`): the
 // JPEG files are what the evaluation scripts read, so their bytes are part of the test-set semantics.  The arithmetic is
 // rod_jpeg.h (shared with the CPU check against cv2.imencode in tests/emu); this file is its parallel schedule:
-//   jpeg_coef_kernel    one thread per 8x8 block: colour conversion (+ h2v2 chroma), islow DCT, reciprocal quantisation,
-//                       zigzag -> int16 coefficients [MCU][6][64]
+//   jpeg_coef_kernel    a CTA per run of 16 MCUs: pixel tile staged in shared memory, colour conversion (+ h2v2 chroma) per
+//                       2x2 quad, then one thread per 8x8 block: islow DCT, reciprocal quantisation, zigzag -> int16
+//                       coefficients [MCU][6][64], written back coalesced
 //   jpeg_dummy_kernel   libjpeg's dummy blocks of partial MCUs at the right / bottom edge (DC of the preceding block)
 //   jpeg_bits_kernel    one thread per MCU: bit length of its entropy-coded segment
 //   jpeg_scan_kernel    one CTA per image: exclusive prefix sum of the MCU bit lengths
@@ -53,29 +54,120 @@ __device__ __forceinline__ int jpeg_image_of(const JpegParams& p, uint32_t m) {
     return i;
 }
 
-__global__ void __launch_bounds__(128) jpeg_coef_kernel(JpegParams p) {
-    const uint32_t t = blockIdx.x * 128u + threadIdx.x;
-    const uint32_t m = t / 6u;
-    if (m >= p.total_mcu) return;
-    const int blk = (int)(t - 6u * m);
-    const JpegImage im = p.images[jpeg_image_of(p, m)];
-    const int lm = (int)(m - im.mcu_first), my = lm / im.mcu_w, mx = lm - my * im.mcu_w;
+// A CTA takes a run of kCoefMcus MCUs of one MCU row: (1) the 16 x (16 * kCoefMcus) pixel tile is staged in shared memory
+// with coalesced loads (edge pixels replicated), (2) every thread converts 2 x 2 pixel quads to 4 luma bytes + one Cb + one
+// Cr byte (h2v2 with the alternating bias) into planar shared arrays, (3) one thread per 8 x 8 block runs the DCT and the
+// quantisation from those planes, (4) the zigzag coefficients leave through shared memory as coalesced 16-byte stores.
+constexpr int kCoefMcus = 16;                       // MCUs per CTA -> 96 block threads
+constexpr int kCoefThreads = 6 * kCoefMcus;
+constexpr int kCoefTileW = 16 * kCoefMcus;          // pixels per tile row
+struct CoefTile {
+    uint32_t mcu_first;   // first MCU (batch-wide index) of the run
+    int32_t image;
+};
+
+__global__ void __launch_bounds__(kCoefThreads) jpeg_coef_kernel(JpegParams p, const CoefTile* tiles) {
+    __shared__ __align__(16) uint8_t pix[16][kCoefTileW * 3];
+    __shared__ __align__(16) uint8_t yplane[16][kCoefTileW];
+    __shared__ __align__(16) uint8_t cplane[2][8][kCoefTileW / 2];
+    __shared__ __align__(16) int16_t cst[kCoefThreads][64 + 8];   // (+8: rows 144 bytes apart spread over the banks)
+    const CoefTile tl = tiles[blockIdx.x];
+    const JpegImage im = p.images[tl.image];
     const jpeg::Geometry g = jpeg::geometry(im.h, im.w);
-    int16_t* zz = p.coef + ((size_t)m * 6 + blk) * 64;
-    const bool real = blk >= 4 || (2 * mx + (blk & 1) < g.yblk_w && 2 * my + (blk >> 1) < g.yblk_h);
-    if (!real) {
-        for (int z = 0; z < 64; ++z) zz[z] = 0;   // DC set by jpeg_dummy_kernel
-        return;
+    const int lm = (int)(tl.mcu_first - im.mcu_first), my = lm / im.mcu_w, mx0 = lm - my * im.mcu_w;
+    const int n_mcu_here = min(kCoefMcus, im.mcu_w - mx0);
+    const int x0 = 16 * mx0, y0 = 16 * my;
+    const int tile_px = 16 * n_mcu_here;
+    const uint8_t* img = p.pixels + im.img_off;
+    // (1) stage: row r of the tile = image row min(y0 + r, h - 1); columns beyond w - 1 replicate the last pixel
+    {
+        const int valid_px = min(tile_px, im.w - x0);           // real pixels per row
+        const int nbytes = 3 * valid_px;
+        for (int r = 0; r < 16; ++r) {
+            const uint8_t* srow = img + (int64_t)min(y0 + r, im.h - 1) * im.pitch + 3 * x0;
+            for (int b = threadIdx.x; b < nbytes; b += kCoefThreads) pix[r][b] = srow[b];
+            for (int b = nbytes + threadIdx.x; b < 3 * tile_px; b += kCoefThreads) {
+                const int c = b % 3;
+                pix[r][b] = srow[3 * (valid_px - 1) + c];
+            }
+        }
     }
-    int d[64];
-    jpeg::block_samples(p.pixels + im.img_off, (long)im.pitch, g, mx, my, blk, d);
-    jpeg::fdct_islow(d);
-    const int tq = blk < 4 ? 0 : 1;
-    const jpeg::Tables& tb = *p.tables;
+    __syncthreads();
+    // (2) quads: luma of the four pixels; chroma quad (cx, cy) averages tile rows of the CLAMPED chroma row (the last real
+    // chroma row is replicated downwards, jcprepct.c), columns as staged
+    {
+        const int quads_x = tile_px >> 1;
+        for (int q = threadIdx.x; q < 8 * quads_x; q += kCoefThreads) {
+            const int qy = q / quads_x, qx = q - qy * quads_x;
 #pragma unroll
-    for (int z = 0; z < 64; ++z) {
-        const int nat = jpeg::natural_order(z);
-        zz[z] = (int16_t)jpeg::quantize(d[nat], tb.recip[tq][nat], tb.corr[tq][nat], tb.shift[tq][nat]);
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const uint8_t* px = &pix[2 * qy + dy][3 * (2 * qx + dx)];
+                    int yy, cb, cr;
+                    jpeg::rgb_to_ycc(px[2], px[1], px[0], &yy, &cb, &cr);
+                    yplane[2 * qy + dy][2 * qx + dx] = (uint8_t)yy;
+                }
+            int cy = 8 * my + qy;
+            if (cy > g.ch - 1) cy = g.ch - 1;
+            const int ra = 2 * cy - y0, rb = min(2 * cy + 1, im.h - 1) - y0;
+            int scb = 0, scr = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint8_t* px = &pix[(k & 2) ? rb : ra][3 * (2 * qx + (k & 1))];
+                int yy, cb, cr;
+                jpeg::rgb_to_ycc(px[2], px[1], px[0], &yy, &cb, &cr);
+                scb += cb; scr += cr;
+            }
+            const int bias = 1 + ((8 * mx0 + qx) & 1);
+            cplane[0][qy][qx] = (uint8_t)((scb + bias) >> 2);
+            cplane[1][qy][qx] = (uint8_t)((scr + bias) >> 2);
+        }
+    }
+    __syncthreads();
+    // (3) one thread per block
+    const int mloc = threadIdx.x / 6, blk = threadIdx.x - 6 * mloc;
+    if (mloc < n_mcu_here) {
+        const int mx = mx0 + mloc;
+        const bool real = blk >= 4 || (2 * mx + (blk & 1) < g.yblk_w && 2 * my + (blk >> 1) < g.yblk_h);
+        int16_t* zz = cst[threadIdx.x];
+        if (!real) {
+#pragma unroll
+            for (int z = 0; z < 64; ++z) zz[z] = 0;   // DC set by jpeg_dummy_kernel
+        } else {
+            int d[64];
+            if (blk < 4) {
+                const int bx = 16 * mloc + 8 * (blk & 1), by = 8 * (blk >> 1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint2 v = *reinterpret_cast<const uint2*>(&yplane[by + j][bx]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[8 * j + i] = (int)(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 0xFFu) - 128;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint2 v = *reinterpret_cast<const uint2*>(&cplane[blk - 4][j][8 * mloc]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[8 * j + i] = (int)(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 0xFFu) - 128;
+                }
+            }
+            jpeg::fdct_islow(d);
+            const int tq = blk < 4 ? 0 : 1;
+            const jpeg::Tables& tb = *p.tables;
+#pragma unroll
+            for (int z = 0; z < 64; ++z) {
+                const int nat = jpeg::natural_order(z);
+                zz[z] = (int16_t)jpeg::quantize(d[nat], tb.recip[tq][nat], tb.corr[tq][nat], tb.shift[tq][nat]);
+            }
+        }
+    }
+    __syncthreads();
+    // (4) 6 * n_mcu_here blocks of 128 bytes, contiguous in global memory
+    {
+        uint4* dst = reinterpret_cast<uint4*>(p.coef + (size_t)tl.mcu_first * 6 * 64);
+        const int n16 = 6 * n_mcu_here * 8;
+        for (int u = threadIdx.x; u < n16; u += kCoefThreads) dst[u] = *reinterpret_cast<const uint4*>(&cst[u >> 3][8 * (u & 7)]);
     }
 }
 
@@ -327,6 +419,8 @@ struct rod_jpeg_encoder {
     uint64_t raw_bytes = 0, out_bytes = 0;
     JpegImage* d_images = nullptr;
     uint32_t* d_mcu_image = nullptr;
+    CoefTile* d_coef_tiles = nullptr;
+    int n_coef_tiles = 0;
     jpeg::Tables* d_tables = nullptr;
     int16_t* d_coef = nullptr;
     uint32_t* d_mcu_bits = nullptr;
@@ -341,7 +435,7 @@ extern "C" void rod_jpeg_destroy(rod_jpeg_encoder* e) {
     if (e == nullptr) return;
     // (the stream-ordered work of the last rod_jpeg_encode is complete: rod_jpeg_download synchronises; a caller that
     // never downloaded must synchronise its stream before destroying the encoder)
-    void* small[] = {e->d_images, e->d_mcu_image, e->d_tables, e->d_total_bits, e->d_out_len};
+    void* small[] = {e->d_images, e->d_mcu_image, e->d_coef_tiles, e->d_tables, e->d_total_bits, e->d_out_len};
     for (void* q : small)
         if (q) cudaFree(q);
     cached_free(e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
@@ -403,8 +497,18 @@ extern "C" int rod_jpeg_create(const rod_image_desc* images, int n_images, const
             e->h_mcu_image[b] = (uint32_t)img;
         }
     }
+    std::vector<CoefTile> ctiles;
+    for (int i = 0; i < n_images; ++i) {
+        const JpegImage& im = e->h_images[i];
+        const int mcu_h = im.n_mcu / im.mcu_w;
+        for (int my = 0; my < mcu_h; ++my)
+            for (int mx = 0; mx < im.mcu_w; mx += kCoefMcus) ctiles.push_back(CoefTile{im.mcu_first + (uint32_t)(my * im.mcu_w + mx), i});
+    }
+    e->n_coef_tiles = (int)ctiles.size();
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void** p, size_t n) { if (err == cudaSuccess) err = cudaMalloc(p, n); };
+    alloc((void**)&e->d_coef_tiles, sizeof(CoefTile) * ctiles.size());
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_coef_tiles, ctiles.data(), sizeof(CoefTile) * ctiles.size(), cudaMemcpyHostToDevice);
     alloc((void**)&e->d_images, sizeof(JpegImage) * n_images);
     alloc((void**)&e->d_mcu_image, sizeof(uint32_t) * e->h_mcu_image.size());
     alloc((void**)&e->d_tables, sizeof(jpeg::Tables));
@@ -445,8 +549,7 @@ extern "C" int rod_jpeg_encode(rod_jpeg_encoder* e, const uint8_t* pixels, void*
     p.mcu_image = e->d_mcu_image; p.total_mcu = e->total_mcu;
     ROD_CUDA(cudaMemsetAsync(e->d_raw, 0, e->raw_bytes + 64, stream));
     const unsigned mcu_blocks = (e->total_mcu + 127u) / 128u;
-    const unsigned blk_blocks = (unsigned)(((uint64_t)e->total_mcu * 6 + 127) / 128);
-    jpeg_coef_kernel<<<blk_blocks, 128, 0, stream>>>(p);
+    jpeg_coef_kernel<<<e->n_coef_tiles, kCoefThreads, 0, stream>>>(p, e->d_coef_tiles);
     jpeg_dummy_kernel<<<mcu_blocks, 128, 0, stream>>>(p);
     jpeg_bits_kernel<<<mcu_blocks, 128, 0, stream>>>(p);
     jpeg_scan_kernel<<<e->n_images, 1024, 0, stream>>>(p);

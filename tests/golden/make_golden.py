@@ -245,8 +245,35 @@ def make_restoration():
     print("wrote", len(out), "restoration arrays (frames smaller than the patch)")
 
 
+JPEG_CASES = [(9300, 16, 16, "noise"), (9301, 37, 53, "smooth"), (9302, 97, 133, "noise"), (9303, 120, 200, "binary"),
+              (9304, 360, 480, "smooth"), (9305, 765, 1360, "noise"), (9306, 540, 960, "smooth"), (9307, 17, 33, "noise")]
+
+
+def jpeg_case_image(seed, h, w, kind):
+    import cv2
+    img = synth(seed, h, w)
+    if kind == "smooth":
+        img = cv2.GaussianBlur(img, (0, 0), 2.5)
+    elif kind == "binary":
+        img = (img > 127).astype(np.uint8) * 255
+    return img
+
+
+def make_jpeg():
+    """sha256 of the files cv2.imencode('.jpg', img) -- the encoder behind the reference's
+    cv2.imwrite(str(dst / name), out), build_corrupted_testsets.py:124 -- produces in the build container."""
+    import cv2
+    out = {f"{seed}_{h}x{w}_{kind}": hashlib.sha256(cv2.imencode(".jpg", jpeg_case_image(seed, h, w, kind))[1].tobytes()).hexdigest()
+           for seed, h, w, kind in JPEG_CASES}
+    with open(os.path.join(HERE, "golden_jpeg.json"), "w") as f:
+        json.dump({"cases": JPEG_CASES, "sha": out, "cv2": cv2.__version__}, f, indent=1)
+    print("wrote", len(out), "JPEG hashes")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "restoration":
+    if len(sys.argv) > 1 and sys.argv[1] == "jpeg":
+        make_jpeg()
+    elif len(sys.argv) > 1 and sys.argv[1] == "restoration":
         make_restoration()
     elif len(sys.argv) > 1 and sys.argv[1] == "angles":
         make_angles()
@@ -257,3 +284,4 @@ if __name__ == "__main__":
         make_angles()
         make_restoration()
         make_letterbox()
+        make_jpeg()

@@ -457,3 +457,26 @@ def test_emu_jpeg_encoder_matches_cv2(emu):
             got = out[:n].tobytes()
             assert len(got) == len(want) and got == want, (h, w, v, len(got), len(want),
                                                            next((k for k in range(min(len(got), len(want))) if got[k] != want[k]), -1))
+
+
+def test_emu_jpeg_encoder_matches_golden(emu):
+    """... and against the hashes tests/golden/make_golden.py recorded from cv2.imencode in the build container
+    (golden_jpeg.json), so the check does not rest on the local OpenCV build alone."""
+    import hashlib
+    import json
+    import cv2
+    emu.emu_jpeg_encode.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_long,
+                                    ctypes.POINTER(ctypes.c_uint8), ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.c_long]
+    emu.emu_jpeg_encode.restype = ctypes.c_long
+    g = json.load(open(os.path.join(HERE, "golden", "golden_jpeg.json")))
+    for seed, h, w, kind in g["cases"]:
+        img = synth(seed, h, w)
+        if kind == "smooth":
+            img = cv2.GaussianBlur(img, (0, 0), 2.5)
+        elif kind == "binary":
+            img = (img > 127).astype(np.uint8) * 255
+        hdr = np.frombuffer(jpeg_header(h, w), np.uint8).copy()
+        out = np.zeros(3 * h * w + 4096, np.uint8)
+        n = emu.emu_jpeg_encode(_p(np.ascontiguousarray(img)), h, w, 3 * w, _p(hdr), len(hdr), _p(out), len(out))
+        assert n > 0
+        assert hashlib.sha256(out[:n].tobytes()).hexdigest() == g["sha"][f"{seed}_{h}x{w}_{kind}"], (seed, h, w, kind)

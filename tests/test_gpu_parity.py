@@ -1248,3 +1248,26 @@ def test_jpeg_encoder_matches_cv2(torch_):
     files = JpegEncoder(shapes, offs[:-1], pitches).encode(torch_.from_numpy(host).cuda())
     for i, (img, got) in enumerate(zip(imgs, files)):
         assert got == cv2.imencode(".jpg", img)[1].tobytes(), (i, shapes[i])
+
+
+def test_jpeg_encoder_matches_golden(torch_):
+    """The device JPEG encoder against the cv2.imencode hashes recorded in the build container (golden_jpeg.json)."""
+    import hashlib
+    import json
+    import cv2
+    from robust_object_detection_b200.batch import CorruptionPlan
+    from robust_object_detection_b200.jpeg import JpegEncoder
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_jpeg.json")))
+    imgs = []
+    for seed, h, w, kind in g["cases"]:
+        img = synth(seed, h, w)
+        if kind == "smooth":
+            img = cv2.GaussianBlur(img, (0, 0), 2.5)
+        elif kind == "binary":
+            img = (img > 127).astype(np.uint8) * 255
+        imgs.append(img)
+    shapes = [(h, w) for _, h, w, _ in g["cases"]]
+    plan = CorruptionPlan.ragged(shapes)
+    files = JpegEncoder(shapes, plan.src_offsets).encode(torch_.from_numpy(plan.pack(imgs)).cuda())
+    for (seed, h, w, kind), f in zip(g["cases"], files):
+        assert f is not None and hashlib.sha256(f).hexdigest() == g["sha"][f"{seed}_{h}x{w}_{kind}"], (seed, h, w, kind)
