@@ -198,28 +198,57 @@ struct BitCounter {
     RJ_HD void put(uint32_t, int size) { bits += (uint32_t)size; }
 };
 
-// jchuff.c encode_one_block for one block of quantised coefficients in ZIGZAG order; last_dc = the previous block's DC of
-// the same component.
+// jchuff.c encode_one_block for one block of quantised coefficients in ZIGZAG order (16-byte aligned); last_dc = the
+// previous block's DC of the same component.  The coefficients are read eight at a time (one 16-byte load) and a chunk of
+// eight zeros only extends the current run.
+struct Coef8 {
+    uint32_t w[4];
+};
+RJ_HD Coef8 load_coef8(const int16_t* zz, int chunk) {
+    Coef8 c;
+#if defined(__CUDA_ARCH__)
+    const uint4 v = reinterpret_cast<const uint4*>(zz)[chunk];
+    c.w[0] = v.x; c.w[1] = v.y; c.w[2] = v.z; c.w[3] = v.w;
+#else
+    for (int i = 0; i < 4; ++i)
+        c.w[i] = (uint32_t)(uint16_t)zz[8 * chunk + 2 * i] | ((uint32_t)(uint16_t)zz[8 * chunk + 2 * i + 1] << 16);
+#endif
+    return c;
+}
 template <typename Sink>
 RJ_HD void encode_block(const int16_t* zz, int last_dc, const uint16_t* dc_co, const uint8_t* dc_si, const uint16_t* ac_co,
                         const uint8_t* ac_si, Sink& sink) {
-    int temp = (int)zz[0] - last_dc, temp2 = temp;
-    if (temp < 0) { temp = -temp; temp2--; }
-    int nbits = nbits_of(temp);
-    sink.put(dc_co[nbits], dc_si[nbits]);
-    if (nbits) sink.put((uint32_t)temp2 & ((1u << nbits) - 1u), nbits);
     int r = 0;
-    for (int k = 1; k < 64; ++k) {
-        temp = zz[k];
-        if (temp == 0) { ++r; continue; }
-        while (r > 15) { sink.put(ac_co[0xF0], ac_si[0xF0]); r -= 16; }
-        temp2 = temp;
-        if (temp < 0) { temp = -temp; temp2--; }
-        nbits = nbits_of(temp);
-        const int sym = (r << 4) + nbits;
-        sink.put(ac_co[sym], ac_si[sym]);
-        sink.put((uint32_t)temp2 & ((1u << nbits) - 1u), nbits);
-        r = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int chunk = 0; chunk < 8; ++chunk) {
+        const Coef8 c = load_coef8(zz, chunk);
+        if (chunk > 0 && (c.w[0] | c.w[1] | c.w[2] | c.w[3]) == 0u) { r += 8; continue; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 8; ++i) {
+            int temp = (int)(int16_t)(c.w[i >> 1] >> (16 * (i & 1)));
+            if (chunk == 0 && i == 0) {   // DC difference
+                temp -= last_dc;
+                int temp2 = temp;
+                if (temp < 0) { temp = -temp; temp2--; }
+                const int nbits = nbits_of(temp);
+                sink.put(dc_co[nbits], dc_si[nbits]);
+                if (nbits) sink.put((uint32_t)temp2 & ((1u << nbits) - 1u), nbits);
+                continue;
+            }
+            if (temp == 0) { ++r; continue; }
+            while (r > 15) { sink.put(ac_co[0xF0], ac_si[0xF0]); r -= 16; }
+            int temp2 = temp;
+            if (temp < 0) { temp = -temp; temp2--; }
+            const int nbits = nbits_of(temp);
+            const int sym = (r << 4) + nbits;
+            sink.put(ac_co[sym], ac_si[sym]);
+            sink.put((uint32_t)temp2 & ((1u << nbits) - 1u), nbits);
+            r = 0;
+        }
     }
     if (r > 0) sink.put(ac_co[0], ac_si[0]);
 }
