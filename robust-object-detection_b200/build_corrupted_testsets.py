@@ -108,9 +108,11 @@ def _corrupt_batch(variant: str, images, philox_index: int, run: "_TreeRun" = No
     return plan.unpack(dst)
 
 
-def _write_bytes(path: str, data: bytes) -> bool:
+def _write_bytes(path: str, data) -> bool:
+    """data: (header bytes, view of the downloaded stream): written by the I/O threads straight from the page-locked buffer"""
     with open(path, "wb") as f:
-        f.write(data)
+        f.write(data[0])
+        f.write(data[1])
     return True
 
 
@@ -163,7 +165,7 @@ def _corrupt_encode_batch(variant: str, decoded, philox_index: int, run: "_TreeR
             plan.blur(src_dev, pix, int(BLUR_KERNEL), float(BLUR_ANGLE_DEG))
         else:
             plan.lowres(src_dev, pix, float(DOWNSCALE_FACTOR))
-    files = enc.encode(pix)
+    files = enc.encode(pix, copy=False)   # views into a ring of three download buffers; at most two batches of writes are pending
     jobs = []
     for (p, _), data, off, (h, w) in zip(decoded, files, plan.dst_offsets, shapes):
         if data is not None and p.suffix.lower() in (".jpg", ".jpeg"):

@@ -12,7 +12,8 @@
 //   jpeg_scan_kernel    one CTA per image: exclusive prefix sum of the MCU bit lengths
 //   jpeg_write_kernel   one thread per MCU: its bits at its absolute bit offset of a zeroed big-endian stream (whole 32-bit
 //                       words stored, the two boundary words OR-ed atomically)
-//   jpeg_stuff_kernel   one CTA per image: pad the last byte with ones, insert 0x00 after every 0xFF, append EOI
+//   jpeg_ffcount / ffscan / stuffwrite   0x00 inserted after every 0xFF: a warp per 2 KB chunk counts, a CTA per image scans
+//                       (+ EOI, length), a warp per chunk copies its bytes to their place
 // The header (SOI .. SOS) is OpenCV's own for that image size and is prepended on the host.
 #include <algorithm>
 #include <new>
@@ -277,7 +278,15 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(JpegParams p) {
         if (threadIdx.x == 0) carry_s += warp_sum[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) p.total_bits[blockIdx.x] = carry_s;
+    if (threadIdx.x == 0) {
+        const uint32_t bits = carry_s, nbytes = (bits + 7u) >> 3;
+        p.total_bits[blockIdx.x] = bits;
+        // flush_bits: the last byte is padded with ones.  OR-ed into the zeroed stream now: the MCU that ends in this word
+        // finishes it with an atomicOr as well (a stream that ends on a word boundary has nothing to pad).
+        if ((bits & 7u) != 0u && (uint64_t)nbytes + 8 <= im.raw_cap)
+            atomicOr(reinterpret_cast<uint32_t*>(p.raw + im.raw_off) + ((nbytes - 1u) >> 2),
+                     (0xFFu >> (bits & 7u)) << (8u * ((nbytes - 1u) & 3u)));
+    }
 }
 
 __global__ void __launch_bounds__(128) jpeg_write_kernel(JpegParams p) {
@@ -285,46 +294,61 @@ __global__ void __launch_bounds__(128) jpeg_write_kernel(JpegParams p) {
     if (m >= p.total_mcu) return;
     const int ii = jpeg_image_of(p, m);
     const JpegImage im = p.images[ii];
-    if (((uint64_t)p.total_bits[ii] + 7) / 8 + 8 > im.raw_cap) return;   // too small: reported by jpeg_stuff_kernel
+    if (((uint64_t)p.total_bits[ii] + 7) / 8 + 8 > im.raw_cap) return;   // too small: reported by jpeg_ffscan_kernel
     GlobalBitWriter w;
     w.init(p.raw + im.raw_off, p.mcu_bits[m]);
     jpeg_encode_mcu(p, im, m, w);
     w.finish();
 }
 
-// one CTA per image: out := stuffed(raw, padded with ones to a byte) + EOI
-__global__ void __launch_bounds__(1024) jpeg_stuff_kernel(JpegParams p) {
+// ---- byte stuffing: out := raw with 0x00 inserted after every 0xFF, + EOI.  A warp per chunk of kStuffChunk stream bytes:
+// (a) count the 0xFF bytes per chunk, (b) a CTA per image scans the counts (and writes EOI + the length), (c) every warp
+// copies its chunk to its place, 128 bytes per step (a lane's four bytes go out as byte stores at the lane's scanned offset)
+constexpr int kStuffChunk = 2048;
+
+__device__ __forceinline__ uint32_t ff_bytes(uint32_t w) { return (uint32_t)__popc(__vcmpeq4(w, 0xFFFFFFFFu)) >> 3; }
+
+__global__ void __launch_bounds__(128) jpeg_ffcount_kernel(JpegParams p, uint32_t* ff_count, const uint32_t* chunk_first) {
+    const int img = blockIdx.y, lane = threadIdx.x & 31;
+    const uint32_t c = blockIdx.x * 4u + (threadIdx.x >> 5);
+    const JpegImage im = p.images[img];
+    const uint32_t nbytes = (p.total_bits[img] + 7u) >> 3;
+    if ((uint64_t)nbytes + 8 > im.raw_cap || (uint64_t)c * kStuffChunk >= nbytes) return;
+    const uint8_t* raw = p.raw + im.raw_off + (size_t)c * kStuffChunk;
+    const uint32_t n_here = min((uint32_t)kStuffChunk, nbytes - c * kStuffChunk);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int step = 0; step < kStuffChunk / 512; ++step) {
+        const uint32_t b0 = 512u * step + 16u * lane;
+        if (b0 < n_here) {
+            const uint4 v = *reinterpret_cast<const uint4*>(raw + b0);   // (bytes beyond the stream's end are zero)
+            cnt += ff_bytes(v.x) + ff_bytes(v.y) + ff_bytes(v.z) + ff_bytes(v.w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (lane == 0) ff_count[chunk_first[img] + c] = cnt;
+}
+
+__global__ void __launch_bounds__(1024) jpeg_ffscan_kernel(JpegParams p, uint32_t* ff_count, const uint32_t* chunk_first) {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry_s;
-    const JpegImage im = p.images[blockIdx.x];
-    const uint32_t bits = p.total_bits[blockIdx.x];
-    const uint32_t nbytes = (bits + 7u) >> 3;
+    const int img = blockIdx.x;
+    const JpegImage im = p.images[img];
+    const uint32_t nbytes = (p.total_bits[img] + 7u) >> 3;
     if ((uint64_t)nbytes + 8 > im.raw_cap) {
-        if (threadIdx.x == 0) p.out_len[blockIdx.x] = 0xFFFFFFFFu;
+        if (threadIdx.x == 0) p.out_len[img] = 0xFFFFFFFFu;
         return;
     }
-    uint8_t* raw = p.raw + im.raw_off;
-    uint8_t* out = p.out + im.out_off;
+    const int n_chunks = (int)((nbytes + kStuffChunk - 1) / kStuffChunk);
+    uint32_t* cnt = ff_count + chunk_first[img];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        carry_s = 0;
-        if (bits & 7u) raw[nbytes - 1] |= (uint8_t)(0xFFu >> (bits & 7u));   // flush_bits: the last byte is padded with ones
-    }
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    bool overflow = false;
-    for (uint32_t base = 0; base < nbytes; base += 1024u * 16u) {
-        // 16 bytes per thread: count the 0xFF bytes, scan, then copy with the inserted zeros
-        const uint32_t b0 = base + 16u * threadIdx.x;
-        uint32_t wds[4] = {0u, 0u, 0u, 0u};
-        int n_here = 0;
-        if (b0 < nbytes) {
-            n_here = (int)min(16u, nbytes - b0);
-            const uint4 v = *reinterpret_cast<const uint4*>(raw + b0);   // raw_off is 16-byte aligned and raw_cap padded
-            wds[0] = v.x; wds[1] = v.y; wds[2] = v.z; wds[3] = v.w;
-        }
-        uint32_t nff = 0;
-        for (int k = 0; k < n_here; ++k) nff += ((wds[k >> 2] >> (8 * (k & 3))) & 0xFFu) == 0xFFu ? 1u : 0u;
-        uint32_t x = nff;
+    for (int base = 0; base < n_chunks; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        const uint32_t v = i < n_chunks ? cnt[i] : 0u;
+        uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
@@ -333,36 +357,66 @@ __global__ void __launch_bounds__(1024) jpeg_stuff_kernel(JpegParams p) {
         if (lane == 31) warp_sum[warp] = x;
         __syncthreads();
         if (warp == 0) {
-            uint32_t s = warp_sum[lane];
+            uint32_t sm = warp_sum[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, o);
-                if (lane >= o) s += y;
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, sm, o);
+                if (lane >= o) sm += y;
             }
-            warp_sum[lane] = s;
+            warp_sum[lane] = sm;
         }
         __syncthreads();
-        const uint32_t ff_before = carry_s + (warp > 0 ? warp_sum[warp - 1] : 0u) + (x - nff);
-        uint64_t o = (uint64_t)b0 + ff_before;
-        if (o + (uint64_t)n_here + nff + 2 > im.out_cap) overflow = overflow || n_here > 0;
-        else
-            for (int k = 0; k < n_here; ++k) {
-                const uint8_t b = (uint8_t)(wds[k >> 2] >> (8 * (k & 3)));
-                out[o++] = b;
-                if (b == 0xFF) out[o++] = 0;
-            }
+        if (i < n_chunks) cnt[i] = carry_s + (warp > 0 ? warp_sum[warp - 1] : 0u) + (x - v);   // 0xFF bytes before the chunk
         __syncthreads();
         if (threadIdx.x == 0) carry_s += warp_sum[31];
         __syncthreads();
     }
-    const int any_overflow = __syncthreads_or(overflow ? 1 : 0);
     if (threadIdx.x == 0) {
         const uint64_t end = (uint64_t)nbytes + carry_s;
-        if (any_overflow || end + 2 > im.out_cap) p.out_len[blockIdx.x] = 0xFFFFFFFFu;
+        if (end + 2 > im.out_cap) p.out_len[img] = 0xFFFFFFFFu;
         else {
+            uint8_t* out = p.out + im.out_off;
             out[end] = 0xFF; out[end + 1] = 0xD9;
-            p.out_len[blockIdx.x] = (uint32_t)(end + 2);
+            p.out_len[img] = (uint32_t)(end + 2);
         }
+    }
+}
+
+__global__ void __launch_bounds__(128) jpeg_stuffwrite_kernel(JpegParams p, const uint32_t* ff_before, const uint32_t* chunk_first) {
+    const int img = blockIdx.y, lane = threadIdx.x & 31;
+    const uint32_t c = blockIdx.x * 4u + (threadIdx.x >> 5);
+    const JpegImage im = p.images[img];
+    const uint32_t nbytes = (p.total_bits[img] + 7u) >> 3;
+    if ((uint64_t)nbytes + 8 > im.raw_cap || (uint64_t)c * kStuffChunk >= nbytes) return;
+    if (p.out_len[img] == 0xFFFFFFFFu) return;
+    const uint8_t* raw = p.raw + im.raw_off + (size_t)c * kStuffChunk;
+    const uint32_t n_here = min((uint32_t)kStuffChunk, nbytes - c * kStuffChunk);
+    uint8_t* out = p.out + im.out_off + (size_t)c * kStuffChunk + ff_before[chunk_first[img] + c];
+    uint32_t run = 0;   // 0xFF bytes of the chunk's earlier steps
+#pragma unroll 1
+    for (uint32_t b0 = 0; b0 < n_here; b0 += 128u) {
+        const uint32_t mine = b0 + 4u * lane;
+        const uint32_t w = mine < n_here ? *reinterpret_cast<const uint32_t*>(raw + mine) : 0u;
+        const uint32_t valid = mine < n_here ? min(4u, n_here - mine) : 0u;
+        const uint32_t wm = valid == 4u ? w : (w & ((1u << (8u * valid)) - 1u));   // (valid == 0: w is 0 already)
+        const uint32_t nff = ff_bytes(wm);
+        uint32_t x = nff;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        uint8_t* o = out + mine + run + (x - nff);
+        if (nff == 0u && valid == 4u) {
+            o[0] = (uint8_t)w; o[1] = (uint8_t)(w >> 8); o[2] = (uint8_t)(w >> 16); o[3] = (uint8_t)(w >> 24);
+        } else {
+            for (uint32_t k = 0; k < valid; ++k) {
+                const uint8_t b = (uint8_t)(w >> (8u * k));
+                *o++ = b;
+                if (b == 0xFF) *o++ = 0;
+            }
+        }
+        run += __shfl_sync(0xFFFFFFFFu, x, 31);
     }
 }
 
@@ -428,6 +482,9 @@ struct rod_jpeg_encoder {
     uint8_t* d_raw = nullptr;
     uint8_t* d_out = nullptr;
     uint32_t* d_out_len = nullptr;
+    uint32_t* d_ff_count = nullptr;      // per stuffing chunk: 0xFF bytes in it, then (after the scan) before it
+    uint32_t* d_chunk_first = nullptr;   // per image: index of its first chunk
+    uint32_t total_chunks = 0, max_chunks = 0;
     std::vector<uint64_t> out_off;
 };
 
@@ -435,7 +492,7 @@ extern "C" void rod_jpeg_destroy(rod_jpeg_encoder* e) {
     if (e == nullptr) return;
     // (the stream-ordered work of the last rod_jpeg_encode is complete: rod_jpeg_download synchronises; a caller that
     // never downloaded must synchronise its stream before destroying the encoder)
-    void* small[] = {e->d_images, e->d_mcu_image, e->d_coef_tiles, e->d_tables, e->d_total_bits, e->d_out_len};
+    void* small[] = {e->d_images, e->d_mcu_image, e->d_coef_tiles, e->d_tables, e->d_total_bits, e->d_out_len, e->d_ff_count, e->d_chunk_first};
     for (void* q : small)
         if (q) cudaFree(q);
     cached_free(e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
@@ -505,6 +562,13 @@ extern "C" int rod_jpeg_create(const rod_image_desc* images, int n_images, const
             for (int mx = 0; mx < im.mcu_w; mx += kCoefMcus) ctiles.push_back(CoefTile{im.mcu_first + (uint32_t)(my * im.mcu_w + mx), i});
     }
     e->n_coef_tiles = (int)ctiles.size();
+    std::vector<uint32_t> chunk_first(n_images);
+    for (int i = 0; i < n_images; ++i) {
+        const uint32_t nc = (uint32_t)((e->h_images[i].raw_cap + kStuffChunk - 1) / kStuffChunk);
+        chunk_first[i] = e->total_chunks;
+        e->total_chunks += nc;
+        e->max_chunks = std::max(e->max_chunks, nc);
+    }
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void** p, size_t n) { if (err == cudaSuccess) err = cudaMalloc(p, n); };
     alloc((void**)&e->d_coef_tiles, sizeof(CoefTile) * ctiles.size());
@@ -519,6 +583,9 @@ extern "C" int rod_jpeg_create(const rod_image_desc* images, int n_images, const
     calloc_((void**)&e->d_raw, e->raw_bytes + 64);
     calloc_((void**)&e->d_out, e->out_bytes + 64);
     alloc((void**)&e->d_out_len, sizeof(uint32_t) * n_images);
+    alloc((void**)&e->d_ff_count, sizeof(uint32_t) * (size_t)e->total_chunks);
+    alloc((void**)&e->d_chunk_first, sizeof(uint32_t) * n_images);
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_chunk_first, chunk_first.data(), sizeof(uint32_t) * n_images, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMemcpy(e->d_images, e->h_images.data(), sizeof(JpegImage) * n_images, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMemcpy(e->d_mcu_image, e->h_mcu_image.data(), sizeof(uint32_t) * e->h_mcu_image.size(), cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMemcpy(e->d_tables, &tb, sizeof(tb), cudaMemcpyHostToDevice);
@@ -554,7 +621,10 @@ extern "C" int rod_jpeg_encode(rod_jpeg_encoder* e, const uint8_t* pixels, void*
     jpeg_bits_kernel<<<mcu_blocks, 128, 0, stream>>>(p);
     jpeg_scan_kernel<<<e->n_images, 1024, 0, stream>>>(p);
     jpeg_write_kernel<<<mcu_blocks, 128, 0, stream>>>(p);
-    jpeg_stuff_kernel<<<e->n_images, 1024, 0, stream>>>(p);
+    const dim3 chunk_grid((e->max_chunks + 3u) / 4u, (unsigned)e->n_images);
+    jpeg_ffcount_kernel<<<chunk_grid, 128, 0, stream>>>(p, e->d_ff_count, e->d_chunk_first);
+    jpeg_ffscan_kernel<<<e->n_images, 1024, 0, stream>>>(p, e->d_ff_count, e->d_chunk_first);
+    jpeg_stuffwrite_kernel<<<chunk_grid, 128, 0, stream>>>(p, e->d_ff_count, e->d_chunk_first);
     ROD_CUDA(cudaGetLastError());
     return ROD_OK;
 }

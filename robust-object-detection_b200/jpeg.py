@@ -18,15 +18,21 @@ from . import _native as N
 from .batch import _ptr, _stream_handle
 
 _HEADER_TEMPLATE = None
-_TLS = threading.local()   # per-thread page-locked download buffer, grow-only (pinning costs ~0.3 s per GB)
+_TLS = threading.local()   # per-thread ring of three page-locked download buffers, grow-only (pinning costs ~0.3 s per GB)
 
 
 def _download_buffer(nbytes: int):
+    """The next buffer of the calling thread's ring.  Views handed out by encode(copy=False) stay valid until the third
+    following encode() call on the same thread."""
     import torch
-    t = getattr(_TLS, "buf", None)
+    ring = getattr(_TLS, "ring", None)
+    if ring is None:
+        ring = _TLS.ring = [None, None, None]
+        _TLS.turn = 0
+    _TLS.turn = (_TLS.turn + 1) % 3
+    t = ring[_TLS.turn]
     if t is None or t.numel() < nbytes:
-        t = torch.empty(max(int(nbytes) * 5 // 4, 1 << 20), dtype=torch.uint8).pin_memory()
-        _TLS.buf = t
+        t = ring[_TLS.turn] = torch.empty(max(int(nbytes) * 5 // 4, 1 << 20), dtype=torch.uint8).pin_memory()
     return t
 
 
@@ -90,17 +96,23 @@ class JpegEncoder:
                 pass
             self._h = None
 
-    def encode(self, pixels, stream=None) -> List[Optional[bytes]]:
-        """pixels: CUDA uint8 tensor holding the batch.  Returns one complete JPEG file (bytes) per image, None where the
-        encoded stream did not fit its device buffer."""
+    def encode(self, pixels, stream=None, copy: bool = True) -> List[Optional[object]]:
+        """pixels: CUDA uint8 tensor holding the batch.  Returns one complete JPEG file per image -- `bytes`, or with
+        copy=False a (header bytes, uint8 array view into a page-locked buffer) pair that is valid until the third following
+        encode() call of this thread -- and None where the encoded stream did not fit its device buffer."""
         st = _stream_handle(stream)
         N.check(N.lib().rod_jpeg_encode(self._h, _ptr(pixels), st), "rod_jpeg_encode")
         hbuf = _download_buffer(self._off[-1])
         lens = np.zeros(self.n_images, dtype=np.uint32)
         N.check(N.lib().rod_jpeg_download(self._h, hbuf.data_ptr(), lens.ctypes.data, st), "rod_jpeg_download")
         host = hbuf.numpy()
-        out: List[Optional[bytes]] = []
+        out: List[Optional[object]] = []
         for i, (h, w) in enumerate(self.shapes):
             n = int(lens[i])
-            out.append(None if n == 0xFFFFFFFF else header_for(h, w) + host[self._off[i]:self._off[i] + n].tobytes())
+            if n == 0xFFFFFFFF:
+                out.append(None)
+            elif copy:
+                out.append(header_for(h, w) + host[self._off[i]:self._off[i] + n].tobytes())
+            else:
+                out.append((header_for(h, w), host[self._off[i]:self._off[i] + n]))
         return out
