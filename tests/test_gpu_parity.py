@@ -1271,3 +1271,23 @@ def test_jpeg_encoder_matches_golden(torch_):
     files = JpegEncoder(shapes, plan.src_offsets).encode(torch_.from_numpy(plan.pack(imgs)).cuda())
     for (seed, h, w, kind), f in zip(g["cases"], files):
         assert f is not None and hashlib.sha256(f).hexdigest() == g["sha"][f"{seed}_{h}x{w}_{kind}"], (seed, h, w, kind)
+
+
+def test_jpeg_encoder_random_shapes_stress(torch_):
+    """Device JPEG encoder on random shapes (1 .. 260 pixels per side, plus a few large odd ones) and content types, as one
+    ragged batch, against cv2.imencode."""
+    import cv2
+    from robust_object_detection_b200.batch import CorruptionPlan
+    from robust_object_detection_b200.jpeg import JpegEncoder
+    rng = np.random.default_rng(77)
+    shapes = [(int(rng.integers(1, 261)), int(rng.integers(1, 261))) for _ in range(40)] + [(1079, 1917), (1499, 1999), (15, 2001), (2001, 17)]
+    imgs = []
+    for i, (h, w) in enumerate(shapes):
+        base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        kind = i % 3
+        imgs.append(base if kind == 0 else cv2.GaussianBlur(base, (0, 0), 1.5 + (i % 5)) if kind == 1 else (base // 64) * 85)
+    plan = CorruptionPlan.ragged(shapes)
+    files = JpegEncoder(shapes, plan.src_offsets).encode(torch_.from_numpy(plan.pack(imgs)).cuda())
+    for i, (img, got) in enumerate(zip(imgs, files)):
+        want = cv2.imencode(".jpg", img)[1].tobytes()
+        assert got is not None and got == want, (i, shapes[i], None if got is None else len(got), len(want))
