@@ -7,7 +7,7 @@ mkdir -p $out
 nvidia-smi --query-gpu=name,memory.total --format=csv > $out/gpu_$tag.txt; nproc >> $out/gpu_$tag.txt
 python -m pytest tests -m gpu -x -q > $out/pytest_$tag.log 2>&1; echo "pytest exit $?" | tee -a $out/pytest_$tag.log
 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; echo "smoke exit $?" | tee -a $out/smoke_$tag.log
-python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench exit $?"
+t0=$(date +%s); python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench exit $? ($(( $(date +%s) - t0 )) s)"
 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; echo "ref exit $?"
 python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/plain_bench_$tag.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches_$tag.csv \
@@ -15,9 +15,15 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-fil
 # the headline launch itself (256 images): DRAM traffic for bench.py's roofline.traffic
 ncu --set full --clock-control none --import-source on -k regex:blur -s 3 -c 1 -f -o $out/prof_bench_$tag \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/ncu_bench_$tag.log 2>&1
-ops="blur noise lowres lowres1080 lowresodd letterbox mixed"
+ops="blur noise lowres lowres1080 lowresodd letterbox mixed jpeg"
 python tools/profile_ops.py $ops > $out/plain_profile_$tag.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'blur|noise|lowres|letterbox' -s 3 -c 40 -f \
+ncu --set full --clock-control none -k regex:'blur|noise|lowres|letterbox|jpeg' -s 3 -c 30 -f \
     -o $out/prof_$tag python tools/profile_ops.py $ops > $out/ncu_full_$tag.log 2>&1
 python tools/time_testset_driver.py 64 > $out/testset_driver_$tag.json 2> $out/testset_driver_$tag.err; echo "driver timing exit $?"
+python tools/time_jpeg.py 64 > $out/time_jpeg_$tag.json 2> $out/time_jpeg_$tag.err; echo "jpeg timing exit $?"
+# gpurun merges back at most 64 MiB: drop the largest report rather than lose everything
+while [ "$(du -sm $out | cut -f1)" -gt 60 ]; do
+  big=$(ls -S $out/*.ncu-rep 2>/dev/null | head -1); [ -z "$big" ] && break
+  echo "dropping $big ($(du -sm $big | cut -f1) MiB) to stay below the merge limit"; rm -f "$big"
+done
 echo "done"

@@ -45,6 +45,15 @@ if "letterbox" in which:
     f16 = torch.empty((n, 3, 640, 640), dtype=torch.float16, device="cuda")
     for _ in range(2):
         plan.corrupt_letterbox(src, ops, f16, 640, 640, 114, seed=1)
+if "jpeg" in which:   # device JPEG encoder on the 64-image batch (uniform noise: every coefficient coded)
+    from robust_object_detection_b200 import _native as N
+    from robust_object_detection_b200.batch import _ptr
+    from robust_object_detection_b200.jpeg import JpegEncoder
+    enc = JpegEncoder([(h, w)] * n, [i * 3 * h * w for i in range(n)])
+    for _ in range(2):
+        N.check(N.lib().rod_jpeg_encode(enc._h, _ptr(src), None), "rod_jpeg_encode")
+    torch.cuda.synchronize()
+    del enc
 if "mixed" in which:
     shapes = [(1080, 1920), (1079, 1917), (1050, 1400), (1500, 2000)] * 8
     rp = CorruptionPlan.ragged(shapes)
