@@ -438,9 +438,7 @@ size_t round_block(size_t n) {
     if (r > (64u << 20)) r = (n + (64u << 20) - 1) / (64u << 20) * (64u << 20);   // large blocks: multiples of 64 MiB
     return r;
 }
-cudaError_t cached_alloc(void** p, size_t n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+cudaError_t cached_alloc(int dev, void** p, size_t n) {
     const size_t r = round_block(n);
     {
         std::lock_guard<std::mutex> lock(g_cache_mutex);
@@ -449,10 +447,8 @@ cudaError_t cached_alloc(void** p, size_t n) {
     }
     return cudaMalloc(p, r);
 }
-void cached_free(void* p, size_t n) {
+void cached_free(int dev, void* p, size_t n) {   // dev: the device the block was allocated on
     if (p == nullptr) return;
-    int dev = 0;
-    cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     g_cache.insert({{dev, round_block(n)}, p});
 }
@@ -466,6 +462,7 @@ extern "C" void rod_jpeg_trim(void) {
 }
 
 struct rod_jpeg_encoder {
+    int device = 0;
     int n_images = 0;
     std::vector<JpegImage> h_images;
     std::vector<uint32_t> h_mcu_image;
@@ -495,10 +492,10 @@ extern "C" void rod_jpeg_destroy(rod_jpeg_encoder* e) {
     void* small[] = {e->d_images, e->d_mcu_image, e->d_coef_tiles, e->d_tables, e->d_total_bits, e->d_out_len, e->d_ff_count, e->d_chunk_first};
     for (void* q : small)
         if (q) cudaFree(q);
-    cached_free(e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
-    cached_free(e->d_mcu_bits, sizeof(uint32_t) * (size_t)e->total_mcu);
-    cached_free(e->d_raw, e->raw_bytes + 64);
-    cached_free(e->d_out, e->out_bytes + 64);
+    cached_free(e->device, e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
+    cached_free(e->device, e->d_mcu_bits, sizeof(uint32_t) * (size_t)e->total_mcu);
+    cached_free(e->device, e->d_raw, e->raw_bytes + 64);
+    cached_free(e->device, e->d_out, e->out_bytes + 64);
     delete e;
 }
 
@@ -515,6 +512,7 @@ extern "C" int rod_jpeg_create(const rod_image_desc* images, int n_images, const
     if (!jpeg::parse_header(header, (size_t)header_len, &info, &tb)) return ROD_ERR_UNSUPPORTED;
     rod_jpeg_encoder* e = new (std::nothrow) rod_jpeg_encoder();
     if (e == nullptr) return ROD_ERR_OOM;
+    if (cudaGetDevice(&e->device) != cudaSuccess) { delete e; cudaGetLastError(); return ROD_ERR_NO_DEVICE; }
     e->n_images = n_images;
     e->h_images.resize(n_images);
     e->out_off.resize(n_images + 1);
@@ -576,7 +574,7 @@ extern "C" int rod_jpeg_create(const rod_image_desc* images, int n_images, const
     alloc((void**)&e->d_images, sizeof(JpegImage) * n_images);
     alloc((void**)&e->d_mcu_image, sizeof(uint32_t) * e->h_mcu_image.size());
     alloc((void**)&e->d_tables, sizeof(jpeg::Tables));
-    auto calloc_ = [&](void** p, size_t n) { if (err == cudaSuccess) err = cached_alloc(p, n); };
+    auto calloc_ = [&](void** p, size_t n) { if (err == cudaSuccess) err = cached_alloc(e->device, p, n); };
     calloc_((void**)&e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
     calloc_((void**)&e->d_mcu_bits, sizeof(uint32_t) * (size_t)e->total_mcu);
     alloc((void**)&e->d_total_bits, sizeof(uint32_t) * n_images);
