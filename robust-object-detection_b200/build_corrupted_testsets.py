@@ -15,9 +15,17 @@ RNG: Test_Noise draws each image's field from NumPy's global legacy generator in
 -- the same stream as the reference's np.random.normal calls, regenerated bit for bit by csrc/np_legacy_rng.cpp with the
 per-sample math on all host threads -- so the noisy files are byte-identical too.
 `NOISE_MODE = "philox"` generates the field on the GPU instead (statistically equivalent, not byte-identical).
+
+Several GPUs (BASELINE configs[3]): started under `torchrun --nproc-per-node N` (RANK / WORLD_SIZE / LOCAL_RANK
+in the environment) every rank builds the same directory trees, owns one contiguous block of each image directory's glob
+list -- blocks balanced by file size (sharding.shard_by_bytes), no pixel ever crosses ranks, no collective -- and uses
+GPU LOCAL_RANK; rank 0 alone copies labels / annotations and writes data.yaml.  The files are the ones a single process
+writes: Philox noise is keyed by an image's position in the glob list, and compat noise -- one serial NumPy stream -- is
+left to rank 0 for the whole directory while the other ranks go on with Test_Blur / Test_LowRes.
 """
 from __future__ import annotations
 
+import os
 import shutil
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
@@ -29,6 +37,7 @@ from .augmentations import apply_lowres, apply_motion_blur, apply_noise  # noqa:
 from .augmentations import legacy_normal_f32
 from .augmentations import _motion_blur_kernel as motion_blur_kernel  # noqa: F401
 from .batch import CorruptionPlan
+from .sharding import shard_by_bytes
 
 # ====== paths (same defaults as the reference, build_corrupted_testsets.py:8-10) ======
 YOLO_SRC = Path("data/processed/visdrone_yolo6")
@@ -52,8 +61,33 @@ ENCODER = "gpu"            # "gpu": device JPEG encoder for .jpg / .jpeg outputs
 DECODE_CACHE_BYTES = 8 << 30  # decoded frames of one tree kept for its later variants (548 VisDrone val frames ~ 2.3 GB)
 DEVICE_CACHE_BYTES = 8 << 30   # ... and their uploaded batches kept on the GPU with their JPEG encoders (ENCODER = "gpu"; ~5 bytes of device memory per cached byte)
 
+SHARD = "env"              # "env": RANK / WORLD_SIZE of torchrun decide | (rank, world) | None: this process does everything
+
 VARIANTS = ["Test_Clean", "Test_Noise", "Test_Blur", "Test_LowRes"]
 _OPS = {"Test_Noise": N.OP_NOISE, "Test_Blur": N.OP_BLUR, "Test_LowRes": N.OP_LOWRES}
+
+
+def _rank_world():
+    """(rank, world) of this process: torchrun's environment, or the SHARD knob."""
+    if SHARD is None:
+        return 0, 1
+    if SHARD == "env":
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    else:
+        rank, world = (int(v) for v in SHARD)
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad shard {rank} of {world}")
+    return rank, world
+
+
+def _shard_of(paths, variant: str):
+    """[lo, hi) of the glob list this rank owns for one variant (see the module docstring)."""
+    rank, world = _rank_world()
+    if world == 1:
+        return 0, len(paths)
+    if variant == "Test_Noise" and NOISE_MODE == "compat":   # np.random's stream is serial: one rank draws all of it
+        return (0, len(paths)) if rank == 0 else (0, 0)
+    return shard_by_bytes([p.stat().st_size for p in paths], world)[rank]
 
 
 def set_seed(seed: int):
@@ -240,7 +274,8 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
     if own:
         run = _TreeRun()
     paths = list(src_img_dir.glob("*.*"))  # filesystem order, like the reference (it fixes the noise stream order)
-    philox_index = 0
+    lo, hi = _shard_of(paths, variant)
+    paths = paths[lo:hi]
 
     # compat noise carries a float32 field of 4 bytes per pixel byte through page-locked memory: smaller batches there
     cap = min(BATCH_BYTES, NOISE_BATCH_BYTES) if (variant == "Test_Noise" and NOISE_MODE == "compat") else BATCH_BYTES
@@ -250,26 +285,39 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
         batch_paths, futs, nbytes = [], [], 0
         while i < len(paths) and (nbytes < cap or not futs):
             futs.append(run.pool.submit(run.decode, paths[i]))
-            batch_paths.append(paths[i])
+            batch_paths.append((lo + i, paths[i]))
             i += 1
             nbytes += 6 << 20  # ~ a decoded VisDrone frame; the real size is known after decoding
         return i, batch_paths, futs
 
+    def readable_runs(batch_paths, futs):
+        """The batch without its unreadable files (skipped like the reference does, :110-111), cut where one was skipped:
+        a GPU batch numbers its images consecutively from its first one's position in the glob list (the Philox key)."""
+        runs, prev = [], None
+        for (pos, p), f in zip(batch_paths, futs):
+            im = f.result()
+            if im is None:
+                continue
+            if prev is None or pos != prev + 1:
+                runs.append((pos, []))
+            runs[-1][1].append((p, im))
+            prev = pos
+        return runs
+
     i, batch_paths, futs = submit_decodes(0)
-    while futs:
-        decoded = [(p, f.result()) for p, f in zip(batch_paths, futs)]
-        i, batch_paths, futs = submit_decodes(i)  # the next batch decodes while this one is corrupted and encoded
-        decoded = [(p, im) for p, im in decoded if im is not None]  # unreadable files are skipped (reference :110-111)
-        if not decoded:
+    work = []
+    while futs or work:
+        if not work:
+            work = readable_runs(batch_paths, futs)
+            i, batch_paths, futs = submit_decodes(i)  # the next batch decodes while this one is corrupted and encoded
             continue
+        philox_index, decoded = work.pop(0)
         for p, im in decoded:
             run.remember(p, im)
         images = [im for _, im in decoded]
         if ENCODER == "gpu":
             run.drain(keep=1)  # the pinned source buffer is repacked below: the previous batch's uploads are complete (encode synchronises)
             jobs = _corrupt_encode_batch(variant, decoded, philox_index, run)
-            if variant != "Test_Clean":
-                philox_index += len(images)
             run.pending.append([run.pool.submit(fn, str(dst_img_dir / p.name), payload) for fn, p, payload in jobs])
             continue
         if variant == "Test_Clean":
@@ -277,7 +325,6 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
         else:
             run.drain(keep=1)  # before the third output slot back is reused
             outs = _corrupt_batch(variant, images, philox_index, run)
-            philox_index += len(images)
         run.drain(keep=1)
         run.pending.append([run.pool.submit(cv2.imwrite, str(dst_img_dir / p.name), o) for (p, _), o in zip(decoded, outs)])
     if own:
@@ -296,12 +343,14 @@ def build_yolo_testsets():
         dst_lbl_dir = dst_root / "labels" / "val"
         ensure_dir(dst_img_dir)
         ensure_dir(dst_lbl_dir)
-        for lbl in src_lbl_dir.glob("*.txt"):
-            shutil.copy2(lbl, dst_lbl_dir / lbl.name)
-        write_yolo_valonly_yaml(dst_root)
+        if _rank_world()[0] == 0:
+            for lbl in src_lbl_dir.glob("*.txt"):
+                shutil.copy2(lbl, dst_lbl_dir / lbl.name)
+            write_yolo_valonly_yaml(dst_root)
         _process_images(src_img_dir, dst_img_dir, v, run)
     run.close()
-    print("YOLO test sets created:", (OUT_ROOT / "yolo6").resolve())
+    if _rank_world()[0] == 0:
+        print("YOLO test sets created:", (OUT_ROOT / "yolo6").resolve())
 
 
 def build_coco_testsets():
@@ -316,17 +365,25 @@ def build_coco_testsets():
         dst_ann_dir = dst_root / "annotations"
         ensure_dir(dst_img_dir)
         ensure_dir(dst_ann_dir)
-        shutil.copy2(src_ann, dst_ann_dir / "instances_val.json")
+        if _rank_world()[0] == 0:
+            shutil.copy2(src_ann, dst_ann_dir / "instances_val.json")
         _process_images(src_img_dir, dst_img_dir, v, run)
     run.close()
-    print("COCO test sets created:", (OUT_ROOT / "coco6").resolve())
+    if _rank_world()[0] == 0:
+        print("COCO test sets created:", (OUT_ROOT / "coco6").resolve())
 
 
 def main():
     set_seed(SEED)
+    rank, world = _rank_world()
+    if world > 1 and "LOCAL_RANK" in os.environ:   # one process per GPU
+        import torch
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]) % max(1, torch.cuda.device_count()))
     build_yolo_testsets()
     build_coco_testsets()
-    print("\nAll corrupted test sets are ready under:", OUT_ROOT.resolve())
+    if rank == 0:
+        print("\nAll corrupted test sets are ready under:", OUT_ROOT.resolve(),
+              "" if world == 1 else f"(this is rank 0 of {world}: the other ranks finish on their own)")
 
 
 if __name__ == "__main__":

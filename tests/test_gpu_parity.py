@@ -1143,6 +1143,44 @@ def test_build_corrupted_testsets_drop_in(tmp_path, monkeypatch):
     assert n_files == 2 * 4 * (len(shapes) + 1)
 
 
+@pytest.mark.parametrize("noise_mode", ["philox", "compat"])
+def test_build_corrupted_testsets_sharded_equals_single(tmp_path, monkeypatch, noise_mode):
+    """BASELINE configs[3] with files: two ranks (run here one after the other through the SHARD knob, which stands for
+    torchrun's RANK / WORLD_SIZE) write, between them, exactly the files one process writes -- byte for byte, in both
+    noise modes (Philox is keyed by the position in the glob list; the serial compat stream belongs to rank 0)."""
+    import cv2
+    from robust_object_detection_b200 import build_corrupted_testsets as drv
+    shapes = [(120, 200), (97, 133), (64, 64), (300, 180), (81, 90), (200, 202), (240, 320), (33, 47), (150, 150)]
+    img_dir = tmp_path / "yolo" / "images" / "val"
+    img_dir.mkdir(parents=True)
+    for i, (h, w) in enumerate(shapes):
+        cv2.imwrite(str(img_dir / f"frame_{i:03d}.jpg"), cv2.GaussianBlur(synth(7300 + i, h, w), (0, 0), 1.5))
+    (img_dir / "broken.jpg").write_bytes(b"not a jpeg")   # unreadable files must not shift the Philox keys of the others
+    (tmp_path / "yolo" / "labels" / "val").mkdir(parents=True)
+    (tmp_path / "yolo" / "labels" / "val" / "frame_000.txt").write_text("0 0.5 0.5 0.1 0.1\n")
+    monkeypatch.setattr(drv, "YOLO_SRC", tmp_path / "yolo")
+    monkeypatch.setattr(drv, "NOISE_MODE", noise_mode)
+    monkeypatch.setattr(drv, "BATCH_BYTES", 20 << 20)   # the readahead counts 6 MB per file: four files per batch
+    trees = {}
+    for name, shards in (("single", [None]), ("sharded", [(1, 2), (0, 2)])):
+        monkeypatch.setattr(drv, "OUT_ROOT", tmp_path / name)
+        for shard in shards:
+            monkeypatch.setattr(drv, "SHARD", shard)
+            drv.set_seed(drv.SEED)
+            drv.build_yolo_testsets()
+        files = {}
+        for q in sorted((tmp_path / name).rglob("*")):
+            if q.is_file():
+                files[str(q.relative_to(tmp_path / name))] = q.read_bytes()
+        trees[name] = files
+    assert len(trees["single"]) == 4 * (len(shapes) + 2)   # images + label + data.yaml per variant
+    assert trees["single"].keys() == trees["sharded"].keys()
+    for k, v in trees["single"].items():
+        if k.endswith("data.yaml"):
+            continue   # carries the absolute output root
+        assert trees["sharded"][k] == v, k
+
+
 def test_random_shapes_stress(torch_):
     """120 random shapes (1..320 x 1..420, biased to the kernels' corner cases: w % 4, w % 8, odd sizes, tiny images) in
     ragged batches with 4-byte packing: blur, lowres and compat noise against the oracle, bit-exact."""

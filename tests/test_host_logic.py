@@ -89,6 +89,40 @@ def test_shard_ranges_cover_everything_once():
         assert max(loads) <= 1.1 * sum(sizes) / world + max(sizes)
 
 
+def test_testset_driver_shards(tmp_path, monkeypatch):
+    """Which glob positions a rank of the sharded test-set build owns (BASELINE configs[3]): contiguous blocks that cover
+    the directory once, torchrun's environment by default, the serial compat noise stream on rank 0 alone."""
+    from robust_object_detection_b200 import build_corrupted_testsets as drv
+    paths = []
+    for i in range(23):
+        q = tmp_path / f"f{i:02d}.jpg"
+        q.write_bytes(b"x" * (1000 + 137 * (i % 5) * (i % 5)))
+        paths.append(q)
+    monkeypatch.setattr(drv, "NOISE_MODE", "philox")
+    for world in (1, 2, 4, 8):
+        for v in drv.VARIANTS:
+            seen = []
+            for r in range(world):
+                monkeypatch.setenv("RANK", str(r))
+                monkeypatch.setenv("WORLD_SIZE", str(world))
+                lo, hi = drv._shard_of(paths, v)
+                seen += list(range(lo, hi))
+            assert seen == list(range(len(paths))), (world, v)
+    monkeypatch.setattr(drv, "NOISE_MODE", "compat")
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    monkeypatch.setenv("RANK", "0")
+    assert drv._shard_of(paths, "Test_Noise") == (0, 23) and drv._shard_of(paths, "Test_Blur")[0] == 0
+    monkeypatch.setenv("RANK", "3")
+    assert drv._shard_of(paths, "Test_Noise") == (0, 0) and drv._shard_of(paths, "Test_Blur")[1] == 23
+    monkeypatch.setattr(drv, "SHARD", (1, 2))   # explicit knob wins over the environment
+    assert drv._rank_world() == (1, 2)
+    monkeypatch.setattr(drv, "SHARD", None)
+    assert drv._rank_world() == (0, 1) and drv._shard_of(paths, "Test_LowRes") == (0, 23)
+    monkeypatch.setattr(drv, "SHARD", (2, 2))
+    with pytest.raises(ValueError):
+        drv._rank_world()
+
+
 _GLOO_WORKER = r"""
 import os, sys, json
 sys.path.insert(0, sys.argv[1])
