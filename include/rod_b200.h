@@ -193,6 +193,31 @@ ROD_API const uint32_t* rod_jpeg_stream_lengths(const rod_jpeg_encoder* enc);
  * (host_out holds rod_jpeg_stream_offset(enc, n_images) bytes); returns when the copies are complete */
 ROD_API int rod_jpeg_download(rod_jpeg_encoder* enc, uint8_t* host_out, uint32_t* host_len, void* stream);
 
+/* SURVEY 8f rank 1, the reading side -- `img = cv2.imread(str(img_path))` (scripts/build_corrupted_testsets.py:109, :149)
+ * for a batch of files: baseline JPEG decoding whose pixels equal OpenCV 4.13.0's (libjpeg-turbo defaults: islow IDCT, fancy
+ * h2v2 chroma upsampling, BGR output) straight into a device-resident HWC batch.  Decodable here: baseline sequential,
+ * 8 bit, Y Cb Cr sampled 2x2 / 1x1 / 1x1 in one interleaved scan, no restart markers, no EXIF rotation, width >= 5 --
+ * what OpenCV's own encoder writes.  Every other file is REPORTED (status >= 10), never approximated: the caller reads it
+ * with the host codec.
+ *   rod_jpegdec_probe        host only: ROD_OK + (height, width) when the device decoder takes the file, else
+ *                            ROD_ERR_UNSUPPORTED
+ *   rod_jpegdec_create       host work for a batch (markers, tables, scans without byte stuffing into page-locked memory,
+ *                            on `host_threads` threads); image i will be written at pixels + dst_offsets[i] with row pitch
+ *                            dst_pitches[i] bytes (NULL or 0: 3 * width)
+ *   rod_jpegdec_host_status  the verdict of create per image (0: decodable; 11: not a JPEG; 12: unsupported layout;
+ *                            13: scan does not end in EOI) and the sizes of the decodable ones
+ *   rod_jpegdec_decode       upload + Huffman decoding + IDCT + upsampling / colour conversion, asynchronous on `stream`
+ *   rod_jpegdec_status       waits for `stream`; per image 0: decoded; 1 / 2: corrupt / truncated entropy data (pixels
+ *                            undefined); >= 10: as above */
+typedef struct rod_jpeg_decoder rod_jpeg_decoder;
+ROD_API int rod_jpegdec_probe(const uint8_t* file, uint64_t n, int* height, int* width);
+ROD_API int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* lens, int n_images, const uint64_t* dst_offsets,
+                       const int64_t* dst_pitches, int host_threads, rod_jpeg_decoder** out_dec);
+ROD_API void rod_jpegdec_destroy(rod_jpeg_decoder* dec);
+ROD_API int rod_jpegdec_host_status(const rod_jpeg_decoder* dec, int32_t* status, int32_t* heights, int32_t* widths);
+ROD_API int rod_jpegdec_decode(rod_jpeg_decoder* dec, uint8_t* pixels, void* stream);
+ROD_API int rod_jpegdec_status(rod_jpeg_decoder* dec, int32_t* status, void* stream);
+
 /* Host-buffer entry points (what a per-image Python/cgo/JNI caller binds): src/dst are HOST
  * pointers laid out by the plan's descriptors; the call stages through pinned memory,
  * overlaps H2D / kernel / D2H in chunks of images, and returns after dst is complete. */

@@ -57,6 +57,12 @@ SYMBOLS = {
     "rod_jpeg_stream_base": (_vp, [_vp]),
     "rod_jpeg_stream_lengths": (_vp, [_vp]),
     "rod_jpeg_download": (_i, [_vp, _vp, _vp, _vp]),
+    "rod_jpegdec_probe": (_i, [_vp, _u64, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "rod_jpegdec_create": (_i, [_vp, _vp, _i, _vp, _vp, _i, ctypes.POINTER(_vp)]),
+    "rod_jpegdec_destroy": (None, [_vp]),
+    "rod_jpegdec_host_status": (_i, [_vp, _vp, _vp, _vp]),
+    "rod_jpegdec_decode": (_i, [_vp, _vp, _vp]),
+    "rod_jpegdec_status": (_i, [_vp, _vp, _vp]),
     "rod_apply_host": (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _d, _u64, _u64, _u32]),
 }
 

@@ -4,7 +4,11 @@ Same module surface (constants, set_seed, build_yolo_testsets, build_coco_testse
 for Test_Clean / Test_Noise / Test_Blur / Test_LowRes the images of `images/val` are read with cv2.imread, corrupted and
 written with cv2.imwrite under the same file name; labels / annotations are copied; data.yaml is written
 (build_corrupted_testsets.py:62-166).  The corruption itself runs on the GPU, one ragged batch at a time
-while JPEG decoding -- the reference's OpenCV codec -- runs on a host thread pool around it (the next batch decodes
+and so does the JPEG codec on both sides of it.  JPEG DECODING (`DECODER = "gpu"`: rod_jpegdec_decode, libjpeg-turbo's
+Huffman decoding / islow IDCT / fancy upsampling / colour conversion restated in CUDA, pixels identical to cv2.imread's): the
+I/O threads only read the files; a file of a layout the device decoder does not take (progressive, other chroma sampling,
+restart markers, EXIF rotation, PNG ...) is read with cv2.imread like the reference does.  A tree's decoded batches stay on
+the device for its four variants.  `DECODER = "host"` decodes with cv2.imread on the I/O threads (the next batch decodes
 while a batch is on the GPU; a tree's decoded frames are reused by its four variants).  JPEG ENCODING runs on the GPU too
 (`ENCODER = "gpu"`: rod_jpeg_encode, libjpeg-turbo's integer algorithms restated in CUDA, the header bytes taken from
 OpenCV itself): the corrupted frames never leave the device, only the compressed streams do, and the files are
@@ -57,6 +61,7 @@ PHILOX_SEED = SEED
 BATCH_BYTES = 512 << 20    # decoded source bytes per GPU batch
 NOISE_BATCH_BYTES = 128 << 20   # ... of a compat-noise batch (its float32 field is 4x that, page-locked)
 IO_THREADS = 16
+DECODER = "gpu"            # "gpu": device JPEG decoder for .jpg / .jpeg sources (same pixels as cv2.imread; needs ENCODER = "gpu") | "host": cv2.imread
 ENCODER = "gpu"            # "gpu": device JPEG encoder for .jpg / .jpeg outputs (same bytes as cv2.imwrite) | "host": cv2.imwrite
 DECODE_CACHE_BYTES = 8 << 30  # decoded frames of one tree kept for its later variants (548 VisDrone val frames ~ 2.3 GB)
 DEVICE_CACHE_BYTES = 8 << 30   # ... and their uploaded batches kept on the GPU with their JPEG encoders (ENCODER = "gpu"; ~5 bytes of device memory per cached byte)
@@ -150,33 +155,92 @@ def _write_bytes(path: str, data) -> bool:
     return True
 
 
-def _corrupt_encode_batch(variant: str, decoded, philox_index: int, run: "_TreeRun"):
-    """One ragged batch on the device: upload, corrupt (Test_Clean: nothing), JPEG-encode; returns the write jobs
-    [(function, path, payload)] -- encoded files as bytes, everything that is not a .jpg / .jpeg (or did not fit the
-    encoder's buffers) as a decoded array for cv2.imwrite."""
+class _Encoded:
+    """A source file the device decoder takes: its bytes and the size cv2.imread would return."""
+    __slots__ = ("data", "shape")
+
+    def __init__(self, data, shape):
+        self.data, self.shape = data, shape
+
+
+def _load_source(path: Path, run: "_TreeRun"):
+    """What an I/O thread does for one source file: with the device decoder the file bytes (+ the frame size from the
+    header); else -- host decoder, other file types, layouts the device decoder does not take -- cv2.imread's array.  None:
+    unreadable (the reference skips such files, build_corrupted_testsets.py:110-111)."""
+    if DECODER == "gpu" and ENCODER == "gpu" and path.suffix.lower() in (".jpg", ".jpeg"):
+        from .jpeg import probe
+        try:
+            data = path.read_bytes()
+        except OSError:
+            return None
+        shape = probe(data)
+        if shape is not None:
+            return _Encoded(data, shape)
+    return run.decode(path)
+
+
+class _DeviceRun:
+    """Consecutive readable files of one directory on the device: the plan of their sizes, the decoded frames, the JPEG
+    encoder for that layout; `skip`: images whose entropy-coded data turned out to be broken and that OpenCV cannot read either."""
+    __slots__ = ("pos", "paths", "plan", "src_dev", "enc", "skip")
+
+
+def _upload_run(pos: int, items, run: "_TreeRun") -> "_DeviceRun":
+    """items: [(path, _Encoded | ndarray)].  Decodes / uploads them into one device batch."""
     import cv2
     import torch
-    from .jpeg import JpegEncoder
-    images = [im for _, im in decoded]
-    shapes = [(im.shape[0], im.shape[1]) for im in images]
-    key = tuple(p for p, _ in decoded)
-    hit = run.dev_cache.get(key)
-    if hit is not None:   # the batch was uploaded for an earlier variant of this tree: it is still on the device
-        plan, src_dev, enc = hit
-    else:
-        plan = CorruptionPlan.ragged(shapes)
-        src = run.pinned("src", plan.src_bytes)
+    from .jpeg import JpegDecoder, JpegEncoder
+    r = _DeviceRun()
+    r.pos, r.paths, r.skip = pos, [p for p, _ in items], set()
+    shapes = [(it.shape[0], it.shape[1]) for _, it in items]
+    r.plan = CorruptionPlan.ragged(shapes)
+    r.src_dev = torch.empty(r.plan.src_bytes, dtype=torch.uint8, device="cuda")
+    enc_idx = [i for i, (_, it) in enumerate(items) if isinstance(it, _Encoded)]
+    dec = None
+    if enc_idx:
+        dec = JpegDecoder([items[i][1].data for i in enc_idx], [r.plan.src_offsets[i] for i in enc_idx], host_threads=IO_THREADS)
+        dec.decode(r.src_dev)
 
-        def put(args):
-            im, off = args
+    def put(i, arr):   # (late, rare: pageable copy)
+        off = r.plan.src_offsets[i]
+        r.src_dev[off:off + arr.size].copy_(torch.from_numpy(np.ascontiguousarray(arr).reshape(-1)))
+
+    host_idx = [i for i, (_, it) in enumerate(items) if not isinstance(it, _Encoded)]
+    if host_idx:   # frames decoded by the host codec: packed into page-locked memory by the I/O threads, then uploaded
+        src = run.pinned("src", r.plan.src_bytes)
+
+        def pack(i):
+            im, off = items[i][1], r.plan.src_offsets[i]
             src[off:off + im.size].reshape(im.shape)[...] = im
 
-        list(run.pool.map(put, zip(images, plan.src_offsets)))
-        src_dev = run.pinned_tensor("src", plan.src_bytes).cuda(non_blocking=True)
-        enc = JpegEncoder(shapes, plan.dst_offsets)
-        if run.dev_cache_bytes + plan.src_bytes <= DEVICE_CACHE_BYTES:
-            run.dev_cache[key] = (plan, src_dev, enc)
-            run.dev_cache_bytes += plan.src_bytes
+        list(run.pool.map(pack, host_idx))
+        pinned = run.pinned_tensor("src", r.plan.src_bytes)
+        if len(host_idx) == len(items):
+            r.src_dev = pinned.cuda(non_blocking=True)
+        else:
+            for i in host_idx:
+                off, n = r.plan.src_offsets[i], items[i][1].size
+                r.src_dev[off:off + n].copy_(pinned[off:off + n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the page-locked buffer is repacked for the next run
+    if dec is not None:
+        for i, st in zip(enc_idx, dec.status()):
+            if st != 0:   # broken entropy-coded data: whatever OpenCV makes of the file is the reference's answer
+                arr = cv2.imread(str(items[i][0]))
+                if arr is not None and arr.shape[:2] == shapes[i] and arr.ndim == 3:
+                    put(i, arr)
+                else:
+                    r.skip.add(i)
+    r.enc = JpegEncoder(shapes, r.plan.dst_offsets)
+    return r
+
+
+def _corrupt_encode(variant: str, r: "_DeviceRun", run: "_TreeRun"):
+    """One device batch: corrupt (Test_Clean: nothing), JPEG-encode; returns the write jobs [(function, path, payload)]
+    -- encoded files as bytes, everything that is not a .jpg / .jpeg (or did not fit the encoder's buffers) as a decoded
+    array for cv2.imwrite."""
+    import cv2
+    import torch
+    plan, src_dev = r.plan, r.src_dev
     if variant == "Test_Clean":
         pix = src_dev
     else:
@@ -184,24 +248,26 @@ def _corrupt_encode_batch(variant: str, decoded, philox_index: int, run: "_TreeR
         if variant == "Test_Noise":
             field = None
             if NOISE_MODE == "compat":   # the draws of augmentations.py:31, one per image, in order
-                total = sum(im.size for im in images)
+                total = sum(3 * h * w for h, w in plan.shapes)
                 noise = run.pinned("noise", 4 * total).view(np.float32)
                 o = 0
-                for im in images:
-                    legacy_normal_f32(NOISE_SIGMA, im.shape, out=noise[o:o + im.size])
-                    o += im.size
+                for h, w in plan.shapes:
+                    legacy_normal_f32(NOISE_SIGMA, (h, w, 3), out=noise[o:o + 3 * h * w])
+                    o += 3 * h * w
                 # (indexed by the plan's packed element index -- images back to back -- as rod_noise_u8 expects)
                 field = run.pinned_tensor("noise", 4 * total).view(torch.float32).cuda(non_blocking=True)
-            plan.noise(src_dev, pix, field, float(NOISE_SIGMA), seed=PHILOX_SEED, first_image_index=philox_index)
+            plan.noise(src_dev, pix, field, float(NOISE_SIGMA), seed=PHILOX_SEED, first_image_index=r.pos)
         elif variant == "Test_Blur":
             if float(BLUR_ANGLE_DEG) != 0.0:
                 plan.set_blur_kernel(motion_blur_kernel(BLUR_KERNEL, BLUR_ANGLE_DEG))
             plan.blur(src_dev, pix, int(BLUR_KERNEL), float(BLUR_ANGLE_DEG))
         else:
             plan.lowres(src_dev, pix, float(DOWNSCALE_FACTOR))
-    files = enc.encode(pix, copy=False)   # views into a ring of three download buffers; at most two batches of writes are pending
+    files = r.enc.encode(pix, copy=False)   # views into a ring of three download buffers; at most two batches of writes are pending
     jobs = []
-    for (p, _), data, off, (h, w) in zip(decoded, files, plan.dst_offsets, shapes):
+    for i, (p, data, off, (h, w)) in enumerate(zip(r.paths, files, plan.dst_offsets, plan.shapes)):
+        if i in r.skip:
+            continue
         if data is not None and p.suffix.lower() in (".jpg", ".jpeg"):
             jobs.append((_write_bytes, p, data))
         else:
@@ -222,7 +288,7 @@ class _TreeRun:
         self.pool = ThreadPoolExecutor(max(1, min(IO_THREADS, cores - 2)) if NOISE_MODE == "compat" else IO_THREADS)
         self.cache = {}
         self.cache_bytes = 0
-        self.dev_cache = {}    # batch (tuple of paths) -> (plan, uploaded source batch, JPEG encoder)
+        self.dev_cache = {}    # batch (tuple of paths) -> [_DeviceRun]: decoded frames, plan and JPEG encoder of its readable runs
         self.dev_cache_bytes = 0
         self.pending = []  # one list of futures per batch in flight
         self._pinned = {}  # name -> page-locked torch uint8 tensor (grow-only)
@@ -279,16 +345,21 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
 
     # compat noise carries a float32 field of 4 bytes per pixel byte through page-locked memory: smaller batches there
     cap = min(BATCH_BYTES, NOISE_BATCH_BYTES) if (variant == "Test_Noise" and NOISE_MODE == "compat") else BATCH_BYTES
+    device = ENCODER == "gpu"
 
-    def submit_decodes(i):
-        """decode ahead until the batch is full (cv2 releases the GIL)"""
-        batch_paths, futs, nbytes = [], [], 0
-        while i < len(paths) and (nbytes < cap or not futs):
-            futs.append(run.pool.submit(run.decode, paths[i]))
+    def submit_loads(i):
+        """read / decode ahead until the batch is full (cv2 and file reads release the GIL); a batch that is still on the
+        device from an earlier variant of this tree is not read again"""
+        batch_paths, nbytes = [], 0
+        while i < len(paths) and (nbytes < cap or not batch_paths):
             batch_paths.append((lo + i, paths[i]))
             i += 1
             nbytes += 6 << 20  # ~ a decoded VisDrone frame; the real size is known after decoding
-        return i, batch_paths, futs
+        key = tuple(p for _, p in batch_paths)
+        if device and key in run.dev_cache:
+            return i, batch_paths, None
+        load = (lambda p: _load_source(p, run)) if device else run.decode
+        return i, batch_paths, [run.pool.submit(load, p) for _, p in batch_paths]
 
     def readable_runs(batch_paths, futs):
         """The batch without its unreadable files (skipped like the reference does, :110-111), cut where one was skipped:
@@ -304,29 +375,40 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
             prev = pos
         return runs
 
-    i, batch_paths, futs = submit_decodes(0)
-    work = []
-    while futs or work:
-        if not work:
-            work = readable_runs(batch_paths, futs)
-            i, batch_paths, futs = submit_decodes(i)  # the next batch decodes while this one is corrupted and encoded
+    i, batch_paths, futs = submit_loads(0)
+    while batch_paths:
+        cur_paths, cur_futs = batch_paths, futs
+        if device:
+            key = tuple(p for _, p in cur_paths)
+            dev_runs = run.dev_cache.get(key)
+            if dev_runs is None:
+                work = readable_runs(cur_paths, cur_futs)
+                i, batch_paths, futs = submit_loads(i)  # the next batch is read while this one is decoded, corrupted and encoded
+                dev_runs = [_upload_run(pos, items, run) for pos, items in work]
+                nbytes = sum(r.plan.src_bytes for r in dev_runs)
+                if run.dev_cache_bytes + nbytes <= DEVICE_CACHE_BYTES:
+                    run.dev_cache[key] = dev_runs
+                    run.dev_cache_bytes += nbytes
+            else:
+                i, batch_paths, futs = submit_loads(i)
+            for r in dev_runs:
+                run.drain(keep=1)  # the encoder's download ring has three buffers: at most two batches of writes are pending
+                jobs = _corrupt_encode(variant, r, run)
+                run.pending.append([run.pool.submit(fn, str(dst_img_dir / p.name), payload) for fn, p, payload in jobs])
             continue
-        philox_index, decoded = work.pop(0)
-        for p, im in decoded:
-            run.remember(p, im)
-        images = [im for _, im in decoded]
-        if ENCODER == "gpu":
-            run.drain(keep=1)  # the pinned source buffer is repacked below: the previous batch's uploads are complete (encode synchronises)
-            jobs = _corrupt_encode_batch(variant, decoded, philox_index, run)
-            run.pending.append([run.pool.submit(fn, str(dst_img_dir / p.name), payload) for fn, p, payload in jobs])
-            continue
-        if variant == "Test_Clean":
-            outs = images
-        else:
-            run.drain(keep=1)  # before the third output slot back is reused
-            outs = _corrupt_batch(variant, images, philox_index, run)
-        run.drain(keep=1)
-        run.pending.append([run.pool.submit(cv2.imwrite, str(dst_img_dir / p.name), o) for (p, _), o in zip(decoded, outs)])
+        work = readable_runs(cur_paths, cur_futs)
+        i, batch_paths, futs = submit_loads(i)  # the next batch decodes while this one is corrupted and encoded
+        for philox_index, decoded in work:
+            for p, im in decoded:
+                run.remember(p, im)
+            images = [im for _, im in decoded]
+            if variant == "Test_Clean":
+                outs = images
+            else:
+                run.drain(keep=1)  # before the third output slot back is reused
+                outs = _corrupt_batch(variant, images, philox_index, run)
+            run.drain(keep=1)
+            run.pending.append([run.pool.submit(cv2.imwrite, str(dst_img_dir / p.name), o) for (p, _), o in zip(decoded, outs)])
     if own:
         run.close()
 

@@ -454,6 +454,11 @@ void cached_free(int dev, void* p, size_t n) {   // dev: the device the block wa
 }
 }  // namespace
 
+namespace rod {   // the same cache serves the decoder (jpegdec.cu)
+cudaError_t block_cache_alloc(int dev, void** p, size_t n) { return cached_alloc(dev, p, n); }
+void block_cache_free(int dev, void* p, size_t n) { cached_free(dev, p, n); }
+}  // namespace rod
+
 // releases the cached device blocks of destroyed encoders
 extern "C" void rod_jpeg_trim(void) {
     std::lock_guard<std::mutex> lock(g_cache_mutex);

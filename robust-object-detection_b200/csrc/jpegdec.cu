@@ -1,0 +1,317 @@
+// jpegdec.cu -- f1: device-side baseline JPEG DECODER whose pixels equal cv2.imread's (sm_100a).
+//
+// Reference: scripts/build_corrupted_testsets.py:109 / :149 (`img = cv2.imread(str(img_path))`): with corruption and encoding
+// on the GPU, decoding the source frames on host threads is what the test-set build spends its time in.  The arithmetic
+// is rod_jpegdec.h (libjpeg-turbo's integer algorithms, checked on the CPU against cv2.imdecode by tests/emu); this file
+// is the batch machinery:
+//   host    rod_jpegdec_create: per file (on `host_threads` threads) walk the markers, build the decoding tables, copy the
+//           entropy-coded segment without its 0xFF00 stuffing into one page-locked buffer; equal table sets are shared
+//   device  jpegdec_huffman_kernel   one warp per image, lane 0 decodes the scan (a JPEG scan without restart markers is
+//                                    one serial bit stream; images are what runs in parallel) with the image's table set
+//                                    in shared memory; coefficients int16, natural order, per-component block rasters
+//           jpegdec_idct_kernel      one thread per 8x8 block: dequantisation + islow IDCT in registers -> Y / Cb / Cr planes
+//           jpegdec_color_kernel     one thread per two output pixels: fancy h2v2 chroma upsampling + YCbCr -> BGR, written
+//                                    straight into the caller's HWC batch (the layout of a rod_plan)
+// Files of another layout (progressive, 4:4:4, restart markers, EXIF rotation ...) are reported per image; the caller
+// decodes those with the host codec.  No CPU decoding in here.
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rod_internal.h"
+#include "rod_jpegdec_host.h"
+
+namespace rod {
+using namespace jpegdec;
+
+struct JpegDecParams {
+    const ImageRec* images;
+    const TableSet* tables;
+    const uint8_t* streams;
+    int16_t* coef;
+    uint8_t* planes;
+    uint8_t* pixels;
+    int32_t* status;
+    const uint32_t* block_start;   // [n + 1] prefix sums of 6 * MCUs
+    const uint32_t* pair_start;    // [n + 1] prefix sums of h * ceil(w / 2)
+    int n_images;
+};
+
+__global__ void __launch_bounds__(32) jpegdec_huffman_kernel(JpegDecParams p) {
+    __shared__ TableSet ts;
+    __shared__ uint8_t nat[64];
+    const ImageRec im = p.images[blockIdx.x];
+    if (im.h == 0) return;   // not decodable here: status set by the host
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.tables + im.table_set);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&ts);
+        for (int i = threadIdx.x; i < (int)(sizeof(TableSet) / 4); i += 32) dst[i] = __ldg(src + i);
+    }
+    nat[threadIdx.x] = (uint8_t)rod::jpeg::natural_order(threadIdx.x);
+    nat[threadIdx.x + 32] = (uint8_t)rod::jpeg::natural_order(threadIdx.x + 32);
+    __syncwarp();
+    if (threadIdx.x == 0) p.status[blockIdx.x] = decode_scan(im, ts, nat, p.streams + im.stream_off, p.coef + im.coef_off);
+}
+
+// image that owns flat index i of a prefix-sum array
+__device__ __forceinline__ int owner_of(const uint32_t* start, int n, uint32_t i) {
+    int lo = 0, hi = n;   // start[lo] <= i < start[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(start + mid) <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) jpegdec_idct_kernel(JpegDecParams p) {
+    const uint32_t gi = blockIdx.x * 128u + threadIdx.x;
+    if (gi >= __ldg(p.block_start + p.n_images)) return;
+    const int img = owner_of(p.block_start, p.n_images, gi);
+    const ImageRec im = p.images[img];
+    if (__ldg(p.status + img) != 0) return;
+    const uint32_t b = gi - __ldg(p.block_start + img);
+    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
+    const uint32_t yblocks = 4u * mcu_w * mcu_h, cblocks = (uint32_t)mcu_w * mcu_h;
+    int comp;
+    uint32_t bi;
+    long pitch;
+    uint8_t* plane = p.planes + im.plane_off;
+    if (b < yblocks) { comp = 0; bi = b; pitch = 16L * mcu_w; }
+    else if (b < yblocks + cblocks) { comp = 1; bi = b - yblocks; pitch = 8L * mcu_w; plane += 256L * mcu_w * mcu_h; }
+    else { comp = 2; bi = b - yblocks - cblocks; pitch = 8L * mcu_w; plane += 320L * mcu_w * mcu_h; }
+    const uint32_t bpr = (uint32_t)(pitch >> 3);
+    const uint32_t by = bi / bpr, bx = bi - by * bpr;
+    __align__(16) int16_t c[64];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.coef + im.coef_off + 64ull * b);
+        uint4* dst = reinterpret_cast<uint4*>(c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = src[i];
+    }
+    __align__(16) uint16_t q[64];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.tables[im.table_set].quant[comp]);
+        uint4* dst = reinterpret_cast<uint4*>(q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = __ldg(src + i);
+    }
+    __align__(8) uint8_t o[64];
+    idct_islow(c, q, o, 8);
+    uint8_t* dst = plane + (8L * by) * pitch + 8 * bx;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2*>(dst + r * pitch) = *reinterpret_cast<const uint2*>(o + 8 * r);
+}
+
+__global__ void __launch_bounds__(256) jpegdec_color_kernel(JpegDecParams p) {
+    const uint32_t gi = blockIdx.x * 256u + threadIdx.x;
+    if (gi >= __ldg(p.pair_start + p.n_images)) return;
+    const int img = owner_of(p.pair_start, p.n_images, gi);
+    const ImageRec im = p.images[img];
+    if (__ldg(p.status + img) != 0) return;
+    const uint32_t k = gi - __ldg(p.pair_start + img);
+    const int cw = (im.w + 1) >> 1, ch = (im.h + 1) >> 1;
+    const int y = (int)(k / (uint32_t)cw), cx = (int)(k - (uint32_t)y * (uint32_t)cw);
+    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
+    const long ypitch = 16L * mcu_w, cpitch = 8L * mcu_w;
+    const uint8_t* yp = p.planes + im.plane_off;
+    const uint8_t* cbp = yp + 256L * mcu_w * mcu_h;
+    const uint8_t* crp = yp + 320L * mcu_w * mcu_h;
+    uint8_t* out = p.pixels + im.dst_off + (int64_t)y * im.dst_pitch + 6 * cx;
+    const int x = 2 * cx;
+    uint8_t px[6];
+    ycc_to_bgr(yp[y * ypitch + x], upsample_h2v2(cbp, cpitch, cw, ch, x, y), upsample_h2v2(crp, cpitch, cw, ch, x, y), px);
+    const bool two = x + 1 < im.w;
+    if (two)
+        ycc_to_bgr(yp[y * ypitch + x + 1], upsample_h2v2(cbp, cpitch, cw, ch, x + 1, y), upsample_h2v2(crp, cpitch, cw, ch, x + 1, y),
+                   px + 3);
+    if (two && ((uintptr_t)out & 1) == 0) {   // 6 bytes at a 2-byte aligned address
+        uint16_t* o2 = reinterpret_cast<uint16_t*>(out);
+        o2[0] = (uint16_t)(px[0] | (px[1] << 8));
+        o2[1] = (uint16_t)(px[2] | (px[3] << 8));
+        o2[2] = (uint16_t)(px[4] | (px[5] << 8));
+    } else {
+        for (int i = 0; i < (two ? 6 : 3); ++i) out[i] = px[i];
+    }
+}
+
+}  // namespace rod
+
+using namespace rod;
+
+struct rod_jpeg_decoder {
+    int device = 0;
+    int n_images = 0;
+    std::vector<ImageRec> h_images;
+    std::vector<int32_t> h_status;       // host verdict per image: 0 decodable, else 10 + ParseStatus / 13 (no EOI)
+    std::vector<TableSet> h_tables;
+    std::vector<uint32_t> h_block_start, h_pair_start;
+    uint8_t* h_streams = nullptr;        // page-locked
+    size_t stream_bytes = 0, coef_elems = 0, plane_bytes = 0;
+    ImageRec* d_images = nullptr;
+    TableSet* d_tables = nullptr;
+    uint32_t* d_block_start = nullptr;
+    uint32_t* d_pair_start = nullptr;
+    int32_t* d_status = nullptr;
+    uint8_t* d_streams = nullptr;
+    int16_t* d_coef = nullptr;
+    uint8_t* d_planes = nullptr;
+};
+
+extern "C" int rod_jpegdec_probe(const uint8_t* file, uint64_t n, int* height, int* width) {
+    if (file == nullptr || height == nullptr || width == nullptr) return ROD_ERR_INVALID_ARG;
+    FileInfo info;
+    std::vector<TableSet> ts(1);
+    const ParseStatus st = parse_file(file, (size_t)n, &info, &ts[0]);
+    if (st != PARSE_OK) return ROD_ERR_UNSUPPORTED;
+    *height = info.height;
+    *width = info.width;
+    return ROD_OK;
+}
+
+extern "C" void rod_jpegdec_destroy(rod_jpeg_decoder* d) {
+    if (d == nullptr) return;
+    void* small[] = {d->d_images, d->d_tables, d->d_block_start, d->d_pair_start, d->d_status};
+    for (void* q : small)
+        if (q) cudaFree(q);
+    block_cache_free(d->device, d->d_streams, d->stream_bytes);
+    block_cache_free(d->device, d->d_coef, d->coef_elems * sizeof(int16_t));
+    block_cache_free(d->device, d->d_planes, d->plane_bytes);
+    if (d->h_streams) cudaFreeHost(d->h_streams);
+    delete d;
+}
+
+extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* lens, int n_images, const uint64_t* dst_offsets,
+                                  const int64_t* dst_pitches, int host_threads, rod_jpeg_decoder** out_dec) {
+    if (files == nullptr || lens == nullptr || dst_offsets == nullptr || n_images < 1 || out_dec == nullptr) return ROD_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return ROD_ERR_NO_DEVICE; }
+    rod_jpeg_decoder* d = new (std::nothrow) rod_jpeg_decoder();
+    if (d == nullptr) return ROD_ERR_OOM;
+    if (cudaGetDevice(&d->device) != cudaSuccess) { delete d; cudaGetLastError(); return ROD_ERR_NO_DEVICE; }
+    d->n_images = n_images;
+    d->h_images.assign(n_images, ImageRec{});
+    d->h_status.assign(n_images, 0);
+    // stream slots: a file's unstuffed scan is never longer than the file
+    std::vector<uint64_t> slot(n_images + 1, 0);
+    for (int i = 0; i < n_images; ++i) slot[i + 1] = slot[i] + ((lens[i] + 32 + 15) & ~(uint64_t)15);
+    d->stream_bytes = (size_t)slot[n_images] + 64;
+    if (cudaHostAlloc((void**)&d->h_streams, d->stream_bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        rod_jpegdec_destroy(d);
+        return ROD_ERR_OOM;
+    }
+    std::vector<TableSet> per_image(n_images);
+    auto work = [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            ImageRec& im = d->h_images[i];
+            FileInfo info;
+            const ParseStatus st = files[i] ? parse_file(files[i], (size_t)lens[i], &info, &per_image[i]) : PARSE_NOT_JPEG;
+            if (st != PARSE_OK) { d->h_status[i] = 10 + (int)st; continue; }
+            const size_t sb = unstuff_scan(files[i], (size_t)lens[i], info.scan_begin, d->h_streams + slot[i]);
+            if (sb == (size_t)-1) { d->h_status[i] = 13; continue; }
+            im.h = info.height; im.w = info.width;
+            im.stream_bytes = (uint32_t)sb;
+            im.stream_off = slot[i];
+            im.dst_off = dst_offsets[i];
+            im.dst_pitch = (dst_pitches && dst_pitches[i]) ? dst_pitches[i] : 3LL * info.width;
+        }
+    };
+    {
+        int nt = host_threads < 1 ? 1 : (host_threads > 64 ? 64 : host_threads);
+        if (nt > n_images) nt = n_images;
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, (int)((long)n_images * t / nt), (int)((long)n_images * (t + 1) / nt));
+        work(0, (int)((long)n_images / nt));
+        for (auto& t : th) t.join();
+    }
+    // shared table sets, buffer layout
+    std::map<std::string, int> seen;
+    d->h_block_start.assign(n_images + 1, 0);
+    d->h_pair_start.assign(n_images + 1, 0);
+    uint64_t blocks = 0, pairs = 0;
+    for (int i = 0; i < n_images; ++i) {
+        ImageRec& im = d->h_images[i];
+        if (d->h_status[i] == 0) {
+            std::string key(reinterpret_cast<const char*>(&per_image[i]), sizeof(TableSet));
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(std::move(key), (int)d->h_tables.size()).first;
+                d->h_tables.push_back(per_image[i]);
+            }
+            im.table_set = it->second;
+            const uint64_t mcus = (uint64_t)((im.w + 15) >> 4) * (uint64_t)((im.h + 15) >> 4);
+            im.coef_off = d->coef_elems;
+            im.plane_off = d->plane_bytes;
+            d->coef_elems += mcus * 6 * 64;
+            d->plane_bytes += mcus * 384;
+            blocks += mcus * 6;
+            pairs += (uint64_t)im.h * (uint64_t)((im.w + 1) >> 1);
+        }
+        d->h_block_start[i + 1] = (uint32_t)blocks;
+        d->h_pair_start[i + 1] = (uint32_t)pairs;
+    }
+    if (blocks >= (1ull << 32) || pairs >= (1ull << 32)) { rod_jpegdec_destroy(d); return ROD_ERR_UNSUPPORTED; }
+    if (d->h_tables.empty()) d->h_tables.push_back(TableSet{});
+    cudaError_t err = cudaSuccess;
+    auto alloc = [&](void** p, size_t n) { if (err == cudaSuccess) err = cudaMalloc(p, n ? n : 16); };
+    auto calloc_ = [&](void** p, size_t n) { if (err == cudaSuccess) err = block_cache_alloc(d->device, p, n ? n : 16); };
+    alloc((void**)&d->d_images, sizeof(ImageRec) * n_images);
+    alloc((void**)&d->d_tables, sizeof(TableSet) * d->h_tables.size());
+    alloc((void**)&d->d_block_start, sizeof(uint32_t) * (n_images + 1));
+    alloc((void**)&d->d_pair_start, sizeof(uint32_t) * (n_images + 1));
+    alloc((void**)&d->d_status, sizeof(int32_t) * n_images);
+    calloc_((void**)&d->d_streams, d->stream_bytes);
+    calloc_((void**)&d->d_coef, d->coef_elems * sizeof(int16_t));
+    calloc_((void**)&d->d_planes, d->plane_bytes);
+    if (err != cudaSuccess) {
+        rod_jpegdec_destroy(d);
+        return cuda_fail(err);
+    }
+    *out_dec = d;
+    return ROD_OK;
+}
+
+extern "C" int rod_jpegdec_host_status(const rod_jpeg_decoder* d, int32_t* status, int32_t* heights, int32_t* widths) {
+    if (d == nullptr || status == nullptr) return ROD_ERR_INVALID_ARG;
+    for (int i = 0; i < d->n_images; ++i) {
+        status[i] = d->h_status[i];
+        if (heights) heights[i] = d->h_images[i].h;
+        if (widths) widths[i] = d->h_images[i].w;
+    }
+    return ROD_OK;
+}
+
+extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* stream) {
+    if (d == nullptr || pixels == nullptr) return ROD_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = d->n_images;
+    ROD_CUDA(cudaMemcpyAsync(d->d_images, d->h_images.data(), sizeof(ImageRec) * n, cudaMemcpyHostToDevice, st));
+    ROD_CUDA(cudaMemcpyAsync(d->d_tables, d->h_tables.data(), sizeof(TableSet) * d->h_tables.size(), cudaMemcpyHostToDevice, st));
+    ROD_CUDA(cudaMemcpyAsync(d->d_block_start, d->h_block_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    ROD_CUDA(cudaMemcpyAsync(d->d_pair_start, d->h_pair_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    ROD_CUDA(cudaMemcpyAsync(d->d_status, d->h_status.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    ROD_CUDA(cudaMemcpyAsync(d->d_streams, d->h_streams, d->stream_bytes, cudaMemcpyHostToDevice, st));
+    if (d->coef_elems == 0) return ROD_OK;
+    ROD_CUDA(cudaMemsetAsync(d->d_coef, 0, d->coef_elems * sizeof(int16_t), st));
+    JpegDecParams p;
+    p.images = d->d_images; p.tables = d->d_tables; p.streams = d->d_streams; p.coef = d->d_coef; p.planes = d->d_planes;
+    p.pixels = pixels; p.status = d->d_status; p.block_start = d->d_block_start; p.pair_start = d->d_pair_start;
+    p.n_images = n;
+    jpegdec_huffman_kernel<<<n, 32, 0, st>>>(p);
+    const uint32_t blocks = d->h_block_start[n], pairs = d->h_pair_start[n];
+    jpegdec_idct_kernel<<<(blocks + 127) / 128, 128, 0, st>>>(p);
+    jpegdec_color_kernel<<<(pairs + 255) / 256, 256, 0, st>>>(p);
+    ROD_CUDA(cudaGetLastError());
+    return ROD_OK;
+}
+
+// per-image result after the work on `stream` is complete: 0 decoded; 1 / 2 corrupt / short stream (pixels undefined);
+// >= 10 not decodable on the device (the verdict of rod_jpegdec_create)
+extern "C" int rod_jpegdec_status(rod_jpeg_decoder* d, int32_t* status, void* stream) {
+    if (d == nullptr || status == nullptr) return ROD_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    ROD_CUDA(cudaMemcpyAsync(status, d->d_status, sizeof(int32_t) * d->n_images, cudaMemcpyDeviceToHost, st));
+    ROD_CUDA(cudaStreamSynchronize(st));
+    return ROD_OK;
+}

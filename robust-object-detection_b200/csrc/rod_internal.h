@@ -165,6 +165,10 @@ inline int cuda_fail(cudaError_t e) {
 
 int grid_for(const rod_plan* plan, int n_tiles, int ctas_per_sm);
 
+// cache of large device blocks keyed by (device, rounded size) (jpeg.cu): cudaMalloc / cudaFree synchronise the device
+cudaError_t block_cache_alloc(int dev, void** p, size_t n);
+void block_cache_free(int dev, void* p, size_t n);
+
 // kernel launchers (one per .cu)
 int launch_noise(const rod_plan* plan, int mode, const uint8_t* src, uint8_t* dst, const float* noise,
                  float* field_out, float sigma, uint64_t seed, uint64_t first_image, uint32_t offset,

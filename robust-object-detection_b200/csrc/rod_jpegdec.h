@@ -1,0 +1,260 @@
+// rod_jpegdec.h -- arithmetic of a baseline JPEG decoder whose pixels equal cv2.imread's, written once for device and host.
+//
+// SURVEY 8f rank 1, the other half: scripts/build_corrupted_testsets.py reads every source frame with cv2.imread (:109 / :149).
+// OpenCV 4.13.0 decodes with libjpeg-turbo 3.1.2 and its defaults: JDCT_ISLOW, fancy (triangle) chroma upsampling, output
+// colour space BGR.  The integer algorithms restated here (published in the IJG / libjpeg-turbo sources, whose SIMD paths are
+// bit-identical to their C paths for in-range data):
+//   jdhuff.c   decode_mcu            canonical Huffman decoding, receive / extend, DC prediction per component
+//   jidctint.c jpeg_idct_islow       13-bit fixed-point 8x8 inverse DCT (dequantisation folded in), range limit to 0..255
+//   jdsample.c h2v2_fancy_upsample   chroma: 3/4 - 1/4 triangle filter in both axes, roundings 8 / 7 alternating by column
+//   jdmainct.c context rows          above the first / below the last REAL chroma row the nearest real row is used
+//   jdcolor.c  ycc_rgb_convert       16-bit fixed-point YCbCr -> RGB (written out as BGR)
+// Supported layout: baseline sequential (SOF0), 8 bit, three components Y Cb Cr sampled 2x2 / 1x1 / 1x1 in one interleaved
+// scan, no restart markers -- what OpenCV itself writes and what the reference's test trees hold.  Anything else is
+// reported as unsupported by the parser and the caller keeps the host codec for that file.
+// The same functions are compiled into tests/emu (CPU check against cv2.imdecode) and into jpegdec.cu.
+#pragma once
+#include <stdint.h>
+
+#include "rod_jpeg.h"   // RJ_HD, natural_order, Geometry
+
+namespace rod {
+namespace jpegdec {
+
+constexpr int kLook = 10;   // bits of the first-level Huffman lookup (jdhuff.h uses 8; a wider table only saves slow-path steps)
+
+// jdhuff.c jpeg_make_d_derived_tbl: one Huffman table in decoding form.
+struct HuffTab {
+    uint16_t look[1 << kLook];   // index = next kLook bits: (code length << 8) | symbol for codes of <= kLook bits, else 0
+    int32_t maxcode[18];         // largest code of length l (-1: none); [17] = sentinel that ends the slow loop
+    int32_t valoffset[17];       // huffval index of a code of length l = code + valoffset[l]
+    uint8_t huffval[256];
+};
+
+// Everything of a file's DQT / DHT / SOF / SOS that the decoder needs; files written by the same encoder share one set.
+struct TableSet {
+    HuffTab dc[2], ac[2];
+    uint16_t quant[3][64];       // per component, natural order
+    uint8_t comp_dc[3], comp_ac[3];
+    uint8_t pad[10];             // sizeof % 16 == 0: the quantisation tables of every set are read as 16-byte words
+};
+static_assert(sizeof(TableSet) % 16 == 0, "TableSet must keep 16-byte alignment in arrays");
+
+// One image of a batch.  Offsets are bytes from the decoder's device buffers; the stream is the entropy-coded segment
+// with the 0xFF00 stuffing removed, starting at a 4-byte aligned offset and followed by >= 16 zero bytes.
+struct ImageRec {
+    int32_t h, w;
+    int32_t table_set;
+    uint32_t stream_bytes;
+    uint64_t stream_off;
+    uint64_t coef_off;           // int16 units: Y blocks [2 mcu_h][2 mcu_w][64], then Cb [mcu_h][mcu_w][64], then Cr
+    uint64_t plane_off;          // bytes: Y plane [16 mcu_h][16 mcu_w], then Cb [8 mcu_h][8 mcu_w], then Cr
+    uint64_t dst_off;            // bytes into the caller's pixel buffer (HWC BGR)
+    int64_t dst_pitch;
+};
+
+// MSB-first reader over the unstuffed stream, 32 bits at a time.
+struct BitReader {
+    const uint32_t* words;
+    uint32_t next;               // index of the next word to load
+    uint32_t limit;              // words that may be read (the stream and its zero padding); beyond, zeros are supplied
+    uint64_t acc;                // valid bits at the top
+    int n;                       // number of valid bits
+    RJ_HD void init(const uint8_t* stream, uint32_t stream_bytes) {
+        words = reinterpret_cast<const uint32_t*>(stream);
+        next = 0; acc = 0; n = 0;
+        limit = (stream_bytes + 3u) / 4u + 2u;
+    }
+    RJ_HD void refill() {        // afterwards n >= 32: enough for the longest code (16) plus the longest value (16)
+        if (n < 32) {
+            uint32_t w = 0u;
+            if (next < limit) {
+#if defined(__CUDA_ARCH__)
+                w = __byte_perm(__ldg(words + next), 0u, 0x0123);
+#else
+                const uint8_t* b = reinterpret_cast<const uint8_t*>(words + next);
+                w = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+#endif
+            }
+            ++next;
+            acc |= (uint64_t)w << (32 - n);
+            n += 32;
+        }
+    }
+    RJ_HD uint32_t peek(int k) const { return (uint32_t)(acc >> (64 - k)); }   // 1 <= k <= 32
+    RJ_HD void skip(int k) { acc <<= k; n -= k; }
+    RJ_HD uint64_t bits_used() const { return 32ull * next - (uint64_t)n; }
+};
+
+// one Huffman symbol; returns -1 on a code that is not in the table
+RJ_HD int decode_symbol(BitReader& br, const HuffTab& t) {
+    const uint32_t e = t.look[br.peek(kLook)];   // (the device keeps the tables in shared memory)
+    if (e != 0u) {
+        br.skip((int)(e >> 8));
+        return (int)(e & 255u);
+    }
+    int l = kLook + 1;
+    int32_t code = (int32_t)br.peek(l);
+    while (code > t.maxcode[l]) {
+        ++l;
+        code = (int32_t)br.peek(l);
+    }
+    if (l > 16) return -1;
+    br.skip(l);
+    return t.huffval[(code + t.valoffset[l]) & 255];
+}
+
+// jdhuff.c HUFF_EXTEND: the s-bit field v as a signed value
+RJ_HD int extend(uint32_t v, int s) { return v < (1u << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v; }
+
+// One block: coefficients (as stored in the file: quantised) into natural order.  blk must be zero-initialised;
+// nat[64]: zigzag position -> natural index (rod::jpeg::natural_order as a table).
+// Returns false on a corrupt stream.
+RJ_HD bool decode_block(BitReader& br, const HuffTab& dc, const HuffTab& ac, const uint8_t* nat, int* last_dc, int16_t* blk) {
+    br.refill();
+    int s = decode_symbol(br, dc);
+    if (s < 0 || s > 16) return false;
+    if (s) {
+        br.refill();
+        const uint32_t v = br.peek(s);
+        br.skip(s);
+        *last_dc += extend(v, s);
+    }
+    blk[0] = (int16_t)*last_dc;
+    for (int k = 1; k < 64; ++k) {
+        br.refill();
+        const int sym = decode_symbol(br, ac);
+        if (sym < 0) return false;
+        const int r = sym >> 4;
+        s = sym & 15;
+        if (s) {
+            k += r;
+            if (k > 63) return false;
+            const uint32_t v = br.peek(s);
+            br.skip(s);
+            blk[nat[k]] = (int16_t)extend(v, s);
+        } else {
+            if (r != 15) break;
+            k += 15;
+        }
+    }
+    return true;
+}
+
+// The whole scan of one image (interleaved 4:2:0 MCUs: Y00 Y01 Y10 Y11 Cb Cr).  coef: this image's zeroed coefficient area.
+// Returns 0, or 1 (corrupt code), 2 (ran past the end of the stream).
+RJ_HD int decode_scan(const ImageRec& im, const TableSet& ts, const uint8_t* nat, const uint8_t* stream, int16_t* coef) {
+    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
+    const long yblocks = 4L * mcu_w * mcu_h, cblocks = (long)mcu_w * mcu_h;
+    int16_t* yc = coef;
+    int16_t* cbc = coef + 64 * yblocks;
+    int16_t* crc = cbc + 64 * cblocks;
+    BitReader br;
+    br.init(stream, im.stream_bytes);
+    int last_dc[3] = {0, 0, 0};
+    const HuffTab& ydc = ts.dc[ts.comp_dc[0]];
+    const HuffTab& yac = ts.ac[ts.comp_ac[0]];
+    const HuffTab& bdc = ts.dc[ts.comp_dc[1]];
+    const HuffTab& bac = ts.ac[ts.comp_ac[1]];
+    const HuffTab& rdc = ts.dc[ts.comp_dc[2]];
+    const HuffTab& rac = ts.ac[ts.comp_ac[2]];
+    for (int my = 0; my < mcu_h; ++my)
+        for (int mx = 0; mx < mcu_w; ++mx) {
+            for (int b = 0; b < 4; ++b) {
+                int16_t* blk = yc + 64 * ((long)(2 * my + (b >> 1)) * (2 * mcu_w) + 2 * mx + (b & 1));
+                if (!decode_block(br, ydc, yac, nat, &last_dc[0], blk)) return 1;
+            }
+            if (!decode_block(br, bdc, bac, nat, &last_dc[1], cbc + 64 * ((long)my * mcu_w + mx))) return 1;
+            if (!decode_block(br, rdc, rac, nat, &last_dc[2], crc + 64 * ((long)my * mcu_w + mx))) return 1;
+        }
+    return br.bits_used() > 8ull * im.stream_bytes ? 2 : 0;
+}
+
+// jidctint.c jpeg_idct_islow: 64 quantised coefficients (natural order) x quantisation table -> 64 samples 0..255.
+RJ_HD int idct_descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+RJ_HD uint8_t idct_limit(int v) {   // range_limit[(v) & RANGE_MASK] for in-range data: clamp(v + 128, 0, 255)
+    v += 128;
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+RJ_HD void idct_1d(int d0, int d1, int d2, int d3, int d4, int d5, int d6, int d7, int even_shift, int* o) {
+    // even part (d0, d4 enter shifted by CONST_BITS = 13)
+    int z1 = (d2 + d6) * 4433;
+    const int tmp2 = z1 + d6 * (-15137), tmp3 = z1 + d2 * 6270;
+    const int tmp0 = (d0 + d4) * 8192, tmp1 = (d0 - d4) * 8192;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    // odd part
+    int t0 = d7, t1 = d5, t2 = d3, t3 = d1;
+    z1 = t0 + t3;
+    int z2 = t1 + t2, z3 = t0 + t2, z4 = t1 + t3;
+    const int z5 = (z3 + z4) * 9633;
+    t0 *= 2446; t1 *= 16819; t2 *= 25172; t3 *= 12299;
+    z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+    z3 += z5; z4 += z5;
+    t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;
+    o[0] = idct_descale(tmp10 + t3, even_shift); o[7] = idct_descale(tmp10 - t3, even_shift);
+    o[1] = idct_descale(tmp11 + t2, even_shift); o[6] = idct_descale(tmp11 - t2, even_shift);
+    o[2] = idct_descale(tmp12 + t1, even_shift); o[5] = idct_descale(tmp12 - t1, even_shift);
+    o[3] = idct_descale(tmp13 + t0, even_shift); o[4] = idct_descale(tmp13 - t0, even_shift);
+}
+RJ_HD void idct_islow(const int16_t* coef, const uint16_t* quant, uint8_t* out, long out_pitch) {
+    int ws[64];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) {   // pass 1: columns; results scaled up by 2^PASS1_BITS
+        int d[8], o[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < 8; ++r) d[r] = (int)coef[8 * r + c] * (int)quant[8 * r + c];
+        idct_1d(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], 13 - 2, o);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < 8; ++r) ws[8 * r + c] = o[r];
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 8; ++r) {   // pass 2: rows; descale by 2^(CONST_BITS + PASS1_BITS + 3)
+        int o[8];
+        idct_1d(ws[8 * r], ws[8 * r + 1], ws[8 * r + 2], ws[8 * r + 3], ws[8 * r + 4], ws[8 * r + 5], ws[8 * r + 6],
+                ws[8 * r + 7], 13 + 2 + 3, o);
+        uint8_t* p = out + r * out_pitch;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int c = 0; c < 8; ++c) p[c] = idct_limit(o[c]);
+    }
+}
+
+// jdsample.c h2v2_fancy_upsample + jdmainct.c: the chroma sample of output pixel (x, y).  plane: the decoded half-resolution
+// plane (pitch bytes per row); cw x ch = its REAL size, ceil(w / 2) x ceil(h / 2).  cw >= 3 (the parser rejects w < 5).
+RJ_HD int upsample_h2v2(const uint8_t* plane, long pitch, int cw, int ch, int x, int y) {
+    const int cy = y >> 1, cx = x >> 1;
+    int ny = (y & 1) ? cy + 1 : cy - 1;          // the further row: below for odd output rows, above for even ones
+    ny = ny < 0 ? 0 : (ny > ch - 1 ? ch - 1 : ny);
+    const uint8_t* r0 = plane + (long)cy * pitch;
+    const uint8_t* r1 = plane + (long)ny * pitch;
+    const int cur = 3 * r0[cx] + r1[cx];
+    if (x & 1) {
+        if (cx == cw - 1) return (4 * cur + 7) >> 4;
+        return (3 * cur + 3 * r0[cx + 1] + r1[cx + 1] + 7) >> 4;
+    }
+    if (cx == 0) return (4 * cur + 8) >> 4;
+    return (3 * cur + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
+}
+
+// jdcolor.c ycc_rgb_convert (SCALEBITS 16), written as B, G, R
+RJ_HD void ycc_to_bgr(int y, int cb, int cr, uint8_t* bgr) {
+    cb -= 128; cr -= 128;
+    const int r = y + ((91881 * cr + 32768) >> 16);
+    const int g = y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+    const int b = y + ((116130 * cb + 32768) >> 16);
+    bgr[0] = (uint8_t)(b < 0 ? 0 : (b > 255 ? 255 : b));
+    bgr[1] = (uint8_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
+    bgr[2] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}
+
+}  // namespace jpegdec
+}  // namespace rod

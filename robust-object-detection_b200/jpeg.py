@@ -1,4 +1,5 @@
-"""Device-side JPEG encoding whose files equal cv2.imwrite's byte for byte.
+"""Device-side JPEG encoding whose files equal cv2.imwrite's byte for byte, and device-side JPEG decoding whose pixels
+equal cv2.imread's.
 
 `cv2.imwrite(str(dst_img_dir / img_path.name), out)` (scripts/build_corrupted_testsets.py:124, :164) is the last step of
 the test-set build; with the corruption on the GPU it is what the build spends its time in.  JpegEncoder encodes a
@@ -116,3 +117,65 @@ class JpegEncoder:
             else:
                 out.append((header_for(h, w), host[self._off[i]:self._off[i] + n]))
         return out
+
+
+def probe(data) -> Optional[Tuple[int, int]]:
+    """(height, width) when the device decoder takes this JPEG file (bytes-like), else None (host codec)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    h, w = ctypes.c_int(), ctypes.c_int()
+    rc = N.lib().rod_jpegdec_probe(buf.ctypes.data, buf.size, ctypes.byref(h), ctypes.byref(w))
+    return (h.value, w.value) if rc == N.ROD_OK else None
+
+
+class JpegDecoder:
+    """Decoder for one batch of JPEG files: `cv2.imread` (scripts/build_corrupted_testsets.py:109, :149) for a device-resident
+    batch.  files: bytes-like objects (whole files); image i is written as HWC BGR uint8 at byte offsets[i] of the tensor
+    given to decode(), row pitch 3 * width unless `pitches` says otherwise -- the layout of a CorruptionPlan built from
+    `shapes`.  The constructor does the host work (markers, Huffman tables, scans copied without their byte stuffing into
+    page-locked memory, on `host_threads` threads); `shapes[i]` is (h, w), or None where the device decoder does not take
+    the file (progressive, other chroma sampling, restart markers, EXIF rotation, not a JPEG ...): the caller reads those
+    with the host codec.  No CPU decoding inside."""
+
+    def __init__(self, files: Sequence, offsets: Sequence[int], pitches: Optional[Sequence[int]] = None, host_threads: int = 8):
+        N.require_device()
+        n = len(files)
+        self._bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]   # keeps the file bytes alive for create()
+        ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in self._bufs])
+        lens = (ctypes.c_uint64 * n)(*[b.size for b in self._bufs])
+        offs = (ctypes.c_uint64 * n)(*[int(o) for o in offsets])
+        pit = (ctypes.c_int64 * n)(*[int(q) for q in pitches]) if pitches is not None else None
+        handle = ctypes.c_void_p()
+        N.check(N.lib().rod_jpegdec_create(ptrs, lens, n, offs, pit, int(host_threads), ctypes.byref(handle)), "rod_jpegdec_create")
+        self._h = handle
+        self._bufs = None   # the scans were copied
+        self.n_images = n
+        st = np.zeros(n, np.int32)
+        hh, ww = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        N.check(N.lib().rod_jpegdec_host_status(handle, st.ctypes.data, hh.ctypes.data, ww.ctypes.data), "rod_jpegdec_host_status")
+        self.host_status = st
+        self.shapes: List[Optional[Tuple[int, int]]] = [(int(h), int(w)) if s == 0 else None for s, h, w in zip(st, hh, ww)]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                N.lib().rod_jpegdec_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def decode(self, pixels, stream=None) -> None:
+        """Asynchronous on `stream` (default: torch's current stream): pixels (CUDA uint8 tensor) receives the images."""
+        N.check(N.lib().rod_jpegdec_decode(self._h, _ptr(pixels), _stream_handle(stream)), "rod_jpegdec_decode")
+
+    def status(self, stream=None) -> np.ndarray:
+        """Waits for the stream.  Per image 0: decoded; 1 / 2: corrupt / truncated entropy-coded data (pixels undefined:
+        read the file with the host codec); >= 10: the constructor's verdict (not decodable on the device)."""
+        st = np.zeros(self.n_images, np.int32)
+        N.check(N.lib().rod_jpegdec_status(self._h, st.ctypes.data, _stream_handle(stream)), "rod_jpegdec_status")
+        return st
+
+
+def sizes_of(files: Sequence) -> List[Optional[Tuple[int, int]]]:
+    """probe() for a list of files."""
+    return [probe(f) for f in files]

@@ -1097,3 +1097,52 @@ extern "C" long emu_jpeg_encode(const uint8_t* bgr, int h, int w, long pitch, co
     out[o++] = 0xFF; out[o++] = 0xD9;
     return o;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// JPEG decoding: sequential replay of the device decoder (csrc/jpegdec.cu) from the same rod_jpegdec.h arithmetic, in the
+// same passes: (1) markers, tables, unstuffed scan (host side of the product too), (2) Huffman decoding into coefficient
+// blocks, (3) dequantisation + islow IDCT into the Y / Cb / Cr planes, (4) fancy chroma upsampling + colour conversion.
+// Returns 0 and fills out (HWC BGR, pitch 3 * w, capacity out_cap bytes) and hw[2]; 1 / 2: ParseStatus; 3: the scan does
+// not end in EOI; 4 / 5: corrupt / short stream; 6: out too small.
+#include "../../robust-object-detection_b200/csrc/rod_jpegdec_host.h"
+
+extern "C" int emu_jpeg_decode(const uint8_t* file, long n, uint8_t* out, long out_cap, int* hw) {
+    using namespace rod::jpegdec;
+    FileInfo info;
+    std::vector<TableSet> tsv(1);
+    TableSet& ts = tsv[0];
+    const ParseStatus st = parse_file(file, (size_t)n, &info, &ts);
+    if (st != PARSE_OK) return (int)st;
+    hw[0] = info.height; hw[1] = info.width;
+    std::vector<uint8_t> stream((size_t)n - info.scan_begin + 64);
+    const size_t sb = unstuff_scan(file, (size_t)n, info.scan_begin, stream.data());
+    if (sb == (size_t)-1) return 3;
+    ImageRec im;
+    memset(&im, 0, sizeof(im));
+    im.h = info.height; im.w = info.width; im.stream_bytes = (uint32_t)sb;
+    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
+    std::vector<int16_t> coef((size_t)mcu_w * mcu_h * 6 * 64, 0);
+    uint8_t nat[64];
+    for (int z = 0; z < 64; ++z) nat[z] = (uint8_t)rod::jpeg::natural_order(z);
+    const int rc = decode_scan(im, ts, nat, stream.data(), coef.data());
+    if (rc) return 3 + rc;
+    const long ypitch = 16L * mcu_w, cpitch = 8L * mcu_w;
+    std::vector<uint8_t> yp((size_t)ypitch * 16 * mcu_h), cbp((size_t)cpitch * 8 * mcu_h), crp((size_t)cpitch * 8 * mcu_h);
+    for (int by = 0; by < 2 * mcu_h; ++by)
+        for (int bx = 0; bx < 2 * mcu_w; ++bx)
+            idct_islow(coef.data() + 64 * ((size_t)by * 2 * mcu_w + bx), ts.quant[0], yp.data() + 8L * by * ypitch + 8 * bx, ypitch);
+    const int16_t* cbc = coef.data() + 64 * (size_t)4 * mcu_w * mcu_h;
+    const int16_t* crc = cbc + 64 * (size_t)mcu_w * mcu_h;
+    for (int by = 0; by < mcu_h; ++by)
+        for (int bx = 0; bx < mcu_w; ++bx) {
+            idct_islow(cbc + 64 * ((size_t)by * mcu_w + bx), ts.quant[1], cbp.data() + 8L * by * cpitch + 8 * bx, cpitch);
+            idct_islow(crc + 64 * ((size_t)by * mcu_w + bx), ts.quant[2], crp.data() + 8L * by * cpitch + 8 * bx, cpitch);
+        }
+    if ((long)im.h * im.w * 3 > out_cap) return 6;
+    const int cw = (im.w + 1) >> 1, ch = (im.h + 1) >> 1;
+    for (int y = 0; y < im.h; ++y)
+        for (int x = 0; x < im.w; ++x)
+            ycc_to_bgr(yp[(size_t)y * ypitch + x], upsample_h2v2(cbp.data(), cpitch, cw, ch, x, y),
+                       upsample_h2v2(crp.data(), cpitch, cw, ch, x, y), out + ((size_t)y * im.w + x) * 3);
+    return 0;
+}

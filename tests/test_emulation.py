@@ -480,3 +480,55 @@ def test_emu_jpeg_encoder_matches_golden(emu):
         n = emu.emu_jpeg_encode(_p(np.ascontiguousarray(img)), h, w, 3 * w, _p(hdr), len(hdr), _p(out), len(out))
         assert n > 0
         assert hashlib.sha256(out[:n].tobytes()).hexdigest() == g["sha"][f"{seed}_{h}x{w}_{kind}"], (seed, h, w, kind)
+
+
+def _emu_decode(emu, data):
+    emu.emu_jpeg_decode.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.c_long,
+                                    ctypes.POINTER(ctypes.c_int)]
+    b = np.frombuffer(data, np.uint8).copy()
+    out = np.zeros(2100 * 2100 * 3, np.uint8)
+    hw = (ctypes.c_int * 2)()
+    rc = emu.emu_jpeg_decode(_p(b), len(b), _p(out), len(out), hw)
+    return rc, (out[:hw[0] * hw[1] * 3].reshape(hw[0], hw[1], 3).copy() if rc == 0 else None)
+
+
+def test_emu_jpeg_decoder_matches_cv2(emu):
+    """The decoder arithmetic of csrc/rod_jpegdec.h (Huffman decoding, dequantisation + islow IDCT, fancy h2v2 chroma
+    upsampling with libjpeg's edge rows / columns, YCbCr -> BGR) and the host side of csrc/rod_jpegdec_host.h (markers,
+    derived tables, unstuffing) replayed on the CPU: the pixels must equal cv2.imdecode's -- every small size from 5 pixels
+    of width on (MCU-partial right / bottom edges, one-row images), several qualities incl. 100, optimised Huffman tables,
+    noise / smooth / flat content, VisDrone frame sizes."""
+    import cv2
+    rng = np.random.default_rng(11)
+    cases = [(h, w) for h in (1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 33) for w in (5, 6, 7, 8, 9, 15, 16, 17, 18, 31, 32, 33, 47, 65)]
+    cases += [(765, 1360), (540, 960), (1078, 1916), (97, 133), (300, 180)]
+    for i, (h, w) in enumerate(cases):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        kind = i % 4
+        if kind == 1:
+            img = cv2.GaussianBlur(img, (0, 0), 2.0)
+        elif kind == 2:
+            img[:] = rng.integers(0, 256, 3, dtype=np.uint8)
+        params = [[], [cv2.IMWRITE_JPEG_QUALITY, 100], [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(5, 95))], [cv2.IMWRITE_JPEG_OPTIMIZE, 1]][(i // 4) % 4]
+        ok, enc = cv2.imencode(".jpg", img, params)
+        assert ok
+        rc, got = _emu_decode(emu, enc.tobytes())
+        assert rc == 0, (h, w, params, rc)
+        assert np.array_equal(got, cv2.imdecode(enc, cv2.IMREAD_COLOR)), (h, w, kind, params)
+
+
+def test_emu_jpeg_decoder_reports_other_layouts(emu):
+    """Files the device decoder does not take are reported, not approximated: other chroma sampling, progressive, restart
+    markers, greyscale, tiny widths (libjpeg-turbo's upsampler reads its padding there), truncated files, other formats."""
+    import cv2
+    img = synth(8300, 64, 64)
+    for params in ([cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444], [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422],
+                   [cv2.IMWRITE_JPEG_PROGRESSIVE, 1], [cv2.IMWRITE_JPEG_RST_INTERVAL, 4]):
+        assert _emu_decode(emu, cv2.imencode(".jpg", img, params)[1].tobytes())[0] == 2, params
+    assert _emu_decode(emu, cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))[1].tobytes())[0] == 2
+    assert _emu_decode(emu, cv2.imencode(".jpg", img[:, :4])[1].tobytes())[0] == 2
+    whole = cv2.imencode(".jpg", img)[1].tobytes()
+    assert _emu_decode(emu, whole[:len(whole) // 2])[0] == 3        # no EOI behind the scan
+    assert _emu_decode(emu, whole[:100])[0] == 1                      # header cut short
+    assert _emu_decode(emu, cv2.imencode(".png", img)[1].tobytes())[0] == 1
+    assert _emu_decode(emu, b"not a jpeg")[0] == 1

@@ -1329,3 +1329,58 @@ def test_jpeg_encoder_random_shapes_stress(torch_):
     for i, (img, got) in enumerate(zip(imgs, files)):
         want = cv2.imencode(".jpg", img)[1].tobytes()
         assert got is not None and got == want, (i, shapes[i], None if got is None else len(got), len(want))
+
+
+def test_jpeg_decoder_matches_cv2(torch_):
+    """Device JPEG decoder (row f1, the reading side: scripts/build_corrupted_testsets.py:109) on one ragged batch: files
+    of many sizes, qualities and contents decode to the pixels of cv2.imdecode, straight into the layout of a CorruptionPlan;
+    files of other layouts are reported per image and leave their slot untouched."""
+    import cv2
+    from robust_object_detection_b200.batch import CorruptionPlan
+    from robust_object_detection_b200.jpeg import JpegDecoder, probe
+    rng = np.random.default_rng(99)
+    shapes = [(int(rng.integers(1, 261)), int(rng.integers(5, 261))) for _ in range(40)] + [(765, 1360), (1079, 1917), (1500, 2000), (15, 2001), (2001, 17)]
+    files, want = [], []
+    for i, (h, w) in enumerate(shapes):
+        base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        kind = i % 3
+        img = base if kind == 0 else cv2.GaussianBlur(base, (0, 0), 1.5 + (i % 5)) if kind == 1 else (base // 64) * 85
+        params = [[], [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(10, 101))], [cv2.IMWRITE_JPEG_OPTIMIZE, 1]][(i // 3) % 3]
+        enc = cv2.imencode(".jpg", img, params)[1]
+        files.append(enc.tobytes())
+        want.append(cv2.imdecode(enc, cv2.IMREAD_COLOR))
+    odd = {3: cv2.imencode(".jpg", want[3], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes(), 7: b"not a jpeg",
+           11: cv2.imencode(".png", want[11])[1].tobytes(), 40: files[40][:len(files[40]) // 2]}
+    for i, f in odd.items():
+        files[i] = f
+    sizes = [probe(f) for f in files]
+    # probe() reads the header only: the file cut off inside its scan (40) is found out by the decoder's constructor
+    assert all((sizes[i] is None) == (i in odd and i != 40) for i in range(len(files)))
+    assert all(sizes[i] == shapes[i] for i in range(len(files)) if i not in odd)
+    plan = CorruptionPlan.ragged(shapes)
+    dec = JpegDecoder(files, plan.src_offsets, host_threads=4)
+    assert dec.shapes == [None if i == 40 else sz for i, sz in enumerate(sizes)]
+    pix = torch_.full((plan.src_bytes + 64,), 0xA5, dtype=torch_.uint8, device="cuda")
+    dec.decode(pix)
+    st = dec.status()
+    assert [int(s) for s in st] == [0 if i not in odd else (12 if i == 3 else 13 if i == 40 else 11) for i in range(len(files))]
+    got = pix.cpu().numpy()
+    assert (got[plan.src_bytes:] == 0xA5).all()
+    for i, ((h, w), off) in enumerate(zip(shapes, plan.src_offsets)):
+        g = got[off:off + 3 * h * w].reshape(h, w, 3)
+        if i in odd:
+            assert (g == 0xA5).all(), i
+        else:
+            assert np.array_equal(g, want[i]), (i, shapes[i])
+    # a stream that breaks off inside the entropy-coded data but still ends in EOI: reported by the device, not decoded
+    bad = bytearray(files[0])
+    scan = bytes(bad).index(b"\xff\xda")
+    cut = bytes(bad[:scan + 14 + (len(bad) - scan) // 3]) + b"\xff\xd9"
+    dec2 = JpegDecoder([cut, files[1]], [0, 3 * shapes[0][0] * shapes[0][1]])
+    if dec2.shapes[0] is not None:
+        pix2 = torch_.zeros(3 * (shapes[0][0] * shapes[0][1] + shapes[1][0] * shapes[1][1]), dtype=torch_.uint8, device="cuda")
+        dec2.decode(pix2)
+        st2 = dec2.status()
+        assert int(st2[0]) in (1, 2) and int(st2[1]) == 0
+        off = 3 * shapes[0][0] * shapes[0][1]
+        assert np.array_equal(pix2.cpu().numpy()[off:].reshape(shapes[1][0], shapes[1][1], 3), want[1])
