@@ -213,7 +213,8 @@ typedef struct rod_jpeg_decoder rod_jpeg_decoder;
 ROD_API int rod_jpegdec_probe(const uint8_t* file, uint64_t n, int* height, int* width);
 ROD_API int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* lens, int n_images, const uint64_t* dst_offsets,
                        const int64_t* dst_pitches, int host_threads, rod_jpeg_decoder** out_dec);
-ROD_API void rod_jpegdec_destroy(rod_jpeg_decoder* dec);
+ROD_API void rod_jpegdec_destroy(rod_jpeg_decoder* dec);   /* its device / page-locked buffers go to caches for the next decoder */
+ROD_API void rod_jpegdec_trim(void);                          /* frees the page-locked cache (the device cache: rod_jpeg_trim) */
 ROD_API int rod_jpegdec_host_status(const rod_jpeg_decoder* dec, int32_t* status, int32_t* heights, int32_t* widths);
 ROD_API int rod_jpegdec_decode(rod_jpeg_decoder* dec, uint8_t* pixels, void* stream);
 ROD_API int rod_jpegdec_status(rod_jpeg_decoder* dec, int32_t* status, void* stream);

@@ -60,6 +60,7 @@ SYMBOLS = {
     "rod_jpegdec_probe": (_i, [_vp, _u64, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "rod_jpegdec_create": (_i, [_vp, _vp, _i, _vp, _vp, _i, ctypes.POINTER(_vp)]),
     "rod_jpegdec_destroy": (None, [_vp]),
+    "rod_jpegdec_trim": (None, []),
     "rod_jpegdec_host_status": (_i, [_vp, _vp, _vp, _vp]),
     "rod_jpegdec_decode": (_i, [_vp, _vp, _vp]),
     "rod_jpegdec_status": (_i, [_vp, _vp, _vp]),

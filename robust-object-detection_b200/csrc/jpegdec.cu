@@ -6,9 +6,16 @@
 // is the batch machinery:
 //   host    rod_jpegdec_create: per file (on `host_threads` threads) walk the markers, build the decoding tables, copy the
 //           entropy-coded segment without its 0xFF00 stuffing into one page-locked buffer; equal table sets are shared
-//   device  jpegdec_huffman_kernel   one warp per image, lane 0 decodes the scan (a JPEG scan without restart markers is
-//                                    one serial bit stream; images are what runs in parallel) with the image's table set
-//                                    in shared memory; coefficients int16, natural order, per-component block rasters
+//   device  Huffman decoding of a scan -- one serial bit stream when there are no restart markers -- in parallel by
+//           self-synchronisation (rod_jpegdec.h decode_span): a thread per 1024-bit subsequence, the image's table set in
+//           shared memory
+//             jpegdec_guess_kernel   end state of every subsequence from a guessed start state
+//             jpegdec_sync_kernel    re-decodes the subsequences whose predecessor's end state changed (each thread up to
+//                                    eight times per launch); launched until one launch changes nothing
+//             jpegdec_scan_kernel    first block of every subsequence (prefix sum of the block counts, a CTA per image)
+//             jpegdec_write_kernel   decodes from the now exact start states and stores the coefficients (int16, natural
+//                                    order, per-component block rasters; DC as the difference)
+//             jpegdec_dc_kernel      DC prediction = prefix sum of the differences per component in MCU order
 //           jpegdec_idct_kernel      one thread per 8x8 block: dequantisation + islow IDCT in registers -> Y / Cb / Cr planes
 //           jpegdec_color_kernel     one thread per two output pixels: fancy h2v2 chroma upsampling + YCbCr -> BGR, written
 //                                    straight into the caller's HWC batch (the layout of a rod_plan)
@@ -35,23 +42,161 @@ struct JpegDecParams {
     int32_t* status;
     const uint32_t* block_start;   // [n + 1] prefix sums of 6 * MCUs
     const uint32_t* pair_start;    // [n + 1] prefix sums of h * ceil(w / 2)
+    const uint32_t* sub_start;     // [n + 1] prefix sums of the number of subsequences
+    const uint2* ctas;             // Huffman kernels: CTA -> (image, first subsequence of the image it covers)
+    uint64_t* end_state;           // E[subsequence]
+    uint64_t* used_start;          // U[subsequence]: the start state E was computed from
+    uint32_t* first_block;         // [subsequence] global block index its first symbol belongs to
+    unsigned int* changed;         // one flag per sync launch
     int n_images;
 };
 
-__global__ void __launch_bounds__(32) jpegdec_huffman_kernel(JpegDecParams p) {
+constexpr int kHuffThreads = 128;
+
+__device__ __forceinline__ void load_tables(TableSet* ts, uint8_t* nat, const TableSet* src_set) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(src_set);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(ts);
+    for (int i = threadIdx.x; i < (int)(sizeof(TableSet) / 4); i += kHuffThreads) dst[i] = __ldg(src + i);
+    if (threadIdx.x < 64) nat[threadIdx.x] = (uint8_t)rod::jpeg::natural_order(threadIdx.x);
+    __syncthreads();
+}
+__device__ __forceinline__ uint64_t ld_volatile64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile64(uint64_t* p, uint64_t v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kHuffThreads) jpegdec_guess_kernel(JpegDecParams p) {
     __shared__ TableSet ts;
     __shared__ uint8_t nat[64];
-    const ImageRec im = p.images[blockIdx.x];
-    if (im.h == 0) return;   // not decodable here: status set by the host
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.tables + im.table_set);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&ts);
-        for (int i = threadIdx.x; i < (int)(sizeof(TableSet) / 4); i += 32) dst[i] = __ldg(src + i);
+    const uint2 c = p.ctas[blockIdx.x];
+    const ImageRec im = p.images[c.x];
+    load_tables(&ts, nat, p.tables + im.table_set);
+    const uint32_t s = c.y + threadIdx.x, n_sub = p.sub_start[c.x + 1] - p.sub_start[c.x];
+    if (s >= n_sub) return;
+    const uint32_t gs = p.sub_start[c.x] + s;
+    const uint64_t u = span_state(s * kSubBits, 0, 0, 0);
+    p.used_start[gs] = u;
+    p.end_state[gs] = decode_span<false>(im, ts, nat, p.streams + im.stream_off, u, (s + 1) * kSubBits, nullptr, 0, 0, nullptr);
+}
+
+__global__ void __launch_bounds__(kHuffThreads) jpegdec_sync_kernel(JpegDecParams p, int flag_slot) {
+    __shared__ TableSet ts;
+    __shared__ uint8_t nat[64];
+    const uint2 c = p.ctas[blockIdx.x];
+    const uint32_t s = c.y + threadIdx.x, n_sub = p.sub_start[c.x + 1] - p.sub_start[c.x];
+    const bool mine = s >= 1 && s < n_sub;
+    const uint32_t gs = p.sub_start[c.x] + s;
+    uint64_t u = 0, st = 0;
+    if (mine) {
+        u = p.used_start[gs];
+        st = state_start(ld_volatile64(p.end_state + gs - 1));
     }
-    nat[threadIdx.x] = (uint8_t)rod::jpeg::natural_order(threadIdx.x);
-    nat[threadIdx.x + 32] = (uint8_t)rod::jpeg::natural_order(threadIdx.x + 32);
-    __syncwarp();
-    if (threadIdx.x == 0) p.status[blockIdx.x] = decode_scan(im, ts, nat, p.streams + im.stream_off, p.coef + im.coef_off);
+    if (!__syncthreads_or(mine && st != u)) return;   // nothing to do for this CTA: the tables are not even loaded
+    const ImageRec im = p.images[c.x];
+    load_tables(&ts, nat, p.tables + im.table_set);
+    if (!mine) return;
+    bool changed = false;
+    for (int it = 0; it < 8 && st != u; ++it) {
+        u = st;
+        st_volatile64(p.end_state + gs, decode_span<false>(im, ts, nat, p.streams + im.stream_off, u, (s + 1) * kSubBits, nullptr, 0, 0, nullptr));
+        changed = true;
+        st = state_start(ld_volatile64(p.end_state + gs - 1));   // the predecessor may have moved on meanwhile
+    }
+    if (changed) {
+        p.used_start[gs] = u;
+        p.changed[flag_slot] = 1u;
+    }
+}
+
+// exclusive prefix sum of the block counts of an image's subsequences; too few blocks in total: truncated data
+__global__ void __launch_bounds__(256) jpegdec_scan_kernel(JpegDecParams p) {
+    __shared__ uint32_t warp_sum[8];
+    __shared__ uint32_t carry_s;
+    const int img = blockIdx.x;
+    const ImageRec im = p.images[img];
+    if (im.h == 0) return;
+    const uint32_t s0 = p.sub_start[img], n_sub = p.sub_start[img + 1] - s0;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_sub; base += 256) {
+        const uint32_t s = base + threadIdx.x;
+        const uint32_t v = s < n_sub ? state_nblk(p.end_state[s0 + s]) : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if ((threadIdx.x & 31) >= d) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        uint32_t before = carry_s;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += warp_sum[w];
+        if (s < n_sub) p.first_block[s0 + s] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t total = 6u * (uint32_t)((im.w + 15) >> 4) * (uint32_t)((im.h + 15) >> 4);
+        if (carry_s < total) p.status[img] = 2;
+    }
+}
+
+__global__ void __launch_bounds__(kHuffThreads) jpegdec_write_kernel(JpegDecParams p) {
+    __shared__ TableSet ts;
+    __shared__ uint8_t nat[64];
+    const uint2 c = p.ctas[blockIdx.x];
+    const ImageRec im = p.images[c.x];
+    load_tables(&ts, nat, p.tables + im.table_set);
+    const uint32_t s = c.y + threadIdx.x, n_sub = p.sub_start[c.x + 1] - p.sub_start[c.x];
+    if (s >= n_sub) return;
+    const uint32_t gs = p.sub_start[c.x] + s;
+    const uint32_t total = 6u * (uint32_t)((im.w + 15) >> 4) * (uint32_t)((im.h + 15) >> 4);
+    const uint32_t g0 = p.first_block[gs];
+    if (g0 >= total) return;   // behind the last block: padding
+    int err = 0;
+    decode_span<true>(im, ts, nat, p.streams + im.stream_off, s == 0 ? span_state(0, 0, 0, 0) : state_start(p.end_state[gs - 1]),
+                      (s + 1) * kSubBits, p.coef + im.coef_off, g0, total, &err);
+    if (err) atomicMax(p.status + c.x, 1);
+}
+
+// DC prediction (jdhuff.c: last_dc_val[ci] += diff): inclusive prefix sum of the stored differences of one component, in
+// the order the blocks were coded.  grid (n_images, 3), 256 threads.
+__global__ void __launch_bounds__(256) jpegdec_dc_kernel(JpegDecParams p) {
+    __shared__ int warp_sum[8];
+    __shared__ int carry_s;
+    const int img = blockIdx.x, comp = blockIdx.y;
+    const ImageRec im = p.images[img];
+    if (im.h == 0 || p.status[img] != 0) return;
+    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
+    const uint32_t n = (comp == 0 ? 4u : 1u) * (uint32_t)mcu_w * (uint32_t)mcu_h;
+    int16_t* coef = p.coef + im.coef_off;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 256) {
+        const uint32_t j = base + threadIdx.x;
+        int16_t* blk = nullptr;
+        if (j < n) blk = block_of(coef, mcu_w, mcu_h, comp == 0 ? 6u * (j >> 2) + (j & 3u) : 6u * j + 3u + (uint32_t)comp);
+        const int v = blk ? (int)blk[0] : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if ((threadIdx.x & 31) >= d) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        int before = carry_s;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += warp_sum[w];
+        if (blk) blk[0] = (int16_t)(before + x);
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = before + x;
+        __syncthreads();
+    }
 }
 
 // image that owns flat index i of a prefix-sum array
@@ -139,19 +284,60 @@ __global__ void __launch_bounds__(256) jpegdec_color_kernel(JpegDecParams p) {
 
 using namespace rod;
 
+// Page-locked staging blocks are recycled like the device blocks (pinning costs ~0.3 ms per MB, more than the decoding).
+#include <mutex>
+namespace {
+std::mutex g_host_mutex;
+std::multimap<size_t, void*> g_host_cache;   // rounded size -> free page-locked block
+size_t round_host(size_t n) {
+    size_t r = 1 << 20;
+    while (r < n) r <<= 1;
+    return r;
+}
+cudaError_t host_cache_alloc(void** p, size_t n) {
+    const size_t r = round_host(n);
+    {
+        std::lock_guard<std::mutex> lock(g_host_mutex);
+        auto it = g_host_cache.find(r);
+        if (it != g_host_cache.end()) { *p = it->second; g_host_cache.erase(it); return cudaSuccess; }
+    }
+    return cudaHostAlloc(p, r, cudaHostAllocDefault);
+}
+void host_cache_free(void* p, size_t n) {
+    if (p == nullptr) return;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    g_host_cache.insert({round_host(n), p});
+}
+}  // namespace
+
+extern "C" void rod_jpegdec_trim(void) {
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    for (auto& kv : g_host_cache) cudaFreeHost(kv.second);
+    g_host_cache.clear();
+}
+
 struct rod_jpeg_decoder {
     int device = 0;
     int n_images = 0;
     std::vector<ImageRec> h_images;
     std::vector<int32_t> h_status;       // host verdict per image: 0 decodable, else 10 + ParseStatus / 13 (no EOI)
     std::vector<TableSet> h_tables;
-    std::vector<uint32_t> h_block_start, h_pair_start;
+    std::vector<uint32_t> h_block_start, h_pair_start, h_sub_start;
+    std::vector<uint2> h_ctas;
     uint8_t* h_streams = nullptr;        // page-locked
     size_t stream_bytes = 0, coef_elems = 0, plane_bytes = 0;
     ImageRec* d_images = nullptr;
     TableSet* d_tables = nullptr;
     uint32_t* d_block_start = nullptr;
     uint32_t* d_pair_start = nullptr;
+    uint32_t* d_sub_start = nullptr;
+    uint2* d_ctas = nullptr;
+    unsigned int* d_changed = nullptr;
+    uint64_t* d_end_state = nullptr;
+    uint64_t* d_used_start = nullptr;
+    uint32_t* d_first_block = nullptr;
+    size_t n_sub = 0;
+    int sync_rounds = 0;                 // launches of the last decode (diagnostics)
     int32_t* d_status = nullptr;
     uint8_t* d_streams = nullptr;
     int16_t* d_coef = nullptr;
@@ -171,13 +357,16 @@ extern "C" int rod_jpegdec_probe(const uint8_t* file, uint64_t n, int* height, i
 
 extern "C" void rod_jpegdec_destroy(rod_jpeg_decoder* d) {
     if (d == nullptr) return;
-    void* small[] = {d->d_images, d->d_tables, d->d_block_start, d->d_pair_start, d->d_status};
+    void* small[] = {d->d_images, d->d_tables, d->d_block_start, d->d_pair_start, d->d_status, d->d_sub_start, d->d_ctas, d->d_changed};
     for (void* q : small)
         if (q) cudaFree(q);
     block_cache_free(d->device, d->d_streams, d->stream_bytes);
     block_cache_free(d->device, d->d_coef, d->coef_elems * sizeof(int16_t));
     block_cache_free(d->device, d->d_planes, d->plane_bytes);
-    if (d->h_streams) cudaFreeHost(d->h_streams);
+    block_cache_free(d->device, d->d_end_state, d->n_sub * sizeof(uint64_t));
+    block_cache_free(d->device, d->d_used_start, d->n_sub * sizeof(uint64_t));
+    block_cache_free(d->device, d->d_first_block, d->n_sub * sizeof(uint32_t));
+    host_cache_free(d->h_streams, d->stream_bytes);
     delete d;
 }
 
@@ -196,7 +385,7 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
     std::vector<uint64_t> slot(n_images + 1, 0);
     for (int i = 0; i < n_images; ++i) slot[i + 1] = slot[i] + ((lens[i] + 32 + 15) & ~(uint64_t)15);
     d->stream_bytes = (size_t)slot[n_images] + 64;
-    if (cudaHostAlloc((void**)&d->h_streams, d->stream_bytes, cudaHostAllocDefault) != cudaSuccess) {
+    if (host_cache_alloc((void**)&d->h_streams, d->stream_bytes) != cudaSuccess) {
         cudaGetLastError();
         rod_jpegdec_destroy(d);
         return ROD_ERR_OOM;
@@ -229,7 +418,8 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
     std::map<std::string, int> seen;
     d->h_block_start.assign(n_images + 1, 0);
     d->h_pair_start.assign(n_images + 1, 0);
-    uint64_t blocks = 0, pairs = 0;
+    d->h_sub_start.assign(n_images + 1, 0);
+    uint64_t blocks = 0, pairs = 0, subs = 0;
     for (int i = 0; i < n_images; ++i) {
         ImageRec& im = d->h_images[i];
         if (d->h_status[i] == 0) {
@@ -247,11 +437,16 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
             d->plane_bytes += mcus * 384;
             blocks += mcus * 6;
             pairs += (uint64_t)im.h * (uint64_t)((im.w + 1) >> 1);
+            const uint32_t n_sub = im.stream_bytes ? (8u * im.stream_bytes + kSubBits - 1) / kSubBits : 1u;
+            for (uint32_t s0 = 0; s0 < n_sub; s0 += kHuffThreads) d->h_ctas.push_back(make_uint2((unsigned)i, s0));
+            subs += n_sub;
         }
+        d->h_sub_start[i + 1] = (uint32_t)subs;
         d->h_block_start[i + 1] = (uint32_t)blocks;
         d->h_pair_start[i + 1] = (uint32_t)pairs;
     }
-    if (blocks >= (1ull << 32) || pairs >= (1ull << 32)) { rod_jpegdec_destroy(d); return ROD_ERR_UNSUPPORTED; }
+    d->n_sub = (size_t)subs;
+    if (blocks >= (1ull << 32) || pairs >= (1ull << 32) || subs >= (1ull << 32)) { rod_jpegdec_destroy(d); return ROD_ERR_UNSUPPORTED; }
     if (d->h_tables.empty()) d->h_tables.push_back(TableSet{});
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void** p, size_t n) { if (err == cudaSuccess) err = cudaMalloc(p, n ? n : 16); };
@@ -261,6 +456,12 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
     alloc((void**)&d->d_block_start, sizeof(uint32_t) * (n_images + 1));
     alloc((void**)&d->d_pair_start, sizeof(uint32_t) * (n_images + 1));
     alloc((void**)&d->d_status, sizeof(int32_t) * n_images);
+    alloc((void**)&d->d_sub_start, sizeof(uint32_t) * (n_images + 1));
+    alloc((void**)&d->d_ctas, sizeof(uint2) * d->h_ctas.size());
+    alloc((void**)&d->d_changed, sizeof(unsigned int) * 4);
+    calloc_((void**)&d->d_end_state, d->n_sub * sizeof(uint64_t));
+    calloc_((void**)&d->d_used_start, d->n_sub * sizeof(uint64_t));
+    calloc_((void**)&d->d_first_block, d->n_sub * sizeof(uint32_t));
     calloc_((void**)&d->d_streams, d->stream_bytes);
     calloc_((void**)&d->d_coef, d->coef_elems * sizeof(int16_t));
     calloc_((void**)&d->d_planes, d->plane_bytes);
@@ -291,14 +492,34 @@ extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* st
     ROD_CUDA(cudaMemcpyAsync(d->d_block_start, d->h_block_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_pair_start, d->h_pair_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_status, d->h_status.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    ROD_CUDA(cudaMemcpyAsync(d->d_sub_start, d->h_sub_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    if (!d->h_ctas.empty())
+        ROD_CUDA(cudaMemcpyAsync(d->d_ctas, d->h_ctas.data(), sizeof(uint2) * d->h_ctas.size(), cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_streams, d->h_streams, d->stream_bytes, cudaMemcpyHostToDevice, st));
-    if (d->coef_elems == 0) return ROD_OK;
+    if (d->coef_elems == 0 || d->h_ctas.empty()) return ROD_OK;
     ROD_CUDA(cudaMemsetAsync(d->d_coef, 0, d->coef_elems * sizeof(int16_t), st));
     JpegDecParams p;
     p.images = d->d_images; p.tables = d->d_tables; p.streams = d->d_streams; p.coef = d->d_coef; p.planes = d->d_planes;
     p.pixels = pixels; p.status = d->d_status; p.block_start = d->d_block_start; p.pair_start = d->d_pair_start;
+    p.sub_start = d->d_sub_start; p.ctas = d->d_ctas; p.end_state = d->d_end_state; p.used_start = d->d_used_start;
+    p.first_block = d->d_first_block; p.changed = d->d_changed;
     p.n_images = n;
-    jpegdec_huffman_kernel<<<n, 32, 0, st>>>(p);
+    const unsigned n_ctas = (unsigned)d->h_ctas.size();
+    jpegdec_guess_kernel<<<n_ctas, kHuffThreads, 0, st>>>(p);
+    // synchronisation rounds, four launches per host round trip, until a launch changes no end state
+    d->sync_rounds = 0;
+    for (;;) {
+        unsigned int flags[4];
+        ROD_CUDA(cudaMemsetAsync(d->d_changed, 0, sizeof(flags), st));
+        for (int q = 0; q < 4; ++q) jpegdec_sync_kernel<<<n_ctas, kHuffThreads, 0, st>>>(p, q);
+        ROD_CUDA(cudaMemcpyAsync(flags, d->d_changed, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        ROD_CUDA(cudaStreamSynchronize(st));
+        d->sync_rounds += 4;
+        if (!(flags[0] && flags[1] && flags[2] && flags[3])) break;
+    }
+    jpegdec_scan_kernel<<<n, 256, 0, st>>>(p);
+    jpegdec_write_kernel<<<n_ctas, kHuffThreads, 0, st>>>(p);
+    jpegdec_dc_kernel<<<dim3(n, 3), 256, 0, st>>>(p);
     const uint32_t blocks = d->h_block_start[n], pairs = d->h_pair_start[n];
     jpegdec_idct_kernel<<<(blocks + 127) / 128, 128, 0, st>>>(p);
     jpegdec_color_kernel<<<(pairs + 255) / 256, 256, 0, st>>>(p);

@@ -81,6 +81,13 @@ struct BitReader {
             n += 32;
         }
     }
+    RJ_HD void init_at(const uint8_t* stream, uint32_t stream_bytes, uint32_t bit) {   // start at an arbitrary bit position
+        init(stream, stream_bytes);
+        next = bit >> 5;
+        refill();
+        skip((int)(bit & 31u));
+    }
+    RJ_HD uint32_t pos() const { return 32u * next - (uint32_t)n; }   // bit position of the next unread bit
     RJ_HD uint32_t peek(int k) const { return (uint32_t)(acc >> (64 - k)); }   // 1 <= k <= 32
     RJ_HD void skip(int k) { acc <<= k; n -= k; }
     RJ_HD uint64_t bits_used() const { return 32ull * next - (uint64_t)n; }
@@ -99,7 +106,10 @@ RJ_HD int decode_symbol(BitReader& br, const HuffTab& t) {
         ++l;
         code = (int32_t)br.peek(l);
     }
-    if (l > 16) return -1;
+    if (l > 16) {   // not a code of this table: corrupt data (or a speculative start inside a symbol, see decode_span)
+        br.skip(16);
+        return -1;
+    }
     br.skip(l);
     return t.huffval[(code + t.valoffset[l]) & 255];
 }
@@ -168,6 +178,91 @@ RJ_HD int decode_scan(const ImageRec& im, const TableSet& ts, const uint8_t* nat
             if (!decode_block(br, rdc, rac, nat, &last_dc[2], crc + 64 * ((long)my * mcu_w + mx))) return 1;
         }
     return br.bits_used() > 8ull * im.stream_bytes ? 2 : 0;
+}
+
+// ---- parallel decoding of one scan (device: jpegdec.cu; CPU replay: tests/emu) ---------------------------------------
+// A baseline scan without restart markers is one serial bit stream, but Huffman codes resynchronise: a decoder started at
+// a wrong bit position / block position falls into step with the true symbol sequence after a few symbols, with high
+// probability (the self-synchronisation used by Weissenberger & Schmidt's GPU Huffman / JPEG decoders).  The stream is cut
+// into SUBSEQUENCES of kSubBits bits; subsequence s owns the symbols that START in [s kSubBits, (s + 1) kSubBits).
+//   state of a decoder between two symbols: (bit position p, zigzag index k of the next coefficient -- 0: a DC symbol is
+//   next --, block b of the MCU 0..5), packed with the number of blocks completed into one 64-bit word;
+//   E[s] = end state of subsequence s = F_s(start state), where the start state of s is E[s - 1] (s = 0: the scan's start).
+// Round 0 guesses every start state as (s kSubBits, 0, 0); later rounds re-decode the subsequences whose predecessor's end
+// state changed, until a whole round changes nothing: then E[s] = F_s(E[s - 1]) for every s with E[0] exact, i.e. every end
+// state is the sequential decoder's (induction over s).  A scan over the block counts gives every subsequence its first
+// block; a last pass decodes from the exact states and writes the coefficients (DC differences; the prediction is a
+// prefix sum per component afterwards).
+constexpr uint32_t kSubBits = 1024;
+RJ_HD uint64_t span_state(uint32_t p, uint32_t nblk, int k, int b) {
+    return (uint64_t)p | ((uint64_t)(nblk & 0xFFFFu) << 32) | ((uint64_t)(uint32_t)k << 48) | ((uint64_t)(uint32_t)b << 56);
+}
+RJ_HD uint32_t state_p(uint64_t e) { return (uint32_t)e; }
+RJ_HD uint32_t state_nblk(uint64_t e) { return (uint32_t)(e >> 32) & 0xFFFFu; }
+RJ_HD int state_k(uint64_t e) { return (int)((e >> 48) & 0xFFu); }
+RJ_HD int state_b(uint64_t e) { return (int)(e >> 56); }
+// the part of a state a successor starts from (the block count belongs to the subsequence that produced it)
+RJ_HD uint64_t state_start(uint64_t e) { return e & 0xFFFF0000FFFFFFFFull; }
+
+// coefficient block of global block index g (MCU g / 6, block g % 6) inside an image's coefficient area
+RJ_HD int16_t* block_of(int16_t* coef, int mcu_w, int mcu_h, uint32_t g) {
+    const uint32_t mcu = g / 6u, b = g - 6u * mcu;
+    const uint32_t my = mcu / (uint32_t)mcu_w, mx = mcu - my * (uint32_t)mcu_w;
+    if (b < 4u) return coef + 64L * ((long)(2u * my + (b >> 1)) * (2 * mcu_w) + 2u * mx + (b & 1u));
+    return coef + 64L * (4L * mcu_w * mcu_h + (long)(b - 4u) * mcu_w * mcu_h + mcu);
+}
+
+// Decodes the symbols that start in [start.p, boundary) from decoder state `start`; returns the end state.  WRITE: also
+// stores the coefficients (DC: the difference) from global block g0 on, stops behind block total_blocks - 1 and reports
+// corrupt data in *err.
+template <bool WRITE>
+RJ_HD uint64_t decode_span(const ImageRec& im, const TableSet& ts, const uint8_t* nat, const uint8_t* stream, uint64_t start,
+                           uint32_t boundary, int16_t* coef, uint32_t g0, uint32_t total_blocks, int* err) {
+    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
+    BitReader br;
+    br.init_at(stream, im.stream_bytes, state_p(start));
+    int k = state_k(start), b = state_b(start);
+    uint32_t nblk = 0, g = g0;
+    int16_t* blk = WRITE ? block_of(coef, mcu_w, mcu_h, g) : nullptr;
+    while (br.pos() < boundary && (!WRITE || g < total_blocks)) {
+        br.refill();
+        const int comp = b < 4 ? 0 : b - 3;
+        if (k == 0) {
+            int s = decode_symbol(br, ts.dc[ts.comp_dc[comp]]);
+            if (s < 0 || s > 16) { if (WRITE) *err = 1; s = 0; }
+            if (s) {
+                const uint32_t v = br.peek(s);
+                br.skip(s);
+                if (WRITE) blk[0] = (int16_t)extend(v, s);
+            }
+            k = 1;
+        } else {
+            int sym = decode_symbol(br, ts.ac[ts.comp_ac[comp]]);
+            if (sym < 0) { if (WRITE) *err = 1; sym = 0; }
+            const int r = sym >> 4, s = sym & 15;
+            if (s) {
+                k += r;
+                if (k > 63) { if (WRITE) *err = 1; k = 63; }
+                const uint32_t v = br.peek(s);
+                br.skip(s);
+                if (WRITE) blk[nat[k]] = (int16_t)extend(v, s);
+                ++k;
+            } else if (r == 15) {
+                k += 16;
+                if (k > 64) { if (WRITE) *err = 1; k = 64; }
+            } else {
+                k = 64;
+            }
+        }
+        if (k >= 64) {
+            k = 0;
+            b = b == 5 ? 0 : b + 1;
+            ++nblk;
+            ++g;
+            if (WRITE) blk = block_of(coef, mcu_w, mcu_h, g < total_blocks ? g : total_blocks - 1);
+        }
+    }
+    return span_state(br.pos(), nblk, k, b);
 }
 
 // jidctint.c jpeg_idct_islow: 64 quantised coefficients (natural order) x quantisation table -> 64 samples 0..255.

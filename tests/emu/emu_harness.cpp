@@ -1106,14 +1106,25 @@ extern "C" long emu_jpeg_encode(const uint8_t* bgr, int h, int w, long pitch, co
 // not end in EOI; 4 / 5: corrupt / short stream; 6: out too small.
 #include "../../robust-object-detection_b200/csrc/rod_jpegdec_host.h"
 
+// mode 0: the sequential scan decoder (decode_scan); mode 1: the device's passes (self-synchronising subsequences, block
+// scan, final pass, DC prefix sums) with the subsequences of a round visited in DESCENDING order, so that a round
+// propagates a corrected state by one subsequence only (the slowest schedule the concurrent device threads can produce);
+// hw[2] receives the number of rounds.
+extern "C" int emu_jpeg_decode_mode(const uint8_t* file, long n, uint8_t* out, long out_cap, int* hw, int mode);
 extern "C" int emu_jpeg_decode(const uint8_t* file, long n, uint8_t* out, long out_cap, int* hw) {
+    int hw3[3];
+    const int rc = emu_jpeg_decode_mode(file, n, out, out_cap, hw3, 0);
+    hw[0] = hw3[0]; hw[1] = hw3[1];
+    return rc;
+}
+extern "C" int emu_jpeg_decode_mode(const uint8_t* file, long n, uint8_t* out, long out_cap, int* hw, int mode) {
     using namespace rod::jpegdec;
     FileInfo info;
     std::vector<TableSet> tsv(1);
     TableSet& ts = tsv[0];
     const ParseStatus st = parse_file(file, (size_t)n, &info, &ts);
     if (st != PARSE_OK) return (int)st;
-    hw[0] = info.height; hw[1] = info.width;
+    hw[0] = info.height; hw[1] = info.width; hw[2] = 0;
     std::vector<uint8_t> stream((size_t)n - info.scan_begin + 64);
     const size_t sb = unstuff_scan(file, (size_t)n, info.scan_begin, stream.data());
     if (sb == (size_t)-1) return 3;
@@ -1124,7 +1135,47 @@ extern "C" int emu_jpeg_decode(const uint8_t* file, long n, uint8_t* out, long o
     std::vector<int16_t> coef((size_t)mcu_w * mcu_h * 6 * 64, 0);
     uint8_t nat[64];
     for (int z = 0; z < 64; ++z) nat[z] = (uint8_t)rod::jpeg::natural_order(z);
-    const int rc = decode_scan(im, ts, nat, stream.data(), coef.data());
+    hw[2] = 0;
+    int rc = 0;
+    if (mode == 0) {
+        rc = decode_scan(im, ts, nat, stream.data(), coef.data());
+    } else {
+        const uint32_t total_bits = 8u * (uint32_t)sb, total_blocks = 6u * (uint32_t)mcu_w * (uint32_t)mcu_h;
+        const uint32_t n_sub = total_bits ? (total_bits + kSubBits - 1) / kSubBits : 1;
+        std::vector<uint64_t> E(n_sub), U(n_sub);
+        for (uint32_t q = 0; q < n_sub; ++q) {
+            U[q] = span_state(q * kSubBits, 0, 0, 0);
+            E[q] = decode_span<false>(im, ts, nat, stream.data(), U[q], (q + 1) * kSubBits, nullptr, 0, 0, nullptr);
+        }
+        for (bool changed = true; changed;) {
+            changed = false;
+            ++hw[2];
+            for (uint32_t q = n_sub - 1; q >= 1; --q) {
+                const uint64_t st = state_start(E[q - 1]);
+                if (st == U[q]) continue;
+                U[q] = st;
+                E[q] = decode_span<false>(im, ts, nat, stream.data(), st, (q + 1) * kSubBits, nullptr, 0, 0, nullptr);
+                changed = true;
+            }
+        }
+        std::vector<uint32_t> blk0(n_sub + 1, 0);
+        for (uint32_t q = 0; q < n_sub; ++q) blk0[q + 1] = blk0[q] + state_nblk(E[q]);
+        if (blk0[n_sub] < total_blocks) rc = 2;
+        int err = 0;
+        for (uint32_t q = 0; q < n_sub && rc == 0; ++q)
+            if (blk0[q] < total_blocks)
+                decode_span<true>(im, ts, nat, stream.data(), q == 0 ? span_state(0, 0, 0, 0) : state_start(E[q - 1]),
+                                  (q + 1) * kSubBits, coef.data(), blk0[q], total_blocks, &err);
+        if (err) rc = 1;
+        // DC prediction: prefix sums per component in MCU order
+        int pred[3] = {0, 0, 0};
+        for (uint32_t g = 0; g < total_blocks && rc == 0; ++g) {
+            int16_t* blk = block_of(coef.data(), mcu_w, mcu_h, g);
+            const int b = (int)(g % 6u), comp = b < 4 ? 0 : b - 3;
+            pred[comp] += blk[0];
+            blk[0] = (int16_t)pred[comp];
+        }
+    }
     if (rc) return 3 + rc;
     const long ypitch = 16L * mcu_w, cpitch = 8L * mcu_w;
     std::vector<uint8_t> yp((size_t)ypitch * 16 * mcu_h), cbp((size_t)cpitch * 8 * mcu_h), crp((size_t)cpitch * 8 * mcu_h);

@@ -482,13 +482,16 @@ def test_emu_jpeg_encoder_matches_golden(emu):
         assert hashlib.sha256(out[:n].tobytes()).hexdigest() == g["sha"][f"{seed}_{h}x{w}_{kind}"], (seed, h, w, kind)
 
 
-def _emu_decode(emu, data):
-    emu.emu_jpeg_decode.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.c_long,
-                                    ctypes.POINTER(ctypes.c_int)]
+def _emu_decode(emu, data, mode=1, rounds=None):
+    """mode 0: sequential scan decoder; mode 1: the device's passes (self-synchronising subsequences, slowest schedule)"""
+    emu.emu_jpeg_decode_mode.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.c_long,
+                                         ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     b = np.frombuffer(data, np.uint8).copy()
     out = np.zeros(2100 * 2100 * 3, np.uint8)
-    hw = (ctypes.c_int * 2)()
-    rc = emu.emu_jpeg_decode(_p(b), len(b), _p(out), len(out), hw)
+    hw = (ctypes.c_int * 3)()
+    rc = emu.emu_jpeg_decode_mode(_p(b), len(b), _p(out), len(out), hw, mode)
+    if rounds is not None:
+        rounds.append(hw[2])
     return rc, (out[:hw[0] * hw[1] * 3].reshape(hw[0], hw[1], 3).copy() if rc == 0 else None)
 
 
@@ -512,9 +515,29 @@ def test_emu_jpeg_decoder_matches_cv2(emu):
         params = [[], [cv2.IMWRITE_JPEG_QUALITY, 100], [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(5, 95))], [cv2.IMWRITE_JPEG_OPTIMIZE, 1]][(i // 4) % 4]
         ok, enc = cv2.imencode(".jpg", img, params)
         assert ok
-        rc, got = _emu_decode(emu, enc.tobytes())
-        assert rc == 0, (h, w, params, rc)
-        assert np.array_equal(got, cv2.imdecode(enc, cv2.IMREAD_COLOR)), (h, w, kind, params)
+        want = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+        for mode in (0, 1):
+            rc, got = _emu_decode(emu, enc.tobytes(), mode)
+            assert rc == 0, (h, w, params, mode, rc)
+            assert np.array_equal(got, want), (h, w, kind, params, mode)
+
+
+def test_emu_jpeg_decoder_self_synchronisation(emu):
+    """The parallel Huffman stage on streams that synchronise badly: constant images (every block is the same few bits, a
+    decoder started at a wrong block of the MCU never falls into step: the states propagate one subsequence per round),
+    uniform noise at quality 100 (long codes), and a corrupt stream, which must be reported, not decoded."""
+    import cv2
+    rounds = []
+    for img, params in ((np.full((300, 500, 3), 77, np.uint8), []), (np.zeros((64, 2000, 3), np.uint8), [cv2.IMWRITE_JPEG_OPTIMIZE, 1]),
+                        (synth(8400, 240, 320), [cv2.IMWRITE_JPEG_QUALITY, 100]), (synth(8401, 200, 200) // 128 * 255, [])):
+        enc = cv2.imencode(".jpg", img, params)[1]
+        rc, got = _emu_decode(emu, enc.tobytes(), 1, rounds)
+        assert rc == 0 and np.array_equal(got, cv2.imdecode(enc, cv2.IMREAD_COLOR))
+    assert max(rounds) > 8, rounds          # the slow-propagation case was really exercised
+    whole = bytearray(cv2.imencode(".jpg", synth(8402, 120, 160))[1].tobytes())
+    scan = bytes(whole).index(b"\xff\xda") + 14
+    cut = bytes(whole[:scan + (len(whole) - scan) // 3]) + b"\xff\xd9"
+    assert _emu_decode(emu, cut, 1)[0] in (4, 5) and _emu_decode(emu, cut, 0)[0] in (4, 5)
 
 
 def test_emu_jpeg_decoder_reports_other_layouts(emu):

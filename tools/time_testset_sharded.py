@@ -27,6 +27,7 @@ from time_testset_driver import VARIANTS, make_tree  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    decoder = sys.argv[2] if len(sys.argv) > 2 else "gpu"
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         dist.init_process_group("gloo")
@@ -43,6 +44,7 @@ def main():
     barrier()
     from robust_object_detection_b200 import build_corrupted_testsets as drv
     drv.YOLO_SRC, drv.COCO_SRC, drv.NOISE_MODE, drv.ENCODER = base / "src" / "yolo", base / "src" / "coco", "philox", "gpu"
+    drv.DECODER = decoder
     keep = sys.stdout
     times = []
     parts = []   # (variant, seconds) of every _process_images call of the timed pass
@@ -85,7 +87,7 @@ def main():
             assert files == 2 * len(VARIANTS) * n, files
             wall = times[1][1]
             print(json.dumps({"n_gpus": world, "images_per_tree": n, "output_files": files, "wall_s": wall,
-                              "files_per_s": files / wall, "per_rank_s": per_rank, "per_rank_variant_s": per_rank_parts, "noise_mode": "philox", "encoder": "gpu",
+                              "files_per_s": files / wall, "per_rank_s": per_rank, "per_rank_variant_s": per_rank_parts, "noise_mode": "philox", "encoder": "gpu", "decoder": decoder,
                               "host_cores": len(os.sched_getaffinity(0)), "files_sha256": digest.hexdigest()}))
     finally:
         barrier()
