@@ -547,7 +547,16 @@ def extras(torch, np, plan, src, dst, peak):
         r["compressed_bytes_per_image"] = stream_bytes // nj
         r["content"] = "uniform noise"
         out["jpeg_encode_64"] = r
-        del enc
+        # ... and the device JPEG decoder (pixels identical to cv2.imread's) on those 64 files: bytes = stream read + pixels
+        # written; the call includes the upload of the streams and the host round trips of the synchronisation rounds
+        from robust_object_detection_b200.jpeg import JpegDecoder
+        dec = JpegDecoder([bytes(f) for f in files], [i * IMG_BYTES for i in range(nj)], host_threads=16)
+        back = torch.empty(nj * IMG_BYTES, dtype=torch.uint8, device="cuda")
+        r = rate(lambda: dec.decode(back), IMG_BYTES * nj + stream_bytes, nj, steps=5, warmup=2)
+        assert (dec.status() == 0).all()
+        r["content"] = "the 64 files of jpeg_encode_64 (uniform noise, 1.2 MB each: the slowest content to decode)"
+        out["jpeg_decode_64"] = r
+        del enc, dec, back
     except Exception as e:  # cv2 (for the header template) is the only extra dependency
         print(f"[bench] JPEG encoder line skipped: {e}", file=sys.stderr)
     import random
