@@ -17,9 +17,9 @@
 //                                    order, per-component block rasters; DC as the difference)
 //             jpegdec_dc_kernel      DC prediction = prefix sum of the differences per component in MCU order
 //           jpegdec_idct_kernel      one thread per 8x8 block: dequantisation + islow IDCT in registers -> Y / Cb / Cr planes
-//           jpegdec_color_kernel     one thread per two output pixels: fancy h2v2 chroma upsampling + YCbCr -> BGR, written
+//           jpegdec_color_kernel     one thread per two output pixels: fancy chroma upsampling + YCbCr -> BGR, written
 //                                    straight into the caller's HWC batch (the layout of a rod_plan)
-// Files of another layout (progressive, 4:4:4, restart markers, EXIF rotation ...) are reported per image; the caller
+// Files of another layout (progressive, restart markers, EXIF rotation, CMYK ...) are reported per image; the caller
 // decodes those with the host codec.  No CPU decoding in here.
 #include <map>
 #include <string>
@@ -40,7 +40,7 @@ struct JpegDecParams {
     uint8_t* planes;
     uint8_t* pixels;
     int32_t* status;
-    const uint32_t* block_start;   // [n + 1] prefix sums of 6 * MCUs
+    const uint32_t* block_start;   // [n + 1] prefix sums of the number of blocks
     const uint32_t* pair_start;    // [n + 1] prefix sums of h * ceil(w / 2)
     const uint32_t* sub_start;     // [n + 1] prefix sums of the number of subsequences
     const uint2* ctas;             // Huffman kernels: CTA -> (image, first subsequence of the image it covers)
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(256) jpegdec_scan_kernel(JpegDecParams p) {
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const uint32_t total = 6u * (uint32_t)((im.w + 15) >> 4) * (uint32_t)((im.h + 15) >> 4);
-        if (carry_s < total) p.status[img] = 2;
+        const Layout L = layout_of(im);
+        if (carry_s < (uint32_t)(L.nb * L.mcus)) p.status[img] = 2;
     }
 }
 
@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(kHuffThreads) jpegdec_write_kernel(JpegDecPara
     const uint32_t s = c.y + threadIdx.x, n_sub = p.sub_start[c.x + 1] - p.sub_start[c.x];
     if (s >= n_sub) return;
     const uint32_t gs = p.sub_start[c.x] + s;
-    const uint32_t total = 6u * (uint32_t)((im.w + 15) >> 4) * (uint32_t)((im.h + 15) >> 4);
+    const Layout L = layout_of(im);
+    const uint32_t total = (uint32_t)(L.nb * L.mcus);
     const uint32_t g0 = p.first_block[gs];
     if (g0 >= total) return;   // behind the last block: padding
     int err = 0;
@@ -171,16 +172,18 @@ __global__ void __launch_bounds__(256) jpegdec_dc_kernel(JpegDecParams p) {
     __shared__ int carry_s;
     const int img = blockIdx.x, comp = blockIdx.y;
     const ImageRec im = p.images[img];
-    if (im.h == 0 || p.status[img] != 0) return;
-    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
-    const uint32_t n = (comp == 0 ? 4u : 1u) * (uint32_t)mcu_w * (uint32_t)mcu_h;
+    if (im.h == 0 || p.status[img] != 0 || comp >= im.ncomp) return;
+    const Layout L = layout_of(im);
+    const uint32_t n = (uint32_t)((comp == 0 ? L.nl : 1) * L.mcus);
     int16_t* coef = p.coef + im.coef_off;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     for (uint32_t base = 0; base < n; base += 256) {
         const uint32_t j = base + threadIdx.x;
         int16_t* blk = nullptr;
-        if (j < n) blk = block_of(coef, mcu_w, mcu_h, comp == 0 ? 6u * (j >> 2) + (j & 3u) : 6u * j + 3u + (uint32_t)comp);
+        if (j < n)
+            blk = block_of(coef, L, comp == 0 ? (uint32_t)L.nb * (j / (uint32_t)L.nl) + j % (uint32_t)L.nl
+                                              : (uint32_t)L.nb * j + (uint32_t)(L.nl + comp - 1));
         const int v = blk ? (int)blk[0] : 0;
         int x = v;
 #pragma unroll
@@ -216,15 +219,15 @@ __global__ void __launch_bounds__(128) jpegdec_idct_kernel(JpegDecParams p) {
     const ImageRec im = p.images[img];
     if (__ldg(p.status + img) != 0) return;
     const uint32_t b = gi - __ldg(p.block_start + img);
-    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
-    const uint32_t yblocks = 4u * mcu_w * mcu_h, cblocks = (uint32_t)mcu_w * mcu_h;
+    const Layout L = layout_of(im);
+    const uint32_t yblocks = (uint32_t)(L.nl * L.mcus), cblocks = (uint32_t)L.mcus;
     int comp;
     uint32_t bi;
     long pitch;
     uint8_t* plane = p.planes + im.plane_off;
-    if (b < yblocks) { comp = 0; bi = b; pitch = 16L * mcu_w; }
-    else if (b < yblocks + cblocks) { comp = 1; bi = b - yblocks; pitch = 8L * mcu_w; plane += 256L * mcu_w * mcu_h; }
-    else { comp = 2; bi = b - yblocks - cblocks; pitch = 8L * mcu_w; plane += 320L * mcu_w * mcu_h; }
+    if (b < yblocks) { comp = 0; bi = b; pitch = 8L * L.hs * L.mcu_w; }
+    else if (b < yblocks + cblocks) { comp = 1; bi = b - yblocks; pitch = 8L * L.mcu_w; plane += 64L * yblocks; }
+    else { comp = 2; bi = b - yblocks - cblocks; pitch = 8L * L.mcu_w; plane += 64L * (yblocks + cblocks); }
     const uint32_t bpr = (uint32_t)(pitch >> 3);
     const uint32_t by = bi / bpr, bx = bi - by * bpr;
     __align__(16) int16_t c[64];
@@ -255,21 +258,25 @@ __global__ void __launch_bounds__(256) jpegdec_color_kernel(JpegDecParams p) {
     const ImageRec im = p.images[img];
     if (__ldg(p.status + img) != 0) return;
     const uint32_t k = gi - __ldg(p.pair_start + img);
-    const int cw = (im.w + 1) >> 1, ch = (im.h + 1) >> 1;
-    const int y = (int)(k / (uint32_t)cw), cx = (int)(k - (uint32_t)y * (uint32_t)cw);
-    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
-    const long ypitch = 16L * mcu_w, cpitch = 8L * mcu_w;
+    const Layout L = layout_of(im);
+    const int pw = (im.w + 1) >> 1;   // pixel pairs per row
+    const int cw = (im.w + L.hs - 1) / L.hs, ch = (im.h + L.vs - 1) / L.vs;
+    const int y = (int)(k / (uint32_t)pw), cx = (int)(k - (uint32_t)y * (uint32_t)pw);
+    const long ypitch = 8L * L.hs * L.mcu_w, cpitch = 8L * L.mcu_w;
     const uint8_t* yp = p.planes + im.plane_off;
-    const uint8_t* cbp = yp + 256L * mcu_w * mcu_h;
-    const uint8_t* crp = yp + 320L * mcu_w * mcu_h;
+    const uint8_t* cbp = yp + 64L * L.nl * L.mcus;
+    const uint8_t* crp = cbp + 64L * L.mcus;
     uint8_t* out = p.pixels + im.dst_off + (int64_t)y * im.dst_pitch + 6 * cx;
     const int x = 2 * cx;
     uint8_t px[6];
-    ycc_to_bgr(yp[y * ypitch + x], upsample_h2v2(cbp, cpitch, cw, ch, x, y), upsample_h2v2(crp, cpitch, cw, ch, x, y), px);
+    auto pixel = [&](int xx, uint8_t* o) {
+        const int yy = yp[y * ypitch + xx];
+        if (im.ncomp == 1) { o[0] = o[1] = o[2] = (uint8_t)yy; return; }
+        ycc_to_bgr(yy, chroma_at(cbp, cpitch, L.hs, L.vs, cw, ch, xx, y), chroma_at(crp, cpitch, L.hs, L.vs, cw, ch, xx, y), o);
+    };
+    pixel(x, px);
     const bool two = x + 1 < im.w;
-    if (two)
-        ycc_to_bgr(yp[y * ypitch + x + 1], upsample_h2v2(cbp, cpitch, cw, ch, x + 1, y), upsample_h2v2(crp, cpitch, cw, ch, x + 1, y),
-                   px + 3);
+    if (two) pixel(x + 1, px + 3);
     if (two && ((uintptr_t)out & 1) == 0) {   // 6 bytes at a 2-byte aligned address
         uint16_t* o2 = reinterpret_cast<uint16_t*>(out);
         o2[0] = (uint16_t)(px[0] | (px[1] << 8));
@@ -400,6 +407,7 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
             const size_t sb = unstuff_scan(files[i], (size_t)lens[i], info.scan_begin, d->h_streams + slot[i]);
             if (sb == (size_t)-1) { d->h_status[i] = 13; continue; }
             im.h = info.height; im.w = info.width;
+            im.hs = (uint8_t)info.hs; im.vs = (uint8_t)info.vs; im.ncomp = (uint8_t)info.ncomp;
             im.stream_bytes = (uint32_t)sb;
             im.stream_off = slot[i];
             im.dst_off = dst_offsets[i];
@@ -430,12 +438,13 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
                 d->h_tables.push_back(per_image[i]);
             }
             im.table_set = it->second;
-            const uint64_t mcus = (uint64_t)((im.w + 15) >> 4) * (uint64_t)((im.h + 15) >> 4);
+            const Layout L = layout_of(im);
+            const uint64_t nblocks = (uint64_t)L.mcus * (uint64_t)L.nb;
             im.coef_off = d->coef_elems;
             im.plane_off = d->plane_bytes;
-            d->coef_elems += mcus * 6 * 64;
-            d->plane_bytes += mcus * 384;
-            blocks += mcus * 6;
+            d->coef_elems += nblocks * 64;
+            d->plane_bytes += nblocks * 64;
+            blocks += nblocks;
             pairs += (uint64_t)im.h * (uint64_t)((im.w + 1) >> 1);
             const uint32_t n_sub = im.stream_bytes ? (8u * im.stream_bytes + kSubBits - 1) / kSubBits : 1u;
             for (uint32_t s0 = 0; s0 < n_sub; s0 += kHuffThreads) d->h_ctas.push_back(make_uint2((unsigned)i, s0));

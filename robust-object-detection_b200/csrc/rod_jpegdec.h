@@ -9,9 +9,10 @@
 //   jdsample.c h2v2_fancy_upsample   chroma: 3/4 - 1/4 triangle filter in both axes, roundings 8 / 7 alternating by column
 //   jdmainct.c context rows          above the first / below the last REAL chroma row the nearest real row is used
 //   jdcolor.c  ycc_rgb_convert       16-bit fixed-point YCbCr -> RGB (written out as BGR)
-// Supported layout: baseline sequential (SOF0), 8 bit, three components Y Cb Cr sampled 2x2 / 1x1 / 1x1 in one interleaved
-// scan, no restart markers -- what OpenCV itself writes and what the reference's test trees hold.  Anything else is
-// reported as unsupported by the parser and the caller keeps the host codec for that file.
+//              h2v1_fancy_upsample   4:2:2 files: the same filter along the row only, roundings 1 / 2
+// Supported layouts: baseline sequential (SOF0), 8 bit, one scan without restart markers, either Y Cb Cr with the luma
+// sampled 2x2 (4:2:0, what OpenCV itself writes), 2x1 (4:2:2) or 1x1 (4:4:4) against 1x1 chroma, or greyscale.  Anything
+// else is reported as unsupported by the parser and the caller keeps the host codec for that file.
 // The same functions are compiled into tests/emu (CPU check against cv2.imdecode) and into jpegdec.cu.
 #pragma once
 #include <stdint.h>
@@ -47,11 +48,31 @@ struct ImageRec {
     int32_t table_set;
     uint32_t stream_bytes;
     uint64_t stream_off;
-    uint64_t coef_off;           // int16 units: Y blocks [2 mcu_h][2 mcu_w][64], then Cb [mcu_h][mcu_w][64], then Cr
-    uint64_t plane_off;          // bytes: Y plane [16 mcu_h][16 mcu_w], then Cb [8 mcu_h][8 mcu_w], then Cr
+    uint64_t coef_off;           // int16 units: Y blocks [vs mcu_h][hs mcu_w][64], then Cb [mcu_h][mcu_w][64], then Cr
+    uint64_t plane_off;          // bytes: Y plane [8 vs mcu_h][8 hs mcu_w], then Cb [8 mcu_h][8 mcu_w], then Cr
     uint64_t dst_off;            // bytes into the caller's pixel buffer (HWC BGR)
     int64_t dst_pitch;
+    uint8_t hs, vs;              // luma sampling factors (chroma: 1 x 1); greyscale: 1, 1
+    uint8_t ncomp;               // 3 or 1
+    uint8_t pad[5];
 };
+
+// MCU geometry of an image: an MCU is hs x vs luma blocks followed by one Cb and one Cr block (greyscale: one block).
+struct Layout {
+    int hs, vs, nl, nb;          // nl = hs * vs luma blocks, nb blocks per MCU
+    int mcu_w, mcu_h;
+    long mcus;
+};
+RJ_HD Layout layout_of(const ImageRec& im) {
+    Layout L;
+    L.hs = im.hs; L.vs = im.vs;
+    L.nl = L.hs * L.vs;
+    L.nb = L.nl + (im.ncomp == 3 ? 2 : 0);
+    L.mcu_w = (im.w + 8 * L.hs - 1) / (8 * L.hs);
+    L.mcu_h = (im.h + 8 * L.vs - 1) / (8 * L.vs);
+    L.mcus = (long)L.mcu_w * L.mcu_h;
+    return L;
+}
 
 // MSB-first reader over the unstuffed stream, 32 bits at a time.
 struct BitReader {
@@ -151,31 +172,27 @@ RJ_HD bool decode_block(BitReader& br, const HuffTab& dc, const HuffTab& ac, con
     return true;
 }
 
-// The whole scan of one image (interleaved 4:2:0 MCUs: Y00 Y01 Y10 Y11 Cb Cr).  coef: this image's zeroed coefficient area.
-// Returns 0, or 1 (corrupt code), 2 (ran past the end of the stream).
+// The whole scan of one image, sequentially (reference for the parallel passes below; CPU replay only).  coef: this
+// image's zeroed coefficient area.  Returns 0, or 1 (corrupt code), 2 (ran past the end of the stream).
 RJ_HD int decode_scan(const ImageRec& im, const TableSet& ts, const uint8_t* nat, const uint8_t* stream, int16_t* coef) {
-    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
-    const long yblocks = 4L * mcu_w * mcu_h, cblocks = (long)mcu_w * mcu_h;
+    const Layout L = layout_of(im);
     int16_t* yc = coef;
-    int16_t* cbc = coef + 64 * yblocks;
-    int16_t* crc = cbc + 64 * cblocks;
+    int16_t* cbc = coef + 64 * L.nl * L.mcus;
+    int16_t* crc = cbc + 64 * L.mcus;
     BitReader br;
     br.init(stream, im.stream_bytes);
     int last_dc[3] = {0, 0, 0};
-    const HuffTab& ydc = ts.dc[ts.comp_dc[0]];
-    const HuffTab& yac = ts.ac[ts.comp_ac[0]];
-    const HuffTab& bdc = ts.dc[ts.comp_dc[1]];
-    const HuffTab& bac = ts.ac[ts.comp_ac[1]];
-    const HuffTab& rdc = ts.dc[ts.comp_dc[2]];
-    const HuffTab& rac = ts.ac[ts.comp_ac[2]];
-    for (int my = 0; my < mcu_h; ++my)
-        for (int mx = 0; mx < mcu_w; ++mx) {
-            for (int b = 0; b < 4; ++b) {
-                int16_t* blk = yc + 64 * ((long)(2 * my + (b >> 1)) * (2 * mcu_w) + 2 * mx + (b & 1));
-                if (!decode_block(br, ydc, yac, nat, &last_dc[0], blk)) return 1;
+    for (int my = 0; my < L.mcu_h; ++my)
+        for (int mx = 0; mx < L.mcu_w; ++mx) {
+            for (int b = 0; b < L.nl; ++b) {
+                int16_t* blk = yc + 64 * ((long)(L.vs * my + b / L.hs) * (L.hs * L.mcu_w) + L.hs * mx + b % L.hs);
+                if (!decode_block(br, ts.dc[ts.comp_dc[0]], ts.ac[ts.comp_ac[0]], nat, &last_dc[0], blk)) return 1;
             }
-            if (!decode_block(br, bdc, bac, nat, &last_dc[1], cbc + 64 * ((long)my * mcu_w + mx))) return 1;
-            if (!decode_block(br, rdc, rac, nat, &last_dc[2], crc + 64 * ((long)my * mcu_w + mx))) return 1;
+            if (im.ncomp == 3) {
+                const long m = (long)my * L.mcu_w + mx;
+                if (!decode_block(br, ts.dc[ts.comp_dc[1]], ts.ac[ts.comp_ac[1]], nat, &last_dc[1], cbc + 64 * m)) return 1;
+                if (!decode_block(br, ts.dc[ts.comp_dc[2]], ts.ac[ts.comp_ac[2]], nat, &last_dc[2], crc + 64 * m)) return 1;
+            }
         }
     return br.bits_used() > 8ull * im.stream_bytes ? 2 : 0;
 }
@@ -186,7 +203,7 @@ RJ_HD int decode_scan(const ImageRec& im, const TableSet& ts, const uint8_t* nat
 // probability (the self-synchronisation used by Weissenberger & Schmidt's GPU Huffman / JPEG decoders).  The stream is cut
 // into SUBSEQUENCES of kSubBits bits; subsequence s owns the symbols that START in [s kSubBits, (s + 1) kSubBits).
 //   state of a decoder between two symbols: (bit position p, zigzag index k of the next coefficient -- 0: a DC symbol is
-//   next --, block b of the MCU 0..5), packed with the number of blocks completed into one 64-bit word;
+//   next --, block b of the MCU 0 .. nb - 1), packed with the number of blocks completed into one 64-bit word;
 //   E[s] = end state of subsequence s = F_s(start state), where the start state of s is E[s - 1] (s = 0: the scan's start).
 // Round 0 guesses every start state as (s kSubBits, 0, 0); later rounds re-decode the subsequences whose predecessor's end
 // state changed, until a whole round changes nothing: then E[s] = F_s(E[s - 1]) for every s with E[0] exact, i.e. every end
@@ -204,12 +221,15 @@ RJ_HD int state_b(uint64_t e) { return (int)(e >> 56); }
 // the part of a state a successor starts from (the block count belongs to the subsequence that produced it)
 RJ_HD uint64_t state_start(uint64_t e) { return e & 0xFFFF0000FFFFFFFFull; }
 
-// coefficient block of global block index g (MCU g / 6, block g % 6) inside an image's coefficient area
-RJ_HD int16_t* block_of(int16_t* coef, int mcu_w, int mcu_h, uint32_t g) {
-    const uint32_t mcu = g / 6u, b = g - 6u * mcu;
-    const uint32_t my = mcu / (uint32_t)mcu_w, mx = mcu - my * (uint32_t)mcu_w;
-    if (b < 4u) return coef + 64L * ((long)(2u * my + (b >> 1)) * (2 * mcu_w) + 2u * mx + (b & 1u));
-    return coef + 64L * (4L * mcu_w * mcu_h + (long)(b - 4u) * mcu_w * mcu_h + mcu);
+// coefficient block of global block index g (MCU g / nb, block g % nb) inside an image's coefficient area
+RJ_HD int16_t* block_of(int16_t* coef, const Layout& L, uint32_t g) {
+    const uint32_t mcu = g / (uint32_t)L.nb, b = g - (uint32_t)L.nb * mcu;
+    if ((int)b < L.nl) {
+        const uint32_t my = mcu / (uint32_t)L.mcu_w, mx = mcu - my * (uint32_t)L.mcu_w;
+        const uint32_t by = b / (uint32_t)L.hs, bx = b - by * (uint32_t)L.hs;
+        return coef + 64L * ((long)(L.vs * my + by) * (L.hs * L.mcu_w) + L.hs * mx + bx);
+    }
+    return coef + 64L * (L.nl * L.mcus + (long)((int)b - L.nl) * L.mcus + mcu);
 }
 
 // Decodes the symbols that start in [start.p, boundary) from decoder state `start`; returns the end state.  WRITE: also
@@ -218,15 +238,15 @@ RJ_HD int16_t* block_of(int16_t* coef, int mcu_w, int mcu_h, uint32_t g) {
 template <bool WRITE>
 RJ_HD uint64_t decode_span(const ImageRec& im, const TableSet& ts, const uint8_t* nat, const uint8_t* stream, uint64_t start,
                            uint32_t boundary, int16_t* coef, uint32_t g0, uint32_t total_blocks, int* err) {
-    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
+    const Layout L = layout_of(im);
     BitReader br;
     br.init_at(stream, im.stream_bytes, state_p(start));
     int k = state_k(start), b = state_b(start);
     uint32_t nblk = 0, g = g0;
-    int16_t* blk = WRITE ? block_of(coef, mcu_w, mcu_h, g) : nullptr;
+    int16_t* blk = WRITE ? block_of(coef, L, g) : nullptr;
     while (br.pos() < boundary && (!WRITE || g < total_blocks)) {
         br.refill();
-        const int comp = b < 4 ? 0 : b - 3;
+        const int comp = b < L.nl ? 0 : b - L.nl + 1;
         if (k == 0) {
             int s = decode_symbol(br, ts.dc[ts.comp_dc[comp]]);
             if (s < 0 || s > 16) { if (WRITE) *err = 1; s = 0; }
@@ -256,10 +276,10 @@ RJ_HD uint64_t decode_span(const ImageRec& im, const TableSet& ts, const uint8_t
         }
         if (k >= 64) {
             k = 0;
-            b = b == 5 ? 0 : b + 1;
+            b = b == L.nb - 1 ? 0 : b + 1;
             ++nblk;
             ++g;
-            if (WRITE) blk = block_of(coef, mcu_w, mcu_h, g < total_blocks ? g : total_blocks - 1);
+            if (WRITE) blk = block_of(coef, L, g < total_blocks ? g : total_blocks - 1);
         }
     }
     return span_state(br.pos(), nblk, k, b);
@@ -338,6 +358,19 @@ RJ_HD int upsample_h2v2(const uint8_t* plane, long pitch, int cw, int ch, int x,
     }
     if (cx == 0) return (4 * cur + 8) >> 4;
     return (3 * cur + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
+}
+
+// jdsample.c h2v1_fancy_upsample (4:2:2): the filter along the row only.  cw >= 3.
+RJ_HD int upsample_h2v1(const uint8_t* plane, long pitch, int cw, int x, int y) {
+    const uint8_t* r0 = plane + (long)y * pitch;
+    const int cx = x >> 1, cur = r0[cx];
+    if (x & 1) return cx == cw - 1 ? cur : (3 * cur + r0[cx + 1] + 2) >> 2;
+    return cx == 0 ? cur : (3 * cur + r0[cx - 1] + 1) >> 2;
+}
+// the chroma sample of output pixel (x, y) for luma sampling hs x vs
+RJ_HD int chroma_at(const uint8_t* plane, long pitch, int hs, int vs, int cw, int ch, int x, int y) {
+    if (hs == 2) return vs == 2 ? upsample_h2v2(plane, pitch, cw, ch, x, y) : upsample_h2v1(plane, pitch, cw, x, y);
+    return plane[(long)y * pitch + x];
 }
 
 // jdcolor.c ycc_rgb_convert (SCALEBITS 16), written as B, G, R

@@ -19,6 +19,7 @@ enum ParseStatus {
 
 struct FileInfo {
     int height = 0, width = 0;
+    int hs = 0, vs = 0, ncomp = 0;   // luma sampling (chroma 1 x 1), 3 components or 1
     size_t scan_begin = 0;       // first byte of the entropy-coded segment
 };
 
@@ -74,7 +75,7 @@ inline ParseStatus parse_file(const uint8_t* f, size_t n, FileInfo* info, TableS
     if (n < 4 || f[0] != 0xFF || f[1] != 0xD8) return PARSE_NOT_JPEG;
     uint16_t qt[4][64];
     bool have_q[4] = {false, false, false, false}, have_dc[2] = {false, false}, have_ac[2] = {false, false};
-    int tq[3] = {0, 0, 0};
+    int tq[3] = {0, 0, 0}, comp_id[3] = {0, 0, 0};
     bool have_sof = false, adobe = false;
     size_t i = 2;
     for (;;) {
@@ -102,18 +103,24 @@ inline ParseStatus parse_file(const uint8_t* f, size_t n, FileInfo* info, TableS
         } else if (m == 0xC0) {
             if (have_sof) return PARSE_UNSUPPORTED;
             if (pl < 6) return PARSE_NOT_JPEG;
-            if (p[0] != 8 || p[5] != 3 || pl < 15) return PARSE_UNSUPPORTED;
+            if (p[0] != 8 || (p[5] != 3 && p[5] != 1) || pl < 6 + 3u * p[5]) return PARSE_UNSUPPORTED;
             info->height = (p[1] << 8) | p[2];
             info->width = (p[3] << 8) | p[4];
-            for (int c = 0; c < 3; ++c) {
+            info->ncomp = p[5];
+            for (int c = 0; c < info->ncomp; ++c) {
                 const int id = p[6 + 3 * c], hs = p[7 + 3 * c] >> 4, vs = p[7 + 3 * c] & 15;
-                if (id != c + 1) return PARSE_UNSUPPORTED;   // libjpeg's YCbCr guess needs ids 1, 2, 3 (or a JFIF marker)
-                if (hs != (c == 0 ? 2 : 1) || vs != (c == 0 ? 2 : 1)) return PARSE_UNSUPPORTED;
+                comp_id[c] = id;
+                if (info->ncomp == 3 && id != c + 1) return PARSE_UNSUPPORTED;   // libjpeg's YCbCr guess: ids 1, 2, 3 (or a JFIF marker)
+                if (c == 0) { info->hs = hs; info->vs = vs; }
+                else if (hs != 1 || vs != 1) return PARSE_UNSUPPORTED;
                 tq[c] = p[8 + 3 * c];
                 if (tq[c] > 3) return PARSE_NOT_JPEG;
             }
-            if (info->height < 1 || info->width < 5) return PARSE_UNSUPPORTED;   // one or two chroma columns: libjpeg-turbo's
-                                                                                 // upsampler reads its padding there
+            if (info->ncomp == 1) info->hs = info->vs = 1;   // a single-component scan is not interleaved: one block per MCU
+            if (!((info->hs == 2 && info->vs == 2) || (info->hs == 2 && info->vs == 1) || (info->hs == 1 && info->vs == 1)))
+                return PARSE_UNSUPPORTED;
+            // one or two chroma columns: libjpeg-turbo's upsampler reads its padding there
+            if (info->height < 1 || info->width < (info->hs == 2 ? 5 : 1)) return PARSE_UNSUPPORTED;
             have_sof = true;
         } else if (m >= 0xC1 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
             return PARSE_UNSUPPORTED;   // extended, progressive, lossless, arithmetic
@@ -140,22 +147,23 @@ inline ParseStatus parse_file(const uint8_t* f, size_t n, FileInfo* info, TableS
             if (pl >= 12 && memcmp(p, "Adobe", 5) == 0) adobe = true;
         } else if (m == 0xDA) {
             if (!have_sof) return PARSE_NOT_JPEG;
-            if (pl < 10 || p[0] != 3) return PARSE_UNSUPPORTED;   // one interleaved scan of all three components
-            for (int c = 0; c < 3; ++c) {
-                if (p[1 + 2 * c] != c + 1) return PARSE_UNSUPPORTED;
+            const int nc = info->ncomp;
+            if (pl < 4 + 2u * nc || p[0] != nc) return PARSE_UNSUPPORTED;   // one scan with all components
+            for (int c = 0; c < nc; ++c) {
+                if (p[1 + 2 * c] != comp_id[c]) return PARSE_UNSUPPORTED;
                 ts->comp_dc[c] = p[2 + 2 * c] >> 4;
                 ts->comp_ac[c] = p[2 + 2 * c] & 15;
                 if (ts->comp_dc[c] > 1 || ts->comp_ac[c] > 1) return PARSE_UNSUPPORTED;
                 if (!have_dc[ts->comp_dc[c]] || !have_ac[ts->comp_ac[c]] || !have_q[tq[c]]) return PARSE_NOT_JPEG;
                 memcpy(ts->quant[c], qt[tq[c]], sizeof(qt[0]));
             }
-            if (p[7] != 0 || p[8] != 63 || p[9] != 0) return PARSE_UNSUPPORTED;
+            if (p[1 + 2 * nc] != 0 || p[2 + 2 * nc] != 63 || p[3 + 2 * nc] != 0) return PARSE_UNSUPPORTED;
             if (adobe) return PARSE_UNSUPPORTED;   // Adobe marker: the colour transform is the marker's, not JFIF's
             info->scan_begin = i + 2 + L;
             // tables of unused slots must not make two equal files look different
             for (int t = 0; t < 2; ++t) {
                 bool dc_used = false, ac_used = false;
-                for (int c = 0; c < 3; ++c) { dc_used |= ts->comp_dc[c] == t; ac_used |= ts->comp_ac[c] == t; }
+                for (int c = 0; c < nc; ++c) { dc_used |= ts->comp_dc[c] == t; ac_used |= ts->comp_ac[c] == t; }
                 if (!dc_used) memset(&ts->dc[t], 0, sizeof(HuffTab));
                 if (!ac_used) memset(&ts->ac[t], 0, sizeof(HuffTab));
             }

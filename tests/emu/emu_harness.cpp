@@ -1131,8 +1131,10 @@ extern "C" int emu_jpeg_decode_mode(const uint8_t* file, long n, uint8_t* out, l
     ImageRec im;
     memset(&im, 0, sizeof(im));
     im.h = info.height; im.w = info.width; im.stream_bytes = (uint32_t)sb;
-    const int mcu_w = (im.w + 15) >> 4, mcu_h = (im.h + 15) >> 4;
-    std::vector<int16_t> coef((size_t)mcu_w * mcu_h * 6 * 64, 0);
+    im.hs = (uint8_t)info.hs; im.vs = (uint8_t)info.vs; im.ncomp = (uint8_t)info.ncomp;
+    const Layout L = layout_of(im);
+    const int mcu_w = L.mcu_w, mcu_h = L.mcu_h;
+    std::vector<int16_t> coef((size_t)L.mcus * L.nb * 64, 0);
     uint8_t nat[64];
     for (int z = 0; z < 64; ++z) nat[z] = (uint8_t)rod::jpeg::natural_order(z);
     hw[2] = 0;
@@ -1140,7 +1142,7 @@ extern "C" int emu_jpeg_decode_mode(const uint8_t* file, long n, uint8_t* out, l
     if (mode == 0) {
         rc = decode_scan(im, ts, nat, stream.data(), coef.data());
     } else {
-        const uint32_t total_bits = 8u * (uint32_t)sb, total_blocks = 6u * (uint32_t)mcu_w * (uint32_t)mcu_h;
+        const uint32_t total_bits = 8u * (uint32_t)sb, total_blocks = (uint32_t)(L.nb * L.mcus);
         const uint32_t n_sub = total_bits ? (total_bits + kSubBits - 1) / kSubBits : 1;
         std::vector<uint64_t> E(n_sub), U(n_sub);
         for (uint32_t q = 0; q < n_sub; ++q) {
@@ -1170,30 +1172,35 @@ extern "C" int emu_jpeg_decode_mode(const uint8_t* file, long n, uint8_t* out, l
         // DC prediction: prefix sums per component in MCU order
         int pred[3] = {0, 0, 0};
         for (uint32_t g = 0; g < total_blocks && rc == 0; ++g) {
-            int16_t* blk = block_of(coef.data(), mcu_w, mcu_h, g);
-            const int b = (int)(g % 6u), comp = b < 4 ? 0 : b - 3;
+            int16_t* blk = block_of(coef.data(), L, g);
+            const int b = (int)(g % (uint32_t)L.nb), comp = b < L.nl ? 0 : b - L.nl + 1;
             pred[comp] += blk[0];
             blk[0] = (int16_t)pred[comp];
         }
     }
     if (rc) return 3 + rc;
-    const long ypitch = 16L * mcu_w, cpitch = 8L * mcu_w;
-    std::vector<uint8_t> yp((size_t)ypitch * 16 * mcu_h), cbp((size_t)cpitch * 8 * mcu_h), crp((size_t)cpitch * 8 * mcu_h);
-    for (int by = 0; by < 2 * mcu_h; ++by)
-        for (int bx = 0; bx < 2 * mcu_w; ++bx)
-            idct_islow(coef.data() + 64 * ((size_t)by * 2 * mcu_w + bx), ts.quant[0], yp.data() + 8L * by * ypitch + 8 * bx, ypitch);
-    const int16_t* cbc = coef.data() + 64 * (size_t)4 * mcu_w * mcu_h;
-    const int16_t* crc = cbc + 64 * (size_t)mcu_w * mcu_h;
-    for (int by = 0; by < mcu_h; ++by)
-        for (int bx = 0; bx < mcu_w; ++bx) {
-            idct_islow(cbc + 64 * ((size_t)by * mcu_w + bx), ts.quant[1], cbp.data() + 8L * by * cpitch + 8 * bx, cpitch);
-            idct_islow(crc + 64 * ((size_t)by * mcu_w + bx), ts.quant[2], crp.data() + 8L * by * cpitch + 8 * bx, cpitch);
-        }
+    const long ypitch = 8L * L.hs * mcu_w, cpitch = 8L * mcu_w;
+    std::vector<uint8_t> yp((size_t)ypitch * 8 * L.vs * mcu_h), cbp((size_t)cpitch * 8 * mcu_h, 128), crp((size_t)cpitch * 8 * mcu_h, 128);
+    for (int by = 0; by < L.vs * mcu_h; ++by)
+        for (int bx = 0; bx < L.hs * mcu_w; ++bx)
+            idct_islow(coef.data() + 64 * ((size_t)by * L.hs * mcu_w + bx), ts.quant[0], yp.data() + 8L * by * ypitch + 8 * bx, ypitch);
+    if (im.ncomp == 3) {
+        const int16_t* cbc = coef.data() + 64 * (size_t)L.nl * L.mcus;
+        const int16_t* crc = cbc + 64 * (size_t)L.mcus;
+        for (int by = 0; by < mcu_h; ++by)
+            for (int bx = 0; bx < mcu_w; ++bx) {
+                idct_islow(cbc + 64 * ((size_t)by * mcu_w + bx), ts.quant[1], cbp.data() + 8L * by * cpitch + 8 * bx, cpitch);
+                idct_islow(crc + 64 * ((size_t)by * mcu_w + bx), ts.quant[2], crp.data() + 8L * by * cpitch + 8 * bx, cpitch);
+            }
+    }
     if ((long)im.h * im.w * 3 > out_cap) return 6;
-    const int cw = (im.w + 1) >> 1, ch = (im.h + 1) >> 1;
+    const int cw = (im.w + L.hs - 1) / L.hs, ch = (im.h + L.vs - 1) / L.vs;
     for (int y = 0; y < im.h; ++y)
-        for (int x = 0; x < im.w; ++x)
-            ycc_to_bgr(yp[(size_t)y * ypitch + x], upsample_h2v2(cbp.data(), cpitch, cw, ch, x, y),
-                       upsample_h2v2(crp.data(), cpitch, cw, ch, x, y), out + ((size_t)y * im.w + x) * 3);
+        for (int x = 0; x < im.w; ++x) {
+            uint8_t* o = out + ((size_t)y * im.w + x) * 3;
+            const int yy = yp[(size_t)y * ypitch + x];
+            if (im.ncomp == 1) { o[0] = o[1] = o[2] = (uint8_t)yy; continue; }
+            ycc_to_bgr(yy, chroma_at(cbp.data(), cpitch, L.hs, L.vs, cw, ch, x, y), chroma_at(crp.data(), cpitch, L.hs, L.vs, cw, ch, x, y), o);
+        }
     return 0;
 }

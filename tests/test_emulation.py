@@ -513,6 +513,14 @@ def test_emu_jpeg_decoder_matches_cv2(emu):
         elif kind == 2:
             img[:] = rng.integers(0, 256, 3, dtype=np.uint8)
         params = [[], [cv2.IMWRITE_JPEG_QUALITY, 100], [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(5, 95))], [cv2.IMWRITE_JPEG_OPTIMIZE, 1]][(i // 4) % 4]
+        # chroma layouts: 4:2:0 (OpenCV's default) mostly, 4:2:2, 4:4:4, greyscale
+        lay = (i // 3) % 5
+        if lay == 3:
+            params = params + [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422]
+        elif lay == 4:
+            params = params + [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+        elif i % 11 == 5:
+            img = np.ascontiguousarray(img[:, :, 0])
         ok, enc = cv2.imencode(".jpg", img, params)
         assert ok
         want = cv2.imdecode(enc, cv2.IMREAD_COLOR)
@@ -541,15 +549,18 @@ def test_emu_jpeg_decoder_self_synchronisation(emu):
 
 
 def test_emu_jpeg_decoder_reports_other_layouts(emu):
-    """Files the device decoder does not take are reported, not approximated: other chroma sampling, progressive, restart
-    markers, greyscale, tiny widths (libjpeg-turbo's upsampler reads its padding there), truncated files, other formats."""
+    """Files the device decoder does not take are reported, not approximated: vertical-only / 4:1:1 chroma sampling,
+    progressive, restart markers, tiny widths of subsampled files (libjpeg-turbo's upsampler reads its padding there),
+    truncated files, other formats."""
     import cv2
     img = synth(8300, 64, 64)
-    for params in ([cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444], [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422],
+    for params in ([cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440], [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411],
                    [cv2.IMWRITE_JPEG_PROGRESSIVE, 1], [cv2.IMWRITE_JPEG_RST_INTERVAL, 4]):
         assert _emu_decode(emu, cv2.imencode(".jpg", img, params)[1].tobytes())[0] == 2, params
-    assert _emu_decode(emu, cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))[1].tobytes())[0] == 2
     assert _emu_decode(emu, cv2.imencode(".jpg", img[:, :4])[1].tobytes())[0] == 2
+    small444 = cv2.imencode(".jpg", img[:3, :2], [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])[1]
+    rc, got = _emu_decode(emu, small444.tobytes())
+    assert rc == 0 and np.array_equal(got, cv2.imdecode(small444, cv2.IMREAD_COLOR))   # no subsampling: any width
     whole = cv2.imencode(".jpg", img)[1].tobytes()
     assert _emu_decode(emu, whole[:len(whole) // 2])[0] == 3        # no EOI behind the scan
     assert _emu_decode(emu, whole[:100])[0] == 1                      # header cut short

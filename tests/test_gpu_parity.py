@@ -1346,6 +1346,12 @@ def test_jpeg_decoder_matches_cv2(torch_):
         kind = i % 3
         img = base if kind == 0 else cv2.GaussianBlur(base, (0, 0), 1.5 + (i % 5)) if kind == 1 else (base // 64) * 85
         params = [[], [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(10, 101))], [cv2.IMWRITE_JPEG_OPTIMIZE, 1]][(i // 3) % 3]
+        if i % 7 == 4:     # 4:2:2, 4:4:4 and greyscale files among the 4:2:0 ones
+            params = params + [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422]
+        elif i % 7 == 5:
+            params = params + [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+        elif i % 7 == 6:
+            img = np.ascontiguousarray(img[:, :, 1])
         enc = cv2.imencode(".jpg", img, params)[1]
         files.append(enc.tobytes())
         want.append(cv2.imdecode(enc, cv2.IMREAD_COLOR))
