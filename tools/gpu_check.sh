@@ -21,6 +21,10 @@ ncu --set full --clock-control none -k regex:'blur|noise|lowres|letterbox|jpeg' 
     -o $out/prof_$tag python tools/profile_ops.py $ops > $out/ncu_full_$tag.log 2>&1
 python tools/time_testset_driver.py 64 > $out/testset_driver_$tag.json 2> $out/testset_driver_$tag.err; echo "driver timing exit $?"
 python tools/time_jpeg.py 64 > $out/time_jpeg_$tag.json 2> $out/time_jpeg_$tag.err; echo "jpeg timing exit $?"
+python tools/time_jpegdec.py 128 > $out/time_jpegdec_$tag.json 2> $out/time_jpegdec_$tag.err; echo "jpeg decoder timing exit $?"
+python tools/time_testset_sharded.py 548 gpu > $out/testset_548_$tag.json 2> $out/testset_548_$tag.err; echo "548-frame trees exit $?"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:jpegdec --csv --log-file $out/jpegdec_launches_$tag.csv \
+    python tools/time_jpegdec.py 128 > /dev/null 2>&1; echo "jpegdec launch list exit $?"
 # gpurun merges back at most 64 MiB: drop the largest report rather than lose everything
 while [ "$(du -sm $out | cut -f1)" -gt 60 ]; do
   big=$(ls -S $out/*.ncu-rep 2>/dev/null | head -1); [ -z "$big" ] && break
