@@ -1390,3 +1390,32 @@ def test_jpeg_decoder_matches_cv2(torch_):
         assert int(st2[0]) in (1, 2) and int(st2[1]) == 0
         off = 3 * shapes[0][0] * shapes[0][1]
         assert np.array_equal(pix2.cpu().numpy()[off:].reshape(shapes[1][0], shapes[1][1], 3), want[1])
+
+
+def test_jpeg_decoder_pitched_destination_guard_bytes(torch_):
+    """The decoder writes image rows at the pitches it is given and nothing else: rows of a pitched destination keep their
+    guard bytes (odd pitches: the colour kernel's 2-byte stores must fall back to byte stores on odd addresses)."""
+    import cv2
+    from robust_object_detection_b200.jpeg import JpegDecoder
+    rng = np.random.default_rng(5)
+    shapes, pads = [(37, 53), (64, 129), (9, 200), (120, 77)], [7, 0, 1, 32]
+    files, want, offs, pitches, cur = [], [], [], [], 3
+    for (h, w), pad in zip(shapes, pads):
+        enc = cv2.imencode(".jpg", cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 1.2))[1]
+        files.append(enc.tobytes())
+        want.append(cv2.imdecode(enc, cv2.IMREAD_COLOR))
+        offs.append(cur)
+        pitches.append(3 * w + pad)
+        cur += h * (3 * w + pad) + 5
+    pix = torch_.full((cur + 16,), 0x5A, dtype=torch_.uint8, device="cuda")
+    dec = JpegDecoder(files, offs, pitches)
+    dec.decode(pix)
+    assert (dec.status() == 0).all()
+    got = pix.cpu().numpy()
+    mask = np.ones(got.size, bool)
+    for (h, w), off, pitch, img in zip(shapes, offs, pitches, want):
+        rows = got[off:off + h * pitch].reshape(h, pitch)
+        assert np.array_equal(rows[:, :3 * w].reshape(h, w, 3), img), (h, w)
+        m = mask[off:off + h * pitch].reshape(h, pitch)
+        m[:, :3 * w] = False
+    assert (got[mask] == 0x5A).all()
