@@ -147,6 +147,117 @@ class CorruptionBatcher:
             k += 1
 
 
+class FileCorruptionBatcher:
+    """The augmented dataloader path from image FILES (BASELINE config 5 as the trainers meet it: Ultralytics' workers
+    start from `cv2.imread`): a batch of JPEG files is read by I/O threads, decoded on the GPU (jpeg.JpegDecoder: the pixels
+    of cv2.imread), corrupted and letterboxed by the fused kernel -- decoded frames never exist in host memory.  Files the
+    device decoder does not take (progressive, PNG, ...) are decoded by the host codec and uploaded into their slot.
+
+        batcher = FileCorruptionBatcher(out_hw=(640, 640), seed=42)
+        for x in batcher.run(batches):      # batches: iterable of lists of paths (or of bytes objects)
+            loss = model(x)                 # x: torch.float16 [B,3,640,640] RGB in [0,1], on the GPU
+
+    Decisions and Philox keying as in CorruptionBatcher: the result equals CorruptionBatcher's on the cv2.imread frames.
+    """
+
+    def __init__(self, out_hw: Tuple[int, int] = (640, 640), pad_value: int = 114, gate: str = "ultralytics",
+                 seed: int = 0, io_threads: int = 16, max_cached_plans: int = 16):
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        self._torch = torch
+        self.out_h, self.out_w = int(out_hw[0]), int(out_hw[1])
+        self.pad_value, self.gate, self.seed = int(pad_value), gate, int(seed)
+        self._plans: dict = {}
+        self._max_plans = max_cached_plans
+        self._pool = ThreadPoolExecutor(max(1, int(io_threads)))
+        self._io_threads = max(1, int(io_threads))
+        self.images_seen = 0
+
+    def _plan(self, shapes) -> CorruptionPlan:
+        key = tuple(shapes)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= self._max_plans:
+                self._plans.pop(next(iter(self._plans)))
+            plan = self._plans[key] = CorruptionPlan.ragged(shapes)
+        return plan
+
+    @staticmethod
+    def _load(item):
+        """I/O thread: (file bytes, (h, w)) for a file the device decoder takes, else (decoded array, (h, w))."""
+        from .jpeg import probe
+        data = item if isinstance(item, (bytes, bytearray, memoryview)) else open(item, "rb").read()
+        shape = probe(data)
+        if shape is not None:
+            return data, shape
+        import cv2
+        arr = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        if arr is None:
+            raise IOError(f"unreadable image: {item if not isinstance(item, (bytes, bytearray, memoryview)) else '<bytes>'}")
+        return arr, (int(arr.shape[0]), int(arr.shape[1]))
+
+    def _submit(self, items):
+        return [self._pool.submit(self._load, it) for it in items]
+
+    def _finish(self, items, futs, ops):
+        torch = self._torch
+        from .jpeg import JpegDecoder
+        loaded = [f.result() for f in futs]
+        shapes = [sh for _, sh in loaded]
+        plan = self._plan(shapes)
+        dev = torch.empty(plan.src_bytes, dtype=torch.uint8, device="cuda")
+        enc = [i for i, (d, _) in enumerate(loaded) if not isinstance(d, np.ndarray)]
+        if enc:
+            dec = JpegDecoder([loaded[i][0] for i in enc], [plan.src_offsets[i] for i in enc], host_threads=self._io_threads)
+            dec.decode(dev)
+        for i, (d, (h, w)) in enumerate(loaded):
+            if isinstance(d, np.ndarray):
+                off = plan.src_offsets[i]
+                dev[off:off + 3 * h * w].copy_(torch.from_numpy(np.ascontiguousarray(d).reshape(-1)))
+        if enc:
+            import cv2
+            for i, st in zip(enc, dec.status()):
+                if st != 0:   # broken entropy-coded data: OpenCV's reading of the file is the reference's answer
+                    arr = cv2.imdecode(np.frombuffer(loaded[i][0], np.uint8), cv2.IMREAD_COLOR)
+                    if arr is None or (int(arr.shape[0]), int(arr.shape[1])) != shapes[i]:
+                        raise IOError("unreadable image in batch")
+                    off = plan.src_offsets[i]
+                    dev[off:off + arr.size].copy_(torch.from_numpy(np.ascontiguousarray(arr).reshape(-1)))
+        n = len(items)
+        if ops is None:
+            ops = draw_decisions(n, gate=self.gate)
+        self.last_ops = np.asarray(ops, dtype=np.uint8)
+        ops_dev = torch.from_numpy(self.last_ops).cuda()
+        out = torch.empty((n, 3, self.out_h, self.out_w), dtype=torch.float16, device="cuda")
+        plan.corrupt_letterbox(dev, ops_dev, out, self.out_h, self.out_w, self.pad_value, seed=self.seed,
+                               first_image_index=self.images_seen)
+        self.images_seen += n
+        return out
+
+    def __call__(self, items: Sequence, ops: Optional[np.ndarray] = None):
+        """One batch of paths / bytes objects -> the fp16 [B,3,H,W] tensor (the drawn op-codes are left in .last_ops)."""
+        return self._finish(items, self._submit(items), ops)
+
+    def run(self, batches: Iterable[Sequence]) -> Iterator:
+        """Pipelined: the files of batch i+1 are read while batch i is decoded, corrupted and letterboxed."""
+        it = iter(batches)
+        try:
+            cur = next(it)
+        except StopIteration:
+            return
+        futs = self._submit(cur)
+        while True:
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            nfuts = self._submit(nxt) if nxt is not None else None
+            yield self._finish(cur, futs, None)
+            if nxt is None:
+                return
+            cur, futs = nxt, nfuts
+
+
 class RestorationPairBatcher:
     """Host-level drop-in for the pair generation of RestorationDataset.__getitem__ (train_restoration.py:104-129), one
     batch at a time: for every decoded frame (HWC BGR uint8; smaller than patch_size: enlarged first like the reference) the decisions are

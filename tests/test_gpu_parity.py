@@ -1419,3 +1419,33 @@ def test_jpeg_decoder_pitched_destination_guard_bytes(torch_):
         m = mask[off:off + h * pitch].reshape(h, pitch)
         m[:, :3 * w] = False
     assert (got[mask] == 0x5A).all()
+
+
+def test_file_batcher_equals_frame_batcher(torch_, tmp_path):
+    """FileCorruptionBatcher (JPEG files -> device decoder -> fused corrupt + letterbox) gives the tensor CorruptionBatcher
+    gives for the cv2.imread frames of the same files, under the same random seed -- including a PNG and a progressive
+    JPEG, which go through the host codec, and a file passed as bytes."""
+    import random
+    import cv2
+    from robust_object_detection_b200.training import CorruptionBatcher, FileCorruptionBatcher
+    rng = np.random.default_rng(12)
+    shapes = [(765, 1360), (540, 960), (360, 480), (97, 133), (300, 180), (788, 1400)]
+    paths = []
+    for i, (h, w) in enumerate(shapes):
+        img = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 1.0 + i % 3)
+        p = tmp_path / (f"f{i}.png" if i == 3 else f"f{i}.jpg")
+        cv2.imwrite(str(p), img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1] if i == 4 else [])
+        paths.append(str(p))
+    frames = [cv2.imread(p) for p in paths]
+    batches = [paths[:3], paths[3:], [open(paths[0], "rb").read(), paths[5]]]
+    frame_batches = [frames[:3], frames[3:], [frames[0], frames[5]]]
+    random.seed(42)
+    want = [x.cpu().numpy() for x in CorruptionBatcher(out_hw=(160, 160), seed=9).run(frame_batches)]
+    random.seed(42)
+    fb = FileCorruptionBatcher(out_hw=(160, 160), seed=9, io_threads=4)
+    got = [x.cpu().numpy() for x in fb.run(batches)]
+    assert len(got) == 3 and all(np.array_equal(g, w) for g, w in zip(got, want))
+    random.seed(42)
+    assert np.array_equal(FileCorruptionBatcher(out_hw=(160, 160), seed=9)(batches[0]).cpu().numpy(), want[0])
+    with pytest.raises(IOError):
+        fb([b"not an image"])
