@@ -307,6 +307,12 @@ class RestorationPairBatcher:
             dec.append((y, x, flip, op))
         self.last_decisions = dec
         src = hbuf.cuda()  # (synchronous for the host: the pinned crop buffer is rewritten by the next call)
+        return self._pairs(plan, src, dec, fields)
+
+    def _pairs(self, plan, src, dec, fields):
+        """src: the n crops back to back on the device; dec: (y, x, flip, op) per sample; fields: compat noise fields"""
+        from .augmentations import NOISE_SIGMA
+        torch, P, n = self._torch, self.size, len(dec)
         flips = torch.tensor([int(d[2]) for d in dec], dtype=torch.uint8).cuda()
         ops = torch.tensor([d[3] for d in dec], dtype=torch.uint8).cuda()
         nz = None
@@ -322,3 +328,57 @@ class RestorationPairBatcher:
                                first_image_index=self.samples_seen)
         self.samples_seen += n
         return corrupted, clean
+
+    def from_files(self, items: Sequence, io_threads: int = 8):
+        """The same pairs starting from image files (`cv2.imread(str(path))`, train_restoration.py:105): paths or bytes
+        objects are read on I/O threads, decoded on the GPU (jpeg.JpegDecoder: the pixels of cv2.imread; other layouts
+        through the host codec), cropped on the device.  Equals __call__([cv2.imread(p) for p in items]) under the same
+        `random` / `np.random` state."""
+        from concurrent.futures import ThreadPoolExecutor
+        from . import _native as N
+        from .augmentations import NOISE_SIGMA, legacy_normal_f32
+        from .batch import _ptr, _stream_handle, draw_restoration_decisions
+        from .jpeg import JpegDecoder
+        torch, P, n = self._torch, self.size, len(items)
+        with ThreadPoolExecutor(max(1, min(int(io_threads), n))) as pool:
+            loaded = list(pool.map(FileCorruptionBatcher._load, items))
+        shapes = [sh for _, sh in loaded]
+        fplan = CorruptionPlan.ragged(shapes)
+        dev = torch.empty(fplan.src_bytes, dtype=torch.uint8, device="cuda")
+        enc = [i for i, (d, _) in enumerate(loaded) if not isinstance(d, np.ndarray)]
+        if enc:
+            dec_ = JpegDecoder([loaded[i][0] for i in enc], [fplan.src_offsets[i] for i in enc], host_threads=io_threads)
+            dec_.decode(dev)
+        for i, (d, (h, w)) in enumerate(loaded):
+            if isinstance(d, np.ndarray):
+                dev[fplan.src_offsets[i]:fplan.src_offsets[i] + 3 * h * w].copy_(torch.from_numpy(np.ascontiguousarray(d).reshape(-1)))
+        if enc:
+            import cv2
+            for i, st in zip(enc, dec_.status()):
+                if st != 0:
+                    arr = cv2.imdecode(np.frombuffer(loaded[i][0], np.uint8), cv2.IMREAD_COLOR)
+                    if arr is None or (int(arr.shape[0]), int(arr.shape[1])) != shapes[i]:
+                        raise IOError("unreadable image in batch")
+                    dev[fplan.src_offsets[i]:fplan.src_offsets[i] + arr.size].copy_(torch.from_numpy(np.ascontiguousarray(arr).reshape(-1)))
+        if n not in self._plans:
+            offs = [i * 3 * P * P for i in range(n)]
+            self._plans[n] = (CorruptionPlan([(P, P)] * n, offs, [0] * n), torch.empty(n * 3 * P * P, dtype=torch.uint8).pin_memory())
+        plan = self._plans[n][0]
+        crops = torch.empty((n, P, P, 3), dtype=torch.uint8, device="cuda")
+        dec, fields = [], []
+        for i, (h, w) in enumerate(shapes):
+            frame = dev[fplan.src_offsets[i]:fplan.src_offsets[i] + 3 * h * w].view(h, w, 3)
+            if h < P or w < P:  # the reference enlarges such a frame first (train_restoration.py:79-81)
+                nh, nw = max(h, P), max(w, P)
+                big = torch.empty((nh, nw, 3), dtype=torch.uint8, device="cuda")
+                N.check(N.lib().rod_resize_linear_u8(_ptr(frame), h, w, 3 * w, _ptr(big), nh, nw, 3 * nw, _stream_handle()), "rod_resize_linear_u8")
+                frame, h, w = big, nh, nw
+            y, x, flip, op = draw_restoration_decisions(h, w, P, self.is_train)
+            crops[i].copy_(frame[y:y + P, x:x + P])
+            if op == 1 and self.noise == "compat":
+                fields.append(legacy_normal_f32(NOISE_SIGMA, (P, P, 3)).reshape(-1))
+            elif self.noise == "compat":
+                fields.append(None)
+            dec.append((y, x, flip, op))
+        self.last_decisions = dec
+        return self._pairs(plan, crops.reshape(-1), dec, fields)

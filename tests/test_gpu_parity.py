@@ -1449,3 +1449,31 @@ def test_file_batcher_equals_frame_batcher(torch_, tmp_path):
     assert np.array_equal(FileCorruptionBatcher(out_hw=(160, 160), seed=9)(batches[0]).cpu().numpy(), want[0])
     with pytest.raises(IOError):
         fb([b"not an image"])
+
+
+def test_restoration_pairs_from_files(torch_, tmp_path):
+    """RestorationPairBatcher.from_files (files -> device JPEG decoder -> crops on the device) equals the batcher on the
+    cv2.imread frames under the same seeds, incl. a frame smaller than the patch (resize-first branch) and a PNG."""
+    import random
+    import cv2
+    from robust_object_detection_b200.training import RestorationPairBatcher
+    rng = np.random.default_rng(13)
+    shapes = [(300, 400), (765, 1360), (200, 180), (97, 300), (256, 256), (540, 960)]
+    paths = []
+    for i, (h, w) in enumerate(shapes):
+        p = tmp_path / (f"r{i}.png" if i == 4 else f"r{i}.jpg")
+        cv2.imwrite(str(p), cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 1.5))
+        paths.append(str(p))
+    frames = [cv2.imread(p) for p in paths]
+    for is_train in (True, False):
+        for noise in ("compat", "philox"):
+            random.seed(7)
+            np.random.seed(7)
+            a = RestorationPairBatcher(patch_size=256, is_train=is_train, noise=noise, seed=3)
+            want = a(frames)
+            random.seed(7)
+            np.random.seed(7)
+            b = RestorationPairBatcher(patch_size=256, is_train=is_train, noise=noise, seed=3)
+            got = b.from_files(paths)
+            assert a.last_decisions == b.last_decisions
+            assert torch_.equal(got[0], want[0]) and torch_.equal(got[1], want[1]), (is_train, noise)
