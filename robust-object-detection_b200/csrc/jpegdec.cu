@@ -17,7 +17,7 @@
 //                                    order, per-component block rasters; DC as the difference)
 //             jpegdec_dc_kernel      DC prediction = prefix sum of the differences per component in MCU order
 //           jpegdec_idct_kernel      one thread per 8x8 block: dequantisation + islow IDCT in registers -> Y / Cb / Cr planes
-//           jpegdec_color_kernel     one thread per two output pixels: fancy chroma upsampling + YCbCr -> BGR, written
+//           jpegdec_color_kernel     one thread per four output pixels: fancy chroma upsampling + YCbCr -> BGR, written
 //                                    straight into the caller's HWC batch (the layout of a rod_plan)
 // Files of another layout (progressive, restart markers, EXIF rotation, CMYK ...) are reported per image; the caller
 // decodes those with the host codec.  No CPU decoding in here.
@@ -41,7 +41,7 @@ struct JpegDecParams {
     uint8_t* pixels;
     int32_t* status;
     const uint32_t* block_start;   // [n + 1] prefix sums of the number of blocks
-    const uint32_t* pair_start;    // [n + 1] prefix sums of h * ceil(w / 2)
+    const uint32_t* quad_start;    // [n + 1] prefix sums of h * ceil(w / 4)
     const uint32_t* sub_start;     // [n + 1] prefix sums of the number of subsequences
     const uint2* ctas;             // Huffman kernels: CTA -> (image, first subsequence of the image it covers)
     uint64_t* end_state;           // E[subsequence]
@@ -253,37 +253,58 @@ __global__ void __launch_bounds__(128) jpegdec_idct_kernel(JpegDecParams p) {
 
 __global__ void __launch_bounds__(256) jpegdec_color_kernel(JpegDecParams p) {
     const uint32_t gi = blockIdx.x * 256u + threadIdx.x;
-    if (gi >= __ldg(p.pair_start + p.n_images)) return;
-    const int img = owner_of(p.pair_start, p.n_images, gi);
+    if (gi >= __ldg(p.quad_start + p.n_images)) return;
+    const int img = owner_of(p.quad_start, p.n_images, gi);
     const ImageRec im = p.images[img];
     if (__ldg(p.status + img) != 0) return;
-    const uint32_t k = gi - __ldg(p.pair_start + img);
+    const uint32_t k = gi - __ldg(p.quad_start + img);
     const Layout L = layout_of(im);
-    const int pw = (im.w + 1) >> 1;   // pixel pairs per row
+    const int qw = (im.w + 3) >> 2;   // groups of four pixels per row
     const int cw = (im.w + L.hs - 1) / L.hs, ch = (im.h + L.vs - 1) / L.vs;
-    const int y = (int)(k / (uint32_t)pw), cx = (int)(k - (uint32_t)y * (uint32_t)pw);
+    const int y = (int)(k / (uint32_t)qw), x0 = 4 * (int)(k - (uint32_t)y * (uint32_t)qw);
     const long ypitch = 8L * L.hs * L.mcu_w, cpitch = 8L * L.mcu_w;
     const uint8_t* yp = p.planes + im.plane_off;
     const uint8_t* cbp = yp + 64L * L.nl * L.mcus;
     const uint8_t* crp = cbp + 64L * L.mcus;
-    uint8_t* out = p.pixels + im.dst_off + (int64_t)y * im.dst_pitch + 6 * cx;
-    const int x = 2 * cx;
-    uint8_t px[6];
-    auto pixel = [&](int xx, uint8_t* o) {
-        const int yy = yp[y * ypitch + xx];
-        if (im.ncomp == 1) { o[0] = o[1] = o[2] = (uint8_t)yy; return; }
-        ycc_to_bgr(yy, chroma_at(cbp, cpitch, L.hs, L.vs, cw, ch, xx, y), chroma_at(crp, cpitch, L.hs, L.vs, cw, ch, xx, y), o);
-    };
-    pixel(x, px);
-    const bool two = x + 1 < im.w;
-    if (two) pixel(x + 1, px + 3);
-    if (two && ((uintptr_t)out & 1) == 0) {   // 6 bytes at a 2-byte aligned address
-        uint16_t* o2 = reinterpret_cast<uint16_t*>(out);
-        o2[0] = (uint16_t)(px[0] | (px[1] << 8));
-        o2[1] = (uint16_t)(px[2] | (px[3] << 8));
-        o2[2] = (uint16_t)(px[4] | (px[5] << 8));
+    uint8_t* out = p.pixels + im.dst_off + (int64_t)y * im.dst_pitch + 3 * x0;
+    const int nv = min(4, im.w - x0);
+    const uint32_t y4 = *reinterpret_cast<const uint32_t*>(yp + y * ypitch + x0);   // (the plane is padded to whole blocks)
+    uint32_t w[3] = {0u, 0u, 0u};   // the twelve output bytes
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int xx = min(x0 + i, im.w - 1), yy = (int)((y4 >> (8 * i)) & 0xFFu);
+        uint8_t t[3];
+        if (im.ncomp == 1) t[0] = t[1] = t[2] = (uint8_t)yy;
+        else ycc_to_bgr(yy, chroma_at(cbp, cpitch, L.hs, L.vs, cw, ch, xx, y), chroma_at(crp, cpitch, L.hs, L.vs, cw, ch, xx, y), t);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) w[(3 * i + c) >> 2] |= (uint32_t)t[c] << (8 * ((3 * i + c) & 3));
+    }
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    if (nv < 4) {
+        for (int i = 0; i < 3 * nv; ++i) out[i] = (uint8_t)((i < 4 ? w0 : (i < 8 ? w1 : w2)) >> (8 * (i & 3)));
+        return;
+    }
+    const uint32_t a = (uint32_t)((uintptr_t)out & 3u);
+    if (a == 0) {   // twelve bytes as aligned words, whatever the row's byte phase is
+        uint32_t* o = reinterpret_cast<uint32_t*>(out);
+        o[0] = w0; o[1] = w1; o[2] = w2;
+    } else if (a == 2) {
+        *reinterpret_cast<uint16_t*>(out) = (uint16_t)w0;
+        uint32_t* o = reinterpret_cast<uint32_t*>(out + 2);
+        o[0] = __funnelshift_r(w0, w1, 16); o[1] = __funnelshift_r(w1, w2, 16);
+        *reinterpret_cast<uint16_t*>(out + 10) = (uint16_t)(w2 >> 16);
+    } else if (a == 1) {
+        out[0] = (uint8_t)w0;
+        *reinterpret_cast<uint16_t*>(out + 1) = (uint16_t)(w0 >> 8);
+        uint32_t* o = reinterpret_cast<uint32_t*>(out + 3);
+        o[0] = __funnelshift_r(w0, w1, 24); o[1] = __funnelshift_r(w1, w2, 24);
+        out[11] = (uint8_t)(w2 >> 24);
     } else {
-        for (int i = 0; i < (two ? 6 : 3); ++i) out[i] = px[i];
+        out[0] = (uint8_t)w0;
+        uint32_t* o = reinterpret_cast<uint32_t*>(out + 1);
+        o[0] = __funnelshift_r(w0, w1, 8); o[1] = __funnelshift_r(w1, w2, 8);
+        *reinterpret_cast<uint16_t*>(out + 9) = (uint16_t)(w2 >> 8);
+        out[11] = (uint8_t)(w2 >> 24);
     }
 }
 
@@ -329,14 +350,14 @@ struct rod_jpeg_decoder {
     std::vector<ImageRec> h_images;
     std::vector<int32_t> h_status;       // host verdict per image: 0 decodable, else 10 + ParseStatus / 13 (no EOI)
     std::vector<TableSet> h_tables;
-    std::vector<uint32_t> h_block_start, h_pair_start, h_sub_start;
+    std::vector<uint32_t> h_block_start, h_quad_start, h_sub_start;
     std::vector<uint2> h_ctas;
     uint8_t* h_streams = nullptr;        // page-locked
     size_t stream_bytes = 0, coef_elems = 0, plane_bytes = 0;
     ImageRec* d_images = nullptr;
     TableSet* d_tables = nullptr;
     uint32_t* d_block_start = nullptr;
-    uint32_t* d_pair_start = nullptr;
+    uint32_t* d_quad_start = nullptr;
     uint32_t* d_sub_start = nullptr;
     uint2* d_ctas = nullptr;
     unsigned int* d_changed = nullptr;
@@ -364,7 +385,7 @@ extern "C" int rod_jpegdec_probe(const uint8_t* file, uint64_t n, int* height, i
 
 extern "C" void rod_jpegdec_destroy(rod_jpeg_decoder* d) {
     if (d == nullptr) return;
-    void* small[] = {d->d_images, d->d_tables, d->d_block_start, d->d_pair_start, d->d_status, d->d_sub_start, d->d_ctas, d->d_changed};
+    void* small[] = {d->d_images, d->d_tables, d->d_block_start, d->d_quad_start, d->d_status, d->d_sub_start, d->d_ctas, d->d_changed};
     for (void* q : small)
         if (q) cudaFree(q);
     block_cache_free(d->device, d->d_streams, d->stream_bytes);
@@ -425,9 +446,9 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
     // shared table sets, buffer layout
     std::map<std::string, int> seen;
     d->h_block_start.assign(n_images + 1, 0);
-    d->h_pair_start.assign(n_images + 1, 0);
+    d->h_quad_start.assign(n_images + 1, 0);
     d->h_sub_start.assign(n_images + 1, 0);
-    uint64_t blocks = 0, pairs = 0, subs = 0;
+    uint64_t blocks = 0, quads = 0, subs = 0;
     for (int i = 0; i < n_images; ++i) {
         ImageRec& im = d->h_images[i];
         if (d->h_status[i] == 0) {
@@ -445,17 +466,17 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
             d->coef_elems += nblocks * 64;
             d->plane_bytes += nblocks * 64;
             blocks += nblocks;
-            pairs += (uint64_t)im.h * (uint64_t)((im.w + 1) >> 1);
+            quads += (uint64_t)im.h * (uint64_t)((im.w + 3) >> 2);
             const uint32_t n_sub = im.stream_bytes ? (8u * im.stream_bytes + kSubBits - 1) / kSubBits : 1u;
             for (uint32_t s0 = 0; s0 < n_sub; s0 += kHuffThreads) d->h_ctas.push_back(make_uint2((unsigned)i, s0));
             subs += n_sub;
         }
         d->h_sub_start[i + 1] = (uint32_t)subs;
         d->h_block_start[i + 1] = (uint32_t)blocks;
-        d->h_pair_start[i + 1] = (uint32_t)pairs;
+        d->h_quad_start[i + 1] = (uint32_t)quads;
     }
     d->n_sub = (size_t)subs;
-    if (blocks >= (1ull << 32) || pairs >= (1ull << 32) || subs >= (1ull << 32)) { rod_jpegdec_destroy(d); return ROD_ERR_UNSUPPORTED; }
+    if (blocks >= (1ull << 32) || quads >= (1ull << 32) || subs >= (1ull << 32)) { rod_jpegdec_destroy(d); return ROD_ERR_UNSUPPORTED; }
     if (d->h_tables.empty()) d->h_tables.push_back(TableSet{});
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void** p, size_t n) { if (err == cudaSuccess) err = cudaMalloc(p, n ? n : 16); };
@@ -463,7 +484,7 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
     alloc((void**)&d->d_images, sizeof(ImageRec) * n_images);
     alloc((void**)&d->d_tables, sizeof(TableSet) * d->h_tables.size());
     alloc((void**)&d->d_block_start, sizeof(uint32_t) * (n_images + 1));
-    alloc((void**)&d->d_pair_start, sizeof(uint32_t) * (n_images + 1));
+    alloc((void**)&d->d_quad_start, sizeof(uint32_t) * (n_images + 1));
     alloc((void**)&d->d_status, sizeof(int32_t) * n_images);
     alloc((void**)&d->d_sub_start, sizeof(uint32_t) * (n_images + 1));
     alloc((void**)&d->d_ctas, sizeof(uint2) * d->h_ctas.size());
@@ -499,7 +520,7 @@ extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* st
     ROD_CUDA(cudaMemcpyAsync(d->d_images, d->h_images.data(), sizeof(ImageRec) * n, cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_tables, d->h_tables.data(), sizeof(TableSet) * d->h_tables.size(), cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_block_start, d->h_block_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
-    ROD_CUDA(cudaMemcpyAsync(d->d_pair_start, d->h_pair_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    ROD_CUDA(cudaMemcpyAsync(d->d_quad_start, d->h_quad_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_status, d->h_status.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_sub_start, d->h_sub_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
     if (!d->h_ctas.empty())
@@ -509,7 +530,7 @@ extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* st
     ROD_CUDA(cudaMemsetAsync(d->d_coef, 0, d->coef_elems * sizeof(int16_t), st));
     JpegDecParams p;
     p.images = d->d_images; p.tables = d->d_tables; p.streams = d->d_streams; p.coef = d->d_coef; p.planes = d->d_planes;
-    p.pixels = pixels; p.status = d->d_status; p.block_start = d->d_block_start; p.pair_start = d->d_pair_start;
+    p.pixels = pixels; p.status = d->d_status; p.block_start = d->d_block_start; p.quad_start = d->d_quad_start;
     p.sub_start = d->d_sub_start; p.ctas = d->d_ctas; p.end_state = d->d_end_state; p.used_start = d->d_used_start;
     p.first_block = d->d_first_block; p.changed = d->d_changed;
     p.n_images = n;
@@ -529,9 +550,9 @@ extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* st
     jpegdec_scan_kernel<<<n, 256, 0, st>>>(p);
     jpegdec_write_kernel<<<n_ctas, kHuffThreads, 0, st>>>(p);
     jpegdec_dc_kernel<<<dim3(n, 3), 256, 0, st>>>(p);
-    const uint32_t blocks = d->h_block_start[n], pairs = d->h_pair_start[n];
+    const uint32_t blocks = d->h_block_start[n], quads = d->h_quad_start[n];
     jpegdec_idct_kernel<<<(blocks + 127) / 128, 128, 0, st>>>(p);
-    jpegdec_color_kernel<<<(pairs + 255) / 256, 256, 0, st>>>(p);
+    jpegdec_color_kernel<<<(quads + 255) / 256, 256, 0, st>>>(p);
     ROD_CUDA(cudaGetLastError());
     return ROD_OK;
 }
