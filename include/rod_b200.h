@@ -195,10 +195,10 @@ ROD_API int rod_jpeg_download(rod_jpeg_encoder* enc, uint8_t* host_out, uint32_t
 
 /* SURVEY 8f rank 1, the reading side -- `img = cv2.imread(str(img_path))` (scripts/build_corrupted_testsets.py:109, :149)
  * for a batch of files: baseline JPEG decoding whose pixels equal OpenCV 4.13.0's (libjpeg-turbo defaults: islow IDCT, fancy
- * h2v2 chroma upsampling, BGR output) straight into a device-resident HWC batch.  Decodable here: baseline sequential,
- * 8 bit, Y Cb Cr sampled 2x2 / 1x1 / 1x1 in one interleaved scan, no restart markers, no EXIF rotation, width >= 5 --
- * what OpenCV's own encoder writes.  Every other file is REPORTED (status >= 10), never approximated: the caller reads it
- * with the host codec.
+ * chroma upsampling, BGR output) straight into a device-resident HWC batch.  Decodable here: baseline sequential, 8 bit,
+ * one scan without restart markers, no EXIF rotation, either Y Cb Cr with the luma sampled 2x2 (4:2:0, what OpenCV's own
+ * encoder writes), 2x1 (4:2:2) or 1x1 (4:4:4) against 1x1 chroma, or greyscale; subsampled files need width >= 5.  Every
+ * other file is REPORTED (status >= 10), never approximated: the caller reads it with the host codec.
  *   rod_jpegdec_probe        host only: ROD_OK + (height, width) when the device decoder takes the file, else
  *                            ROD_ERR_UNSUPPORTED
  *   rod_jpegdec_create       host work for a batch (markers, tables, scans without byte stuffing into page-locked memory,
@@ -206,7 +206,8 @@ ROD_API int rod_jpeg_download(rod_jpeg_encoder* enc, uint8_t* host_out, uint32_t
  *                            dst_pitches[i] bytes (NULL or 0: 3 * width)
  *   rod_jpegdec_host_status  the verdict of create per image (0: decodable; 11: not a JPEG; 12: unsupported layout;
  *                            13: scan does not end in EOI) and the sizes of the decodable ones
- *   rod_jpegdec_decode       upload + Huffman decoding + IDCT + upsampling / colour conversion, asynchronous on `stream`
+ *   rod_jpegdec_decode       upload + Huffman decoding + IDCT + upsampling / colour conversion on `stream`; returns when the
+ *                            Huffman stage has synchronised (a few host round trips), the rest is asynchronous
  *   rod_jpegdec_status       waits for `stream`; per image 0: decoded; 1 / 2: corrupt / truncated entropy data (pixels
  *                            undefined); >= 10: as above */
 typedef struct rod_jpeg_decoder rod_jpeg_decoder;

@@ -133,8 +133,8 @@ class JpegDecoder:
     given to decode(), row pitch 3 * width unless `pitches` says otherwise -- the layout of a CorruptionPlan built from
     `shapes`.  The constructor does the host work (markers, Huffman tables, scans copied without their byte stuffing into
     page-locked memory, on `host_threads` threads); `shapes[i]` is (h, w), or None where the device decoder does not take
-    the file (progressive, other chroma sampling, restart markers, EXIF rotation, not a JPEG ...): the caller reads those
-    with the host codec.  No CPU decoding inside."""
+    the file (it takes baseline 4:2:0 / 4:2:2 / 4:4:4 / greyscale files; not: progressive, restart markers, EXIF rotation,
+    CMYK, not a JPEG ...): the caller reads those with the host codec.  No CPU decoding inside."""
 
     def __init__(self, files: Sequence, offsets: Sequence[int], pitches: Optional[Sequence[int]] = None, host_threads: int = 8):
         N.require_device()
@@ -165,7 +165,8 @@ class JpegDecoder:
             self._h = None
 
     def decode(self, pixels, stream=None) -> None:
-        """Asynchronous on `stream` (default: torch's current stream): pixels (CUDA uint8 tensor) receives the images."""
+        """On `stream` (default: torch's current stream): pixels (CUDA uint8 tensor) receives the images.  Returns when the
+        Huffman stage has synchronised (a few host round trips); IDCT and colour conversion are still in flight."""
         N.check(N.lib().rod_jpegdec_decode(self._h, _ptr(pixels), _stream_handle(stream)), "rod_jpegdec_decode")
 
     def status(self, stream=None) -> np.ndarray:
