@@ -306,3 +306,31 @@ def test_numpy_legacy_normal_random_call_sequences():
         assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]
 
     run()
+
+
+def test_jpeg_probe_through_the_c_abi(built):
+    """rod_jpegdec_probe is host code (no device needed): the frame size for the layouts the device decoder takes, None
+    for the ones it reports (the driver then reads the file with cv2.imread)."""
+    import cv2
+    from robust_object_detection_b200.jpeg import probe
+    rng = np.random.default_rng(21)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
+    for params in ([], [cv2.IMWRITE_JPEG_QUALITY, 30], [cv2.IMWRITE_JPEG_OPTIMIZE, 1], [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422],
+                   [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]):
+        assert probe(cv2.imencode(".jpg", img, params)[1].tobytes()) == (37, 53), params
+    assert probe(cv2.imencode(".jpg", img[:, :, 0])[1].tobytes()) == (37, 53)
+    for params in ([cv2.IMWRITE_JPEG_PROGRESSIVE, 1], [cv2.IMWRITE_JPEG_RST_INTERVAL, 2], [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440],
+                   [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]):
+        assert probe(cv2.imencode(".jpg", img, params)[1].tobytes()) is None, params
+    assert probe(cv2.imencode(".jpg", img[:, :4])[1].tobytes()) is None           # subsampled and narrower than 5 pixels
+    assert probe(cv2.imencode(".png", img)[1].tobytes()) is None
+    assert probe(b"") is None and probe(b"\xff\xd8\xff") is None
+    # EXIF orientation other than 1 (cv2.imread rotates such files): spliced in as an APP1 segment behind SOI
+    base = cv2.imencode(".jpg", img)[1].tobytes()
+    def exif(orientation):
+        tiff = b"II*\x00\x08\x00\x00\x00" + b"\x01\x00" + b"\x12\x01\x03\x00\x01\x00\x00\x00" + bytes([orientation, 0, 0, 0]) + b"\x00\x00\x00\x00"
+        body = b"Exif\x00\x00" + tiff
+        return base[:2] + b"\xff\xe1" + (len(body) + 2).to_bytes(2, "big") + body + base[2:]
+    assert probe(exif(1)) == (37, 53)
+    assert probe(exif(6)) is None
