@@ -196,7 +196,7 @@ ROD_API int rod_jpeg_download(rod_jpeg_encoder* enc, uint8_t* host_out, uint32_t
 /* SURVEY 8f rank 1, the reading side -- `img = cv2.imread(str(img_path))` (scripts/build_corrupted_testsets.py:109, :149)
  * for a batch of files: baseline JPEG decoding whose pixels equal OpenCV 4.13.0's (libjpeg-turbo defaults: islow IDCT, fancy
  * chroma upsampling, BGR output) straight into a device-resident HWC batch.  Decodable here: baseline sequential, 8 bit,
- * one scan without restart markers, no EXIF rotation, either Y Cb Cr with the luma sampled 2x2 (4:2:0, what OpenCV's own
+ * one scan (restart markers are fine), no EXIF rotation, either Y Cb Cr with the luma sampled 2x2 (4:2:0, what OpenCV's own
  * encoder writes), 2x1 (4:2:2) or 1x1 (4:4:4) against 1x1 chroma, or greyscale; subsampled files need width >= 5.  Every
  * other file is REPORTED (status >= 10), never approximated: the caller reads it with the host codec.
  *   rod_jpegdec_probe        host only: ROD_OK + (height, width) when the device decoder takes the file, else

@@ -7,7 +7,7 @@ written with cv2.imwrite under the same file name; labels / annotations are copi
 and so does the JPEG codec on both sides of it.  JPEG DECODING (`DECODER = "gpu"`: rod_jpegdec_decode, libjpeg-turbo's
 Huffman decoding / islow IDCT / fancy upsampling / colour conversion restated in CUDA, pixels identical to cv2.imread's): the
 I/O threads only read the files; a file of a layout the device decoder does not take (progressive, other chroma sampling,
-restart markers, EXIF rotation, PNG ...) is read with cv2.imread like the reference does.  A tree's decoded batches stay on
+EXIF rotation, CMYK, PNG ...) is read with cv2.imread like the reference does.  A tree's decoded batches stay on
 the device for its four variants.  `DECODER = "host"` decodes with cv2.imread on the I/O threads (the next batch decodes
 while a batch is on the GPU; a tree's decoded frames are reused by its four variants).  JPEG ENCODING runs on the GPU too
 (`ENCODER = "gpu"`: rod_jpeg_encode, libjpeg-turbo's integer algorithms restated in CUDA, the header bytes taken from

@@ -19,7 +19,7 @@
 //           jpegdec_idct_kernel      one thread per 8x8 block: dequantisation + islow IDCT in registers -> Y / Cb / Cr planes
 //           jpegdec_color_kernel     one thread per four output pixels: fancy chroma upsampling + YCbCr -> BGR, written
 //                                    straight into the caller's HWC batch (the layout of a rod_plan)
-// Files of another layout (progressive, restart markers, EXIF rotation, CMYK ...) are reported per image; the caller
+// Files of another layout (progressive, EXIF rotation, CMYK, 4:1:1 ...) are reported per image; the caller
 // decodes those with the host codec.  No CPU decoding in here.
 #include <map>
 #include <string>
@@ -42,8 +42,10 @@ struct JpegDecParams {
     int32_t* status;
     const uint32_t* block_start;   // [n + 1] prefix sums of the number of blocks
     const uint32_t* quad_start;    // [n + 1] prefix sums of h * ceil(w / 4)
-    const uint32_t* sub_start;     // [n + 1] prefix sums of the number of subsequences
-    const uint2* ctas;             // Huffman kernels: CTA -> (image, first subsequence of the image it covers)
+    const SegRec* segs;            // restart intervals of all images (an image without restart markers: one)
+    const uint32_t* sub_start;     // [n_segs + 1] prefix sums of the number of subsequences
+    const uint2* ctas;             // Huffman kernels: CTA -> (segment, first subsequence of the segment it covers)
+    int n_segs;
     uint64_t* end_state;           // E[subsequence]
     uint64_t* used_start;          // U[subsequence]: the start state E was computed from
     uint32_t* first_block;         // [subsequence] global block index its first symbol belongs to
@@ -73,14 +75,16 @@ __global__ void __launch_bounds__(kHuffThreads) jpegdec_guess_kernel(JpegDecPara
     __shared__ TableSet ts;
     __shared__ uint8_t nat[64];
     const uint2 c = p.ctas[blockIdx.x];
-    const ImageRec im = p.images[c.x];
+    const SegRec sg = p.segs[c.x];
+    const ImageRec im = p.images[sg.image];
     load_tables(&ts, nat, p.tables + im.table_set);
     const uint32_t s = c.y + threadIdx.x, n_sub = p.sub_start[c.x + 1] - p.sub_start[c.x];
     if (s >= n_sub) return;
-    const uint32_t gs = p.sub_start[c.x] + s;
-    const uint64_t u = span_state(s * kSubBits, 0, 0, 0);
+    const uint32_t gs = p.sub_start[c.x] + s, bit0 = 8u * sg.byte0;
+    const uint64_t u = span_state(bit0 + s * kSubBits, 0, 0, 0);
     p.used_start[gs] = u;
-    p.end_state[gs] = decode_span<false>(im, ts, nat, p.streams + im.stream_off, u, (s + 1) * kSubBits, nullptr, 0, 0, nullptr);
+    p.end_state[gs] = decode_span<false>(layout_of(im), sg.stream_bytes, ts, nat, p.streams + sg.stream_off, u, bit0 + (s + 1) * kSubBits,
+                                         nullptr, 0, 0, nullptr);
 }
 
 __global__ void __launch_bounds__(kHuffThreads) jpegdec_sync_kernel(JpegDecParams p, int flag_slot) {
@@ -96,13 +100,17 @@ __global__ void __launch_bounds__(kHuffThreads) jpegdec_sync_kernel(JpegDecParam
         st = state_start(ld_volatile64(p.end_state + gs - 1));
     }
     if (!__syncthreads_or(mine && st != u)) return;   // nothing to do for this CTA: the tables are not even loaded
-    const ImageRec im = p.images[c.x];
+    const SegRec sg = p.segs[c.x];
+    const ImageRec im = p.images[sg.image];
     load_tables(&ts, nat, p.tables + im.table_set);
     if (!mine) return;
+    const Layout L = layout_of(im);
+    const uint32_t bit0 = 8u * sg.byte0;
     bool changed = false;
     for (int it = 0; it < 8 && st != u; ++it) {
         u = st;
-        st_volatile64(p.end_state + gs, decode_span<false>(im, ts, nat, p.streams + im.stream_off, u, (s + 1) * kSubBits, nullptr, 0, 0, nullptr));
+        st_volatile64(p.end_state + gs, decode_span<false>(L, sg.stream_bytes, ts, nat, p.streams + sg.stream_off, u, bit0 + (s + 1) * kSubBits,
+                                                           nullptr, 0, 0, nullptr));
         changed = true;
         st = state_start(ld_volatile64(p.end_state + gs - 1));   // the predecessor may have moved on meanwhile
     }
@@ -112,14 +120,12 @@ __global__ void __launch_bounds__(kHuffThreads) jpegdec_sync_kernel(JpegDecParam
     }
 }
 
-// exclusive prefix sum of the block counts of an image's subsequences; too few blocks in total: truncated data
+// exclusive prefix sum of the block counts of a segment's subsequences; too few blocks in total: truncated data
 __global__ void __launch_bounds__(256) jpegdec_scan_kernel(JpegDecParams p) {
     __shared__ uint32_t warp_sum[8];
     __shared__ uint32_t carry_s;
-    const int img = blockIdx.x;
-    const ImageRec im = p.images[img];
-    if (im.h == 0) return;
-    const uint32_t s0 = p.sub_start[img], n_sub = p.sub_start[img + 1] - s0;
+    const int seg = blockIdx.x;
+    const uint32_t s0 = p.sub_start[seg], n_sub = p.sub_start[seg + 1] - s0;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     for (uint32_t base = 0; base < n_sub; base += 256) {
@@ -141,8 +147,8 @@ __global__ void __launch_bounds__(256) jpegdec_scan_kernel(JpegDecParams p) {
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const Layout L = layout_of(im);
-        if (carry_s < (uint32_t)(L.nb * L.mcus)) p.status[img] = 2;
+        const SegRec sg = p.segs[seg];
+        if (carry_s < sg.n_blocks) atomicMax(p.status + sg.image, 2);
     }
 }
 
@@ -150,31 +156,32 @@ __global__ void __launch_bounds__(kHuffThreads) jpegdec_write_kernel(JpegDecPara
     __shared__ TableSet ts;
     __shared__ uint8_t nat[64];
     const uint2 c = p.ctas[blockIdx.x];
-    const ImageRec im = p.images[c.x];
+    const SegRec sg = p.segs[c.x];
+    const ImageRec im = p.images[sg.image];
     load_tables(&ts, nat, p.tables + im.table_set);
     const uint32_t s = c.y + threadIdx.x, n_sub = p.sub_start[c.x + 1] - p.sub_start[c.x];
     if (s >= n_sub) return;
-    const uint32_t gs = p.sub_start[c.x] + s;
-    const Layout L = layout_of(im);
-    const uint32_t total = (uint32_t)(L.nb * L.mcus);
-    const uint32_t g0 = p.first_block[gs];
-    if (g0 >= total) return;   // behind the last block: padding
+    const uint32_t gs = p.sub_start[c.x] + s, bit0 = 8u * sg.byte0;
+    const uint32_t local = p.first_block[gs];
+    if (local >= sg.n_blocks) return;   // behind the segment's last block: padding
     int err = 0;
-    decode_span<true>(im, ts, nat, p.streams + im.stream_off, s == 0 ? span_state(0, 0, 0, 0) : state_start(p.end_state[gs - 1]),
-                      (s + 1) * kSubBits, p.coef + im.coef_off, g0, total, &err);
-    if (err) atomicMax(p.status + c.x, 1);
+    decode_span<true>(layout_of(im), sg.stream_bytes, ts, nat, p.streams + sg.stream_off,
+                      s == 0 ? span_state(bit0, 0, 0, 0) : state_start(p.end_state[gs - 1]), bit0 + (s + 1) * kSubBits,
+                      p.coef + im.coef_off, sg.first_block + local, sg.first_block + sg.n_blocks, &err);
+    if (err) atomicMax(p.status + sg.image, 1);
 }
 
 // DC prediction (jdhuff.c: last_dc_val[ci] += diff): inclusive prefix sum of the stored differences of one component, in
-// the order the blocks were coded.  grid (n_images, 3), 256 threads.
+// the order the blocks were coded, from 0 in every restart interval.  grid (n_segs, 3), 256 threads.
 __global__ void __launch_bounds__(256) jpegdec_dc_kernel(JpegDecParams p) {
     __shared__ int warp_sum[8];
     __shared__ int carry_s;
-    const int img = blockIdx.x, comp = blockIdx.y;
-    const ImageRec im = p.images[img];
-    if (im.h == 0 || p.status[img] != 0 || comp >= im.ncomp) return;
+    const int comp = blockIdx.y;
+    const SegRec sg = p.segs[blockIdx.x];
+    const ImageRec im = p.images[sg.image];
+    if (p.status[sg.image] != 0 || comp >= im.ncomp) return;
     const Layout L = layout_of(im);
-    const uint32_t n = (uint32_t)((comp == 0 ? L.nl : 1) * L.mcus);
+    const uint32_t n = (uint32_t)(comp == 0 ? L.nl : 1) * (sg.n_blocks / (uint32_t)L.nb);
     int16_t* coef = p.coef + im.coef_off;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -182,8 +189,8 @@ __global__ void __launch_bounds__(256) jpegdec_dc_kernel(JpegDecParams p) {
         const uint32_t j = base + threadIdx.x;
         int16_t* blk = nullptr;
         if (j < n)
-            blk = block_of(coef, L, comp == 0 ? (uint32_t)L.nb * (j / (uint32_t)L.nl) + j % (uint32_t)L.nl
-                                              : (uint32_t)L.nb * j + (uint32_t)(L.nl + comp - 1));
+            blk = block_of(coef, L, sg.first_block + (comp == 0 ? (uint32_t)L.nb * (j / (uint32_t)L.nl) + j % (uint32_t)L.nl
+                                                                : (uint32_t)L.nb * j + (uint32_t)(L.nl + comp - 1)));
         const int v = blk ? (int)blk[0] : 0;
         int x = v;
 #pragma unroll
@@ -352,6 +359,7 @@ struct rod_jpeg_decoder {
     std::vector<TableSet> h_tables;
     std::vector<uint32_t> h_block_start, h_quad_start, h_sub_start;
     std::vector<uint2> h_ctas;
+    std::vector<SegRec> h_segs;
     uint8_t* h_streams = nullptr;        // page-locked
     size_t stream_bytes = 0, coef_elems = 0, plane_bytes = 0;
     ImageRec* d_images = nullptr;
@@ -360,6 +368,7 @@ struct rod_jpeg_decoder {
     uint32_t* d_quad_start = nullptr;
     uint32_t* d_sub_start = nullptr;
     uint2* d_ctas = nullptr;
+    SegRec* d_segs = nullptr;
     unsigned int* d_changed = nullptr;
     uint64_t* d_end_state = nullptr;
     uint64_t* d_used_start = nullptr;
@@ -385,7 +394,7 @@ extern "C" int rod_jpegdec_probe(const uint8_t* file, uint64_t n, int* height, i
 
 extern "C" void rod_jpegdec_destroy(rod_jpeg_decoder* d) {
     if (d == nullptr) return;
-    void* small[] = {d->d_images, d->d_tables, d->d_block_start, d->d_quad_start, d->d_status, d->d_sub_start, d->d_ctas, d->d_changed};
+    void* small[] = {d->d_images, d->d_tables, d->d_block_start, d->d_quad_start, d->d_status, d->d_sub_start, d->d_ctas, d->d_changed, d->d_segs};
     for (void* q : small)
         if (q) cudaFree(q);
     block_cache_free(d->device, d->d_streams, d->stream_bytes);
@@ -419,20 +428,26 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
         return ROD_ERR_OOM;
     }
     std::vector<TableSet> per_image(n_images);
+    std::vector<std::vector<SegRec>> per_image_segs(n_images);
     auto work = [&](int lo, int hi) {
         for (int i = lo; i < hi; ++i) {
             ImageRec& im = d->h_images[i];
             FileInfo info;
             const ParseStatus st = files[i] ? parse_file(files[i], (size_t)lens[i], &info, &per_image[i]) : PARSE_NOT_JPEG;
             if (st != PARSE_OK) { d->h_status[i] = 10 + (int)st; continue; }
-            const size_t sb = unstuff_scan(files[i], (size_t)lens[i], info.scan_begin, d->h_streams + slot[i]);
+            std::vector<uint32_t> rst;
+            const size_t sb = unstuff_scan(files[i], (size_t)lens[i], info.scan_begin, d->h_streams + slot[i], &rst);
             if (sb == (size_t)-1) { d->h_status[i] = 13; continue; }
-            im.h = info.height; im.w = info.width;
-            im.hs = (uint8_t)info.hs; im.vs = (uint8_t)info.vs; im.ncomp = (uint8_t)info.ncomp;
-            im.stream_bytes = (uint32_t)sb;
-            im.stream_off = slot[i];
-            im.dst_off = dst_offsets[i];
-            im.dst_pitch = (dst_pitches && dst_pitches[i]) ? dst_pitches[i] : 3LL * info.width;
+            ImageRec r{};
+            r.h = info.height; r.w = info.width;
+            r.hs = (uint8_t)info.hs; r.vs = (uint8_t)info.vs; r.ncomp = (uint8_t)info.ncomp;
+            r.stream_bytes = (uint32_t)sb;
+            r.stream_off = slot[i];
+            r.dst_off = dst_offsets[i];
+            r.dst_pitch = (dst_pitches && dst_pitches[i]) ? dst_pitches[i] : 3LL * info.width;
+            // the restart markers found must be the ones the DRI segment announces
+            if (!make_segments(r, (uint32_t)i, info.restart_interval, slot[i], sb, rst, &per_image_segs[i])) { d->h_status[i] = 13; continue; }
+            im = r;
         }
     };
     {
@@ -447,7 +462,7 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
     std::map<std::string, int> seen;
     d->h_block_start.assign(n_images + 1, 0);
     d->h_quad_start.assign(n_images + 1, 0);
-    d->h_sub_start.assign(n_images + 1, 0);
+    d->h_sub_start.assign(1, 0);
     uint64_t blocks = 0, quads = 0, subs = 0;
     for (int i = 0; i < n_images; ++i) {
         ImageRec& im = d->h_images[i];
@@ -467,11 +482,16 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
             d->plane_bytes += nblocks * 64;
             blocks += nblocks;
             quads += (uint64_t)im.h * (uint64_t)((im.w + 3) >> 2);
-            const uint32_t n_sub = im.stream_bytes ? (8u * im.stream_bytes + kSubBits - 1) / kSubBits : 1u;
-            for (uint32_t s0 = 0; s0 < n_sub; s0 += kHuffThreads) d->h_ctas.push_back(make_uint2((unsigned)i, s0));
-            subs += n_sub;
+            for (const SegRec& sg : per_image_segs[i]) {
+                const uint32_t bits = 8u * (sg.stream_bytes - sg.byte0);
+                const uint32_t n_sub = bits ? (bits + kSubBits - 1) / kSubBits : 1u;
+                const unsigned seg = (unsigned)d->h_segs.size();
+                for (uint32_t s0 = 0; s0 < n_sub; s0 += kHuffThreads) d->h_ctas.push_back(make_uint2(seg, s0));
+                subs += n_sub;
+                d->h_segs.push_back(sg);
+                d->h_sub_start.push_back((uint32_t)subs);
+            }
         }
-        d->h_sub_start[i + 1] = (uint32_t)subs;
         d->h_block_start[i + 1] = (uint32_t)blocks;
         d->h_quad_start[i + 1] = (uint32_t)quads;
     }
@@ -486,7 +506,8 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
     alloc((void**)&d->d_block_start, sizeof(uint32_t) * (n_images + 1));
     alloc((void**)&d->d_quad_start, sizeof(uint32_t) * (n_images + 1));
     alloc((void**)&d->d_status, sizeof(int32_t) * n_images);
-    alloc((void**)&d->d_sub_start, sizeof(uint32_t) * (n_images + 1));
+    alloc((void**)&d->d_sub_start, sizeof(uint32_t) * d->h_sub_start.size());
+    alloc((void**)&d->d_segs, sizeof(SegRec) * d->h_segs.size());
     alloc((void**)&d->d_ctas, sizeof(uint2) * d->h_ctas.size());
     alloc((void**)&d->d_changed, sizeof(unsigned int) * 4);
     calloc_((void**)&d->d_end_state, d->n_sub * sizeof(uint64_t));
@@ -522,7 +543,9 @@ extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* st
     ROD_CUDA(cudaMemcpyAsync(d->d_block_start, d->h_block_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_quad_start, d->h_quad_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_status, d->h_status.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-    ROD_CUDA(cudaMemcpyAsync(d->d_sub_start, d->h_sub_start.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    ROD_CUDA(cudaMemcpyAsync(d->d_sub_start, d->h_sub_start.data(), sizeof(uint32_t) * d->h_sub_start.size(), cudaMemcpyHostToDevice, st));
+    if (!d->h_segs.empty())
+        ROD_CUDA(cudaMemcpyAsync(d->d_segs, d->h_segs.data(), sizeof(SegRec) * d->h_segs.size(), cudaMemcpyHostToDevice, st));
     if (!d->h_ctas.empty())
         ROD_CUDA(cudaMemcpyAsync(d->d_ctas, d->h_ctas.data(), sizeof(uint2) * d->h_ctas.size(), cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_streams, d->h_streams, d->stream_bytes, cudaMemcpyHostToDevice, st));
@@ -531,6 +554,7 @@ extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* st
     JpegDecParams p;
     p.images = d->d_images; p.tables = d->d_tables; p.streams = d->d_streams; p.coef = d->d_coef; p.planes = d->d_planes;
     p.pixels = pixels; p.status = d->d_status; p.block_start = d->d_block_start; p.quad_start = d->d_quad_start;
+    p.segs = d->d_segs; p.n_segs = (int)d->h_segs.size();
     p.sub_start = d->d_sub_start; p.ctas = d->d_ctas; p.end_state = d->d_end_state; p.used_start = d->d_used_start;
     p.first_block = d->d_first_block; p.changed = d->d_changed;
     p.n_images = n;
@@ -547,9 +571,9 @@ extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* st
         d->sync_rounds += 4;
         if (!(flags[0] && flags[1] && flags[2] && flags[3])) break;
     }
-    jpegdec_scan_kernel<<<n, 256, 0, st>>>(p);
+    jpegdec_scan_kernel<<<p.n_segs, 256, 0, st>>>(p);
     jpegdec_write_kernel<<<n_ctas, kHuffThreads, 0, st>>>(p);
-    jpegdec_dc_kernel<<<dim3(n, 3), 256, 0, st>>>(p);
+    jpegdec_dc_kernel<<<dim3(p.n_segs, 3), 256, 0, st>>>(p);
     const uint32_t blocks = d->h_block_start[n], quads = d->h_quad_start[n];
     jpegdec_idct_kernel<<<(blocks + 127) / 128, 128, 0, st>>>(p);
     jpegdec_color_kernel<<<(quads + 255) / 256, 256, 0, st>>>(p);

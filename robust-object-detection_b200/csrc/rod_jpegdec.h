@@ -10,7 +10,7 @@
 //   jdmainct.c context rows          above the first / below the last REAL chroma row the nearest real row is used
 //   jdcolor.c  ycc_rgb_convert       16-bit fixed-point YCbCr -> RGB (written out as BGR)
 //              h2v1_fancy_upsample   4:2:2 files: the same filter along the row only, roundings 1 / 2
-// Supported layouts: baseline sequential (SOF0), 8 bit, one scan without restart markers, either Y Cb Cr with the luma
+// Supported layouts: baseline sequential (SOF0), 8 bit, one scan (with or without restart markers), either Y Cb Cr with the luma
 // sampled 2x2 (4:2:0, what OpenCV itself writes), 2x1 (4:2:2) or 1x1 (4:4:4) against 1x1 chroma, or greyscale.  Anything
 // else is reported as unsupported by the parser and the caller keeps the host codec for that file.
 // The same functions are compiled into tests/emu (CPU check against cv2.imdecode) and into jpegdec.cu.
@@ -73,6 +73,19 @@ RJ_HD Layout layout_of(const ImageRec& im) {
     L.mcus = (long)L.mcu_w * L.mcu_h;
     return L;
 }
+
+// One restart interval of an image's scan (a scan without restart markers is one segment).  Its entropy-coded bytes sit
+// at byte stream_off + byte0 of the stream buffer, stream_off 4-byte aligned (the reader loads words), so bit positions
+// count from stream_off and the segment starts at bit 8 * byte0.  The DC predictions start from 0 in every segment.
+struct SegRec {
+    uint64_t stream_off;
+    uint32_t image;
+    uint32_t byte0;              // 0..3
+    uint32_t stream_bytes;       // byte0 + length of the segment: the bytes a reader may use, counted from stream_off
+    uint32_t first_block;        // global block index (MCU order) of the segment's first block
+    uint32_t n_blocks;
+    uint32_t pad;
+};
 
 // MSB-first reader over the unstuffed stream, 32 bits at a time.
 struct BitReader {
@@ -172,29 +185,24 @@ RJ_HD bool decode_block(BitReader& br, const HuffTab& dc, const HuffTab& ac, con
     return true;
 }
 
-// The whole scan of one image, sequentially (reference for the parallel passes below; CPU replay only).  coef: this
-// image's zeroed coefficient area.  Returns 0, or 1 (corrupt code), 2 (ran past the end of the stream).
-RJ_HD int decode_scan(const ImageRec& im, const TableSet& ts, const uint8_t* nat, const uint8_t* stream, int16_t* coef) {
+// The whole scan of one image, sequentially, segment by segment (reference for the parallel passes below; CPU replay
+// only).  coef: this image's zeroed coefficient area.  Returns 0, or 1 (corrupt code), 2 (ran past the end of a segment).
+RJ_HD int16_t* block_of(int16_t* coef, const Layout& L, uint32_t g);
+RJ_HD int decode_scan(const ImageRec& im, const SegRec* segs, int n_segs, const TableSet& ts, const uint8_t* nat,
+                      const uint8_t* streams, int16_t* coef) {
     const Layout L = layout_of(im);
-    int16_t* yc = coef;
-    int16_t* cbc = coef + 64 * L.nl * L.mcus;
-    int16_t* crc = cbc + 64 * L.mcus;
-    BitReader br;
-    br.init(stream, im.stream_bytes);
-    int last_dc[3] = {0, 0, 0};
-    for (int my = 0; my < L.mcu_h; ++my)
-        for (int mx = 0; mx < L.mcu_w; ++mx) {
-            for (int b = 0; b < L.nl; ++b) {
-                int16_t* blk = yc + 64 * ((long)(L.vs * my + b / L.hs) * (L.hs * L.mcu_w) + L.hs * mx + b % L.hs);
-                if (!decode_block(br, ts.dc[ts.comp_dc[0]], ts.ac[ts.comp_ac[0]], nat, &last_dc[0], blk)) return 1;
-            }
-            if (im.ncomp == 3) {
-                const long m = (long)my * L.mcu_w + mx;
-                if (!decode_block(br, ts.dc[ts.comp_dc[1]], ts.ac[ts.comp_ac[1]], nat, &last_dc[1], cbc + 64 * m)) return 1;
-                if (!decode_block(br, ts.dc[ts.comp_dc[2]], ts.ac[ts.comp_ac[2]], nat, &last_dc[2], crc + 64 * m)) return 1;
-            }
+    for (int q = 0; q < n_segs; ++q) {
+        const SegRec& sg = segs[q];
+        BitReader br;
+        br.init_at(streams + sg.stream_off, sg.stream_bytes, 8u * sg.byte0);
+        int last_dc[3] = {0, 0, 0};
+        for (uint32_t g = sg.first_block; g < sg.first_block + sg.n_blocks; ++g) {
+            const int b = (int)(g % (uint32_t)L.nb), comp = b < L.nl ? 0 : b - L.nl + 1;
+            if (!decode_block(br, ts.dc[ts.comp_dc[comp]], ts.ac[ts.comp_ac[comp]], nat, &last_dc[comp], block_of(coef, L, g))) return 1;
         }
-    return br.bits_used() > 8ull * im.stream_bytes ? 2 : 0;
+        if (br.bits_used() > 8ull * sg.stream_bytes) return 2;
+    }
+    return 0;
 }
 
 // ---- parallel decoding of one scan (device: jpegdec.cu; CPU replay: tests/emu) ---------------------------------------
@@ -205,6 +213,7 @@ RJ_HD int decode_scan(const ImageRec& im, const TableSet& ts, const uint8_t* nat
 //   state of a decoder between two symbols: (bit position p, zigzag index k of the next coefficient -- 0: a DC symbol is
 //   next --, block b of the MCU 0 .. nb - 1), packed with the number of blocks completed into one 64-bit word;
 //   E[s] = end state of subsequence s = F_s(start state), where the start state of s is E[s - 1] (s = 0: the scan's start).
+// With restart markers every interval (SegRec) is such a stream of its own with an exactly known start.
 // Round 0 guesses every start state as (s kSubBits, 0, 0); later rounds re-decode the subsequences whose predecessor's end
 // state changed, until a whole round changes nothing: then E[s] = F_s(E[s - 1]) for every s with E[0] exact, i.e. every end
 // state is the sequential decoder's (induction over s).  A scan over the block counts gives every subsequence its first
@@ -233,14 +242,14 @@ RJ_HD int16_t* block_of(int16_t* coef, const Layout& L, uint32_t g) {
 }
 
 // Decodes the symbols that start in [start.p, boundary) from decoder state `start`; returns the end state.  WRITE: also
-// stores the coefficients (DC: the difference) from global block g0 on, stops behind block total_blocks - 1 and reports
+// stores the coefficients (DC: the difference) from global block g0 on, stops behind block total_blocks - 1 (the segment's
+// last block) and reports
 // corrupt data in *err.
 template <bool WRITE>
-RJ_HD uint64_t decode_span(const ImageRec& im, const TableSet& ts, const uint8_t* nat, const uint8_t* stream, uint64_t start,
+RJ_HD uint64_t decode_span(const Layout& L, uint32_t stream_bytes, const TableSet& ts, const uint8_t* nat, const uint8_t* stream, uint64_t start,
                            uint32_t boundary, int16_t* coef, uint32_t g0, uint32_t total_blocks, int* err) {
-    const Layout L = layout_of(im);
     BitReader br;
-    br.init_at(stream, im.stream_bytes, state_p(start));
+    br.init_at(stream, stream_bytes, state_p(start));
     int k = state_k(start), b = state_b(start);
     uint32_t nblk = 0, g = g0;
     int16_t* blk = WRITE ? block_of(coef, L, g) : nullptr;

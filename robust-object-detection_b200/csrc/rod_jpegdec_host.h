@@ -20,6 +20,7 @@ enum ParseStatus {
 struct FileInfo {
     int height = 0, width = 0;
     int hs = 0, vs = 0, ncomp = 0;   // luma sampling (chroma 1 x 1), 3 components or 1
+    int restart_interval = 0;        // MCUs per restart interval (DRI), 0: none
     size_t scan_begin = 0;       // first byte of the entropy-coded segment
 };
 
@@ -140,7 +141,7 @@ inline ParseStatus parse_file(const uint8_t* f, size_t n, FileInfo* info, TableS
             }
         } else if (m == 0xDD) {
             if (pl < 2) return PARSE_NOT_JPEG;
-            if (((p[0] << 8) | p[1]) != 0) return PARSE_UNSUPPORTED;
+            info->restart_interval = (p[0] << 8) | p[1];
         } else if (m == 0xE1) {
             if (exif_rotates(p, pl)) return PARSE_UNSUPPORTED;
         } else if (m == 0xEE) {
@@ -173,10 +174,11 @@ inline ParseStatus parse_file(const uint8_t* f, size_t n, FileInfo* info, TableS
     }
 }
 
-// Copies the entropy-coded segment f[begin ..] up to the next marker into out without the stuffed zero bytes.
-// out must hold n - begin + 16 bytes; the 16 bytes behind the returned length are zeroed.  Returns the length, or
-// (size_t)-1 when the segment does not end in EOI (restart markers or further scans: not a single-scan baseline file).
-inline size_t unstuff_scan(const uint8_t* f, size_t n, size_t begin, uint8_t* out) {
+// Copies the entropy-coded data f[begin ..] up to EOI into out without the stuffed zero bytes and without the restart
+// markers, whose positions in `out` (= the starts of the following intervals) are appended to *rst.  out must hold
+// n - begin + 16 bytes; the 16 bytes behind the returned length are zeroed.  Returns the length, or (size_t)-1 when the
+// data does not end in EOI (further scans, truncated file).
+inline size_t unstuff_scan(const uint8_t* f, size_t n, size_t begin, uint8_t* out, std::vector<uint32_t>* rst) {
     size_t o = 0, i = begin;
     bool eoi = false;
     while (i < n) {
@@ -190,11 +192,43 @@ inline size_t unstuff_scan(const uint8_t* f, size_t n, size_t begin, uint8_t* ou
         const uint8_t m = f[i + 1];
         if (m == 0x00) { out[o++] = 0xFF; i += 2; continue; }
         if (m == 0xFF) { ++i; continue; }   // fill byte
+        if (m >= 0xD0 && m <= 0xD7) { if (rst) rst->push_back((uint32_t)o); i += 2; continue; }
         eoi = (m == 0xD9);
         break;
     }
     memset(out + o, 0, 16);
     return eoi ? o : (size_t)-1;
+}
+
+}  // namespace jpegdec
+}  // namespace rod
+
+namespace rod {
+namespace jpegdec {
+
+// The restart intervals of one image as segment records.  slot: 4-byte aligned offset of the image's unstuffed scan in the
+// stream buffer, sb its length, rst the interval starts found by unstuff_scan.  false: the markers do not match the DRI.
+inline bool make_segments(const ImageRec& im, uint32_t image, int restart_interval, uint64_t slot, size_t sb,
+                          const std::vector<uint32_t>& rst, std::vector<SegRec>* out) {
+    const Layout L = layout_of(im);
+    const long ri = restart_interval > 0 ? restart_interval : L.mcus;
+    const long n_seg = (L.mcus + ri - 1) / ri;
+    if ((long)rst.size() != n_seg - 1) return false;
+    for (long q = 0; q < n_seg; ++q) {
+        const uint64_t b0 = q == 0 ? 0 : rst[q - 1], b1 = q + 1 < n_seg ? rst[q] : sb;
+        if (b1 < b0) return false;
+        SegRec sg;
+        const uint64_t abs0 = slot + b0;
+        sg.stream_off = abs0 & ~(uint64_t)3;
+        sg.byte0 = (uint32_t)(abs0 & 3);
+        sg.stream_bytes = sg.byte0 + (uint32_t)(b1 - b0);
+        sg.image = image;
+        sg.first_block = (uint32_t)(q * ri * L.nb);
+        sg.n_blocks = (uint32_t)((q + 1 < n_seg ? ri : L.mcus - q * ri) * L.nb);
+        sg.pad = 0;
+        out->push_back(sg);
+    }
+    return true;
 }
 
 }  // namespace jpegdec

@@ -133,7 +133,8 @@ class JpegDecoder:
     given to decode(), row pitch 3 * width unless `pitches` says otherwise -- the layout of a CorruptionPlan built from
     `shapes`.  The constructor does the host work (markers, Huffman tables, scans copied without their byte stuffing into
     page-locked memory, on `host_threads` threads); `shapes[i]` is (h, w), or None where the device decoder does not take
-    the file (it takes baseline 4:2:0 / 4:2:2 / 4:4:4 / greyscale files; not: progressive, restart markers, EXIF rotation,
+    the file (it takes baseline 4:2:0 / 4:2:2 / 4:4:4 / greyscale files; with or without restart
+    markers; not: progressive, EXIF rotation,
     CMYK, not a JPEG ...): the caller reads those with the host codec.  No CPU decoding inside."""
 
     def __init__(self, files: Sequence, offsets: Sequence[int], pitches: Optional[Sequence[int]] = None, host_threads: int = 8):

@@ -1126,7 +1126,8 @@ extern "C" int emu_jpeg_decode_mode(const uint8_t* file, long n, uint8_t* out, l
     if (st != PARSE_OK) return (int)st;
     hw[0] = info.height; hw[1] = info.width; hw[2] = 0;
     std::vector<uint8_t> stream((size_t)n - info.scan_begin + 64);
-    const size_t sb = unstuff_scan(file, (size_t)n, info.scan_begin, stream.data());
+    std::vector<uint32_t> rst;
+    const size_t sb = unstuff_scan(file, (size_t)n, info.scan_begin, stream.data(), &rst);
     if (sb == (size_t)-1) return 3;
     ImageRec im;
     memset(&im, 0, sizeof(im));
@@ -1134,49 +1135,56 @@ extern "C" int emu_jpeg_decode_mode(const uint8_t* file, long n, uint8_t* out, l
     im.hs = (uint8_t)info.hs; im.vs = (uint8_t)info.vs; im.ncomp = (uint8_t)info.ncomp;
     const Layout L = layout_of(im);
     const int mcu_w = L.mcu_w, mcu_h = L.mcu_h;
+    std::vector<SegRec> segs;
+    if (!make_segments(im, 0, info.restart_interval, 0, sb, rst, &segs)) return 3;
     std::vector<int16_t> coef((size_t)L.mcus * L.nb * 64, 0);
     uint8_t nat[64];
     for (int z = 0; z < 64; ++z) nat[z] = (uint8_t)rod::jpeg::natural_order(z);
     hw[2] = 0;
     int rc = 0;
     if (mode == 0) {
-        rc = decode_scan(im, ts, nat, stream.data(), coef.data());
+        rc = decode_scan(im, segs.data(), (int)segs.size(), ts, nat, stream.data(), coef.data());
     } else {
-        const uint32_t total_bits = 8u * (uint32_t)sb, total_blocks = (uint32_t)(L.nb * L.mcus);
-        const uint32_t n_sub = total_bits ? (total_bits + kSubBits - 1) / kSubBits : 1;
-        std::vector<uint64_t> E(n_sub), U(n_sub);
-        for (uint32_t q = 0; q < n_sub; ++q) {
-            U[q] = span_state(q * kSubBits, 0, 0, 0);
-            E[q] = decode_span<false>(im, ts, nat, stream.data(), U[q], (q + 1) * kSubBits, nullptr, 0, 0, nullptr);
-        }
-        for (bool changed = true; changed;) {
-            changed = false;
-            ++hw[2];
-            for (uint32_t q = n_sub - 1; q >= 1; --q) {
-                const uint64_t st = state_start(E[q - 1]);
-                if (st == U[q]) continue;
-                U[q] = st;
-                E[q] = decode_span<false>(im, ts, nat, stream.data(), st, (q + 1) * kSubBits, nullptr, 0, 0, nullptr);
-                changed = true;
+        int err = 0;
+        for (const SegRec& sg : segs) {   // every restart interval is a stream of its own
+            const uint8_t* sbase = stream.data() + sg.stream_off;
+            const uint32_t bit0 = 8u * sg.byte0, total_bits = 8u * sg.stream_bytes - bit0;
+            const uint32_t n_sub = total_bits ? (total_bits + kSubBits - 1) / kSubBits : 1;
+            std::vector<uint64_t> E(n_sub), U(n_sub);
+            for (uint32_t q = 0; q < n_sub; ++q) {
+                U[q] = span_state(bit0 + q * kSubBits, 0, 0, 0);
+                E[q] = decode_span<false>(L, sg.stream_bytes, ts, nat, sbase, U[q], bit0 + (q + 1) * kSubBits, nullptr, 0, 0, nullptr);
+            }
+            int rounds = 0;
+            for (bool changed = true; changed;) {
+                changed = false;
+                ++rounds;
+                for (uint32_t q = n_sub - 1; q >= 1; --q) {
+                    const uint64_t st = state_start(E[q - 1]);
+                    if (st == U[q]) continue;
+                    U[q] = st;
+                    E[q] = decode_span<false>(L, sg.stream_bytes, ts, nat, sbase, st, bit0 + (q + 1) * kSubBits, nullptr, 0, 0, nullptr);
+                    changed = true;
+                }
+            }
+            if (rounds > hw[2]) hw[2] = rounds;
+            std::vector<uint32_t> blk0(n_sub + 1, 0);
+            for (uint32_t q = 0; q < n_sub; ++q) blk0[q + 1] = blk0[q] + state_nblk(E[q]);
+            if (blk0[n_sub] < sg.n_blocks) { rc = 2; break; }
+            for (uint32_t q = 0; q < n_sub; ++q)
+                if (blk0[q] < sg.n_blocks)
+                    decode_span<true>(L, sg.stream_bytes, ts, nat, sbase, q == 0 ? span_state(bit0, 0, 0, 0) : state_start(E[q - 1]),
+                                      bit0 + (q + 1) * kSubBits, coef.data(), sg.first_block + blk0[q], sg.first_block + sg.n_blocks, &err);
+            // DC prediction: prefix sums per component in coded order, from 0 in every interval
+            int pred[3] = {0, 0, 0};
+            for (uint32_t g = sg.first_block; g < sg.first_block + sg.n_blocks; ++g) {
+                int16_t* blk = block_of(coef.data(), L, g);
+                const int b = (int)(g % (uint32_t)L.nb), comp = b < L.nl ? 0 : b - L.nl + 1;
+                pred[comp] += blk[0];
+                blk[0] = (int16_t)pred[comp];
             }
         }
-        std::vector<uint32_t> blk0(n_sub + 1, 0);
-        for (uint32_t q = 0; q < n_sub; ++q) blk0[q + 1] = blk0[q] + state_nblk(E[q]);
-        if (blk0[n_sub] < total_blocks) rc = 2;
-        int err = 0;
-        for (uint32_t q = 0; q < n_sub && rc == 0; ++q)
-            if (blk0[q] < total_blocks)
-                decode_span<true>(im, ts, nat, stream.data(), q == 0 ? span_state(0, 0, 0, 0) : state_start(E[q - 1]),
-                                  (q + 1) * kSubBits, coef.data(), blk0[q], total_blocks, &err);
-        if (err) rc = 1;
-        // DC prediction: prefix sums per component in MCU order
-        int pred[3] = {0, 0, 0};
-        for (uint32_t g = 0; g < total_blocks && rc == 0; ++g) {
-            int16_t* blk = block_of(coef.data(), L, g);
-            const int b = (int)(g % (uint32_t)L.nb), comp = b < L.nl ? 0 : b - L.nl + 1;
-            pred[comp] += blk[0];
-            blk[0] = (int16_t)pred[comp];
-        }
+        if (err && rc == 0) rc = 1;
     }
     if (rc) return 3 + rc;
     const long ypitch = 8L * L.hs * mcu_w, cpitch = 8L * mcu_w;

@@ -521,6 +521,8 @@ def test_emu_jpeg_decoder_matches_cv2(emu):
             params = params + [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
         elif i % 11 == 5:
             img = np.ascontiguousarray(img[:, :, 0])
+        if i % 5 == 2:   # restart markers: every interval is a bit stream of its own (DC predictions from 0)
+            params = params + [cv2.IMWRITE_JPEG_RST_INTERVAL, 1 + i % 7]
         ok, enc = cv2.imencode(".jpg", img, params)
         assert ok
         want = cv2.imdecode(enc, cv2.IMREAD_COLOR)
@@ -550,12 +552,12 @@ def test_emu_jpeg_decoder_self_synchronisation(emu):
 
 def test_emu_jpeg_decoder_reports_other_layouts(emu):
     """Files the device decoder does not take are reported, not approximated: vertical-only / 4:1:1 chroma sampling,
-    progressive, restart markers, tiny widths of subsampled files (libjpeg-turbo's upsampler reads its padding there),
+    progressive, tiny widths of subsampled files (libjpeg-turbo's upsampler reads its padding there),
     truncated files, other formats."""
     import cv2
     img = synth(8300, 64, 64)
     for params in ([cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440], [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411],
-                   [cv2.IMWRITE_JPEG_PROGRESSIVE, 1], [cv2.IMWRITE_JPEG_RST_INTERVAL, 4]):
+                   [cv2.IMWRITE_JPEG_PROGRESSIVE, 1]):
         assert _emu_decode(emu, cv2.imencode(".jpg", img, params)[1].tobytes())[0] == 2, params
     assert _emu_decode(emu, cv2.imencode(".jpg", img[:, :4])[1].tobytes())[0] == 2
     small444 = cv2.imencode(".jpg", img[:3, :2], [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])[1]

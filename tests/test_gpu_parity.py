@@ -1352,6 +1352,8 @@ def test_jpeg_decoder_matches_cv2(torch_):
             params = params + [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
         elif i % 7 == 6:
             img = np.ascontiguousarray(img[:, :, 1])
+        if i % 4 == 1:     # restart markers (intervals of 1 .. 9 MCUs)
+            params = params + [cv2.IMWRITE_JPEG_RST_INTERVAL, 1 + i % 9]
         enc = cv2.imencode(".jpg", img, params)[1]
         files.append(enc.tobytes())
         want.append(cv2.imdecode(enc, cv2.IMREAD_COLOR))

@@ -317,10 +317,10 @@ def test_jpeg_probe_through_the_c_abi(built):
     img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
     S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
     for params in ([], [cv2.IMWRITE_JPEG_QUALITY, 30], [cv2.IMWRITE_JPEG_OPTIMIZE, 1], [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422],
-                   [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]):
+                   [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444], [cv2.IMWRITE_JPEG_RST_INTERVAL, 2]):
         assert probe(cv2.imencode(".jpg", img, params)[1].tobytes()) == (37, 53), params
     assert probe(cv2.imencode(".jpg", img[:, :, 0])[1].tobytes()) == (37, 53)
-    for params in ([cv2.IMWRITE_JPEG_PROGRESSIVE, 1], [cv2.IMWRITE_JPEG_RST_INTERVAL, 2], [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440],
+    for params in ([cv2.IMWRITE_JPEG_PROGRESSIVE, 1], [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440],
                    [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]):
         assert probe(cv2.imencode(".jpg", img, params)[1].tobytes()) is None, params
     assert probe(cv2.imencode(".jpg", img[:, :4])[1].tobytes()) is None           # subsampled and narrower than 5 pixels
