@@ -556,7 +556,18 @@ def extras(torch, np, plan, src, dst, peak):
         assert (dec.status() == 0).all()
         r["content"] = "the 64 files of jpeg_encode_64 (uniform noise, 1.2 MB each: the slowest content to decode)"
         out["jpeg_decode_64"] = r
-        del enc, dec, back
+        # the same on smooth content (9 x 9 box average of the noise frames: ~0.2 MB per file, what camera frames compress to)
+        smooth = torch.nn.functional.avg_pool2d(src[:nj].permute(0, 3, 1, 2).float(), 9, 1, 4).round_().clamp_(0, 255) \
+            .to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        files_s = enc.encode(smooth.reshape(-1))
+        sbytes = sum(len(f) for f in files_s if f is not None)
+        dec_s = JpegDecoder([bytes(f) for f in files_s], [i * IMG_BYTES for i in range(nj)], host_threads=16)
+        r = rate(lambda: dec_s.decode(back), IMG_BYTES * nj + sbytes, nj, steps=5, warmup=2)
+        assert (dec_s.status() == 0).all()
+        r["compressed_bytes_per_image"] = sbytes // nj
+        r["content"] = "box-averaged noise (smooth)"
+        out["jpeg_decode_64_smooth"] = r
+        del enc, dec, dec_s, back, smooth
     except Exception as e:  # cv2 (for the header template) is the only extra dependency
         print(f"[bench] JPEG encoder line skipped: {e}", file=sys.stderr)
     import random
