@@ -270,8 +270,47 @@ def make_jpeg():
     print("wrote", len(out), "JPEG hashes")
 
 
+JPEGDEC_CASES = [  # (seed, h, w, kind, imencode parameters as (name, value) pairs)
+    (9400, 37, 53, "smooth", []), (9401, 64, 48, "noise", [("QUALITY", 60)]), (9402, 17, 33, "noise", [("OPTIMIZE", 1)]),
+    (9403, 97, 133, "smooth", [("SAMPLING_FACTOR", "422")]), (9404, 40, 41, "noise", [("SAMPLING_FACTOR", "444"), ("QUALITY", 100)]),
+    (9405, 50, 70, "grey", []), (9406, 120, 200, "smooth", [("RST_INTERVAL", 5)]), (9407, 9, 5, "noise", [("QUALITY", 20)]),
+    (9408, 33, 64, "binary", [("RST_INTERVAL", 1), ("SAMPLING_FACTOR", "422")])]
+
+
+def jpegdec_case_file(seed, h, w, kind, params):
+    import cv2
+    img = jpeg_case_image(seed, h, w, "noise" if kind == "grey" else kind)
+    if kind == "grey":
+        img = np.ascontiguousarray(img[:, :, 0])
+    flat = []
+    for name, val in params:
+        flat.append(getattr(cv2, "IMWRITE_JPEG_" + name))
+        flat.append(getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + val) if name == "SAMPLING_FACTOR" else val)
+    return cv2.imencode(".jpg", img, flat)[1].tobytes()
+
+
+def make_jpegdec():
+    """SURVEY 8f rank 1, reading side: small JPEG files written in the build container (OpenCV's encoder, several layouts)
+    together with the sha256 of the pixels cv2.imdecode(file, IMREAD_COLOR) -- the decoder behind the reference's
+    cv2.imread(str(img_path)), build_corrupted_testsets.py:109 -- returns there.  The files themselves are stored (base64):
+    the check does not depend on the local OpenCV build at all."""
+    import base64
+    import cv2
+    cases = []
+    for seed, h, w, kind, params in JPEGDEC_CASES:
+        data = jpegdec_case_file(seed, h, w, kind, params)
+        pix = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        cases.append({"name": f"{seed}_{h}x{w}_{kind}", "params": params, "shape": list(pix.shape), "file_b64": base64.b64encode(data).decode(),
+                      "pixels_sha256": hashlib.sha256(np.ascontiguousarray(pix).tobytes()).hexdigest()})
+    with open(os.path.join(HERE, "golden_jpegdec.json"), "w") as f:
+        json.dump({"cases": cases, "cv2": cv2.__version__}, f, indent=1)
+    print("wrote", len(cases), "JPEG files with the hashes of their decoded pixels")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "jpeg":
+    if len(sys.argv) > 1 and sys.argv[1] == "jpegdec":
+        make_jpegdec()
+    elif len(sys.argv) > 1 and sys.argv[1] == "jpeg":
         make_jpeg()
     elif len(sys.argv) > 1 and sys.argv[1] == "restoration":
         make_restoration()
@@ -285,3 +324,4 @@ if __name__ == "__main__":
         make_restoration()
         make_letterbox()
         make_jpeg()
+        make_jpegdec()

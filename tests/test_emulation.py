@@ -568,3 +568,20 @@ def test_emu_jpeg_decoder_reports_other_layouts(emu):
     assert _emu_decode(emu, whole[:100])[0] == 1                      # header cut short
     assert _emu_decode(emu, cv2.imencode(".png", img)[1].tobytes())[0] == 1
     assert _emu_decode(emu, b"not a jpeg")[0] == 1
+
+
+def test_emu_jpeg_decoder_matches_golden(emu):
+    """... and against the files and pixel hashes recorded in the build container (golden_jpegdec.json: OpenCV's decoder on
+    4:2:0 / 4:2:2 / 4:4:4 / greyscale files, optimised tables, restart intervals), so the check does not rest on the local
+    OpenCV build."""
+    import base64
+    import hashlib
+    import json
+    g = json.load(open(os.path.join(HERE, "golden", "golden_jpegdec.json")))
+    assert len(g["cases"]) >= 9
+    for c in g["cases"]:
+        data = base64.b64decode(c["file_b64"])
+        for mode in (0, 1):
+            rc, got = _emu_decode(emu, data, mode)
+            assert rc == 0 and list(got.shape) == c["shape"], (c["name"], mode, rc)
+            assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == c["pixels_sha256"], (c["name"], mode)

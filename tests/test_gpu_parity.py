@@ -1479,3 +1479,24 @@ def test_restoration_pairs_from_files(torch_, tmp_path):
             got = b.from_files(paths)
             assert a.last_decisions == b.last_decisions
             assert torch_.equal(got[0], want[0]) and torch_.equal(got[1], want[1]), (is_train, noise)
+
+
+def test_jpeg_decoder_matches_golden(torch_):
+    """Device JPEG decoder against the files and pixel hashes recorded in the build container (golden_jpegdec.json)."""
+    import base64
+    import hashlib
+    import json
+    from robust_object_detection_b200.batch import CorruptionPlan
+    from robust_object_detection_b200.jpeg import JpegDecoder
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_jpegdec.json")))
+    files = [base64.b64decode(c["file_b64"]) for c in g["cases"]]
+    shapes = [tuple(c["shape"][:2]) for c in g["cases"]]
+    plan = CorruptionPlan.ragged(shapes)
+    dec = JpegDecoder(files, plan.src_offsets)
+    assert dec.shapes == shapes
+    pix = torch_.empty(plan.src_bytes, dtype=torch_.uint8, device="cuda")
+    dec.decode(pix)
+    assert (dec.status() == 0).all()
+    got = pix.cpu().numpy()
+    for c, (h, w), off in zip(g["cases"], shapes, plan.src_offsets):
+        assert hashlib.sha256(got[off:off + 3 * h * w].tobytes()).hexdigest() == c["pixels_sha256"], c["name"]
