@@ -546,6 +546,7 @@ def extras(torch, np, plan, src, dst, peak):
         r = rate(lambda: N.check(N.lib().rod_jpeg_encode(enc._h, _ptr(src), None), "rod_jpeg_encode"), IMG_BYTES * nj + stream_bytes, nj)
         r["compressed_bytes_per_image"] = stream_bytes // nj
         r["content"] = "uniform noise"
+        r["bound"] = "entropy coding (instruction / latency), not HBM: the fraction of the copy bandwidth is for scale only"
         out["jpeg_encode_64"] = r
         # ... and the device JPEG decoder (pixels identical to cv2.imread's) on those 64 files: bytes = stream read + pixels
         # written; the call includes the upload of the streams and the host round trips of the synchronisation rounds
@@ -555,6 +556,7 @@ def extras(torch, np, plan, src, dst, peak):
         r = rate(lambda: dec.decode(back), IMG_BYTES * nj + stream_bytes, nj, steps=5, warmup=2)
         assert (dec.status() == 0).all()
         r["content"] = "the 64 files of jpeg_encode_64 (uniform noise, 1.2 MB each: the slowest content to decode)"
+        r["bound"] = "Huffman decoding (dependent bit-buffer chain per symbol, synchronisation rounds), not HBM"
         out["jpeg_decode_64"] = r
         # the same on smooth content (9 x 9 box average of the noise frames: ~0.2 MB per file, what camera frames compress to)
         smooth = torch.nn.functional.avg_pool2d(src[:nj].permute(0, 3, 1, 2).float(), 9, 1, 4).round_().clamp_(0, 255) \
@@ -566,6 +568,7 @@ def extras(torch, np, plan, src, dst, peak):
         assert (dec_s.status() == 0).all()
         r["compressed_bytes_per_image"] = sbytes // nj
         r["content"] = "box-averaged noise (smooth)"
+        r["bound"] = "Huffman decoding, not HBM"
         out["jpeg_decode_64_smooth"] = r
         del enc, dec, dec_s, back, smooth
     except Exception as e:  # cv2 (for the header template) is the only extra dependency
