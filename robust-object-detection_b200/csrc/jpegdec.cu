@@ -453,6 +453,9 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
     {
         int nt = host_threads < 1 ? 1 : (host_threads > 64 ? 64 : host_threads);
         if (nt > n_images) nt = n_images;
+        // a thread is worth starting for about a megabyte of file data (unstuffing runs at memory speed)
+        const uint64_t by_bytes = 1 + (slot[n_images] >> 20);
+        if ((uint64_t)nt > by_bytes) nt = (int)by_bytes;
         std::vector<std::thread> th;
         for (int t = 1; t < nt; ++t) th.emplace_back(work, (int)((long)n_images * t / nt), (int)((long)n_images * (t + 1) / nt));
         work(0, (int)((long)n_images / nt));
