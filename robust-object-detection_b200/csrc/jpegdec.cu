@@ -374,6 +374,8 @@ struct rod_jpeg_decoder {
     uint64_t* d_used_start = nullptr;
     uint32_t* d_first_block = nullptr;
     size_t n_sub = 0;
+    uint8_t* d_small = nullptr;
+    size_t small_bytes = 0;
     int sync_rounds = 0;                 // launches of the last decode (diagnostics)
     int32_t* d_status = nullptr;
     uint8_t* d_streams = nullptr;
@@ -394,9 +396,7 @@ extern "C" int rod_jpegdec_probe(const uint8_t* file, uint64_t n, int* height, i
 
 extern "C" void rod_jpegdec_destroy(rod_jpeg_decoder* d) {
     if (d == nullptr) return;
-    void* small[] = {d->d_images, d->d_tables, d->d_block_start, d->d_quad_start, d->d_status, d->d_sub_start, d->d_ctas, d->d_changed, d->d_segs};
-    for (void* q : small)
-        if (q) cudaFree(q);
+    block_cache_free(d->device, d->d_small, d->small_bytes);   // the descriptor arrays are carved out of one block
     block_cache_free(d->device, d->d_streams, d->stream_bytes);
     block_cache_free(d->device, d->d_coef, d->coef_elems * sizeof(int16_t));
     block_cache_free(d->device, d->d_planes, d->plane_bytes);
@@ -502,17 +502,25 @@ extern "C" int rod_jpegdec_create(const uint8_t* const* files, const uint64_t* l
     if (blocks >= (1ull << 32) || quads >= (1ull << 32) || subs >= (1ull << 32)) { rod_jpegdec_destroy(d); return ROD_ERR_UNSUPPORTED; }
     if (d->h_tables.empty()) d->h_tables.push_back(TableSet{});
     cudaError_t err = cudaSuccess;
-    auto alloc = [&](void** p, size_t n) { if (err == cudaSuccess) err = cudaMalloc(p, n ? n : 16); };
     auto calloc_ = [&](void** p, size_t n) { if (err == cudaSuccess) err = block_cache_alloc(d->device, p, n ? n : 16); };
-    alloc((void**)&d->d_images, sizeof(ImageRec) * n_images);
-    alloc((void**)&d->d_tables, sizeof(TableSet) * d->h_tables.size());
-    alloc((void**)&d->d_block_start, sizeof(uint32_t) * (n_images + 1));
-    alloc((void**)&d->d_quad_start, sizeof(uint32_t) * (n_images + 1));
-    alloc((void**)&d->d_status, sizeof(int32_t) * n_images);
-    alloc((void**)&d->d_sub_start, sizeof(uint32_t) * d->h_sub_start.size());
-    alloc((void**)&d->d_segs, sizeof(SegRec) * d->h_segs.size());
-    alloc((void**)&d->d_ctas, sizeof(uint2) * d->h_ctas.size());
-    alloc((void**)&d->d_changed, sizeof(unsigned int) * 4);
+    // descriptor arrays: one cached block (cudaMalloc / cudaFree per decoder would synchronise the device every batch)
+    size_t sizes[9] = {sizeof(ImageRec) * n_images, sizeof(TableSet) * d->h_tables.size(), sizeof(uint32_t) * (n_images + 1),
+                       sizeof(uint32_t) * (n_images + 1), sizeof(int32_t) * n_images, sizeof(uint32_t) * d->h_sub_start.size(),
+                       sizeof(SegRec) * d->h_segs.size(), sizeof(uint2) * d->h_ctas.size(), sizeof(unsigned int) * 4};
+    size_t offs[9];
+    for (int q = 0; q < 9; ++q) { offs[q] = d->small_bytes; d->small_bytes += (sizes[q] + 255) & ~(size_t)255; }
+    calloc_((void**)&d->d_small, d->small_bytes);
+    if (err == cudaSuccess) {
+        d->d_images = reinterpret_cast<ImageRec*>(d->d_small + offs[0]);
+        d->d_tables = reinterpret_cast<TableSet*>(d->d_small + offs[1]);
+        d->d_block_start = reinterpret_cast<uint32_t*>(d->d_small + offs[2]);
+        d->d_quad_start = reinterpret_cast<uint32_t*>(d->d_small + offs[3]);
+        d->d_status = reinterpret_cast<int32_t*>(d->d_small + offs[4]);
+        d->d_sub_start = reinterpret_cast<uint32_t*>(d->d_small + offs[5]);
+        d->d_segs = reinterpret_cast<SegRec*>(d->d_small + offs[6]);
+        d->d_ctas = reinterpret_cast<uint2*>(d->d_small + offs[7]);
+        d->d_changed = reinterpret_cast<unsigned int*>(d->d_small + offs[8]);
+    }
     calloc_((void**)&d->d_end_state, d->n_sub * sizeof(uint64_t));
     calloc_((void**)&d->d_used_start, d->n_sub * sizeof(uint64_t));
     calloc_((void**)&d->d_first_block, d->n_sub * sizeof(uint32_t));
