@@ -433,7 +433,7 @@ namespace {
 std::mutex g_cache_mutex;
 std::multimap<std::pair<int, size_t>, void*> g_cache;   // (device, rounded size) -> free block
 size_t round_block(size_t n) {
-    size_t r = 1 << 20;
+    size_t r = 1 << 16;   // (plans keep ~25 small arrays each)
     while (r < n) r <<= 1;
     if (r > (64u << 20)) r = (n + (64u << 20) - 1) / (64u << 20) * (64u << 20);   // large blocks: multiples of 64 MiB
     return r;

@@ -377,6 +377,7 @@ struct rod_jpeg_decoder {
     uint8_t* d_small = nullptr;
     size_t small_bytes = 0;
     int sync_rounds = 0;                 // launches of the last decode (diagnostics)
+    bool in_flight = false;              // decode() issued, status() not yet waited for
     int32_t* d_status = nullptr;
     uint8_t* d_streams = nullptr;
     int16_t* d_coef = nullptr;
@@ -396,6 +397,7 @@ extern "C" int rod_jpegdec_probe(const uint8_t* file, uint64_t n, int* height, i
 
 extern "C" void rod_jpegdec_destroy(rod_jpeg_decoder* d) {
     if (d == nullptr) return;
+    if (d->in_flight) cudaDeviceSynchronize();   // the buffers go to caches and may be reused at once
     block_cache_free(d->device, d->d_small, d->small_bytes);   // the descriptor arrays are carved out of one block
     block_cache_free(d->device, d->d_streams, d->stream_bytes);
     block_cache_free(d->device, d->d_coef, d->coef_elems * sizeof(int16_t));
@@ -560,6 +562,7 @@ extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* st
     if (!d->h_ctas.empty())
         ROD_CUDA(cudaMemcpyAsync(d->d_ctas, d->h_ctas.data(), sizeof(uint2) * d->h_ctas.size(), cudaMemcpyHostToDevice, st));
     ROD_CUDA(cudaMemcpyAsync(d->d_streams, d->h_streams, d->stream_bytes, cudaMemcpyHostToDevice, st));
+    d->in_flight = true;
     if (d->coef_elems == 0 || d->h_ctas.empty()) return ROD_OK;
     ROD_CUDA(cudaMemsetAsync(d->d_coef, 0, d->coef_elems * sizeof(int16_t), st));
     JpegDecParams p;
@@ -599,5 +602,6 @@ extern "C" int rod_jpegdec_status(rod_jpeg_decoder* d, int32_t* status, void* st
     cudaStream_t st = (cudaStream_t)stream;
     ROD_CUDA(cudaMemcpyAsync(status, d->d_status, sizeof(int32_t) * d->n_images, cudaMemcpyDeviceToHost, st));
     ROD_CUDA(cudaStreamSynchronize(st));
+    d->in_flight = false;
     return ROD_OK;
 }

@@ -16,11 +16,35 @@ int grid_for(const rod_plan* plan, int n_tiles, int ctas_per_sm) {
     return (int)(n_tiles < cap ? n_tiles : cap);
 }
 
+// The device arrays of a plan come from the block cache (jpeg.cu) and go back to it: a batch driver builds and drops a plan
+// per batch, and ~30 cudaMalloc / cudaFree calls per plan (each a device-wide synchronisation) cost more than its kernels.
+static cudaError_t plan_alloc(const rod_plan* plan, void** p, size_t n) {
+    const cudaError_t e = block_cache_alloc(plan->device, p, n);
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(plan->cached_mutex);
+        plan->cached_blocks.push_back({*p, n});
+    }
+    return e;
+}
+static void plan_free(const rod_plan* plan, void* p) {
+    if (p == nullptr) return;
+    {
+        std::lock_guard<std::mutex> lock(plan->cached_mutex);
+        for (size_t i = 0; i < plan->cached_blocks.size(); ++i)
+            if (plan->cached_blocks[i].first == p) {
+                block_cache_free(plan->device, p, plan->cached_blocks[i].second);
+                plan->cached_blocks.erase(plan->cached_blocks.begin() + (long)i);
+                return;
+            }
+    }
+    cudaFree(p);   // allocated elsewhere (staging buffers of the host entry points)
+}
+
 template <typename T>
-static int upload(const std::vector<T>& v, T** dptr) {
+static int upload(const rod_plan* plan, const std::vector<T>& v, T** dptr) {
     *dptr = nullptr;
     if (v.empty()) return ROD_OK;
-    ROD_CUDA(cudaMalloc((void**)dptr, v.size() * sizeof(T)));
+    ROD_CUDA(plan_alloc(plan, (void**)dptr, v.size() * sizeof(T)));
     ROD_CUDA(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return ROD_OK;
 }
@@ -156,31 +180,30 @@ int ensure_lowres_tables(rod_plan* plan, double factor) {
                    plan->d_lowres_x2f_tiles[0], plan->d_lowres_x2f_tiles[1], plan->d_lowres_x2f_tiles[2], plan->d_lowres_x2g_tiles,
                    plan->d_lowres_x2h_tiles[0], plan->d_lowres_x2h_tiles[1], plan->d_lowres_x2h_tiles[2],
                    plan->d_lowres_x2i_tiles[0], plan->d_lowres_x2i_tiles[1]};
-    for (void* q : old)
-        if (q) cudaFree(q);
+    for (void* q : old) plan_free(plan, q);
     plan->d_shapes = nullptr; plan->d_tab = nullptr; plan->d_lowres_tiles = nullptr; plan->d_lowres_x2_tiles = nullptr;
     plan->d_lowres_x2w_tiles = nullptr; plan->d_lowres_x2w4_tiles = nullptr; plan->d_lowres_x2_rest_tiles = nullptr;
-    int rc = upload(shapes, &plan->d_shapes);
+    int rc = upload(plan, shapes, &plan->d_shapes);
     plan->d_lowres_x2g_tiles = nullptr;
-    if (rc == ROD_OK) rc = upload(x2g_tiles, &plan->d_lowres_x2g_tiles);
+    if (rc == ROD_OK) rc = upload(plan, x2g_tiles, &plan->d_lowres_x2g_tiles);
     for (int u = 0; u < 2; ++u) {
         plan->d_lowres_x2i_tiles[u] = nullptr;
-        if (rc == ROD_OK) rc = upload(x2i_tiles[u], &plan->d_lowres_x2i_tiles[u]);
+        if (rc == ROD_OK) rc = upload(plan, x2i_tiles[u], &plan->d_lowres_x2i_tiles[u]);
     }
     for (int u = 0; u < 3; ++u) {
         plan->d_lowres_x2p_tiles[u] = nullptr;
-        if (rc == ROD_OK) rc = upload(x2p_tiles[u], &plan->d_lowres_x2p_tiles[u]);
+        if (rc == ROD_OK) rc = upload(plan, x2p_tiles[u], &plan->d_lowres_x2p_tiles[u]);
         plan->d_lowres_x2f_tiles[u] = nullptr;
-        if (rc == ROD_OK) rc = upload(x2f_tiles[u], &plan->d_lowres_x2f_tiles[u]);
+        if (rc == ROD_OK) rc = upload(plan, x2f_tiles[u], &plan->d_lowres_x2f_tiles[u]);
         plan->d_lowres_x2h_tiles[u] = nullptr;
-        if (rc == ROD_OK) rc = upload(x2h_tiles[u], &plan->d_lowres_x2h_tiles[u]);
+        if (rc == ROD_OK) rc = upload(plan, x2h_tiles[u], &plan->d_lowres_x2h_tiles[u]);
     }
-    if (rc == ROD_OK) rc = upload(blob, &plan->d_tab);
-    if (rc == ROD_OK) rc = upload(gen_tiles, &plan->d_lowres_tiles);
-    if (rc == ROD_OK) rc = upload(x2_tiles, &plan->d_lowres_x2_tiles);
-    if (rc == ROD_OK) rc = upload(x2w_tiles, &plan->d_lowres_x2w_tiles);
-    if (rc == ROD_OK) rc = upload(x2w4_tiles, &plan->d_lowres_x2w4_tiles);
-    if (rc == ROD_OK) rc = upload(x2_rest_tiles, &plan->d_lowres_x2_rest_tiles);
+    if (rc == ROD_OK) rc = upload(plan, blob, &plan->d_tab);
+    if (rc == ROD_OK) rc = upload(plan, gen_tiles, &plan->d_lowres_tiles);
+    if (rc == ROD_OK) rc = upload(plan, x2_tiles, &plan->d_lowres_x2_tiles);
+    if (rc == ROD_OK) rc = upload(plan, x2w_tiles, &plan->d_lowres_x2w_tiles);
+    if (rc == ROD_OK) rc = upload(plan, x2w4_tiles, &plan->d_lowres_x2w4_tiles);
+    if (rc == ROD_OK) rc = upload(plan, x2_rest_tiles, &plan->d_lowres_x2_rest_tiles);
     if (rc != ROD_OK) return rc;
     plan->n_lowres_tiles = (int)gen_tiles.size();
     plan->n_lowres_x2_tiles = (int)x2_tiles.size();
@@ -268,14 +291,14 @@ int ensure_letterbox_tables(rod_plan* plan, int out_h, int out_w) {
     for (int i = 0; i < plan->n_images; ++i)
         for (int y = 0; y < out_h; y += kLbTH)
             for (int x = 0; x < out_w; x += kLbTW) tiles.push_back(Tile{i, y, x, 0});
-    if (plan->d_lb) { cudaFree(plan->d_lb); plan->d_lb = nullptr; }
-    if (plan->d_lb_tab) { cudaFree(plan->d_lb_tab); plan->d_lb_tab = nullptr; }
-    if (plan->d_lb_tiles) { cudaFree(plan->d_lb_tiles); plan->d_lb_tiles = nullptr; }
-    int rc = upload(lbs, &plan->d_lb);
+    if (plan->d_lb) { plan_free(plan, plan->d_lb); plan->d_lb = nullptr; }
+    if (plan->d_lb_tab) { plan_free(plan, plan->d_lb_tab); plan->d_lb_tab = nullptr; }
+    if (plan->d_lb_tiles) { plan_free(plan, plan->d_lb_tiles); plan->d_lb_tiles = nullptr; }
+    int rc = upload(plan, lbs, &plan->d_lb);
     if (rc != ROD_OK) return rc;
-    rc = upload(blob, &plan->d_lb_tab);
+    rc = upload(plan, blob, &plan->d_lb_tab);
     if (rc != ROD_OK) return rc;
-    rc = upload(tiles, &plan->d_lb_tiles);
+    rc = upload(plan, tiles, &plan->d_lb_tiles);
     if (rc != ROD_OK) return rc;
     plan->n_lb_tiles = (int)tiles.size();
     plan->lb_all_linear = true;
@@ -356,10 +379,10 @@ extern "C" int rod_plan_create(const rod_image_desc* images, int n_images, rod_p
     }
     plan->n_noise_tiles = (int)nt.size();
     plan->n_blur_tiles = (int)bt.size();
-    if (cudaMalloc((void**)&plan->d_counters, kCounterRing * sizeof(unsigned int)) != cudaSuccess) { rod_plan_destroy(plan); return ROD_ERR_OOM; }
-    int rc = upload(plan->h_images, &plan->d_images);
-    if (rc == ROD_OK) rc = upload(nt, &plan->d_noise_tiles);
-    if (rc == ROD_OK) rc = upload(bt, &plan->d_blur_tiles);
+    if (plan_alloc(plan, (void**)&plan->d_counters, kCounterRing * sizeof(unsigned int)) != cudaSuccess) { rod_plan_destroy(plan); return ROD_ERR_OOM; }
+    int rc = upload(plan, plan->h_images, &plan->d_images);
+    if (rc == ROD_OK) rc = upload(plan, nt, &plan->d_noise_tiles);
+    if (rc == ROD_OK) rc = upload(plan, bt, &plan->d_blur_tiles);
     if (rc != ROD_OK) { rod_plan_destroy(plan); return rc; }
     *out_plan = plan;
     return ROD_OK;
@@ -390,13 +413,13 @@ extern "C" int rod_set_blur_kernel(rod_plan* plan, const float* kernel, int k) {
             taps.push_back(t);
         }
     if (taps.empty()) return ROD_ERR_INVALID_ARG;
-    if (plan->d_f2d_taps) { cudaFree(plan->d_f2d_taps); plan->d_f2d_taps = nullptr; }
-    int rc = upload(taps, &plan->d_f2d_taps);
+    if (plan->d_f2d_taps) { plan_free(plan, plan->d_f2d_taps); plan->d_f2d_taps = nullptr; }
+    int rc = upload(plan, taps, &plan->d_f2d_taps);
     if (rc != ROD_OK) return rc;
     if (plan->d_f2d_tiles == nullptr) {
         std::vector<Tile> tiles;
         build_grid_tiles(plan->h_images, kF2dTH, kF2dTWB, tiles);
-        rc = upload(tiles, &plan->d_f2d_tiles);
+        rc = upload(plan, tiles, &plan->d_f2d_tiles);
         if (rc != ROD_OK) return rc;
         plan->n_f2d_tiles = (int)tiles.size();
         tile_starts(tiles, plan->n_images, plan->f2d_tile_start);
@@ -409,6 +432,9 @@ extern "C" int rod_set_blur_kernel(rod_plan* plan, const float* kernel, int k) {
 extern "C" void rod_plan_destroy(rod_plan* plan) {
     if (plan == nullptr) return;
     if (plan->inner) rod_plan_destroy(plan->inner);
+    // the arrays go back to a cache and may be handed to the next plan at once: kernels of this plan that are still running
+    // must be done first (what the implicit synchronisation of cudaFree used to guarantee, once instead of thirty times)
+    cudaDeviceSynchronize();
     if (plan->d_patch_clean) cudaFree(plan->d_patch_clean);
     if (plan->d_patch_corrupted) cudaFree(plan->d_patch_corrupted);
     void* ptrs[] = {plan->d_images, plan->d_noise_tiles, plan->d_blur_tiles, plan->d_lowres_tiles, plan->d_lowres_x2_tiles,
@@ -420,8 +446,7 @@ extern "C" void rod_plan_destroy(rod_plan* plan) {
                     plan->d_tab, plan->d_lb, plan->d_lb_tab, plan->d_lb_tiles, plan->d_scratch, plan->d_stage_src,
                     plan->d_f2d_taps, plan->d_f2d_tiles, plan->d_counters,
                     plan->d_stage_dst, plan->d_stage_noise, plan->d_stage_ops};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
+    for (void* p : ptrs) plan_free(plan, p);
     for (cudaStream_t s : plan->streams)
         if (s) cudaStreamDestroy(s);
     for (cudaStream_t s : plan->aux_streams)

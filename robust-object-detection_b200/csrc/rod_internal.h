@@ -145,6 +145,9 @@ struct rod_plan {
     // fork/join of the per-op kernels of a mixed batch (small batches do not fill the GPU one op at a time)
     cudaStream_t aux_streams[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    // device arrays that came from the block cache (plan.cu plan_alloc), with their sizes
+    mutable std::mutex cached_mutex;
+    mutable std::vector<std::pair<void*, size_t>> cached_blocks;
     // fork/join of the LowRes launches of one call (several tile lists: lowres.cu launch_lowres); created on first use
     mutable std::mutex lr_mutex;
     mutable cudaStream_t lr_streams[2] = {nullptr, nullptr};
