@@ -438,19 +438,35 @@ size_t round_block(size_t n) {
     if (r > (64u << 20)) r = (n + (64u << 20) - 1) / (64u << 20) * (64u << 20);   // large blocks: multiples of 64 MiB
     return r;
 }
+size_t g_cache_bytes = 0;                                     // bytes parked in the cache
+size_t cache_limit() {   // more than this is handed back to the driver (knob: ROD_BLOCK_CACHE_MB, default 16 GiB)
+    static const size_t lim = [] {
+        const char* e = getenv("ROD_BLOCK_CACHE_MB");
+        return (size_t)(e && atol(e) >= 0 ? atol(e) : 16384) << 20;
+    }();
+    return lim;
+}
 cudaError_t cached_alloc(int dev, void** p, size_t n) {
     const size_t r = round_block(n);
     {
         std::lock_guard<std::mutex> lock(g_cache_mutex);
         auto it = g_cache.find({dev, r});
-        if (it != g_cache.end()) { *p = it->second; g_cache.erase(it); return cudaSuccess; }
+        if (it != g_cache.end()) { *p = it->second; g_cache.erase(it); g_cache_bytes -= r; return cudaSuccess; }
     }
     return cudaMalloc(p, r);
 }
 void cached_free(int dev, void* p, size_t n) {   // dev: the device the block was allocated on
     if (p == nullptr) return;
-    std::lock_guard<std::mutex> lock(g_cache_mutex);
-    g_cache.insert({{dev, round_block(n)}, p});
+    const size_t r = round_block(n);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        if (g_cache_bytes + r <= cache_limit()) {
+            g_cache.insert({{dev, r}, p});
+            g_cache_bytes += r;
+            return;
+        }
+    }
+    cudaFree(p);
 }
 }  // namespace
 
@@ -464,6 +480,7 @@ extern "C" void rod_jpeg_trim(void) {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     for (auto& kv : g_cache) cudaFree(kv.second);
     g_cache.clear();
+    g_cache_bytes = 0;
 }
 
 struct rod_jpeg_encoder {

@@ -324,6 +324,8 @@ using namespace rod;
 namespace {
 std::mutex g_host_mutex;
 std::multimap<size_t, void*> g_host_cache;   // rounded size -> free page-locked block
+size_t g_host_cache_bytes = 0;
+constexpr size_t kHostCacheLimit = (size_t)4 << 30;   // page-locked memory parked here at most
 size_t round_host(size_t n) {
     size_t r = 1 << 20;
     while (r < n) r <<= 1;
@@ -334,14 +336,22 @@ cudaError_t host_cache_alloc(void** p, size_t n) {
     {
         std::lock_guard<std::mutex> lock(g_host_mutex);
         auto it = g_host_cache.find(r);
-        if (it != g_host_cache.end()) { *p = it->second; g_host_cache.erase(it); return cudaSuccess; }
+        if (it != g_host_cache.end()) { *p = it->second; g_host_cache.erase(it); g_host_cache_bytes -= r; return cudaSuccess; }
     }
     return cudaHostAlloc(p, r, cudaHostAllocDefault);
 }
 void host_cache_free(void* p, size_t n) {
     if (p == nullptr) return;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    g_host_cache.insert({round_host(n), p});
+    const size_t r = round_host(n);
+    {
+        std::lock_guard<std::mutex> lock(g_host_mutex);
+        if (g_host_cache_bytes + r <= kHostCacheLimit) {
+            g_host_cache.insert({r, p});
+            g_host_cache_bytes += r;
+            return;
+        }
+    }
+    cudaFreeHost(p);
 }
 }  // namespace
 
@@ -349,6 +359,7 @@ extern "C" void rod_jpegdec_trim(void) {
     std::lock_guard<std::mutex> lock(g_host_mutex);
     for (auto& kv : g_host_cache) cudaFreeHost(kv.second);
     g_host_cache.clear();
+    g_host_cache_bytes = 0;
 }
 
 struct rod_jpeg_decoder {
