@@ -509,11 +509,17 @@ struct rod_jpeg_encoder {
 
 extern "C" void rod_jpeg_destroy(rod_jpeg_encoder* e) {
     if (e == nullptr) return;
-    // (the stream-ordered work of the last rod_jpeg_encode is complete: rod_jpeg_download synchronises; a caller that
-    // never downloaded must synchronise its stream before destroying the encoder)
-    void* small[] = {e->d_images, e->d_mcu_image, e->d_coef_tiles, e->d_tables, e->d_total_bits, e->d_out_len, e->d_ff_count, e->d_chunk_first};
-    for (void* q : small)
-        if (q) cudaFree(q);
+    // every buffer goes to the block cache and may be handed out again at once: kernels still reading them must be done
+    cudaDeviceSynchronize();
+    const size_t n = (size_t)e->n_images;
+    cached_free(e->device, e->d_images, sizeof(JpegImage) * n);
+    cached_free(e->device, e->d_mcu_image, sizeof(uint32_t) * e->h_mcu_image.size());
+    cached_free(e->device, e->d_coef_tiles, sizeof(CoefTile) * (size_t)e->n_coef_tiles);
+    cached_free(e->device, e->d_tables, sizeof(jpeg::Tables));
+    cached_free(e->device, e->d_total_bits, sizeof(uint32_t) * n);
+    cached_free(e->device, e->d_out_len, sizeof(uint32_t) * n);
+    cached_free(e->device, e->d_ff_count, sizeof(uint32_t) * (size_t)e->total_chunks);
+    cached_free(e->device, e->d_chunk_first, sizeof(uint32_t) * n);
     cached_free(e->device, e->d_coef, (size_t)e->total_mcu * 6 * 64 * sizeof(int16_t));
     cached_free(e->device, e->d_mcu_bits, sizeof(uint32_t) * (size_t)e->total_mcu);
     cached_free(e->device, e->d_raw, e->raw_bytes + 64);
@@ -590,7 +596,7 @@ extern "C" int rod_jpeg_create(const rod_image_desc* images, int n_images, const
         e->max_chunks = std::max(e->max_chunks, nc);
     }
     cudaError_t err = cudaSuccess;
-    auto alloc = [&](void** p, size_t n) { if (err == cudaSuccess) err = cudaMalloc(p, n); };
+    auto alloc = [&](void** p, size_t n) { if (err == cudaSuccess) err = cached_alloc(e->device, p, n); };   // (sizes repeated in rod_jpeg_destroy)
     alloc((void**)&e->d_coef_tiles, sizeof(CoefTile) * ctiles.size());
     if (err == cudaSuccess) err = cudaMemcpy(e->d_coef_tiles, ctiles.data(), sizeof(CoefTile) * ctiles.size(), cudaMemcpyHostToDevice);
     alloc((void**)&e->d_images, sizeof(JpegImage) * n_images);
