@@ -54,6 +54,15 @@ if "jpeg" in which:   # device JPEG encoder on the 64-image batch (uniform noise
         N.check(N.lib().rod_jpeg_encode(enc._h, _ptr(src), None), "rod_jpeg_encode")
     torch.cuda.synchronize()
     del enc
+if "jpegdec" in which:   # device JPEG decoder on 64 smooth files of the batch's size (one decode: every kernel of the chain)
+    import cv2
+    from robust_object_detection_b200.jpeg import JpegDecoder
+    rng = np.random.default_rng(3)
+    files = [cv2.imencode(".jpg", cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 3.0))[1].tobytes() for _ in range(8)] * (n // 8)
+    dec = JpegDecoder(files, [i * 3 * h * w for i in range(len(files))])
+    dec.decode(dst)
+    assert (dec.status() == 0).all()
+    del dec
 if "mixed" in which:
     shapes = [(1080, 1920), (1079, 1917), (1050, 1400), (1500, 2000)] * 8
     rp = CorruptionPlan.ragged(shapes)
