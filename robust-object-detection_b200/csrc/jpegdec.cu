@@ -277,12 +277,17 @@ __global__ void __launch_bounds__(256) jpegdec_color_kernel(JpegDecParams p) {
     const int nv = min(4, im.w - x0);
     const uint32_t y4 = *reinterpret_cast<const uint32_t*>(yp + y * ypitch + x0);   // (the plane is padded to whole blocks)
     uint32_t w[3] = {0u, 0u, 0u};   // the twelve output bytes
+    int cb[4] = {128, 128, 128, 128}, cr[4] = {128, 128, 128, 128};
+    if (im.ncomp == 3) {
+        chroma_quad(cbp, cpitch, L.hs, L.vs, cw, ch, x0, y, cb);
+        chroma_quad(crp, cpitch, L.hs, L.vs, cw, ch, x0, y, cr);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int xx = min(x0 + i, im.w - 1), yy = (int)((y4 >> (8 * i)) & 0xFFu);
+        const int yy = (int)((y4 >> (8 * i)) & 0xFFu);
         uint8_t t[3];
         if (im.ncomp == 1) t[0] = t[1] = t[2] = (uint8_t)yy;
-        else ycc_to_bgr(yy, chroma_at(cbp, cpitch, L.hs, L.vs, cw, ch, xx, y), chroma_at(crp, cpitch, L.hs, L.vs, cw, ch, xx, y), t);
+        else ycc_to_bgr(yy, cb[i], cr[i], t);
 #pragma unroll
         for (int c = 0; c < 3; ++c) w[(3 * i + c) >> 2] |= (uint32_t)t[c] << (8 * ((3 * i + c) & 3));
     }

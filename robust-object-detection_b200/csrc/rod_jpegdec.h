@@ -382,6 +382,38 @@ RJ_HD int chroma_at(const uint8_t* plane, long pitch, int hs, int vs, int cw, in
     return plane[(long)y * pitch + x];
 }
 
+// The chroma samples of the four output pixels x0 .. x0 + 3 (x0 a multiple of 4) of row y in one go: the same values as four
+// chroma_at calls, with the two or three plane columns they share read once.  Pixels at or beyond the image width get
+// unspecified values.
+RJ_HD void chroma_quad(const uint8_t* plane, long pitch, int hs, int vs, int cw, int ch, int x0, int y, int* o) {
+    if (hs == 1) {
+        const uint8_t* r = plane + (long)y * pitch + x0;   // (planes are padded to whole blocks: reading 4 bytes is safe)
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+        return;
+    }
+    const int c0 = x0 >> 1;
+    const int cl = c0 > 0 ? c0 - 1 : 0, c1 = c0 + 1 < cw ? c0 + 1 : cw - 1, c2 = c0 + 2 < cw ? c0 + 2 : cw - 1;
+    if (vs == 2) {
+        const int cy = y >> 1;
+        int ny = (y & 1) ? cy + 1 : cy - 1;
+        ny = ny < 0 ? 0 : (ny > ch - 1 ? ch - 1 : ny);
+        const uint8_t* r0 = plane + (long)cy * pitch;
+        const uint8_t* r1 = plane + (long)ny * pitch;
+        const int sl = 3 * r0[cl] + r1[cl], s0 = 3 * r0[c0] + r1[c0], s1 = 3 * r0[c1] + r1[c1], s2 = 3 * r0[c2] + r1[c2];
+        o[0] = c0 == 0 ? (4 * s0 + 8) >> 4 : (3 * s0 + sl + 8) >> 4;
+        o[1] = c0 == cw - 1 ? (4 * s0 + 7) >> 4 : (3 * s0 + s1 + 7) >> 4;
+        o[2] = (3 * s1 + s0 + 8) >> 4;
+        o[3] = c0 + 1 >= cw - 1 ? (4 * s1 + 7) >> 4 : (3 * s1 + s2 + 7) >> 4;
+        return;
+    }
+    const uint8_t* r0 = plane + (long)y * pitch;
+    const int vl = r0[cl], v0 = r0[c0], v1 = r0[c1], v2 = r0[c2];
+    o[0] = c0 == 0 ? v0 : (3 * v0 + vl + 1) >> 2;
+    o[1] = c0 == cw - 1 ? v0 : (3 * v0 + v1 + 2) >> 2;
+    o[2] = (3 * v1 + v0 + 1) >> 2;
+    o[3] = c0 + 1 >= cw - 1 ? v1 : (3 * v1 + v2 + 2) >> 2;
+}
+
 // jdcolor.c ycc_rgb_convert (SCALEBITS 16), written as B, G, R
 RJ_HD void ycc_to_bgr(int y, int cb, int cr, uint8_t* bgr) {
     cb -= 128; cr -= 128;

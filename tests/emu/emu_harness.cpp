@@ -1204,11 +1204,22 @@ extern "C" int emu_jpeg_decode_mode(const uint8_t* file, long n, uint8_t* out, l
     if ((long)im.h * im.w * 3 > out_cap) return 6;
     const int cw = (im.w + L.hs - 1) / L.hs, ch = (im.h + L.vs - 1) / L.vs;
     for (int y = 0; y < im.h; ++y)
-        for (int x = 0; x < im.w; ++x) {
-            uint8_t* o = out + ((size_t)y * im.w + x) * 3;
-            const int yy = yp[(size_t)y * ypitch + x];
-            if (im.ncomp == 1) { o[0] = o[1] = o[2] = (uint8_t)yy; continue; }
-            ycc_to_bgr(yy, chroma_at(cbp.data(), cpitch, L.hs, L.vs, cw, ch, x, y), chroma_at(crp.data(), cpitch, L.hs, L.vs, cw, ch, x, y), o);
+        for (int x0 = 0; x0 < im.w; x0 += 4) {   // four pixels at a time, like a thread of jpegdec_color_kernel
+            int cb[4] = {128, 128, 128, 128}, cr[4] = {128, 128, 128, 128};
+            if (im.ncomp == 3) {
+                chroma_quad(cbp.data(), cpitch, L.hs, L.vs, cw, ch, x0, y, cb);
+                chroma_quad(crp.data(), cpitch, L.hs, L.vs, cw, ch, x0, y, cr);
+            }
+            for (int i = 0; i < 4 && x0 + i < im.w; ++i) {
+                uint8_t* o = out + ((size_t)y * im.w + x0 + i) * 3;
+                const int yy = yp[(size_t)y * ypitch + x0 + i];
+                if (im.ncomp == 1) { o[0] = o[1] = o[2] = (uint8_t)yy; continue; }
+                ycc_to_bgr(yy, cb[i], cr[i], o);
+                // (the per-pixel form of the same arithmetic must agree)
+                uint8_t q[3];
+                ycc_to_bgr(yy, chroma_at(cbp.data(), cpitch, L.hs, L.vs, cw, ch, x0 + i, y), chroma_at(crp.data(), cpitch, L.hs, L.vs, cw, ch, x0 + i, y), q);
+                if (q[0] != o[0] || q[1] != o[1] || q[2] != o[2]) return 9;
+            }
         }
     return 0;
 }
