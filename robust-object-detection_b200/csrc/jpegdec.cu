@@ -21,6 +21,7 @@
 //                                    straight into the caller's HWC batch (the layout of a rod_plan)
 // Files of another layout (progressive, EXIF rotation, CMYK, 4:1:1 ...) are reported per image; the caller
 // decodes those with the host codec.  No CPU decoding in here.
+#include <algorithm>
 #include <map>
 #include <string>
 #include <thread>
@@ -40,7 +41,7 @@ struct JpegDecParams {
     uint8_t* planes;
     uint8_t* pixels;
     int32_t* status;
-    const uint32_t* block_start;   // [n + 1] prefix sums of the number of blocks
+    const uint32_t* block_start;   // [n + 1] prefix sums of the number of blocks (the kernels use the differences)
     const uint32_t* quad_start;    // [n + 1] prefix sums of h * ceil(w / 4)
     const SegRec* segs;            // restart intervals of all images (an image without restart markers: one)
     const uint32_t* sub_start;     // [n_segs + 1] prefix sums of the number of subsequences
@@ -209,23 +210,12 @@ __global__ void __launch_bounds__(256) jpegdec_dc_kernel(JpegDecParams p) {
     }
 }
 
-// image that owns flat index i of a prefix-sum array
-__device__ __forceinline__ int owner_of(const uint32_t* start, int n, uint32_t i) {
-    int lo = 0, hi = n;   // start[lo] <= i < start[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(start + mid) <= i) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
-__global__ void __launch_bounds__(128) jpegdec_idct_kernel(JpegDecParams p) {
-    const uint32_t gi = blockIdx.x * 128u + threadIdx.x;
-    if (gi >= __ldg(p.block_start + p.n_images)) return;
-    const int img = owner_of(p.block_start, p.n_images, gi);
+__global__ void __launch_bounds__(128) jpegdec_idct_kernel(JpegDecParams p) {   // grid (blocks of the largest image / 128, image)
+    const int img = blockIdx.y;
     const ImageRec im = p.images[img];
-    if (__ldg(p.status + img) != 0) return;
-    const uint32_t b = gi - __ldg(p.block_start + img);
+    if (im.h == 0 || __ldg(p.status + img) != 0) return;
+    const uint32_t b = blockIdx.x * 128u + threadIdx.x;
+    if (b >= __ldg(p.block_start + img + 1) - __ldg(p.block_start + img)) return;
     const Layout L = layout_of(im);
     const uint32_t yblocks = (uint32_t)(L.nl * L.mcus), cblocks = (uint32_t)L.mcus;
     int comp;
@@ -258,13 +248,12 @@ __global__ void __launch_bounds__(128) jpegdec_idct_kernel(JpegDecParams p) {
     for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2*>(dst + r * pitch) = *reinterpret_cast<const uint2*>(o + 8 * r);
 }
 
-__global__ void __launch_bounds__(256) jpegdec_color_kernel(JpegDecParams p) {
-    const uint32_t gi = blockIdx.x * 256u + threadIdx.x;
-    if (gi >= __ldg(p.quad_start + p.n_images)) return;
-    const int img = owner_of(p.quad_start, p.n_images, gi);
+__global__ void __launch_bounds__(256) jpegdec_color_kernel(JpegDecParams p) {   // grid (quads of the largest image / 256, image)
+    const int img = blockIdx.y;
     const ImageRec im = p.images[img];
-    if (__ldg(p.status + img) != 0) return;
-    const uint32_t k = gi - __ldg(p.quad_start + img);
+    if (im.h == 0 || __ldg(p.status + img) != 0) return;
+    const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+    if (k >= __ldg(p.quad_start + img + 1) - __ldg(p.quad_start + img)) return;
     const Layout L = layout_of(im);
     const int qw = (im.w + 3) >> 2;   // groups of four pixels per row
     const int cw = (im.w + L.hs - 1) / L.hs, ch = (im.h + L.vs - 1) / L.vs;
@@ -604,9 +593,18 @@ extern "C" int rod_jpegdec_decode(rod_jpeg_decoder* d, uint8_t* pixels, void* st
     jpegdec_scan_kernel<<<p.n_segs, 256, 0, st>>>(p);
     jpegdec_write_kernel<<<n_ctas, kHuffThreads, 0, st>>>(p);
     jpegdec_dc_kernel<<<dim3(p.n_segs, 3), 256, 0, st>>>(p);
-    const uint32_t blocks = d->h_block_start[n], quads = d->h_quad_start[n];
-    jpegdec_idct_kernel<<<(blocks + 127) / 128, 128, 0, st>>>(p);
-    jpegdec_color_kernel<<<(quads + 255) / 256, 256, 0, st>>>(p);
+    uint32_t max_blocks = 0, max_quads = 0;
+    for (int i = 0; i < n; ++i) {
+        max_blocks = std::max(max_blocks, d->h_block_start[i + 1] - d->h_block_start[i]);
+        max_quads = std::max(max_quads, d->h_quad_start[i + 1] - d->h_quad_start[i]);
+    }
+    for (int i0 = 0; i0 < n; i0 += 65535) {   // (grid.y is limited to 65535)
+        JpegDecParams q = p;
+        q.images += i0; q.status += i0; q.block_start += i0; q.quad_start += i0;
+        const int ny = std::min(n - i0, 65535);
+        jpegdec_idct_kernel<<<dim3((max_blocks + 127) / 128, ny), 128, 0, st>>>(q);
+        jpegdec_color_kernel<<<dim3((max_quads + 255) / 256, ny), 256, 0, st>>>(q);
+    }
     ROD_CUDA(cudaGetLastError());
     return ROD_OK;
 }
