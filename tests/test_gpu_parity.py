@@ -1500,3 +1500,34 @@ def test_jpeg_decoder_matches_golden(torch_):
     got = pix.cpu().numpy()
     for c, (h, w), off in zip(g["cases"], shapes, plan.src_offsets):
         assert hashlib.sha256(got[off:off + 3 * h * w].tobytes()).hexdigest() == c["pixels_sha256"], c["name"]
+
+
+def test_jpeg_codec_full_size_config4_round_trip(torch_):
+    """Both halves of the device JPEG codec at the size of BASELINE config 4: 1610 VisDrone-shaped frames (8 frame sizes,
+    same draw as bench.py) in one ragged batch are encoded on the device, the 1610 files are decoded back on the device.
+    Parity at this size by replication: one distinct frame per size, so every file must equal cv2.imencode's file for that
+    frame and every decoded frame cv2.imdecode's pixels of it (8 host codec runs instead of 1610)."""
+    import cv2
+    from robust_object_detection_b200.batch import CorruptionPlan
+    from robust_object_detection_b200.jpeg import JpegDecoder, JpegEncoder
+    pool = [(765, 1360), (1050, 1400), (788, 1400), (1078, 1916), (1080, 1920), (1500, 2000), (540, 960), (360, 480)]
+    kinds = np.random.default_rng(4000).integers(0, 8, 1610)
+    shapes = [pool[i] for i in kinds]
+    base = [cv2.GaussianBlur(synth(9100 + i, h, w), (0, 0), 2.0) for i, (h, w) in enumerate(pool)]
+    want_files = [cv2.imencode(".jpg", b)[1] for b in base]
+    want_pixels = [torch_.from_numpy(cv2.imdecode(f, cv2.IMREAD_COLOR).reshape(-1)).cuda() for f in want_files]
+    dbase = [torch_.from_numpy(b.reshape(-1)).cuda() for b in base]
+    plan = CorruptionPlan.ragged(shapes)
+    src = torch_.zeros(plan.src_bytes, dtype=torch_.uint8, device="cuda")
+    for off, k in zip(plan.src_offsets, kinds):
+        src[off:off + dbase[k].numel()] = dbase[k]
+    files = JpegEncoder(shapes, plan.src_offsets).encode(src)
+    for i in range(1610):
+        assert files[i] is not None and files[i] == want_files[kinds[i]].tobytes(), i
+    back = torch_.empty_like(src)
+    dec = JpegDecoder(files, plan.src_offsets, host_threads=16)
+    assert dec.shapes == shapes
+    dec.decode(back)
+    assert (dec.status() == 0).all()
+    for i, (off, k) in enumerate(zip(plan.src_offsets, kinds)):
+        assert torch_.equal(back[off:off + want_pixels[k].numel()], want_pixels[k]), i
