@@ -328,6 +328,16 @@ class _TreeRun:
                 if not f.result():
                     raise IOError("cv2.imwrite failed")
 
+    def submit_writes(self, jobs):
+        """[(function, path, payload)] spread over the I/O threads, a slice of the files per task (a future per file costs
+        more than writing a VisDrone-sized JPEG to a page-cached file system)"""
+        n = max(1, min(len(jobs), self.pool._max_workers))
+
+        def write_slice(part):
+            return all(fn(path, payload) for fn, path, payload in part)
+
+        return [self.pool.submit(write_slice, jobs[k::n]) for k in range(n)]
+
     def close(self):
         self.drain()
         self.pool.shutdown()
@@ -375,6 +385,7 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
             prev = pos
         return runs
 
+    dst_dir_s = str(dst_img_dir)
     i, batch_paths, futs = submit_loads(0)
     while batch_paths:
         cur_paths, cur_futs = batch_paths, futs
@@ -394,7 +405,7 @@ def _process_images(src_img_dir: Path, dst_img_dir: Path, variant: str, run: "_T
             for r in dev_runs:
                 run.drain(keep=1)  # the encoder's download ring has three buffers: at most two batches of writes are pending
                 jobs = _corrupt_encode(variant, r, run)
-                run.pending.append([run.pool.submit(fn, str(dst_img_dir / p.name), payload) for fn, p, payload in jobs])
+                run.pending.append(run.submit_writes([(fn, os.path.join(dst_dir_s, p.name), payload) for fn, p, payload in jobs]))
             continue
         work = readable_runs(cur_paths, cur_futs)
         i, batch_paths, futs = submit_loads(i)  # the next batch decodes while this one is corrupted and encoded
