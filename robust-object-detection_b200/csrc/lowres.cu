@@ -1846,8 +1846,20 @@ namespace {
 struct LrStreams {
     cudaStream_t s[3];
     int n, i;
-    cudaStream_t pick() { const cudaStream_t r = s[i]; i = (i + 1) % n; return r; }
+    bool lanes = false;   // issue-bound kernels on s[1], the HBM-bound ones on s[0]: a kernel of each kind shares every SM
+    cudaStream_t pick() {
+        if (lanes && n == 3) return s[0];
+        const cudaStream_t r = s[i]; i = (i + 1) % n; return r;
+    }
+    cudaStream_t lane(bool issue_bound) { return (lanes && n == 3 && issue_bound) ? s[1] : pick(); }
 };
+
+int env_int(const char* name, int lo, int hi, int dflt) {
+    const char* e = getenv(name);
+    if (!e) return dflt;
+    const int v = atoi(e);
+    return (v >= lo && v <= hi) ? v : dflt;
+}
 
 int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const uint8_t* opcodes, LrStreams& ls,
                         int img_lo, int img_hi) {
@@ -1882,7 +1894,7 @@ int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, 
         const int t_lo = plan->lowres_x2g_tile_start[img_lo], t_hi = plan->lowres_x2g_tile_start[img_hi];
         if (t_hi > t_lo) {
             LowresX2wParams p;
-            const cudaStream_t lst = ls.pick();
+            const cudaStream_t lst = ls.lane(true);
             p.images = plan->d_images;
             p.tiles = plan->d_lowres_x2g_tiles + t_lo;
             p.n_tiles = t_hi - t_lo;
@@ -1909,12 +1921,13 @@ int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, 
         }
     }
     // ... and of those, the shapes with a regular y axis: the low-res-row loop kernel ([0]: odd h, carried tap row; [1]: even h)
+    auto launch_x2i = [&]() -> int {
     for (int u = 0; u < 2; ++u) {
         if (plan->n_lowres_x2i_tiles[u] == 0) continue;
         const int t_lo = plan->lowres_x2i_tile_start[u][img_lo], t_hi = plan->lowres_x2i_tile_start[u][img_hi];
         if (t_hi <= t_lo) continue;
         LowresX2wParams p;
-        const cudaStream_t lst = ls.pick();
+        const cudaStream_t lst = ls.lane(true);
         p.images = plan->d_images;
         p.tiles = plan->d_lowres_x2i_tiles[u] + t_lo;
         p.n_tiles = t_hi - t_lo;
@@ -1928,10 +1941,11 @@ int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, 
         int per_sm = 3;  // knob ROD_X2I_CTAS = 2 | 3 | 4
         const char* e_ctas = getenv("ROD_X2I_CTAS");
         if (e_ctas && atoi(e_ctas) >= 2 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
+        const int grid_mult = env_int("ROD_X2I_GRID", 1, 4, per_sm);
 #define ROD_X2I_LAUNCH(C, B)                                                                                              \
     do {                                                                                                                  \
         ROD_CUDA(cudaFuncSetAttribute(lowres_x2i_kernel<C, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        lowres_x2i_kernel<C, B><<<grid_for(plan, ctas, B), 128, smem, lst>>>(p);                                       \
+        lowres_x2i_kernel<C, B><<<grid_for(plan, ctas, grid_mult), 128, smem, lst>>>(p);                                       \
     } while (0)
         if (u == 0) {
             if (per_sm == 2) ROD_X2I_LAUNCH(true, 2);
@@ -1945,6 +1959,10 @@ int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, 
 #undef ROD_X2I_LAUNCH
         ROD_CUDA(cudaGetLastError());
     }
+    return ROD_OK;
+    };
+    const bool x2i_last = env_int("ROD_LR_X2I_LAST", 0, 1, 0) != 0;
+    if (!x2i_last) { const int rc = launch_x2i(); if (rc != ROD_OK) return rc; }
     // exact-2x shapes: warp-marching kernel when the rows are 4-byte aligned, full-width strips otherwise
     const int n_packed = plan->n_lowres_x2p_tiles[0] + plan->n_lowres_x2p_tiles[1] + plan->n_lowres_x2p_tiles[2] +
                          plan->n_lowres_x2f_tiles[0] + plan->n_lowres_x2f_tiles[1] + plan->n_lowres_x2f_tiles[2] +
@@ -1960,7 +1978,7 @@ int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, 
             const int t_lo = st[img_lo], t_hi = st[img_hi];
             if (t_hi <= t_lo) continue;
             LowresX2wParams p;
-            const cudaStream_t lst = ls.pick();
+            const cudaStream_t lst = ls.lane(kind != 0);
             p.images = plan->d_images;
             p.tiles = (kind == 0 ? plan->d_lowres_x2p_tiles[u] : kind == 1 ? plan->d_lowres_x2f_tiles[u] : plan->d_lowres_x2h_tiles[u]) + t_lo;
             p.n_tiles = t_hi - t_lo;
@@ -1974,6 +1992,7 @@ int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, 
             int per_sm = kind == 0 ? 3 : 4;  // the float-tap kernel is issue-bound: more warps win (4: 3.69, 3: 3.34, 2: 2.74 TB/s)
             const char* e_ctas = getenv(kind == 0 ? "ROD_X2P_CTAS" : kind == 1 ? "ROD_X2F_CTAS" : "ROD_X2H_CTAS");
             if (e_ctas && atoi(e_ctas) >= 2 && atoi(e_ctas) <= 4) per_sm = atoi(e_ctas);
+            const int grid_mult = env_int(kind == 0 ? "ROD_X2P_GRID" : kind == 1 ? "ROD_X2F_GRID" : "ROD_X2H_GRID", 1, 4, per_sm);
             // the list's copy unit holds for offsets and pitches; the base pointers may be less aligned
             const uintptr_t base = (uintptr_t)src | (uintptr_t)dst;
             const int unit = std::min(u == 0 ? 16 : (u == 1 ? 8 : 4), (base & 15) == 0 ? 16 : ((base & 7) == 0 ? 8 : 4));
@@ -1981,7 +2000,7 @@ int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, 
 #define ROD_STAGED_LAUNCH(K, U, B)                                                                         \
     do {                                                                                                   \
         ROD_CUDA(cudaFuncSetAttribute(K<U, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        K<U, B><<<grid_for(plan, ctas, B), 128, smem, lst>>>(p);                                        \
+        K<U, B><<<grid_for(plan, ctas, grid_mult), 128, smem, lst>>>(p);                                        \
     } while (0)
 #define ROD_STAGED_LAUNCH_B(K, U)                                 \
     do {                                                          \
@@ -2004,6 +2023,7 @@ int launch_lowres_lists(const rod_plan* plan, const uint8_t* src, uint8_t* dst, 
             ROD_CUDA(cudaGetLastError());
         }
     }
+    if (x2i_last) { const int rc = launch_x2i(); if (rc != ROD_OK) return rc; }
     if (use_bands) {
         const size_t smem = 4 * sizeof(X2wWarpTables);
         for (int pass = 0; pass < 2; ++pass) {  // 0: images with 8-byte aligned rows (64-bit loads), 1: the others
@@ -2102,6 +2122,7 @@ int launch_lowres(const rod_plan* plan, const uint8_t* src, uint8_t* dst, const 
     for (auto& s : plan->lr_streams) ROD_CUDA(cudaStreamWaitEvent(s, plan->lr_ev_fork, 0));
     ls.s[1] = plan->lr_streams[0]; ls.s[2] = plan->lr_streams[1];
     ls.n = 3;
+    ls.lanes = env_int("ROD_LR_LANES", 0, 1, 0) != 0;
     int rc = launch_lowres_lists(plan, src, dst, opcodes, ls, img_lo, img_hi);
     for (int i = 0; i < 2; ++i) {  // the join is executed on every path
         cudaError_t e = cudaEventRecord(plan->lr_ev_join[i], plan->lr_streams[i]);

@@ -47,7 +47,8 @@ WORKLOADS = {
     "odd_only_96": [POOL[8 + i % 3] for i in range(96)],
 }
 KNOBS = ("ROD_X2_PACKED", "ROD_X2P_CTAS", "ROD_X2_FLOAT_STAGED", "ROD_X2F_CTAS", "ROD_X2_ODD_STAGED", "ROD_X2G_CTAS",
-         "ROD_X2G_BAND_DIV", "ROD_X2_REGULAR", "ROD_X2H_CTAS", "ROD_X2_BAND", "ROD_X2_ODD_REGULAR", "ROD_X2I_CTAS")
+         "ROD_X2G_BAND_DIV", "ROD_X2_REGULAR", "ROD_X2H_CTAS", "ROD_X2_BAND", "ROD_X2_ODD_REGULAR", "ROD_X2I_CTAS",
+         "ROD_X2I_GRID", "ROD_X2P_GRID", "ROD_X2F_GRID", "ROD_X2H_GRID", "ROD_LR_LANES", "ROD_LR_X2I_LAST", "ROD_LR_HELPERS")
 
 # usage: sweep_lowres.py <workload,workload,...> <name:K=V,K=V> <name:K=V> ...   (a bare "name:" is the default setting)
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else list(WORKLOADS)
