@@ -429,6 +429,7 @@ using namespace rod;
 // size, so that building one encoder per batch does not pay cudaMalloc / cudaFree (a device-wide synchronisation) each time.
 #include <map>
 #include <mutex>
+#include <vector>
 namespace {
 std::mutex g_cache_mutex;
 std::multimap<std::pair<int, size_t>, void*> g_cache;   // (device, rounded size) -> free block
@@ -453,7 +454,24 @@ cudaError_t cached_alloc(int dev, void** p, size_t n) {
         auto it = g_cache.find({dev, r});
         if (it != g_cache.end()) { *p = it->second; g_cache.erase(it); g_cache_bytes -= r; return cudaSuccess; }
     }
-    return cudaMalloc(p, r);
+    cudaError_t e = cudaMalloc(p, r);
+    if (e == cudaErrorMemoryAllocation) {   // hand the parked blocks of this device back to the driver and try once more
+        std::vector<void*> parked;
+        {
+            std::lock_guard<std::mutex> lock(g_cache_mutex);
+            for (auto it = g_cache.begin(); it != g_cache.end();) {
+                if (it->first.first == dev) { parked.push_back(it->second); g_cache_bytes -= it->first.second; it = g_cache.erase(it); }
+                else ++it;
+            }
+        }
+        (void)cudaGetLastError();
+        if (!parked.empty()) {
+            cudaDeviceSynchronize();   // blocks are parked after their owner synchronised; this covers the caller's own streams
+            for (void* q : parked) cudaFree(q);
+            e = cudaMalloc(p, r);
+        }
+    }
+    return e;
 }
 void cached_free(int dev, void* p, size_t n) {   // dev: the device the block was allocated on
     if (p == nullptr) return;
