@@ -433,7 +433,8 @@ def test_lowres_marching_kernel_alignments(torch_):
     that is not 4-byte aligned (falls back to the strip kernel)."""
     from robust_object_detection_b200.batch import CorruptionPlan
     shapes = [(765, 1360), (360, 480), (100, 8), (9, 4), (2, 4), (5, 12), (64, 64), (65, 128), (131, 36), (201, 1400),
-              (97, 1916), (540, 960), (33, 2000), (40, 20), (77, 1364), (1080, 1920), (1050, 1400), (41, 44)]
+              (97, 1916), (540, 960), (33, 2000), (40, 20), (77, 1364), (1080, 1920), (1050, 1400), (41, 44),
+              (98, 1916), (6, 244), (4, 248), (10, 1204), (12, 1448)]   # rows at 4- / 8-byte phases, last strips of one (two-pixel) chunk
     imgs = [synth(4200 + i, h, w) for i, (h, w) in enumerate(shapes)]
     want = [orc.apply_lowres(im, 0.5) for im in imgs]
     for align in (4, 256):
