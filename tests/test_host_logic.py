@@ -123,6 +123,41 @@ def test_testset_driver_shards(tmp_path, monkeypatch):
         drv._rank_world()
 
 
+def test_testset_driver_write_slices(tmp_path):
+    """File writes of one batch go to the I/O threads in slices (one future per thread, not per file): every file is
+    written once, a failed write surfaces as IOError when the batch is drained, an empty batch is fine."""
+    import threading
+    from robust_object_detection_b200 import build_corrupted_testsets as drv
+    run = drv._TreeRun()
+    try:
+        lock, seen = threading.Lock(), []
+
+        def write(path, payload):
+            with lock:
+                seen.append((path, payload))
+            with open(path, "wb") as f:
+                f.write(payload)
+            return True
+
+        jobs = [(write, str(tmp_path / f"o{i:03d}.jpg"), bytes([i]) * (i + 1)) for i in range(37)]
+        futs = run.submit_writes(jobs)
+        assert 1 <= len(futs) <= run.pool._max_workers
+        run.pending.append(futs)
+        run.pending.append(run.submit_writes([]))
+        run.drain(keep=1)
+        assert len(run.pending) == 1
+        run.drain()
+        assert sorted(seen) == sorted((q, d) for _, q, d in jobs)
+        for _, q, d in jobs:
+            assert open(q, "rb").read() == d
+        run.pending.append(run.submit_writes([(write, str(tmp_path / "a.jpg"), b"a"), (lambda q, d: False, "b", b"")]))
+        with pytest.raises(IOError):
+            run.drain()
+    finally:
+        run.pending.clear()
+        run.close()
+
+
 _GLOO_WORKER = r"""
 import os, sys, json
 sys.path.insert(0, sys.argv[1])
