@@ -5,11 +5,14 @@
 // (MT19937) feeding the legacy polar Gaussian (numpy/random/src/legacy/legacy-distributions.c legacy_gauss,
 // numpy/random/src/mt19937/mt19937.h mt19937_next_double), one scalar at a time.  In compat mode the GPU kernel
 // consumes that field bit for bit, so the field has to be this exact stream.  This file regenerates it faster without
-// changing a bit: the calling thread produces the MT19937 word stream (a linear recurrence: sequential) in 0.5 MB chunks
-// while the other host threads already run the polar method on the chunks that are ready -- rejection test, log, sqrt
-// and division are independent per candidate pair -- each chunk's accepted pairs are then compacted into the output
-// in order, and the generator state handed back (key, pos, has_gauss, cached gaussian) is exactly what NumPy's would
-// be after the call, so any later np.random use continues on the same stream.
+// changing a bit: the MT19937 word stream is a linear recurrence (sequential), so the calling thread runs the recurrence
+// alone -- in two 2.5 KB buffers that stay in its L1 cache, 0.3 ns per word -- and only publishes the generator STATE at the
+// start of every chunk of 52 blocks; the host threads pick chunks up, regenerate the chunk's words from its state into a
+// buffer of their own (130 KB: L2) and run the polar method on them -- rejection test, log, sqrt and division are
+// independent per candidate pair.  (The first version had the calling thread write the whole 32 MB word stream of a frame
+// to memory for the others to read: 7 of the 9-11 ms of a frame were that thread.)  Each chunk's accepted pairs are then
+// compacted into the output in order, and the generator state handed back (key, pos, has_gauss, cached gaussian) is exactly
+// what NumPy's would be after the call, so any later np.random use continues on the same stream.
 //
 // Bit-exactness rests on: identical integer stream; (a * 2^26 + b) / 2^53 and 2x - 1 exact in double; x1*x1 + x2*x2,
 // the division and sqrt are IEEE operations (this file is built with -ffp-contract=off: no FMA); log() is the same libm
@@ -33,20 +36,16 @@ namespace {
 constexpr int kN = 624, kM = 397;
 constexpr uint32_t kMatrixA = 0x9908b0dfu, kUpper = 0x80000000u, kLower = 0x7fffffffu;
 
-// (cloned for AVX2 with run-time dispatch: both loops vectorise, dependence distances are 227 and 397 words)
-__attribute__((target_clones("avx2", "default"))) void mt_regenerate(uint32_t* mt) {
-    int i = 0;
-    uint32_t y;
-    for (; i < kN - kM; ++i) {
-        y = (mt[i] & kUpper) | (mt[i + 1] & kLower);
-        mt[i] = mt[i + kM] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrixA);
-    }
-    for (; i < kN - 1; ++i) {
-        y = (mt[i] & kUpper) | (mt[i + 1] & kLower);
-        mt[i] = mt[i + (kM - kN)] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrixA);
-    }
-    y = (mt[kN - 1] & kUpper) | (mt[0] & kLower);
-    mt[kN - 1] = mt[kM - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrixA);
+inline uint32_t twist(uint32_t a, uint32_t b) {
+    const uint32_t y = (a & kUpper) | (b & kLower);
+    return (y >> 1) ^ ((0u - (y & 1u)) & kMatrixA);
+}
+// nw := the block of 624 raw state words that follows the block `old` (out of place; cloned for AVX2 with run-time
+// dispatch: all loops vectorise, the only dependence inside a block has distance 227 words)
+__attribute__((target_clones("avx2", "default"))) void mt_next(const uint32_t* __restrict old, uint32_t* __restrict nw) {
+    for (int i = 0; i < kN - kM; ++i) nw[i] = old[i + kM] ^ twist(old[i], old[i + 1]);
+    for (int i = kN - kM; i < kN - 1; ++i) nw[i] = nw[i - (kN - kM)] ^ twist(old[i], old[i + 1]);
+    nw[kN - 1] = nw[kM - 1] ^ twist(old[kN - 1], nw[0]);
 }
 inline uint32_t temper(uint32_t y) {
     y ^= y >> 11;
@@ -73,15 +72,6 @@ inline Candidate candidate(const uint32_t* w) {  // w: four RAW state words (tem
     return c;
 }
 
-template <typename F>
-void parallel_ranges(uint64_t n, int threads, F fn) {
-    threads = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (n + 4095) / 4096));
-    if (threads == 1) { fn(0, 0, n); return; }
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t) pool.emplace_back(fn, t, n * t / threads, n * (t + 1) / threads);
-    for (auto& th : pool) th.join();
-}
-
 }  // namespace
 
 // RandomState state in, field out, state after the call out.  key: 624 words (np.random.get_state()[1]), *pos the
@@ -98,59 +88,94 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
         *has_gauss = 0;
         *cached = 0.0;
     }
-    // raw MT19937 word stream: leftover of the current block, then whole blocks; and the accepted pairs of every chunk before
-    // they are compacted into `out`.  Kept per calling thread between calls: fresh 32 MB buffers per frame cost more in
-    // page faults than generating the words
-    static thread_local std::vector<uint32_t> tl_words;
+    // the generator states at the chunk starts and this thread's chunk of words and of accepted pairs.  Kept per calling
+    // thread between calls
     static thread_local std::vector<float> tl_pairs;
-    std::vector<uint32_t>& words = tl_words;  // (local references: the worker lambdas must see THIS thread's buffers)
-    std::vector<float>& pairs = tl_pairs;
-    constexpr uint64_t kChunk = 1u << 15;     // candidates per work item (128 K words, 0.5 MB)
+    static thread_local std::vector<uint32_t> tl_states, tl_local;
+    std::vector<uint32_t>& states = tl_states;  // (local reference: the worker lambdas must see THIS thread's buffer)
+    constexpr int kBlocksPerChunk = 52;                                  // 52 blocks of 624 words = 8112 candidates of 4 words
+    constexpr uint64_t kChunk = (uint64_t)kBlocksPerChunk * kN / 4;      // candidates per work item
+    constexpr size_t kLocalWords = (size_t)(kBlocksPerChunk + 1) * kN;   // a chunk that starts inside a block touches 53
     while (done < n) {
         const uint64_t need_pairs = (n - done + 1) / 2;
         // candidates to draw this round: expectation 4/pi per accepted pair, plus slack; bounded per round
         uint64_t cand = (uint64_t)((double)need_pairs * 1.2740) + 64;
         cand = std::min<uint64_t>(cand, 1ull << 24);
         const int start_pos = *pos;
+        // the word stream of this round: the rest of the present block (block 0 = key), then `fresh_blocks` whole blocks.
+        // Stream word s is word (start_pos + s) % 624 of block (start_pos + s) / 624.
         const uint64_t in_first = (uint64_t)(kN - start_pos);
         const uint64_t fresh_blocks = (4 * cand > in_first) ? (4 * cand - in_first + kN - 1) / kN : 0;
         const uint64_t total_words = in_first + fresh_blocks * kN;
         cand = total_words / 4;
         const uint64_t n_chunks = (cand + kChunk - 1) / kChunk;
+        const uint64_t base = (uint64_t)(start_pos / kN);   // 1 when the present block is used up (pos == 624), else 0
+        const int off = start_pos - (int)base * kN;         // every chunk starts at this word of block base + 52 c
         try {
-            if (words.size() < total_words) words.resize(total_words);
-            if (pairs.size() < 2 * cand) pairs.resize(2 * cand);
+            if (tl_pairs.size() < 2 * kChunk) tl_pairs.resize(2 * kChunk);
+            if (states.size() < n_chunks * kN) states.resize(n_chunks * kN);
+            if (tl_local.size() < kLocalWords) tl_local.resize(kLocalWords);
         } catch (const std::bad_alloc&) {
             return ROD_ERR_OOM;  // nothing consumed yet in this round: the generator state is still the caller's
         }
-        std::vector<uint32_t> chunk_count((size_t)n_chunks, 0);
-        std::atomic<uint64_t> words_ready{0}, next_chunk{0};
+        // prefix[c] = accepted pairs of the chunks before c, valid once prefix_upto >= c: the thread that finishes chunk c
+        // waits for it (chunks are handed out in order: it is there or about to be), publishes prefix[c + 1] and copies
+        // its pairs -- still in its cache -- to their place in `out`; the need_pairs-th accepted pair ends the round
+        std::vector<uint64_t> prefix((size_t)n_chunks + 1, 0);
+        std::atomic<uint64_t> states_ready{0}, next_chunk{0}, prefix_upto{0};
 
-        // one work item: the accepted pairs of chunk c, in order, as float32 outputs at pairs[2 * c * kChunk ...]
-        auto process_chunk = [&](uint64_t c) {
+        // the raw words of chunk c (candidates [c * kChunk, hi)) from the state at its start -> local[off ...]
+        auto fill_chunk = [&](uint64_t c, uint64_t hi, uint32_t* local) {
+            const uint64_t n_words = (uint64_t)off + 4 * (hi - c * kChunk);
+            const uint64_t n_blocks = (n_words + kN - 1) / kN;   // <= 53
+            memcpy(local, &states[(size_t)c * kN], sizeof(uint32_t) * kN);
+            for (uint64_t b = 1; b < n_blocks; ++b) mt_next(local + (b - 1) * kN, local + b * kN);
+        };
+        // one work item: the accepted pairs of chunk c, in order, as float32 outputs in the thread's buffer, then in `out`
+        auto process_chunk = [&](uint64_t c, uint32_t* local, float* dstp) {
             const uint64_t lo = c * kChunk, hi = std::min(cand, lo + kChunk);
-            float* dstp = &pairs[2 * lo];
-            uint32_t cnt = 0;
-            for (uint64_t i = lo; i < hi; ++i) {
-                const Candidate cd = candidate(&words[4 * i]);
+            fill_chunk(c, hi, local);
+            const uint32_t* w = local + off;
+            uint64_t cnt = 0;
+            for (uint64_t i = 0; i < hi - lo; ++i) {
+                const Candidate cd = candidate(w + 4 * i);
                 if (!cd.ok) continue;
                 const double f = sqrt(-2.0 * log(cd.r2) / cd.r2);
                 dstp[2 * cnt] = (float)(0.0 + sigma * (f * cd.x2));      // returned first
                 dstp[2 * cnt + 1] = (float)(0.0 + sigma * (f * cd.x1));  // the "cached" second value
                 ++cnt;
             }
-            chunk_count[(size_t)c] = cnt;
+            while (prefix_upto.load(std::memory_order_acquire) < c) std::this_thread::yield();
+            const uint64_t p0 = prefix[(size_t)c];
+            prefix[(size_t)c + 1] = p0 + cnt;
+            prefix_upto.store(c + 1, std::memory_order_release);
+            if (p0 < need_pairs) {
+                const uint64_t np = std::min<uint64_t>(cnt, need_pairs - p0);
+                const uint64_t o = done + 2 * p0;
+                const uint64_t nf = std::min<uint64_t>(2 * np, n - o);  // an odd count drops the very last second value
+                memcpy(out + o, dstp, nf * sizeof(float));
+            }
         };
-        auto worker = [&]() {
+        auto work = [&](uint32_t* local, float* local_pairs) {
             for (;;) {
                 const uint64_t c = next_chunk.fetch_add(1, std::memory_order_relaxed);
                 if (c >= n_chunks) return;
-                const uint64_t need_words = 4 * std::min(cand, (c + 1) * kChunk);
-                while (words_ready.load(std::memory_order_acquire) < need_words) std::this_thread::yield();
-                process_chunk(c);
+                while (states_ready.load(std::memory_order_acquire) <= c) std::this_thread::yield();
+                process_chunk(c, local, local_pairs);
             }
         };
-        // the MT19937 word stream is sequential: this thread produces it while the others already consume it
+        auto worker = [&]() {
+            std::vector<uint32_t> local;
+            std::vector<float> local_pairs;
+            try {
+                local.resize(kLocalWords);
+                local_pairs.resize(2 * kChunk);
+            } catch (const std::bad_alloc&) {
+                return;  // the other threads (the caller at the latest) do this one's chunks
+            }
+            work(local.data(), local_pairs.data());
+        };
+        // the recurrence is sequential: this thread runs it while the others already consume the states it publishes
         const int n_workers = cand < 8192 ? 0 : (int)std::min<uint64_t>((uint64_t)std::max(0, threads - 1), n_chunks);
         std::vector<std::thread> pool;
         for (int t = 0; t < n_workers; ++t) {
@@ -161,52 +186,39 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
             }
         }
         {
-            // raw state words: the rest of the present block, then each fresh block regenerated in place from a copy of
-            // its predecessor (the tempering is left to the consumers: this thread is the serial part)
-            uint64_t w = 0;
-            for (int i = start_pos; i < kN; ++i) words[w++] = key[i];
-            const uint32_t* prev = key;
-            uint64_t published = 0;
-            for (uint64_t b = 0; b < fresh_blocks; ++b) {
-                memcpy(&words[w], prev, sizeof(uint32_t) * kN);
-                mt_regenerate(&words[w]);
-                prev = &words[w];
-                w += kN;
-                if (w - published >= 4 * kChunk / 2) { words_ready.store(w, std::memory_order_release); published = w; }
+            alignas(64) uint32_t pp[2][kN];
+            const uint32_t* cur = key;   // block 0
+            uint64_t c = 0;
+            for (uint64_t b = 0; c < n_chunks; ++b) {
+                if (b == base + (uint64_t)kBlocksPerChunk * c) {   // the state at the start of chunk c
+                    memcpy(&states[(size_t)c * kN], cur, sizeof(uint32_t) * kN);
+                    states_ready.store(++c, std::memory_order_release);
+                    if (c == n_chunks) break;
+                }
+                mt_next(cur, pp[b & 1]);
+                cur = pp[b & 1];
             }
-            words_ready.store(w, std::memory_order_release);
         }
-        worker();  // the producer helps with whatever is left (all of it when threads == 1)
+        work(tl_local.data(), tl_pairs.data());  // the producer helps with whatever is left (all of it when threads == 1)
         for (auto& th : pool) th.join();
 
-        // compaction: chunk c's pairs go to out[done + 2 * prefix(c) ...]; the need_pairs-th accepted pair ends the round
-        std::vector<uint64_t> prefix((size_t)n_chunks + 1, 0);
-        for (uint64_t c = 0; c < n_chunks; ++c) prefix[(size_t)c + 1] = prefix[(size_t)c] + chunk_count[(size_t)c];
         const uint64_t accepted = prefix[(size_t)n_chunks];
         const uint64_t take_pairs = std::min(accepted, need_pairs);
-        parallel_ranges(n_chunks, threads, [&](int, uint64_t clo, uint64_t chi) {
-            for (uint64_t c = clo; c < chi; ++c) {
-                const uint64_t p0 = prefix[(size_t)c];
-                if (p0 >= take_pairs) break;
-                const uint64_t np = std::min<uint64_t>(chunk_count[(size_t)c], take_pairs - p0);
-                const uint64_t o = done + 2 * p0;
-                const uint64_t nf = std::min<uint64_t>(2 * np, n - o);  // an odd count drops the very last second value
-                memcpy(out + o, &pairs[2 * c * kChunk], nf * sizeof(float));
-            }
-        });
         uint64_t consumed_cand = cand;  // all of them when this round did not reach the target
         if (take_pairs == need_pairs) {
             // the candidate that produced the last pair: rescan its chunk
             uint64_t c = 0;
             while (prefix[(size_t)c + 1] < need_pairs) ++c;
             uint64_t left = need_pairs - prefix[(size_t)c];
-            uint64_t i = c * kChunk;
-            Candidate last = candidate(&words[4 * i]);
+            fill_chunk(c, std::min(cand, (c + 1) * kChunk), tl_local.data());
+            const uint32_t* w = tl_local.data() + off;
+            uint64_t i = 0;
+            Candidate last = candidate(w);
             for (;; ++i) {
-                last = candidate(&words[4 * i]);
+                last = candidate(w + 4 * i);
                 if (last.ok && --left == 0) break;
             }
-            consumed_cand = i + 1;
+            consumed_cand = c * kChunk + i + 1;
             if (done + 2 * need_pairs > n) {  // odd count: the second value of the last pair stays cached, as a double
                 const double f = sqrt(-2.0 * log(last.r2) / last.r2);
                 *has_gauss = 1;
@@ -221,7 +233,13 @@ extern "C" ROD_API int rod_numpy_legacy_normal_f32(uint32_t* key, int32_t* pos, 
         } else {
             const uint64_t beyond = consumed_words - in_first;         // words taken from fresh blocks
             const uint64_t blk = (beyond - 1) / kN;                    // 0-based fresh block holding the last word
-            memcpy(key, &words[in_first + blk * kN], sizeof(uint32_t) * kN);  // its raw words are the state
+            // its raw words are the state: block blk + 1 of the round, reached from the nearest chunk state before it
+            const uint64_t cs = std::min(n_chunks - 1, (blk + 1 - base) / kBlocksPerChunk);
+            uint32_t* pp = tl_local.data();
+            memcpy(pp, &states[(size_t)cs * kN], sizeof(uint32_t) * kN);
+            uint64_t at = base + (uint64_t)kBlocksPerChunk * cs, flip = 0;
+            for (; at < blk + 1; ++at, flip ^= 1) mt_next(pp + flip * kN, pp + (flip ^ 1) * kN);
+            memcpy(key, pp + flip * kN, sizeof(uint32_t) * kN);
             *pos = (int)(beyond - blk * kN);
         }
     }

@@ -256,7 +256,8 @@ def test_numpy_legacy_normal_stream_bit_exact():
     Gaussian), from any generator state (fresh seed: pos = 624; mid-block; with a cached Gaussian pending), and must
     leave np.random in exactly the state the NumPy call would, so that mixed use continues on the same stream."""
     from robust_object_detection_b200 import augmentations as aug
-    sizes = [1, 2, 3, 7, 155, 156, 157, 311, 312, 313, 1000, 4097, 65536, 100001, (37, 53, 3), (765, 1360, 3)]
+    sizes = [1, 2, 3, 7, 155, 156, 157, 311, 312, 313, 1000, 4097, 8112, 12740, 12745, 16224, 65536, 100001, (37, 53, 3),
+             (765, 1360, 3)]   # (a work item is 52 blocks of 624 words = 8112 candidate pairs, ~12 740 outputs)
     for seed in (0, 42, 123456789):
         np.random.seed(seed)
         want = [np.random.normal(0, 15, s).astype(np.float32) for s in sizes]
