@@ -32,6 +32,20 @@
 
 #include "../../include/rod_b200.h"
 
+// Instruction-set variants are picked at run time (GCC function multi-versioning).  ROD_RNG_ISA_AVX2 / ROD_RNG_ISA_DEFAULT
+// pin one variant at compile time: tests/test_host_logic.py builds those two and checks them against np.random as well, so
+// the paths a machine without AVX-512 / AVX2 would take are tested on any machine.
+#if defined(ROD_RNG_ISA_DEFAULT)
+#define ROD_RNG_CLONES_WIDE
+#define ROD_RNG_CLONES
+#elif defined(ROD_RNG_ISA_AVX2)
+#define ROD_RNG_CLONES_WIDE __attribute__((target("avx2")))
+#define ROD_RNG_CLONES __attribute__((target("avx2")))
+#else
+#define ROD_RNG_CLONES_WIDE __attribute__((target_clones("avx512f", "avx2", "default")))
+#define ROD_RNG_CLONES __attribute__((target_clones("avx2", "default")))
+#endif
+
 namespace {
 
 constexpr int kN = 624, kM = 397;
@@ -43,7 +57,7 @@ inline uint32_t twist(uint32_t a, uint32_t b) {
 }
 // nw := the block of 624 raw state words that follows the block `old` (out of place; cloned for AVX2 with run-time
 // dispatch: all loops vectorise, the only dependence inside a block has distance 227 words)
-__attribute__((target_clones("avx2", "default"))) void mt_next_generic(const uint32_t* __restrict old, uint32_t* __restrict nw) {
+ROD_RNG_CLONES void mt_next_generic(const uint32_t* __restrict old, uint32_t* __restrict nw) {
     for (int i = 0; i < kN - kM; ++i) nw[i] = old[i + kM] ^ twist(old[i], old[i + 1]);
     for (int i = kN - kM; i < kN - 1; ++i) nw[i] = nw[i - (kN - kM)] ^ twist(old[i], old[i + 1]);
     nw[kN - 1] = nw[kM - 1] ^ twist(old[kN - 1], nw[0]);
@@ -71,8 +85,12 @@ __attribute__((target("avx512f"))) void mt_next_avx512(const uint32_t* old, uint
 }
 using MtNextFn = void (*)(const uint32_t*, uint32_t*);
 MtNextFn pick_mt_next() {
+#if defined(ROD_RNG_ISA_DEFAULT) || defined(ROD_RNG_ISA_AVX2)
+    return mt_next_generic;
+#else
     __builtin_cpu_init();
     return __builtin_cpu_supports("avx512f") ? mt_next_avx512 : static_cast<MtNextFn>(mt_next_generic);
+#endif
 }
 const MtNextFn mt_next = pick_mt_next();
 inline uint32_t temper(uint32_t y) {
@@ -106,7 +124,7 @@ inline Candidate candidate(const uint32_t* w) {  // w: four RAW state words (tem
 //   polar_candidates: words -> x1, x2, r2 of every candidate;  polar_accept: keeps the accepted ones, in order;
 //   log() per accepted r2 (scalar);  polar_finish: the two float32 outputs of every accepted pair.
 constexpr int kBatch = 1024;   // candidates per batch: 4 arrays of 8 KB, resident in L1
-__attribute__((target_clones("avx512f", "avx2", "default")))
+ROD_RNG_CLONES_WIDE
 void polar_candidates(const uint32_t* __restrict w, int n, double* __restrict x1, double* __restrict x2, double* __restrict r2) {
     for (int i = 0; i < n; ++i) {
         const uint32_t t0 = temper(w[4 * i]), t1 = temper(w[4 * i + 1]), t2 = temper(w[4 * i + 2]), t3 = temper(w[4 * i + 3]);
@@ -129,7 +147,7 @@ inline int polar_accept(int n, double* x1, double* x2, double* r2) {
     }
     return m;
 }
-__attribute__((target_clones("avx512f", "avx2", "default")))
+ROD_RNG_CLONES_WIDE
 void polar_finish(const double* __restrict x1, const double* __restrict x2, const double* __restrict r2, const double* __restrict lg,
                   int m, double sigma, float* __restrict dst) {
     for (int i = 0; i < m; ++i) {

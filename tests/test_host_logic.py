@@ -312,6 +312,43 @@ def test_numpy_legacy_normal_stream_bit_exact():
         assert has.value == want_state[3] and cached.value == want_state[4], threads
 
 
+def test_numpy_legacy_normal_other_instruction_sets(tmp_path):
+    """The generator picks AVX-512 / AVX2 / plain variants at run time; the two a machine with AVX-512 never takes are
+    built here with the variant pinned (csrc/np_legacy_rng.cpp ROD_RNG_ISA_*) and checked against np.random too."""
+    import ctypes
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "robust-object-detection_b200", "csrc", "np_legacy_rng.cpp")
+    flags = open("/proc/cpuinfo").read() if os.path.exists("/proc/cpuinfo") else ""
+    for isa in ("DEFAULT", "AVX2"):
+        if isa == "AVX2" and " avx2" not in flags:
+            continue
+        so = str(tmp_path / f"rng_{isa.lower()}.so")
+        subprocess.check_call(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-math-errno", "-pthread",
+                               f"-DROD_RNG_ISA_{isa}", "-I", os.path.join(root, "include"), src, "-o", so])
+        fn = ctypes.CDLL(so).rod_numpy_legacy_normal_f32
+        fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_double, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int]
+        for seed, pre, sizes, threads in ((1, 0, (3, 12741, 100001), 1), (2, 333, (8113, 1, 360901), 3), (3, 624, (40000, 7), 0)):
+            np.random.seed(seed)
+            np.random.random(pre)
+            want = [np.random.normal(0, 15, n).astype(np.float32) for n in sizes]
+            want_state = np.random.get_state(legacy=True)
+            np.random.seed(seed)
+            np.random.random(pre)
+            for n, w in zip(sizes, want):
+                st = np.random.get_state(legacy=True)
+                key = np.array(st[1], dtype=np.uint32)
+                pos, has, cached = ctypes.c_int32(st[2]), ctypes.c_int32(st[3]), ctypes.c_double(st[4])
+                out = np.empty(n, np.float32)
+                assert fn(key.ctypes.data, ctypes.byref(pos), ctypes.byref(has), ctypes.byref(cached), 15.0, n, out.ctypes.data, threads) == 0
+                np.random.set_state(("MT19937", key, pos.value, has.value, cached.value))
+                assert np.array_equal(out, w), (isa, seed, n)
+            got_state = np.random.get_state(legacy=True)
+            assert np.array_equal(got_state[1], want_state[1]) and got_state[2:] == want_state[2:], (isa, seed)
+
+
 def test_numpy_legacy_normal_random_call_sequences():
     """Property test (hypothesis): any interleaving of np.random consumers and legacy_normal_f32 calls of random sizes,
     from any seed, produces the same values as the all-NumPy run and leaves the same generator state."""
